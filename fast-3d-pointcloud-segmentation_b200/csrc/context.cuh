@@ -1,0 +1,101 @@
+// context.cuh -- the handle behind f3ps_ctx: device buffers, device-resident scalars, launch helpers.
+#pragma once
+#include <string>
+#include <vector>
+#include "../../include/f3ps.h"
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "kernels_vccs.cuh"
+#include "kernels_graph.cuh"
+
+#define F3PS_MERGE_ERR_TOUCHED 4u
+#include "kernels_merge.cuh"
+
+namespace f3ps {
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// everything the kernels count or decide lives here, on the device; the host mirrors it on demand
+struct DevScalars {
+    FrameParams fp;
+    unsigned n_valid, n_voxels, n_cells, n_seeds;
+    unsigned n_sv, n_edges, n_out, edge_overflow;
+    unsigned bad_bin, nan_weights_init, pad0, pad1;
+    float lambda; float padf[3];
+    SweepFlags flags;
+    MergeCtl mctl;
+    SeedBox sb;
+};
+
+enum Progress { P_NONE = 0, P_INPUT, P_VOXELS, P_NEIGHBORS, P_NORMALS, P_SEEDS, P_EXPANDED, P_GRAPH, P_MERGED };
+
+} // namespace f3ps
+
+struct f3ps_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    f3ps::VccsParams vp{0.008f, 0.08f, 0.2f, 0.4f, 1.0f, 1, 1};
+    f3ps::MergeParams mp{0, 0, 1, 0.5f, 500};
+    int progress = f3ps::P_NONE;
+    bool graph_from_host = false;
+    long long launches = 0;
+
+    // input
+    const uint8_t* d_points = nullptr; int64_t n_points = 0; int stride = 32;
+    f3ps::DevBuf in_buf;
+    // scalars
+    f3ps::DevScalars* d_sc = nullptr;
+    f3ps::DevScalars* h_sc = nullptr;      // pinned mirror
+    short* d_lab_lut = nullptr;
+    // host-known sizes (after the syncs)
+    int depth = 0; unsigned V = 0, n_valid = 0, n_cells = 0, S0 = 0, S = 0, E = 0, n_out = 0;
+    int rounds = 0, key_bits = 0;
+    bool key64 = false;
+
+    // K1
+    f3ps::DevBuf keys_a, keys_b, vals_a, vals_b, starts, point_voxel, sort_scratch, compact_scratch;
+    void* sorted_keys = nullptr; unsigned* sorted_idx = nullptr;
+    f3ps::DevBuf vox_xyz, vox_rgb, vox_key;
+    // K2
+    f3ps::DevBuf hash_slots, hash_vals, nbr_row, nbr_col;
+    unsigned hash_mask = 0;
+    // K3
+    f3ps::DevBuf vox_normal, vox_curv;
+    // K4
+    f3ps::DevBuf cell_code, cell_code_b, cell_vox, cell_vox_b, vox_cell, cell_start, cell_codes, cell_nn, cell_keep, seeds;
+    // K5
+    f3ps::DevBuf owner0, owner1, dist0, dist1, st0, st1, cen_xyz, cen_rgb, cen_nrm, lab_keys_a, lab_keys_b, lab_vals_a, lab_vals_b, seg_start, seg_end;
+    unsigned* sorted_label = nullptr; unsigned* sorted_vox = nullptr;
+    // K6
+    f3ps::DevBuf sv_label, rank_of_label, run_start, run_end, pos_run, edge_set, edge_keys_a, edge_keys_b, edge_vals_a, edge_vals_b;
+    f3ps::DevBuf dbits_a, dbits_b, dbits_c, dbits_d, cdf_c, cdf_g, cdf_hist;
+    f3ps::DevBuf reg_init, reg_work, edge_init, edge_work;     // packed RegionArrays / EdgeArrays storage
+    f3ps::RegionArrays R0{}, R1{}; f3ps::EdgeArrays E0{}, E1{};
+    unsigned long long* sorted_edge_keys = nullptr;
+    unsigned edge_set_mask = 0; int edge_kb = 0;
+    // K7
+    f3ps::DevBuf mlog, run_out_off, run_dense, region_dense, out_xyz, out_label, out_voxel, vox_segment;
+    f3ps::MergeLog ML{};
+    unsigned n_pos = 0;           // positions of the label-ordered voxel list
+    const unsigned* order = nullptr;
+    const float4* gxyz = nullptr; // voxel xyz(+rgba) array the graph stages read
+
+    static constexpr int kEvents = 11;   // 0..8 stage boundaries, 9/10 around the merge kernel alone
+    cudaEvent_t ev[kEvents] = {};
+    bool ev_valid[kEvents] = {};
+};

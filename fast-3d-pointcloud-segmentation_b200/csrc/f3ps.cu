@@ -1,0 +1,1083 @@
+// f3ps.cu -- host orchestration and the C ABI (include/f3ps.h) of the B200-native
+// supervoxel-plus-merging path.  One handle = one device + one stream; every stage is a short
+// chain of kernels on that stream; the host only waits where an array size must be known.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+
+#include "context.cuh"
+
+using namespace f3ps;
+
+extern "C" const unsigned char f3ps_lab_lut_begin[];   // lab_lut.S (.incbin of data/lab_lut_s16.bin)
+extern "C" const unsigned char f3ps_lab_lut_end[];
+
+namespace {
+
+int ctx_fail(f3ps_ctx* ctx, int code, const std::string& msg) { ctx->err = msg; return code; }
+int ctx_fail_cuda(f3ps_ctx* ctx, cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    ctx->err = buf;
+    return F3PS_ERR_CUDA;
+}
+
+inline int grid_for(int64_t n, int threads, int max_blocks = kSMs * 16) {
+    int64_t b = (n + threads - 1) / threads;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(b, max_blocks));
+}
+inline unsigned next_pow2(unsigned v) { unsigned p = 1; while (p < v) p <<= 1; return p; }
+inline int bits_for(unsigned maxval) { int b = 1; while ((maxval >> b) != 0 && b < 32) ++b; return b; }
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                                         \
+    do {                                                                                    \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                    \
+        (ctx)->launches++;                                                                  \
+        F3PS_CUDA_OK(cudaPeekAtLastError());                                                \
+    } while (0)
+
+int pull_scalars(f3ps_ctx* ctx) {
+    F3PS_CUDA_OK(cudaMemcpyAsync(ctx->h_sc, ctx->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->stream));
+    F3PS_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return F3PS_OK;
+}
+#define SC(field) (&ctx->d_sc->field)
+
+int mark(f3ps_ctx* ctx, int i) {
+    F3PS_CUDA_OK(cudaEventRecord(ctx->ev[i], ctx->stream));
+    ctx->ev_valid[i] = true;
+    return F3PS_OK;
+}
+
+// ---- radix sort driver ------------------------------------------------------------------------
+// pass 0 reads (src_k, src_v) -- src_v == nullptr means the payload is the element index -- and the
+// passes ping-pong between scratch pairs A and B (A may alias the source when it can be clobbered).
+template <typename KeyT>
+int sort_pairs(f3ps_ctx* ctx, const KeyT* src_k, const unsigned* src_v, KeyT* a_k, unsigned* a_v, KeyT* b_k, unsigned* b_v,
+               const unsigned* n_ptr, int64_t n_cap, int bits, KeyT** keys_out, unsigned** vals_out) {
+    const int passes = std::max(1, (bits + kRadixBits - 1) / kRadixBits);
+    const bool small = n_cap < (1 << 20);
+    const int tile = kSortThreads * (small ? 4 : 16);
+    const int64_t tiles = std::max<int64_t>(1, (n_cap + tile - 1) / tile);
+    const size_t hist_words = (size_t)passes * kRadix;
+    const size_t state_words = (size_t)passes * tiles * kRadix;
+    const size_t words = hist_words + state_words + passes;
+    F3PS_CUDA_OK(ctx->sort_scratch.ensure(words * 4));
+    unsigned* ghist = ctx->sort_scratch.as<unsigned>();
+    unsigned* state = ghist + hist_words;
+    unsigned* tickets = state + state_words;
+    F3PS_CUDA_OK(cudaMemsetAsync(ghist, 0, words * 4, ctx->stream));
+    LAUNCH(ctx, radix_histogram_kernel<KeyT>, grid_for(n_cap, 256 * 8, kSMs * 4), 256, hist_words * 4, src_k, n_ptr, n_cap, passes, ghist);
+    LAUNCH(ctx, radix_scan_hist_kernel, passes, kRadix, 0, ghist);
+    const KeyT* ki = src_k; const unsigned* vi = src_v;
+    KeyT* ko = a_k; unsigned* vo = a_v;
+    for (int p = 0; p < passes; ++p) {
+        if (small)
+            LAUNCH(ctx, (radix_onesweep_kernel<KeyT, 4>), (int)tiles, kSortThreads, 0, ki, vi, ko, vo, n_ptr, n_cap, p * kRadixBits,
+                   ghist + (size_t)p * kRadix, state + (size_t)p * tiles * kRadix, tickets + p);
+        else
+            LAUNCH(ctx, (radix_onesweep_kernel<KeyT, 16>), (int)tiles, kSortThreads, 0, ki, vi, ko, vo, n_ptr, n_cap, p * kRadixBits,
+                   ghist + (size_t)p * kRadix, state + (size_t)p * tiles * kRadix, tickets + p);
+        ki = ko; vi = vo;
+        if (ko == a_k) { ko = b_k; vo = b_v; } else { ko = a_k; vo = a_v; }
+    }
+    *keys_out = const_cast<KeyT*>(ki); *vals_out = const_cast<unsigned*>(vi);
+    return F3PS_OK;
+}
+
+template <typename Op>
+int run_compact(f3ps_ctx* ctx, Op op, const unsigned* n_ptr, int64_t n_cap, unsigned* count) {
+    const int tile = kSelThreads * kSelItems;
+    const int64_t tiles = std::max<int64_t>(1, (n_cap + tile - 1) / tile);
+    F3PS_CUDA_OK(ctx->compact_scratch.ensure((tiles + 1) * 4));
+    unsigned* state = ctx->compact_scratch.as<unsigned>();
+    F3PS_CUDA_OK(cudaMemsetAsync(state, 0, (tiles + 1) * 4, ctx->stream));
+    LAUNCH(ctx, compact_kernel<Op>, (int)tiles, kSelThreads, 0, op, n_ptr, n_cap, count, state, state + tiles);
+    return F3PS_OK;
+}
+
+__global__ void fill_float_kernel(float* p, float v, unsigned n) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void iota_kernel(unsigned* p, unsigned n) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
+}
+__global__ void pos_run_kernel(const unsigned* __restrict__ sorted_label, const unsigned* __restrict__ rank_of_label, unsigned n, unsigned* __restrict__ pos_run) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned l = sorted_label[i];
+        pos_run[i] = l ? rank_of_label[l] : 0xffffffffu;
+    }
+}
+__global__ void decode_edge_keys_kernel(const unsigned long long* __restrict__ compact, unsigned n, int kb, unsigned long long* __restrict__ wide) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long k = compact[i];
+        wide[i] = ((k >> kb) << 32) | (k & ((1ull << kb) - 1ull));
+    }
+}
+struct EdgeSlotCompactOp {      // hash-set slots -> compact keys (rank_a << kb | rank_b), unsorted
+    const unsigned long long* slots; unsigned long long* keys; unsigned* vals; int kb;
+    typedef int Payload;
+    __device__ __forceinline__ bool test(int64_t i, Payload&) const { return slots[i] != 0ull; }
+    __device__ __forceinline__ void emit(unsigned pos, int64_t i, const Payload&) const {
+        const unsigned long long k = slots[i] - 1ull;
+        keys[pos] = ((k >> 32) << kb) | (k & 0xffffffffull); vals[pos] = pos;
+    }
+};
+__global__ void lab_test_kernel(const short* lut, const float* rgb, float* lab, int64_t n) {
+    for (int64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float o[3]; rgb2lab(lut, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], o);
+        lab[3 * i] = o[0]; lab[3 * i + 1] = o[1]; lab[3 * i + 2] = o[2];
+    }
+}
+__global__ void ciede_test_kernel(const float* l1, const float* l2, float* out, int64_t n) {
+    for (int64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = lab_ciede00(l1 + 3 * i, l2 + 3 * i);
+}
+__global__ void rgb_eucl_test_kernel(const float* c1, const float* c2, float* out, int64_t n) {
+    for (int64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = rgb_eucl(c1 + 3 * i, c2 + 3 * i);
+}
+RegionArrays carve_regions(void* base, size_t S) {
+    RegionArrays R; char* p = (char*)base;
+    auto take = [&](size_t bytes) { char* q = p; p += (bytes + 255) & ~(size_t)255; return q; };
+    R.mean = (float4*)take(S * 16); R.accu0 = (float4*)take(S * 16); R.accu1 = (float4*)take(S * 16); R.accu2 = (float4*)take(S * 16);
+    R.centroid = (float4*)take(S * 16); R.normal = (float4*)take(S * 16);
+    R.n = (int*)take(S * 4); R.head = (int*)take(S * 4); R.tail = (int*)take(S * 4); R.next_run = (int*)take(S * 4);
+    return R;
+}
+size_t region_bytes(size_t S) { return 6 * ((S * 16 + 255) & ~(size_t)255) + 4 * ((S * 4 + 255) & ~(size_t)255); }
+EdgeArrays carve_edges(void* base, size_t E) {
+    EdgeArrays A; char* p = (char*)base;
+    auto take = [&](size_t bytes) { char* q = p; p += (bytes + 255) & ~(size_t)255; return q; };
+    A.stamp = (long long*)take(E * 8);
+    A.a = (unsigned*)take(E * 4); A.b = (unsigned*)take(E * 4); A.dc = (float*)take(E * 4); A.dg = (float*)take(E * 4); A.w = (float*)take(E * 4);
+    return A;
+}
+size_t edge_bytes(size_t E) { return ((E * 8 + 255) & ~(size_t)255) + 5 * ((E * 4 + 255) & ~(size_t)255); }
+
+EdgeParams edge_params(const f3ps_ctx* ctx) {
+    EdgeParams ep;
+    ep.color_mode = ctx->mp.color_mode; ep.geom_mode = ctx->mp.geom_mode; ep.merge_mode = ctx->mp.merge_mode;
+    ep.bins = ctx->mp.bins; ep.lambda = ctx->mp.lambda;
+    ep.cdf_c = ctx->cdf_c.as<float>(); ep.cdf_g = ctx->cdf_g.as<float>(); ep.lab_lut = ctx->d_lab_lut;
+    return ep;
+}
+
+int need(f3ps_ctx* ctx, int level, const char* what) {
+    if (ctx->progress < level) return ctx_fail(ctx, F3PS_ERR_LOGIC, std::string(what) + ": earlier stage has not run");
+    return F3PS_OK;
+}
+
+// ---- K1 -------------------------------------------------------------------------------------------
+template <typename KeyT>
+int voxelize_typed(f3ps_ctx* ctx, PointLoader pl) {
+    const int64_t N = ctx->n_points;
+    F3PS_CUDA_OK(ctx->keys_a.ensure(N * sizeof(KeyT))); F3PS_CUDA_OK(ctx->keys_b.ensure(N * sizeof(KeyT)));
+    F3PS_CUDA_OK(ctx->vals_a.ensure(N * 4)); F3PS_CUDA_OK(ctx->vals_b.ensure(N * 4));
+    F3PS_CUDA_OK(ctx->starts.ensure((N + 1) * 4));
+    KeygenOp<KeyT> kop{pl, ctx->vp.use_transform, SC(fp), ctx->keys_a.as<KeyT>(), ctx->vals_a.as<unsigned>()};
+    int rc = run_compact(ctx, kop, nullptr, N, SC(n_valid));
+    if (rc) return rc;
+    KeyT* sk; unsigned* sv;
+    rc = sort_pairs<KeyT>(ctx, ctx->keys_a.as<KeyT>(), ctx->vals_a.as<unsigned>(), ctx->keys_b.as<KeyT>(), ctx->vals_b.as<unsigned>(),
+                          ctx->keys_a.as<KeyT>(), ctx->vals_a.as<unsigned>(), SC(n_valid), N, 3 * ctx->depth, &sk, &sv);
+    if (rc) return rc;
+    ctx->sorted_keys = sk; ctx->sorted_idx = sv;
+    HeadOp<KeyT> hop{sk, ctx->starts.as<unsigned>()};
+    rc = run_compact(ctx, hop, SC(n_valid), N, SC(n_voxels));
+    if (rc) return rc;
+    rc = pull_scalars(ctx);                                   // host needs V to size the voxel arrays
+    if (rc) return rc;
+    ctx->V = ctx->h_sc->n_voxels; ctx->n_valid = ctx->h_sc->n_valid;
+    const size_t V = std::max(1u, ctx->V);
+    F3PS_CUDA_OK(ctx->vox_xyz.ensure(V * 16)); F3PS_CUDA_OK(ctx->vox_rgb.ensure(V * 16)); F3PS_CUDA_OK(ctx->vox_key.ensure(V * 8));
+    if (ctx->V)
+        LAUNCH(ctx, voxel_accumulate_kernel<KeyT>, grid_for(ctx->V, 128), 128, 0, pl, sk, sv, ctx->starts.as<unsigned>(), SC(n_voxels), SC(n_valid),
+               ctx->vox_xyz.as<float4>(), ctx->vox_rgb.as<float4>(), ctx->vox_key.as<uint64_t>(), ctx->point_voxel.as<int>());
+    return F3PS_OK;
+}
+
+} // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* f3ps_version(void) { return "f3ps-b200 0.1 (sm_100a)"; }
+
+int f3ps_create(int device, void* stream, f3ps_ctx** out) {
+    if (!out) return F3PS_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return F3PS_ERR_CUDA;   // no CPU fallback
+    f3ps_ctx* ctx = new (std::nothrow) f3ps_ctx();
+    if (!ctx) return F3PS_ERR_CUDA;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return F3PS_ERR_CUDA; }
+    if (stream) ctx->stream = (cudaStream_t)stream;
+    else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return F3PS_ERR_CUDA; } ctx->own_stream = true; }
+    bool ok = cudaMalloc(&ctx->d_sc, sizeof(DevScalars)) == cudaSuccess &&
+              cudaMallocHost(&ctx->h_sc, sizeof(DevScalars)) == cudaSuccess;
+    const size_t lut_bytes = (size_t)(f3ps_lab_lut_end - f3ps_lab_lut_begin);
+    ok = ok && lut_bytes == 33 * 33 * 33 * 3 * 2 && cudaMalloc(&ctx->d_lab_lut, lut_bytes) == cudaSuccess &&
+         cudaMemcpy(ctx->d_lab_lut, f3ps_lab_lut_begin, lut_bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    for (int i = 0; i < f3ps_ctx::kEvents && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    if (!ok) { f3ps_destroy(ctx); return F3PS_ERR_CUDA; }
+    cudaMemset(ctx->d_sc, 0, sizeof(DevScalars));
+    memset(ctx->h_sc, 0, sizeof(DevScalars));
+    *out = ctx;
+    return F3PS_OK;
+}
+
+void f3ps_destroy(f3ps_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->in_buf, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->starts, &ctx->point_voxel, &ctx->sort_scratch,
+        &ctx->compact_scratch, &ctx->vox_xyz, &ctx->vox_rgb, &ctx->vox_key, &ctx->hash_slots, &ctx->hash_vals, &ctx->nbr_row, &ctx->nbr_col,
+        &ctx->vox_normal, &ctx->vox_curv, &ctx->cell_code, &ctx->cell_code_b, &ctx->cell_vox, &ctx->cell_vox_b, &ctx->vox_cell, &ctx->cell_start,
+        &ctx->cell_codes, &ctx->cell_nn, &ctx->cell_keep, &ctx->seeds, &ctx->owner0, &ctx->owner1, &ctx->dist0, &ctx->dist1, &ctx->st0, &ctx->st1,
+        &ctx->cen_xyz, &ctx->cen_rgb, &ctx->cen_nrm, &ctx->lab_keys_b, &ctx->lab_vals_a, &ctx->lab_vals_b, &ctx->seg_start, &ctx->seg_end,
+        &ctx->sv_label, &ctx->rank_of_label, &ctx->run_start, &ctx->run_end, &ctx->pos_run, &ctx->edge_set, &ctx->edge_keys_a, &ctx->edge_keys_b,
+        &ctx->edge_vals_a, &ctx->edge_vals_b, &ctx->dbits_a, &ctx->dbits_b, &ctx->dbits_c, &ctx->dbits_d, &ctx->cdf_c, &ctx->cdf_g, &ctx->cdf_hist,
+        &ctx->reg_init, &ctx->reg_work, &ctx->edge_init, &ctx->edge_work, &ctx->mlog, &ctx->run_out_off, &ctx->run_dense, &ctx->region_dense,
+        &ctx->out_xyz, &ctx->out_label, &ctx->out_voxel, &ctx->vox_segment};
+    for (DevBuf* b : bufs) b->release();
+    if (ctx->d_sc) cudaFree(ctx->d_sc);
+    if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
+    if (ctx->d_lab_lut) cudaFree(ctx->d_lab_lut);
+    for (int i = 0; i < f3ps_ctx::kEvents; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* f3ps_last_error(const f3ps_ctx* ctx) { return ctx ? ctx->err.c_str() : "null handle"; }
+int64_t f3ps_launch_count(const f3ps_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int f3ps_set_vccs_params(f3ps_ctx* ctx, float rv, float rs, float wc, float ws, float wn, int use_transform, int fold_negative_z) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    if (!(rv > 0) || !(rs > 0)) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "resolutions must be positive");
+    ctx->vp = VccsParams{rv, rs, wc, ws, wn, use_transform ? 1 : 0, fold_negative_z ? 1 : 0};
+    ctx->progress = std::min(ctx->progress, (int)P_INPUT);
+    return F3PS_OK;
+}
+
+// Clustering::set_merging / set_lambda / set_bins_num, src/clustering.cpp:562-597
+int f3ps_set_merge_params(f3ps_ctx* ctx, int color, int geom, int merging, float lambda, int bins) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    if (color < 0 || color > 1 || geom < 0 || geom > 1 || merging < 0 || merging > 2)
+        return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "unknown distance / merging enum value");
+    if (merging == F3PS_MANUAL_LAMBDA && (lambda < 0 || lambda > 1 || lambda != lambda))
+        return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "Argument outside range [0, 1]");
+    if (merging == F3PS_EQUALIZATION && (bins <= 0 || bins > 32767))
+        return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "Argument lower than 0");
+    ctx->mp = MergeParams{color, geom, merging, merging == F3PS_MANUAL_LAMBDA ? lambda : 0.5f, merging == F3PS_EQUALIZATION ? bins : 500};
+    if (ctx->progress >= P_GRAPH) ctx->progress = ctx->graph_from_host ? (int)P_GRAPH - 1 : (int)P_EXPANDED;   // weights are stale
+    return F3PS_OK;
+}
+
+int f3ps_set_input(f3ps_ctx* ctx, const void* points, int64_t n, int stride, int on_device) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    if (n < 0 || (stride != 16 && stride != 32) || (n > 0 && !points)) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "bad input description");
+    if (n >= (1ll << 31)) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "more than 2^31 points per handle");
+    cudaSetDevice(ctx->device);
+    if (on_device) ctx->d_points = (const uint8_t*)points;
+    else {
+        F3PS_CUDA_OK(ctx->in_buf.ensure(std::max<int64_t>(n, 1) * stride));
+        if (n) F3PS_CUDA_OK(cudaMemcpyAsync(ctx->in_buf.p, points, (size_t)n * stride, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->d_points = ctx->in_buf.as<uint8_t>();
+    }
+    ctx->n_points = n; ctx->stride = stride;
+    ctx->progress = P_INPUT; ctx->graph_from_host = false;
+    return F3PS_OK;
+}
+
+int f3ps_sync(f3ps_ctx* ctx) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    F3PS_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return F3PS_OK;
+}
+
+// ---- K1 -------------------------------------------------------------------------------------------
+int f3ps_voxelize(f3ps_ctx* ctx) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_INPUT, "f3ps_voxelize"); if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    rc = mark(ctx, 0); if (rc) return rc;
+    const int64_t N = ctx->n_points;
+    PointLoader pl{ctx->d_points, ctx->stride, ctx->vp.fold_negative_z};
+    DevScalars init; memset(&init, 0, sizeof init);
+    for (int a = 0; a < 3; ++a) { init.fp.ord_min[a] = 0xffffffffu; init.fp.ord_max[a] = 0u; }
+    *ctx->h_sc = init;
+    F3PS_CUDA_OK(cudaMemcpyAsync(ctx->d_sc, ctx->h_sc, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
+    F3PS_CUDA_OK(ctx->point_voxel.ensure(std::max<int64_t>(N, 1) * 4));
+    F3PS_CUDA_OK(cudaMemsetAsync(ctx->point_voxel.p, 0xff, std::max<int64_t>(N, 1) * 4, ctx->stream));
+    ctx->V = 0; ctx->n_valid = 0; ctx->depth = 0;
+    if (N > 0) {
+        LAUNCH(ctx, bbox_kernel, grid_for(N, 256 * 4, kSMs * 8), 256, 0, pl, N, ctx->vp.use_transform, SC(fp));
+        LAUNCH(ctx, frame_setup_kernel, 1, 1, 0, SC(fp), ctx->vp.voxel_res);
+        rc = pull_scalars(ctx); if (rc) return rc;            // host needs the depth to pick the key width / pass count
+        ctx->depth = ctx->h_sc->fp.depth;
+        if (ctx->h_sc->fp.any_finite) {
+            if (ctx->depth > 21) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "adjacency octree depth > 21");
+            ctx->key64 = 3 * ctx->depth > 32;
+            rc = ctx->key64 ? voxelize_typed<uint64_t>(ctx, pl) : voxelize_typed<uint32_t>(ctx, pl);
+            if (rc) return rc;
+        }
+    }
+    ctx->progress = P_VOXELS;
+    return mark(ctx, 1);
+}
+
+// ---- K2 -------------------------------------------------------------------------------------------
+int f3ps_neighbors(f3ps_ctx* ctx) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_VOXELS, "f3ps_neighbors"); if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    const unsigned V = ctx->V; const size_t Vc = std::max(1u, V);
+    const unsigned cap = next_pow2(std::max(64u, 2 * V));
+    ctx->hash_mask = cap - 1;
+    F3PS_CUDA_OK(ctx->hash_slots.ensure((size_t)cap * 8)); F3PS_CUDA_OK(ctx->hash_vals.ensure((size_t)cap * 4));
+    F3PS_CUDA_OK(ctx->nbr_row.ensure(Vc * kNbrStride * 4)); F3PS_CUDA_OK(ctx->nbr_col.ensure(Vc * 27 * 4));
+    F3PS_CUDA_OK(cudaMemsetAsync(ctx->hash_slots.p, 0, (size_t)cap * 8, ctx->stream));
+    if (V) {
+        LAUNCH(ctx, hash_build_kernel, grid_for(V, 256), 256, 0, ctx->vox_key.as<uint64_t>(), SC(n_voxels),
+               ctx->hash_slots.as<unsigned long long>(), ctx->hash_vals.as<unsigned>(), ctx->hash_mask);
+        LAUNCH(ctx, neighbors_kernel, grid_for(V, 128), 128, 0, ctx->vox_key.as<uint64_t>(), SC(n_voxels), SC(fp),
+               ctx->hash_slots.as<unsigned long long>(), ctx->hash_vals.as<unsigned>(), ctx->hash_mask, ctx->nbr_row.as<int>(),
+               ctx->nbr_col.as<int>(), V);
+    }
+    ctx->progress = P_NEIGHBORS;
+    return mark(ctx, 2);
+}
+
+// ---- K3 -------------------------------------------------------------------------------------------
+int f3ps_normals(f3ps_ctx* ctx) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_NEIGHBORS, "f3ps_normals"); if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    const unsigned V = ctx->V; const size_t Vc = std::max(1u, V);
+    F3PS_CUDA_OK(ctx->vox_normal.ensure(Vc * 16)); F3PS_CUDA_OK(ctx->vox_curv.ensure(Vc * 4));
+    if (V)
+        LAUNCH(ctx, voxel_normals_kernel, grid_for(V, 128), 128, 0, ctx->vox_xyz.as<float4>(), ctx->nbr_row.as<int>(), SC(n_voxels),
+               ctx->vox_normal.as<float4>(), ctx->vox_curv.as<float>());
+    ctx->progress = P_NORMALS;
+    return mark(ctx, 3);
+}
+
+// ---- K4 -------------------------------------------------------------------------------------------
+int f3ps_seeds(f3ps_ctx* ctx) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_NORMALS, "f3ps_seeds"); if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    const unsigned V = ctx->V; const size_t Vc = std::max(1u, V);
+    ctx->n_cells = 0; ctx->S0 = 0;
+    DevBuf* b8[] = {&ctx->cell_code, &ctx->cell_code_b, &ctx->vox_cell, &ctx->cell_codes};
+    for (DevBuf* b : b8) F3PS_CUDA_OK(b->ensure(Vc * 8));
+    DevBuf* b4[] = {&ctx->cell_vox, &ctx->cell_vox_b, &ctx->cell_start, &ctx->cell_nn, &ctx->cell_keep, &ctx->seeds};
+    for (DevBuf* b : b4) F3PS_CUDA_OK(b->ensure((Vc + 1) * 4));
+    if (V) {
+        LAUNCH(ctx, seed_box_kernel, 1, 1024, 0, ctx->vox_xyz.as<float4>(), SC(n_voxels), ctx->vp.seed_res, SC(sb));
+        LAUNCH(ctx, seed_cell_kernel, grid_for(V, 256), 256, 0, ctx->vox_xyz.as<float4>(), SC(n_voxels), SC(sb), ctx->vox_cell.as<uint64_t>());
+        rc = pull_scalars(ctx); if (rc) return rc;            // seed octree depth decides the sort width
+        const SeedBox& sb = ctx->h_sc->sb;
+        if (sb.n_events > kMaxSeedEvents) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "seed octree grew more than 48 times");
+        if (sb.depth > 21) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "seed octree depth > 21");
+        uint64_t* sc; unsigned* sv;
+        rc = sort_pairs<uint64_t>(ctx, ctx->vox_cell.as<uint64_t>(), nullptr, ctx->cell_code.as<uint64_t>(), ctx->cell_vox.as<unsigned>(),
+                                  ctx->cell_code_b.as<uint64_t>(), ctx->cell_vox_b.as<unsigned>(), SC(n_voxels), V, 3 * sb.depth, &sc, &sv);
+        if (rc) return rc;
+        HeadOp<uint64_t> hop{sc, ctx->cell_start.as<unsigned>()};
+        rc = run_compact(ctx, hop, SC(n_voxels), V, SC(n_cells)); if (rc) return rc;
+        LAUNCH(ctx, gather_cell_codes_kernel, grid_for(V, 256), 256, 0, sc, ctx->cell_start.as<unsigned>(), SC(n_cells), ctx->cell_codes.as<uint64_t>());
+        LAUNCH(ctx, seed_select_kernel, grid_for((int64_t)V * 4, 256), 256, 0, ctx->vox_xyz.as<float4>(), ctx->vox_cell.as<uint64_t>(), sv,
+               ctx->cell_start.as<unsigned>(), ctx->cell_codes.as<uint64_t>(), SC(n_cells), SC(n_voxels), SC(sb), ctx->vp.seed_res,
+               ctx->vp.voxel_res, ctx->cell_nn.as<int>(), ctx->cell_keep.as<unsigned>());
+        KeepOp kop{ctx->cell_keep.as<unsigned>(), ctx->cell_nn.as<int>(), ctx->seeds.as<int>()};
+        rc = run_compact(ctx, kop, SC(n_cells), V, SC(n_seeds)); if (rc) return rc;
+        rc = pull_scalars(ctx); if (rc) return rc;            // S0 sizes the per-label tables
+        ctx->n_cells = ctx->h_sc->n_cells; ctx->S0 = ctx->h_sc->n_seeds;
+    }
+    ctx->progress = P_SEEDS;
+    return mark(ctx, 4);
+}
+
+// ---- K5 -------------------------------------------------------------------------------------------
+// voxels grouped by owner label (stable => idx order inside a label) + per-label bounds
+static int group_by_label(f3ps_ctx* ctx, const unsigned* owner) {
+    const unsigned V = ctx->V; const size_t Sc = (size_t)ctx->S0 + 2;
+    unsigned* sk; unsigned* sv;
+    int rc = sort_pairs<unsigned>(ctx, owner, nullptr, ctx->lab_keys_a.as<unsigned>(), ctx->lab_vals_a.as<unsigned>(), ctx->lab_keys_b.as<unsigned>(),
+                                  ctx->lab_vals_b.as<unsigned>(), SC(n_voxels), V, bits_for(ctx->S0), &sk, &sv);
+    if (rc) return rc;
+    F3PS_CUDA_OK(cudaMemsetAsync(ctx->seg_start.p, 0, Sc * 4, ctx->stream));
+    F3PS_CUDA_OK(cudaMemsetAsync(ctx->seg_end.p, 0, Sc * 4, ctx->stream));
+    LAUNCH(ctx, label_bounds_kernel, grid_for(V, 256), 256, 0, sk, SC(n_voxels), ctx->seg_start.as<unsigned>(), ctx->seg_end.as<unsigned>());
+    ctx->sorted_label = sk; ctx->sorted_vox = sv;
+    return F3PS_OK;
+}
+
+static int expand_once(f3ps_ctx* ctx, int max_sweeps) {
+    const unsigned V = ctx->V, S0 = ctx->S0; const size_t Vc = std::max(1u, V);
+    DevBuf* bv[] = {&ctx->owner0, &ctx->owner1, &ctx->dist0, &ctx->dist1, &ctx->st0, &ctx->st1, &ctx->lab_keys_a, &ctx->lab_keys_b, &ctx->lab_vals_a, &ctx->lab_vals_b};
+    for (DevBuf* b : bv) F3PS_CUDA_OK(b->ensure(Vc * 4));
+    const size_t Sc = (size_t)S0 + 2;
+    F3PS_CUDA_OK(ctx->cen_xyz.ensure(Sc * 16)); F3PS_CUDA_OK(ctx->cen_rgb.ensure(Sc * 16)); F3PS_CUDA_OK(ctx->cen_nrm.ensure(Sc * 16));
+    F3PS_CUDA_OK(ctx->seg_start.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->seg_end.ensure(Sc * 4));
+    Centroids cen{ctx->cen_xyz.as<float4>(), ctx->cen_rgb.as<float4>(), ctx->cen_nrm.as<float4>()};
+    F3PS_CUDA_OK(cudaMemsetAsync(SC(flags), 0, sizeof(SweepFlags), ctx->stream));
+    F3PS_CUDA_OK(cudaMemsetAsync(ctx->owner0.p, 0, Vc * 4, ctx->stream));
+    F3PS_CUDA_OK(cudaMemsetAsync(ctx->cen_xyz.p, 0, Sc * 16, ctx->stream));
+    F3PS_CUDA_OK(cudaMemsetAsync(ctx->cen_rgb.p, 0, Sc * 16, ctx->stream));
+    F3PS_CUDA_OK(cudaMemsetAsync(ctx->cen_nrm.p, 0, Sc * 16, ctx->stream));
+    const int max_depth = (int)(1.8f * ctx->vp.seed_res / ctx->vp.voxel_res);     // SupervoxelClustering::extract
+    ctx->rounds = std::max(0, max_depth - 1);
+    if (!V) return F3PS_OK;
+    LAUNCH(ctx, fill_float_kernel, grid_for(V, 256), 256, 0, ctx->dist0.as<float>(), FLT_MAX, V);
+    if (S0) {
+        F3PS_CUDA_OK(cudaMemsetAsync(ctx->st1.p, 0, Vc * 4, ctx->stream));      // claim counters
+        LAUNCH(ctx, expand_init_kernel, grid_for(S0, 256), 256, 0, ctx->seeds.as<int>(), SC(n_seeds), ctx->owner0.as<unsigned>(),
+               ctx->st1.as<unsigned>(), cen);
+        LAUNCH(ctx, expand_init_shared_kernel, grid_for(S0, 256), 256, 0, ctx->seeds.as<int>(), SC(n_seeds), ctx->owner0.as<unsigned>(),
+               ctx->st1.as<unsigned>(), ctx->dist0.as<float>(), ctx->vox_xyz.as<float4>(), ctx->vox_rgb.as<float4>(), ctx->vox_normal.as<float4>(), ctx->vp);
+    }
+    unsigned* own[2] = {ctx->owner0.as<unsigned>(), ctx->owner1.as<unsigned>()};
+    float* dst[2] = {ctx->dist0.as<float>(), ctx->dist1.as<float>()};
+    unsigned* st[2] = {ctx->st0.as<unsigned>(), ctx->st1.as<unsigned>()};
+    int cur = 0;
+    const int sweep_grid = grid_for(V, 256);
+    for (int round = 0; round < ctx->rounds && S0; ++round) {
+        F3PS_CUDA_OK(cudaMemsetAsync(st[0], 0xff, (size_t)V * 4, ctx->stream));
+        for (int s = 0; s < max_sweeps; ++s)
+            LAUNCH(ctx, expand_sweep_kernel, sweep_grid, 256, 0, s, ctx->nbr_col.as<int>(), V, SC(n_voxels), own[cur], dst[cur], st[s & 1], st[(s + 1) & 1],
+                   own[cur ^ 1], dst[cur ^ 1], ctx->vox_xyz.as<float4>(), ctx->vox_rgb.as<float4>(), ctx->vox_normal.as<float4>(),
+                   ctx->nbr_row.as<int>(), cen, ctx->vp, SC(flags));
+        LAUNCH(ctx, expand_round_end_kernel, 1, 1, 0, SC(flags), max_sweeps);
+        cur ^= 1;
+        // SupervoxelHelper::updateCentroid: ordered sums per helper over its voxels in idx order
+        int rc = group_by_label(ctx, own[cur]); if (rc) return rc;
+        LAUNCH(ctx, centroid_fold_kernel, grid_for((int64_t)S0 * 32, 256), 256, 0, ctx->sorted_vox, ctx->seg_start.as<unsigned>(),
+               ctx->seg_end.as<unsigned>(), SC(n_seeds), ctx->vox_xyz.as<float4>(), ctx->vox_rgb.as<float4>(), ctx->vox_normal.as<float4>(), cen);
+    }
+    if (cur == 1) {                                            // canonical result arrays: owner0 / dist0
+        F3PS_CUDA_OK(cudaMemcpyAsync(own[0], own[1], (size_t)V * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        F3PS_CUDA_OK(cudaMemcpyAsync(dst[0], dst[1], (size_t)V * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (ctx->rounds == 0 || !S0) { int rc = group_by_label(ctx, own[0]); if (rc) return rc; }
+    return F3PS_OK;
+}
+
+int f3ps_expand(f3ps_ctx* ctx) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_SEEDS, "f3ps_expand"); if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    for (int max_sweeps = 6;; max_sweeps = kMaxSweeps) {
+        rc = expand_once(ctx, max_sweeps); if (rc) return rc;
+        // alive helpers -> ranks (makeSupervoxels); the same readback verifies the fixed point
+        const size_t Sc = (size_t)ctx->S0 + 2;
+        F3PS_CUDA_OK(ctx->sv_label.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->rank_of_label.ensure(Sc * 4));
+        F3PS_CUDA_OK(cudaMemsetAsync(SC(n_sv), 0, 4, ctx->stream));
+        if (ctx->S0) {
+            AliveOp aop{ctx->seg_start.as<unsigned>(), ctx->seg_end.as<unsigned>(), ctx->sv_label.as<unsigned>(), ctx->rank_of_label.as<unsigned>()};
+            rc = run_compact(ctx, aop, nullptr, ctx->S0, SC(n_sv)); if (rc) return rc;
+        }
+        rc = pull_scalars(ctx); if (rc) return rc;
+        if (!ctx->h_sc->flags.not_converged) break;
+        if (max_sweeps == kMaxSweeps) return ctx_fail(ctx, F3PS_ERR_NOT_CONVERGED, "expansion fixed point not reached within 16 sweeps");
+    }
+    ctx->S = ctx->h_sc->n_sv;
+    ctx->progress = P_EXPANDED;
+    return mark(ctx, 5);
+}
+
+// ---- K6 -------------------------------------------------------------------------------------------
+static int init_weights(f3ps_ctx* ctx, unsigned E_cap) {     // Clustering::init_weights on R0 / E0 + the edge keys
+    EdgeParams ep = edge_params(ctx);
+    const float* lambda_dev = nullptr;
+    F3PS_CUDA_OK(ctx->dbits_a.ensure((size_t)E_cap * 4)); F3PS_CUDA_OK(ctx->dbits_b.ensure((size_t)E_cap * 4));
+    F3PS_CUDA_OK(ctx->dbits_c.ensure((size_t)E_cap * 4)); F3PS_CUDA_OK(ctx->dbits_d.ensure((size_t)E_cap * 4));
+    F3PS_CUDA_OK(ctx->edge_vals_a.ensure((size_t)E_cap * 4)); F3PS_CUDA_OK(ctx->edge_vals_b.ensure((size_t)E_cap * 4));
+    F3PS_CUDA_OK(ctx->cdf_c.ensure((size_t)std::max(1, ctx->mp.bins) * 4)); F3PS_CUDA_OK(ctx->cdf_g.ensure((size_t)std::max(1, ctx->mp.bins) * 4));
+    ep.cdf_c = ctx->cdf_c.as<float>(); ep.cdf_g = ctx->cdf_g.as<float>();
+    LAUNCH(ctx, edge_delta_kernel, grid_for(E_cap, 128), 128, 0, ctx->sorted_edge_keys, SC(n_edges), ctx->R0, ep, ctx->E0,
+           ctx->dbits_a.as<unsigned>(), ctx->dbits_c.as<unsigned>());
+    if (ctx->mp.merge_mode == F3PS_ADAPTIVE_LAMBDA) {
+        unsigned *sc, *sg, *dummy;
+        int rc = sort_pairs<unsigned>(ctx, ctx->dbits_a.as<unsigned>(), nullptr, ctx->dbits_b.as<unsigned>(), ctx->edge_vals_a.as<unsigned>(),
+                                      ctx->dbits_a.as<unsigned>(), ctx->edge_vals_b.as<unsigned>(), SC(n_edges), E_cap, 32, &sc, &dummy);
+        if (rc) return rc;
+        rc = sort_pairs<unsigned>(ctx, ctx->dbits_c.as<unsigned>(), nullptr, ctx->dbits_d.as<unsigned>(), ctx->edge_vals_a.as<unsigned>(),
+                                  ctx->dbits_c.as<unsigned>(), ctx->edge_vals_b.as<unsigned>(), SC(n_edges), E_cap, 32, &sg, &dummy);
+        if (rc) return rc;
+        LAUNCH(ctx, adaptive_lambda_kernel, 1, 64, 0, sc, sg, SC(n_edges), SC(lambda));
+        lambda_dev = SC(lambda);
+    } else if (ctx->mp.merge_mode == F3PS_EQUALIZATION) {
+        const int bins = ctx->mp.bins;
+        F3PS_CUDA_OK(ctx->cdf_hist.ensure((size_t)2 * bins * 4));
+        LAUNCH(ctx, cdf_kernel, 2, 1024, bins <= 8192 ? (size_t)bins * 4 : 0, ctx->E0.dc, ctx->E0.dg, SC(n_edges), bins, ctx->cdf_c.as<float>(),
+               ctx->cdf_g.as<float>(), ctx->cdf_hist.as<unsigned>(), SC(bad_bin));
+    }
+    if (ctx->mp.merge_mode != F3PS_ADAPTIVE_LAMBDA) {
+        const float lam = ctx->mp.lambda;
+        F3PS_CUDA_OK(cudaMemcpyAsync(SC(lambda), &lam, 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    LAUNCH(ctx, edge_weight_kernel, grid_for(E_cap, 256), 256, 0, SC(n_edges), ep, lambda_dev, ctx->E0, SC(nan_weights_init));
+    return F3PS_OK;
+}
+
+int f3ps_graph(f3ps_ctx* ctx) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (ctx->graph_from_host) {                                // weights only (parameters changed after f3ps_set_graph)
+        int rc = need(ctx, P_GRAPH - 1, "f3ps_graph"); if (rc) return rc;
+        F3PS_CUDA_OK(cudaMemsetAsync(SC(nan_weights_init), 0, 4, ctx->stream));
+        rc = init_weights(ctx, std::max(1u, ctx->E)); if (rc) return rc;
+        ctx->progress = P_GRAPH;
+        return F3PS_OK;
+    }
+    int rc = need(ctx, P_EXPANDED, "f3ps_graph"); if (rc) return rc;
+    const unsigned V = ctx->V, S = ctx->S; const size_t Sc = std::max(1u, S), Vc = std::max(1u, V);
+    F3PS_CUDA_OK(ctx->reg_init.ensure(region_bytes(Sc))); F3PS_CUDA_OK(ctx->reg_work.ensure(region_bytes(Sc)));
+    ctx->R0 = carve_regions(ctx->reg_init.p, Sc); ctx->R1 = carve_regions(ctx->reg_work.p, Sc);
+    F3PS_CUDA_OK(ctx->run_start.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->run_end.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->pos_run.ensure(Vc * 4));
+    Centroids cen{ctx->cen_xyz.as<float4>(), ctx->cen_rgb.as<float4>(), ctx->cen_nrm.as<float4>()};
+    ctx->order = ctx->sorted_vox; ctx->gxyz = ctx->vox_xyz.as<float4>(); ctx->n_pos = V;
+    const unsigned set_cap = next_pow2(std::max(1024u, 32 * S));
+    ctx->edge_set_mask = set_cap - 1; ctx->edge_kb = bits_for(std::max(1u, S));
+    F3PS_CUDA_OK(ctx->edge_set.ensure((size_t)set_cap * 8));
+    F3PS_CUDA_OK(ctx->edge_keys_a.ensure((size_t)set_cap * 8)); F3PS_CUDA_OK(ctx->edge_keys_b.ensure((size_t)set_cap * 8));
+    F3PS_CUDA_OK(ctx->edge_vals_a.ensure((size_t)set_cap * 4)); F3PS_CUDA_OK(ctx->edge_vals_b.ensure((size_t)set_cap * 4));
+    F3PS_CUDA_OK(ctx->edge_init.ensure(edge_bytes(set_cap))); F3PS_CUDA_OK(ctx->edge_work.ensure(edge_bytes(set_cap)));
+    ctx->E0 = carve_edges(ctx->edge_init.p, set_cap); ctx->E1 = carve_edges(ctx->edge_work.p, set_cap);
+    F3PS_CUDA_OK(cudaMemsetAsync(ctx->edge_set.p, 0, (size_t)set_cap * 8, ctx->stream));
+    F3PS_CUDA_OK(cudaMemsetAsync(SC(n_edges), 0, 4, ctx->stream));
+    F3PS_CUDA_OK(cudaMemsetAsync(SC(edge_overflow), 0, 16, ctx->stream));   // edge_overflow, bad_bin, nan_weights_init, pad
+    if (V && S) {
+        LAUNCH(ctx, pos_run_kernel, grid_for(V, 256), 256, 0, ctx->sorted_label, ctx->rank_of_label.as<unsigned>(), V, ctx->pos_run.as<unsigned>());
+        LAUNCH(ctx, region_init_kernel, grid_for((int64_t)S * 32, 256), 256, 0, ctx->sv_label.as<unsigned>(), SC(n_sv), ctx->seg_start.as<unsigned>(),
+               ctx->seg_end.as<unsigned>(), ctx->sorted_vox, ctx->vox_xyz.as<float4>(), cen, ctx->R0, ctx->run_start.as<unsigned>(),
+               ctx->run_end.as<unsigned>());
+        LAUNCH(ctx, edge_collect_kernel, grid_for(V, 256), 256, 0, ctx->nbr_col.as<int>(), V, ctx->nbr_row.as<int>(), SC(n_voxels), ctx->owner0.as<unsigned>(),
+               ctx->rank_of_label.as<unsigned>(), ctx->edge_set.as<unsigned long long>(), ctx->edge_set_mask, SC(edge_overflow));
+        EdgeSlotCompactOp sop{ctx->edge_set.as<unsigned long long>(), ctx->edge_keys_a.as<unsigned long long>(), ctx->edge_vals_a.as<unsigned>(), ctx->edge_kb};
+        rc = run_compact(ctx, sop, nullptr, set_cap, SC(n_edges)); if (rc) return rc;
+        unsigned long long* sk; unsigned* sv;
+        rc = sort_pairs<unsigned long long>(ctx, ctx->edge_keys_a.as<unsigned long long>(), nullptr, ctx->edge_keys_b.as<unsigned long long>(),
+                                            ctx->edge_vals_b.as<unsigned>(), ctx->edge_keys_a.as<unsigned long long>(), ctx->edge_vals_a.as<unsigned>(),
+                                            SC(n_edges), set_cap, 2 * ctx->edge_kb, &sk, &sv);
+        if (rc) return rc;
+        unsigned long long* wide = (sk == ctx->edge_keys_a.as<unsigned long long>()) ? ctx->edge_keys_b.as<unsigned long long>()
+                                                                                      : ctx->edge_keys_a.as<unsigned long long>();
+        rc = pull_scalars(ctx); if (rc) return rc;             // E (and the overflow flag) before the weights
+        if (ctx->h_sc->edge_overflow) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "supervoxel edge set overflow");
+        ctx->E = ctx->h_sc->n_edges;
+        if (ctx->E) {
+            LAUNCH(ctx, decode_edge_keys_kernel, grid_for(ctx->E, 256), 256, 0, sk, ctx->E, ctx->edge_kb, wide);
+            ctx->sorted_edge_keys = wide;
+            rc = init_weights(ctx, ctx->E); if (rc) return rc;
+        }
+    } else ctx->E = 0;
+    ctx->progress = P_GRAPH;
+    return mark(ctx, 6);
+}
+
+int f3ps_set_graph(f3ps_ctx* ctx, int64_t n_voxels, const float* voxel_xyz, const uint32_t* voxel_rgba, int32_t n_sv, const uint32_t* labels,
+                   const int64_t* voxel_offsets, const float* centroids_xyz, const float* normals_xyz, int64_t n_adj, const uint32_t* adj_pairs) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    if (n_voxels < 0 || n_sv < 0 || n_adj < 0) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "negative size");
+    cudaSetDevice(ctx->device);
+    const unsigned V = (unsigned)n_voxels, S = (unsigned)n_sv;
+    // supervoxels by ascending label (std::map order), voxel ranges regrouped accordingly
+    std::vector<int> perm(S);
+    for (unsigned s = 0; s < S; ++s) perm[s] = (int)s;
+    std::sort(perm.begin(), perm.end(), [&](int x, int y) { return labels[x] < labels[y]; });
+    std::map<uint32_t, unsigned> rank;
+    std::vector<float4> h_xyz(std::max(1u, V));
+    std::vector<unsigned> h_start(std::max(1u, S)), h_end(std::max(1u, S)), h_label(std::max(1u, S)), h_posrun(std::max(1u, V));
+    std::vector<float4> h_cen(std::max(1u, S)), h_nrm(std::max(1u, S));
+    unsigned pos = 0;
+    for (unsigned r = 0; r < S; ++r) {
+        const int s = perm[r];
+        if (rank.count(labels[s])) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "duplicate supervoxel label");
+        rank[labels[s]] = r; h_label[r] = labels[s];
+        h_start[r] = pos;
+        for (int64_t i = voxel_offsets[s]; i < voxel_offsets[s + 1]; ++i, ++pos) {
+            float w; uint32_t c = voxel_rgba[i] & 0x00ffffffu; memcpy(&w, &c, 4);
+            h_xyz[pos] = make_float4(voxel_xyz[3 * i], voxel_xyz[3 * i + 1], voxel_xyz[3 * i + 2], w);
+            h_posrun[pos] = r;
+        }
+        h_end[r] = pos;
+        h_cen[r] = make_float4(centroids_xyz[3 * s], centroids_xyz[3 * s + 1], centroids_xyz[3 * s + 2], 0.0f);
+        h_nrm[r] = make_float4(normals_xyz[3 * s], normals_xyz[3 * s + 1], normals_xyz[3 * s + 2], 0.0f);
+    }
+    if (pos != V) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "voxel offsets do not cover the voxel arrays");
+    // clear_adjacency keeps first <= second (src/clustering.cpp:476-486); iteration order = insertion order of the weights
+    std::vector<unsigned long long> h_keys;
+    for (int64_t i = 0; i < n_adj; ++i) {
+        const uint32_t a = adj_pairs[2 * i], b = adj_pairs[2 * i + 1];
+        if (a > b) continue;
+        if (a == b) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "self-adjacent supervoxel");
+        auto ia = rank.find(a), ib = rank.find(b);
+        if (ia == rank.end() || ib == rank.end()) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "adjacency names an unknown label");   // map::at
+        h_keys.push_back(((unsigned long long)ia->second << 32) | ib->second);
+    }
+    const unsigned E = (unsigned)h_keys.size();
+    const size_t Sc = std::max(1u, S), Vc = std::max(1u, V), Ec = std::max(1u, E);
+    F3PS_CUDA_OK(ctx->vox_xyz.ensure(Vc * 16)); F3PS_CUDA_OK(ctx->lab_vals_a.ensure(Vc * 4)); F3PS_CUDA_OK(ctx->pos_run.ensure(Vc * 4));
+    F3PS_CUDA_OK(ctx->run_start.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->run_end.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->sv_label.ensure(Sc * 4));
+    F3PS_CUDA_OK(ctx->reg_init.ensure(region_bytes(Sc))); F3PS_CUDA_OK(ctx->reg_work.ensure(region_bytes(Sc)));
+    ctx->R0 = carve_regions(ctx->reg_init.p, Sc); ctx->R1 = carve_regions(ctx->reg_work.p, Sc);
+    F3PS_CUDA_OK(ctx->edge_init.ensure(edge_bytes(Ec))); F3PS_CUDA_OK(ctx->edge_work.ensure(edge_bytes(Ec)));
+    ctx->E0 = carve_edges(ctx->edge_init.p, Ec); ctx->E1 = carve_edges(ctx->edge_work.p, Ec);
+    F3PS_CUDA_OK(ctx->edge_keys_a.ensure(Ec * 8));
+    auto up = [&](void* d, const void* h, size_t bytes) { return bytes ? cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess; };
+    F3PS_CUDA_OK(up(ctx->vox_xyz.p, h_xyz.data(), (size_t)V * 16)); F3PS_CUDA_OK(up(ctx->pos_run.p, h_posrun.data(), (size_t)V * 4));
+    F3PS_CUDA_OK(up(ctx->run_start.p, h_start.data(), (size_t)S * 4)); F3PS_CUDA_OK(up(ctx->run_end.p, h_end.data(), (size_t)S * 4));
+    F3PS_CUDA_OK(up(ctx->sv_label.p, h_label.data(), (size_t)S * 4));
+    F3PS_CUDA_OK(up(ctx->R0.centroid, h_cen.data(), (size_t)S * 16)); F3PS_CUDA_OK(up(ctx->R0.normal, h_nrm.data(), (size_t)S * 16));
+    F3PS_CUDA_OK(up(ctx->edge_keys_a.p, h_keys.data(), (size_t)E * 8));
+    DevScalars init; memset(&init, 0, sizeof init);
+    init.n_voxels = V; init.n_sv = S; init.n_edges = E;
+    *ctx->h_sc = init;
+    F3PS_CUDA_OK(cudaMemcpyAsync(ctx->d_sc, ctx->h_sc, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
+    if (V) LAUNCH(ctx, iota_kernel, grid_for(V, 256), 256, 0, ctx->lab_vals_a.as<unsigned>(), V);
+    if (S) LAUNCH(ctx, region_init_ranges_kernel, grid_for((int64_t)S * 32, 256), 256, 0, S, ctx->run_start.as<unsigned>(), ctx->run_end.as<unsigned>(),
+                  ctx->lab_vals_a.as<unsigned>(), ctx->vox_xyz.as<float4>(), ctx->R0);
+    ctx->V = V; ctx->S = S; ctx->S0 = S; ctx->E = E; ctx->n_pos = V;
+    ctx->order = ctx->lab_vals_a.as<unsigned>(); ctx->sorted_vox = ctx->lab_vals_a.as<unsigned>(); ctx->gxyz = ctx->vox_xyz.as<float4>();
+    ctx->sorted_edge_keys = ctx->edge_keys_a.as<unsigned long long>();
+    ctx->graph_from_host = true;
+    ctx->progress = P_GRAPH - 1;
+    F3PS_CUDA_OK(cudaStreamSynchronize(ctx->stream));        // host staging vectors go out of scope
+    return f3ps_graph(ctx);
+}
+
+// ---- K7 -------------------------------------------------------------------------------------------
+int f3ps_merge(f3ps_ctx* ctx, float threshold) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    if (ctx->progress < P_EXPANDED)                            // std::logic_error of Clustering::cluster (src/clustering.cpp:671-673)
+        return ctx_fail(ctx, F3PS_ERR_LOGIC, "Cannot call 'cluster' before setting an initial state with 'set_initialstate'");
+    cudaSetDevice(ctx->device);
+    int rc;
+    if (ctx->progress < P_GRAPH) { rc = f3ps_graph(ctx); if (rc) return rc; }   // if (!init_initial_weights) init_weights()  (:675-676)
+    rc = mark(ctx, 7); if (rc) return rc;
+    const unsigned S = ctx->S, E = ctx->E, P = ctx->n_pos; const size_t Sc = std::max(1u, S), Ec = std::max(1u, E), Pc = std::max(1u, P);
+    // cluster(float) always restarts from initial_state (:678)
+    F3PS_CUDA_OK(cudaMemcpyAsync(ctx->reg_work.p, ctx->reg_init.p, region_bytes(Sc), cudaMemcpyDeviceToDevice, ctx->stream));
+    const size_t eb = std::min(ctx->edge_init.cap, ctx->edge_work.cap);
+    F3PS_CUDA_OK(cudaMemcpyAsync(ctx->edge_work.p, ctx->edge_init.p, eb, cudaMemcpyDeviceToDevice, ctx->stream));
+    F3PS_CUDA_OK(cudaMemsetAsync(SC(mctl), 0, sizeof(MergeCtl), ctx->stream));
+    F3PS_CUDA_OK(ctx->mlog.ensure(Sc * 20));
+    char* lp = (char*)ctx->mlog.p;
+    ctx->ML.a = (unsigned*)lp; ctx->ML.b = (unsigned*)(lp + Sc * 4); ctx->ML.w = (float*)(lp + Sc * 8);
+    ctx->ML.edges_left = (unsigned*)(lp + Sc * 12); ctx->ML.regions_left = (unsigned*)(lp + Sc * 16);
+    F3PS_CUDA_OK(ctx->run_out_off.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->run_dense.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->region_dense.ensure(Sc * 4));
+    F3PS_CUDA_OK(ctx->out_xyz.ensure(Pc * 12)); F3PS_CUDA_OK(ctx->out_label.ensure(Pc * 4)); F3PS_CUDA_OK(ctx->out_voxel.ensure(Pc * 4));
+    F3PS_CUDA_OK(ctx->vox_segment.ensure(Pc * 4));
+    F3PS_CUDA_OK(cudaMemsetAsync(ctx->vox_segment.p, 0xff, Pc * 4, ctx->stream));
+    F3PS_CUDA_OK(cudaMemsetAsync(SC(n_out), 0, 4, ctx->stream));
+    if (S) {
+        EdgeParams ep = edge_params(ctx);
+        rc = mark(ctx, 9); if (rc) return rc;
+        LAUNCH(ctx, merge_kernel, 1, kMergeThreads, 0, ctx->R1, ctx->E1, SC(n_edges), SC(n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
+               ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl));
+        rc = mark(ctx, 10); if (rc) return rc;
+        LAUNCH(ctx, dense_label_kernel, 1, 1, 0, ctx->R1, SC(n_sv), ctx->run_start.as<unsigned>(), ctx->run_end.as<unsigned>(), ctx->run_out_off.as<unsigned>(),
+               ctx->run_dense.as<unsigned>(), ctx->region_dense.as<unsigned>(), SC(n_out));
+        if (P) LAUNCH(ctx, labeled_cloud_kernel, grid_for(P, 256), 256, 0, ctx->pos_run.as<unsigned>(), P, ctx->order, ctx->run_start.as<unsigned>(),
+                      ctx->run_out_off.as<unsigned>(), ctx->run_dense.as<unsigned>(), ctx->gxyz, ctx->out_xyz.as<float>(), ctx->out_label.as<unsigned>(),
+                      ctx->out_voxel.as<unsigned>(), ctx->vox_segment.as<unsigned>());
+    }
+    rc = mark(ctx, 8); if (rc) return rc;
+    rc = pull_scalars(ctx); if (rc) return rc;
+    if (ctx->h_sc->mctl.error == F3PS_MERGE_ERR_TOUCHED) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "a merge touched more than 1024 edges");
+    ctx->n_out = ctx->h_sc->n_out;
+    ctx->progress = P_MERGED;
+    return F3PS_OK;
+}
+
+int f3ps_extract(f3ps_ctx* ctx) {
+    int rc;
+    if ((rc = f3ps_voxelize(ctx))) return rc;
+    if ((rc = f3ps_neighbors(ctx))) return rc;
+    if ((rc = f3ps_normals(ctx))) return rc;
+    if ((rc = f3ps_seeds(ctx))) return rc;
+    if ((rc = f3ps_expand(ctx))) return rc;
+    return f3ps_graph(ctx);
+}
+int f3ps_run(f3ps_ctx* ctx, float threshold) {
+    int rc = f3ps_extract(ctx);
+    if (rc) return rc;
+    return f3ps_merge(ctx, threshold);
+}
+
+int f3ps_merge_profile(f3ps_ctx* ctx, uint64_t cycles[8]) {
+    if (!ctx || !cycles) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_MERGED, "f3ps_merge_profile"); if (rc) return rc;
+    for (int i = 0; i < 8; ++i) cycles[i] = ctx->h_sc->mctl.phase_cycles[i];
+    return F3PS_OK;
+}
+
+int f3ps_stage_ms(f3ps_ctx* ctx, int stage, float* ms) {
+    if (!ctx || !ms || stage < 0 || stage > 8) return F3PS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    F3PS_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    int i0, i1;
+    if (stage == F3PS_STAGE_TOTAL) { i0 = 0; i1 = 8; }
+    else if (stage == F3PS_STAGE_MERGE_KERNEL) { i0 = 9; i1 = 10; }
+    else if (stage == F3PS_STAGE_MERGE) { i0 = 7; i1 = 8; }
+    else { i0 = stage; i1 = stage + 1; }
+    if (!ctx->ev_valid[i0] || !ctx->ev_valid[i1]) return ctx_fail(ctx, F3PS_ERR_LOGIC, "stage has not run");
+    F3PS_CUDA_OK(cudaEventElapsedTime(ms, ctx->ev[i0], ctx->ev[i1]));
+    return F3PS_OK;
+}
+
+} // extern "C"
+
+// =====================================================================================================
+// results
+namespace {
+int d2h(f3ps_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!bytes || !dst) return F3PS_OK;
+    F3PS_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return F3PS_OK;
+}
+int fin(f3ps_ctx* ctx) { F3PS_CUDA_OK(cudaStreamSynchronize(ctx->stream)); return F3PS_OK; }
+int cap_check(f3ps_ctx* ctx, int64_t need_n, int64_t capacity) {
+    if (capacity < need_n) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "output capacity too small");
+    return F3PS_OK;
+}
+}
+
+extern "C" {
+
+int f3ps_get_counts(f3ps_ctx* ctx, f3ps_counts* out) {
+    if (!ctx || !out) return F3PS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    int rc = pull_scalars(ctx); if (rc) return rc;
+    const DevScalars& h = *ctx->h_sc;
+    memset(out, 0, sizeof *out);
+    out->n_points = ctx->n_points; out->n_valid = ctx->n_valid; out->n_voxels = ctx->V; out->depth = ctx->depth;
+    out->seed_depth = h.sb.depth; out->n_seed_cells = (int)ctx->n_cells; out->n_seeds = (int)ctx->S0;
+    out->n_supervoxels = (int)ctx->S; out->n_edges = (int)ctx->E;
+    out->n_merges = (int)h.mctl.n_merges; out->n_segments = (int)h.mctl.regions_alive; out->n_edges_left = (int)h.mctl.edges_alive;
+    out->rounds = ctx->rounds; out->sweeps = (int)h.flags.sweeps_total; out->n_labeled = (int)ctx->n_out;
+    out->lambda = h.lambda;
+    out->max_touched = (int)h.mctl.max_touched; out->fold_steps = (int64_t)h.mctl.fold_steps;
+    out->nan_weights = (int)(h.mctl.nan_weights + h.nan_weights_init);
+    if (ctx->progress < P_MERGED) { out->n_segments = (int)ctx->S; out->n_edges_left = (int)ctx->E; }
+    return F3PS_OK;
+}
+
+int f3ps_get_voxel_keys(f3ps_ctx* ctx, uint32_t* keys, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_VOXELS, "f3ps_get_voxel_keys"); if (rc) return rc;
+    if ((rc = cap_check(ctx, ctx->V, capacity))) return rc;
+    std::vector<uint64_t> m(ctx->V);
+    if ((rc = d2h(ctx, m.data(), ctx->vox_key.p, (size_t)ctx->V * 8))) return rc;
+    if ((rc = fin(ctx))) return rc;
+    for (unsigned v = 0; v < ctx->V; ++v) morton_decode(m[v], keys[3 * v], keys[3 * v + 1], keys[3 * v + 2]);
+    return F3PS_OK;
+}
+
+int f3ps_get_voxel_centroids(f3ps_ctx* ctx, float* xyz, float* rgb, uint32_t* rgba, int32_t* count, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_VOXELS, "f3ps_get_voxel_centroids"); if (rc) return rc;
+    if ((rc = cap_check(ctx, ctx->V, capacity))) return rc;
+    const unsigned V = ctx->V;
+    std::vector<float4> a(V), b(V);
+    if ((rc = d2h(ctx, a.data(), ctx->vox_xyz.p, (size_t)V * 16))) return rc;
+    if ((rc = d2h(ctx, b.data(), ctx->vox_rgb.p, (size_t)V * 16))) return rc;
+    if ((rc = fin(ctx))) return rc;
+    for (unsigned v = 0; v < V; ++v) {
+        if (xyz) { xyz[3 * v] = a[v].x; xyz[3 * v + 1] = a[v].y; xyz[3 * v + 2] = a[v].z; }
+        if (rgb) { rgb[3 * v] = b[v].x; rgb[3 * v + 1] = b[v].y; rgb[3 * v + 2] = b[v].z; }
+        if (rgba) memcpy(&rgba[v], &a[v].w, 4);
+        if (count) count[v] = (int)b[v].w;
+    }
+    return F3PS_OK;
+}
+
+int f3ps_get_point_voxel(f3ps_ctx* ctx, int32_t* pv, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_VOXELS, "f3ps_get_point_voxel"); if (rc) return rc;
+    if ((rc = cap_check(ctx, ctx->n_points, capacity))) return rc;
+    if ((rc = d2h(ctx, pv, ctx->point_voxel.p, (size_t)ctx->n_points * 4))) return rc;
+    return fin(ctx);
+}
+
+int f3ps_get_voxel_neighbors(f3ps_ctx* ctx, int32_t* nbr, int32_t* nbr_count, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_NEIGHBORS, "f3ps_get_voxel_neighbors"); if (rc) return rc;
+    if ((rc = cap_check(ctx, ctx->V, capacity))) return rc;
+    const unsigned V = ctx->V;
+    std::vector<int> rows((size_t)V * kNbrStride);
+    if ((rc = d2h(ctx, rows.data(), ctx->nbr_row.p, rows.size() * 4))) return rc;
+    if ((rc = fin(ctx))) return rc;
+    for (unsigned v = 0; v < V; ++v) {
+        if (nbr) for (int r = 0; r < 27; ++r) nbr[(size_t)v * 27 + r] = rows[(size_t)v * kNbrStride + r];
+        if (nbr_count) nbr_count[v] = rows[(size_t)v * kNbrStride + 27];
+    }
+    return F3PS_OK;
+}
+
+int f3ps_get_voxel_normals(f3ps_ctx* ctx, float* normal4, float* curvature, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_NORMALS, "f3ps_get_voxel_normals"); if (rc) return rc;
+    if ((rc = cap_check(ctx, ctx->V, capacity))) return rc;
+    if ((rc = d2h(ctx, normal4, ctx->vox_normal.p, (size_t)ctx->V * 16))) return rc;
+    if ((rc = d2h(ctx, curvature, ctx->vox_curv.p, (size_t)ctx->V * 4))) return rc;
+    return fin(ctx);
+}
+
+int f3ps_get_seeds(f3ps_ctx* ctx, int32_t* seed_voxel, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_SEEDS, "f3ps_get_seeds"); if (rc) return rc;
+    if ((rc = cap_check(ctx, ctx->S0, capacity))) return rc;
+    if ((rc = d2h(ctx, seed_voxel, ctx->seeds.p, (size_t)ctx->S0 * 4))) return rc;
+    return fin(ctx);
+}
+
+int f3ps_get_voxel_labels(f3ps_ctx* ctx, uint32_t* label, float* distance, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_EXPANDED, "f3ps_get_voxel_labels"); if (rc) return rc;
+    if (ctx->graph_from_host) return ctx_fail(ctx, F3PS_ERR_LOGIC, "no voxel labels: graph was supplied by the caller");
+    if ((rc = cap_check(ctx, ctx->V, capacity))) return rc;
+    if ((rc = d2h(ctx, label, ctx->owner0.p, (size_t)ctx->V * 4))) return rc;
+    if ((rc = d2h(ctx, distance, ctx->dist0.p, (size_t)ctx->V * 4))) return rc;
+    return fin(ctx);
+}
+
+int f3ps_get_supervoxels(f3ps_ctx* ctx, uint32_t* label, float* centroid, float* mean_rgb, float* normal4, int32_t* n_voxels, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_EXPANDED, "f3ps_get_supervoxels"); if (rc) return rc;
+    if (ctx->graph_from_host) return ctx_fail(ctx, F3PS_ERR_LOGIC, "supervoxels were supplied by the caller");
+    if ((rc = cap_check(ctx, ctx->S, capacity))) return rc;
+    const unsigned S = ctx->S, Sc = ctx->S0 + 2;
+    std::vector<unsigned> lab(S);
+    std::vector<float4> x(Sc), c(Sc), n(Sc);
+    if ((rc = d2h(ctx, lab.data(), ctx->sv_label.p, (size_t)S * 4))) return rc;
+    if ((rc = d2h(ctx, x.data(), ctx->cen_xyz.p, (size_t)Sc * 16))) return rc;
+    if ((rc = d2h(ctx, c.data(), ctx->cen_rgb.p, (size_t)Sc * 16))) return rc;
+    if ((rc = d2h(ctx, n.data(), ctx->cen_nrm.p, (size_t)Sc * 16))) return rc;
+    if ((rc = fin(ctx))) return rc;
+    for (unsigned s = 0; s < S; ++s) {
+        const unsigned l = lab[s];
+        if (label) label[s] = l;
+        if (centroid) { centroid[3 * s] = x[l].x; centroid[3 * s + 1] = x[l].y; centroid[3 * s + 2] = x[l].z; }
+        if (mean_rgb) { mean_rgb[3 * s] = c[l].x; mean_rgb[3 * s + 1] = c[l].y; mean_rgb[3 * s + 2] = c[l].z; }
+        if (normal4) { normal4[4 * s] = n[l].x; normal4[4 * s + 1] = n[l].y; normal4[4 * s + 2] = n[l].z; normal4[4 * s + 3] = n[l].w; }
+        if (n_voxels) n_voxels[s] = (int)x[l].w;
+    }
+    return F3PS_OK;
+}
+
+int f3ps_get_supervoxel_voxels(f3ps_ctx* ctx, int32_t* voxel_index, int64_t* offsets, int64_t cap_voxels, int64_t cap_sv) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_GRAPH, "f3ps_get_supervoxel_voxels"); if (rc) return rc;
+    const unsigned S = ctx->S, P = ctx->n_pos;
+    if ((rc = cap_check(ctx, S, cap_sv))) return rc;
+    std::vector<unsigned> rs(S), re(S), ord(P);
+    if ((rc = d2h(ctx, rs.data(), ctx->run_start.p, (size_t)S * 4))) return rc;
+    if ((rc = d2h(ctx, re.data(), ctx->run_end.p, (size_t)S * 4))) return rc;
+    if ((rc = d2h(ctx, ord.data(), ctx->order, (size_t)P * 4))) return rc;
+    if ((rc = fin(ctx))) return rc;
+    int64_t tot = 0;
+    for (unsigned s = 0; s < S; ++s) tot += re[s] - rs[s];
+    if ((rc = cap_check(ctx, tot, cap_voxels))) return rc;
+    int64_t o = 0;
+    for (unsigned s = 0; s < S; ++s) {
+        if (offsets) offsets[s] = o;
+        for (unsigned i = rs[s]; i < re[s]; ++i) { if (voxel_index) voxel_index[o] = (int)ord[i]; ++o; }
+    }
+    if (offsets) offsets[S] = o;
+    return F3PS_OK;
+}
+
+static int fetch_edges(f3ps_ctx* ctx, const EdgeArrays& EA, unsigned n, std::vector<unsigned>& a, std::vector<unsigned>& b, std::vector<float>& dc,
+                       std::vector<float>& dg, std::vector<float>& w, std::vector<long long>& st, std::vector<unsigned>& lab) {
+    a.resize(n); b.resize(n); dc.resize(n); dg.resize(n); w.resize(n); st.resize(n); lab.resize(ctx->S);
+    int rc;
+    if ((rc = d2h(ctx, a.data(), EA.a, (size_t)n * 4))) return rc;
+    if ((rc = d2h(ctx, b.data(), EA.b, (size_t)n * 4))) return rc;
+    if ((rc = d2h(ctx, dc.data(), EA.dc, (size_t)n * 4))) return rc;
+    if ((rc = d2h(ctx, dg.data(), EA.dg, (size_t)n * 4))) return rc;
+    if ((rc = d2h(ctx, w.data(), EA.w, (size_t)n * 4))) return rc;
+    if ((rc = d2h(ctx, st.data(), EA.stamp, (size_t)n * 8))) return rc;
+    if ((rc = d2h(ctx, lab.data(), ctx->sv_label.p, (size_t)ctx->S * 4))) return rc;
+    return fin(ctx);
+}
+
+int f3ps_get_edges(f3ps_ctx* ctx, uint32_t* ab, float* delta_c, float* delta_g, float* weight, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_GRAPH, "f3ps_get_edges"); if (rc) return rc;
+    if ((rc = cap_check(ctx, ctx->E, capacity))) return rc;
+    std::vector<unsigned> a, b, lab; std::vector<float> dc, dg, w; std::vector<long long> st;
+    if ((rc = fetch_edges(ctx, ctx->E0, ctx->E, a, b, dc, dg, w, st, lab))) return rc;
+    for (unsigned e = 0; e < ctx->E; ++e) {
+        if (ab) { ab[2 * e] = lab[a[e]]; ab[2 * e + 1] = lab[b[e]]; }
+        if (delta_c) delta_c[e] = dc[e];
+        if (delta_g) delta_g[e] = dg[e];
+        if (weight) weight[e] = w[e];
+    }
+    return F3PS_OK;
+}
+
+int f3ps_get_adjacency(f3ps_ctx* ctx, uint32_t* pairs, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_GRAPH, "f3ps_get_adjacency"); if (rc) return rc;
+    if ((rc = cap_check(ctx, 2 * (int64_t)ctx->E, capacity))) return rc;
+    std::vector<unsigned> a, b, lab; std::vector<float> dc, dg, w; std::vector<long long> st;
+    if ((rc = fetch_edges(ctx, ctx->E0, ctx->E, a, b, dc, dg, w, st, lab))) return rc;
+    std::vector<std::pair<unsigned, unsigned>> p;
+    for (unsigned e = 0; e < ctx->E; ++e) { p.push_back({lab[a[e]], lab[b[e]]}); p.push_back({lab[b[e]], lab[a[e]]}); }
+    std::sort(p.begin(), p.end());
+    for (size_t i = 0; i < p.size(); ++i) { pairs[2 * i] = p[i].first; pairs[2 * i + 1] = p[i].second; }
+    return F3PS_OK;
+}
+
+int f3ps_get_cdf(f3ps_ctx* ctx, float* cdf_c, float* cdf_g, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_GRAPH, "f3ps_get_cdf"); if (rc) return rc;
+    if (ctx->mp.merge_mode != F3PS_EQUALIZATION) return ctx_fail(ctx, F3PS_ERR_LOGIC, "no CDF unless the merging criterion is EQUALIZATION");
+    if ((rc = cap_check(ctx, ctx->mp.bins, capacity))) return rc;
+    if ((rc = d2h(ctx, cdf_c, ctx->cdf_c.p, (size_t)ctx->mp.bins * 4))) return rc;
+    if ((rc = d2h(ctx, cdf_g, ctx->cdf_g.p, (size_t)ctx->mp.bins * 4))) return rc;
+    return fin(ctx);
+}
+
+int f3ps_get_merge_log(f3ps_ctx* ctx, uint32_t* ab, float* weight, uint32_t* left, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_MERGED, "f3ps_get_merge_log"); if (rc) return rc;
+    const unsigned M = ctx->h_sc->mctl.n_merges;
+    if ((rc = cap_check(ctx, M, capacity))) return rc;
+    std::vector<unsigned> a(M), b(M), el(M), rl(M);
+    if ((rc = d2h(ctx, a.data(), ctx->ML.a, (size_t)M * 4))) return rc;
+    if ((rc = d2h(ctx, b.data(), ctx->ML.b, (size_t)M * 4))) return rc;
+    if ((rc = d2h(ctx, el.data(), ctx->ML.edges_left, (size_t)M * 4))) return rc;
+    if ((rc = d2h(ctx, rl.data(), ctx->ML.regions_left, (size_t)M * 4))) return rc;
+    if ((rc = d2h(ctx, weight, ctx->ML.w, (size_t)M * 4))) return rc;
+    if ((rc = fin(ctx))) return rc;
+    for (unsigned m = 0; m < M; ++m) {
+        if (ab) { ab[2 * m] = a[m]; ab[2 * m + 1] = b[m]; }
+        if (left) { left[2 * m] = el[m]; left[2 * m + 1] = rl[m]; }
+    }
+    return F3PS_OK;
+}
+
+int f3ps_get_state_regions(f3ps_ctx* ctx, uint32_t* label, float* centroid, float* normal, int32_t* n_voxels, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_GRAPH, "f3ps_get_state_regions"); if (rc) return rc;
+    const RegionArrays& R = ctx->progress >= P_MERGED ? ctx->R1 : ctx->R0;
+    const unsigned S = ctx->S;
+    std::vector<int> n(S); std::vector<float4> c(S), nn(S); std::vector<unsigned> lab(S);
+    if ((rc = d2h(ctx, n.data(), R.n, (size_t)S * 4))) return rc;
+    if ((rc = d2h(ctx, c.data(), R.centroid, (size_t)S * 16))) return rc;
+    if ((rc = d2h(ctx, nn.data(), R.normal, (size_t)S * 16))) return rc;
+    if ((rc = d2h(ctx, lab.data(), ctx->sv_label.p, (size_t)S * 4))) return rc;
+    if ((rc = fin(ctx))) return rc;
+    int64_t k = 0;
+    for (unsigned s = 0; s < S; ++s) if (n[s] > 0) ++k;
+    if ((rc = cap_check(ctx, k, capacity))) return rc;
+    k = 0;
+    for (unsigned s = 0; s < S; ++s) {
+        if (n[s] <= 0) continue;
+        if (label) label[k] = lab[s];
+        if (centroid) { centroid[3 * k] = c[s].x; centroid[3 * k + 1] = c[s].y; centroid[3 * k + 2] = c[s].z; }
+        if (normal) { normal[3 * k] = nn[s].x; normal[3 * k + 1] = nn[s].y; normal[3 * k + 2] = nn[s].z; }
+        if (n_voxels) n_voxels[k] = n[s];
+        ++k;
+    }
+    return F3PS_OK;
+}
+
+int f3ps_get_state_edges(f3ps_ctx* ctx, uint32_t* ab, float* weight, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_GRAPH, "f3ps_get_state_edges"); if (rc) return rc;
+    const EdgeArrays& EA = ctx->progress >= P_MERGED ? ctx->E1 : ctx->E0;
+    std::vector<unsigned> a, b, lab; std::vector<float> dc, dg, w; std::vector<long long> st;
+    if ((rc = fetch_edges(ctx, EA, ctx->E, a, b, dc, dg, w, st, lab))) return rc;
+    std::vector<unsigned> idx;
+    for (unsigned e = 0; e < ctx->E; ++e) if (st[e] != kDeadStamp) idx.push_back(e);
+    if ((rc = cap_check(ctx, (int64_t)idx.size(), capacity))) return rc;
+    std::sort(idx.begin(), idx.end(), [&](unsigned x, unsigned y) { return w[x] < w[y] || (w[x] == w[y] && st[x] < st[y]); });   // multimap order
+    for (size_t i = 0; i < idx.size(); ++i) {
+        const unsigned e = idx[i];
+        if (ab) { ab[2 * i] = lab[a[e]]; ab[2 * i + 1] = lab[b[e]]; }
+        if (weight) weight[i] = w[e];
+    }
+    return F3PS_OK;
+}
+
+int f3ps_get_labeled_cloud(f3ps_ctx* ctx, float* xyz, uint32_t* label, uint32_t* voxel_index, int64_t capacity) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_MERGED, "f3ps_get_labeled_cloud"); if (rc) return rc;
+    if ((rc = cap_check(ctx, ctx->n_out, capacity))) return rc;
+    if ((rc = d2h(ctx, xyz, ctx->out_xyz.p, (size_t)ctx->n_out * 12))) return rc;
+    if ((rc = d2h(ctx, label, ctx->out_label.p, (size_t)ctx->n_out * 4))) return rc;
+    if ((rc = d2h(ctx, voxel_index, ctx->out_voxel.p, (size_t)ctx->n_out * 4))) return rc;
+    return fin(ctx);
+}
+
+int f3ps_get_voxel_segments_device(f3ps_ctx* ctx, const uint32_t** device_ptr, int64_t* n) {
+    if (!ctx || !device_ptr || !n) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_MERGED, "f3ps_get_voxel_segments_device"); if (rc) return rc;
+    *device_ptr = ctx->vox_segment.as<uint32_t>(); *n = ctx->n_pos;
+    return F3PS_OK;
+}
+
+// ---- device self tests ------------------------------------------------------------------------------
+static int test_map3(f3ps_ctx* ctx, int which, const float* in1, const float* in2, float* out, int64_t n) {
+    if (!ctx || n < 0) return F3PS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    DevBuf a, b, o;
+    const size_t nb = (size_t)std::max<int64_t>(n, 1) * 12;
+    int rc = F3PS_OK;
+    do {
+        if (a.ensure(nb) != cudaSuccess || b.ensure(nb) != cudaSuccess || o.ensure(nb) != cudaSuccess) { rc = ctx_fail(ctx, F3PS_ERR_CUDA, "cudaMalloc failed"); break; }
+        cudaMemcpyAsync(a.p, in1, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream);
+        if (in2) cudaMemcpyAsync(b.p, in2, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream);
+        const int g = grid_for(n, 128);
+        if (which == 0) lab_test_kernel<<<g, 128, 0, ctx->stream>>>(ctx->d_lab_lut, a.as<float>(), o.as<float>(), n);
+        else if (which == 1) ciede_test_kernel<<<g, 128, 0, ctx->stream>>>(a.as<float>(), b.as<float>(), o.as<float>(), n);
+        else rgb_eucl_test_kernel<<<g, 128, 0, ctx->stream>>>(a.as<float>(), b.as<float>(), o.as<float>(), n);
+        ctx->launches++;
+        cudaMemcpyAsync(out, o.p, (size_t)n * (which == 0 ? 12 : 4), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = ctx_fail_cuda(ctx, e, "self test", __FILE__, __LINE__);
+    } while (0);
+    a.release(); b.release(); o.release();
+    return rc;
+}
+int f3ps_test_rgb2lab(f3ps_ctx* ctx, const float* rgb255, float* lab, int64_t n) { return test_map3(ctx, 0, rgb255, nullptr, lab, n); }
+int f3ps_test_lab_ciede00(f3ps_ctx* ctx, const float* l1, const float* l2, float* out, int64_t n) { return test_map3(ctx, 1, l1, l2, out, n); }
+int f3ps_test_rgb_eucl(f3ps_ctx* ctx, const float* c1, const float* c2, float* out, int64_t n) { return test_map3(ctx, 2, c1, c2, out, n); }
+
+int f3ps_test_sort_pairs(f3ps_ctx* ctx, uint64_t* keys, uint32_t* values, int64_t n, int key_bits) {
+    if (!ctx || n < 0 || key_bits < 1 || key_bits > 64) return F3PS_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    DevBuf ka, kb, va, vb;
+    const size_t nk = (size_t)std::max<int64_t>(n, 1);
+    int rc = F3PS_OK;
+    do {
+        if (ka.ensure(nk * 8) != cudaSuccess || kb.ensure(nk * 8) != cudaSuccess || va.ensure(nk * 4) != cudaSuccess || vb.ensure(nk * 4) != cudaSuccess) {
+            rc = ctx_fail(ctx, F3PS_ERR_CUDA, "cudaMalloc failed"); break; }
+        cudaMemcpyAsync(ka.p, keys, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(va.p, values, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+        unsigned long long* sk = ka.as<unsigned long long>(); unsigned* sv = va.as<unsigned>();
+        if (n) {
+            rc = sort_pairs<unsigned long long>(ctx, ka.as<unsigned long long>(), va.as<unsigned>(), kb.as<unsigned long long>(), vb.as<unsigned>(),
+                                                ka.as<unsigned long long>(), va.as<unsigned>(), nullptr, n, key_bits, &sk, &sv);
+            if (rc) break;
+        }
+        cudaMemcpyAsync(keys, sk, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(values, sv, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = ctx_fail_cuda(ctx, e, "sort self test", __FILE__, __LINE__);
+    } while (0);
+    ka.release(); kb.release(); va.release(); vb.release();
+    return rc;
+}
+
+} // extern "C"

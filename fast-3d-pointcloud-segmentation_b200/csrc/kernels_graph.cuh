@@ -1,0 +1,243 @@
+// kernels_graph.cuh -- K6: supervoxel table, supervoxel adjacency, initial region statistics and
+// the initial edge weights.
+//   pcl makeSupervoxels / getSupervoxelAdjacency            
+//   Clustering::set_initialstate / init_weights / init_merging_parameters / compute_cdf
+//                                                           (src/clustering.cpp:212-314, 605-612)
+#pragma once
+#include "colour.cuh"
+#include "kernels_vccs.cuh"
+
+namespace f3ps {
+
+// graph nodes are indexed by RANK s in [0,S): ascending label order (a < b  <=>  rank a < rank b)
+struct RegionArrays {
+    float4* mean;      // cnt, r, g, b
+    float4* accu0;     // a0..a3
+    float4* accu1;     // a4..a7
+    float4* accu2;     // a8, -, -, -
+    float4* centroid;  // cx, cy, cz, -
+    float4* normal;    // nx, ny, nz, curvature
+    int* n;            // voxel count, 0 = erased
+    int* head;         // rope: first / last run (run id = rank of an initial supervoxel), next pointer per run
+    int* tail;
+    int* next_run;
+};
+
+__device__ __forceinline__ void load_stats(const RegionArrays& R, int s, RegionStats& st) {
+    const float4 m = R.mean[s], a0 = R.accu0[s], a1 = R.accu1[s], a2 = R.accu2[s];
+    st.cnt = m.x; st.r = m.y; st.g = m.z; st.b = m.w;
+    st.accu[0] = a0.x; st.accu[1] = a0.y; st.accu[2] = a0.z; st.accu[3] = a0.w;
+    st.accu[4] = a1.x; st.accu[5] = a1.y; st.accu[6] = a1.z; st.accu[7] = a1.w; st.accu[8] = a2.x;
+    st.n = R.n[s];
+}
+__device__ __forceinline__ void store_stats(const RegionArrays& R, int s, const RegionStats& st) {
+    R.mean[s] = make_float4(st.cnt, st.r, st.g, st.b);
+    R.accu0[s] = make_float4(st.accu[0], st.accu[1], st.accu[2], st.accu[3]);
+    R.accu1[s] = make_float4(st.accu[4], st.accu[5], st.accu[6], st.accu[7]);
+    R.accu2[s] = make_float4(st.accu[8], 0, 0, 0);
+    R.n[s] = st.n;
+}
+
+// Warp-cooperative ordered fold of the voxels order[s..e) into `st` (replicated in every lane):
+// the lanes fetch 32 voxels at a time, then every lane replays them in order.
+__device__ __forceinline__ void fold_run(RegionStats& st, const unsigned* __restrict__ order, unsigned s, unsigned e,
+                                         const float4* __restrict__ vox_xyz, int lane) {
+    for (unsigned base = s; base < e; base += 32) {
+        const unsigned m = min(32u, e - base);
+        float4 mine = make_float4(0, 0, 0, 0);
+        if (base + lane < e) mine = vox_xyz[order[base + lane]];
+        for (unsigned j = 0; j < m; ++j) {
+            const float x = __shfl_sync(kFull, mine.x, j), y = __shfl_sync(kFull, mine.y, j), z = __shfl_sync(kFull, mine.z, j);
+            const uint32_t c = __float_as_uint(__shfl_sync(kFull, mine.w, j));
+            stats_step(st, x, y, z, c);
+        }
+    }
+}
+
+// alive labels -> ranks
+struct AliveOp {
+    const unsigned* seg_start; const unsigned* seg_end; unsigned* sv_label; unsigned* rank_of_label;
+    typedef int Payload;
+    __device__ __forceinline__ bool test(int64_t i, Payload&) const { unsigned l = (unsigned)i + 1; return seg_end[l] > seg_start[l]; }
+    __device__ __forceinline__ void emit(unsigned pos, int64_t i, const Payload&) const { sv_label[pos] = (unsigned)i + 1; rank_of_label[i + 1] = pos; }
+};
+
+// initial regions: one warp per supervoxel; statistics over its own voxels, geometry from the
+// helper centroid (pcl::Supervoxel::centroid_ / normal_, NOT the covariance normal -- C.3)
+__global__ void __launch_bounds__(256) region_init_kernel(const unsigned* __restrict__ sv_label, const unsigned* __restrict__ n_sv_ptr,
+        const unsigned* __restrict__ seg_start, const unsigned* __restrict__ seg_end, const unsigned* __restrict__ sorted_vox,
+        const float4* __restrict__ vox_xyz, Centroids cen, RegionArrays R, unsigned* __restrict__ run_start, unsigned* __restrict__ run_end) {
+    const unsigned S = *n_sv_ptr;
+    const int lane = threadIdx.x & 31;
+    const unsigned warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < S; s += warps_total) {
+        const unsigned l = sv_label[s];
+        const unsigned b = seg_start[l], e = seg_end[l];
+        RegionStats st; st.cnt = st.r = st.g = st.b = 0.0f; st.n = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) st.accu[k] = 0.0f;
+        fold_run(st, sorted_vox, b, e, vox_xyz, lane);
+        if (lane == 0) {
+            store_stats(R, s, st);
+            const float4 c = cen.xyz[l], nn = cen.nrm[l];
+            R.centroid[s] = make_float4(c.x, c.y, c.z, 0.0f);
+            R.normal[s] = make_float4(nn.x, nn.y, nn.z, 0.0f);
+            R.head[s] = (int)s; R.tail[s] = (int)s; R.next_run[s] = -1;
+            run_start[s] = b; run_end[s] = e;
+        }
+    }
+}
+
+// f3ps_set_graph path: statistics over caller-supplied voxel ranges (order = identity)
+__global__ void __launch_bounds__(256) region_init_ranges_kernel(unsigned S, const unsigned* __restrict__ run_start,
+        const unsigned* __restrict__ run_end, const unsigned* __restrict__ order, const float4* __restrict__ vox_xyz, RegionArrays R) {
+    const int lane = threadIdx.x & 31;
+    const unsigned warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < S; s += warps_total) {
+        RegionStats st; st.cnt = st.r = st.g = st.b = 0.0f; st.n = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) st.accu[k] = 0.0f;
+        fold_run(st, order, run_start[s], run_end[s], vox_xyz, lane);
+        if (lane == 0) { store_stats(R, s, st); R.head[s] = (int)s; R.tail[s] = (int)s; R.next_run[s] = -1; }
+    }
+}
+
+// getSupervoxelAdjacency + clear_adjacency: unique (a<b) label pairs through a hash set
+__global__ void __launch_bounds__(256) edge_collect_kernel(const int* __restrict__ nbr_col, unsigned V_cap, const int* __restrict__ nbr_row,
+        const unsigned* __restrict__ n_vox_ptr, const unsigned* __restrict__ owner, const unsigned* __restrict__ rank_of_label,
+        unsigned long long* __restrict__ set_slots, unsigned mask, unsigned* __restrict__ overflow) {
+    const unsigned V = *n_vox_ptr;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        const unsigned lv = owner[v];
+        if (!lv) continue;
+        const int cnt = nbr_row[(size_t)v * kNbrStride + 27];
+        unsigned last = 0;
+        for (int r = 0; r < cnt; ++r) {
+            const unsigned lu = owner[nbr_col[(size_t)r * V_cap + v]];
+            if (lu == 0 || lu <= lv || lu == last) continue;     // keep a < b only (clear_adjacency)
+            last = lu;
+            const unsigned long long k = (((unsigned long long)rank_of_label[lv]) << 32 | rank_of_label[lu]) + 1ull;
+            unsigned h = hash64(k) & mask;
+            unsigned probes = 0;
+            while (true) {
+                const unsigned long long prev = atomicCAS(&set_slots[h], 0ull, k);
+                if (prev == 0ull || prev == k) break;
+                h = (h + 1) & mask;
+                if (++probes > mask) { *overflow = 1; break; }
+            }
+        }
+    }
+}
+struct EdgeSlotOp {      // hash-set slots -> dense key list (rank_a << 32 | rank_b), unsorted
+    const unsigned long long* slots; unsigned long long* keys; unsigned* vals;
+    typedef int Payload;
+    __device__ __forceinline__ bool test(int64_t i, Payload&) const { return slots[i] != 0ull; }
+    __device__ __forceinline__ void emit(unsigned pos, int64_t i, const Payload&) const { keys[pos] = slots[i] - 1ull; vals[pos] = pos; }
+};
+
+struct EdgeArrays {
+    unsigned* a; unsigned* b;        // ranks, a < b
+    float* dc; float* dg; float* w;
+    long long* stamp;                // tie key; dead edges carry kDeadStamp
+};
+constexpr long long kDeadStamp = 0x7fffffffffffffffll;
+
+__device__ __forceinline__ void region_inputs(const RegionArrays& R, int s, float rgb[3], float n[3], float c[3]) {
+    const float4 m = R.mean[s], cc = R.centroid[s], nn = R.normal[s];
+    rgb[0] = m.y; rgb[1] = m.z; rgb[2] = m.w;
+    n[0] = nn.x; n[1] = nn.y; n[2] = nn.z;
+    c[0] = cc.x; c[1] = cc.y; c[2] = cc.z;
+}
+
+// init_weights first loop: (delta_c, delta_g) of every initial edge, lexicographic order
+__global__ void __launch_bounds__(128) edge_delta_kernel(const unsigned long long* __restrict__ sorted_keys, const unsigned* __restrict__ n_edges_ptr,
+        RegionArrays R, EdgeParams ep, EdgeArrays E, unsigned* __restrict__ dc_bits, unsigned* __restrict__ dg_bits) {
+    const unsigned n = *n_edges_ptr;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const unsigned long long k = sorted_keys[e];
+        const unsigned a = (unsigned)(k >> 32), b = (unsigned)k;
+        float rgb1[3], n1[3], c1[3], rgb2[3], n2[3], c2[3];
+        region_inputs(R, a, rgb1, n1, c1); region_inputs(R, b, rgb2, n2, c2);
+        float dc, dg;
+        delta_c_g(ep, rgb1, rgb2, n1, c1, n2, c2, dc, dg);
+        E.a[e] = a; E.b[e] = b; E.dc[e] = dc; E.dg[e] = dg;
+        dc_bits[e] = __float_as_uint(dc); dg_bits[e] = __float_as_uint(dg);   // sortable: deltas are >= 0
+    }
+}
+
+// Clustering::deltas_mean over the ascending-sorted deltas (two chains: thread 0 -> c, thread 32 -> g),
+// then lambda = mean_g / (mean_c + mean_g)  (init_merging_parameters, ADAPTIVE_LAMBDA)
+__global__ void adaptive_lambda_kernel(const unsigned* __restrict__ sorted_dc, const unsigned* __restrict__ sorted_dg,
+                                       const unsigned* __restrict__ n_edges_ptr, float* __restrict__ lambda_out) {
+    __shared__ float s_mean[2];
+    const unsigned n = *n_edges_ptr;
+    if (threadIdx.x == 0 || threadIdx.x == 32) {
+        const unsigned* src = threadIdx.x == 0 ? sorted_dc : sorted_dg;
+        float count = 0, mean_d = 0;
+        for (unsigned i = 0; i < n; ++i) {
+            const float delta = __uint_as_float(src[i]);
+            count = count + 1.0f;
+            mean_d = mean_d + (1 / count) * (delta - mean_d);
+        }
+        s_mean[threadIdx.x >> 5] = mean_d;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *lambda_out = s_mean[1] / (s_mean[0] + s_mean[1]);
+}
+
+// Clustering::compute_cdf for both distributions: histogram (shared-memory atomics when the bins
+// fit, else global), inclusive scan, cdf[i] = float(cum_i) / float(n).  One block per distribution.
+__global__ void __launch_bounds__(1024) cdf_kernel(const float* __restrict__ dc, const float* __restrict__ dg, const unsigned* __restrict__ n_edges_ptr,
+        int bins, float* __restrict__ cdf_c, float* __restrict__ cdf_g, unsigned* __restrict__ ghist, unsigned* __restrict__ bad_bin) {
+    extern __shared__ unsigned s_bins[];
+    const unsigned n = *n_edges_ptr;
+    const float* src = blockIdx.x == 0 ? dc : dg;
+    float* cdf = blockIdx.x == 0 ? cdf_c : cdf_g;
+    const bool use_smem = bins <= 8192;
+    unsigned* hist = use_smem ? s_bins : ghist + (size_t)blockIdx.x * bins;
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        short bin = (short)floorf(src[i] * bins);
+        if (bin == bins) bin--;
+        if (bin < 0 || bin >= bins) { *bad_bin = 1; continue; }   // the reference indexes out of bounds here (UB)
+        atomicAdd(&hist[bin], 1u);
+    }
+    __syncthreads();
+    // inclusive scan in chunks of blockDim with a running carry
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < bins; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        unsigned v = i < bins ? hist[i] : 0u;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { unsigned t = __shfl_up_sync(kFull, v, off); if (lane >= off) v += t; }
+        if (lane == 31) s_warp[warp] = v;
+        __syncthreads();
+        unsigned wb = 0;
+        for (int w = 0; w < warp; ++w) wb += s_warp[w];
+        const unsigned cum = s_carry + wb + v;
+        if (i < bins) cdf[i] = (float)cum / (float)(int)n;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = cum;
+        __syncthreads();
+    }
+}
+
+// init_weights second loop: w = t_c(dc) + t_g(dg); stamp = lexicographic rank (multimap insertion order)
+__global__ void __launch_bounds__(256) edge_weight_kernel(const unsigned* __restrict__ n_edges_ptr, EdgeParams ep, const float* __restrict__ lambda_dev,
+                                                          EdgeArrays E, unsigned* __restrict__ nan_count) {
+    const unsigned n = *n_edges_ptr;
+    if (lambda_dev) ep.lambda = *lambda_dev;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const float w = unify(ep, E.dc[e], E.dg[e]);
+        if (isnan(w)) atomicAdd(nan_count, 1u);
+        E.w[e] = w;
+        E.stamp[e] = (long long)e;
+    }
+}
+
+} // namespace f3ps

@@ -1,0 +1,314 @@
+"""ctypes binding of libf3ps.so (the C ABI in include/f3ps.h).
+
+This is the Python-side mirror of the reference's plugin interface for the hot path
+(pcl::SupervoxelClustering as driven by main() + Clustering): same parameter names,
+same error behaviour (std::logic_error -> LogicError, std::invalid_argument ->
+ValueError).  There is no CPU fallback: without the CUDA library or without a GPU every
+call raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(PKG, "libf3ps.so")
+
+LAB_CIEDE00, RGB_EUCL = 0, 1
+NORMALS_DIFF, CONVEX_NORMALS_DIFF = 0, 1
+MANUAL_LAMBDA, ADAPTIVE_LAMBDA, EQUALIZATION = 0, 1, 2
+STAGES = ["voxelize", "neighbors", "normals", "seeds", "expand", "graph", "merge", "total", "merge_kernel"]
+
+
+class F3psError(RuntimeError):
+    pass
+
+
+class LogicError(F3psError):
+    """std::logic_error of the reference (src/clustering.cpp:576,591,672)."""
+
+
+class Counts(C.Structure):
+    _fields_ = [("n_points", C.c_int64), ("n_valid", C.c_int64), ("n_voxels", C.c_int64),
+                ("depth", C.c_int32), ("seed_depth", C.c_int32), ("n_seed_cells", C.c_int32),
+                ("n_seeds", C.c_int32), ("n_supervoxels", C.c_int32), ("n_edges", C.c_int32),
+                ("n_merges", C.c_int32), ("n_segments", C.c_int32), ("n_edges_left", C.c_int32),
+                ("rounds", C.c_int32), ("sweeps", C.c_int32), ("n_labeled", C.c_int32),
+                ("lambda_", C.c_float), ("max_touched", C.c_int32),
+                ("fold_steps", C.c_int64), ("nan_weights", C.c_int32), ("reserved", C.c_int32)]
+
+
+_lib = None
+
+
+def build(force=False):
+    """Compile libf3ps.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(PKG, "csrc", f) for f in os.listdir(os.path.join(PKG, "csrc"))
+            if f.endswith((".cu", ".cuh", ".S"))]
+    srcs.append(os.path.join(os.path.dirname(PKG), "include", "f3ps.h"))
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
+        subprocess.check_call(["make", "-C", PKG, "-s"])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise F3psError("libf3ps.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+    sig = {
+        "f3ps_create": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
+        "f3ps_destroy": (None, [vp]),
+        "f3ps_last_error": (C.c_char_p, [vp]),
+        "f3ps_version": (C.c_char_p, []),
+        "f3ps_set_vccs_params": (C.c_int, [vp, f32, f32, f32, f32, f32, C.c_int, C.c_int]),
+        "f3ps_set_merge_params": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, f32, C.c_int]),
+        "f3ps_set_input": (C.c_int, [vp, vp, i64, C.c_int, C.c_int]),
+        "f3ps_voxelize": (C.c_int, [vp]), "f3ps_neighbors": (C.c_int, [vp]), "f3ps_normals": (C.c_int, [vp]),
+        "f3ps_seeds": (C.c_int, [vp]), "f3ps_expand": (C.c_int, [vp]), "f3ps_graph": (C.c_int, [vp]),
+        "f3ps_merge": (C.c_int, [vp, f32]), "f3ps_extract": (C.c_int, [vp]), "f3ps_run": (C.c_int, [vp, f32]),
+        "f3ps_sync": (C.c_int, [vp]),
+        "f3ps_set_graph": (C.c_int, [vp, i64, vp, vp, i32, vp, vp, vp, vp, i64, vp]),
+        "f3ps_get_counts": (C.c_int, [vp, C.POINTER(Counts)]),
+        "f3ps_get_voxel_keys": (C.c_int, [vp, vp, i64]),
+        "f3ps_get_voxel_centroids": (C.c_int, [vp, vp, vp, vp, vp, i64]),
+        "f3ps_get_point_voxel": (C.c_int, [vp, vp, i64]),
+        "f3ps_get_voxel_neighbors": (C.c_int, [vp, vp, vp, i64]),
+        "f3ps_get_voxel_normals": (C.c_int, [vp, vp, vp, i64]),
+        "f3ps_get_seeds": (C.c_int, [vp, vp, i64]),
+        "f3ps_get_voxel_labels": (C.c_int, [vp, vp, vp, i64]),
+        "f3ps_get_supervoxels": (C.c_int, [vp, vp, vp, vp, vp, vp, i64]),
+        "f3ps_get_supervoxel_voxels": (C.c_int, [vp, vp, vp, i64, i64]),
+        "f3ps_get_adjacency": (C.c_int, [vp, vp, i64]),
+        "f3ps_get_edges": (C.c_int, [vp, vp, vp, vp, vp, i64]),
+        "f3ps_get_cdf": (C.c_int, [vp, vp, vp, i64]),
+        "f3ps_get_merge_log": (C.c_int, [vp, vp, vp, vp, i64]),
+        "f3ps_get_state_regions": (C.c_int, [vp, vp, vp, vp, vp, i64]),
+        "f3ps_get_state_edges": (C.c_int, [vp, vp, vp, i64]),
+        "f3ps_get_labeled_cloud": (C.c_int, [vp, vp, vp, vp, i64]),
+        "f3ps_get_voxel_segments_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+        "f3ps_stage_ms": (C.c_int, [vp, C.c_int, C.POINTER(f32)]),
+        "f3ps_launch_count": (i64, [vp]),
+        "f3ps_merge_profile": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
+        "f3ps_test_rgb2lab": (C.c_int, [vp, vp, vp, i64]),
+        "f3ps_test_lab_ciede00": (C.c_int, [vp, vp, vp, vp, i64]),
+        "f3ps_test_rgb_eucl": (C.c_int, [vp, vp, vp, vp, i64]),
+        "f3ps_test_sort_pairs": (C.c_int, [vp, vp, vp, i64, C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTED = ["f3ps_create", "f3ps_destroy", "f3ps_last_error", "f3ps_version", "f3ps_set_vccs_params",
+            "f3ps_set_merge_params", "f3ps_set_input", "f3ps_voxelize", "f3ps_neighbors", "f3ps_normals", "f3ps_seeds",
+            "f3ps_expand", "f3ps_graph", "f3ps_merge", "f3ps_extract", "f3ps_run", "f3ps_sync", "f3ps_set_graph",
+            "f3ps_get_counts", "f3ps_get_voxel_keys", "f3ps_get_voxel_centroids", "f3ps_get_point_voxel",
+            "f3ps_get_voxel_neighbors", "f3ps_get_voxel_normals", "f3ps_get_seeds", "f3ps_get_voxel_labels",
+            "f3ps_get_supervoxels", "f3ps_get_supervoxel_voxels", "f3ps_get_adjacency", "f3ps_get_edges", "f3ps_get_cdf",
+            "f3ps_get_merge_log", "f3ps_get_state_regions", "f3ps_get_state_edges", "f3ps_get_labeled_cloud",
+            "f3ps_get_voxel_segments_device", "f3ps_stage_ms", "f3ps_launch_count", "f3ps_merge_profile", "f3ps_test_rgb2lab",
+            "f3ps_test_lab_ciede00", "f3ps_test_rgb_eucl", "f3ps_test_sort_pairs"]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Segmenter:
+    """One handle = one GPU + one stream (f3ps_create)."""
+
+    def __init__(self, device=0, stream=None):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.f3ps_create(device, stream, C.byref(h))
+        if rc:
+            raise F3psError("f3ps_create failed (status %d): no usable CUDA device; there is no CPU fallback" % rc)
+        self.h = h
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.f3ps_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc == 0:
+            return
+        msg = self.L.f3ps_last_error(self.h).decode()
+        if rc == 1:
+            raise ValueError(msg)
+        if rc == 2:
+            raise LogicError(msg)
+        raise F3psError("status %d: %s" % (rc, msg))
+
+    # ---- parameters (same defaults as the CLI, src/supervoxel_clustering.cpp:247-267) ----
+    def set_vccs_params(self, voxel_res=0.008, seed_res=0.08, color=0.2, spatial=0.4, normal=1.0,
+                        use_transform=True, fold_negative_z=True):
+        self._chk(self.L.f3ps_set_vccs_params(self.h, voxel_res, seed_res, color, spatial, normal,
+                                              int(use_transform), int(fold_negative_z)))
+
+    def set_merge_params(self, color_mode=LAB_CIEDE00, geom_mode=NORMALS_DIFF, merge_mode=ADAPTIVE_LAMBDA, lam=0.5, bins=500):
+        self._chk(self.L.f3ps_set_merge_params(self.h, color_mode, geom_mode, merge_mode, lam, bins))
+        self._bins = bins
+
+    # ---- input ----
+    def set_input(self, pts):
+        """pts: numpy structured array (32-byte pcl::PointXYZRGBA records) or any 16/32-byte record array."""
+        pts = np.ascontiguousarray(pts)
+        self._keep = pts
+        self._chk(self.L.f3ps_set_input(self.h, _p(pts), pts.shape[0], pts.dtype.itemsize, 0))
+
+    def set_input_device(self, dev_ptr, n, stride=32):
+        self._chk(self.L.f3ps_set_input(self.h, C.c_void_p(dev_ptr), n, stride, 1))
+
+    # ---- stages ----
+    def voxelize(self): self._chk(self.L.f3ps_voxelize(self.h))
+    def neighbors(self): self._chk(self.L.f3ps_neighbors(self.h))
+    def normals(self): self._chk(self.L.f3ps_normals(self.h))
+    def seeds(self): self._chk(self.L.f3ps_seeds(self.h))
+    def expand(self): self._chk(self.L.f3ps_expand(self.h))
+    def graph(self): self._chk(self.L.f3ps_graph(self.h))
+    def merge(self, threshold): self._chk(self.L.f3ps_merge(self.h, threshold))
+    def extract(self): self._chk(self.L.f3ps_extract(self.h))
+    def run(self, threshold=0.2): self._chk(self.L.f3ps_run(self.h, threshold))
+    def sync(self): self._chk(self.L.f3ps_sync(self.h))
+
+    def set_graph(self, vxyz, vrgba, labels, vox_lists, centroids, normals, adj_pairs):
+        """Clustering::set_initialstate on caller-supplied supervoxels (voxel index lists per supervoxel)."""
+        vxyz = np.ascontiguousarray(vxyz, np.float32)
+        vrgba = np.ascontiguousarray(vrgba, np.uint32)
+        labels = np.ascontiguousarray(labels, np.uint32)
+        order = np.concatenate(vox_lists).astype(np.int64) if len(vox_lists) else np.zeros(0, np.int64)
+        off = np.zeros(len(vox_lists) + 1, np.int64)
+        off[1:] = np.cumsum([len(v) for v in vox_lists])
+        gx = np.ascontiguousarray(vxyz[order])
+        gc = np.ascontiguousarray(vrgba[order])
+        centroids = np.ascontiguousarray(centroids, np.float32)
+        normals = np.ascontiguousarray(normals, np.float32)
+        adj = np.ascontiguousarray(adj_pairs, np.uint32).reshape(-1, 2)
+        self._graph_order = order
+        self._chk(self.L.f3ps_set_graph(self.h, gx.shape[0], _p(gx), _p(gc), len(labels), _p(labels), _p(off),
+                                        _p(centroids), _p(normals), adj.shape[0], _p(adj)))
+
+    # ---- results ----
+    def counts(self):
+        c = Counts()
+        self._chk(self.L.f3ps_get_counts(self.h, C.byref(c)))
+        return c
+
+    def stage_ms(self):
+        out = {}
+        v = C.c_float()
+        for i, name in enumerate(STAGES):
+            if self.L.f3ps_stage_ms(self.h, i, C.byref(v)) == 0:
+                out[name] = v.value
+        return out
+
+    def merge_profile(self):
+        a = (C.c_uint64 * 8)()
+        self._chk(self.L.f3ps_merge_profile(self.h, C.byref(a)))
+        return dict(zip(["argmin", "fold_scan", "order", "delta", "stamps"], list(a)[:5]))
+
+    def launch_count(self):
+        return int(self.L.f3ps_launch_count(self.h))
+
+    def array(self, name):
+        """Named result arrays (the names the parity tests use for both sides)."""
+        c = self.counts()
+        V, S0, S, E = c.n_voxels, c.n_seeds, c.n_supervoxels, c.n_edges
+        if name == "keys":
+            a = np.zeros((V, 3), np.uint32); self._chk(self.L.f3ps_get_voxel_keys(self.h, _p(a), V)); return a
+        if name in ("voxel_xyz", "voxel_rgb", "voxel_rgba", "voxel_count"):
+            x = np.zeros((V, 3), np.float32); r = np.zeros((V, 3), np.float32); q = np.zeros(V, np.uint32); n = np.zeros(V, np.int32)
+            self._chk(self.L.f3ps_get_voxel_centroids(self.h, _p(x), _p(r), _p(q), _p(n), V))
+            return {"voxel_xyz": x, "voxel_rgb": r, "voxel_rgba": q, "voxel_count": n}[name]
+        if name == "point_voxel":
+            a = np.zeros(c.n_points, np.int32); self._chk(self.L.f3ps_get_point_voxel(self.h, _p(a), c.n_points)); return a
+        if name in ("nbr", "nbr_count"):
+            a = np.zeros((V, 27), np.int32); n = np.zeros(V, np.int32)
+            self._chk(self.L.f3ps_get_voxel_neighbors(self.h, _p(a), _p(n), V)); return a if name == "nbr" else n
+        if name in ("normals", "curvature"):
+            a = np.zeros((V, 4), np.float32); k = np.zeros(V, np.float32)
+            self._chk(self.L.f3ps_get_voxel_normals(self.h, _p(a), _p(k), V)); return a if name == "normals" else k
+        if name == "seeds":
+            a = np.zeros(S0, np.int32); self._chk(self.L.f3ps_get_seeds(self.h, _p(a), S0)); return a
+        if name in ("labels", "dist"):
+            a = np.zeros(V, np.uint32); d = np.zeros(V, np.float32)
+            self._chk(self.L.f3ps_get_voxel_labels(self.h, _p(a), _p(d), V)); return a if name == "labels" else d
+        if name in ("sv_label", "sv_xyz", "sv_rgb", "sv_normal", "sv_count"):
+            l = np.zeros(S, np.uint32); x = np.zeros((S, 3), np.float32); r = np.zeros((S, 3), np.float32)
+            n4 = np.zeros((S, 4), np.float32); n = np.zeros(S, np.int32)
+            self._chk(self.L.f3ps_get_supervoxels(self.h, _p(l), _p(x), _p(r), _p(n4), _p(n), S))
+            return {"sv_label": l, "sv_xyz": x, "sv_rgb": r, "sv_normal": n4, "sv_count": n}[name]
+        if name == "adj":
+            a = np.zeros((2 * E, 2), np.uint32); self._chk(self.L.f3ps_get_adjacency(self.h, _p(a), 2 * E)); return a
+        if name in ("edges_ab", "edges_dc", "edges_dg", "edges_w"):
+            ab = np.zeros((E, 2), np.uint32); dc = np.zeros(E, np.float32); dg = np.zeros(E, np.float32); w = np.zeros(E, np.float32)
+            self._chk(self.L.f3ps_get_edges(self.h, _p(ab), _p(dc), _p(dg), _p(w), E))
+            return {"edges_ab": ab, "edges_dc": dc, "edges_dg": dg, "edges_w": w}[name]
+        if name in ("cdf_c", "cdf_g"):
+            n = self._bins
+            a = np.zeros(n, np.float32); b = np.zeros(n, np.float32)
+            self._chk(self.L.f3ps_get_cdf(self.h, _p(a), _p(b), n)); return a if name == "cdf_c" else b
+        if name in ("merges_ab", "merges_w", "merges_left"):
+            M = c.n_merges
+            ab = np.zeros((M, 2), np.uint32); w = np.zeros(M, np.float32); left = np.zeros((M, 2), np.uint32)
+            self._chk(self.L.f3ps_get_merge_log(self.h, _p(ab), _p(w), _p(left), M))
+            return {"merges_ab": ab, "merges_w": w, "merges_left": left}[name]
+        if name in ("final_ab", "final_w"):
+            n = c.n_edges_left
+            ab = np.zeros((n, 2), np.uint32); w = np.zeros(n, np.float32)
+            self._chk(self.L.f3ps_get_state_edges(self.h, _p(ab), _p(w), n)); return ab if name == "final_ab" else w
+        if name in ("out_xyz", "out_label", "out_voxel"):
+            n = c.n_labeled
+            x = np.zeros((n, 3), np.float32); l = np.zeros(n, np.uint32); v = np.zeros(n, np.uint32)
+            self._chk(self.L.f3ps_get_labeled_cloud(self.h, _p(x), _p(l), _p(v), n))
+            return {"out_xyz": x, "out_label": l, "out_voxel": v}[name]
+        raise KeyError(name)
+
+    def state_regions(self):
+        n = self.counts().n_segments
+        l = np.zeros(n, np.uint32); x = np.zeros((n, 3), np.float32); nn = np.zeros((n, 3), np.float32); k = np.zeros(n, np.int32)
+        self._chk(self.L.f3ps_get_state_regions(self.h, _p(l), _p(x), _p(nn), _p(k), n))
+        return l, x, nn, k
+
+    def supervoxel_voxels(self):
+        c = self.counts()
+        idx = np.zeros(c.n_voxels, np.int32); off = np.zeros(c.n_supervoxels + 1, np.int64)
+        self._chk(self.L.f3ps_get_supervoxel_voxels(self.h, _p(idx), _p(off), c.n_voxels, c.n_supervoxels))
+        return idx[:off[-1]], off
+
+    # ---- device self tests ----
+    def test_rgb2lab(self, rgb255):
+        a = np.ascontiguousarray(rgb255, np.float32).reshape(-1, 3); o = np.zeros_like(a)
+        self._chk(self.L.f3ps_test_rgb2lab(self.h, _p(a), _p(o), a.shape[0])); return o
+
+    def test_lab_ciede00(self, l1, l2):
+        a = np.ascontiguousarray(l1, np.float32).reshape(-1, 3); b = np.ascontiguousarray(l2, np.float32).reshape(-1, 3)
+        o = np.zeros(a.shape[0], np.float32)
+        self._chk(self.L.f3ps_test_lab_ciede00(self.h, _p(a), _p(b), _p(o), a.shape[0])); return o
+
+    def test_rgb_eucl(self, c1, c2):
+        a = np.ascontiguousarray(c1, np.float32).reshape(-1, 3); b = np.ascontiguousarray(c2, np.float32).reshape(-1, 3)
+        o = np.zeros(a.shape[0], np.float32)
+        self._chk(self.L.f3ps_test_rgb_eucl(self.h, _p(a), _p(b), _p(o), a.shape[0])); return o
+
+    def test_sort_pairs(self, keys, values, key_bits):
+        k = np.ascontiguousarray(keys, np.uint64).copy(); v = np.ascontiguousarray(values, np.uint32).copy()
+        self._chk(self.L.f3ps_test_sort_pairs(self.h, _p(k), _p(v), k.shape[0], key_bits)); return k, v
+
+    _bins = 500

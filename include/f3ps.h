@@ -1,0 +1,172 @@
+/* f3ps.h -- C ABI of the B200-native supervoxel-plus-merging hot path.
+ *
+ * Drop-in boundary for the path SURVEY.md section 8 scopes: everything the
+ * reference's main() does between "cloud loaded" and "labelled voxel cloud"
+ * (/root/reference/src/supervoxel_clustering.cpp:315-367, 408-449), i.e.
+ *   pcl::SupervoxelClustering<PointXYZRGBA> (ctor, setters, extract,
+ *       getSupervoxelAdjacency)                         supervoxel_clustering.cpp:348-367
+ *   Clustering::set_initialstate / cluster / get_*       src/clustering.cpp:605-679
+ *   ColorUtilities::mean_color / rgb2lab / lab_ciede00 / rgb_eucl
+ *                                                        src/color_utilities.cpp:117-319
+ * The C++ facade in include/supervoxel_clustering/ re-creates the reference's
+ * class names on top of these calls; a reference maintainer binds them as shown
+ * in INTEGRATION.md.
+ *
+ * Conventions: plain C, opaque handle, int status (0 = ok), no exceptions and no
+ * torch / PCL types across the boundary.  One handle owns one CUDA device + stream
+ * and all device memory; handles are independent (one per GPU for -d sweeps), a
+ * single handle is not thread safe.  Host buffers belong to the caller.
+ * There is NO CPU fallback: every entry point fails with F3PS_ERR_CUDA when no
+ * device is usable.
+ */
+#ifndef F3PS_H_
+#define F3PS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct f3ps_ctx f3ps_ctx;
+
+enum f3ps_status {
+    F3PS_OK = 0,
+    F3PS_ERR_INVALID_ARGUMENT = 1, /* std::invalid_argument in the reference (clustering.cpp:579,594) */
+    F3PS_ERR_LOGIC = 2,            /* std::logic_error (clustering.cpp:576,591,672) */
+    F3PS_ERR_CUDA = 3,             /* CUDA runtime failure / no device */
+    F3PS_ERR_CAPACITY = 4,         /* an internal fixed-capacity structure overflowed */
+    F3PS_ERR_NOT_CONVERGED = 5     /* expansion fixed point not reached within the sweep budget */
+};
+
+/* enums of include/supervoxel_clustering/clustering.h:62-72, same numeric values */
+enum f3ps_color_distance { F3PS_LAB_CIEDE00 = 0, F3PS_RGB_EUCL = 1 };
+enum f3ps_geometric_distance { F3PS_NORMALS_DIFF = 0, F3PS_CONVEX_NORMALS_DIFF = 1 };
+enum f3ps_merging_criterion { F3PS_MANUAL_LAMBDA = 0, F3PS_ADAPTIVE_LAMBDA = 1, F3PS_EQUALIZATION = 2 };
+
+/* stages for f3ps_stage_ms (K1..K7 of SURVEY.md section 2) */
+enum f3ps_stage {
+    F3PS_STAGE_VOXELIZE = 0, F3PS_STAGE_NEIGHBORS = 1, F3PS_STAGE_NORMALS = 2, F3PS_STAGE_SEEDS = 3,
+    F3PS_STAGE_EXPAND = 4, F3PS_STAGE_GRAPH = 5, F3PS_STAGE_MERGE = 6, F3PS_STAGE_TOTAL = 7,
+    F3PS_STAGE_MERGE_KERNEL = 8   /* the persistent merge kernel alone (inside F3PS_STAGE_MERGE) */
+};
+
+typedef struct f3ps_counts {
+    int64_t n_points;      /* N: input points (NaNs included) */
+    int64_t n_valid;       /* points that entered a voxel */
+    int64_t n_voxels;      /* V */
+    int32_t depth;         /* adjacency-octree depth */
+    int32_t seed_depth;    /* seed-octree depth */
+    int32_t n_seed_cells;  /* occupied seed cells */
+    int32_t n_seeds;       /* S0: seeds kept (labels 1..S0) */
+    int32_t n_supervoxels; /* S: supervoxels alive after expansion */
+    int32_t n_edges;       /* E: initial supervoxel-graph edges (a<b) */
+    int32_t n_merges;      /* M: merges performed by the last f3ps_merge */
+    int32_t n_segments;    /* regions left */
+    int32_t n_edges_left;  /* edges left */
+    int32_t rounds;        /* VCCS expansion rounds I */
+    int32_t sweeps;        /* total fixed-point sweeps over all rounds */
+    int32_t n_labeled;     /* points in the labelled voxel cloud */
+    float lambda;          /* lambda in use (adaptive value after f3ps_graph) */
+    int32_t max_touched;   /* largest number of edges re-weighted by one merge */
+    int64_t fold_steps;    /* voxel steps folded by the merge loop (sum of |b|) */
+    int32_t nan_weights;   /* edge weights that evaluated to NaN (regions with < 3 voxels) */
+    int32_t reserved;
+} f3ps_counts;
+
+/* ---- life cycle ------------------------------------------------------------ */
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on, or NULL for a private one. */
+int f3ps_create(int device, void* stream, f3ps_ctx** out);
+void f3ps_destroy(f3ps_ctx* ctx);
+const char* f3ps_last_error(const f3ps_ctx* ctx);
+const char* f3ps_version(void);
+
+/* ---- parameters ------------------------------------------------------------ */
+/* SupervoxelClustering(Rv,Rs) + setColor/Spatial/NormalImportance + setUseSingleCameraTransform
+ * (supervoxel_clustering.cpp:348-353); fold_negative_z = main()'s z<0 -> |z| (:317-321). */
+int f3ps_set_vccs_params(f3ps_ctx* ctx, float voxel_resolution, float seed_resolution, float color_importance,
+                         float spatial_importance, float normal_importance, int use_single_camera_transform,
+                         int fold_negative_z);
+/* Clustering::set_delta_c / set_delta_g / set_merging / set_lambda / set_bins_num
+ * (clustering.h:126-137, clustering.cpp:562-597).  Range errors as in the reference. */
+int f3ps_set_merge_params(f3ps_ctx* ctx, int color_distance, int geometric_distance, int merging_criterion,
+                          float lambda, int bins_num);
+
+/* ---- input ----------------------------------------------------------------- */
+/* points: n records of stride_bytes (32 = pcl::PointXYZRGBA {x,y,z,_, b,g,r,a, pad}, 16 = {x,y,z,bgra}).
+ * on_device != 0: `points` is device memory valid until the next f3ps_set_input. */
+int f3ps_set_input(f3ps_ctx* ctx, const void* points, int64_t n, int stride_bytes, int on_device);
+
+/* ---- stages (each needs the previous one) ------------------------------------ */
+int f3ps_voxelize(f3ps_ctx* ctx);   /* K1 OctreePointCloudAdjacency::addPointsFromInputCloud */
+int f3ps_neighbors(f3ps_ctx* ctx);  /* K2 computeNeighbors */
+int f3ps_normals(f3ps_ctx* ctx);    /* K3 computeVoxelData */
+int f3ps_seeds(f3ps_ctx* ctx);      /* K4 selectInitialSupervoxelSeeds */
+int f3ps_expand(f3ps_ctx* ctx);     /* K5 expandSupervoxels */
+int f3ps_graph(f3ps_ctx* ctx);      /* K6 makeSupervoxels + getSupervoxelAdjacency + set_initialstate + init_weights */
+int f3ps_merge(f3ps_ctx* ctx, float threshold); /* K7 Clustering::cluster(threshold): restarts from the initial state */
+/* SupervoxelClustering::extract + getSupervoxelAdjacency = K1..K5 + supervoxel tables */
+int f3ps_extract(f3ps_ctx* ctx);
+/* whole path: K1..K7 */
+int f3ps_run(f3ps_ctx* ctx, float threshold);
+/* blocks until every queued stage is finished */
+int f3ps_sync(f3ps_ctx* ctx);
+
+/* Clustering::set_initialstate on caller-supplied supervoxels (clustering.cpp:605-612):
+ * voxel arrays (xyz float3, truncated colour 0x00RRGGBB) in the order of each
+ * supervoxel's voxels_, supervoxels by ascending label with their voxel ranges,
+ * centroid_ (xyz) and normal_ (xyz), and the adjacency multimap in iteration order. */
+int f3ps_set_graph(f3ps_ctx* ctx, int64_t n_voxels, const float* voxel_xyz, const uint32_t* voxel_rgba,
+                   int32_t n_supervoxels, const uint32_t* labels, const int64_t* voxel_offsets,
+                   const float* centroids_xyz, const float* normals_xyz,
+                   int64_t n_adjacency, const uint32_t* adjacency_pairs);
+
+/* ---- results (copy out; capacity in elements of the leading dimension) --------- */
+int f3ps_get_counts(f3ps_ctx* ctx, f3ps_counts* out);
+int f3ps_get_voxel_keys(f3ps_ctx* ctx, uint32_t* keys_xyz /*[V][3]*/, int64_t capacity);
+int f3ps_get_voxel_centroids(f3ps_ctx* ctx, float* xyz /*[V][3]*/, float* rgb /*[V][3]*/, uint32_t* rgba /*[V]*/,
+                             int32_t* count /*[V]*/, int64_t capacity);
+int f3ps_get_point_voxel(f3ps_ctx* ctx, int32_t* voxel_of_point /*[N]*/, int64_t capacity);
+int f3ps_get_voxel_neighbors(f3ps_ctx* ctx, int32_t* nbr /*[V][27] list order, -1 padded*/, int32_t* nbr_count /*[V]*/,
+                             int64_t capacity);
+int f3ps_get_voxel_normals(f3ps_ctx* ctx, float* normal4 /*[V][4]*/, float* curvature /*[V]*/, int64_t capacity);
+int f3ps_get_seeds(f3ps_ctx* ctx, int32_t* seed_voxel /*[S0]*/, int64_t capacity);
+int f3ps_get_voxel_labels(f3ps_ctx* ctx, uint32_t* label /*[V], 0 = unowned*/, float* distance /*[V]*/, int64_t capacity);
+int f3ps_get_supervoxels(f3ps_ctx* ctx, uint32_t* label /*[S]*/, float* centroid_xyz /*[S][3]*/, float* mean_rgb /*[S][3]*/,
+                         float* normal4 /*[S][4]*/, int32_t* n_voxels /*[S]*/, int64_t capacity);
+/* voxel indices grouped by supervoxel label (ascending), idx order inside = Supervoxel::voxels_ */
+int f3ps_get_supervoxel_voxels(f3ps_ctx* ctx, int32_t* voxel_index /*[n_owned]*/, int64_t* offsets /*[S+1]*/,
+                               int64_t capacity_voxels, int64_t capacity_supervoxels);
+int f3ps_get_adjacency(f3ps_ctx* ctx, uint32_t* pairs /*[2E][2] both directions, sorted*/, int64_t capacity);
+int f3ps_get_edges(f3ps_ctx* ctx, uint32_t* ab /*[E][2]*/, float* delta_c, float* delta_g, float* weight, int64_t capacity);
+int f3ps_get_cdf(f3ps_ctx* ctx, float* cdf_c /*[bins]*/, float* cdf_g /*[bins]*/, int64_t capacity);
+/* the reference's per-merge debug line (clustering.cpp:390-392): edges left, regions left, w, a, b */
+int f3ps_get_merge_log(f3ps_ctx* ctx, uint32_t* ab /*[M][2]*/, float* weight /*[M]*/, uint32_t* left /*[M][2]*/, int64_t capacity);
+/* Clustering::get_currentstate(): regions (label, centroid, normal, size) and remaining weighted edges in map order */
+int f3ps_get_state_regions(f3ps_ctx* ctx, uint32_t* label, float* centroid_xyz, float* normal_xyz, int32_t* n_voxels, int64_t capacity);
+int f3ps_get_state_edges(f3ps_ctx* ctx, uint32_t* ab, float* weight, int64_t capacity);
+/* Clustering::get_labeled_cloud(): voxel centroids with dense labels 0..K-1 in ascending region label order */
+int f3ps_get_labeled_cloud(f3ps_ctx* ctx, float* xyz /*[n][3]*/, uint32_t* label /*[n]*/, uint32_t* voxel_index /*[n]*/, int64_t capacity);
+/* per-voxel final segment label (dense, 0xffffffff = unowned) resident on the device; for device consumers */
+int f3ps_get_voxel_segments_device(f3ps_ctx* ctx, const uint32_t** device_ptr, int64_t* n);
+
+/* CUDA-event time of the last run of a stage, ms (valid after f3ps_sync) */
+int f3ps_stage_ms(f3ps_ctx* ctx, int stage, float* ms);
+/* SM cycles the last f3ps_merge spent per phase of the merge loop: argmin, fold||edge scan, ordering,
+ * re-weighting, tie stamps (thread 0's clock64; profiling aid) */
+int f3ps_merge_profile(f3ps_ctx* ctx, uint64_t cycles[8]);
+/* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
+int64_t f3ps_launch_count(const f3ps_ctx* ctx);
+
+/* metric kernels on the device, for known-answer tests (ColorUtilities::rgb2lab / lab_ciede00 / rgb_eucl):
+ * n colour pairs in, n values out; host pointers. */
+int f3ps_test_rgb2lab(f3ps_ctx* ctx, const float* rgb255 /*[n][3]*/, float* lab /*[n][3]*/, int64_t n);
+int f3ps_test_lab_ciede00(f3ps_ctx* ctx, const float* lab1, const float* lab2, float* out, int64_t n);
+int f3ps_test_rgb_eucl(f3ps_ctx* ctx, const float* rgb1, const float* rgb2, float* out, int64_t n);
+/* radix sort self-test: sorts (key,value) pairs on the device, stable */
+int f3ps_test_sort_pairs(f3ps_ctx* ctx, uint64_t* keys, uint32_t* values, int64_t n, int key_bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F3PS_H_ */

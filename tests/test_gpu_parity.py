@@ -1,0 +1,287 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs and against the committed golden fixture.  Integer / index / key results must be
+identical; float results are compared bit for bit as well (the kernels replay the scalar IEEE
+sequence), which is stricter than BASELINE.json's 1e-5 relative bound on edge weights."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "small_frame.npz")
+AL = dict(color_mode=0, geom_mode=1, merge_mode=1)
+EQ = dict(color_mode=0, geom_mode=0, merge_mode=2, bins=200)
+RGB_ML = dict(color_mode=1, geom_mode=0, merge_mode=0, lam=0.5)
+
+STAGE_ARRAYS = ["keys", "voxel_xyz", "voxel_rgb", "voxel_rgba", "voxel_count", "point_voxel", "nbr_count", "nbr", "normals",
+                "curvature", "seeds", "labels", "dist", "sv_label", "sv_xyz", "sv_rgb", "sv_normal", "sv_count", "adj",
+                "edges_ab", "edges_dc", "edges_dg", "edges_w"]
+MERGE_ARRAYS = ["merges_ab", "merges_w", "merges_left", "final_ab", "final_w", "out_label", "out_voxel", "out_xyz"]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def same(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    if a.shape != b.shape:
+        return False
+    if a.dtype.kind == "f":
+        return bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+    return bool(np.array_equal(a, b))
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import f3ps
+    f3ps.build()
+    return f3ps
+
+
+def run_both(gpu, oracle_mod, pts, mp, thr, merge_impl=1, **vccs):
+    g = gpu.Segmenter()
+    g.set_vccs_params(**vccs)
+    gm = dict(mp)
+    g.set_merge_params(**gm)
+    g.set_input(pts)
+    g.run(thr)
+    o = oracle_mod.Oracle()
+    o.set_vccs_params(**vccs)
+    o.set_merge_params(merge_impl=merge_impl, **mp)
+    o.set_input(pts)
+    o.run(0, thr)
+    return g, o
+
+
+def assert_parity(g, o, names):
+    bad = [n for n in names if not same(g.array(n), o.array(n))]
+    assert not bad, "GPU differs from the oracle in: %s" % bad
+
+
+def test_golden_fixture(gpu):
+    """No oracle involved: the committed vectors the oracle produced (tools/gen_golden.py)."""
+    gold = np.load(GOLD)
+    pts = gpu.synth.pack_points(gold["xyz"], gold["rgba"])
+    g = gpu.Segmenter(); g.set_vccs_params(); g.set_merge_params(**AL); g.set_input(pts); g.run(0.2)
+    for n in ("keys", "voxel_count", "nbr_count", "seeds", "labels", "sv_label", "sv_count"):
+        assert np.array_equal(g.array(n), gold[n]), n
+    for n in ("voxel_xyz", "voxel_rgb", "normals", "nbr", "dist"):
+        d = np.frombuffer(hashlib.sha256(np.ascontiguousarray(g.array(n)).tobytes()).digest(), np.uint8)
+        assert np.array_equal(d, gold[n + "_sha256"]), n
+    assert np.array_equal(g.array("edges_ab"), gold["al_edges_ab"])
+    assert np.array_equal(bits(g.array("edges_w")), gold["al_edges_w_bits"])
+    assert np.array_equal(g.array("merges_ab"), gold["al_merges_ab"])
+    assert np.array_equal(bits(g.array("merges_w")), gold["al_merges_w_bits"])
+    assert np.array_equal(g.array("out_label"), gold["al_out_label"])
+    assert np.array_equal(g.array("out_voxel"), gold["al_out_voxel"])
+    assert np.array_equal(bits(np.array([g.counts().lambda_], np.float32)), gold["al_lambda_bits"])
+    # --EQ 200: heavy exact ties, the multimap insertion order decides
+    g.set_merge_params(**EQ); g.merge(float(gold["eq_threshold"][0]))
+    assert np.array_equal(bits(g.array("edges_w")), gold["eq_edges_w_bits"])
+    assert np.array_equal(g.array("merges_ab"), gold["eq_merges_ab"])
+    assert np.array_equal(bits(g.array("merges_w")), gold["eq_merges_w_bits"])
+    assert np.array_equal(g.array("out_label"), gold["eq_out_label"])
+
+
+@pytest.mark.parametrize("mp,thr", [(AL, 0.2), (EQ, 0.6), (RGB_ML, 0.2)])
+def test_small_frame_all_stages_literal_oracle(gpu, oracle_mod, small_frame, mp, thr):
+    g, o = run_both(gpu, oracle_mod, small_frame, mp, thr, merge_impl=0)
+    assert_parity(g, o, STAGE_ARRAYS + MERGE_ARRAYS)
+    if mp["merge_mode"] == 2:
+        assert same(g.array("cdf_c"), o.array("cdf_c")) and same(g.array("cdf_g"), o.array("cdf_g"))
+    assert len(o.array("merges_w")) > 50
+    assert g.counts().nan_weights == int(o.scalars()["nan_weights"]) == 0
+
+
+def test_vga_frame_config2_exact_merge_sequence(gpu, oracle_mod, vga_frame):
+    """BASELINE.json configs[1]: 640x480 frame, --CVX --AL -t 0.2, exact merge-sequence parity."""
+    g, o = run_both(gpu, oracle_mod, vga_frame, AL, 0.2, merge_impl=1)
+    assert_parity(g, o, STAGE_ARRAYS + MERGE_ARRAYS)
+    c = g.counts()
+    assert c.n_points == 307200 and c.n_merges == len(o.array("merges_w")) > 500
+    agree = np.mean(g.array("labels") == o.array("labels"))
+    assert agree >= 0.995                       # BASELINE bar; measured 1.0
+    rel = np.abs(g.array("edges_w") - o.array("edges_w")) / np.abs(o.array("edges_w"))
+    assert np.nanmax(rel) <= 1e-5               # BASELINE bar; measured 0
+
+
+@pytest.mark.parametrize("seed", [30000, 30001, 30002])
+def test_sweep_frames_config3_eq200(gpu, oracle_mod, seed):
+    """configs[2] frames (seeds 30000+i), --EQ 200; threshold raised to 0.5 so merges happen under ties."""
+    pts = gpu.synth.make_frame(seed=seed, width=320, height=240)
+    g, o = run_both(gpu, oracle_mod, pts, EQ, 0.5, merge_impl=1)
+    assert_parity(g, o, STAGE_ARRAYS + MERGE_ARRAYS)
+    assert len(o.array("merges_w")) > 20
+
+
+def test_no_transform_and_other_resolutions(gpu, oracle_mod, small_frame):
+    g, o = run_both(gpu, oracle_mod, small_frame, RGB_ML, 0.2, use_transform=False, voxel_res=0.02, seed_res=0.15)
+    assert_parity(g, o, STAGE_ARRAYS + MERGE_ARRAYS)
+    g, o = run_both(gpu, oracle_mod, small_frame, AL, 0.3, voxel_res=0.01, seed_res=0.1, color=0.5, spatial=0.2, normal=0.7)
+    assert_parity(g, o, STAGE_ARRAYS + MERGE_ARRAYS)
+
+
+def test_negative_z_fold_and_packed_stride(gpu, oracle_mod, small_frame):
+    p2 = small_frame.copy(); p2["z"] = -p2["z"]
+    g, o = run_both(gpu, oracle_mod, p2, AL, 0.2)
+    assert_parity(g, o, ["keys", "labels", "merges_ab"])
+    packed = np.zeros(len(small_frame), np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("rgba", "<u4")]))
+    for k in ("x", "y", "z", "rgba"):
+        packed[k] = small_frame[k]
+    g2 = gpu.Segmenter(); g2.set_vccs_params(); g2.set_merge_params(**AL); g2.set_input(packed); g2.run(0.2)
+    g1 = gpu.Segmenter(); g1.set_vccs_params(); g1.set_merge_params(**AL); g1.set_input(small_frame); g1.run(0.2)
+    for n in ("keys", "labels", "merges_ab", "merges_w"):
+        assert same(g1.array(n), g2.array(n)), n
+
+
+def test_edge_cases_empty_nan_single(gpu, oracle_mod):
+    S = gpu.synth
+    cases = [np.zeros(0, S.POINT_DTYPE),
+             S.pack_points(np.full((300, 3), np.nan, np.float32), np.zeros(300, np.uint32)),
+             S.pack_points(np.array([[0.1, 0.2, 1.0]], np.float32), np.array([0x00ff8040], np.uint32)),
+             S.pack_points(np.array([[0.1, 0.2, 1.0], [0.1, 0.2, 1.0], [np.nan, 0, 1], [0.5, 0.5, 0.0], [0.3, 0.1, 2.0]], np.float32),
+                           np.arange(5, dtype=np.uint32) * 0x00101010)]
+    for pts in cases:
+        g, o = run_both(gpu, oracle_mod, pts, AL, 0.2)
+        assert_parity(g, o, ["keys", "voxel_xyz", "voxel_count", "point_voxel", "nbr", "seeds", "labels", "edges_ab", "merges_ab", "out_label"])
+
+
+def test_ragged_sizes(gpu, oracle_mod, small_frame):
+    for n in (1, 31, 257, 1023, 1025, 4097, 8191):
+        g, o = run_both(gpu, oracle_mod, small_frame[:n], AL, 0.2)
+        assert_parity(g, o, ["keys", "voxel_xyz", "point_voxel", "nbr", "normals", "seeds", "labels", "edges_w", "merges_ab", "out_voxel"])
+
+
+def test_threshold_prefix_property_and_restart(gpu, oracle_mod, small_frame):
+    """cluster(t) restarts from the initial state; a lower threshold yields a prefix of the same sequence (CS4)."""
+    g = gpu.Segmenter(); g.set_vccs_params(); g.set_merge_params(**AL); g.set_input(small_frame); g.run(1.0)
+    full_ab, full_w = g.array("merges_ab"), g.array("merges_w")
+    for thr in (0.05, 0.2, 0.6):
+        g.merge(thr)
+        ab, w = g.array("merges_ab"), g.array("merges_w")
+        k = len(w)
+        assert np.array_equal(ab, full_ab[:k]) and np.array_equal(bits(w), bits(full_w[:k]))
+        assert k == len(full_w) or not (full_w[k] < np.float32(thr))
+        assert np.all(w < np.float32(thr))
+    g.merge(1.0)
+    assert np.array_equal(g.array("merges_ab"), full_ab)
+
+
+def test_set_graph_facade_path(gpu, oracle_mod, small_frame):
+    """Clustering::set_initialstate on caller-supplied supervoxels (what the C++ facade does)."""
+    o = oracle_mod.Oracle(); o.set_vccs_params(); o.set_merge_params(merge_impl=0, **AL); o.set_input(small_frame); o.run(0, 0.25)
+    labels = o.array("sv_label"); vl = o.array("labels")
+    lists = [np.nonzero(vl == l)[0] for l in labels]
+    g = gpu.Segmenter(); g.set_merge_params(**AL)
+    g.set_graph(o.array("voxel_xyz"), o.array("voxel_rgba"), labels, lists, o.array("sv_xyz"), o.array("sv_normal")[:, :3], o.array("adj"))
+    g.merge(0.25)
+    for n in ("edges_ab", "edges_dc", "edges_dg", "edges_w", "merges_ab", "merges_w", "merges_left", "out_label"):
+        assert same(g.array(n), o.array(n)), n
+    assert np.array_equal(g._graph_order[g.array("out_voxel")], o.array("out_voxel"))
+
+
+def test_error_behaviour_matches_reference(gpu):
+    g = gpu.Segmenter()
+    with pytest.raises(gpu.LogicError):          # cluster before set_initialstate (src/clustering.cpp:671-673)
+        g.merge(0.2)
+    with pytest.raises(ValueError):              # set_lambda outside [0,1] (:578-579)
+        g.set_merge_params(merge_mode=gpu.MANUAL_LAMBDA, lam=1.5)
+    with pytest.raises(ValueError):              # set_bins_num < 0 (:593-594)
+        g.set_merge_params(merge_mode=gpu.EQUALIZATION, bins=-3)
+    with pytest.raises(gpu.LogicError):
+        g.voxelize()
+
+
+def test_device_colour_kernels_known_answers(gpu):
+    from test_oracle_color import CIEDE_KAT, RGB_KAT
+    import json
+    g = gpu.Segmenter()
+    l1 = np.array([k[:3] for k in CIEDE_KAT], np.float32); l2 = np.array([k[3:6] for k in CIEDE_KAT], np.float32)
+    exp = np.array([k[6] for k in CIEDE_KAT], np.float32)
+    assert np.max(np.abs(g.test_lab_ciede00(l1, l2) - exp)) < 1e-4
+    c1 = np.array([k[0] for k in RGB_KAT], np.float32); c2 = np.array([k[1] for k in RGB_KAT], np.float32)
+    assert np.array_equal(g.test_rgb_eucl(c1, c2), np.array([k[2] for k in RGB_KAT], np.float32))
+    kat = json.load(open(os.path.join(HERE, "golden", "lab_kat.json")))
+    rgb = np.array([[float.fromhex(h) for h in r] for r in kat["rgb255_f32_hex"]], np.float32)
+    lab = np.array([[float.fromhex(h) for h in r] for r in kat["lab_f32_hex"]], np.float32)
+    assert np.array_equal(g.test_rgb2lab(rgb), lab)
+
+
+def test_device_colour_kernels_vs_oracle_random(gpu, oracle_mod):
+    g = gpu.Segmenter(); o = oracle_mod.Oracle()
+    rng = np.random.default_rng(9)
+    rgb = (rng.random((20000, 3)) * 255).astype(np.float32)
+    lab = g.test_rgb2lab(rgb)
+    ref = np.stack([o.rgb2lab(c) for c in rgb[:3000]])
+    assert np.array_equal(lab[:3000], ref)
+    d = g.test_lab_ciede00(lab[:10000], lab[10000:])
+    refd = np.array([o.lab_ciede00(a, b) for a, b in zip(lab[:3000], lab[10000:13000])], np.float32)
+    assert np.mean(d[:3000] != refd) < 1e-3 and np.max(np.abs(d[:3000] - refd) / np.maximum(refd, 1e-6)) < 1e-6
+
+
+@pytest.mark.parametrize("n,bits_", [(0, 8), (1, 8), (1000, 13), (4096, 24), (100003, 30), (1 << 20, 40), (3000001, 63)])
+def test_radix_sort_stable(gpu, n, bits_):
+    g = gpu.Segmenter()
+    rng = np.random.default_rng(n + bits_)
+    keys = rng.integers(0, 1 << min(bits_, 62), n, dtype=np.uint64) if n else np.zeros(0, np.uint64)
+    if n > 10:
+        keys[: n // 3] = keys[n // 3: 2 * (n // 3)]          # many duplicates: stability is visible
+    vals = np.arange(n, dtype=np.uint32)
+    k, v = g.test_sort_pairs(keys, vals, bits_)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[order]) and np.array_equal(v, vals[order])
+
+
+def test_larger_frame_against_fast_oracle(gpu, oracle_mod):
+    """1.2 M-point frame (1280x960): everything still identical (oracle with the stamp-based merge)."""
+    pts = gpu.synth.make_frame(seed=777, width=1280, height=960)
+    g, o = run_both(gpu, oracle_mod, pts, AL, 0.2, merge_impl=1)
+    assert_parity(g, o, STAGE_ARRAYS + MERGE_ARRAYS)
+
+
+def test_full_size_properties_config4(gpu):
+    """configs[3] shape (10 M points, -v 0.004 -s 0.04 --RGB --ML 0.5): size-independent properties."""
+    pts = gpu.synth.make_dense_scene(seed=40000)
+    g = gpu.Segmenter(); g.set_vccs_params(voxel_res=0.004, seed_res=0.04); g.set_merge_params(**RGB_ML)
+    g.set_input(pts); g.extract()
+    c = g.counts()
+    finite = np.isfinite(pts["x"]) & np.isfinite(pts["y"]) & np.isfinite(pts["z"])
+    assert c.n_points == len(pts) and c.n_valid == int(finite.sum())
+    keys = g.array("keys").astype(np.uint64)
+    assert keys.max() < (1 << c.depth)
+    cnt = g.array("voxel_count"); pv = g.array("point_voxel")
+    assert int(cnt.sum()) == c.n_valid and np.array_equal(pv >= 0, finite)
+    assert np.array_equal(np.bincount(pv[pv >= 0], minlength=c.n_voxels), cnt)      # checksum of the point->voxel map
+    # per-voxel centroid = mean of its points (float64 check of the float32 ordered sums)
+    vx = g.array("voxel_xyz").astype(np.float64)
+    order = np.argsort(pv[finite], kind="stable"); fi = np.nonzero(finite)[0][order]
+    starts = np.concatenate([[0], np.cumsum(cnt)])
+    for v in range(0, c.n_voxels, max(1, c.n_voxels // 300)):
+        idx = fi[starts[v]:starts[v + 1]]
+        m = np.stack([pts["x"][idx], pts["y"][idx], pts["z"][idx]], -1).astype(np.float64).mean(0)
+        assert np.allclose(vx[v], m, rtol=1e-5, atol=1e-6)
+    nbrc = g.array("nbr_count"); nbr = g.array("nbr")
+    assert nbrc.min() >= 1 and nbrc.max() <= 27
+    rows = np.arange(0, c.n_voxels, 1009)
+    for v in rows[:500]:
+        for u in nbr[v, :nbrc[v]]:
+            assert v in nbr[u, :nbrc[u]]
+            assert np.max(np.abs(keys[u].astype(np.int64) - keys[v].astype(np.int64))) <= 1
+    labels = g.array("labels")
+    assert labels.max() <= c.n_seeds and np.mean(labels > 0) > 0.95
+    sv = g.array("sv_label"); svc = g.array("sv_count")
+    assert np.array_equal(np.bincount(labels, minlength=c.n_seeds + 1)[sv], svc)
+    ab = g.array("edges_ab")
+    assert np.all(ab[:, 0] < ab[:, 1]) and len(np.unique(ab, axis=0)) == len(ab)
+    # merge: idempotent restart, prefix property, monotone region count
+    g.merge(0.2)
+    m1 = g.array("merges_ab"); left = g.array("merges_left")
+    assert np.all(np.diff(left[:, 1].astype(np.int64)) == -1)
+    g.merge(0.2)
+    assert np.array_equal(g.array("merges_ab"), m1)
+    out = g.array("out_label")
+    assert len(out) == int((labels > 0).sum()) and out.max() + 1 == g.counts().n_segments
