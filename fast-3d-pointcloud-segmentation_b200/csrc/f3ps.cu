@@ -992,6 +992,17 @@ int f3ps_get_state_regions(f3ps_ctx* ctx, uint32_t* label, float* centroid, floa
     return F3PS_OK;
 }
 
+int f3ps_get_region_mean_color(f3ps_ctx* ctx, int32_t rank, float rgb[3]) {
+    if (!ctx || !rgb) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_GRAPH, "f3ps_get_region_mean_color"); if (rc) return rc;
+    if (rank < 0 || (unsigned)rank >= ctx->S) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "region rank out of range");
+    float4 m;
+    if ((rc = d2h(ctx, &m, ctx->R0.mean + rank, 16))) return rc;
+    if ((rc = fin(ctx))) return rc;
+    rgb[0] = m.y; rgb[1] = m.z; rgb[2] = m.w;
+    return F3PS_OK;
+}
+
 int f3ps_get_state_edges(f3ps_ctx* ctx, uint32_t* ab, float* weight, int64_t capacity) {
     if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
     int rc = need(ctx, P_GRAPH, "f3ps_get_state_edges"); if (rc) return rc;

@@ -90,6 +90,7 @@ def lib():
         "f3ps_get_state_regions": (C.c_int, [vp, vp, vp, vp, vp, i64]),
         "f3ps_get_state_edges": (C.c_int, [vp, vp, vp, i64]),
         "f3ps_get_labeled_cloud": (C.c_int, [vp, vp, vp, vp, i64]),
+        "f3ps_get_region_mean_color": (C.c_int, [vp, i32, vp]),
         "f3ps_get_voxel_segments_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "f3ps_stage_ms": (C.c_int, [vp, C.c_int, C.POINTER(f32)]),
         "f3ps_launch_count": (i64, [vp]),
@@ -113,7 +114,7 @@ EXPORTED = ["f3ps_create", "f3ps_destroy", "f3ps_last_error", "f3ps_version", "f
             "f3ps_get_counts", "f3ps_get_voxel_keys", "f3ps_get_voxel_centroids", "f3ps_get_point_voxel",
             "f3ps_get_voxel_neighbors", "f3ps_get_voxel_normals", "f3ps_get_seeds", "f3ps_get_voxel_labels",
             "f3ps_get_supervoxels", "f3ps_get_supervoxel_voxels", "f3ps_get_adjacency", "f3ps_get_edges", "f3ps_get_cdf",
-            "f3ps_get_merge_log", "f3ps_get_state_regions", "f3ps_get_state_edges", "f3ps_get_labeled_cloud",
+            "f3ps_get_merge_log", "f3ps_get_state_regions", "f3ps_get_state_edges", "f3ps_get_labeled_cloud", "f3ps_get_region_mean_color",
             "f3ps_get_voxel_segments_device", "f3ps_stage_ms", "f3ps_launch_count", "f3ps_merge_profile", "f3ps_test_rgb2lab",
             "f3ps_test_lab_ciede00", "f3ps_test_rgb_eucl", "f3ps_test_sort_pairs"]
 

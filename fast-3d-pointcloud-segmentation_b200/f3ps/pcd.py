@@ -91,3 +91,16 @@ def read_pcd(path):
         pts["rgba"] = c.view(np.uint32) if c.dtype.itemsize == 4 else c.astype(np.uint32)
     label = cols.get("label")
     return pts, (label.astype(np.uint32) if label is not None else None), hdr
+
+
+def write_pcd_binary(path, pts):
+    """pcl::PointXYZRGBA-layout points -> PCD v0.7 DATA binary with FIELDS x y z rgba."""
+    n = len(pts)
+    rec = np.zeros(n, dtype=np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("rgba", "<u4")]))
+    for k in ("x", "y", "z", "rgba"):
+        rec[k] = pts[k]
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z rgba\nSIZE 4 4 4 4\nTYPE F F F U\nCOUNT 1 1 1 1\n"
+           "WIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary\n" % (n, n))
+    with open(path, "wb") as f:
+        f.write(hdr.encode("ascii"))
+        f.write(rec.tobytes())

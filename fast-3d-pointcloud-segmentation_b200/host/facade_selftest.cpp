@@ -1,0 +1,92 @@
+// facade_selftest <file.pcd> [threshold]: runs one cloud through (a) the fused C-ABI path and (b) the
+// reference-shaped classes (SupervoxelClustering -> Clustering), and checks that both give the same merge
+// sequence and labelled cloud, plus the reference's error behaviour and colour known answers.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "pcd_io.h"
+#include "supervoxel_clustering/clustering.h"
+
+#define CHECK(cond, msg) do { if (!(cond)) { fprintf(stderr, "FACADE FAIL: %s (%s:%d)\n", msg, __FILE__, __LINE__); return 1; } } while (0)
+
+int main(int argc, char** argv) {
+    if (argc < 2) { fprintf(stderr, "usage: %s file.pcd [threshold]\n", argv[0]); return 2; }
+    const float thr = argc > 2 ? (float)atof(argv[2]) : 0.2f;
+    pcl::PointCloud<pcl::PointXYZRGBL> input;
+    CHECK(f3ps::loadPCDFile(argv[1], input) == 0, "cannot read the PCD file");
+    for (auto& p : input.points) if (p.z < 0) p.z = std::abs(p.z);
+    pcl::PointCloud<pcl::PointXYZRGBA>::Ptr cloud(new pcl::PointCloud<pcl::PointXYZRGBA>());
+    pcl::copyPointCloud(input, *cloud);
+
+    // error behaviour of the reference (src/clustering.cpp:574-597, 670-673)
+    {
+        Clustering c;
+        bool threw = false;
+        try { c.cluster(0.2f); } catch (const std::logic_error&) { threw = true; }
+        CHECK(threw, "cluster before set_initialstate must throw std::logic_error");
+        threw = false;
+        try { c.set_lambda(0.3f); } catch (const std::logic_error&) { threw = true; }
+        CHECK(threw, "set_lambda under ADAPTIVE_LAMBDA must throw std::logic_error");
+        c.set_merging(MANUAL_LAMBDA);
+        threw = false;
+        try { c.set_lambda(1.5f); } catch (const std::invalid_argument&) { threw = true; }
+        CHECK(threw, "set_lambda(1.5) must throw std::invalid_argument");
+        c.set_merging(EQUALIZATION);
+        CHECK(c.get_bins_num() == 500 && c.get_lambda() == 0.5f, "set_merging resets lambda=0.5, bins=500");
+        threw = false;
+        try { c.set_bins_num(-1); } catch (const std::invalid_argument&) { threw = true; }
+        CHECK(threw, "set_bins_num(-1) must throw std::invalid_argument");
+    }
+    CHECK(ColorUtilities::rgb_test() == 0.0f, "rgb_eucl known answers");
+    CHECK(ColorUtilities::lab_test() < 1e-4f, "CIEDE2000 known answers");
+
+    // (a) fused path
+    f3ps::Handle h(0);
+    h.check(f3ps_set_vccs_params(h.get(), 0.008f, 0.08f, 0.2f, 0.4f, 1.0f, 1, 0));
+    h.check(f3ps_set_merge_params(h.get(), F3PS_LAB_CIEDE00, F3PS_CONVEX_NORMALS_DIFF, F3PS_ADAPTIVE_LAMBDA, 0.5f, 500));
+    h.check(f3ps_set_input(h.get(), cloud->points.data(), (int64_t)cloud->size(), 32, 0));
+    h.check(f3ps_run(h.get(), thr));
+    f3ps_counts n; h.check(f3ps_get_counts(h.get(), &n));
+    std::vector<uint32_t> ab(2 * (size_t)n.n_merges), left(2 * (size_t)n.n_merges); std::vector<float> w(n.n_merges);
+    h.check(f3ps_get_merge_log(h.get(), ab.data(), w.data(), left.data(), n.n_merges));
+    std::vector<float> xyz(3 * (size_t)n.n_labeled); std::vector<uint32_t> lab(n.n_labeled), vox(n.n_labeled);
+    h.check(f3ps_get_labeled_cloud(h.get(), xyz.data(), lab.data(), vox.data(), n.n_labeled));
+
+    // (b) the reference's call sequence (src/supervoxel_clustering.cpp:348-367, 408-449)
+    pcl::SupervoxelClustering<pcl::PointXYZRGBA> super(0.008f, 0.08f);
+    super.setUseSingleCameraTransform(true);
+    super.setInputCloud(cloud);
+    super.setColorImportance(0.2f); super.setSpatialImportance(0.4f); super.setNormalImportance(1.0f);
+    std::map<uint32_t, pcl::Supervoxel<pcl::PointXYZRGBA>::Ptr> supervoxel_clusters;
+    super.extract(supervoxel_clusters);
+    std::multimap<uint32_t, uint32_t> label_adjacency;
+    super.getSupervoxelAdjacency(label_adjacency);
+    CHECK((int)supervoxel_clusters.size() == n.n_supervoxels, "supervoxel count");
+    CHECK((int)label_adjacency.size() == 2 * n.n_edges, "adjacency size");
+    CHECK((int64_t)super.getVoxelCentroidCloud()->size() == n.n_voxels, "voxel centroid cloud size");
+    CHECK(super.getLabeledCloud()->size() == cloud->size(), "labelled input cloud size");
+    Clustering segmentation;
+    segmentation.set_delta_g(CONVEX_NORMALS_DIFF);
+    segmentation.set_initialstate(supervoxel_clusters, label_adjacency);
+    CHECK(segmentation.get_lambda() == 0.5f, "lambda reads 0.5 before the weights are initialised (quirk D.6)");
+    segmentation.cluster(thr);
+    const std::vector<MergeStep>& log = segmentation.get_merge_log();
+    CHECK((int)log.size() == n.n_merges, "merge count differs between the fused path and the class path");
+    for (size_t m = 0; m < log.size(); ++m)
+        CHECK(log[m].a == ab[2 * m] && log[m].b == ab[2 * m + 1] && log[m].w == w[m] && log[m].edges_left == left[2 * m], "merge sequence differs");
+    CHECK(std::fabs(segmentation.get_lambda() - n.lambda) == 0.0f, "adaptive lambda differs");
+    PointLCloudT::Ptr labeled = segmentation.get_labeled_cloud();
+    CHECK((int)labeled->size() == n.n_labeled, "labelled cloud size");
+    for (size_t i = 0; i < labeled->size(); ++i)
+        CHECK(labeled->points[i].label == lab[i] && labeled->points[i].x == xyz[3 * i] && labeled->points[i].z == xyz[3 * i + 2], "labelled cloud differs");
+    std::pair<ClusteringT, AdjacencyMapT> st = segmentation.get_currentstate();
+    CHECK((int)st.first.size() == n.n_segments && (int)st.second.size() == n.n_edges_left, "current state size");
+    // restart from the initial state with a lower threshold: a prefix of the same sequence
+    segmentation.cluster(thr * 0.5f);
+    const std::vector<MergeStep>& log2 = segmentation.get_merge_log();
+    CHECK(log2.size() <= (size_t)n.n_merges, "prefix length");
+    for (size_t m = 0; m < log2.size(); ++m) CHECK(log2[m].a == ab[2 * m] && log2[m].b == ab[2 * m + 1], "prefix differs");
+    printf("FACADE OK: N=%zu V=%lld S=%d E=%d M=%d segments=%d\n", cloud->size(), (long long)n.n_voxels, n.n_supervoxels, n.n_edges, n.n_merges, n.n_segments);
+    return 0;
+}

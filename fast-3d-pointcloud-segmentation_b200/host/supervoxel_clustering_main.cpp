@@ -1,0 +1,168 @@
+// supervoxel_clustering -- the reference's CLI (src/supervoxel_clustering.cpp:136-476) over the f3ps CUDA path.
+// Same flags, same defaults, same quirks for the hot path:
+//   {-d <dir> | -p <file>}  -v -s -c -z -n  -t  --RGB --CVX --ML [l] --AL --EQ [bins]  --NT --V
+// Not built here (out of the hot-path scope): the auto-threshold sweep (needs the
+// evaluation module, so -t is required), -r / -f, the viewer.  Additions: -o <file.pcd> writes the labelled voxel
+// cloud, --facade routes through the Clustering / SupervoxelClustering classes instead of the fused f3ps_run,
+// --gpus N shards the files of a -d sweep over N GPUs (one host thread + handle + stream per GPU, no collective).
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <mutex>
+#include <thread>
+
+#include "pcd_io.h"
+#include "supervoxel_clustering/clustering.h"
+
+namespace {
+// pcl::console::find_switch / parse_argument semantics: exact strcmp match, value = the next argv
+bool find_switch(int argc, char** argv, const char* name) {
+    for (int i = 1; i < argc; ++i) if (strcmp(argv[i], name) == 0) return true;
+    return false;
+}
+int find_argument(int argc, char** argv, const char* name) {
+    for (int i = 1; i < argc; ++i) if (strcmp(argv[i], name) == 0) return i;
+    return -1;
+}
+bool parse(int argc, char** argv, const char* name, float& v) { int i = find_argument(argc, argv, name); if (i > 0 && i + 1 < argc) { v = (float)atof(argv[i + 1]); return true; } return false; }
+bool parse(int argc, char** argv, const char* name, int& v) { int i = find_argument(argc, argv, name); if (i > 0 && i + 1 < argc) { v = atoi(argv[i + 1]); return true; } return false; }
+bool parse(int argc, char** argv, const char* name, std::string& v) { int i = find_argument(argc, argv, name); if (i > 0 && i + 1 < argc) { v = argv[i + 1]; return true; } return false; }
+
+struct Options {
+    float voxel_resolution = 0.008f, seed_resolution = 0.08f, color_importance = 0.2f, spatial_importance = 0.4f, normal_importance = 1.0f;
+    float thresh = 0; bool rgb = false, cvx = false, ml = false, al = false, eq = false, disable_transform = false, verbose = false, facade = false;
+    float lambda = 0; int bin_num = 0; std::string out;
+};
+
+void usage(const char* a0) {
+    printf("Syntax is: %s {-d <direcory-of-pcd-files> OR -p <pcd-file>} [arguments] \n\n"
+           "\tSUPERVOXEL optional arguments: \n"
+           "\t -v <voxel-resolution>          (default: 0.008) \n\t -s <seed-resolution>           (default: 0.08) \n"
+           "\t -c <color-weight>              (default: 0.2) \n\t -z <spatial-weight>            (default: 0.4) \n"
+           "\t -n <normal-weight>             (default: 1.0) \n\n"
+           "\tSEGMENTATION optional arguments: \n"
+           "\t -t <threshold>                 (required in this build: the automatic threshold needs the evaluation module)\n"
+           "\t --RGB                          (RGB colour distance instead of L*A*B* CIEDE2000) \n"
+           "\t --CVX                          (convexity criterion on the geometric distance) \n"
+           "\t --ML [manual-lambda] *         (Manual Lambda; lambda=0.5 when no value is given) \n"
+           "\t --AL                 *         (Adaptive Lambda, the default) \n"
+           "\t --EQ [bins-number]   *         (Equalization; 500 bins when no value is given -- the reference's text says 200) \n"
+           "\t  * only one of these can be passed at a time \n\n"
+           "\tOTHER optional arguments: \n"
+           "\t --NT                           (disables the single camera transform) \n"
+           "\t --V                            (verbose: prints the merge sequence) \n"
+           "\t -o <file.pcd>                  (writes the labelled voxel cloud) \n"
+           "\t --facade                       (runs through the Clustering / SupervoxelClustering classes) \n"
+           "\t --gpus <N>                     (shards the files of -d over N GPUs) \n", a0);
+}
+
+int process_file(const std::string& file, const Options& o, int device, std::mutex& io) {
+    pcl::PointCloud<pcl::PointXYZRGBL> input;
+    f3ps::loadPCDFile(file, input);                                      // return value ignored, as in the reference (:313)
+    pcl::PointCloud<pcl::PointXYZRGBA>::Ptr cloud(new pcl::PointCloud<pcl::PointXYZRGBA>());
+    for (auto& p : input.points) if (p.z < 0) p.z = std::abs(p.z);       // :317-321
+    pcl::copyPointCloud(input, *cloud);
+    const int merging = o.ml ? F3PS_MANUAL_LAMBDA : (o.eq ? F3PS_EQUALIZATION : F3PS_ADAPTIVE_LAMBDA);
+    const float lam = (o.ml && o.lambda != 0) ? o.lambda : 0.5f;         // --ML 0 means "unset" (:417)
+    const int bins = (o.eq && o.bin_num != 0) ? o.bin_num : 500;         // --EQ 0 means "unset" (:421)
+    auto t0 = std::chrono::steady_clock::now();
+    pcl::PointCloud<pcl::PointXYZL>::Ptr labeled(new pcl::PointCloud<pcl::PointXYZL>());
+    size_t n_sv = 0, n_seg = 0, n_merges = 0; float stage[9] = {0};
+    std::vector<MergeStep> log;
+    if (o.facade) {
+        pcl::SupervoxelClustering<pcl::PointXYZRGBA> super(o.voxel_resolution, o.seed_resolution, device);
+        super.setUseSingleCameraTransform(!o.disable_transform);
+        super.setInputCloud(cloud);
+        super.setColorImportance(o.color_importance); super.setSpatialImportance(o.spatial_importance); super.setNormalImportance(o.normal_importance);
+        std::map<uint32_t, pcl::Supervoxel<pcl::PointXYZRGBA>::Ptr> supervoxel_clusters;
+        super.extract(supervoxel_clusters);
+        std::multimap<uint32_t, uint32_t> label_adjacency;
+        super.getSupervoxelAdjacency(label_adjacency);
+        Clustering segmentation;
+        if (o.rgb) segmentation.set_delta_c(RGB_EUCL);
+        if (o.cvx) segmentation.set_delta_g(CONVEX_NORMALS_DIFF);
+        if (o.ml) { segmentation.set_merging(MANUAL_LAMBDA); if (o.lambda != 0) segmentation.set_lambda(o.lambda); }
+        else if (o.eq) { segmentation.set_merging(EQUALIZATION); if (o.bin_num != 0) segmentation.set_bins_num((short)o.bin_num); }
+        segmentation.set_initialstate(supervoxel_clusters, label_adjacency);
+        segmentation.cluster(o.thresh);
+        labeled = segmentation.get_labeled_cloud();
+        n_sv = supervoxel_clusters.size(); n_seg = segmentation.get_currentstate().first.size();
+        log = segmentation.get_merge_log(); n_merges = log.size();
+    } else {
+        f3ps::Handle h(device);
+        h.check(f3ps_set_vccs_params(h.get(), o.voxel_resolution, o.seed_resolution, o.color_importance, o.spatial_importance,
+                                     o.normal_importance, o.disable_transform ? 0 : 1, 0));
+        h.check(f3ps_set_merge_params(h.get(), o.rgb ? F3PS_RGB_EUCL : F3PS_LAB_CIEDE00, o.cvx ? F3PS_CONVEX_NORMALS_DIFF : F3PS_NORMALS_DIFF, merging, lam, bins));
+        h.check(f3ps_set_input(h.get(), cloud->points.data(), (int64_t)cloud->size(), 32, 0));
+        h.check(f3ps_run(h.get(), o.thresh));
+        f3ps_counts n; h.check(f3ps_get_counts(h.get(), &n));
+        n_sv = n.n_supervoxels; n_seg = n.n_segments; n_merges = n.n_merges;
+        std::vector<float> xyz(3 * (size_t)n.n_labeled); std::vector<uint32_t> lab(n.n_labeled), vox(n.n_labeled);
+        h.check(f3ps_get_labeled_cloud(h.get(), xyz.data(), lab.data(), vox.data(), n.n_labeled));
+        labeled->resize(n.n_labeled);
+        for (int i = 0; i < n.n_labeled; ++i) { auto& p = labeled->points[i]; p.x = xyz[3 * i]; p.y = xyz[3 * i + 1]; p.z = xyz[3 * i + 2]; p.label = lab[i]; }
+        for (int s = 0; s < 9; ++s) f3ps_stage_ms(h.get(), s, &stage[s]);
+        if (o.verbose) {
+            std::vector<uint32_t> ab(2 * n_merges), left(2 * n_merges); std::vector<float> w(n_merges);
+            h.check(f3ps_get_merge_log(h.get(), ab.data(), w.data(), left.data(), (int64_t)n_merges));
+            for (size_t m = 0; m < n_merges; ++m) log.push_back(MergeStep{ab[2 * m], ab[2 * m + 1], w[m], left[2 * m], left[2 * m + 1]});
+        }
+    }
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::lock_guard<std::mutex> g(io);
+    printf("Loading pointcloud from PCD file '%s'...\n", file.c_str());
+    printf("Found %zu supervoxels\n", n_sv);
+    if (o.verbose) for (auto& m : log) printf("left: %de/%dp - w: %f - [%d, %d]...OK\n", m.edges_left, m.regions_left, m.w, m.a, m.b);
+    printf("Clustering complete: %zu points -> %zu merges -> %zu segments over %zu voxels in %.3f ms (GPU %d)\n",
+           cloud->size(), n_merges, n_seg, labeled->size(), ms, device);
+    if (!o.facade) printf("  stage ms: voxelize %.3f neighbors %.3f normals %.3f seeds %.3f expand %.3f graph %.3f merge %.3f total %.3f\n",
+                          stage[0], stage[1], stage[2], stage[3], stage[4], stage[5], stage[6], stage[7]);
+    if (!o.out.empty()) f3ps::savePCDFileASCII(o.out, *labeled);
+    return 0;
+}
+} // namespace
+
+int main(int argc, char** argv) {
+    if (argc < 3) { usage(argv[0]); return 1; }
+    Options o;
+    o.verbose = find_switch(argc, argv, "--V");
+    o.disable_transform = find_switch(argc, argv, "--NT");
+    o.facade = find_switch(argc, argv, "--facade");
+    std::vector<std::string> file_list; std::string path;
+    if (find_switch(argc, argv, "-d")) {
+        parse(argc, argv, "-d", path);
+        if (!std::filesystem::exists(path) || !std::filesystem::is_directory(path)) { fprintf(stderr, "Specified directory doesn't exists or can't be opened\n"); return 1; }
+        for (auto& e : std::filesystem::recursive_directory_iterator(path))
+            if (e.is_regular_file() && e.path().extension() == ".pcd") file_list.push_back(e.path().string());
+        printf("Found %zu files\n", file_list.size());
+    } else if (find_switch(argc, argv, "-p")) { parse(argc, argv, "-p", path); file_list.push_back(path); }
+    else { fprintf(stderr, "No input file or directory specified\n"); return 1; }
+    if (!find_switch(argc, argv, "-t")) {
+        fprintf(stderr, "Automatic threshold selection needs the evaluation module (Testing), which is outside this build's scope: pass -t <threshold>\n");
+        return 1;
+    }
+    parse(argc, argv, "-t", o.thresh);
+    parse(argc, argv, "-v", o.voxel_resolution); parse(argc, argv, "-s", o.seed_resolution);
+    parse(argc, argv, "-c", o.color_importance); parse(argc, argv, "-z", o.spatial_importance); parse(argc, argv, "-n", o.normal_importance);
+    o.rgb = find_switch(argc, argv, "--RGB"); o.cvx = find_switch(argc, argv, "--CVX");
+    o.ml = find_switch(argc, argv, "--ML"); o.al = find_switch(argc, argv, "--AL"); o.eq = find_switch(argc, argv, "--EQ");
+    if (!(o.ml || o.al || o.eq)) o.al = true;
+    else if (!(o.ml ^ o.al ^ o.eq)) { fprintf(stderr, "Only one parameter between --ML --AL and --EQ can be specified at a time\n"); return 1; }   // XOR quirk kept (:280)
+    if (o.ml) parse(argc, argv, "--ML", o.lambda);
+    if (o.eq) parse(argc, argv, "--EQ", o.bin_num);
+    parse(argc, argv, "-o", o.out);
+    int gpus = 1; parse(argc, argv, "--gpus", gpus); gpus = std::max(1, gpus);
+    std::mutex io; int rc = 0;
+    try {
+        if (gpus == 1 || file_list.size() <= 1) { for (auto& f : file_list) rc |= process_file(f, o, 0, io); }
+        else {
+            std::vector<std::thread> th;
+            for (int g = 0; g < gpus; ++g) th.emplace_back([&, g]() { for (size_t i = g; i < file_list.size(); i += gpus) process_file(file_list[i], o, g, io); });
+            for (auto& t : th) t.join();
+        }
+    } catch (const std::exception& e) { fprintf(stderr, "error: %s\n", e.what()); return 2; }
+    return rc;
+}

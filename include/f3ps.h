@@ -145,6 +145,8 @@ int f3ps_get_merge_log(f3ps_ctx* ctx, uint32_t* ab /*[M][2]*/, float* weight /*[
 /* Clustering::get_currentstate(): regions (label, centroid, normal, size) and remaining weighted edges in map order */
 int f3ps_get_state_regions(f3ps_ctx* ctx, uint32_t* label, float* centroid_xyz, float* normal_xyz, int32_t* n_voxels, int64_t capacity);
 int f3ps_get_state_edges(f3ps_ctx* ctx, uint32_t* ab, float* weight, int64_t capacity);
+/* ColorUtilities::mean_color of initial region `rank` (ascending-label order), as the edge weights use it */
+int f3ps_get_region_mean_color(f3ps_ctx* ctx, int32_t rank, float rgb[3]);
 /* Clustering::get_labeled_cloud(): voxel centroids with dense labels 0..K-1 in ascending region label order */
 int f3ps_get_labeled_cloud(f3ps_ctx* ctx, float* xyz /*[n][3]*/, uint32_t* label /*[n]*/, uint32_t* voxel_index /*[n]*/, int64_t capacity);
 /* per-voxel final segment label (dense, 0xffffffff = unowned) resident on the device; for device consumers */

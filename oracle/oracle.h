@@ -55,6 +55,7 @@ struct Params {
     float lambda = 0.5f;             // clustering.cpp:564
     int bins = 500;                  // clustering.cpp:565
     int merge_impl = 0;              // 0 literal std::multimap replay, 1 stamp/prefix "fixed" variant
+    int expand_impl = 0;             // 0 literal sequential helpers, 1 data-parallel fixed-point formulation (what the GPU runs)
     Switches sw;
 };
 
@@ -105,6 +106,7 @@ struct Oracle {
     std::vector<uint32_t> sv_label;       // S surviving labels ascending
     std::vector<float> sv_xyz, sv_rgb, sv_normal; // 3S,3S,4S helper centroids
     std::vector<int> sv_count;
+    std::vector<std::vector<int>> sv_leaves; // per surviving helper: its leaf set in idx order (may hold a phantom leaf)
     std::vector<uint32_t> adj;            // 2*(2E) directed pairs, sorted
     // ---- K6b / K7 ----
     std::map<uint32_t, Region> initial_segments;
@@ -128,6 +130,8 @@ struct Oracle {
     void voxel_normals();       // K3  (A.3)
     void select_seeds();        // K4  (A.4)
     void expand();              // K5  (A.5)
+    void expand_fixed_point();  // K5, restated as the per-voxel fold + steal-table fixed point
+    int sweeps_total = 0;
     void make_supervoxels();    // K6a (A.6)
     void set_initialstate();    // clustering.cpp:605-612 on the VCCS output
     void init_weights();        // clustering.cpp:212-251

@@ -40,6 +40,7 @@ void orc_set_merge_params(void* hv, int color_mode, int geom_mode, int merge_mod
     P.color_mode = color_mode; P.geom_mode = geom_mode; P.merge_mode = merge_mode; P.lambda = lambda; P.bins = bins;
     P.merge_impl = merge_impl;
 }
+void orc_set_expand_impl(void* hv, int impl) { ((Handle*)hv)->O.P.expand_impl = impl; }
 void orc_set_switches(void* hv, int leaf_desc, int keybits_floor, int init_seed_voxel, int shifted_cov) {
     Switches& s = ((Handle*)hv)->O.P.sw;
     s.leaf_order_descending = leaf_desc; s.keybits_floor = keybits_floor;

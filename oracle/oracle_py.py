@@ -54,6 +54,7 @@ def lib():
         L.orc_last_error.argtypes = [C.c_void_p]
         L.orc_set_vccs_params.argtypes = [C.c_void_p] + [C.c_float] * 5 + [C.c_int, C.c_int]
         L.orc_set_merge_params.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
+        L.orc_set_expand_impl.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_switches.argtypes = [C.c_void_p] + [C.c_int] * 4
         L.orc_set_input.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int]
         L.orc_run.argtypes = [C.c_void_p, C.c_int, C.c_float]
@@ -105,6 +106,9 @@ class Oracle:
 
     def set_merge_params(self, color_mode=0, geom_mode=0, merge_mode=1, lam=0.5, bins=500, merge_impl=0):
         self.L.orc_set_merge_params(self.h, color_mode, geom_mode, merge_mode, lam, bins, merge_impl)
+
+    def set_expand_impl(self, impl):
+        self.L.orc_set_expand_impl(self.h, impl)
 
     def set_switches(self, leaf_desc=0, keybits_floor=0, init_seed_voxel=0, shifted_cov=0):
         self.L.orc_set_switches(self.h, leaf_desc, keybits_floor, init_seed_voxel, shifted_cov)

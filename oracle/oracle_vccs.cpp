@@ -404,6 +404,7 @@ struct Helper {
 }
 
 void Oracle::expand() {
+    if (P.expand_impl == 1) { expand_fixed_point(); return; }
     double t0 = now_ms();
     const int V = (int)morton.size();
     labels.assign(V, 0); dist.assign(V, std::numeric_limits<float>::max());
@@ -469,9 +470,10 @@ void Oracle::expand() {
     }
     for (int v = 0; v < V; ++v) labels[v] = owner[v] >= 0 ? H[owner[v]].label : 0;
     // K6a part 1: helper centroids of survivors (makeSupervoxels)
-    sv_label.clear(); sv_xyz.clear(); sv_rgb.clear(); sv_normal.clear(); sv_count.clear();
+    sv_label.clear(); sv_xyz.clear(); sv_rgb.clear(); sv_normal.clear(); sv_count.clear(); sv_leaves.clear();
     for (auto& h : H) {
         if (!h.alive) continue;
+        sv_leaves.push_back(std::vector<int>(h.leaves.begin(), h.leaves.end()));
         // a helper that never ran updateCentroid (max_depth<=1) keeps its initial centroid
         sv_label.push_back(h.label);
         for (int k = 0; k < 3; ++k) { sv_xyz.push_back(h.xyz[k]); sv_rgb.push_back(h.rgb[k]); }
@@ -481,31 +483,150 @@ void Oracle::expand() {
     stage_ms[4] = now_ms() - t0;
 }
 
-// K6a: makeSupervoxels + getSupervoxelAdjacency (A.6)
-void Oracle::make_supervoxels() {
+// ---------------------------------------------------------------------------------
+// K5 restated as a data-parallel fixed point -- the formulation the CUDA kernels run,
+// kept here so that its equivalence with the literal sequential form above is testable without a GPU.
+//   per round: start-of-round owner0/D0; ST[u] = label of the first helper that steals u this round.
+//   sweep: every voxel n folds, in ascending label order, the helpers that hold a leaf adjacent to n at
+//   their turn: regular leaves u != n with owner0[u] == h and ST[u] > h, plus "phantom" leaves.
+//   Phantom leaf: two seed cells elected the same voxel u; createSupervoxelHelpers puts u into both
+//   helpers' leaf sets but only the later helper owns it.  The earlier helper keeps expanding from u
+//   (also onto u itself), counts u in its centroid, and lists u in its voxels_, until it steals u.
+void Oracle::expand_fixed_point() {
     double t0 = now_ms();
     const int V = (int)morton.size();
+    const int S0 = (int)seeds.size();
+    const uint32_t NONE = 0xffffffffu;
+    labels.assign(V, 0); dist.assign(V, std::numeric_limits<float>::max());
+    steals_per_round.clear(); sweeps_total = 0;
+    std::vector<uint32_t> owner0(V, 0), owner1(V, 0), phantom(V, 0);     // phantom[u] = label holding u without owning it
+    std::vector<float> D0(V, std::numeric_limits<float>::max()), D1(V);
+    std::vector<int> phantom_leaf(S0 + 1, -1);                           // per label
+    struct Cen { float xyz[3] = {0, 0, 0}, rgb[3] = {0, 0, 0}, nrm[4] = {0, 0, 0, 0}; bool alive = true; };
+    std::vector<Cen> cen(S0 + 1);
+    long triple = 0;
+    for (int i = 0; i < S0; ++i) {                                       // createSupervoxelHelpers: last helper owns
+        const int u = seeds[i]; const uint32_t l = (uint32_t)i + 1;
+        if (owner0[u]) { if (phantom[u]) ++triple; phantom[u] = owner0[u]; phantom_leaf[owner0[u]] = u; }
+        owner0[u] = l;
+    }
+    if (triple) throw std::runtime_error("oracle(fixed point): three helpers on one seed voxel is not modelled");
+    auto vdist = [&](const Cen& h, int u) {
+        float dx[3], dc[3];
+        for (int k = 0; k < 3; ++k) { dx[k] = h.xyz[k] - vxyz[3 * u + k]; dc[k] = h.rgb[k] - vrgb[3 * u + k]; }
+        float spatial = std::sqrt(dot3(dx, dx)) / P.seed_res;
+        float color = std::sqrt(dot3(dc, dc)) / 255.0f;
+        const float* m = &normals[(size_t)u * 4];
+        float cosang = 1.0f - std::abs(sum4(h.nrm[0] * m[0], h.nrm[1] * m[1], h.nrm[2] * m[2], h.nrm[3] * m[3]));
+        return cosang * P.normal_imp + color * P.color_imp + spatial * P.spatial_imp;
+    };
+    auto fold_centroids = [&](const std::vector<uint32_t>& owner) {
+        // voxels grouped by owner in idx order (stable), phantom leaf merged in at its idx position
+        std::vector<std::vector<int>> lists(S0 + 1);
+        for (int v = 0; v < V; ++v) if (owner[v]) lists[owner[v]].push_back(v);
+        for (int l = 1; l <= S0; ++l) {
+            Cen& c = cen[l];
+            if (!c.alive) continue;
+            std::vector<int>& L = lists[l];
+            if (phantom_leaf[l] >= 0) L.insert(std::lower_bound(L.begin(), L.end(), phantom_leaf[l]), phantom_leaf[l]);
+            if (L.empty()) { c.alive = false; continue; }
+            float n[4] = {0, 0, 0, 0}, x[3] = {0, 0, 0}, col[3] = {0, 0, 0};
+            for (int u : L) {
+                for (int k = 0; k < 4; ++k) n[k] += normals[(size_t)u * 4 + k];
+                for (int k = 0; k < 3; ++k) { x[k] += vxyz[3 * u + k]; col[k] += vrgb[3 * u + k]; }
+            }
+            float z = sum4(n[0] * n[0], n[1] * n[1], n[2] * n[2], n[3] * n[3]);
+            if (z > 0.0f) { float s = std::sqrt(z); for (int k = 0; k < 4; ++k) n[k] /= s; }
+            float cnt = (float)L.size();
+            for (int k = 0; k < 3; ++k) { c.xyz[k] = x[k] / cnt; c.rgb[k] = col[k] / cnt; }
+            for (int k = 0; k < 4; ++k) c.nrm[k] = n[k];
+        }
+    };
+    if (P.sw.init_centroid_seed_voxel) fold_centroids(owner0);
+    const int max_depth = (int)(1.8f * P.seed_res / P.voxel_res);
+    rounds = 0;
+    std::vector<uint32_t> st_in(V), st_out(V);
+    for (int it = 1; it < max_depth; ++it) {
+        std::fill(st_in.begin(), st_in.end(), NONE);
+        int sweeps = 0;
+        while (true) {
+            bool changed = false;
+            for (int n = 0; n < V; ++n) {
+                uint32_t cur = owner0[n]; float D = D0[n];
+                std::vector<uint32_t> cand;
+                for (int a = 0; a < nbr_count[n]; ++a) {
+                    const int u = nbr[(size_t)n * 27 + a];
+                    if (u != n) { const uint32_t h = owner0[u]; if (h && st_in[u] > h) cand.push_back(h); }
+                    if (phantom[u]) cand.push_back(phantom[u]);            // phantom leaves support every neighbour, u itself included
+                }
+                std::sort(cand.begin(), cand.end());
+                cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+                uint32_t first = NONE;
+                for (uint32_t h : cand) {
+                    if (h == cur || !cen[h].alive) continue;
+                    const float d = vdist(cen[h], n);
+                    if (d < D) { if (first == NONE) first = h; D = d; cur = h; }
+                }
+                owner1[n] = cur; D1[n] = D; st_out[n] = first;
+                if (first != st_in[n]) changed = true;
+            }
+            ++sweeps;
+            st_in.swap(st_out);
+            if (!changed) break;
+            if (sweeps > 64) throw std::runtime_error("oracle(fixed point): no convergence");
+        }
+        sweeps_total += sweeps;
+        int steals = 0;
+        for (int v = 0; v < V; ++v) if (owner0[v] && owner1[v] != owner0[v]) ++steals;
+        steals_per_round.push_back(steals);
+        owner0 = owner1; D0 = D1;
+        for (int v = 0; v < V; ++v) if (phantom[v] && owner0[v] == phantom[v]) { phantom_leaf[phantom[v]] = -1; phantom[v] = 0; }
+        fold_centroids(owner0);
+        ++rounds;
+    }
+    for (int v = 0; v < V; ++v) { labels[v] = owner0[v]; dist[v] = D0[v]; }
+    sv_label.clear(); sv_xyz.clear(); sv_rgb.clear(); sv_normal.clear(); sv_count.clear(); sv_leaves.clear();
+    std::vector<int> counts(S0 + 1, 0);
+    for (int v = 0; v < V; ++v) counts[owner0[v]]++;
+    std::vector<std::vector<int>> final_lists(S0 + 1);
+    for (int v = 0; v < V; ++v) if (owner0[v]) final_lists[owner0[v]].push_back(v);
+    for (int l = 1; l <= S0; ++l) if (phantom_leaf[l] >= 0) {
+        std::vector<int>& L = final_lists[l];
+        L.insert(std::lower_bound(L.begin(), L.end(), phantom_leaf[l]), phantom_leaf[l]);
+    }
+    for (int l = 1; l <= S0; ++l) {
+        if (rounds == 0) { if (!counts[l] && phantom_leaf[l] < 0) continue; }
+        else if (!cen[l].alive) continue;
+        sv_label.push_back((uint32_t)l);
+        for (int k = 0; k < 3; ++k) { sv_xyz.push_back(cen[l].xyz[k]); sv_rgb.push_back(cen[l].rgb[k]); }
+        for (int k = 0; k < 4; ++k) sv_normal.push_back(cen[l].nrm[k]);
+        sv_count.push_back(counts[l] + (phantom_leaf[l] >= 0 ? 1 : 0));
+        sv_leaves.push_back(final_lists[l]);
+    }
+    stage_ms[4] = now_ms() - t0;
+}
+
+// K6a: makeSupervoxels + getSupervoxelAdjacency (A.6): both walk the helpers' LEAF SETS (getVoxels,
+// getNeighborLabels), so a phantom leaf (see expand_fixed_point) is listed by its holder as well.
+void Oracle::make_supervoxels() {
+    double t0 = now_ms();
     initial_segments.clear(); adj.clear();
-    std::unordered_map<uint32_t, size_t> slot;
+    std::set<std::pair<uint32_t, uint32_t>> pairs;
     for (size_t s = 0; s < sv_label.size(); ++s) {
         Region r;
         r.cx = sv_xyz[3 * s]; r.cy = sv_xyz[3 * s + 1]; r.cz = sv_xyz[3 * s + 2];
         r.nx = sv_normal[4 * s]; r.ny = sv_normal[4 * s + 1]; r.nz = sv_normal[4 * s + 2];
         r.curvature = 0.0f;
-        initial_segments[sv_label[s]] = r; slot[sv_label[s]] = s;
+        r.voxels = sv_leaves[s];
+        const uint32_t l = sv_label[s];
+        for (int v : r.voxels)
+            for (int a = 0; a < nbr_count[v]; ++a) {
+                uint32_t m = labels[nbr[(size_t)v * 27 + a]];
+                if (m && m != l) pairs.insert({l, m});
+            }
+        initial_segments[l] = r;
     }
-    for (int v = 0; v < V; ++v) if (labels[v]) {
-        auto it = initial_segments.find(labels[v]);
-        if (it != initial_segments.end()) it->second.voxels.push_back(v);   // idx order
-    }
-    std::set<std::pair<uint32_t, uint32_t>> pairs;
-    for (int v = 0; v < V; ++v) {
-        uint32_t l = labels[v]; if (!l) continue;
-        for (int a = 0; a < nbr_count[v]; ++a) {
-            uint32_t m = labels[nbr[(size_t)v * 27 + a]];
-            if (m && m != l) pairs.insert({l, m});
-        }
-    }
+    // adjacency is symmetric in PCL only through both helpers' walks; a phantom leaf adds (holder -> owner) one way
     for (auto& p : pairs) { adj.push_back(p.first); adj.push_back(p.second); }
     stage_ms[5] = now_ms() - t0;
 }

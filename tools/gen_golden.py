@@ -9,6 +9,15 @@ sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.joi
 import oracle_py
 from f3ps import synth
 
+def digest(a):
+    """sha256 of an array with every NaN replaced by one canonical NaN (payload/sign of a NaN is not part of parity)."""
+    a = np.ascontiguousarray(a)
+    if a.dtype.kind == "f":
+        a = np.where(np.isnan(a), np.float32(np.nan), a).astype(np.float32)
+        a = a.view(np.uint32).copy()
+        a[a == 0x80000000] = 0          # -0.0 == +0.0
+    return hashlib.sha256(a.tobytes()).digest()
+
 def bits(a): return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 def main():
@@ -21,7 +30,7 @@ def main():
             for n in ("keys", "voxel_count", "nbr_count", "seeds", "labels", "sv_label", "sv_count"):
                 out[n] = o.array(n)
             for n in ("voxel_xyz", "voxel_rgb", "normals", "nbr", "dist"):       # digests of the big arrays
-                out[n + "_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(o.array(n)).tobytes()).digest(), np.uint8)
+                out[n + "_sha256"] = np.frombuffer(digest(o.array(n)), np.uint8)
         out[tag + "_edges_ab"] = o.array("edges_ab"); out[tag + "_edges_w_bits"] = bits(o.array("edges_w"))
         out[tag + "_merges_ab"] = o.array("merges_ab"); out[tag + "_merges_w_bits"] = bits(o.array("merges_w"))
         out[tag + "_out_label"] = o.array("out_label"); out[tag + "_out_voxel"] = o.array("out_voxel")
