@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "radix_sort.cuh"
 #include "kernels_vccs.cuh"
+#include "kernels_expand.cuh"
 #include "kernels_graph.cuh"
 
 #define F3PS_MERGE_ERR_TOUCHED 4u
@@ -32,10 +33,10 @@ struct DevBuf {
 struct DevScalars {
     FrameParams fp;
     unsigned n_valid, n_voxels, n_cells, n_seeds;
-    unsigned n_sv, n_edges, n_out, edge_overflow;
+    unsigned pad_sv, n_edges, n_out, edge_overflow;
     unsigned bad_bin, nan_weights_init, pad0, pad1;
     float lambda; float padf[3];
-    SweepFlags flags;
+    ExpandCtl xctl;
     MergeCtl mctl;
     SeedBox sb;
 };
@@ -79,7 +80,10 @@ struct f3ps_ctx {
     // K4
     f3ps::DevBuf cell_code, cell_code_b, cell_vox, cell_vox_b, vox_cell, cell_start, cell_codes, cell_nn, cell_keep, seeds;
     // K5
-    f3ps::DevBuf owner0, owner1, dist0, dist1, st0, st1, cen_xyz, cen_rgb, cen_nrm, lab_keys_a, lab_keys_b, lab_vals_a, lab_vals_b, seg_start, seg_end;
+    f3ps::DevBuf owner0, dist0;                       // results: clean label / stored distance per voxel
+    f3ps::DevBuf own_a, own_b, dst_a, dst_b, st0, st1, phantom, phantom_leaf, lab_count, lab_count2, lab_fill;
+    f3ps::DevBuf cen_xyz, cen_rgb, cen_nrm, lab_keys_a, lab_keys_b, lab_vals_a, lab_vals_b, seg_start, seg_end;
+    int expand_blocks_per_sm = 0, sm_count = 0;
     unsigned* sorted_label = nullptr; unsigned* sorted_vox = nullptr;
     // K6
     f3ps::DevBuf sv_label, rank_of_label, run_start, run_end, pos_run, edge_set, edge_keys_a, edge_keys_b, edge_vals_a, edge_vals_b;

@@ -99,9 +99,6 @@ int run_compact(f3ps_ctx* ctx, Op op, const unsigned* n_ptr, int64_t n_cap, unsi
     return F3PS_OK;
 }
 
-__global__ void fill_float_kernel(float* p, float v, unsigned n) {
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
-}
 __global__ void iota_kernel(unsigned* p, unsigned n) {
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
 }
@@ -237,7 +234,8 @@ void f3ps_destroy(f3ps_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->in_buf, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->starts, &ctx->point_voxel, &ctx->sort_scratch,
         &ctx->compact_scratch, &ctx->vox_xyz, &ctx->vox_rgb, &ctx->vox_key, &ctx->hash_slots, &ctx->hash_vals, &ctx->nbr_row, &ctx->nbr_col,
         &ctx->vox_normal, &ctx->vox_curv, &ctx->cell_code, &ctx->cell_code_b, &ctx->cell_vox, &ctx->cell_vox_b, &ctx->vox_cell, &ctx->cell_start,
-        &ctx->cell_codes, &ctx->cell_nn, &ctx->cell_keep, &ctx->seeds, &ctx->owner0, &ctx->owner1, &ctx->dist0, &ctx->dist1, &ctx->st0, &ctx->st1,
+        &ctx->cell_codes, &ctx->cell_nn, &ctx->cell_keep, &ctx->seeds, &ctx->owner0, &ctx->dist0, &ctx->own_a, &ctx->own_b, &ctx->dst_a, &ctx->dst_b, &ctx->st0, &ctx->st1, &ctx->phantom, &ctx->phantom_leaf,
+        &ctx->lab_count, &ctx->lab_count2, &ctx->lab_fill, &ctx->lab_keys_a,
         &ctx->cen_xyz, &ctx->cen_rgb, &ctx->cen_nrm, &ctx->lab_keys_b, &ctx->lab_vals_a, &ctx->lab_vals_b, &ctx->seg_start, &ctx->seg_end,
         &ctx->sv_label, &ctx->rank_of_label, &ctx->run_start, &ctx->run_end, &ctx->pos_run, &ctx->edge_set, &ctx->edge_keys_a, &ctx->edge_keys_b,
         &ctx->edge_vals_a, &ctx->edge_vals_b, &ctx->dbits_a, &ctx->dbits_b, &ctx->dbits_c, &ctx->dbits_d, &ctx->cdf_c, &ctx->cdf_g, &ctx->cdf_hist,
@@ -404,89 +402,58 @@ int f3ps_seeds(f3ps_ctx* ctx) {
 }
 
 // ---- K5 -------------------------------------------------------------------------------------------
-// voxels grouped by owner label (stable => idx order inside a label) + per-label bounds
-static int group_by_label(f3ps_ctx* ctx, const unsigned* owner) {
-    const unsigned V = ctx->V; const size_t Sc = (size_t)ctx->S0 + 2;
-    unsigned* sk; unsigned* sv;
-    int rc = sort_pairs<unsigned>(ctx, owner, nullptr, ctx->lab_keys_a.as<unsigned>(), ctx->lab_vals_a.as<unsigned>(), ctx->lab_keys_b.as<unsigned>(),
-                                  ctx->lab_vals_b.as<unsigned>(), SC(n_voxels), V, bits_for(ctx->S0), &sk, &sv);
-    if (rc) return rc;
-    F3PS_CUDA_OK(cudaMemsetAsync(ctx->seg_start.p, 0, Sc * 4, ctx->stream));
-    F3PS_CUDA_OK(cudaMemsetAsync(ctx->seg_end.p, 0, Sc * 4, ctx->stream));
-    LAUNCH(ctx, label_bounds_kernel, grid_for(V, 256), 256, 0, sk, SC(n_voxels), ctx->seg_start.as<unsigned>(), ctx->seg_end.as<unsigned>());
-    ctx->sorted_label = sk; ctx->sorted_vox = sv;
-    return F3PS_OK;
-}
-
-static int expand_once(f3ps_ctx* ctx, int max_sweeps) {
-    const unsigned V = ctx->V, S0 = ctx->S0; const size_t Vc = std::max(1u, V);
-    DevBuf* bv[] = {&ctx->owner0, &ctx->owner1, &ctx->dist0, &ctx->dist1, &ctx->st0, &ctx->st1, &ctx->lab_keys_a, &ctx->lab_keys_b, &ctx->lab_vals_a, &ctx->lab_vals_b};
-    for (DevBuf* b : bv) F3PS_CUDA_OK(b->ensure(Vc * 4));
-    const size_t Sc = (size_t)S0 + 2;
-    F3PS_CUDA_OK(ctx->cen_xyz.ensure(Sc * 16)); F3PS_CUDA_OK(ctx->cen_rgb.ensure(Sc * 16)); F3PS_CUDA_OK(ctx->cen_nrm.ensure(Sc * 16));
-    F3PS_CUDA_OK(ctx->seg_start.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->seg_end.ensure(Sc * 4));
-    Centroids cen{ctx->cen_xyz.as<float4>(), ctx->cen_rgb.as<float4>(), ctx->cen_nrm.as<float4>()};
-    F3PS_CUDA_OK(cudaMemsetAsync(SC(flags), 0, sizeof(SweepFlags), ctx->stream));
-    F3PS_CUDA_OK(cudaMemsetAsync(ctx->owner0.p, 0, Vc * 4, ctx->stream));
-    F3PS_CUDA_OK(cudaMemsetAsync(ctx->cen_xyz.p, 0, Sc * 16, ctx->stream));
-    F3PS_CUDA_OK(cudaMemsetAsync(ctx->cen_rgb.p, 0, Sc * 16, ctx->stream));
-    F3PS_CUDA_OK(cudaMemsetAsync(ctx->cen_nrm.p, 0, Sc * 16, ctx->stream));
-    const int max_depth = (int)(1.8f * ctx->vp.seed_res / ctx->vp.voxel_res);     // SupervoxelClustering::extract
-    ctx->rounds = std::max(0, max_depth - 1);
-    if (!V) return F3PS_OK;
-    LAUNCH(ctx, fill_float_kernel, grid_for(V, 256), 256, 0, ctx->dist0.as<float>(), FLT_MAX, V);
-    if (S0) {
-        F3PS_CUDA_OK(cudaMemsetAsync(ctx->st1.p, 0, Vc * 4, ctx->stream));      // claim counters
-        LAUNCH(ctx, expand_init_kernel, grid_for(S0, 256), 256, 0, ctx->seeds.as<int>(), SC(n_seeds), ctx->owner0.as<unsigned>(),
-               ctx->st1.as<unsigned>(), cen);
-        LAUNCH(ctx, expand_init_shared_kernel, grid_for(S0, 256), 256, 0, ctx->seeds.as<int>(), SC(n_seeds), ctx->owner0.as<unsigned>(),
-               ctx->st1.as<unsigned>(), ctx->dist0.as<float>(), ctx->vox_xyz.as<float4>(), ctx->vox_rgb.as<float4>(), ctx->vox_normal.as<float4>(), ctx->vp);
-    }
-    unsigned* own[2] = {ctx->owner0.as<unsigned>(), ctx->owner1.as<unsigned>()};
-    float* dst[2] = {ctx->dist0.as<float>(), ctx->dist1.as<float>()};
-    unsigned* st[2] = {ctx->st0.as<unsigned>(), ctx->st1.as<unsigned>()};
-    int cur = 0;
-    const int sweep_grid = grid_for(V, 256);
-    for (int round = 0; round < ctx->rounds && S0; ++round) {
-        F3PS_CUDA_OK(cudaMemsetAsync(st[0], 0xff, (size_t)V * 4, ctx->stream));
-        for (int s = 0; s < max_sweeps; ++s)
-            LAUNCH(ctx, expand_sweep_kernel, sweep_grid, 256, 0, s, ctx->nbr_col.as<int>(), V, SC(n_voxels), own[cur], dst[cur], st[s & 1], st[(s + 1) & 1],
-                   own[cur ^ 1], dst[cur ^ 1], ctx->vox_xyz.as<float4>(), ctx->vox_rgb.as<float4>(), ctx->vox_normal.as<float4>(),
-                   ctx->nbr_row.as<int>(), cen, ctx->vp, SC(flags));
-        LAUNCH(ctx, expand_round_end_kernel, 1, 1, 0, SC(flags), max_sweeps);
-        cur ^= 1;
-        // SupervoxelHelper::updateCentroid: ordered sums per helper over its voxels in idx order
-        int rc = group_by_label(ctx, own[cur]); if (rc) return rc;
-        LAUNCH(ctx, centroid_fold_kernel, grid_for((int64_t)S0 * 32, 256), 256, 0, ctx->sorted_vox, ctx->seg_start.as<unsigned>(),
-               ctx->seg_end.as<unsigned>(), SC(n_seeds), ctx->vox_xyz.as<float4>(), ctx->vox_rgb.as<float4>(), ctx->vox_normal.as<float4>(), cen);
-    }
-    if (cur == 1) {                                            // canonical result arrays: owner0 / dist0
-        F3PS_CUDA_OK(cudaMemcpyAsync(own[0], own[1], (size_t)V * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        F3PS_CUDA_OK(cudaMemcpyAsync(dst[0], dst[1], (size_t)V * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-    if (ctx->rounds == 0 || !S0) { int rc = group_by_label(ctx, own[0]); if (rc) return rc; }
-    return F3PS_OK;
-}
-
+// One cooperative launch runs createSupervoxelHelpers, every expansion round and makeSupervoxels' lists
+// (kernels_expand.cuh); the host only learns the number of surviving helpers afterwards.
 int f3ps_expand(f3ps_ctx* ctx) {
     if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
     int rc = need(ctx, P_SEEDS, "f3ps_expand"); if (rc) return rc;
     cudaSetDevice(ctx->device);
-    for (int max_sweeps = 6;; max_sweeps = kMaxSweeps) {
-        rc = expand_once(ctx, max_sweeps); if (rc) return rc;
-        // alive helpers -> ranks (makeSupervoxels); the same readback verifies the fixed point
-        const size_t Sc = (size_t)ctx->S0 + 2;
-        F3PS_CUDA_OK(ctx->sv_label.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->rank_of_label.ensure(Sc * 4));
-        F3PS_CUDA_OK(cudaMemsetAsync(SC(n_sv), 0, 4, ctx->stream));
-        if (ctx->S0) {
-            AliveOp aop{ctx->seg_start.as<unsigned>(), ctx->seg_end.as<unsigned>(), ctx->sv_label.as<unsigned>(), ctx->rank_of_label.as<unsigned>()};
-            rc = run_compact(ctx, aop, nullptr, ctx->S0, SC(n_sv)); if (rc) return rc;
+    const unsigned V = ctx->V, S0 = ctx->S0; const size_t Vc = std::max(1u, V), Sc = (size_t)S0 + 2, Lc = Vc + Sc;
+    DevBuf* bv[] = {&ctx->own_a, &ctx->own_b, &ctx->dst_a, &ctx->dst_b, &ctx->st0, &ctx->st1, &ctx->phantom, &ctx->owner0, &ctx->dist0};
+    for (DevBuf* b : bv) F3PS_CUDA_OK(b->ensure(Vc * 4));
+    DevBuf* bl[] = {&ctx->lab_keys_a, &ctx->lab_vals_a, &ctx->lab_vals_b};
+    for (DevBuf* b : bl) F3PS_CUDA_OK(b->ensure(Lc * 4));
+    DevBuf* bs[] = {&ctx->seg_start, &ctx->seg_end, &ctx->lab_count, &ctx->lab_count2, &ctx->lab_fill, &ctx->phantom_leaf, &ctx->sv_label, &ctx->rank_of_label};
+    for (DevBuf* b : bs) F3PS_CUDA_OK(b->ensure(Sc * 4));
+    F3PS_CUDA_OK(ctx->cen_xyz.ensure(Sc * 16)); F3PS_CUDA_OK(ctx->cen_rgb.ensure(Sc * 16)); F3PS_CUDA_OK(ctx->cen_nrm.ensure(Sc * 16));
+    const int max_depth = (int)(1.8f * ctx->vp.seed_res / ctx->vp.voxel_res);     // SupervoxelClustering::extract
+    ctx->rounds = std::max(0, max_depth - 1);
+    F3PS_CUDA_OK(cudaMemsetAsync(SC(xctl), 0, sizeof(ExpandCtl), ctx->stream));
+    ctx->sorted_label = ctx->lab_keys_a.as<unsigned>(); ctx->sorted_vox = ctx->lab_vals_b.as<unsigned>();
+    if (V) {
+        ExpandArgs A;
+        A.nbr_col = ctx->nbr_col.as<int>(); A.nbr_row = ctx->nbr_row.as<int>(); A.V_cap = V;
+        A.vox_xyz = ctx->vox_xyz.as<float4>(); A.vox_rgb = ctx->vox_rgb.as<float4>(); A.vox_nrm = ctx->vox_normal.as<float4>();
+        A.seeds = ctx->seeds.as<int>(); A.V = V; A.S0 = S0; A.rounds = ctx->rounds; A.P = ctx->vp;
+        A.owner[0] = ctx->own_a.as<unsigned>(); A.owner[1] = ctx->own_b.as<unsigned>();
+        A.dist[0] = ctx->dst_a.as<float>(); A.dist[1] = ctx->dst_b.as<float>();
+        A.st[0] = ctx->st0.as<unsigned>(); A.st[1] = ctx->st1.as<unsigned>();
+        A.phantom = ctx->phantom.as<unsigned>(); A.phantom_leaf = ctx->phantom_leaf.as<int>();
+        A.cen = Centroids{ctx->cen_xyz.as<float4>(), ctx->cen_rgb.as<float4>(), ctx->cen_nrm.as<float4>()};
+        A.count[0] = ctx->lab_count.as<unsigned>(); A.count[1] = ctx->lab_count2.as<unsigned>(); A.fill = ctx->lab_fill.as<unsigned>(); A.off = ctx->seg_start.as<unsigned>();
+        A.list_raw = ctx->lab_vals_a.as<unsigned>(); A.list_sorted = ctx->lab_vals_b.as<unsigned>(); A.pos_label = ctx->lab_keys_a.as<unsigned>();
+        A.labels_out = ctx->owner0.as<unsigned>(); A.dist_out = ctx->dist0.as<float>();
+        A.seg_end = ctx->seg_end.as<unsigned>(); A.sv_label = ctx->sv_label.as<unsigned>(); A.rank_of_label = ctx->rank_of_label.as<unsigned>();
+        A.ctl = SC(xctl);
+        if (!ctx->expand_blocks_per_sm) {
+            int nb = 0;
+            F3PS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, expand_persistent_kernel, kExpandThreads, 0));
+            int sms = 0;
+            F3PS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+            ctx->expand_blocks_per_sm = std::max(1, nb); ctx->sm_count = std::max(1, sms);
         }
-        rc = pull_scalars(ctx); if (rc) return rc;
-        if (!ctx->h_sc->flags.not_converged) break;
-        if (max_sweeps == kMaxSweeps) return ctx_fail(ctx, F3PS_ERR_NOT_CONVERGED, "expansion fixed point not reached within 16 sweeps");
+        const int64_t want = ((int64_t)V + kExpandThreads - 1) / kExpandThreads;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)std::min(ctx->expand_blocks_per_sm, 2) * ctx->sm_count));
+        void* args[] = {&A};
+        F3PS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)expand_persistent_kernel, dim3(grid), dim3(kExpandThreads), args, 0, ctx->stream));
+        ctx->launches++;
     }
-    ctx->S = ctx->h_sc->n_sv;
+    rc = pull_scalars(ctx); if (rc) return rc;
+    const ExpandCtl& x = ctx->h_sc->xctl;
+    if (x.error & EXPAND_ERR_TRIPLE) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "three seed cells elected the same voxel (not modelled)");
+    if (x.error & EXPAND_ERR_CAND) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "more than 32 candidate helpers around one voxel");
+    if (x.error & EXPAND_ERR_SWEEPS) return ctx_fail(ctx, F3PS_ERR_NOT_CONVERGED, "expansion fixed point not reached within 32 sweeps");
+    ctx->S = V ? x.n_sv : 0; ctx->n_pos = V ? x.n_pos : 0;
     ctx->progress = P_EXPANDED;
     return mark(ctx, 5);
 }
@@ -540,9 +507,10 @@ int f3ps_graph(f3ps_ctx* ctx) {
     const unsigned V = ctx->V, S = ctx->S; const size_t Sc = std::max(1u, S), Vc = std::max(1u, V);
     F3PS_CUDA_OK(ctx->reg_init.ensure(region_bytes(Sc))); F3PS_CUDA_OK(ctx->reg_work.ensure(region_bytes(Sc)));
     ctx->R0 = carve_regions(ctx->reg_init.p, Sc); ctx->R1 = carve_regions(ctx->reg_work.p, Sc);
-    F3PS_CUDA_OK(ctx->run_start.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->run_end.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->pos_run.ensure(Vc * 4));
+    F3PS_CUDA_OK(ctx->run_start.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->run_end.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->pos_run.ensure((Vc + Sc) * 4));
     Centroids cen{ctx->cen_xyz.as<float4>(), ctx->cen_rgb.as<float4>(), ctx->cen_nrm.as<float4>()};
-    ctx->order = ctx->sorted_vox; ctx->gxyz = ctx->vox_xyz.as<float4>(); ctx->n_pos = V;
+    ctx->order = ctx->sorted_vox; ctx->gxyz = ctx->vox_xyz.as<float4>();
+    const unsigned P = ctx->n_pos;
     const unsigned set_cap = next_pow2(std::max(1024u, 32 * S));
     ctx->edge_set_mask = set_cap - 1; ctx->edge_kb = bits_for(std::max(1u, S));
     F3PS_CUDA_OK(ctx->edge_set.ensure((size_t)set_cap * 8));
@@ -554,12 +522,12 @@ int f3ps_graph(f3ps_ctx* ctx) {
     F3PS_CUDA_OK(cudaMemsetAsync(SC(n_edges), 0, 4, ctx->stream));
     F3PS_CUDA_OK(cudaMemsetAsync(SC(edge_overflow), 0, 16, ctx->stream));   // edge_overflow, bad_bin, nan_weights_init, pad
     if (V && S) {
-        LAUNCH(ctx, pos_run_kernel, grid_for(V, 256), 256, 0, ctx->sorted_label, ctx->rank_of_label.as<unsigned>(), V, ctx->pos_run.as<unsigned>());
-        LAUNCH(ctx, region_init_kernel, grid_for((int64_t)S * 32, 256), 256, 0, ctx->sv_label.as<unsigned>(), SC(n_sv), ctx->seg_start.as<unsigned>(),
+        LAUNCH(ctx, pos_run_kernel, grid_for(P, 256), 256, 0, ctx->sorted_label, ctx->rank_of_label.as<unsigned>(), P, ctx->pos_run.as<unsigned>());
+        LAUNCH(ctx, region_init_kernel, grid_for((int64_t)S * 32, 256), 256, 0, ctx->sv_label.as<unsigned>(), SC(xctl.n_sv), ctx->seg_start.as<unsigned>(),
                ctx->seg_end.as<unsigned>(), ctx->sorted_vox, ctx->vox_xyz.as<float4>(), cen, ctx->R0, ctx->run_start.as<unsigned>(),
                ctx->run_end.as<unsigned>());
-        LAUNCH(ctx, edge_collect_kernel, grid_for(V, 256), 256, 0, ctx->nbr_col.as<int>(), V, ctx->nbr_row.as<int>(), SC(n_voxels), ctx->owner0.as<unsigned>(),
-               ctx->rank_of_label.as<unsigned>(), ctx->edge_set.as<unsigned long long>(), ctx->edge_set_mask, SC(edge_overflow));
+        LAUNCH(ctx, edge_collect_kernel, grid_for(P, 256), 256, 0, ctx->nbr_col.as<int>(), V, ctx->nbr_row.as<int>(), P, ctx->sorted_label, ctx->sorted_vox,
+               ctx->owner0.as<unsigned>(), ctx->rank_of_label.as<unsigned>(), ctx->edge_set.as<unsigned long long>(), ctx->edge_set_mask, SC(edge_overflow));
         EdgeSlotCompactOp sop{ctx->edge_set.as<unsigned long long>(), ctx->edge_keys_a.as<unsigned long long>(), ctx->edge_vals_a.as<unsigned>(), ctx->edge_kb};
         rc = run_compact(ctx, sop, nullptr, set_cap, SC(n_edges)); if (rc) return rc;
         unsigned long long* sk; unsigned* sv;
@@ -638,7 +606,7 @@ int f3ps_set_graph(f3ps_ctx* ctx, int64_t n_voxels, const float* voxel_xyz, cons
     F3PS_CUDA_OK(up(ctx->R0.centroid, h_cen.data(), (size_t)S * 16)); F3PS_CUDA_OK(up(ctx->R0.normal, h_nrm.data(), (size_t)S * 16));
     F3PS_CUDA_OK(up(ctx->edge_keys_a.p, h_keys.data(), (size_t)E * 8));
     DevScalars init; memset(&init, 0, sizeof init);
-    init.n_voxels = V; init.n_sv = S; init.n_edges = E;
+    init.n_voxels = V; init.xctl.n_sv = S; init.n_edges = E;
     *ctx->h_sc = init;
     F3PS_CUDA_OK(cudaMemcpyAsync(ctx->d_sc, ctx->h_sc, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
     if (V) LAUNCH(ctx, iota_kernel, grid_for(V, 256), 256, 0, ctx->lab_vals_a.as<unsigned>(), V);
@@ -680,14 +648,15 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
     if (S) {
         EdgeParams ep = edge_params(ctx);
         rc = mark(ctx, 9); if (rc) return rc;
-        LAUNCH(ctx, merge_kernel, 1, kMergeThreads, 0, ctx->R1, ctx->E1, SC(n_edges), SC(n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
+        LAUNCH(ctx, merge_kernel, 1, kMergeThreads, 0, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
                ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl));
         rc = mark(ctx, 10); if (rc) return rc;
-        LAUNCH(ctx, dense_label_kernel, 1, 1, 0, ctx->R1, SC(n_sv), ctx->run_start.as<unsigned>(), ctx->run_end.as<unsigned>(), ctx->run_out_off.as<unsigned>(),
+        LAUNCH(ctx, dense_label_kernel, 1, 1, 0, ctx->R1, SC(xctl.n_sv), ctx->run_start.as<unsigned>(), ctx->run_end.as<unsigned>(), ctx->run_out_off.as<unsigned>(),
                ctx->run_dense.as<unsigned>(), ctx->region_dense.as<unsigned>(), SC(n_out));
         if (P) LAUNCH(ctx, labeled_cloud_kernel, grid_for(P, 256), 256, 0, ctx->pos_run.as<unsigned>(), P, ctx->order, ctx->run_start.as<unsigned>(),
                       ctx->run_out_off.as<unsigned>(), ctx->run_dense.as<unsigned>(), ctx->gxyz, ctx->out_xyz.as<float>(), ctx->out_label.as<unsigned>(),
-                      ctx->out_voxel.as<unsigned>(), ctx->vox_segment.as<unsigned>());
+                      ctx->out_voxel.as<unsigned>(), ctx->vox_segment.as<unsigned>(), ctx->graph_from_host ? nullptr : ctx->sorted_label,
+                      ctx->graph_from_host ? nullptr : ctx->owner0.as<unsigned>());
     }
     rc = mark(ctx, 8); if (rc) return rc;
     rc = pull_scalars(ctx); if (rc) return rc;
@@ -716,6 +685,14 @@ int f3ps_merge_profile(f3ps_ctx* ctx, uint64_t cycles[8]) {
     if (!ctx || !cycles) return F3PS_ERR_INVALID_ARGUMENT;
     int rc = need(ctx, P_MERGED, "f3ps_merge_profile"); if (rc) return rc;
     for (int i = 0; i < 8; ++i) cycles[i] = ctx->h_sc->mctl.phase_cycles[i];
+    return F3PS_OK;
+}
+
+int f3ps_expand_profile(f3ps_ctx* ctx, uint64_t ns[8]) {
+    if (!ctx || !ns) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_EXPANDED, "f3ps_expand_profile"); if (rc) return rc;
+    if ((rc = pull_scalars(ctx))) return rc;
+    for (int i = 0; i < 8; ++i) ns[i] = ctx->h_sc->xctl.t_phase[i];
     return F3PS_OK;
 }
 
@@ -762,7 +739,7 @@ int f3ps_get_counts(f3ps_ctx* ctx, f3ps_counts* out) {
     out->seed_depth = h.sb.depth; out->n_seed_cells = (int)ctx->n_cells; out->n_seeds = (int)ctx->S0;
     out->n_supervoxels = (int)ctx->S; out->n_edges = (int)ctx->E;
     out->n_merges = (int)h.mctl.n_merges; out->n_segments = (int)h.mctl.regions_alive; out->n_edges_left = (int)h.mctl.edges_alive;
-    out->rounds = ctx->rounds; out->sweeps = (int)h.flags.sweeps_total; out->n_labeled = (int)ctx->n_out;
+    out->rounds = ctx->rounds; out->sweeps = (int)h.xctl.sweeps_total; out->n_labeled = (int)ctx->n_out;
     out->lambda = h.lambda;
     out->max_touched = (int)h.mctl.max_touched; out->fold_steps = (int64_t)h.mctl.fold_steps;
     out->nan_weights = (int)(h.mctl.nan_weights + h.nan_weights_init);

@@ -102,14 +102,15 @@ __global__ void __launch_bounds__(256) region_init_ranges_kernel(unsigned S, con
     }
 }
 
-// getSupervoxelAdjacency + clear_adjacency: unique (a<b) label pairs through a hash set
+// getSupervoxelAdjacency + clear_adjacency: unique (a<b) label pairs through a hash set.  Walks the helpers'
+// LEAF lists (position i: helper pos_label[i] holds voxel pos_vox[i]), as getNeighborLabels does, so a phantom
+// leaf contributes (holder -> owners around it) as well; only pairs with first < second survive clear_adjacency.
 __global__ void __launch_bounds__(256) edge_collect_kernel(const int* __restrict__ nbr_col, unsigned V_cap, const int* __restrict__ nbr_row,
-        const unsigned* __restrict__ n_vox_ptr, const unsigned* __restrict__ owner, const unsigned* __restrict__ rank_of_label,
-        unsigned long long* __restrict__ set_slots, unsigned mask, unsigned* __restrict__ overflow) {
-    const unsigned V = *n_vox_ptr;
-    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
-        const unsigned lv = owner[v];
-        if (!lv) continue;
+        unsigned n_pos, const unsigned* __restrict__ pos_label, const unsigned* __restrict__ pos_vox, const unsigned* __restrict__ owner,
+        const unsigned* __restrict__ rank_of_label, unsigned long long* __restrict__ set_slots, unsigned mask, unsigned* __restrict__ overflow) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pos; i += gridDim.x * blockDim.x) {
+        const unsigned lv = pos_label[i];
+        const unsigned v = pos_vox[i];
         const int cnt = nbr_row[(size_t)v * kNbrStride + 27];
         unsigned last = 0;
         for (int r = 0; r < cnt; ++r) {

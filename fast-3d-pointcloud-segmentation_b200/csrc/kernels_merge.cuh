@@ -226,7 +226,7 @@ __global__ void dense_label_kernel(RegionArrays R, const unsigned* __restrict__ 
 __global__ void __launch_bounds__(256) labeled_cloud_kernel(const unsigned* __restrict__ pos_run, unsigned n_pos, const unsigned* __restrict__ order,
         const unsigned* __restrict__ run_start, const unsigned* __restrict__ run_out_off, const unsigned* __restrict__ run_dense,
         const float4* __restrict__ vox_xyz, float* __restrict__ out_xyz, unsigned* __restrict__ out_label, unsigned* __restrict__ out_voxel,
-        unsigned* __restrict__ vox_segment) {
+        unsigned* __restrict__ vox_segment, const unsigned* __restrict__ pos_label, const unsigned* __restrict__ owner) {
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pos; i += gridDim.x * blockDim.x) {
         const unsigned run = pos_run[i];
         if (run == 0xffffffffu) continue;                 // unowned voxel: absent from every region
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) labeled_cloud_kernel(const unsigned* __re
         const float4 p = vox_xyz[v];
         out_xyz[3 * (size_t)o] = p.x; out_xyz[3 * (size_t)o + 1] = p.y; out_xyz[3 * (size_t)o + 2] = p.z;
         out_label[o] = run_dense[run]; out_voxel[o] = v;
-        vox_segment[v] = run_dense[run];
+        if (!owner || owner[v] == pos_label[i]) vox_segment[v] = run_dense[run];   // a phantom leaf does not relabel its voxel
     }
 }
 

@@ -537,7 +537,7 @@ struct KeepOp {
     __device__ __forceinline__ void emit(unsigned pos, int64_t i, const Payload&) const { seeds[pos] = cell_nn[i]; }
 };
 
-// ---- K5: flow-constrained expansion as an exact data-parallel fixed point (A.5) -------------
+// ---- K5 helpers shared with kernels_expand.cuh (A.5) ---------------------------------------
 struct Centroids {            // per label (index = label, 0 unused)
     float4* xyz;              // mean xyz, w = voxel count
     float4* rgb;              // mean rgb
@@ -545,22 +545,6 @@ struct Centroids {            // per label (index = label, 0 unused)
 };
 
 constexpr unsigned kNoSteal = 0xffffffffu;
-
-// createSupervoxelHelpers.  Two seed cells can elect the same voxel; then both helpers hold the leaf,
-// the later one owns it, and in round 1 the EARLIER helper steals it back at distance(zero centroid, leaf)
-// and the later helper is erased (A.4 quirk).  Net effect reproduced here: the lowest label owns the
-// voxel, and a shared seed voxel starts with that stolen distance instead of FLT_MAX.
-__global__ void __launch_bounds__(256) expand_init_kernel(const int* __restrict__ seeds, const unsigned* __restrict__ n_seeds_ptr,
-        unsigned* __restrict__ owner, unsigned* __restrict__ claims, Centroids cen) {
-    const unsigned S = *n_seeds_ptr;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
-        atomicMax(&owner[seeds[i]], 0xffffffffu - (i + 1));   // inverted label: max == lowest label
-        atomicAdd(&claims[seeds[i]], 1u);
-        cen.xyz[i + 1] = make_float4(0, 0, 0, 1.0f);  // SupervoxelHelper::centroid_ starts at zero (literal)
-        cen.rgb[i + 1] = make_float4(0, 0, 0, 0);
-        cen.nrm[i + 1] = make_float4(0, 0, 0, 0);
-    }
-}
 
 __device__ __forceinline__ float voxel_data_distance(const float4& cx, const float4& cc, const float4& cn, const float4& vx,
                                                      const float4& vc, const float4& vn, const VccsParams& P) {
@@ -570,133 +554,6 @@ __device__ __forceinline__ float voxel_data_distance(const float4& cx, const flo
     float color = sqrtf(sum3(dc0 * dc0, dc1 * dc1, dc2 * dc2)) / 255.0f;
     float cosang = 1.0f - fabsf(sum4(cn.x * vn.x, cn.y * vn.y, cn.z * vn.z, cn.w * vn.w));
     return cosang * P.normal_imp + color * P.color_imp + spatial * P.spatial_imp;
-}
-
-__global__ void __launch_bounds__(256) expand_init_shared_kernel(const int* __restrict__ seeds, const unsigned* __restrict__ n_seeds_ptr,
-        unsigned* __restrict__ owner, const unsigned* __restrict__ claims, float* __restrict__ dist, const float4* __restrict__ vox_xyz,
-        const float4* __restrict__ vox_rgb, const float4* __restrict__ vox_nrm, VccsParams P) {
-    const unsigned S = *n_seeds_ptr;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
-        const int u = seeds[i];
-        if (owner[u] != 0xffffffffu - (i + 1)) continue;      // not the lowest label on this voxel
-        owner[u] = i + 1;
-        if (claims[u] > 1) {
-            const float4 z = make_float4(0, 0, 0, 0);
-            dist[u] = voxel_data_distance(z, z, z, vox_xyz[u], vox_rgb[u], vox_nrm[u], P);
-        }
-    }
-}
-
-struct SweepFlags {           // device-resident control block of one expansion
-    unsigned changed[16];     // per sweep index of the current round
-    unsigned not_converged;   // sticky
-    unsigned sweeps_total;
-    unsigned pad[2];
-};
-constexpr int kMaxSweeps = 16;
-
-// One sweep.  Voxel n folds, in ascending label order, every helper h that still owns a
-// neighbour u != n at its turn (owner0[u] == h and no lower label stole u: st_in[u] > h).
-__global__ void __launch_bounds__(256) expand_sweep_kernel(int sweep, const int* __restrict__ nbr_col, unsigned V_cap,
-        const unsigned* __restrict__ n_vox_ptr, const unsigned* __restrict__ owner0, const float* __restrict__ dist0,
-        const unsigned* __restrict__ st_in, unsigned* __restrict__ st_out, unsigned* __restrict__ owner1, float* __restrict__ dist1,
-        const float4* __restrict__ vox_xyz, const float4* __restrict__ vox_rgb, const float4* __restrict__ vox_nrm,
-        const int* __restrict__ nbr_row, Centroids cen, VccsParams P, SweepFlags* flags) {
-    for (int j = 0; j < sweep; ++j) if (flags->changed[j] == 0) return;   // fixed point already reached this round
-    const unsigned V = *n_vox_ptr;
-    unsigned any_change = 0;
-    for (unsigned n = blockIdx.x * blockDim.x + threadIdx.x; n < V; n += gridDim.x * blockDim.x) {
-        unsigned cur = owner0[n];
-        float D = dist0[n];
-        const int cnt = nbr_row[(size_t)n * kNbrStride + 27];
-        unsigned cand[26]; int nc = 0;
-        for (int r = 0; r < cnt; ++r) {
-            const unsigned u = (unsigned)nbr_col[(size_t)r * V_cap + n];
-            if (u == n) continue;
-            const unsigned h = owner0[u];
-            if (h == 0 || !(st_in[u] > h)) continue;
-            // sorted insert, distinct
-            int p = nc;
-            bool dup = false;
-            while (p > 0 && cand[p - 1] >= h) { if (cand[p - 1] == h) { dup = true; break; } --p; }
-            if (dup) continue;
-            for (int q = nc; q > p; --q) cand[q] = cand[q - 1];
-            cand[p] = h; ++nc;
-        }
-        unsigned first = kNoSteal;
-        if (nc) {
-            const float4 vx = vox_xyz[n], vc = vox_rgb[n], vn = vox_nrm[n];
-            for (int q = 0; q < nc; ++q) {
-                const unsigned h = cand[q];
-                if (h == cur) continue;
-                const float d = voxel_data_distance(cen.xyz[h], cen.rgb[h], cen.nrm[h], vx, vc, vn, P);
-                if (d < D) { if (first == kNoSteal) first = h; D = d; cur = h; }
-            }
-        }
-        owner1[n] = cur; dist1[n] = D; st_out[n] = first;
-        if (first != st_in[n]) any_change = 1;
-    }
-    if (__syncthreads_or(any_change) && threadIdx.x == 0) atomicOr(&flags->changed[sweep], 1u);
-}
-
-// end of round: changed[j] == 0 after sweep j means "sweep j proved the fixed point" (a skipped
-// sweep leaves its flag at 0 as well); count the sweeps that ran and reset the flags.
-__global__ void expand_round_end_kernel(SweepFlags* flags, int max_sweeps) {
-    if (threadIdx.x || blockIdx.x) return;
-    int done = -1;
-    for (int j = 0; j < max_sweeps; ++j) if (flags->changed[j] == 0) { done = j; break; }
-    if (done < 0) { flags->not_converged = 1; done = max_sweeps - 1; }
-    flags->sweeps_total += (unsigned)(done + 1);
-    for (int j = 0; j < kMaxSweeps; ++j) flags->changed[j] = 0;
-}
-
-// segment bounds of the label-sorted voxel list
-__global__ void __launch_bounds__(256) label_bounds_kernel(const unsigned* __restrict__ sorted_label, const unsigned* __restrict__ n_vox_ptr,
-        unsigned* __restrict__ seg_start, unsigned* __restrict__ seg_end) {
-    const unsigned V = *n_vox_ptr;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < V; i += gridDim.x * blockDim.x) {
-        const unsigned l = sorted_label[i];
-        if (i == 0 || sorted_label[i - 1] != l) seg_start[l] = i;
-        if (i + 1 == V || sorted_label[i + 1] != l) seg_end[l] = i + 1;
-    }
-}
-
-// SupervoxelHelper::updateCentroid: ordered sums over the helper's voxels (idx order), one
-// warp per label, lanes 0..9 each own one accumulator chain (n0..n3, x,y,z, r,g,b).
-__global__ void __launch_bounds__(256) centroid_fold_kernel(const unsigned* __restrict__ sorted_vox, const unsigned* __restrict__ seg_start,
-        const unsigned* __restrict__ seg_end, const unsigned* __restrict__ n_seeds_ptr, const float4* __restrict__ vox_xyz,
-        const float4* __restrict__ vox_rgb, const float4* __restrict__ vox_nrm, Centroids cen) {
-    const unsigned S = *n_seeds_ptr;
-    const int lane = threadIdx.x & 31;
-    const unsigned warps_total = (gridDim.x * blockDim.x) >> 5;
-    const float* src = lane < 4 ? reinterpret_cast<const float*>(vox_nrm) + lane
-                     : lane < 7 ? reinterpret_cast<const float*>(vox_xyz) + (lane - 4)
-                                : reinterpret_cast<const float*>(vox_rgb) + (lane - 7);
-    for (unsigned l = 1 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); l <= S; l += warps_total) {
-        const unsigned s = seg_start[l], e = seg_end[l];
-        if (e <= s) { if (lane == 0) cen.xyz[l].w = 0.0f; continue; }   // helper erased (no leaves)
-        float acc = 0.0f;
-        for (unsigned base = s; base < e; base += 32) {
-            const unsigned m = min(32u, e - base);
-            const unsigned mine = (base + lane < e) ? sorted_vox[base + lane] : 0u;
-            for (unsigned j = 0; j < m; ++j) {
-                const unsigned u = __shfl_sync(kFull, mine, j);
-                if (lane < 10) acc += src[(size_t)u * 4];
-            }
-        }
-        // gather the ten sums
-        float n0 = __shfl_sync(kFull, acc, 0), n1 = __shfl_sync(kFull, acc, 1), n2 = __shfl_sync(kFull, acc, 2), n3 = __shfl_sync(kFull, acc, 3);
-        float x = __shfl_sync(kFull, acc, 4), y = __shfl_sync(kFull, acc, 5), z = __shfl_sync(kFull, acc, 6);
-        float r = __shfl_sync(kFull, acc, 7), g = __shfl_sync(kFull, acc, 8), b = __shfl_sync(kFull, acc, 9);
-        if (lane == 0) {
-            float zz = sum4(n0 * n0, n1 * n1, n2 * n2, n3 * n3);
-            if (zz > 0.0f) { float sq = sqrtf(zz); n0 /= sq; n1 /= sq; n2 /= sq; n3 /= sq; }
-            const float cnt = (float)(e - s);
-            cen.nrm[l] = make_float4(n0, n1, n2, n3);
-            cen.xyz[l] = make_float4(x / cnt, y / cnt, z / cnt, cnt);
-            cen.rgb[l] = make_float4(r / cnt, g / cnt, b / cnt, 0.0f);
-        }
-    }
 }
 
 } // namespace f3ps

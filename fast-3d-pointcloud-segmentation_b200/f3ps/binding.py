@@ -95,6 +95,7 @@ def lib():
         "f3ps_stage_ms": (C.c_int, [vp, C.c_int, C.POINTER(f32)]),
         "f3ps_launch_count": (i64, [vp]),
         "f3ps_merge_profile": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
+        "f3ps_expand_profile": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
         "f3ps_test_rgb2lab": (C.c_int, [vp, vp, vp, i64]),
         "f3ps_test_lab_ciede00": (C.c_int, [vp, vp, vp, vp, i64]),
         "f3ps_test_rgb_eucl": (C.c_int, [vp, vp, vp, vp, i64]),
@@ -115,7 +116,7 @@ EXPORTED = ["f3ps_create", "f3ps_destroy", "f3ps_last_error", "f3ps_version", "f
             "f3ps_get_voxel_neighbors", "f3ps_get_voxel_normals", "f3ps_get_seeds", "f3ps_get_voxel_labels",
             "f3ps_get_supervoxels", "f3ps_get_supervoxel_voxels", "f3ps_get_adjacency", "f3ps_get_edges", "f3ps_get_cdf",
             "f3ps_get_merge_log", "f3ps_get_state_regions", "f3ps_get_state_edges", "f3ps_get_labeled_cloud", "f3ps_get_region_mean_color",
-            "f3ps_get_voxel_segments_device", "f3ps_stage_ms", "f3ps_launch_count", "f3ps_merge_profile", "f3ps_test_rgb2lab",
+            "f3ps_get_voxel_segments_device", "f3ps_stage_ms", "f3ps_launch_count", "f3ps_merge_profile", "f3ps_expand_profile", "f3ps_test_rgb2lab",
             "f3ps_test_lab_ciede00", "f3ps_test_rgb_eucl", "f3ps_test_sort_pairs"]
 
 
@@ -224,6 +225,11 @@ class Segmenter:
         self._chk(self.L.f3ps_merge_profile(self.h, C.byref(a)))
         return dict(zip(["argmin", "fold_scan", "order", "delta", "stamps"], list(a)[:5]))
 
+    def expand_profile(self):
+        a = (C.c_uint64 * 8)()
+        self._chk(self.L.f3ps_expand_profile(self.h, C.byref(a)))
+        return dict(zip(["init", "sweeps", "count", "alloc", "fill", "fold", "tail"], list(a)[:7]))
+
     def launch_count(self):
         return int(self.L.f3ps_launch_count(self.h))
 
@@ -289,8 +295,9 @@ class Segmenter:
 
     def supervoxel_voxels(self):
         c = self.counts()
-        idx = np.zeros(c.n_voxels, np.int32); off = np.zeros(c.n_supervoxels + 1, np.int64)
-        self._chk(self.L.f3ps_get_supervoxel_voxels(self.h, _p(idx), _p(off), c.n_voxels, c.n_supervoxels))
+        cap = c.n_voxels + c.n_supervoxels          # a surviving phantom leaf is listed by its holder as well
+        idx = np.zeros(cap, np.int32); off = np.zeros(c.n_supervoxels + 1, np.int64)
+        self._chk(self.L.f3ps_get_supervoxel_voxels(self.h, _p(idx), _p(off), cap, c.n_supervoxels))
         return idx[:off[-1]], off
 
     # ---- device self tests ----

@@ -47,8 +47,8 @@ void SupervoxelClustering<PointT>::extract(std::map<uint32_t, typename pcl::Supe
     h_->check(f3ps_get_voxel_normals(c, vn.data(), vcurv.data(), (int64_t)V));
     std::vector<uint32_t> label(S); std::vector<float> cen(3 * S), rgb(3 * S), nrm(4 * S); std::vector<int32_t> cnt(S);
     h_->check(f3ps_get_supervoxels(c, label.data(), cen.data(), rgb.data(), nrm.data(), cnt.data(), (int64_t)S));
-    std::vector<int32_t> idx(V); std::vector<int64_t> off(S + 1);
-    h_->check(f3ps_get_supervoxel_voxels(c, idx.data(), off.data(), (int64_t)V, (int64_t)S));
+    std::vector<int32_t> idx(V + S); std::vector<int64_t> off(S + 1);     // + S: a helper may also list one phantom leaf
+    h_->check(f3ps_get_supervoxel_voxels(c, idx.data(), off.data(), (int64_t)(V + S), (int64_t)S));
     for (size_t s = 0; s < S; ++s) {
         typename pcl::Supervoxel<PointT>::Ptr sv(new pcl::Supervoxel<PointT>());
         sv->centroid_.x = cen[3 * s]; sv->centroid_.y = cen[3 * s + 1]; sv->centroid_.z = cen[3 * s + 2];

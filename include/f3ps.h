@@ -157,6 +157,8 @@ int f3ps_stage_ms(f3ps_ctx* ctx, int stage, float* ms);
 /* SM cycles the last f3ps_merge spent per phase of the merge loop: argmin, fold||edge scan, ordering,
  * re-weighting, tie stamps (thread 0's clock64; profiling aid) */
 int f3ps_merge_profile(f3ps_ctx* ctx, uint64_t cycles[8]);
+/* nanoseconds the expansion kernel spent per phase: init, sweeps, count, scan, fill, centroid fold, tail, (spare) */
+int f3ps_expand_profile(f3ps_ctx* ctx, uint64_t ns[8]);
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t f3ps_launch_count(const f3ps_ctx* ctx);
 

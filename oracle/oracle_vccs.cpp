@@ -546,6 +546,7 @@ void Oracle::expand_fixed_point() {
     const int max_depth = (int)(1.8f * P.seed_res / P.voxel_res);
     rounds = 0;
     std::vector<uint32_t> st_in(V), st_out(V);
+    std::vector<uint8_t> ph_won(V, 0);                                   // the phantom holder stole its own leaf this round
     for (int it = 1; it < max_depth; ++it) {
         std::fill(st_in.begin(), st_in.end(), NONE);
         int sweeps = 0;
@@ -562,12 +563,13 @@ void Oracle::expand_fixed_point() {
                 std::sort(cand.begin(), cand.end());
                 cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
                 uint32_t first = NONE;
+                bool won = false;
                 for (uint32_t h : cand) {
                     if (h == cur || !cen[h].alive) continue;
                     const float d = vdist(cen[h], n);
-                    if (d < D) { if (first == NONE) first = h; D = d; cur = h; }
+                    if (d < D) { if (first == NONE) first = h; D = d; cur = h; if (h == phantom[n]) won = true; }
                 }
-                owner1[n] = cur; D1[n] = D; st_out[n] = first;
+                owner1[n] = cur; D1[n] = D; st_out[n] = first; ph_won[n] = won ? 1 : 0;
                 if (first != st_in[n]) changed = true;
             }
             ++sweeps;
@@ -580,7 +582,9 @@ void Oracle::expand_fixed_point() {
         for (int v = 0; v < V; ++v) if (owner0[v] && owner1[v] != owner0[v]) ++steals;
         steals_per_round.push_back(steals);
         owner0 = owner1; D0 = D1;
-        for (int v = 0; v < V; ++v) if (phantom[v] && owner0[v] == phantom[v]) { phantom_leaf[phantom[v]] = -1; phantom[v] = 0; }
+        // a holder that stole its phantom leaf owns it regularly from then on (and loses it for good if a later helper
+        // steals it again in the same round: removeLeaf erases it from the holder's set)
+        for (int v = 0; v < V; ++v) if (phantom[v] && ph_won[v]) { phantom_leaf[phantom[v]] = -1; phantom[v] = 0; }
         fold_centroids(owner0);
         ++rounds;
     }

@@ -67,8 +67,40 @@ def run_both(gpu, oracle_mod, pts, mp, thr, merge_impl=1, **vccs):
     return g, o
 
 
+# CIEDE2000 is evaluated in FP64 through libm (glibc on the host, CUDA's on the device): the two differ in the last
+# double bit now and then, and about one edge in 10^4 sees that survive the final cast to float.  For these arrays the
+# bar is BASELINE.json's (1e-5 relative) tightened to 1e-6 and at most 0.2 % of the entries not bit-identical.
+LIBM_ARRAYS = {"edges_dc", "edges_w", "merges_w", "final_w"}
+
+
+def close_enough(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    if a.shape != b.shape:
+        return False
+    ne = ~((a == b) | (np.isnan(a) & np.isnan(b)))
+    if not ne.any():
+        return True
+    rel = np.abs(a[ne] - b[ne]) / np.maximum(np.abs(b[ne]), 1e-30)
+    return bool(ne.mean() <= 2e-3 and rel.max() <= 1e-6)
+
+
+def upper(adj):
+    """Clustering::clear_adjacency (src/clustering.cpp:476-486): what set_initialstate keeps of the adjacency multimap."""
+    adj = np.asarray(adj).reshape(-1, 2)
+    return adj[adj[:, 0] <= adj[:, 1]]
+
+
 def assert_parity(g, o, names):
-    bad = [n for n in names if not same(g.array(n), o.array(n))]
+    """'adj' is compared after clear_adjacency (a surviving phantom leaf adds a ONE-WAY pair to PCL's multimap, the C ABI
+    returns the symmetric closure of what Clustering keeps).  When the reference's weights are NaN (degenerate regions) its
+    multimap order is undefined behaviour, so the order of the surviving edges is not compared."""
+    names = list(names)
+    if "adj" in names:
+        names.remove("adj")
+        assert np.array_equal(upper(g.array("adj")), upper(o.array("adj"))), "adj"
+    if o.scalars()["nan_weights"] > 0:
+        names = [n for n in names if n not in ("final_ab", "final_w")]
+    bad = [n for n in names if not (close_enough if n in LIBM_ARRAYS else same)(g.array(n), o.array(n))]
     assert not bad, "GPU differs from the oracle in: %s" % bad
 
 
@@ -126,6 +158,22 @@ def test_sweep_frames_config3_eq200(gpu, oracle_mod, seed):
     g, o = run_both(gpu, oracle_mod, pts, EQ, 0.5, merge_impl=1)
     assert_parity(g, o, STAGE_ARRAYS + MERGE_ARRAYS)
     assert len(o.array("merges_w")) > 20
+
+
+@pytest.mark.parametrize("seed,w,h", [(52, 160, 120), (127, 160, 120), (16, 160, 120), (30005, 320, 240)])
+def test_phantom_seed_leaves(gpu, oracle_mod, seed, w, h):
+    """Two seed cells electing one voxel: the earlier helper keeps a 'phantom' leaf (kernels_expand.cuh).  Seeds 52, 127 and 16
+    keep one to the end (it is listed twice in the labelled cloud, and adds a one-way adjacency pair, so the raw multimap is
+    compared after clear_adjacency).  Seed 16 is the degenerate form: two helpers on one isolated voxel -> identical centroids
+    -> NaN delta_g -> NaN lambda -> every weight NaN in the reference; nothing merges and the map order is undefined."""
+    pts = gpu.synth.make_frame(seed=seed, width=w, height=h)
+    g, o = run_both(gpu, oracle_mod, pts, AL, 0.2, merge_impl=1)
+    if seed == 16:
+        assert np.all(np.isnan(g.array("edges_w"))) and len(g.array("merges_w")) == 0
+    assert_parity(g, o, STAGE_ARRAYS + MERGE_ARRAYS)
+    if seed in (52, 127, 16):
+        assert int(g.array("sv_count").sum()) > int((g.array("labels") > 0).sum())
+        assert len(g.array("out_voxel")) == int(g.array("sv_count").sum())
 
 
 def test_no_transform_and_other_resolutions(gpu, oracle_mod, small_frame):

@@ -190,3 +190,24 @@ def test_bundled_frame_config1(oracle_mod):
     assert len(o.array("sv_label")) == 597 and len(o.array("edges_w")) == 1556
     assert abs(o.scalars()["lambda"] - 0.637) < 0.01
     assert 560 <= len(o.array("merges_w")) <= 600
+
+
+@pytest.mark.parametrize("seed,w,h", [(11, 160, 120), (16, 160, 120), (52, 160, 120), (127, 160, 120), (30000, 320, 240), (30005, 320, 240)])
+def test_expansion_fixed_point_equals_literal_sequential(oracle_mod, seed, w, h):
+    """the per-voxel fold + steal-table fixed point (what the CUDA kernel runs) reproduces PCL's
+    sequential helper loop exactly, including 'phantom' seed leaves (two seed cells electing one voxel; seeds 16, 52
+    and 127 keep such a leaf to the end, so it shows up in voxels_, the adjacency and the labelled cloud)."""
+    from f3ps import synth
+    pts = synth.make_frame(seed=seed, width=w, height=h)
+    res = []
+    for impl in (0, 1):
+        o = oracle_mod.Oracle(); o.set_vccs_params(); o.set_merge_params(merge_impl=1, **AL); o.set_expand_impl(impl)
+        o.set_input(pts); o.run(0, 0.2)
+        res.append(o)
+    lit, fp = res
+    for n in ("labels", "sv_label", "sv_count", "adj", "edges_ab", "merges_ab", "out_label", "out_voxel"):
+        assert np.array_equal(lit.array(n), fp.array(n)), n
+    for n in ("dist", "sv_xyz", "sv_rgb", "sv_normal", "edges_w", "merges_w"):
+        assert np.array_equal(bits(lit.array(n)), bits(fp.array(n))), n
+    if seed in (16, 52, 127):
+        assert int(lit.array("sv_count").sum()) > int((lit.array("labels") > 0).sum())      # a phantom leaf survived

@@ -67,6 +67,7 @@ def main():
         g.set_input(pts); t = time.time(); g.run(thr); print("full run wall %.2f ms" % ((time.time() - t) * 1e3), g.stage_ms())
     print("launches", g.launch_count())
     print("merge profile (cycles)", g.merge_profile())
+    print("expand profile (ns)", g.expand_profile())
     return 0
 
 if __name__ == "__main__":
