@@ -6,6 +6,7 @@
 // Same float/double mix per expression as the reference; compiled with -fmad=false.
 #pragma once
 #include "common.cuh"
+#include "ciede_fast.h"
 
 namespace f3ps {
 
@@ -41,58 +42,8 @@ __device__ inline void rgb2lab(const short* __restrict__ lut, float r255, float 
     lab[2] = ((float)out[2] / 16384.0f) * 256.0f - 128.0f;
 }
 
-__device__ inline float lab_ciede00(const float lab1[3], const float lab2[3]) {
-    const double kL = 1.0, kC = 1.0, kH = 1.0;
-    const float L1 = lab1[0], a1 = lab1[1], b1 = lab1[2];
-    const float L2 = lab2[0], a2 = lab2[1], b2 = lab2[2];
-    const double Cab1 = (double)sqrtf(a1 * a1 + b1 * b1);
-    const double Cab2 = (double)sqrtf(a2 * a2 + b2 * b2);
-    const double Cab = (Cab1 + Cab2) / 2.0;
-    const double p25_7 = 6103515625.0;                       // pow(25.0, 7.0), exact
-    const double Cab7 = pow(Cab, 7.0);
-    const double G = 0.5 * (1.0 - sqrt(Cab7 / (Cab7 + p25_7)));
-    const double ap1 = (1.0 + G) * (double)a1;
-    const double ap2 = (1.0 + G) * (double)a2;
-    const double Cp1 = sqrt(ap1 * ap1 + (double)(b1 * b1));
-    const double Cp2 = sqrt(ap2 * ap2 + (double)(b2 * b2));
-    const double Cp_prod = (Cp2 * Cp1);
-    double hp1 = 0;
-    if ((fabs(ap1) + (double)fabsf(b1)) != 0.0) {
-        hp1 = atan2((double)b1, ap1);
-        if (hp1 < 0) hp1 += 2.0 * F3PS_PI;
-    }
-    double hp2 = 0;
-    if ((fabs(ap2) + (double)fabsf(b2)) != 0.0) {
-        hp2 = atan2((double)b2, ap2);
-        if (hp2 < 0) hp2 += 2.0 * F3PS_PI;
-    }
-    const double dL = (double)(L2 - L1);
-    const double dC = (Cp2 - Cp1);
-    double dhp = (hp2 - hp1);
-    if (dhp > F3PS_PI) dhp -= 2.0 * F3PS_PI;
-    else if (dhp < -F3PS_PI) dhp += 2.0 * F3PS_PI;
-    if (Cp_prod == 0.0) dhp = 0.0;
-    const double dH = 2.0 * sqrt(Cp_prod) * sin(dhp / 2.0);
-    const double Lp = (double)(L2 + L1) / 2.0;
-    const double Cp = (Cp1 + Cp2) / 2.0;
-    double hp = (hp1 + hp2) / 2.0;
-    if (fabs(hp1 - hp2) > F3PS_PI) hp -= F3PS_PI;
-    if (hp < 0) hp += 2.0 * F3PS_PI;
-    if (Cp_prod == 0.0) hp = hp1 + hp2;
-    const double Lpm502 = (Lp - 50.0) * (Lp - 50.0);
-    const double T = 1.0 - 0.17 * cos(hp - F3PS_PI / 6.0) + 0.24 * cos(2.0 * hp)
-                   + 0.32 * cos(3.0 * hp + F3PS_PI / 30.0) - 0.20 * cos(4.0 * hp - 63.0 * F3PS_PI / 180.0);
-    const double hq = ((180.0 / F3PS_PI * hp - 275.0) / 25.0);
-    const double dheta_rad = (30.0 * F3PS_PI / 180.0) * exp(-(hq * hq));       // pow(x, 2.0) == x*x rounded
-    const double Cp7 = pow(Cp, 7.0);
-    const double Rc = 2.0 * sqrt(Cp7 / (Cp7 + p25_7));
-    const double kLSL = kL * (1.0 + 0.015 * Lpm502 / sqrt(20.0 + Lpm502));
-    const double kLSC = kC * (1.0 + 0.045 * Cp);
-    const double kHSH = kH * (1.0 + 0.015 * Cp * T);
-    const double RT = -sin(2.0 * dheta_rad) * Rc;
-    const double tL = dL / kLSL, tC = dC / kLSC, tH = dH / kHSH;
-    return (float)sqrt(tL * tL + tC * tC + tH * tH + RT * tC * tH);
-}
+// CIEDE2000 (src/color_utilities.cpp:190-294): branch-free FP64 evaluation shared with the host-side accuracy tests
+__device__ __forceinline__ float lab_ciede00(const float lab1[3], const float lab2[3]) { return f3ps_fastmath::ciede00(lab1, lab2); }
 
 __device__ inline float rgb_eucl(const float c1[3], const float c2[3]) {
     const float d0 = c1[0] - c2[0], d1 = c1[1] - c2[1], d2 = c1[2] - c2[2];
@@ -160,6 +111,19 @@ __device__ inline void delta_c_g(const EdgeParams& ep, const float rgb1[3], cons
     }
     delta_g = normals_diff(n1, c1, n2, c2);
     if (ep.geom_mode == 1 && is_convex(n1, c1, n2, c2)) delta_g *= 0.5f;
+}
+// The same on the regions' cached colour vectors (cvec = Lab of the mean colour under LAB_CIEDE00, the mean colour
+// itself under RGB_EUCL): rgb2lab is a pure function of the mean, so it is evaluated once per region state.
+__device__ inline void delta_cached(const EdgeParams& ep, const float cv1[3], const float cv2[3], const float n1[3], const float c1[3],
+                                    const float n2[3], const float c2[3], float& delta_c, float& delta_g) {
+    if (ep.color_mode == 0) { delta_c = lab_ciede00(cv1, cv2); delta_c /= F3PS_LAB_RANGE; }
+    else { delta_c = rgb_eucl(cv1, cv2); delta_c /= F3PS_RGB_RANGE; }
+    delta_g = normals_diff(n1, c1, n2, c2);
+    if (ep.geom_mode == 1 && is_convex(n1, c1, n2, c2)) delta_g *= 0.5f;
+}
+__device__ inline void colour_vector(const EdgeParams& ep, float r, float g, float b, float cv[3]) {
+    if (ep.color_mode == 0) rgb2lab(ep.lab_lut, r, g, b, cv);
+    else { cv[0] = r; cv[1] = g; cv[2] = b; }
 }
 // Clustering::t_c + t_g (:324-376).  Out-of-range bins (NaN deltas; the reference throws from
 // map::at there) are clamped and flagged by the caller through the NaN weight they produce.

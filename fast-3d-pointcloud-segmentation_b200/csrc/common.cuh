@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <float.h>
 #include <math.h>
+#include "ciede_fast.h"
 
 namespace f3ps {
 
@@ -29,9 +30,13 @@ __device__ __forceinline__ float sum4(float a0, float a1, float a2, float a3) { 
 
 // correctly rounded float libm model
 __device__ __forceinline__ float cr_logf(float x) { return (float)log((double)x); }
-__device__ __forceinline__ float cr_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
-__device__ __forceinline__ float cr_cosf(float x) { return (float)cos((double)x); }
-__device__ __forceinline__ float cr_sinf(float x) { return (float)sin((double)x); }
+// (branch-free FP64 kernels of ciede_fast.h, <= 2 ulp(double): the rounded float is the same except within ~2^-28 of a tie)
+__device__ __forceinline__ float cr_atan2f(float y, float x) {
+    if (y == 0.0f && x == 0.0f) return 0.0f;                 // atan2(+0, +0)
+    return (float)f3ps_fastmath::atan2_fast((double)y, (double)x);
+}
+__device__ __forceinline__ float cr_cosf(float x) { return (float)f3ps_fastmath::cos_fast((double)x); }
+__device__ __forceinline__ float cr_sinf(float x) { return (float)f3ps_fastmath::sin_fast((double)x); }
 
 __device__ __forceinline__ bool finite3(float x, float y, float z) { return isfinite(x) && isfinite(y) && isfinite(z); }
 

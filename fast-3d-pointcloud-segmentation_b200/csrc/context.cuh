@@ -11,6 +11,7 @@
 
 #define F3PS_MERGE_ERR_TOUCHED 4u
 #include "kernels_merge.cuh"
+#include "kernels_merge_fast.cuh"
 
 namespace f3ps {
 
@@ -94,6 +95,10 @@ struct f3ps_ctx {
     unsigned edge_set_mask = 0; int edge_kb = 0;
     // K7
     f3ps::DevBuf mlog, run_out_off, run_dense, region_dense, out_xyz, out_label, out_voxel, vox_segment;
+    f3ps::DevBuf pos_data_buf, merge_scratch;
+    const float4* pos_data = nullptr;   // voxel (x,y,z,rgba) in position order (what the merge folds stream)
+    int merge_path = 0;                 // 1 = resident kernel, 2 = general kernel (last f3ps_merge)
+    bool force_general_merge = false;   // test hook (F3PS_FORCE_GENERAL_MERGE=1)
     f3ps::MergeLog ML{};
     unsigned n_pos = 0;           // positions of the label-ordered voxel list
     const unsigned* order = nullptr;

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <new>
 
@@ -108,6 +109,9 @@ __global__ void pos_run_kernel(const unsigned* __restrict__ sorted_label, const 
         pos_run[i] = l ? rank_of_label[l] : 0xffffffffu;
     }
 }
+__global__ void pos_gather_kernel(const unsigned* __restrict__ order, const float4* __restrict__ vox_xyz, unsigned n, float4* __restrict__ pos_data) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) pos_data[i] = vox_xyz[order[i]];
+}
 __global__ void decode_edge_keys_kernel(const unsigned long long* __restrict__ compact, unsigned n, int kb, unsigned long long* __restrict__ wide) {
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned long long k = compact[i];
@@ -139,11 +143,11 @@ RegionArrays carve_regions(void* base, size_t S) {
     RegionArrays R; char* p = (char*)base;
     auto take = [&](size_t bytes) { char* q = p; p += (bytes + 255) & ~(size_t)255; return q; };
     R.mean = (float4*)take(S * 16); R.accu0 = (float4*)take(S * 16); R.accu1 = (float4*)take(S * 16); R.accu2 = (float4*)take(S * 16);
-    R.centroid = (float4*)take(S * 16); R.normal = (float4*)take(S * 16);
+    R.centroid = (float4*)take(S * 16); R.normal = (float4*)take(S * 16); R.cvec = (float4*)take(S * 16);
     R.n = (int*)take(S * 4); R.head = (int*)take(S * 4); R.tail = (int*)take(S * 4); R.next_run = (int*)take(S * 4);
     return R;
 }
-size_t region_bytes(size_t S) { return 6 * ((S * 16 + 255) & ~(size_t)255) + 4 * ((S * 4 + 255) & ~(size_t)255); }
+size_t region_bytes(size_t S) { return 7 * ((S * 16 + 255) & ~(size_t)255) + 4 * ((S * 4 + 255) & ~(size_t)255); }
 EdgeArrays carve_edges(void* base, size_t E) {
     EdgeArrays A; char* p = (char*)base;
     auto take = [&](size_t bytes) { char* q = p; p += (bytes + 255) & ~(size_t)255; return q; };
@@ -205,6 +209,9 @@ const char* f3ps_version(void) { return "f3ps-b200 0.1 (sm_100a)"; }
 int f3ps_create(int device, void* stream, f3ps_ctx** out) {
     if (!out) return F3PS_ERR_INVALID_ARGUMENT;
     *out = nullptr;
+    // Frames of a sweep run on independent handles / streams; the default of 8 hardware work queues would serialise
+    // their persistent merge kernels 4-8 at a time.  Only effective when set before the CUDA context exists.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return F3PS_ERR_CUDA;   // no CPU fallback
@@ -240,7 +247,7 @@ void f3ps_destroy(f3ps_ctx* ctx) {
         &ctx->sv_label, &ctx->rank_of_label, &ctx->run_start, &ctx->run_end, &ctx->pos_run, &ctx->edge_set, &ctx->edge_keys_a, &ctx->edge_keys_b,
         &ctx->edge_vals_a, &ctx->edge_vals_b, &ctx->dbits_a, &ctx->dbits_b, &ctx->dbits_c, &ctx->dbits_d, &ctx->cdf_c, &ctx->cdf_g, &ctx->cdf_hist,
         &ctx->reg_init, &ctx->reg_work, &ctx->edge_init, &ctx->edge_work, &ctx->mlog, &ctx->run_out_off, &ctx->run_dense, &ctx->region_dense,
-        &ctx->out_xyz, &ctx->out_label, &ctx->out_voxel, &ctx->vox_segment};
+        &ctx->out_xyz, &ctx->out_label, &ctx->out_voxel, &ctx->vox_segment, &ctx->pos_data_buf, &ctx->merge_scratch};
     for (DevBuf* b : bufs) b->release();
     if (ctx->d_sc) cudaFree(ctx->d_sc);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
@@ -467,6 +474,7 @@ static int init_weights(f3ps_ctx* ctx, unsigned E_cap) {     // Clustering::init
     F3PS_CUDA_OK(ctx->edge_vals_a.ensure((size_t)E_cap * 4)); F3PS_CUDA_OK(ctx->edge_vals_b.ensure((size_t)E_cap * 4));
     F3PS_CUDA_OK(ctx->cdf_c.ensure((size_t)std::max(1, ctx->mp.bins) * 4)); F3PS_CUDA_OK(ctx->cdf_g.ensure((size_t)std::max(1, ctx->mp.bins) * 4));
     ep.cdf_c = ctx->cdf_c.as<float>(); ep.cdf_g = ctx->cdf_g.as<float>();
+    LAUNCH(ctx, region_cvec_kernel, grid_for(std::max(1u, ctx->S), 256), 256, 0, SC(xctl.n_sv), ctx->R0, ep);
     LAUNCH(ctx, edge_delta_kernel, grid_for(E_cap, 128), 128, 0, ctx->sorted_edge_keys, SC(n_edges), ctx->R0, ep, ctx->E0,
            ctx->dbits_a.as<unsigned>(), ctx->dbits_c.as<unsigned>());
     if (ctx->mp.merge_mode == F3PS_ADAPTIVE_LAMBDA) {
@@ -523,6 +531,9 @@ int f3ps_graph(f3ps_ctx* ctx) {
     F3PS_CUDA_OK(cudaMemsetAsync(SC(edge_overflow), 0, 16, ctx->stream));   // edge_overflow, bad_bin, nan_weights_init, pad
     if (V && S) {
         LAUNCH(ctx, pos_run_kernel, grid_for(P, 256), 256, 0, ctx->sorted_label, ctx->rank_of_label.as<unsigned>(), P, ctx->pos_run.as<unsigned>());
+        F3PS_CUDA_OK(ctx->pos_data_buf.ensure((size_t)std::max(1u, P) * 16));
+        LAUNCH(ctx, pos_gather_kernel, grid_for(P, 256), 256, 0, ctx->sorted_vox, ctx->vox_xyz.as<float4>(), P, ctx->pos_data_buf.as<float4>());
+        ctx->pos_data = ctx->pos_data_buf.as<float4>();
         LAUNCH(ctx, region_init_kernel, grid_for((int64_t)S * 32, 256), 256, 0, ctx->sv_label.as<unsigned>(), SC(xctl.n_sv), ctx->seg_start.as<unsigned>(),
                ctx->seg_end.as<unsigned>(), ctx->sorted_vox, ctx->vox_xyz.as<float4>(), cen, ctx->R0, ctx->run_start.as<unsigned>(),
                ctx->run_end.as<unsigned>());
@@ -614,6 +625,7 @@ int f3ps_set_graph(f3ps_ctx* ctx, int64_t n_voxels, const float* voxel_xyz, cons
                   ctx->lab_vals_a.as<unsigned>(), ctx->vox_xyz.as<float4>(), ctx->R0);
     ctx->V = V; ctx->S = S; ctx->S0 = S; ctx->E = E; ctx->n_pos = V;
     ctx->order = ctx->lab_vals_a.as<unsigned>(); ctx->sorted_vox = ctx->lab_vals_a.as<unsigned>(); ctx->gxyz = ctx->vox_xyz.as<float4>();
+    ctx->pos_data = ctx->vox_xyz.as<float4>();               // identity order
     ctx->sorted_edge_keys = ctx->edge_keys_a.as<unsigned long long>();
     ctx->graph_from_host = true;
     ctx->progress = P_GRAPH - 1;
@@ -647,10 +659,50 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
     F3PS_CUDA_OK(cudaMemsetAsync(SC(n_out), 0, 4, ctx->stream));
     if (S) {
         EdgeParams ep = edge_params(ctx);
-        rc = mark(ctx, 9); if (rc) return rc;
-        LAUNCH(ctx, merge_kernel, 1, kMergeThreads, 0, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
-               ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl));
-        rc = mark(ctx, 10); if (rc) return rc;
+        // resident kernel when the graph fits one SM (kernels_merge_fast.cuh), else the general one
+        const unsigned S_cap = (S + 7u) & ~7u;
+        int slots = 0;
+        for (int sl : {4, 8, 12, 16}) if (!slots && (size_t)E <= (size_t)sl * kFastOwners) slots = sl;
+        const unsigned E_cap = (unsigned)std::max(slots, 4) * kFastOwners;
+        const size_t fast_bytes = FastSmem(nullptr, S_cap, E_cap).bytes;
+        bool fast = !ctx->force_general_merge && slots && S < 65535u && fast_bytes <= 227u * 1024u && P > 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            if (attempt == 1) {                                    // a merge overflowed the resident kernel's touched list: start over
+                F3PS_CUDA_OK(cudaMemcpyAsync(ctx->reg_work.p, ctx->reg_init.p, region_bytes(Sc), cudaMemcpyDeviceToDevice, ctx->stream));
+                F3PS_CUDA_OK(cudaMemcpyAsync(ctx->edge_work.p, ctx->edge_init.p, eb, cudaMemcpyDeviceToDevice, ctx->stream));
+                F3PS_CUDA_OK(cudaMemsetAsync(SC(mctl), 0, sizeof(MergeCtl), ctx->stream));
+            }
+            rc = mark(ctx, 9); if (rc) return rc;
+            if (fast) {
+                FastArgs A;
+                A.R = ctx->R1; A.E = ctx->E1; A.n_edges_ptr = SC(n_edges); A.n_sv_ptr = SC(xctl.n_sv); A.ep = ep; A.lambda_dev = SC(lambda);
+                A.threshold = threshold; A.run_start = ctx->run_start.as<unsigned>(); A.run_end = ctx->run_end.as<unsigned>();
+                A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
+                A.ctl = SC(mctl); A.S_cap = S_cap; A.E_cap = E_cap;
+                void (*kern)(FastArgs) = slots == 4 ? merge_fast_kernel<4> : slots == 8 ? merge_fast_kernel<8> : slots == 12 ? merge_fast_kernel<12> : merge_fast_kernel<16>;
+                F3PS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // same value from every handle / thread
+                kern<<<1, kFastThreads, fast_bytes, ctx->stream>>>(A);
+                ctx->launches++;
+                F3PS_CUDA_OK(cudaPeekAtLastError());
+                ctx->merge_path = 1;
+            } else {
+                const size_t per = ((size_t)Ec * 4 + 255) & ~(size_t)255, per8 = ((size_t)Ec * 8 + 255) & ~(size_t)255;
+                F3PS_CUDA_OK(ctx->merge_scratch.ensure(6 * per + 2 * per8 + per));
+                char* sp = (char*)ctx->merge_scratch.p;
+                MergeScratch scr;
+                scr.st[0] = (long long*)sp; sp += per8; scr.st[1] = (long long*)sp; sp += per8;
+                scr.e[0] = (int*)sp; sp += per; scr.e[1] = (int*)sp; sp += per; scr.w[0] = (float*)sp; sp += per; scr.w[1] = (float*)sp; sp += per;
+                scr.x[0] = (unsigned*)sp; sp += per; scr.x[1] = (unsigned*)sp; sp += per; scr.cls = (unsigned char*)sp;
+                LAUNCH(ctx, merge_kernel, 1, kMergeThreads, 0, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
+                       ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr);
+                ctx->merge_path = 2;
+            }
+            rc = mark(ctx, 10); if (rc) return rc;
+            if (!fast) break;
+            rc = pull_scalars(ctx); if (rc) return rc;           // did the resident kernel finish?
+            if (ctx->h_sc->mctl.error == 0) break;
+            fast = false;
+        }
         LAUNCH(ctx, dense_label_kernel, 1, 1, 0, ctx->R1, SC(xctl.n_sv), ctx->run_start.as<unsigned>(), ctx->run_end.as<unsigned>(), ctx->run_out_off.as<unsigned>(),
                ctx->run_dense.as<unsigned>(), ctx->region_dense.as<unsigned>(), SC(n_out));
         if (P) LAUNCH(ctx, labeled_cloud_kernel, grid_for(P, 256), 256, 0, ctx->pos_run.as<unsigned>(), P, ctx->order, ctx->run_start.as<unsigned>(),
@@ -660,9 +712,15 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
     }
     rc = mark(ctx, 8); if (rc) return rc;
     rc = pull_scalars(ctx); if (rc) return rc;
-    if (ctx->h_sc->mctl.error == F3PS_MERGE_ERR_TOUCHED) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "a merge touched more than 1024 edges");
+    if (ctx->h_sc->mctl.error) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "merge kernel reported an internal capacity error");
     ctx->n_out = ctx->h_sc->n_out;
     ctx->progress = P_MERGED;
+    return F3PS_OK;
+}
+
+int f3ps_set_merge_kernel(f3ps_ctx* ctx, int which) {
+    if (!ctx || (which != 0 && which != 2)) return F3PS_ERR_INVALID_ARGUMENT;
+    ctx->force_general_merge = which == 2;
     return F3PS_OK;
 }
 
@@ -681,10 +739,10 @@ int f3ps_run(f3ps_ctx* ctx, float threshold) {
     return f3ps_merge(ctx, threshold);
 }
 
-int f3ps_merge_profile(f3ps_ctx* ctx, uint64_t cycles[8]) {
+int f3ps_merge_profile(f3ps_ctx* ctx, uint64_t cycles[32]) {
     if (!ctx || !cycles) return F3PS_ERR_INVALID_ARGUMENT;
     int rc = need(ctx, P_MERGED, "f3ps_merge_profile"); if (rc) return rc;
-    for (int i = 0; i < 8; ++i) cycles[i] = ctx->h_sc->mctl.phase_cycles[i];
+    for (int i = 0; i < 32; ++i) cycles[i] = ctx->h_sc->mctl.phase_cycles[i];
     return F3PS_OK;
 }
 
@@ -743,6 +801,7 @@ int f3ps_get_counts(f3ps_ctx* ctx, f3ps_counts* out) {
     out->lambda = h.lambda;
     out->max_touched = (int)h.mctl.max_touched; out->fold_steps = (int64_t)h.mctl.fold_steps;
     out->nan_weights = (int)(h.mctl.nan_weights + h.nan_weights_init);
+    out->merge_path = ctx->merge_path;
     if (ctx->progress < P_MERGED) { out->n_segments = (int)ctx->S; out->n_edges_left = (int)ctx->E; }
     return F3PS_OK;
 }

@@ -17,6 +17,7 @@ struct RegionArrays {
     float4* accu2;     // a8, -, -, -
     float4* centroid;  // cx, cy, cz, -
     float4* normal;    // nx, ny, nz, curvature
+    float4* cvec;      // colour vector the edge weights use: Lab of the mean colour (LAB_CIEDE00) or the mean colour (RGB_EUCL)
     int* n;            // voxel count, 0 = erased
     int* head;         // rope: first / last run (run id = rank of an initial supervoxel), next pointer per run
     int* tail;
@@ -143,11 +144,21 @@ struct EdgeArrays {
 };
 constexpr long long kDeadStamp = 0x7fffffffffffffffll;
 
-__device__ __forceinline__ void region_inputs(const RegionArrays& R, int s, float rgb[3], float n[3], float c[3]) {
-    const float4 m = R.mean[s], cc = R.centroid[s], nn = R.normal[s];
-    rgb[0] = m.y; rgb[1] = m.z; rgb[2] = m.w;
+__device__ __forceinline__ void region_inputs(const RegionArrays& R, int s, float cv[3], float n[3], float c[3]) {
+    const float4 m = R.cvec[s], cc = R.centroid[s], nn = R.normal[s];
+    cv[0] = m.x; cv[1] = m.y; cv[2] = m.z;
     n[0] = nn.x; n[1] = nn.y; n[2] = nn.z;
     c[0] = cc.x; c[1] = cc.y; c[2] = cc.z;
+}
+
+// colour vectors of the initial regions (depends on the colour distance in force, so it belongs to init_weights)
+__global__ void __launch_bounds__(256) region_cvec_kernel(const unsigned* __restrict__ n_sv_ptr, RegionArrays R, EdgeParams ep) {
+    const unsigned S = *n_sv_ptr;
+    for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+        const float4 m = R.mean[s];
+        float cv[3]; colour_vector(ep, m.y, m.z, m.w, cv);
+        R.cvec[s] = make_float4(cv[0], cv[1], cv[2], 0.0f);
+    }
 }
 
 // init_weights first loop: (delta_c, delta_g) of every initial edge, lexicographic order
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(128) edge_delta_kernel(const unsigned long lon
         float rgb1[3], n1[3], c1[3], rgb2[3], n2[3], c2[3];
         region_inputs(R, a, rgb1, n1, c1); region_inputs(R, b, rgb2, n2, c2);
         float dc, dg;
-        delta_c_g(ep, rgb1, rgb2, n1, c1, n2, c2, dc, dg);
+        delta_cached(ep, rgb1, rgb2, n1, c1, n2, c2, dc, dg);
         E.a[e] = a; E.b[e] = b; E.dc[e] = dc; E.dg[e] = dg;
         dc_bits[e] = __float_as_uint(dc); dg_bits[e] = __float_as_uint(dg);   // sortable: deltas are >= 0
     }

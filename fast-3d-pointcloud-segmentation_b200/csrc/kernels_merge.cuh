@@ -13,7 +13,7 @@
 namespace f3ps {
 
 constexpr int kMergeThreads = 1024;
-constexpr int kMaxTouched = 1024;
+struct MergeScratch { int* e[2]; float* w[2]; long long* st[2]; unsigned* x[2]; unsigned char* cls; };
 
 struct MergeLog { unsigned* a; unsigned* b; float* w; unsigned* edges_left; unsigned* regions_left; };
 struct MergeCtl {
@@ -21,7 +21,7 @@ struct MergeCtl {
     unsigned nan_weights, max_touched, pad0, pad1;
     long long counter;
     unsigned long long fold_steps;
-    unsigned long long phase_cycles[8];   // argmin, fold||scan, order, delta, stamps, (spare) -- thread 0's clock64 deltas
+    unsigned long long phase_cycles[32];  // clock64 deltas / event counts per phase (see f3ps_merge_profile)
 };
 
 __device__ __forceinline__ bool key_less(float w1, long long s1, float w2, long long s2) {
@@ -31,13 +31,12 @@ __device__ __forceinline__ bool key_less(float w1, long long s1, float w2, long 
 __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R, EdgeArrays E, const unsigned* __restrict__ n_edges_ptr,
         const unsigned* __restrict__ n_sv_ptr, EdgeParams ep, const float* __restrict__ lambda_dev, float threshold,
         const unsigned* __restrict__ run_start, const unsigned* __restrict__ run_end, const unsigned* __restrict__ order,
-        const float4* __restrict__ vox_xyz, const unsigned* __restrict__ sv_label, MergeLog mlog, unsigned log_cap, MergeCtl* ctl) {
+        const float4* __restrict__ vox_xyz, const unsigned* __restrict__ sv_label, MergeLog mlog, unsigned log_cap, MergeCtl* ctl, MergeScratch scr) {
     __shared__ float s_rw[32]; __shared__ long long s_rs[32]; __shared__ int s_ri[32];
     __shared__ int s_head; __shared__ float s_head_w;
     __shared__ int s_tcount;
-    __shared__ int s_e[2][kMaxTouched]; __shared__ float s_w[2][kMaxTouched]; __shared__ long long s_st[2][kMaxTouched];
-    __shared__ unsigned s_x[2][kMaxTouched];
-    __shared__ unsigned char s_class[kMaxTouched];
+    int* const s_e[2] = {scr.e[0], scr.e[1]}; float* const s_w[2] = {scr.w[0], scr.w[1]}; long long* const s_st[2] = {scr.st[0], scr.st[1]};
+    unsigned* const s_x[2] = {scr.x[0], scr.x[1]}; unsigned char* const s_class = scr.cls;     // global scratch, capacity = E
     __shared__ unsigned s_nm, s_ealive, s_ralive; __shared__ long long s_counter;
     __shared__ unsigned long long s_fold;
     unsigned long long pc[6] = {0, 0, 0, 0, 0, 0};
@@ -113,6 +112,8 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R,
                 flip_and_normalize(cx, cy, cz, n);                                                // :418-420
                 R.centroid[a] = make_float4(cx, cy, cz, 0.0f);
                 R.normal[a] = make_float4(n[0], n[1], n[2], curv);
+                float cv[3]; colour_vector(ep, st.r, st.g, st.b, cv);
+                R.cvec[a] = make_float4(cv[0], cv[1], cv[2], 0.0f);
                 s_fold += steps;
             }
         } else {
@@ -121,70 +122,74 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R,
                 const unsigned ea = E.a[e], eb = E.b[e];
                 if (ea == a || eb == a || ea == b || eb == b) {
                     const int slot = atomicAdd(&s_tcount, 1);
-                    if (slot < kMaxTouched) s_e[0][slot] = (int)e;
+                    s_e[0][slot] = (int)e;
                 }
             }
         }
-        __threadfence_block();
+        __threadfence();
         __syncthreads();
         PHASE(1);
         const int T = s_tcount;
-        if (T > kMaxTouched) { if (tid == 0) ctl->error = F3PS_MERGE_ERR_TOUCHED; break; }
         // ---- C: order the touched edges by their old key ---------------------------------
-        if (tid < T) {
-            const int e = s_e[0][tid];
-            s_w[0][tid] = E.w[e]; s_st[0][tid] = E.stamp[e];
+        for (int i = tid; i < T; i += kMergeThreads) {
+            const int e = s_e[0][i];
+            s_w[0][i] = E.w[e]; s_st[0][i] = E.stamp[e];
             const unsigned ea = E.a[e], eb = E.b[e];
-            s_x[0][tid] = (ea == a || ea == b) ? eb : ea;
+            s_x[0][i] = (ea == a || ea == b) ? eb : ea;
         }
+        __threadfence();
         __syncthreads();
-        if (tid < T) {
-            const float w = s_w[0][tid]; const long long st = s_st[0][tid];
+        for (int i = tid; i < T; i += kMergeThreads) {
+            const float w = s_w[0][i]; const long long st = s_st[0][i];
             int r = 0;
             for (int j = 0; j < T; ++j) r += key_less(s_w[0][j], s_st[0][j], w, st) ? 1 : 0;
-            s_e[1][r] = s_e[0][tid]; s_w[1][r] = w; s_st[1][r] = st; s_x[1][r] = s_x[0][tid];
+            s_e[1][r] = s_e[0][i]; s_w[1][r] = w; s_st[1][r] = st; s_x[1][r] = s_x[0][i];
         }
+        __threadfence();
         __syncthreads();
         PHASE(2);
         // ---- D: dedupe (earlier survives), recompute, classify ---------------------------
-        float w_new = 0.0f; unsigned lo = 0, hi = 0;
-        if (tid < T) {
-            const unsigned x = s_x[1][tid];
+        for (int i = tid; i < T; i += kMergeThreads) {
+            const unsigned x = s_x[1][i];
             bool dup = false;
-            for (int q = 0; q < tid; ++q) dup = dup || (s_x[1][q] == x);
-            if (dup) s_class[tid] = C_DUP;
+            for (int q = 0; q < i; ++q) dup = dup || (s_x[1][q] == x);
+            if (dup) s_class[i] = C_DUP;
             else {
-                lo = min(a, x); hi = max(a, x);
+                const unsigned lo = min(a, x), hi = max(a, x);
                 float rgb1[3], n1[3], c1[3], rgb2[3], n2[3], c2[3];
                 region_inputs(R, (int)lo, rgb1, n1, c1); region_inputs(R, (int)hi, rgb2, n2, c2);
                 float dc, dg;
-                delta_c_g(ep, rgb1, rgb2, n1, c1, n2, c2, dc, dg);
-                w_new = unify(ep, dc, dg);
+                delta_cached(ep, rgb1, rgb2, n1, c1, n2, c2, dc, dg);
+                float w_new = unify(ep, dc, dg);
                 if (isnan(w_new)) { atomicAdd(&ctl->nan_weights, 1u); w_new = INF; }
-                const float w_old = s_w[1][tid];
-                s_class[tid] = (w_new == w_old) ? C_KEEP : (w_new > w_old ? C_FRONT : C_BACK);
+                const float w_old = s_w[1][i];
+                s_class[i] = (w_new == w_old) ? C_KEEP : (w_new > w_old ? C_FRONT : C_BACK);
+                s_w[0][i] = w_new;                                 // slot 0 of the scratch is free again: new weights
             }
         }
+        __threadfence();
         __syncthreads();
         PHASE(3);
         // ---- E: tie stamps (C.2) and write back -------------------------------------------
-        if (tid < T) {
-            const int cls = s_class[tid];
-            const int e = s_e[1][tid];
+        for (int i = tid; i < T; i += kMergeThreads) {
+            const int cls = s_class[i];
+            const int e = s_e[1][i];
             if (cls == C_DUP) E.stamp[e] = kDeadStamp;
             else {
                 int nb = 0, nf = 0, rb = 0, rf = 0;
                 for (int q = 0; q < T; ++q) {
                     const int c = s_class[q];
                     nb += (c == C_BACK); nf += (c == C_FRONT);
-                    if (q < tid) { rb += (c == C_BACK); rf += (c == C_FRONT); }
+                    if (q < i) { rb += (c == C_BACK); rf += (c == C_FRONT); }
                 }
-                long long st = s_st[1][tid];
+                long long st = s_st[1][i];
                 if (cls == C_BACK) st = s_counter + rb;
                 else if (cls == C_FRONT) st = -(s_counter + nb + (nf - 1 - rf));
-                E.a[e] = lo; E.b[e] = hi; E.w[e] = w_new; E.stamp[e] = st;
+                const unsigned x = s_x[1][i];
+                E.a[e] = min(a, x); E.b[e] = max(a, x); E.w[e] = s_w[0][i]; E.stamp[e] = st;
             }
         }
+        __threadfence();
         __syncthreads();
         if (tid == 0) {
             int nb = 0, nf = 0, nd = 0;
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R,
             s_ealive -= 1 + nd; s_ralive -= 1; s_nm += 1;
             if ((unsigned)T > ctl->max_touched) ctl->max_touched = (unsigned)T;
         }
-        __threadfence_block();
+        __threadfence();
         __syncthreads();
         PHASE(4);
     }

@@ -36,7 +36,7 @@ class Counts(C.Structure):
                 ("n_merges", C.c_int32), ("n_segments", C.c_int32), ("n_edges_left", C.c_int32),
                 ("rounds", C.c_int32), ("sweeps", C.c_int32), ("n_labeled", C.c_int32),
                 ("lambda_", C.c_float), ("max_touched", C.c_int32),
-                ("fold_steps", C.c_int64), ("nan_weights", C.c_int32), ("reserved", C.c_int32)]
+                ("fold_steps", C.c_int64), ("nan_weights", C.c_int32), ("merge_path", C.c_int32)]
 
 
 _lib = None
@@ -70,7 +70,7 @@ def lib():
         "f3ps_set_input": (C.c_int, [vp, vp, i64, C.c_int, C.c_int]),
         "f3ps_voxelize": (C.c_int, [vp]), "f3ps_neighbors": (C.c_int, [vp]), "f3ps_normals": (C.c_int, [vp]),
         "f3ps_seeds": (C.c_int, [vp]), "f3ps_expand": (C.c_int, [vp]), "f3ps_graph": (C.c_int, [vp]),
-        "f3ps_merge": (C.c_int, [vp, f32]), "f3ps_extract": (C.c_int, [vp]), "f3ps_run": (C.c_int, [vp, f32]),
+        "f3ps_merge": (C.c_int, [vp, f32]), "f3ps_set_merge_kernel": (C.c_int, [vp, C.c_int]), "f3ps_extract": (C.c_int, [vp]), "f3ps_run": (C.c_int, [vp, f32]),
         "f3ps_sync": (C.c_int, [vp]),
         "f3ps_set_graph": (C.c_int, [vp, i64, vp, vp, i32, vp, vp, vp, vp, i64, vp]),
         "f3ps_get_counts": (C.c_int, [vp, C.POINTER(Counts)]),
@@ -94,7 +94,7 @@ def lib():
         "f3ps_get_voxel_segments_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "f3ps_stage_ms": (C.c_int, [vp, C.c_int, C.POINTER(f32)]),
         "f3ps_launch_count": (i64, [vp]),
-        "f3ps_merge_profile": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
+        "f3ps_merge_profile": (C.c_int, [vp, C.POINTER(C.c_uint64 * 32)]),
         "f3ps_expand_profile": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
         "f3ps_test_rgb2lab": (C.c_int, [vp, vp, vp, i64]),
         "f3ps_test_lab_ciede00": (C.c_int, [vp, vp, vp, vp, i64]),
@@ -111,7 +111,7 @@ def lib():
 
 EXPORTED = ["f3ps_create", "f3ps_destroy", "f3ps_last_error", "f3ps_version", "f3ps_set_vccs_params",
             "f3ps_set_merge_params", "f3ps_set_input", "f3ps_voxelize", "f3ps_neighbors", "f3ps_normals", "f3ps_seeds",
-            "f3ps_expand", "f3ps_graph", "f3ps_merge", "f3ps_extract", "f3ps_run", "f3ps_sync", "f3ps_set_graph",
+            "f3ps_expand", "f3ps_graph", "f3ps_merge", "f3ps_set_merge_kernel", "f3ps_extract", "f3ps_run", "f3ps_sync", "f3ps_set_graph",
             "f3ps_get_counts", "f3ps_get_voxel_keys", "f3ps_get_voxel_centroids", "f3ps_get_point_voxel",
             "f3ps_get_voxel_neighbors", "f3ps_get_voxel_normals", "f3ps_get_seeds", "f3ps_get_voxel_labels",
             "f3ps_get_supervoxels", "f3ps_get_supervoxel_voxels", "f3ps_get_adjacency", "f3ps_get_edges", "f3ps_get_cdf",
@@ -185,6 +185,7 @@ class Segmenter:
     def expand(self): self._chk(self.L.f3ps_expand(self.h))
     def graph(self): self._chk(self.L.f3ps_graph(self.h))
     def merge(self, threshold): self._chk(self.L.f3ps_merge(self.h, threshold))
+    def set_merge_kernel(self, which): self._chk(self.L.f3ps_set_merge_kernel(self.h, which))
     def extract(self): self._chk(self.L.f3ps_extract(self.h))
     def run(self, threshold=0.2): self._chk(self.L.f3ps_run(self.h, threshold))
     def sync(self): self._chk(self.L.f3ps_sync(self.h))
@@ -221,9 +222,16 @@ class Segmenter:
         return out
 
     def merge_profile(self):
-        a = (C.c_uint64 * 8)()
+        a = (C.c_uint64 * 32)()
         self._chk(self.L.f3ps_merge_profile(self.h, C.byref(a)))
-        return dict(zip(["argmin", "fold_scan", "order", "delta", "stamps"], list(a)[:5]))
+        v = list(a)
+        if self.counts().merge_path == 1:      # resident kernel (see include/f3ps.h)
+            return {"delta": dict(zip(["head", "wait_touched", "order_dedupe_small", "spec_ciede", "wait_fold", "miss_ciede", "weights_stamps", "order_dedupe_big"], v[0:8])),
+                    "owner": dict(zip(["apply_argmin", "b1_head", "scan_publish", "wait_results"], v[8:12])),
+                    "mean": dict(zip(["wait_voxels", "fold", "lab_publish"], v[12:15])),
+                    "cov": dict(zip(["wait_voxels", "fold", "eigen_publish"], v[16:19])),
+                    "guess_misses": v[24], "ciede_evals": v[25], "merges_T_gt_32": v[26], "sum_T": v[27]}
+        return dict(zip(["argmin", "fold_scan", "order", "delta", "stamps"], v[:5]))
 
     def expand_profile(self):
         a = (C.c_uint64 * 8)()

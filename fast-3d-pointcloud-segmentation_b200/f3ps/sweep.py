@@ -26,3 +26,56 @@ def reduce_sweep(local_points, local_seconds, dist=None):
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     dist.all_reduce(m, op=dist.ReduceOp.MAX)
     return float(t[0]), float(m[0])
+
+
+class FramePool:
+    """Frames in flight on ONE GPU: `n_handles` independent f3ps handles, each with its own CUDA stream and
+    host thread (ctypes releases the GIL inside every C-ABI call).  The reference processes the files of a
+    -d sweep strictly one after the other (src/supervoxel_clustering.cpp:303); they are independent, and the
+    serial stage of a frame (K7, one persistent CTA on one SM) leaves 147 SMs idle, so a sweep keeps several
+    frames in flight.  Frame k goes to handle k % n_handles; results come back in frame order."""
+
+    def __init__(self, n_handles, device=0, vccs=None, merge=None, threshold=0.2):
+        from . import binding
+        import threading
+        self.segs = [binding.Segmenter(device=device) for _ in range(n_handles)]
+        for s in self.segs:
+            s.set_vccs_params(**(vccs or {}))
+            s.set_merge_params(**(merge or {}))
+        self.threshold = threshold
+        self._threading = threading
+
+    def close(self):
+        for s in self.segs:
+            s.close()
+        self.segs = []
+
+    def run(self, frames, on_device=False, npts=None, collect=None):
+        """frames: list of numpy point arrays (host) or device pointers (on_device=True, npts each).
+        collect(seg, k) is called on the worker thread after frame k finished (result read-back)."""
+        n = len(self.segs)
+        errors = []
+        results = [None] * len(frames)
+
+        def worker(w):
+            seg = self.segs[w]
+            try:
+                for k in range(w, len(frames), n):
+                    if on_device:
+                        seg.set_input_device(frames[k], npts, 32)
+                    else:
+                        seg.set_input(frames[k])
+                    seg.run(self.threshold)
+                    if collect is not None:
+                        results[k] = collect(seg, k)
+            except Exception as e:          # surfaced to the caller, never swallowed
+                errors.append(e)
+
+        th = [self._threading.Thread(target=worker, args=(w,)) for w in range(n)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errors:
+            raise errors[0]
+        return results

@@ -71,7 +71,7 @@ typedef struct f3ps_counts {
     int32_t max_touched;   /* largest number of edges re-weighted by one merge */
     int64_t fold_steps;    /* voxel steps folded by the merge loop (sum of |b|) */
     int32_t nan_weights;   /* edge weights that evaluated to NaN (regions with < 3 voxels) */
-    int32_t reserved;
+    int32_t merge_path;    /* kernel the last f3ps_merge ran: 1 = resident (one SM, edges in registers), 2 = general */
 } f3ps_counts;
 
 /* ---- life cycle ------------------------------------------------------------ */
@@ -105,6 +105,9 @@ int f3ps_seeds(f3ps_ctx* ctx);      /* K4 selectInitialSupervoxelSeeds */
 int f3ps_expand(f3ps_ctx* ctx);     /* K5 expandSupervoxels */
 int f3ps_graph(f3ps_ctx* ctx);      /* K6 makeSupervoxels + getSupervoxelAdjacency + set_initialstate + init_weights */
 int f3ps_merge(f3ps_ctx* ctx, float threshold); /* K7 Clustering::cluster(threshold): restarts from the initial state */
+/* which K7 kernel f3ps_merge uses: 0 = automatic (resident when the graph fits one SM, else general), 2 = always general.
+ * Both replay the same merge sequence; the switch exists for tests and profiling. */
+int f3ps_set_merge_kernel(f3ps_ctx* ctx, int which);
 /* SupervoxelClustering::extract + getSupervoxelAdjacency = K1..K5 + supervoxel tables */
 int f3ps_extract(f3ps_ctx* ctx);
 /* whole path: K1..K7 */
@@ -154,9 +157,14 @@ int f3ps_get_voxel_segments_device(f3ps_ctx* ctx, const uint32_t** device_ptr, i
 
 /* CUDA-event time of the last run of a stage, ms (valid after f3ps_sync) */
 int f3ps_stage_ms(f3ps_ctx* ctx, int stage, float* ms);
-/* SM cycles the last f3ps_merge spent per phase of the merge loop: argmin, fold||edge scan, ordering,
- * re-weighting, tie stamps (thread 0's clock64; profiling aid) */
-int f3ps_merge_profile(f3ps_ctx* ctx, uint64_t cycles[8]);
+/* Profiling aid: SM cycles (clock64) the last f3ps_merge spent per phase, and event counts.
+ * General kernel: [0..4] argmin, fold||edge scan, ordering, re-weighting, tie stamps (thread 0).
+ * Resident kernel: [0..7] delta warps: head, wait for the touched list, order/dedupe, speculative CIEDE, wait for the
+ * fold, CIEDE after a wrong guess, weights + stamps, -;  [8..11] an owner warp: apply + local argmin, B1 + head, scan + publish,
+ * wait for results;  [12..15] colour-mean warp: wait for the voxels, fold, Lab + publish, -;  [16..19] covariance warp: wait,
+ * fold, centroid + eigen-solve, -;  [24] wrong colour guesses, [25] CIEDE evaluations, [26] merges touching > 32 edges,
+ * [27] touched edges in total. */
+int f3ps_merge_profile(f3ps_ctx* ctx, uint64_t cycles[32]);
 /* nanoseconds the expansion kernel spent per phase: init, sweeps, count, scan, fill, centroid fold, tail, (spare) */
 int f3ps_expand_profile(f3ps_ctx* ctx, uint64_t ns[8]);
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */

@@ -144,6 +144,8 @@ long orc_array(void* hv, const char* name, const void** ptr) {
 // metric kernels for known-answer tests
 void orc_rgb2lab(void* hv, const float* rgb255, float* lab) { rgb2lab(((Handle*)hv)->O.lab_lut, rgb255, lab); }
 float orc_lab_ciede00(const float* lab1, const float* lab2) { return lab_ciede00(lab1, lab2); }
+void orc_rgb2lab_batch(void* hv, const float* rgb255, float* lab, long n) { for (long i = 0; i < n; ++i) rgb2lab(((Handle*)hv)->O.lab_lut, rgb255 + 3 * i, lab + 3 * i); }
+void orc_lab_ciede00_batch(const float* lab1, const float* lab2, float* out, long n) { for (long i = 0; i < n; ++i) out[i] = lab_ciede00(lab1 + 3 * i, lab2 + 3 * i); }
 float orc_rgb_eucl(const float* a, const float* b) { return rgb_eucl(a, b); }
 float orc_normals_diff(const float* n1, const float* c1, const float* n2, const float* c2) { return normals_diff(n1, c1, n2, c2); }
 int orc_is_convex(const float* n1, const float* c1, const float* n2, const float* c2) { return is_convex(n1, c1, n2, c2) ? 1 : 0; }

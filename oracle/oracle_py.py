@@ -67,6 +67,8 @@ def lib():
         L.orc_rgb2lab.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_lab_ciede00.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_lab_ciede00.restype = C.c_float
+        L.orc_rgb2lab_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+        L.orc_lab_ciede00_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
         L.orc_rgb_eucl.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_rgb_eucl.restype = C.c_float
         L.orc_normals_diff.argtypes = [C.c_void_p] * 4
@@ -166,6 +168,19 @@ class Oracle:
         a = np.ascontiguousarray(l1, np.float32)
         b = np.ascontiguousarray(l2, np.float32)
         return float(self.L.orc_lab_ciede00(_p(a), _p(b)))
+
+    def rgb2lab_batch(self, rgb255):
+        a = np.ascontiguousarray(rgb255, np.float32).reshape(-1, 3)
+        o = np.zeros_like(a)
+        self.L.orc_rgb2lab_batch(self.h, _p(a), _p(o), C.c_long(len(a)))
+        return o
+
+    def lab_ciede00_batch(self, l1, l2):
+        a = np.ascontiguousarray(l1, np.float32).reshape(-1, 3)
+        b = np.ascontiguousarray(l2, np.float32).reshape(-1, 3)
+        o = np.zeros(len(a), np.float32)
+        self.L.orc_lab_ciede00_batch(_p(a), _p(b), _p(o), C.c_long(len(a)))
+        return o
 
     def rgb_eucl(self, c1, c2):
         a = np.ascontiguousarray(c1, np.float32)

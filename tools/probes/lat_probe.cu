@@ -1,0 +1,70 @@
+// Micro-probe: latencies that bound the per-merge critical path of the resident merge kernel (development aid).
+#include <cstdio>
+#include <cuda_runtime.h>
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__global__ void chase(const unsigned* next, int n, long long* out, unsigned* sink) {
+    unsigned i = 0; long long t0 = clock64();
+    for (int k = 0; k < n; ++k) i = __ldcg(next + i);
+    long long t1 = clock64(); out[0] = (t1 - t0) / n; *sink = i;
+}
+__global__ void bulk_lat(const float4* src, long long* out, int bytes, int reps, float* sink) {
+    __shared__ __align__(128) float4 stage[512];
+    __shared__ unsigned long long mbar;
+    const unsigned mb = smem_addr(&mbar), st = smem_addr(stage);
+    if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb)); asm volatile("fence.proxy.async.shared::cta;"); }
+    __syncthreads();
+    unsigned parity = 0; long long tot = 0; float acc = 0;
+    for (int r = 0; r < reps; ++r) {
+        long long t0 = clock64();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st), "l"(src + (r * 64) % 4096), "r"(bytes), "r"(mb) : "memory");
+        }
+        unsigned ok;
+        do { asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(mb), "r"(parity) : "memory"); } while (!ok);
+        parity ^= 1;
+        long long t1 = clock64(); tot += t1 - t0; acc += stage[threadIdx.x & 15].x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = tot / reps; *sink = acc; }
+}
+__global__ void bar_lat(long long* out, int reps) {
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) __syncthreads();
+    long long t1 = clock64();
+    if (threadIdx.x == 0) out[0] = (t1 - t0) / reps;
+}
+__global__ void redux_lat(long long* out, int reps, unsigned* sink) {
+    unsigned v = threadIdx.x * 2654435761u; long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) v = __reduce_min_sync(0xffffffffu, v + threadIdx.x) + r;
+    long long t1 = clock64(); unsigned w = v; long long t2 = clock64();
+    for (int r = 0; r < reps; ++r) w = __shfl_sync(0xffffffffu, w + 1, r & 31);
+    long long t3 = clock64(); unsigned b = w; long long t4 = clock64();
+    for (int r = 0; r < reps; ++r) b = __ballot_sync(0xffffffffu, (b + threadIdx.x) & 1) + r;
+    long long t5 = clock64();
+    __shared__ unsigned s[64]; s[threadIdx.x & 63] = 0; __syncthreads();
+    long long t6 = clock64(); unsigned q = 0;
+    for (int r = 0; r < reps; ++r) q = s[(q + r) & 63] + 1;
+    long long t7 = clock64();
+    __shared__ unsigned short h[64]; h[threadIdx.x & 63] = 0xffff; __syncthreads();
+    long long t8 = clock64();
+    for (int r = 0; r < reps; ++r) q += atomicCAS(&h[(threadIdx.x * 2) & 63], (unsigned short)0xffff, (unsigned short)r);
+    long long t9 = clock64();
+    if (threadIdx.x == 0) { out[0] = (t1 - t0) / reps; out[1] = (t3 - t2) / reps; out[2] = (t5 - t4) / reps; out[3] = (t7 - t6) / reps; out[4] = (t9 - t8) / reps; *sink = v + w + b + q; }
+}
+int main() {
+    const int N = 1 << 16;   // 256 KB chain: L2-resident, larger than nothing else
+    unsigned* h = new unsigned[N]; for (int i = 0; i < N; ++i) h[i] = (unsigned)((i * 40503u + 12345u) % N);
+    unsigned* d; long long* o; unsigned* sink; float4* src; float* fs;
+    cudaMalloc(&d, N * 4); cudaMalloc(&o, 64); cudaMalloc(&sink, 4); cudaMalloc(&src, 4096 * 16 + 8192); cudaMalloc(&fs, 4);
+    cudaMemcpy(d, h, N * 4, cudaMemcpyHostToDevice); cudaMemset(src, 0, 4096 * 16 + 8192);
+    long long r[8];
+    chase<<<1, 1>>>(d, 2000, o, sink); chase<<<1, 1>>>(d, 4000, o, sink); cudaMemcpy(r, o, 8, cudaMemcpyDeviceToHost);
+    printf("ld.global.cg dependent chase (L2): %lld cycles\n", r[0]);
+    for (int bytes : {16, 256, 1024, 8192}) { bulk_lat<<<1, 32>>>(src, o, bytes, 200, fs); cudaMemcpy(r, o, 8, cudaMemcpyDeviceToHost); printf("cp.async.bulk %5d B issue->mbarrier observed: %lld cycles\n", bytes, r[0]); }
+    for (int t : {64, 256, 1024}) { bar_lat<<<1, t>>>(o, 1000); cudaMemcpy(r, o, 8, cudaMemcpyDeviceToHost); printf("__syncthreads %4d threads: %lld cycles\n", t, r[0]); }
+    redux_lat<<<1, 32>>>(o, 1000, sink); cudaMemcpy(r, o, 40, cudaMemcpyDeviceToHost);
+    printf("redux.min %lld, shfl %lld, ballot %lld, lds %lld, smem atomicCAS16 %lld cycles (dependent)\n", r[0], r[1], r[2], r[3], r[4]);
+    printf("status %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+    return 0;
+}
