@@ -46,6 +46,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            return int(json.load(f)["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -294,7 +304,8 @@ def run_ours(args):
             "single_frame_latency_ms": {"median": statistics.median(lat), "min": min(lat), "stage_ms": {k: round(v, 4) for k, v in solo_stage.items()}},
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
             "roofline": {"bound": "hbm", "kernel": "merge_fast_kernel (K7, one persistent CTA per frame; latency-bound serial replay, see DESIGN.md)",
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": load_traffic(), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(alg_bytes),
                          "merge_path": int(counts.merge_path),
                          "e2e_algorithmic_bytes": e2e_bytes,
                          "e2e_achieved_gbs": e2e_bytes / t_frame / 1e9 if t_frame > 0 else 0.0,

@@ -703,7 +703,7 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
             if (ctx->h_sc->mctl.error == 0) break;
             fast = false;
         }
-        LAUNCH(ctx, dense_label_kernel, 1, 1, 0, ctx->R1, SC(xctl.n_sv), ctx->run_start.as<unsigned>(), ctx->run_end.as<unsigned>(), ctx->run_out_off.as<unsigned>(),
+        LAUNCH(ctx, dense_label_kernel, 1, 1024, 0, ctx->R1, SC(xctl.n_sv), ctx->run_start.as<unsigned>(), ctx->run_end.as<unsigned>(), ctx->run_out_off.as<unsigned>(),
                ctx->run_dense.as<unsigned>(), ctx->region_dense.as<unsigned>(), SC(n_out));
         if (P) LAUNCH(ctx, labeled_cloud_kernel, grid_for(P, 256), 256, 0, ctx->pos_run.as<unsigned>(), P, ctx->order, ctx->run_start.as<unsigned>(),
                       ctx->run_out_off.as<unsigned>(), ctx->run_dense.as<unsigned>(), ctx->gxyz, ctx->out_xyz.as<float>(), ctx->out_label.as<unsigned>(),

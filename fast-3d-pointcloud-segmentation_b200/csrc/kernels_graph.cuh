@@ -177,22 +177,33 @@ __global__ void __launch_bounds__(128) edge_delta_kernel(const unsigned long lon
     }
 }
 
-// Clustering::deltas_mean over the ascending-sorted deltas (two chains: thread 0 -> c, thread 32 -> g),
-// then lambda = mean_g / (mean_c + mean_g)  (init_merging_parameters, ADAPTIVE_LAMBDA)
-__global__ void adaptive_lambda_kernel(const unsigned* __restrict__ sorted_dc, const unsigned* __restrict__ sorted_dg,
-                                       const unsigned* __restrict__ n_edges_ptr, float* __restrict__ lambda_out) {
+// Clustering::deltas_mean over the ascending-sorted deltas (src/clustering.cpp:515-528): one warp per distribution;
+// the warp stages 32 deltas and their reciprocals 1/count in shared memory (next chunk prefetched meanwhile) and
+// lane 0 runs the dependent chain mean += (1/count)(delta - mean).  Then lambda = mean_g / (mean_c + mean_g)
+// (init_merging_parameters, ADAPTIVE_LAMBDA).
+__global__ void __launch_bounds__(64) adaptive_lambda_kernel(const unsigned* __restrict__ sorted_dc, const unsigned* __restrict__ sorted_dg,
+                                                             const unsigned* __restrict__ n_edges_ptr, float* __restrict__ lambda_out) {
+    __shared__ float s_val[2][2][32], s_inv[2][2][32];
     __shared__ float s_mean[2];
     const unsigned n = *n_edges_ptr;
-    if (threadIdx.x == 0 || threadIdx.x == 32) {
-        const unsigned* src = threadIdx.x == 0 ? sorted_dc : sorted_dg;
-        float count = 0, mean_d = 0;
-        for (unsigned i = 0; i < n; ++i) {
-            const float delta = __uint_as_float(src[i]);
-            count = count + 1.0f;
-            mean_d = mean_d + (1 / count) * (delta - mean_d);
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned* src = w == 0 ? sorted_dc : sorted_dg;
+    float mean_d = 0.0f;
+    float v = lane < n ? __uint_as_float(src[lane]) : 0.0f;
+    int buf = 0;
+    for (unsigned base = 0; base < n; base += 32, buf ^= 1) {
+        s_val[w][buf][lane] = v; s_inv[w][buf][lane] = 1 / (float)(base + lane + 1);     // count = count + 1.0f is exact here
+        const unsigned nxt = base + 32 + lane;
+        v = nxt < n ? __uint_as_float(src[nxt]) : 0.0f;
+        __syncwarp();
+        if (lane == 0) {
+            const int m = (int)min(32u, n - base);
+#pragma unroll 8
+            for (int j = 0; j < m; ++j) mean_d = mean_d + s_inv[w][buf][j] * (s_val[w][buf][j] - mean_d);
         }
-        s_mean[threadIdx.x >> 5] = mean_d;
+        __syncwarp();
     }
+    if (lane == 0) s_mean[w] = mean_d;
     __syncthreads();
     if (threadIdx.x == 0) *lambda_out = s_mean[1] / (s_mean[0] + s_mean[1]);
 }

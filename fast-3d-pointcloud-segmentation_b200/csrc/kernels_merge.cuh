@@ -210,23 +210,50 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R,
 }
 
 // ---- result extraction: Clustering::get_labeled_cloud (:640-663) ---------------------------------
-// dense labels 0..K-1 in ascending region label order; output offset of every run of every rope
-__global__ void dense_label_kernel(RegionArrays R, const unsigned* __restrict__ n_sv_ptr, const unsigned* __restrict__ run_start,
+// dense labels 0..K-1 in ascending region label order; output offset of every run of every rope.
+// One block: two exclusive scans over the regions (alive flag -> dense label, voxel count -> output offset), then one
+// thread per surviving region walks its rope.
+__global__ void __launch_bounds__(1024) dense_label_kernel(RegionArrays R, const unsigned* __restrict__ n_sv_ptr, const unsigned* __restrict__ run_start,
         const unsigned* __restrict__ run_end, unsigned* __restrict__ run_out_off, unsigned* __restrict__ run_dense,
         unsigned* __restrict__ region_dense, unsigned* __restrict__ n_out) {
-    if (threadIdx.x || blockIdx.x) return;
+    __shared__ unsigned s_wa[32], s_wn[32];
+    __shared__ unsigned s_ca, s_cn;
     const unsigned S = *n_sv_ptr;
-    unsigned dense = 0, off = 0;
-    for (unsigned s = 0; s < S; ++s) {
-        if (R.n[s] <= 0) { region_dense[s] = 0xffffffffu; continue; }
-        region_dense[s] = dense;
-        for (int run = R.head[s]; run >= 0; run = R.next_run[run]) {
-            run_out_off[run] = off; run_dense[run] = dense;
-            off += run_end[run] - run_start[run];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_ca = 0; s_cn = 0; }
+    __syncthreads();
+    for (unsigned base = 0; base < S; base += blockDim.x) {
+        const unsigned s = base + threadIdx.x;
+        const int nv = s < S ? R.n[s] : 0;
+        const unsigned alive = nv > 0 ? 1u : 0u, cnt = nv > 0 ? (unsigned)nv : 0u;
+        unsigned ia = alive, in = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned ta = __shfl_up_sync(kFull, ia, o), tn = __shfl_up_sync(kFull, in, o);
+            if (lane >= o) { ia += ta; in += tn; }
         }
-        ++dense;
+        if (lane == 31) { s_wa[warp] = ia; s_wn[warp] = in; }
+        __syncthreads();
+        unsigned wa = 0, wn = 0;
+        for (int w = 0; w < warp; ++w) { wa += s_wa[w]; wn += s_wn[w]; }
+        const unsigned ca = s_ca, cn = s_cn;
+        if (s < S) {
+            if (!alive) region_dense[s] = 0xffffffffu;
+            else {
+                const unsigned dense = ca + wa + ia - 1u;
+                unsigned off = cn + wn + in - cnt;
+                region_dense[s] = dense;
+                for (int run = R.head[s]; run >= 0; run = R.next_run[run]) {
+                    run_out_off[run] = off; run_dense[run] = dense;
+                    off += run_end[run] - run_start[run];
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) { s_ca = ca + wa + ia; s_cn = cn + wn + in; }
+        __syncthreads();
     }
-    *n_out = off;
+    if (threadIdx.x == 0) *n_out = s_cn;
 }
 __global__ void __launch_bounds__(256) labeled_cloud_kernel(const unsigned* __restrict__ pos_run, unsigned n_pos, const unsigned* __restrict__ order,
         const unsigned* __restrict__ run_start, const unsigned* __restrict__ run_out_off, const unsigned* __restrict__ run_dense,
