@@ -40,9 +40,18 @@ inline int bits_for(unsigned maxval) { int b = 1; while ((maxval >> b) != 0 && b
         F3PS_CUDA_OK(cudaPeekAtLastError());                                                \
     } while (0)
 
+// Wait for the handle's stream.  Spinning (cudaStreamSynchronize) has the lowest latency for one frame; a sweep with more
+// frames in flight than host cores must sleep instead (blocking event), or the spinning waiters starve the launching threads.
+cudaError_t wait_stream(f3ps_ctx* ctx) {
+    if (!ctx->blocking_wait) return cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaEventRecord(ctx->ev_wait, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->ev_wait);
+}
+
 int pull_scalars(f3ps_ctx* ctx) {
     F3PS_CUDA_OK(cudaMemcpyAsync(ctx->h_sc, ctx->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->stream));
-    F3PS_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    F3PS_CUDA_OK(wait_stream(ctx));
     return F3PS_OK;
 }
 #define SC(field) (&ctx->d_sc->field)
@@ -227,6 +236,7 @@ int f3ps_create(int device, void* stream, f3ps_ctx** out) {
     ok = ok && lut_bytes == 33 * 33 * 33 * 3 * 2 && cudaMalloc(&ctx->d_lab_lut, lut_bytes) == cudaSuccess &&
          cudaMemcpy(ctx->d_lab_lut, f3ps_lab_lut_begin, lut_bytes, cudaMemcpyHostToDevice) == cudaSuccess;
     for (int i = 0; i < f3ps_ctx::kEvents && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { f3ps_destroy(ctx); return F3PS_ERR_CUDA; }
     cudaMemset(ctx->d_sc, 0, sizeof(DevScalars));
     memset(ctx->h_sc, 0, sizeof(DevScalars));
@@ -253,6 +263,7 @@ void f3ps_destroy(f3ps_ctx* ctx) {
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->d_lab_lut) cudaFree(ctx->d_lab_lut);
     for (int i = 0; i < f3ps_ctx::kEvents; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->ev_wait) cudaEventDestroy(ctx->ev_wait);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -300,7 +311,7 @@ int f3ps_set_input(f3ps_ctx* ctx, const void* points, int64_t n, int stride, int
 
 int f3ps_sync(f3ps_ctx* ctx) {
     if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
-    F3PS_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    F3PS_CUDA_OK(wait_stream(ctx));
     return F3PS_OK;
 }
 
@@ -718,6 +729,12 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
     return F3PS_OK;
 }
 
+int f3ps_set_blocking_wait(f3ps_ctx* ctx, int blocking) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    ctx->blocking_wait = blocking != 0;
+    return F3PS_OK;
+}
+
 int f3ps_set_merge_kernel(f3ps_ctx* ctx, int which) {
     if (!ctx || (which != 0 && which != 2)) return F3PS_ERR_INVALID_ARGUMENT;
     ctx->force_general_merge = which == 2;
@@ -778,7 +795,7 @@ int d2h(f3ps_ctx* ctx, void* dst, const void* src, size_t bytes) {
     F3PS_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return F3PS_OK;
 }
-int fin(f3ps_ctx* ctx) { F3PS_CUDA_OK(cudaStreamSynchronize(ctx->stream)); return F3PS_OK; }
+int fin(f3ps_ctx* ctx) { F3PS_CUDA_OK(wait_stream(ctx)); return F3PS_OK; }
 int cap_check(f3ps_ctx* ctx, int64_t need_n, int64_t capacity) {
     if (capacity < need_n) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "output capacity too small");
     return F3PS_OK;

@@ -70,7 +70,7 @@ def lib():
         "f3ps_set_input": (C.c_int, [vp, vp, i64, C.c_int, C.c_int]),
         "f3ps_voxelize": (C.c_int, [vp]), "f3ps_neighbors": (C.c_int, [vp]), "f3ps_normals": (C.c_int, [vp]),
         "f3ps_seeds": (C.c_int, [vp]), "f3ps_expand": (C.c_int, [vp]), "f3ps_graph": (C.c_int, [vp]),
-        "f3ps_merge": (C.c_int, [vp, f32]), "f3ps_set_merge_kernel": (C.c_int, [vp, C.c_int]), "f3ps_extract": (C.c_int, [vp]), "f3ps_run": (C.c_int, [vp, f32]),
+        "f3ps_merge": (C.c_int, [vp, f32]), "f3ps_set_merge_kernel": (C.c_int, [vp, C.c_int]), "f3ps_set_blocking_wait": (C.c_int, [vp, C.c_int]), "f3ps_extract": (C.c_int, [vp]), "f3ps_run": (C.c_int, [vp, f32]),
         "f3ps_sync": (C.c_int, [vp]),
         "f3ps_set_graph": (C.c_int, [vp, i64, vp, vp, i32, vp, vp, vp, vp, i64, vp]),
         "f3ps_get_counts": (C.c_int, [vp, C.POINTER(Counts)]),
@@ -111,7 +111,7 @@ def lib():
 
 EXPORTED = ["f3ps_create", "f3ps_destroy", "f3ps_last_error", "f3ps_version", "f3ps_set_vccs_params",
             "f3ps_set_merge_params", "f3ps_set_input", "f3ps_voxelize", "f3ps_neighbors", "f3ps_normals", "f3ps_seeds",
-            "f3ps_expand", "f3ps_graph", "f3ps_merge", "f3ps_set_merge_kernel", "f3ps_extract", "f3ps_run", "f3ps_sync", "f3ps_set_graph",
+            "f3ps_expand", "f3ps_graph", "f3ps_merge", "f3ps_set_merge_kernel", "f3ps_set_blocking_wait", "f3ps_extract", "f3ps_run", "f3ps_sync", "f3ps_set_graph",
             "f3ps_get_counts", "f3ps_get_voxel_keys", "f3ps_get_voxel_centroids", "f3ps_get_point_voxel",
             "f3ps_get_voxel_neighbors", "f3ps_get_voxel_normals", "f3ps_get_seeds", "f3ps_get_voxel_labels",
             "f3ps_get_supervoxels", "f3ps_get_supervoxel_voxels", "f3ps_get_adjacency", "f3ps_get_edges", "f3ps_get_cdf",
@@ -186,6 +186,7 @@ class Segmenter:
     def graph(self): self._chk(self.L.f3ps_graph(self.h))
     def merge(self, threshold): self._chk(self.L.f3ps_merge(self.h, threshold))
     def set_merge_kernel(self, which): self._chk(self.L.f3ps_set_merge_kernel(self.h, which))
+    def set_blocking_wait(self, on): self._chk(self.L.f3ps_set_blocking_wait(self.h, int(on)))
     def extract(self): self._chk(self.L.f3ps_extract(self.h))
     def run(self, threshold=0.2): self._chk(self.L.f3ps_run(self.h, threshold))
     def sync(self): self._chk(self.L.f3ps_sync(self.h))

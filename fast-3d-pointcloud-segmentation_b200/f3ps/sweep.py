@@ -39,9 +39,12 @@ class FramePool:
         from . import binding
         import threading
         self.segs = [binding.Segmenter(device=device) for _ in range(n_handles)]
+        import os
+        blocking = n_handles > max(1, (os.cpu_count() or 1) // 2)     # spinning waiters must not outnumber the cores
         for s in self.segs:
             s.set_vccs_params(**(vccs or {}))
             s.set_merge_params(**(merge or {}))
+            s.set_blocking_wait(blocking)
         self.threshold = threshold
         self._threading = threading
 

@@ -105,6 +105,9 @@ int f3ps_seeds(f3ps_ctx* ctx);      /* K4 selectInitialSupervoxelSeeds */
 int f3ps_expand(f3ps_ctx* ctx);     /* K5 expandSupervoxels */
 int f3ps_graph(f3ps_ctx* ctx);      /* K6 makeSupervoxels + getSupervoxelAdjacency + set_initialstate + init_weights */
 int f3ps_merge(f3ps_ctx* ctx, float threshold); /* K7 Clustering::cluster(threshold): restarts from the initial state */
+/* How the host waits where it needs a size from the device: 0 = spin (lowest latency, the default), 1 = sleep on a
+ * blocking event.  Sweeps that keep more frames in flight than there are host cores must use 1. */
+int f3ps_set_blocking_wait(f3ps_ctx* ctx, int blocking);
 /* which K7 kernel f3ps_merge uses: 0 = automatic (resident when the graph fits one SM, else general), 2 = always general.
  * Both replay the same merge sequence; the switch exists for tests and profiling. */
 int f3ps_set_merge_kernel(f3ps_ctx* ctx, int which);
