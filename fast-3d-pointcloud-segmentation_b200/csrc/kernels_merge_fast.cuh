@@ -3,7 +3,7 @@
 // working set lives on the SM (SURVEY.md Appendix C for the replay rules):
 //
 //   edges         registers of 25 "owner" warps: order key (weight bits, 32-bit tie stamp) + packed (a,b);
-//                 edge e belongs to owner thread e % 800, slot e / 800
+//                 owner warp w holds edges [w*32*SLOTS, (w+1)*32*SLOTS): slot j, lane l = edge base + 32 j + l
 //   ropes / sizes shared memory (per region: head / tail / next run, run bounds, voxel count)
 //   voxels        position-ordered float4 (x,y,z,rgba) array in HBM/L2; the runs of region b are brought
 //                 into a shared-memory stage by cp.async.bulk (one elected thread, mbarrier completion)
@@ -68,8 +68,10 @@ struct FastSmem {
     float* dc;                               // colour delta of every edge (owner-managed), valid for the current colour vectors of both ends
     unsigned *wm_hi, *wm_lo, *wm_e, *wm_ab;
     float* newgeo;                           // cvec[3], centroid[3], normal[3]
+    unsigned* prof;                          // owner-side cycle counters (one lane)
     int* misc;                               // tcount, ealive, ralive, counter, nd, nanw, error, maxt
     unsigned *rs, *re; int* n;
+    unsigned* wmask;                         // per region: owner warps that hold an edge incident to it (superset)
     unsigned short *head, *tail, *next, *mark, *partner; unsigned char* cls;
     size_t bytes;
     __host__ __device__ FastSmem(char* base, unsigned S, unsigned E_cap) {
@@ -82,8 +84,9 @@ struct FastSmem {
         te_dc = (float*)take(kFastMaxTouched * 4); te_ce = (float4*)take(kFastMaxTouched * 16); te_nr = (float4*)take(kFastMaxTouched * 16);
         need = (unsigned short*)take(kFastMaxTouched * 2); dc = (float*)take((size_t)E_cap * 4);
         wm_hi = (unsigned*)take(32 * 4); wm_lo = (unsigned*)take(32 * 4); wm_e = (unsigned*)take(32 * 4); wm_ab = (unsigned*)take(32 * 4);
-        newgeo = (float*)take(16 * 4); misc = (int*)take(16 * 4);
+        newgeo = (float*)take(16 * 4); misc = (int*)take(16 * 4); prof = (unsigned*)take(16 * 4);
         rs = (unsigned*)take((size_t)S * 4); re = (unsigned*)take((size_t)S * 4); n = (int*)take((size_t)S * 4);
+        wmask = (unsigned*)take((size_t)S * 4);
         head = (unsigned short*)take((size_t)S * 2); tail = (unsigned short*)take((size_t)S * 2); next = (unsigned short*)take((size_t)S * 2);
         mark = (unsigned short*)take((size_t)S * 2); partner = (unsigned short*)take(kFastMaxTouched * 2);
         cls = (unsigned char*)take(kFastMaxTouched);
@@ -169,10 +172,9 @@ __device__ __forceinline__ FastHead fast_head(const FastSmem& sm, int lane) {
 
 enum { FC_KEEP = 0, FC_FRONT = 1, FC_BACK = 2, FC_DUP = 3, FC_REUSE = 0x10 };
 enum { BAR_TOUCHED = 1, BAR_STAGE = 2, BAR_FOLDED = 3, BAR_RESULTS = 4, BAR_DELTA = 5 };
-__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
-    __threadfence_block();
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
+// producer side of a named barrier: the barrier itself orders the producer's earlier shared / global writes before the
+// consumers' reads after their bar.sync (PTX: barrier instructions order prior accesses among the participants)
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // delta_c of Clustering::delta_c_g (src/clustering.cpp:113-122) on two colour vectors, first argument = smaller label.
 // One copy of the FP64 code in the kernel (the instruction cache, not the FP64 pipe, bounds a replicated version).
@@ -207,16 +209,17 @@ __global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(FastArgs A)
         sm.rs[s] = A.run_start[s]; sm.re[s] = A.run_end[s]; sm.n[s] = R.n[s];
         const int h = R.head[s], t = R.tail[s], nx = R.next_run[s];
         sm.head[s] = (unsigned short)(h < 0 ? kNil16 : (unsigned)h); sm.tail[s] = (unsigned short)(t < 0 ? kNil16 : (unsigned)t);
-        sm.next[s] = (unsigned short)(nx < 0 ? kNil16 : (unsigned)nx); sm.mark[s] = (unsigned short)kNil16;
+        sm.next[s] = (unsigned short)(nx < 0 ? kNil16 : (unsigned)nx); sm.mark[s] = (unsigned short)kNil16; sm.wmask[s] = 0u;
     }
     for (int i = tid; i < kFastHash; i += kFastThreads) { sm.hkey[i] = kDeadKey; sm.hcnt[i] = 0u; }
     if (tid == 0) {
-        for (int i = 0; i < 16; ++i) sm.misc[i] = 0;
+        for (int i = 0; i < 16; ++i) { sm.misc[i] = 0; sm.prof[i] = 0u; }
         sm.misc[FM_EALIVE] = (int)nE; sm.misc[FM_RALIVE] = (int)S; sm.misc[FM_COUNTER] = (int)nE;
         mbar_init(mbar, 1u);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     unsigned n_merges = 0;
+    __syncthreads();                                          // tables initialised (the owners add to wmask[] next)
 
     if (warp == 0) {
         // =========== covariance sums + xyz sums: lanes 0..8 each continue one accumulator of region a over b's voxels =====
@@ -386,6 +389,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(FastArgs A)
             if (lane == 0) {
                 sm.next[sm.tail[a]] = sm.head[b]; sm.tail[a] = sm.tail[b];
                 sm.n[a] = na + nb; sm.n[b] = 0;
+                sm.wmask[a] |= sm.wmask[b];                    // b's edges now name a (every owner read the masks before BAR_TOUCHED)
             }
         }
     } else if (warp < kFastRoleWarps) {
@@ -606,24 +610,33 @@ __global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(FastArgs A)
 #undef FPHASE
     } else {
         // =========== owners: the weight map itself, in registers =====
-        const int o = tid - 32 * kFastRoleWarps;
+        // Blocked assignment: owner warp w holds edges [w * 32 * SLOTS, (w + 1) * 32 * SLOTS), slot j / lane l = edge
+        // base + 32 j + l.  The initial edges are sorted by (a, b), so the edges of a region sit in one or two warps (plus
+        // the warps of its lower-labelled neighbours); wmask[] lets every other warp skip the scan of a merge entirely.
+        const int ow = warp - kFastRoleWarps;                                               // 0..24
+        const unsigned ebase = (unsigned)ow * 32u * SLOTS + (unsigned)lane;
         unsigned khi[SLOTS], klo[SLOTS], kab[SLOTS];
         unsigned pending = 0;                                 // slots whose new key is waiting in res_*[klo[slot]]
 #pragma unroll
         for (int j = 0; j < SLOTS; ++j) {
             khi[j] = kDeadKey; klo[j] = kDeadKey; kab[j] = 0xffffffffu;
-            const unsigned e = (unsigned)j * kFastOwners + (unsigned)o;
+            const unsigned e = ebase + 32u * j;
             if (e < nE && A.E.stamp[e] != kDeadStamp) {
                 const float w = A.E.w[e];
                 khi[j] = isnan(w) ? 0x7f800000u : __float_as_uint(w);
                 klo[j] = (unsigned)(int)A.E.stamp[e] ^ 0x80000000u;
-                kab[j] = (A.E.a[e] << 16) | A.E.b[e];
+                const unsigned ea = A.E.a[e], eb = A.E.b[e];
+                kab[j] = (ea << 16) | eb;
                 sm.dc[e] = A.E.dc[e];
+                atomicOr(&sm.wmask[ea], 1u << ow); atomicOr(&sm.wmask[eb], 1u << ow);
             }
         }
         bool dirty = true;
         unsigned l_hi = kDeadKey, l_lo = kDeadKey, l_ab = 0xffffffffu; int l_slot = 0;
+        const bool probe = ow == 0 && lane == 0;
+#define OPROF(i) do { if (probe) { const unsigned t_ = (unsigned)clock(); sm.prof[i] += t_ - sm.prof[15]; sm.prof[15] = t_; } } while (0)
         __syncthreads();
+        if (probe) sm.prof[15] = (unsigned)clock();
         while (true) {
             // ---- take the previous merge's results, local minimum, warp minimum ----
             if (pending) {                                     // a new key below the cached minimum replaces it; the minimum's own slot
@@ -632,7 +645,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(FastArgs A)
                     if (pending & (1u << j)) {
                         const unsigned p = klo[j];
                         khi[j] = sm.res_hi[p]; klo[j] = sm.res_lo[p]; kab[j] = khi[j] == kDeadKey ? 0xffffffffu : sm.res_ab[p];
-                        sm.dc[(unsigned)j * kFastOwners + (unsigned)o] = sm.te_dc[p];
+                        sm.dc[ebase + 32u * j] = sm.te_dc[p];
                         if (j == l_slot) dirty = true;
                         else if (key_less32(khi[j], klo[j], l_hi, l_lo)) { l_hi = khi[j]; l_lo = klo[j]; l_ab = kab[j]; l_slot = j; }
                     }
@@ -648,63 +661,67 @@ __global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(FastArgs A)
             {
                 unsigned m_hi, m_lo;
                 const int win = warp_argmin(l_hi, l_lo, m_hi, m_lo);
-                if (lane == win) {
-                    const int w = warp - kFastRoleWarps;
-                    sm.wm_hi[w] = m_hi; sm.wm_lo[w] = m_lo; sm.wm_e[w] = ((unsigned)l_slot << 16) | (unsigned)o; sm.wm_ab[w] = l_ab;
-                }
+                OPROF(0);
+                if (lane == win) { sm.wm_hi[ow] = m_hi; sm.wm_lo[ow] = m_lo; sm.wm_e[ow] = ((unsigned)l_slot << 16) | (unsigned)(ow * 32 + lane); sm.wm_ab[ow] = l_ab; }
             }
             __syncthreads();                                                                   // B1
+            OPROF(1);
             const FastHead hd = fast_head(sm, lane);
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;   // strict <, src/clustering.cpp:388-389
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
-            if ((hd.e & 0xffffu) == (unsigned)o) {                                             // the head edge leaves the map
-                const int hs = (int)(hd.e >> 16);
+            OPROF(2);
+            if (((sm.wmask[a] | sm.wmask[b]) >> ow) & 1u) {                                    // warp-uniform: does this warp hold an incident edge?
+                if ((hd.e & 0xffffu) == (unsigned)(ow * 32 + lane)) {                          // the head edge leaves the map
+                    const int hs = (int)(hd.e >> 16);
 #pragma unroll
-                for (int j = 0; j < SLOTS; ++j) if (j == hs) { khi[j] = kDeadKey; klo[j] = kDeadKey; kab[j] = 0xffffffffu; }
-                dirty = true;
-            }
-            // ---- edges incident to a or b: both ends of a slot compared at once (dead slots hold 0xffff:0xffff) ----
-            const unsigned aa = a * 0x10001u, bb = b * 0x10001u;
-            unsigned hits = 0;
+                    for (int j = 0; j < SLOTS; ++j) if (j == hs) { khi[j] = kDeadKey; klo[j] = kDeadKey; kab[j] = 0xffffffffu; }
+                    dirty = true;
+                }
+                // ---- edges incident to a or b: both ends of a slot compared at once (dead slots hold 0xffff:0xffff) ----
+                const unsigned aa = a * 0x10001u, bb = b * 0x10001u;
+                unsigned hits = 0;
 #pragma unroll
-            for (int j = 0; j < SLOTS; ++j) hits |= ((__vcmpeq2(kab[j], aa) | __vcmpeq2(kab[j], bb)) != 0u ? 1u : 0u) << j;
-            __syncwarp();
-            if (__any_sync(kFull, hits != 0u)) {
-                const int cnt = __popc(hits);
-                int incl = cnt;
+                for (int j = 0; j < SLOTS; ++j) hits |= ((__vcmpeq2(kab[j], aa) | __vcmpeq2(kab[j], bb)) != 0u ? 1u : 0u) << j;
+                if (__any_sync(kFull, hits != 0u)) {
+                    const int cnt = __popc(hits);
+                    int incl = cnt;
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(kFull, incl, off); if (lane >= off) incl += t; }
-                int base = 0;
-                if (lane == 31) base = atomicAdd(&sm.misc[FM_TCOUNT], incl);
-                int p = __shfl_sync(kFull, base, 31) + incl - cnt;
+                    for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(kFull, incl, off); if (lane >= off) incl += t; }
+                    int base = 0;
+                    if (lane == 31) base = atomicAdd(&sm.misc[FM_TCOUNT], incl);
+                    int p = __shfl_sync(kFull, base, 31) + incl - cnt;
 #pragma unroll
-                for (int j = 0; j < SLOTS; ++j) {
-                    if (!((hits >> j) & 1u)) continue;
-                    if (p < kFastMaxTouched) {
-                        const unsigned ea = kab[j] >> 16, eb = kab[j] & 0xffffu;
-                        const bool on_a = ea == a || eb == a;
-                        const unsigned x = (ea == a || ea == b) ? eb : ea;
-                        sm.te_hi[p] = khi[j]; sm.te_lo[p] = klo[j]; sm.te_x[p] = x | (on_a ? 0x10000u : 0u);
-                        sm.te_dc[p] = sm.dc[(unsigned)j * kFastOwners + (unsigned)o];
-                        sm.partner[p] = (unsigned short)kNil16;
-                        klo[j] = (unsigned)p; pending |= 1u << j;
+                    for (int j = 0; j < SLOTS; ++j) {
+                        if (!((hits >> j) & 1u)) continue;
+                        if (p < kFastMaxTouched) {
+                            const unsigned ea = kab[j] >> 16, eb = kab[j] & 0xffffu;
+                            const bool on_a = ea == a || eb == a;
+                            const unsigned x = (ea == a || ea == b) ? eb : ea;
+                            sm.te_hi[p] = khi[j]; sm.te_lo[p] = klo[j]; sm.te_x[p] = x | (on_a ? 0x10000u : 0u);
+                            sm.te_dc[p] = sm.dc[ebase + 32u * j];
+                            sm.partner[p] = (unsigned short)kNil16;
+                            klo[j] = (unsigned)p; pending |= 1u << j;
+                        }
+                        ++p;
                     }
-                    ++p;
                 }
             }
             __syncwarp();
+            OPROF(3);
             bar_arrive(BAR_TOUCHED, kFastOwners + kFastDeltaThreads);
-            if (o == 0 && n_merges < A.log_cap) {                                              // debug line of :390-392 (ranks; labels at the end)
+            if (ow == 0 && lane == 0 && n_merges < A.log_cap) {                                // debug line of :390-392 (ranks; labels at the end)
                 A.mlog.a[n_merges] = a; A.mlog.b[n_merges] = b; A.mlog.w[n_merges] = __uint_as_float(hd.hi);
                 A.mlog.edges_left[n_merges] = (unsigned)sm.misc[FM_EALIVE]; A.mlog.regions_left[n_merges] = (unsigned)sm.misc[FM_RALIVE];
             }
             named_bar(BAR_RESULTS, kFastOwners + kFastDeltaThreads);                           // new keys are in res_*
+            OPROF(4);
             ++n_merges;
         }
+#undef OPROF
         // ---- write the weight map back ----
 #pragma unroll
         for (int j = 0; j < SLOTS; ++j) {
-            const unsigned e = (unsigned)j * kFastOwners + (unsigned)o;
+            const unsigned e = ebase + 32u * j;
             if (e >= nE) continue;
             if (khi[j] == kDeadKey && klo[j] == kDeadKey) A.E.stamp[e] = kDeadStamp;
             else {
@@ -727,6 +744,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(FastArgs A)
     for (unsigned m = tid; m < n_merges && m < A.log_cap; m += kFastThreads) { A.mlog.a[m] = A.sv_label[A.mlog.a[m]]; A.mlog.b[m] = A.sv_label[A.mlog.b[m]]; }
     if (tid == 0) {
         MergeCtl* ctl = A.ctl;
+        for (int i = 0; i < 4; ++i) ctl->phase_cycles[20 + i] = sm.prof[i];
+        ctl->phase_cycles[28] = sm.prof[4];
         ctl->phase_cycles[24] = (unsigned long long)sm.misc[FM_MISS]; ctl->phase_cycles[25] = (unsigned long long)sm.misc[FM_EVALS];
         ctl->phase_cycles[26] = (unsigned long long)sm.misc[FM_BIGT]; ctl->phase_cycles[27] = (unsigned long long)sm.misc[FM_SUMT];
         ctl->n_merges = n_merges; ctl->edges_alive = (unsigned)sm.misc[FM_EALIVE]; ctl->regions_alive = (unsigned)sm.misc[FM_RALIVE];

@@ -228,9 +228,9 @@ class Segmenter:
         v = list(a)
         if self.counts().merge_path == 1:      # resident kernel (see include/f3ps.h)
             return {"delta": dict(zip(["head", "wait_touched", "order_dedupe_small", "spec_ciede", "wait_fold", "miss_ciede", "weights_stamps", "order_dedupe_big"], v[0:8])),
-                    "owner": dict(zip(["apply_argmin", "b1_head", "scan_publish", "wait_results"], v[8:12])),
-                    "mean": dict(zip(["wait_voxels", "fold", "lab_publish"], v[12:15])),
-                    "cov": dict(zip(["wait_voxels", "fold", "eigen_publish"], v[16:19])),
+                    "owner": dict(zip(["apply_argmin", "wait_b1", "head", "scan_publish", "wait_results"], v[20:24] + [v[28]])),
+                    "mean": dict(zip(["wait_voxels", "fold", "lab_publish", "wait_b1"], v[12:16])),
+                    "cov": dict(zip(["wait_voxels", "fold", "eigen_publish", "wait_b1"], v[16:20])),
                     "guess_misses": v[24], "ciede_evals": v[25], "merges_T_gt_32": v[26], "sum_T": v[27]}
         return dict(zip(["argmin", "fold_scan", "order", "delta", "stamps"], v[:5]))
 

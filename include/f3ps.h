@@ -163,9 +163,9 @@ int f3ps_stage_ms(f3ps_ctx* ctx, int stage, float* ms);
 /* Profiling aid: SM cycles (clock64) the last f3ps_merge spent per phase, and event counts.
  * General kernel: [0..4] argmin, fold||edge scan, ordering, re-weighting, tie stamps (thread 0).
  * Resident kernel: [0..7] delta warps: head, wait for the touched list, order/dedupe, speculative CIEDE, wait for the
- * fold, CIEDE after a wrong guess, weights + stamps, -;  [8..11] an owner warp: apply + local argmin, B1 + head, scan + publish,
- * wait for results;  [12..15] colour-mean warp: wait for the voxels, fold, Lab + publish, -;  [16..19] covariance warp: wait,
- * fold, centroid + eigen-solve, -;  [24] wrong colour guesses, [25] CIEDE evaluations, [26] merges touching > 32 edges,
+ * fold, CIEDE after a wrong guess, weights + stamps, order/dedupe of the > 32-edge path;  [12..15] colour-mean warp: wait for
+ * the voxels, fold, Lab + publish, wait for the next head;  [16..19] covariance warp: same with centroid + eigen-solve;
+ * [20..23], [28] one owner lane: apply + local argmin, wait at the CTA barrier, head, scan + publish, wait for results;  [24] wrong colour guesses, [25] CIEDE evaluations, [26] merges touching > 32 edges,
  * [27] touched edges in total. */
 int f3ps_merge_profile(f3ps_ctx* ctx, uint64_t cycles[32]);
 /* nanoseconds the expansion kernel spent per phase: init, sweeps, count, scan, fill, centroid fold, tail, (spare) */

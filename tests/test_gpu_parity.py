@@ -229,6 +229,43 @@ def test_threshold_prefix_property_and_restart(gpu, oracle_mod, small_frame):
     assert np.array_equal(g.array("merges_ab"), full_ab)
 
 
+@pytest.mark.parametrize("mp", [AL, EQ, RGB_ML], ids=["cvx_al", "eq200", "rgb_ml"])
+def test_resident_and_general_merge_kernels_agree(gpu, vga_frame, small_frame, mp):
+    """K7 has two kernels (one SM with the weight map in registers / everything in global memory); both replay the
+    same sequence.  f3ps_set_merge_kernel(2) forces the general one."""
+    for pts, thr in ((small_frame, 0.2), (vga_frame, 0.2), (small_frame, 1.0)):
+        g = gpu.Segmenter(); g.set_vccs_params(); g.set_merge_params(**mp); g.set_input(pts); g.run(thr)
+        assert g.counts().merge_path == 1
+        fast = {n: g.array(n).copy() for n in MERGE_ARRAYS}
+        g.set_merge_kernel(2); g.merge(thr)
+        assert g.counts().merge_path == 2
+        for n in MERGE_ARRAYS:
+            assert same(fast[n], g.array(n)), n
+        g.set_merge_kernel(0); g.merge(thr)
+        assert g.counts().merge_path == 1
+        for n in MERGE_ARRAYS:
+            assert same(fast[n], g.array(n)), n
+
+
+def test_frames_in_flight_pool(gpu, oracle_mod, small_frame):
+    """FramePool: several handles / streams / host threads on one GPU give the same result per frame as one handle alone."""
+    from f3ps import sweep, synth
+    frames = [small_frame] + [synth.make_frame(seed=100 + i, width=160, height=120) for i in range(5)]
+    solo = []
+    g = gpu.Segmenter(); g.set_vccs_params(); g.set_merge_params(**AL)
+    for f in frames:
+        g.set_input(f); g.run(0.2)
+        solo.append((g.array("merges_ab").copy(), g.array("out_label").copy()))
+    for n_handles, blocking in ((3, False), (6, True)):
+        pool = sweep.FramePool(n_handles, merge=AL, threshold=0.2)
+        for s_ in pool.segs:
+            s_.set_blocking_wait(blocking)
+        got = pool.run(frames * 2, collect=lambda s_, k: (s_.array("merges_ab").copy(), s_.array("out_label").copy()))
+        pool.close()
+        for k, (ab, lab) in enumerate(got):
+            assert np.array_equal(ab, solo[k % len(frames)][0]) and np.array_equal(lab, solo[k % len(frames)][1])
+
+
 def test_set_graph_facade_path(gpu, oracle_mod, small_frame):
     """Clustering::set_initialstate on caller-supplied supervoxels (what the C++ facade does)."""
     o = oracle_mod.Oracle(); o.set_vccs_params(); o.set_merge_params(merge_impl=0, **AL); o.set_input(small_frame); o.run(0, 0.25)

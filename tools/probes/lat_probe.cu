@@ -52,6 +52,36 @@ __global__ void redux_lat(long long* out, int reps, unsigned* sink) {
     long long t9 = clock64();
     if (threadIdx.x == 0) { out[0] = (t1 - t0) / reps; out[1] = (t3 - t2) / reps; out[2] = (t5 - t4) / reps; out[3] = (t7 - t6) / reps; out[4] = (t9 - t8) / reps; *sink = v + w + b + q; }
 }
+__device__ __forceinline__ int warp_argmin(unsigned hi, unsigned lo, unsigned& m_hi, unsigned& m_lo) {
+    m_hi = __reduce_min_sync(0xffffffffu, hi);
+    m_lo = __reduce_min_sync(0xffffffffu, hi == m_hi ? lo : 0xffffffffu);
+    return __ffs(__ballot_sync(0xffffffffu, hi == m_hi && lo == m_lo)) - 1;
+}
+// the argmin skeleton of the merge kernel: 25 warps publish a partial minimum, one CTA barrier, every warp derives the head
+__global__ void head_loop(long long* out, int reps, unsigned* sink) {
+    __shared__ unsigned wm_hi[32], wm_lo[32], wm_e[32], wm_ab[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned l_hi = threadIdx.x * 2654435761u >> 4, l_lo = threadIdx.x, acc = 0;
+    if (threadIdx.x < 32) { wm_hi[lane] = wm_lo[lane] = 0xffffffffu; wm_e[lane] = wm_ab[lane] = 0; }
+    __syncthreads();
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+        if (warp >= 7) {
+            unsigned m_hi, m_lo; const int win = warp_argmin(l_hi, l_lo, m_hi, m_lo);
+            if (lane == win) { wm_hi[warp - 7] = m_hi; wm_lo[warp - 7] = m_lo; wm_e[warp - 7] = threadIdx.x; wm_ab[warp - 7] = l_hi ^ l_lo; }
+        }
+        __syncthreads();
+        unsigned h_hi, h_lo;
+        const unsigned hi = lane < 25 ? wm_hi[lane] : 0xffffffffu, lo = lane < 25 ? wm_lo[lane] : 0xffffffffu;
+        const int win = warp_argmin(hi, lo, h_hi, h_lo);
+        const unsigned e = wm_e[win], ab = wm_ab[win];
+        acc += e + ab;
+        if (threadIdx.x == e) l_hi += 977u;          // the head changes every round
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) out[0] = (t1 - t0) / reps;
+    sink[0] = acc;
+}
 int main() {
     const int N = 1 << 16;   // 256 KB chain: L2-resident, larger than nothing else
     unsigned* h = new unsigned[N]; for (int i = 0; i < N; ++i) h[i] = (unsigned)((i * 40503u + 12345u) % N);
@@ -65,6 +95,7 @@ int main() {
     for (int t : {64, 256, 1024}) { bar_lat<<<1, t>>>(o, 1000); cudaMemcpy(r, o, 8, cudaMemcpyDeviceToHost); printf("__syncthreads %4d threads: %lld cycles\n", t, r[0]); }
     redux_lat<<<1, 32>>>(o, 1000, sink); cudaMemcpy(r, o, 40, cudaMemcpyDeviceToHost);
     printf("redux.min %lld, shfl %lld, ballot %lld, lds %lld, smem atomicCAS16 %lld cycles (dependent)\n", r[0], r[1], r[2], r[3], r[4]);
+    head_loop<<<1, 1024>>>(o, 2000, sink); cudaMemcpy(r, o, 8, cudaMemcpyDeviceToHost); printf("argmin skeleton (publish + barrier + head in all 32 warps): %lld cycles per round\n", r[0]);
     printf("status %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
