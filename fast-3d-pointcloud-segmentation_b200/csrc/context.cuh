@@ -12,6 +12,7 @@
 #define F3PS_MERGE_ERR_TOUCHED 4u
 #include "kernels_merge.cuh"
 #include "kernels_merge_fast.cuh"
+#include "kernels_merge_cluster.cuh"
 
 namespace f3ps {
 
@@ -98,7 +99,8 @@ struct f3ps_ctx {
     f3ps::DevBuf pos_data_buf, merge_scratch;
     const float4* pos_data = nullptr;   // voxel (x,y,z,rgba) in position order (what the merge folds stream)
     int merge_path = 0;                 // 1 = resident kernel, 2 = general kernel (last f3ps_merge)
-    bool force_general_merge = false;   // test hook (F3PS_FORCE_GENERAL_MERGE=1)
+    bool force_general_merge = false;   // f3ps_set_merge_kernel(ctx, 2)
+    int merge_kernel_choice = 0;        // 0 auto, 1 resident single CTA, 2 general, 3 four-CTA cluster
     f3ps::MergeLog ML{};
     unsigned n_pos = 0;           // positions of the label-ordered voxel list
     const unsigned* order = nullptr;

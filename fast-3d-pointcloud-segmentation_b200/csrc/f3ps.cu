@@ -676,7 +676,13 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
         for (int sl : {4, 8, 12, 16}) if (!slots && (size_t)E <= (size_t)sl * kFastOwners) slots = sl;
         const unsigned E_cap = (unsigned)std::max(slots, 4) * kFastOwners;
         const size_t fast_bytes = FastSmem(nullptr, S_cap, E_cap).bytes;
-        bool fast = !ctx->force_general_merge && slots && S < 65535u && fast_bytes <= 227u * 1024u && P > 0;
+        int cl_slots = 0;
+        for (int sl : {2, 4, 6, 8}) if (!cl_slots && (size_t)E <= (size_t)sl * 2048u) cl_slots = sl;
+        const size_t cl_bytes = ClusterSmem(nullptr, S_cap, (unsigned)std::max(cl_slots, 2) * 1024u).bytes;
+        const bool cluster_ok = cl_slots && S < 65535u && cl_bytes <= 227u * 1024u && P > 0;
+        const bool single_ok = slots && S < 65535u && fast_bytes <= 227u * 1024u && P > 0;
+        const bool use_cluster = cluster_ok && ctx->merge_kernel_choice == 3;
+        bool fast = !ctx->force_general_merge && (use_cluster || single_ok);
         for (int attempt = 0; attempt < 2; ++attempt) {
             if (attempt == 1) {                                    // a merge overflowed the resident kernel's touched list: start over
                 F3PS_CUDA_OK(cudaMemcpyAsync(ctx->reg_work.p, ctx->reg_init.p, region_bytes(Sc), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -689,13 +695,28 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
                 A.R = ctx->R1; A.E = ctx->E1; A.n_edges_ptr = SC(n_edges); A.n_sv_ptr = SC(xctl.n_sv); A.ep = ep; A.lambda_dev = SC(lambda);
                 A.threshold = threshold; A.run_start = ctx->run_start.as<unsigned>(); A.run_end = ctx->run_end.as<unsigned>();
                 A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
-                A.ctl = SC(mctl); A.S_cap = S_cap; A.E_cap = E_cap;
-                void (*kern)(FastArgs) = slots == 4 ? merge_fast_kernel<4> : slots == 8 ? merge_fast_kernel<8> : slots == 12 ? merge_fast_kernel<12> : merge_fast_kernel<16>;
-                F3PS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // same value from every handle / thread
-                kern<<<1, kFastThreads, fast_bytes, ctx->stream>>>(A);
-                ctx->launches++;
-                F3PS_CUDA_OK(cudaPeekAtLastError());
-                ctx->merge_path = 1;
+                A.ctl = SC(mctl); A.S_cap = S_cap;
+                if (use_cluster) {
+                    A.E_cap = (unsigned)cl_slots * 2048u;
+                    void (*kern)(FastArgs) = cl_slots == 2 ? merge_cluster_kernel<2> : cl_slots == 4 ? merge_cluster_kernel<4> : cl_slots == 6 ? merge_cluster_kernel<6> : merge_cluster_kernel<8>;
+                    F3PS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(4); cfg.blockDim = dim3(kClThreads); cfg.dynamicSmemBytes = cl_bytes; cfg.stream = ctx->stream;
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                    cfg.attrs = attr; cfg.numAttrs = 1;
+                    F3PS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, A));
+                    ctx->launches++;
+                    ctx->merge_path = 3;
+                } else {
+                    A.E_cap = E_cap;
+                    void (*kern)(FastArgs) = slots == 4 ? merge_fast_kernel<4> : slots == 8 ? merge_fast_kernel<8> : slots == 12 ? merge_fast_kernel<12> : merge_fast_kernel<16>;
+                    F3PS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // same value from every handle / thread
+                    kern<<<1, kFastThreads, fast_bytes, ctx->stream>>>(A);
+                    ctx->launches++;
+                    F3PS_CUDA_OK(cudaPeekAtLastError());
+                    ctx->merge_path = 1;
+                }
             } else {
                 const size_t per = ((size_t)Ec * 4 + 255) & ~(size_t)255, per8 = ((size_t)Ec * 8 + 255) & ~(size_t)255;
                 F3PS_CUDA_OK(ctx->merge_scratch.ensure(6 * per + 2 * per8 + per));
@@ -736,8 +757,9 @@ int f3ps_set_blocking_wait(f3ps_ctx* ctx, int blocking) {
 }
 
 int f3ps_set_merge_kernel(f3ps_ctx* ctx, int which) {
-    if (!ctx || (which != 0 && which != 2)) return F3PS_ERR_INVALID_ARGUMENT;
+    if (!ctx || which < 0 || which > 3) return F3PS_ERR_INVALID_ARGUMENT;
     ctx->force_general_merge = which == 2;
+    ctx->merge_kernel_choice = which;
     return F3PS_OK;
 }
 

@@ -107,6 +107,12 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
+// per-lane 16-byte asynchronous copy (LDGSTS) and a plain CTA-scope arrive (used by the cluster variant's loader)
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_local(unsigned mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
     unsigned ok;
     do {
@@ -409,7 +415,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(FastArgs A)
             FPHASE(0);
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
-            const bool big_is_a = sm.n[a] >= sm.n[b];
+            const int na_ = sm.n[a], nb_ = sm.n[b];
+            const bool big_is_a = na_ >= nb_;
+            // guess the merged colour vector only when one side dominates (4x): two comparable regions move the mean for sure,
+            // and a wasted CIEDE2000 evaluation sits on the critical path of the short folds
+            const bool speculate = max(na_, nb_) >= 4 * min(na_, nb_);
             const float4 guess = __ldcg(R.cvec + (big_is_a ? a : b));
             named_bar(BAR_TOUCHED, kFastOwners + kFastDeltaThreads);                           // owners published the touched edges
             const int T = sm.misc[FM_TCOUNT];
@@ -443,14 +453,15 @@ __global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(FastArgs A)
                     const bool need = live && !reuse;
                     FPHASE(2);
                     __syncwarp();
-                    if (__any_sync(kFull, need)) { if (need) dc = a < x ? colour_delta(ep.color_mode, guess, xcv) : colour_delta(ep.color_mode, xcv, guess); }
+                    if (speculate && __any_sync(kFull, need)) { if (need) dc = a < x ? colour_delta(ep.color_mode, guess, xcv) : colour_delta(ep.color_mode, xcv, guess); }
                     FPHASE(3);
                     named_bar(BAR_FOLDED, kFastFoldedCount);                                   // region a's new colour vector / centroid / normal
                     FPHASE(4);
                     const bool hit = newgeo_i[9] != 0;
-                    if (!hit && __any_sync(kFull, live)) {
+                    const bool redo = hit ? (need && !speculate) : live;                      // wrong guess: every survivor; no guess made: the ones that cannot reuse
+                    if (__any_sync(kFull, redo)) {
                         const float4 acv = make_float4(sm.newgeo[0], sm.newgeo[1], sm.newgeo[2], 0.0f);
-                        if (live) dc = a < x ? colour_delta(ep.color_mode, acv, xcv) : colour_delta(ep.color_mode, xcv, acv);
+                        if (redo) dc = a < x ? colour_delta(ep.color_mode, acv, xcv) : colour_delta(ep.color_mode, xcv, acv);
                     }
                     FPHASE(5);
                     __syncwarp();

@@ -231,14 +231,18 @@ def test_threshold_prefix_property_and_restart(gpu, oracle_mod, small_frame):
 
 @pytest.mark.parametrize("mp", [AL, EQ, RGB_ML], ids=["cvx_al", "eq200", "rgb_ml"])
 def test_resident_and_general_merge_kernels_agree(gpu, vga_frame, small_frame, mp):
-    """K7 has two kernels (one SM with the weight map in registers / everything in global memory); both replay the
-    same sequence.  f3ps_set_merge_kernel(2) forces the general one."""
+    """K7 has three kernels (one SM with the weight map in registers / a four-SM cluster with one role per SM /
+    everything in global memory); all replay the same sequence.  f3ps_set_merge_kernel selects."""
     for pts, thr in ((small_frame, 0.2), (vga_frame, 0.2), (small_frame, 1.0)):
         g = gpu.Segmenter(); g.set_vccs_params(); g.set_merge_params(**mp); g.set_input(pts); g.run(thr)
         assert g.counts().merge_path == 1
         fast = {n: g.array(n).copy() for n in MERGE_ARRAYS}
         g.set_merge_kernel(2); g.merge(thr)
         assert g.counts().merge_path == 2
+        for n in MERGE_ARRAYS:
+            assert same(fast[n], g.array(n)), n
+        g.set_merge_kernel(3); g.merge(thr)                 # four-CTA cluster variant (one role per SM)
+        assert g.counts().merge_path == 3
         for n in MERGE_ARRAYS:
             assert same(fast[n], g.array(n)), n
         g.set_merge_kernel(0); g.merge(thr)

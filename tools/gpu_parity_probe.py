@@ -39,6 +39,7 @@ def main():
     o = oracle_py.Oracle(); o.set_vccs_params(); o.set_merge_params(merge_impl=0, **mp); o.set_input(pts)
     t = time.time(); o.run(0, thr); print("oracle %.1f ms" % ((time.time() - t) * 1e3), o.array("stage_ms"))
     g = f3ps.Segmenter(); g.set_vccs_params(); g.set_merge_params(**mp); g.set_input(pts)
+    if os.environ.get("F3PS_MERGE_KERNEL"): g.set_merge_kernel(int(os.environ["F3PS_MERGE_KERNEL"]))
     stages = [("voxelize", ["keys", "voxel_xyz", "voxel_rgb", "voxel_rgba", "voxel_count", "point_voxel"]),
               ("neighbors", ["nbr_count", "nbr"]), ("normals", ["normals", "curvature"]), ("seeds", ["seeds"]),
               ("expand", ["labels", "dist", "sv_label", "sv_xyz", "sv_rgb", "sv_normal", "sv_count"]),

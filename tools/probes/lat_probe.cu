@@ -82,12 +82,55 @@ __global__ void head_loop(long long* out, int reps, unsigned* sink) {
     if (threadIdx.x == 0) out[0] = (t1 - t0) / reps;
     sink[0] = acc;
 }
+// rope walk + staging of R runs of 20 voxels, as the merge loader does it (one warp)
+__global__ void loader_loop(const float4* pos_data, long long* out, int R, int reps, int mode, float* sink) {
+    __shared__ __align__(128) float4 stage[2048];
+    __shared__ unsigned rs[512], re[512]; __shared__ unsigned short nx[512];
+    __shared__ unsigned long long mbar;
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 512; i += 32) { rs[i] = (unsigned)((i * 37) % 500) * 20u; re[i] = rs[i] + 20u; nx[i] = (unsigned short)((i * 7 + 3) % 512); }
+    const unsigned mb = smem_addr(&mbar), st = smem_addr(stage);
+    if (lane == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb)); asm volatile("fence.proxy.async.shared::cta;"); }
+    __syncwarp();
+    unsigned parity = 0; float acc = 0; long long tot = 0; unsigned run0 = 1;
+    for (int r = 0; r < reps; ++r) {
+        long long t0 = clock64();
+        unsigned run = run0; unsigned pos = rs[run]; int off = 0; const int cn = R * 20;
+        if (mode == 0) {
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(cn * 16) : "memory");
+                while (off < cn) {
+                    const unsigned end = re[run]; const int take = min((int)(end - pos), cn - off);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st + off * 16), "l"(pos_data + pos), "r"(take * 16), "r"(mb) : "memory");
+                    off += take; pos += take;
+                    if (pos == end) { run = nx[run]; pos = rs[run]; }
+                }
+            }
+        } else {
+            while (off < cn) {
+                const unsigned end = re[run]; const int take = min((int)(end - pos), cn - off);
+                for (int i = lane; i < take; i += 32) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + (off + i) * 16), "l"(pos_data + pos + i) : "memory");
+                off += take; pos += take;
+                if (pos == end) { run = nx[run]; pos = rs[run]; }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
+        }
+        unsigned ok;
+        do { asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(mb), "r"(parity) : "memory"); } while (!ok);
+        parity ^= 1;
+        long long t1 = clock64(); tot += t1 - t0; acc += stage[lane].x; run0 = run;
+        __syncwarp();
+    }
+    if (lane == 0) { out[0] = tot / reps; *sink = acc; }
+}
 int main() {
     const int N = 1 << 16;   // 256 KB chain: L2-resident, larger than nothing else
     unsigned* h = new unsigned[N]; for (int i = 0; i < N; ++i) h[i] = (unsigned)((i * 40503u + 12345u) % N);
     unsigned* d; long long* o; unsigned* sink; float4* src; float* fs;
-    cudaMalloc(&d, N * 4); cudaMalloc(&o, 64); cudaMalloc(&sink, 4); cudaMalloc(&src, 4096 * 16 + 8192); cudaMalloc(&fs, 4);
-    cudaMemcpy(d, h, N * 4, cudaMemcpyHostToDevice); cudaMemset(src, 0, 4096 * 16 + 8192);
+    cudaMalloc(&d, N * 4); cudaMalloc(&o, 64); cudaMalloc(&sink, 4); cudaMalloc(&src, 16384 * 16); cudaMalloc(&fs, 4);
+    cudaMemcpy(d, h, N * 4, cudaMemcpyHostToDevice); cudaMemset(src, 0, 16384 * 16);
     long long r[8];
     chase<<<1, 1>>>(d, 2000, o, sink); chase<<<1, 1>>>(d, 4000, o, sink); cudaMemcpy(r, o, 8, cudaMemcpyDeviceToHost);
     printf("ld.global.cg dependent chase (L2): %lld cycles\n", r[0]);
@@ -95,6 +138,7 @@ int main() {
     for (int t : {64, 256, 1024}) { bar_lat<<<1, t>>>(o, 1000); cudaMemcpy(r, o, 8, cudaMemcpyDeviceToHost); printf("__syncthreads %4d threads: %lld cycles\n", t, r[0]); }
     redux_lat<<<1, 32>>>(o, 1000, sink); cudaMemcpy(r, o, 40, cudaMemcpyDeviceToHost);
     printf("redux.min %lld, shfl %lld, ballot %lld, lds %lld, smem atomicCAS16 %lld cycles (dependent)\n", r[0], r[1], r[2], r[3], r[4]);
+    for (int mode = 0; mode < 2; ++mode) for (int R : {1, 6, 24}) { loader_loop<<<1, 32>>>(src, o, R, 200, mode, fs); cudaMemcpy(r, o, 8, cudaMemcpyDeviceToHost); printf("loader %s, %2d runs of 20 voxels: %lld cycles\n", mode ? "cp.async per lane" : "bulk copy per run", R, r[0]); }
     head_loop<<<1, 1024>>>(o, 2000, sink); cudaMemcpy(r, o, 8, cudaMemcpyDeviceToHost); printf("argmin skeleton (publish + barrier + head in all 32 warps): %lld cycles per round\n", r[0]);
     printf("status %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
