@@ -111,4 +111,5 @@ struct f3ps_ctx {
     bool ev_valid[kEvents] = {};
     cudaEvent_t ev_wait = nullptr;     // blocking-sync event for sweeps (f3ps_set_blocking_wait)
     bool blocking_wait = false;
+    bool lambda_attr_set = false, fast_attr_set[4] = {false, false, false, false};
 };

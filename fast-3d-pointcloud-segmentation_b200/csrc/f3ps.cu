@@ -488,7 +488,15 @@ static int init_weights(f3ps_ctx* ctx, unsigned E_cap) {     // Clustering::init
     LAUNCH(ctx, region_cvec_kernel, grid_for(std::max(1u, ctx->S), 256), 256, 0, SC(xctl.n_sv), ctx->R0, ep);
     LAUNCH(ctx, edge_delta_kernel, grid_for(E_cap, 128), 128, 0, ctx->sorted_edge_keys, SC(n_edges), ctx->R0, ep, ctx->E0,
            ctx->dbits_a.as<unsigned>(), ctx->dbits_c.as<unsigned>());
-    if (ctx->mp.merge_mode == F3PS_ADAPTIVE_LAMBDA) {
+    if (ctx->mp.merge_mode == F3PS_ADAPTIVE_LAMBDA && E_cap <= 16384u) {
+        const unsigned n_pow2 = next_pow2(std::max(2u, E_cap));
+        if (!ctx->lambda_attr_set) {
+            F3PS_CUDA_OK(cudaFuncSetAttribute(adaptive_lambda_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4));
+            ctx->lambda_attr_set = true;
+        }
+        LAUNCH(ctx, adaptive_lambda_smem_kernel, 2, 1024, (size_t)n_pow2 * 4, ctx->E0.dc, ctx->E0.dg, SC(n_edges), n_pow2, SC(padf[0]), SC(pad0), SC(lambda));
+        lambda_dev = SC(lambda);
+    } else if (ctx->mp.merge_mode == F3PS_ADAPTIVE_LAMBDA) {
         unsigned *sc, *sg, *dummy;
         int rc = sort_pairs<unsigned>(ctx, ctx->dbits_a.as<unsigned>(), nullptr, ctx->dbits_b.as<unsigned>(), ctx->edge_vals_a.as<unsigned>(),
                                       ctx->dbits_a.as<unsigned>(), ctx->edge_vals_b.as<unsigned>(), SC(n_edges), E_cap, 32, &sc, &dummy);
@@ -711,7 +719,7 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
                 } else {
                     A.E_cap = E_cap;
                     void (*kern)(FastArgs) = slots == 4 ? merge_fast_kernel<4> : slots == 8 ? merge_fast_kernel<8> : slots == 12 ? merge_fast_kernel<12> : merge_fast_kernel<16>;
-                    F3PS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // same value from every handle / thread
+                    if (!ctx->fast_attr_set[slots / 4 - 1]) { F3PS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); ctx->fast_attr_set[slots / 4 - 1] = true; }   // same value from every handle / thread
                     kern<<<1, kFastThreads, fast_bytes, ctx->stream>>>(A);
                     ctx->launches++;
                     F3PS_CUDA_OK(cudaPeekAtLastError());

@@ -208,6 +208,53 @@ __global__ void __launch_bounds__(64) adaptive_lambda_kernel(const unsigned* __r
     if (threadIdx.x == 0) *lambda_out = s_mean[1] / (s_mean[0] + s_mean[1]);
 }
 
+// The same for graphs whose deltas fit shared memory (E <= 16384): block 0 sorts delta_c, block 1 delta_g (bitonic, in
+// place), runs the chain, and the block that finishes last forms lambda -- one launch instead of two radix sorts.
+__global__ void __launch_bounds__(1024) adaptive_lambda_smem_kernel(const float* __restrict__ dc, const float* __restrict__ dg,
+        const unsigned* __restrict__ n_edges_ptr, unsigned n_pow2, float* __restrict__ means, unsigned* __restrict__ done, float* __restrict__ lambda_out) {
+    extern __shared__ unsigned s_sort[];
+    __shared__ float s_inv2[32];
+    const unsigned n = *n_edges_ptr;
+    const float* src = blockIdx.x == 0 ? dc : dg;
+    for (unsigned i = threadIdx.x; i < n_pow2; i += blockDim.x) s_sort[i] = i < n ? __float_as_uint(src[i]) : 0xffffffffu;   // deltas are >= 0: bit order = value order
+    __syncthreads();
+    for (unsigned k = 2; k <= n_pow2; k <<= 1)
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const unsigned l = i ^ j;
+                if (l > i) {
+                    const unsigned x = s_sort[i], y = s_sort[l];
+                    if (((i & k) == 0) == (x > y)) { s_sort[i] = y; s_sort[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        float mean_d = 0.0f;
+        for (unsigned base = 0; base < n; base += 32) {
+            s_inv2[lane] = 1 / (float)(base + lane + 1);                                  // count = count + 1.0f is exact here
+            __syncwarp();
+            if (lane == 0) {
+                const int m = (int)min(32u, n - base);
+#pragma unroll 8
+                for (int j = 0; j < m; ++j) mean_d = mean_d + s_inv2[j] * (__uint_as_float(s_sort[base + j]) - mean_d);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            means[blockIdx.x] = mean_d;
+            __threadfence();
+            if (atomicAdd(done, 1u) == 1u) {                                              // the other distribution is finished too
+                __threadfence();
+                const float mc = *(volatile float*)&means[0], mg = *(volatile float*)&means[1];
+                *lambda_out = mg / (mc + mg);
+                *done = 0u;
+            }
+        }
+    }
+}
+
 // Clustering::compute_cdf for both distributions: histogram (shared-memory atomics when the bins
 // fit, else global), inclusive scan, cdf[i] = float(cum_i) / float(n).  One block per distribution.
 __global__ void __launch_bounds__(1024) cdf_kernel(const float* __restrict__ dc, const float* __restrict__ dg, const unsigned* __restrict__ n_edges_ptr,
