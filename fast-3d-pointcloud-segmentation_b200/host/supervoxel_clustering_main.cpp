@@ -4,7 +4,8 @@
 // Not built here (out of the hot-path scope): the auto-threshold sweep (needs the
 // evaluation module, so -t is required), -r / -f, the viewer.  Additions: -o <file.pcd> writes the labelled voxel
 // cloud, --facade routes through the Clustering / SupervoxelClustering classes instead of the fused f3ps_run,
-// --gpus N shards the files of a -d sweep over N GPUs (one host thread + handle + stream per GPU, no collective).
+// --gpus N shards the files of a -d sweep over N GPUs, --inflight K keeps K frames in flight per GPU (one host thread +
+// handle + stream each, no collective).
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -12,6 +13,7 @@
 #include <cstring>
 #include <filesystem>
 #include <mutex>
+#include <memory>
 #include <thread>
 
 #include "pcd_io.h"
@@ -56,10 +58,11 @@ void usage(const char* a0) {
            "\t --V                            (verbose: prints the merge sequence) \n"
            "\t -o <file.pcd>                  (writes the labelled voxel cloud) \n"
            "\t --facade                       (runs through the Clustering / SupervoxelClustering classes) \n"
-           "\t --gpus <N>                     (shards the files of -d over N GPUs) \n", a0);
+           "\t --gpus <N>                     (shards the files of -d over N GPUs) \n"
+           "\t --inflight <K>                 (frames in flight per GPU during a -d sweep, default 8) \n", a0);
 }
 
-int process_file(const std::string& file, const Options& o, int device, std::mutex& io) {
+int process_file(const std::string& file, const Options& o, int device, std::string& report, f3ps::Handle* worker) {
     pcl::PointCloud<pcl::PointXYZRGBL> input;
     f3ps::loadPCDFile(file, input);                                      // return value ignored, as in the reference (:313)
     pcl::PointCloud<pcl::PointXYZRGBA>::Ptr cloud(new pcl::PointCloud<pcl::PointXYZRGBA>());
@@ -92,7 +95,9 @@ int process_file(const std::string& file, const Options& o, int device, std::mut
         n_sv = supervoxel_clusters.size(); n_seg = segmentation.get_currentstate().first.size();
         log = segmentation.get_merge_log(); n_merges = log.size();
     } else {
-        f3ps::Handle h(device);
+        std::unique_ptr<f3ps::Handle> local;                                 // -p: a handle of its own; sweeps reuse the worker's (buffers stay allocated)
+        if (!worker) local.reset(new f3ps::Handle(device));
+        f3ps::Handle& h = worker ? *worker : *local;
         h.check(f3ps_set_vccs_params(h.get(), o.voxel_resolution, o.seed_resolution, o.color_importance, o.spatial_importance,
                                      o.normal_importance, o.disable_transform ? 0 : 1, 0));
         h.check(f3ps_set_merge_params(h.get(), o.rgb ? F3PS_RGB_EUCL : F3PS_LAB_CIEDE00, o.cvx ? F3PS_CONVEX_NORMALS_DIFF : F3PS_NORMALS_DIFF, merging, lam, bins));
@@ -112,14 +117,13 @@ int process_file(const std::string& file, const Options& o, int device, std::mut
         }
     }
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    std::lock_guard<std::mutex> g(io);
-    printf("Loading pointcloud from PCD file '%s'...\n", file.c_str());
-    printf("Found %zu supervoxels\n", n_sv);
-    if (o.verbose) for (auto& m : log) printf("left: %de/%dp - w: %f - [%d, %d]...OK\n", m.edges_left, m.regions_left, m.w, m.a, m.b);
-    printf("Clustering complete: %zu points -> %zu merges -> %zu segments over %zu voxels in %.3f ms (GPU %d)\n",
-           cloud->size(), n_merges, n_seg, labeled->size(), ms, device);
-    if (!o.facade) printf("  stage ms: voxelize %.3f neighbors %.3f normals %.3f seeds %.3f expand %.3f graph %.3f merge %.3f total %.3f\n",
-                          stage[0], stage[1], stage[2], stage[3], stage[4], stage[5], stage[6], stage[7]);
+    char buf[512];
+    snprintf(buf, sizeof buf, "Loading pointcloud from PCD file '%s'...\nFound %zu supervoxels\n", file.c_str(), n_sv); report += buf;
+    if (o.verbose) for (auto& m : log) { snprintf(buf, sizeof buf, "left: %de/%dp - w: %f - [%d, %d]...OK\n", m.edges_left, m.regions_left, m.w, m.a, m.b); report += buf; }
+    snprintf(buf, sizeof buf, "Clustering complete: %zu points -> %zu merges -> %zu segments over %zu voxels in %.3f ms (GPU %d)\n",
+             cloud->size(), n_merges, n_seg, labeled->size(), ms, device); report += buf;
+    if (!o.facade) { snprintf(buf, sizeof buf, "  stage ms: voxelize %.3f neighbors %.3f normals %.3f seeds %.3f expand %.3f graph %.3f merge %.3f total %.3f\n",
+                              stage[0], stage[1], stage[2], stage[3], stage[4], stage[5], stage[6], stage[7]); report += buf; }
     if (!o.out.empty()) f3ps::savePCDFileASCII(o.out, *labeled);
     return 0;
 }
@@ -155,14 +159,29 @@ int main(int argc, char** argv) {
     if (o.eq) parse(argc, argv, "--EQ", o.bin_num);
     parse(argc, argv, "-o", o.out);
     int gpus = 1; parse(argc, argv, "--gpus", gpus); gpus = std::max(1, gpus);
-    std::mutex io; int rc = 0;
+    int inflight = 8; parse(argc, argv, "--inflight", inflight); inflight = std::max(1, inflight);
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);                     // before the CUDA context exists (see f3ps_create)
+    int rc = 0;
+    std::vector<std::string> reports(file_list.size());
     try {
-        if (gpus == 1 || file_list.size() <= 1) { for (auto& f : file_list) rc |= process_file(f, o, 0, io); }
+        if (file_list.size() <= 1 || o.facade) { for (size_t i = 0; i < file_list.size(); ++i) rc |= process_file(file_list[i], o, 0, reports[i], nullptr); }
         else {
-            std::vector<std::thread> th;
-            for (int g = 0; g < gpus; ++g) th.emplace_back([&, g]() { for (size_t i = g; i < file_list.size(); i += gpus) process_file(file_list[i], o, g, io); });
+            // -d sweep: files are independent (fresh SupervoxelClustering + Clustering per file in the reference, :348,408).
+            // `inflight` frames per GPU, each on its own handle / stream / host thread; reports are printed in file order.
+            const int workers = (int)std::min<size_t>((size_t)gpus * inflight, file_list.size());
+            const bool blocking = workers > (int)std::max(1u, std::thread::hardware_concurrency() / 2);
+            std::vector<std::thread> th; std::mutex emu; std::string first_error;
+            for (int w = 0; w < workers; ++w) th.emplace_back([&, w]() {
+                try {
+                    f3ps::Handle h(w % gpus);
+                    f3ps_set_blocking_wait(h.get(), blocking ? 1 : 0);
+                    for (size_t i = w; i < file_list.size(); i += workers) process_file(file_list[i], o, w % gpus, reports[i], &h);
+                } catch (const std::exception& e) { std::lock_guard<std::mutex> g(emu); if (first_error.empty()) first_error = e.what(); }
+            });
             for (auto& t : th) t.join();
+            if (!first_error.empty()) throw std::runtime_error(first_error);
         }
+        for (auto& r : reports) fputs(r.c_str(), stdout);
     } catch (const std::exception& e) { fprintf(stderr, "error: %s\n", e.what()); return 2; }
     return rc;
 }

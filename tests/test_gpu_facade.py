@@ -51,3 +51,31 @@ def test_cli_flags_and_merge_trace(pcd_file, oracle_mod, small_frame, tmp_path):
     run2 = subprocess.run([cli, "-p", pcd_file, "-t", "0.2", "--CVX", "--AL", "--V", "--facade"], capture_output=True, text=True, timeout=300)
     assert run2.returncode == 0, run2.stdout + run2.stderr
     assert [l for l in run2.stdout.splitlines() if l.startswith("left: ")] == trace
+
+
+def test_cli_directory_sweep_frames_in_flight(tmp_path, oracle_mod):
+    """-d sweep: several frames in flight per GPU (one handle / stream / host thread each); reports come back in file
+    order and every file merges exactly as it does alone."""
+    import f3ps
+    from f3ps import pcd, synth
+    subprocess.check_call(["make", "-C", HOST, "-s"])
+    d = tmp_path / "sweep"; d.mkdir()
+    want = {}
+    for i in range(7):
+        pts = synth.make_frame(seed=300 + i, width=160, height=120)
+        path = str(d / ("f%02d.pcd" % i))
+        pcd.write_pcd_binary(path, pts)
+        o = oracle_mod.Oracle(); o.set_vccs_params(fold_negative_z=True); o.set_merge_params(color_mode=0, geom_mode=0, merge_mode=2, bins=200, merge_impl=1)
+        o.set_input(pts); o.run(0, 0.3)
+        want[path] = (len(o.array("merges_ab")), len(o.array("out_label")))
+    cli = os.path.join(HOST, "supervoxel_clustering")
+    run = subprocess.run([cli, "-d", str(d), "-t", "0.3", "--EQ", "200", "--inflight", "3"], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stdout + run.stderr
+    lines = run.stdout.splitlines()
+    assert lines[0] == "Found 7 files"
+    files = [l.split("'")[1] for l in lines if l.startswith("Loading pointcloud")]
+    done = [l for l in lines if l.startswith("Clustering complete")]
+    assert sorted(files) == sorted(want) and len(done) == 7
+    for f, l in zip(files, done):
+        tok = l.split()
+        assert int(tok[5]) == want[f][0] and int(tok[11]) == want[f][1], (f, l, want[f])
