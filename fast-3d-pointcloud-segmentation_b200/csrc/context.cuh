@@ -7,6 +7,7 @@
 #include "radix_sort.cuh"
 #include "kernels_vccs.cuh"
 #include "kernels_expand.cuh"
+#include "kernels_slab.cuh"
 #include "kernels_graph.cuh"
 
 #define F3PS_MERGE_ERR_TOUCHED 4u
@@ -111,5 +112,10 @@ struct f3ps_ctx {
     bool ev_valid[kEvents] = {};
     cudaEvent_t ev_wait = nullptr;     // blocking-sync event for sweeps (f3ps_set_blocking_wait)
     bool blocking_wait = false;
+    // slab mode (f3ps_slab_*): injected global frame, owned voxel range, K5 phase state
+    bool slab_frame = false; f3ps::FrameParams slab_fp{};
+    bool slab_range = false; unsigned own_begin = 0, own_end = 0;
+    f3ps::DevBuf slab_dest, slab_tot;
+    f3ps::ExpandArgs slab_A{}; int slab_cur = 0; unsigned slab_k = 0; unsigned slab_sweeps = 0; int slab_round = 0; bool slab_expanding = false;
     bool lambda_attr_set = false, fast_attr_set[4] = {false, false, false, false};
 };

@@ -238,7 +238,9 @@ int f3ps_create(int device, void* stream, f3ps_ctx** out) {
     for (int i = 0; i < f3ps_ctx::kEvents && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { f3ps_destroy(ctx); return F3PS_ERR_CUDA; }
-    cudaMemset(ctx->d_sc, 0, sizeof(DevScalars));
+    // the handle's stream is non-blocking: it does not wait for the legacy stream the two copies above ran on
+    cudaMemsetAsync(ctx->d_sc, 0, sizeof(DevScalars), ctx->stream);
+    if (cudaDeviceSynchronize() != cudaSuccess) { f3ps_destroy(ctx); return F3PS_ERR_CUDA; }
     memset(ctx->h_sc, 0, sizeof(DevScalars));
     *out = ctx;
     return F3PS_OK;
@@ -275,6 +277,7 @@ int f3ps_set_vccs_params(f3ps_ctx* ctx, float rv, float rs, float wc, float ws, 
     if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
     if (!(rv > 0) || !(rs > 0)) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "resolutions must be positive");
     ctx->vp = VccsParams{rv, rs, wc, ws, wn, use_transform ? 1 : 0, fold_negative_z ? 1 : 0};
+    ctx->slab_frame = false; ctx->slab_range = false;
     ctx->progress = std::min(ctx->progress, (int)P_INPUT);
     return F3PS_OK;
 }
@@ -325,12 +328,20 @@ int f3ps_voxelize(f3ps_ctx* ctx) {
     PointLoader pl{ctx->d_points, ctx->stride, ctx->vp.fold_negative_z};
     DevScalars init; memset(&init, 0, sizeof init);
     for (int a = 0; a < 3; ++a) { init.fp.ord_min[a] = 0xffffffffu; init.fp.ord_max[a] = 0u; }
+    if (ctx->slab_frame) init.fp = ctx->slab_fp;
     *ctx->h_sc = init;
     F3PS_CUDA_OK(cudaMemcpyAsync(ctx->d_sc, ctx->h_sc, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
     F3PS_CUDA_OK(ctx->point_voxel.ensure(std::max<int64_t>(N, 1) * 4));
     F3PS_CUDA_OK(cudaMemsetAsync(ctx->point_voxel.p, 0xff, std::max<int64_t>(N, 1) * 4, ctx->stream));
     ctx->V = 0; ctx->n_valid = 0; ctx->depth = 0;
-    if (N > 0) {
+    ctx->slab_range = false;
+    if (ctx->slab_frame) {                                    // slab mode: the frame of the WHOLE cloud, agreed on by all ranks
+        ctx->depth = ctx->slab_fp.depth;
+        if (N > 0 && ctx->slab_fp.any_finite) {
+            rc = ctx->key64 ? voxelize_typed<uint64_t>(ctx, pl) : voxelize_typed<uint32_t>(ctx, pl);
+            if (rc) return rc;
+        }
+    } else if (N > 0) {
         LAUNCH(ctx, bbox_kernel, grid_for(N, 256 * 4, kSMs * 8), 256, 0, pl, N, ctx->vp.use_transform, SC(fp));
         LAUNCH(ctx, frame_setup_kernel, 1, 1, 0, SC(fp), ctx->vp.voxel_res);
         rc = pull_scalars(ctx); if (rc) return rc;            // host needs the depth to pick the key width / pass count
@@ -375,9 +386,10 @@ int f3ps_normals(f3ps_ctx* ctx) {
     cudaSetDevice(ctx->device);
     const unsigned V = ctx->V; const size_t Vc = std::max(1u, V);
     F3PS_CUDA_OK(ctx->vox_normal.ensure(Vc * 16)); F3PS_CUDA_OK(ctx->vox_curv.ensure(Vc * 4));
-    if (V)
-        LAUNCH(ctx, voxel_normals_kernel, grid_for(V, 128), 128, 0, ctx->vox_xyz.as<float4>(), ctx->nbr_row.as<int>(), SC(n_voxels),
-               ctx->vox_normal.as<float4>(), ctx->vox_curv.as<float>());
+    const unsigned vb = ctx->slab_range ? ctx->own_begin : 0u, ve = ctx->slab_range ? ctx->own_end : 0xffffffffu;
+    if (V && ve > vb)
+        LAUNCH(ctx, voxel_normals_kernel, grid_for(std::min(V, ve) - vb, 128), 128, 0, ctx->vox_xyz.as<float4>(), ctx->nbr_row.as<int>(), SC(n_voxels),
+               ctx->vox_normal.as<float4>(), ctx->vox_curv.as<float>(), vb, ve);
     ctx->progress = P_NORMALS;
     return mark(ctx, 3);
 }
@@ -422,10 +434,7 @@ int f3ps_seeds(f3ps_ctx* ctx) {
 // ---- K5 -------------------------------------------------------------------------------------------
 // One cooperative launch runs createSupervoxelHelpers, every expansion round and makeSupervoxels' lists
 // (kernels_expand.cuh); the host only learns the number of surviving helpers afterwards.
-int f3ps_expand(f3ps_ctx* ctx) {
-    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
-    int rc = need(ctx, P_SEEDS, "f3ps_expand"); if (rc) return rc;
-    cudaSetDevice(ctx->device);
+static int expand_prepare(f3ps_ctx* ctx, ExpandArgs& A) {
     const unsigned V = ctx->V, S0 = ctx->S0; const size_t Vc = std::max(1u, V), Sc = (size_t)S0 + 2, Lc = Vc + Sc;
     DevBuf* bv[] = {&ctx->own_a, &ctx->own_b, &ctx->dst_a, &ctx->dst_b, &ctx->st0, &ctx->st1, &ctx->phantom, &ctx->owner0, &ctx->dist0};
     for (DevBuf* b : bv) F3PS_CUDA_OK(b->ensure(Vc * 4));
@@ -438,21 +447,41 @@ int f3ps_expand(f3ps_ctx* ctx) {
     ctx->rounds = std::max(0, max_depth - 1);
     F3PS_CUDA_OK(cudaMemsetAsync(SC(xctl), 0, sizeof(ExpandCtl), ctx->stream));
     ctx->sorted_label = ctx->lab_keys_a.as<unsigned>(); ctx->sorted_vox = ctx->lab_vals_b.as<unsigned>();
+    A.nbr_col = ctx->nbr_col.as<int>(); A.nbr_row = ctx->nbr_row.as<int>(); A.V_cap = V;
+    A.vox_xyz = ctx->vox_xyz.as<float4>(); A.vox_rgb = ctx->vox_rgb.as<float4>(); A.vox_nrm = ctx->vox_normal.as<float4>();
+    A.seeds = ctx->seeds.as<int>(); A.V = V; A.S0 = S0; A.rounds = ctx->rounds; A.P = ctx->vp;
+    A.owner[0] = ctx->own_a.as<unsigned>(); A.owner[1] = ctx->own_b.as<unsigned>();
+    A.dist[0] = ctx->dst_a.as<float>(); A.dist[1] = ctx->dst_b.as<float>();
+    A.st[0] = ctx->st0.as<unsigned>(); A.st[1] = ctx->st1.as<unsigned>();
+    A.phantom = ctx->phantom.as<unsigned>(); A.phantom_leaf = ctx->phantom_leaf.as<int>();
+    A.cen = Centroids{ctx->cen_xyz.as<float4>(), ctx->cen_rgb.as<float4>(), ctx->cen_nrm.as<float4>()};
+    A.count[0] = ctx->lab_count.as<unsigned>(); A.count[1] = ctx->lab_count2.as<unsigned>(); A.fill = ctx->lab_fill.as<unsigned>(); A.off = ctx->seg_start.as<unsigned>();
+    A.list_raw = ctx->lab_vals_a.as<unsigned>(); A.list_sorted = ctx->lab_vals_b.as<unsigned>(); A.pos_label = ctx->lab_keys_a.as<unsigned>();
+    A.labels_out = ctx->owner0.as<unsigned>(); A.dist_out = ctx->dist0.as<float>();
+    A.seg_end = ctx->seg_end.as<unsigned>(); A.sv_label = ctx->sv_label.as<unsigned>(); A.rank_of_label = ctx->rank_of_label.as<unsigned>();
+    A.ctl = SC(xctl);
+    return F3PS_OK;
+}
+
+static int expand_finish(f3ps_ctx* ctx) {
+    int rc = pull_scalars(ctx); if (rc) return rc;
+    const ExpandCtl& x = ctx->h_sc->xctl;
+    if (x.error & EXPAND_ERR_TRIPLE) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "three seed cells elected the same voxel (not modelled)");
+    if (x.error & EXPAND_ERR_CAND) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "more than 32 candidate helpers around one voxel");
+    if (x.error & EXPAND_ERR_SWEEPS) return ctx_fail(ctx, F3PS_ERR_NOT_CONVERGED, "expansion fixed point not reached within 32 sweeps");
+    ctx->S = ctx->V ? x.n_sv : 0; ctx->n_pos = ctx->V ? x.n_pos : 0;
+    ctx->progress = P_EXPANDED;
+    return mark(ctx, 5);
+}
+
+int f3ps_expand(f3ps_ctx* ctx) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_SEEDS, "f3ps_expand"); if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    const unsigned V = ctx->V;
+    ExpandArgs A;
+    rc = expand_prepare(ctx, A); if (rc) return rc;
     if (V) {
-        ExpandArgs A;
-        A.nbr_col = ctx->nbr_col.as<int>(); A.nbr_row = ctx->nbr_row.as<int>(); A.V_cap = V;
-        A.vox_xyz = ctx->vox_xyz.as<float4>(); A.vox_rgb = ctx->vox_rgb.as<float4>(); A.vox_nrm = ctx->vox_normal.as<float4>();
-        A.seeds = ctx->seeds.as<int>(); A.V = V; A.S0 = S0; A.rounds = ctx->rounds; A.P = ctx->vp;
-        A.owner[0] = ctx->own_a.as<unsigned>(); A.owner[1] = ctx->own_b.as<unsigned>();
-        A.dist[0] = ctx->dst_a.as<float>(); A.dist[1] = ctx->dst_b.as<float>();
-        A.st[0] = ctx->st0.as<unsigned>(); A.st[1] = ctx->st1.as<unsigned>();
-        A.phantom = ctx->phantom.as<unsigned>(); A.phantom_leaf = ctx->phantom_leaf.as<int>();
-        A.cen = Centroids{ctx->cen_xyz.as<float4>(), ctx->cen_rgb.as<float4>(), ctx->cen_nrm.as<float4>()};
-        A.count[0] = ctx->lab_count.as<unsigned>(); A.count[1] = ctx->lab_count2.as<unsigned>(); A.fill = ctx->lab_fill.as<unsigned>(); A.off = ctx->seg_start.as<unsigned>();
-        A.list_raw = ctx->lab_vals_a.as<unsigned>(); A.list_sorted = ctx->lab_vals_b.as<unsigned>(); A.pos_label = ctx->lab_keys_a.as<unsigned>();
-        A.labels_out = ctx->owner0.as<unsigned>(); A.dist_out = ctx->dist0.as<float>();
-        A.seg_end = ctx->seg_end.as<unsigned>(); A.sv_label = ctx->sv_label.as<unsigned>(); A.rank_of_label = ctx->rank_of_label.as<unsigned>();
-        A.ctl = SC(xctl);
         if (!ctx->expand_blocks_per_sm) {
             int nb = 0;
             F3PS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, expand_persistent_kernel, kExpandThreads, 0));
@@ -466,14 +495,7 @@ int f3ps_expand(f3ps_ctx* ctx) {
         F3PS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)expand_persistent_kernel, dim3(grid), dim3(kExpandThreads), args, 0, ctx->stream));
         ctx->launches++;
     }
-    rc = pull_scalars(ctx); if (rc) return rc;
-    const ExpandCtl& x = ctx->h_sc->xctl;
-    if (x.error & EXPAND_ERR_TRIPLE) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "three seed cells elected the same voxel (not modelled)");
-    if (x.error & EXPAND_ERR_CAND) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "more than 32 candidate helpers around one voxel");
-    if (x.error & EXPAND_ERR_SWEEPS) return ctx_fail(ctx, F3PS_ERR_NOT_CONVERGED, "expansion fixed point not reached within 32 sweeps");
-    ctx->S = V ? x.n_sv : 0; ctx->n_pos = V ? x.n_pos : 0;
-    ctx->progress = P_EXPANDED;
-    return mark(ctx, 5);
+    return expand_finish(ctx);
 }
 
 // ---- K6 -------------------------------------------------------------------------------------------
@@ -784,6 +806,245 @@ int f3ps_run(f3ps_ctx* ctx, float threshold) {
     int rc = f3ps_extract(ctx);
     if (rc) return rc;
     return f3ps_merge(ctx, threshold);
+}
+
+
+// =====================================================================================================
+// Slab mode (BASELINE config 5): one cloud, one slab of the x-major Morton key space per
+// GPU.  The per-rank pieces live here; the host driver (f3ps/slab.py) issues the exchanges between them on this
+// handle's stream: all-reduce of the bounding box and the key histogram, all-to-all of the points, all-gather of the
+// voxel slices, the normal slices and -- per expansion sweep -- the steal-table slices.
+extern "C++" {
+namespace {
+template <typename KeyT>
+int slab_keys_typed(f3ps_ctx* ctx, PointLoader pl, int shift, unsigned bins, unsigned* d_hist) {
+    const int64_t N = ctx->n_points;
+    F3PS_CUDA_OK(ctx->keys_a.ensure(N * sizeof(KeyT))); F3PS_CUDA_OK(ctx->keys_b.ensure(N * sizeof(KeyT)));
+    F3PS_CUDA_OK(ctx->vals_a.ensure(N * 4)); F3PS_CUDA_OK(ctx->vals_b.ensure(N * 4));
+    KeygenOp<KeyT> kop{pl, ctx->vp.use_transform, SC(fp), ctx->keys_a.as<KeyT>(), ctx->vals_a.as<unsigned>()};
+    int rc = run_compact(ctx, kop, nullptr, N, SC(n_valid)); if (rc) return rc;
+    LAUNCH(ctx, slab_key_hist_kernel<KeyT>, grid_for(N, 256 * 4, kSMs * 8), 256, 0, ctx->keys_a.as<KeyT>(), SC(n_valid), shift, bins, d_hist);
+    return F3PS_OK;
+}
+template <typename KeyT>
+int slab_route_typed(f3ps_ctx* ctx, PointLoader pl, const SlabSplitters& sp, int world, float4* d_send) {
+    const int64_t N = ctx->n_points;
+    F3PS_CUDA_OK(ctx->slab_dest.ensure(N * 4)); F3PS_CUDA_OK(ctx->starts.ensure((N + 1) * 4));
+    LAUNCH(ctx, slab_dest_kernel<KeyT>, grid_for(N, 256 * 4, kSMs * 8), 256, 0, ctx->keys_a.as<KeyT>(), SC(n_valid), sp,
+           ctx->slab_dest.as<unsigned>(), ctx->slab_tot.as<unsigned>());
+    unsigned* sk; unsigned* sv;        // stable: input order survives inside a destination
+    int rc = sort_pairs<unsigned>(ctx, ctx->slab_dest.as<unsigned>(), ctx->vals_a.as<unsigned>(), ctx->starts.as<unsigned>(), ctx->vals_b.as<unsigned>(),
+                                  ctx->slab_dest.as<unsigned>(), ctx->vals_a.as<unsigned>(), SC(n_valid), N, bits_for((unsigned)std::max(1, world - 1)), &sk, &sv);
+    if (rc) return rc;
+    LAUNCH(ctx, slab_pack_kernel, grid_for(N, 256 * 2, kSMs * 8), 256, 0, pl, sv, SC(n_valid), d_send);
+    return F3PS_OK;
+}
+} // namespace
+} // extern "C++"
+
+int f3ps_slab_reset(f3ps_ctx* ctx) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    ctx->slab_frame = false; ctx->slab_range = false; ctx->slab_expanding = false;
+    ctx->progress = std::min(ctx->progress, (int)P_INPUT);
+    return F3PS_OK;
+}
+
+// bounding box of this rank's points (transformed space): d_box8 = ord_min[3], ord_max[3], any_finite, 0 in the
+// order-preserving unsigned encoding (all-reduce MIN / MAX / MAX as unsigned)
+int f3ps_slab_bbox(f3ps_ctx* ctx, uint32_t* d_box8) {
+    if (!ctx || !d_box8) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_INPUT, "f3ps_slab_bbox"); if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    DevScalars init; memset(&init, 0, sizeof init);
+    for (int a = 0; a < 3; ++a) { init.fp.ord_min[a] = 0xffffffffu; init.fp.ord_max[a] = 0u; }
+    *ctx->h_sc = init;
+    F3PS_CUDA_OK(cudaMemcpyAsync(ctx->d_sc, ctx->h_sc, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
+    PointLoader pl{ctx->d_points, ctx->stride, ctx->vp.fold_negative_z};
+    if (ctx->n_points > 0)
+        LAUNCH(ctx, bbox_kernel, grid_for(ctx->n_points, 256 * 4, kSMs * 8), 256, 0, pl, ctx->n_points, ctx->vp.use_transform, SC(fp));
+    F3PS_CUDA_OK(cudaMemcpyAsync(d_box8, SC(fp.ord_min), 24, cudaMemcpyDeviceToDevice, ctx->stream));
+    F3PS_CUDA_OK(cudaMemcpyAsync(d_box8 + 6, SC(fp.any_finite), 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    F3PS_CUDA_OK(cudaMemsetAsync(d_box8 + 7, 0, 4, ctx->stream));
+    ctx->slab_frame = false;
+    return F3PS_OK;
+}
+
+// the reduced box of the whole cloud -> OctreePointCloud::defineBoundingBox / getKeyBitSize, identical on every rank
+int f3ps_slab_set_frame(f3ps_ctx* ctx, const uint32_t* d_box8) {
+    if (!ctx || !d_box8) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_INPUT, "f3ps_slab_set_frame"); if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    F3PS_CUDA_OK(cudaMemcpyAsync(SC(fp.ord_min), d_box8, 24, cudaMemcpyDeviceToDevice, ctx->stream));
+    F3PS_CUDA_OK(cudaMemcpyAsync(SC(fp.any_finite), d_box8 + 6, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(ctx, frame_setup_kernel, 1, 1, 0, SC(fp), ctx->vp.voxel_res);
+    rc = pull_scalars(ctx); if (rc) return rc;
+    ctx->slab_fp = ctx->h_sc->fp; ctx->slab_frame = true;
+    ctx->depth = ctx->slab_fp.depth;
+    if (ctx->depth > 21) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "adjacency octree depth > 21");
+    ctx->key64 = 3 * ctx->depth > 32;
+    return F3PS_OK;
+}
+
+// Morton keys of this rank's valid points + histogram of their top `top_bits` bits (d_hist: 1 << top_bits counters, device);
+// *used_bits / *shift describe the binning: bin = key >> shift, min(top_bits, 3 * depth) bits
+int f3ps_slab_keys(f3ps_ctx* ctx, int top_bits, uint32_t* d_hist, int* used_bits, int* shift_out) {
+    if (!ctx || !d_hist || top_bits < 1 || top_bits > kSlabHistBitsMax) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_INPUT, "f3ps_slab_keys"); if (rc) return rc;
+    if (!ctx->slab_frame) return ctx_fail(ctx, F3PS_ERR_LOGIC, "f3ps_slab_keys: f3ps_slab_set_frame has not run");
+    cudaSetDevice(ctx->device);
+    const int kb = 3 * ctx->depth, tb = std::min(top_bits, std::max(1, kb)), shift = std::max(0, kb - tb);
+    if (used_bits) *used_bits = tb;
+    if (shift_out) *shift_out = shift;
+    F3PS_CUDA_OK(cudaMemsetAsync(d_hist, 0, (size_t)4 << top_bits, ctx->stream));
+    PointLoader pl{ctx->d_points, ctx->stride, ctx->vp.fold_negative_z};
+    if (ctx->n_points == 0) { F3PS_CUDA_OK(cudaMemsetAsync(SC(n_valid), 0, 4, ctx->stream)); return F3PS_OK; }
+    return ctx->key64 ? slab_keys_typed<uint64_t>(ctx, pl, shift, 1u << tb, d_hist) : slab_keys_typed<uint32_t>(ctx, pl, shift, 1u << tb, d_hist);
+}
+
+// splitters[world - 1]: ascending Morton keys, rank r owns [splitters[r-1], splitters[r]).  Packs this rank's valid points as
+// 16-byte records {x, y, z, rgba} into d_send (capacity: n points), grouped by destination rank, input order kept inside
+// a group; counts[world] = records per destination.
+int f3ps_slab_route(f3ps_ctx* ctx, int world, const uint64_t* splitters, void* d_send, int64_t* counts) {
+    if (!ctx || world < 1 || world > kSlabMaxWorld || (world > 1 && !splitters) || !counts) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_INPUT, "f3ps_slab_route"); if (rc) return rc;
+    if (!ctx->slab_frame) return ctx_fail(ctx, F3PS_ERR_LOGIC, "f3ps_slab_route: f3ps_slab_set_frame / f3ps_slab_keys have not run");
+    cudaSetDevice(ctx->device);
+    for (int r = 0; r < world; ++r) counts[r] = 0;
+    if (ctx->n_points == 0) return F3PS_OK;
+    SlabSplitters sp; memset(&sp, 0, sizeof sp); sp.n = world - 1;
+    for (int r = 0; r + 1 < world; ++r) { sp.key[r] = splitters[r]; if (r && splitters[r] < splitters[r - 1]) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "splitters must ascend"); }
+    F3PS_CUDA_OK(ctx->slab_tot.ensure(kSlabMaxWorld * 4));
+    F3PS_CUDA_OK(cudaMemsetAsync(ctx->slab_tot.p, 0, kSlabMaxWorld * 4, ctx->stream));
+    PointLoader pl{ctx->d_points, ctx->stride, ctx->vp.fold_negative_z};
+    rc = ctx->key64 ? slab_route_typed<uint64_t>(ctx, pl, sp, world, (float4*)d_send) : slab_route_typed<uint32_t>(ctx, pl, sp, world, (float4*)d_send);
+    if (rc) return rc;
+    unsigned tot[kSlabMaxWorld];
+    F3PS_CUDA_OK(cudaMemcpyAsync(tot, ctx->slab_tot.p, sizeof tot, cudaMemcpyDeviceToHost, ctx->stream));
+    F3PS_CUDA_OK(wait_stream(ctx));
+    for (int r = 0; r < world; ++r) counts[r] = tot[r];
+    return F3PS_OK;
+}
+
+// device arrays the driver exchanges in place (pointer, elements, bytes per element)
+int f3ps_slab_array(f3ps_ctx* ctx, int which, void** ptr, int64_t* n, int* elem_bytes) {
+    if (!ctx || !ptr || !n || !elem_bytes) return F3PS_ERR_INVALID_ARGUMENT;
+    const int64_t V = ctx->V, L = (int64_t)ctx->S0 + 2;
+    const ExpandArgs& A = ctx->slab_A;
+    switch (which) {
+    case F3PS_SLAB_VOX_XYZ: *ptr = ctx->vox_xyz.p; *n = V; *elem_bytes = 16; break;
+    case F3PS_SLAB_VOX_RGB: *ptr = ctx->vox_rgb.p; *n = V; *elem_bytes = 16; break;
+    case F3PS_SLAB_VOX_KEY: *ptr = ctx->vox_key.p; *n = V; *elem_bytes = 8; break;
+    case F3PS_SLAB_VOX_NORMAL: *ptr = ctx->vox_normal.p; *n = V; *elem_bytes = 16; break;
+    case F3PS_SLAB_VOX_CURV: *ptr = ctx->vox_curv.p; *n = V; *elem_bytes = 4; break;
+    case F3PS_SLAB_STEAL: if (!ctx->slab_expanding) return ctx_fail(ctx, F3PS_ERR_LOGIC, "no expansion in progress");
+        *ptr = A.st[ctx->slab_k & 1]; *n = V; *elem_bytes = 4; break;
+    case F3PS_SLAB_OWNER_NEXT: if (!ctx->slab_expanding) return ctx_fail(ctx, F3PS_ERR_LOGIC, "no expansion in progress");
+        *ptr = A.owner[ctx->slab_cur ^ 1]; *n = V; *elem_bytes = 4; break;
+    case F3PS_SLAB_DIST: if (!ctx->slab_expanding) return ctx_fail(ctx, F3PS_ERR_LOGIC, "no expansion in progress");
+        *ptr = A.dist[ctx->slab_cur]; *n = V; *elem_bytes = 4; break;
+    case F3PS_SLAB_COUNT: if (!ctx->slab_expanding) return ctx_fail(ctx, F3PS_ERR_LOGIC, "no expansion in progress");
+        *ptr = A.count[(ctx->slab_k + 1) & 1]; *n = L; *elem_bytes = 4; break;     // tallies of the last sweep
+    default: return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "unknown slab array");
+    }
+    return F3PS_OK;
+}
+
+// the voxel table of the WHOLE cloud (every rank's slice, leaf order) and the slice [own_begin, own_end) this rank computes
+int f3ps_slab_set_voxels(f3ps_ctx* ctx, const void* d_xyz, const void* d_rgb, const void* d_key, int64_t n_voxels, int64_t own_begin, int64_t own_end) {
+    if (!ctx || n_voxels < 0 || own_begin < 0 || own_end < own_begin || own_end > n_voxels) return F3PS_ERR_INVALID_ARGUMENT;
+    if (n_voxels >= (1ll << 30)) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "more than 2^30 voxels");
+    if (!ctx->slab_frame) return ctx_fail(ctx, F3PS_ERR_LOGIC, "f3ps_slab_set_voxels: f3ps_slab_set_frame has not run");
+    cudaSetDevice(ctx->device);
+    const size_t V = (size_t)n_voxels, Vc = std::max<size_t>(1, V);
+    if (d_xyz != ctx->vox_xyz.p) {
+        F3PS_CUDA_OK(wait_stream(ctx));
+        F3PS_CUDA_OK(ctx->vox_xyz.ensure(Vc * 16)); F3PS_CUDA_OK(ctx->vox_rgb.ensure(Vc * 16)); F3PS_CUDA_OK(ctx->vox_key.ensure(Vc * 8));
+        if (V) {
+            F3PS_CUDA_OK(cudaMemcpyAsync(ctx->vox_xyz.p, d_xyz, V * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+            F3PS_CUDA_OK(cudaMemcpyAsync(ctx->vox_rgb.p, d_rgb, V * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+            F3PS_CUDA_OK(cudaMemcpyAsync(ctx->vox_key.p, d_key, V * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    ctx->V = (unsigned)V;
+    const unsigned v32 = (unsigned)V;
+    F3PS_CUDA_OK(cudaMemcpyAsync(SC(n_voxels), &v32, 4, cudaMemcpyHostToDevice, ctx->stream));
+    F3PS_CUDA_OK(wait_stream(ctx));
+    ctx->own_begin = (unsigned)own_begin; ctx->own_end = (unsigned)own_end; ctx->slab_range = true;
+    ctx->progress = P_VOXELS;
+    return mark(ctx, 1);
+}
+
+// ---- K5 in slab mode: createSupervoxelHelpers, then per round {sweeps over the owned slice, round end}, then the tail ----
+int f3ps_slab_expand_begin(f3ps_ctx* ctx) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_SEEDS, "f3ps_slab_expand_begin"); if (rc) return rc;
+    if (!ctx->slab_range) return ctx_fail(ctx, F3PS_ERR_LOGIC, "f3ps_slab_expand_begin: not in slab mode");
+    cudaSetDevice(ctx->device);
+    rc = expand_prepare(ctx, ctx->slab_A); if (rc) return rc;
+    const ExpandArgs& A = ctx->slab_A;
+    ctx->slab_cur = 0; ctx->slab_k = 0; ctx->slab_sweeps = 0; ctx->slab_round = 0; ctx->slab_expanding = true;
+    if (ctx->V) {
+        LAUNCH(ctx, slab_expand_init_kernel, grid_for(ctx->V, 256), 256, 0, A);
+        if (ctx->S0) {
+            LAUNCH(ctx, slab_expand_seed_kernel, grid_for(ctx->S0, 256), 256, 0, A);
+            LAUNCH(ctx, slab_expand_phantom_kernel, grid_for(ctx->S0, 256), 256, 0, A);
+        }
+    }
+    return F3PS_OK;
+}
+
+// one sweep over [own_begin, own_end); *d_changed (device) = 1 if a steal-table entry of the slice moved.  Afterwards
+// F3PS_SLAB_STEAL is the table this sweep wrote: exchange its slices, all-reduce the flag (MAX), repeat until it is 0.
+int f3ps_slab_expand_sweep(f3ps_ctx* ctx, uint32_t* d_changed) {
+    if (!ctx || !d_changed) return F3PS_ERR_INVALID_ARGUMENT;
+    if (!ctx->slab_expanding) return ctx_fail(ctx, F3PS_ERR_LOGIC, "f3ps_slab_expand_sweep: f3ps_slab_expand_begin has not run");
+    cudaSetDevice(ctx->device);
+    const ExpandArgs& A = ctx->slab_A;
+    F3PS_CUDA_OK(cudaMemsetAsync(d_changed, 0, 4, ctx->stream));
+    F3PS_CUDA_OK(cudaMemsetAsync(A.count[ctx->slab_k & 1], 0, ((size_t)ctx->S0 + 2) * 4, ctx->stream));
+    const unsigned nb = ctx->own_end - ctx->own_begin;
+    if (nb)
+        LAUNCH(ctx, slab_expand_sweep_kernel, grid_for(nb, kExpandThreads, kSMs * 2), kExpandThreads, 0, A, ctx->own_begin, ctx->own_end, ctx->slab_cur,
+               ctx->slab_k, d_changed);
+    ctx->slab_k++; ctx->slab_sweeps++;
+    return F3PS_OK;
+}
+
+// after the converged sweep of a round, with F3PS_SLAB_OWNER_NEXT slices exchanged and F3PS_SLAB_COUNT all-reduced (SUM):
+// helper lists, SupervoxelHelper::updateCentroid (every rank, whole cloud).  With zero expansion rounds call it once, without sweeps.
+int f3ps_slab_expand_round_end(f3ps_ctx* ctx) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    if (!ctx->slab_expanding) return ctx_fail(ctx, F3PS_ERR_LOGIC, "f3ps_slab_expand_round_end: f3ps_slab_expand_begin has not run");
+    cudaSetDevice(ctx->device);
+    const ExpandArgs& A = ctx->slab_A;
+    const unsigned V = ctx->V, S0 = ctx->S0;
+    unsigned* cnt_final;
+    if (ctx->rounds > 0) { cnt_final = A.count[(ctx->slab_k + 1) & 1]; ctx->slab_cur ^= 1; }
+    else {
+        cnt_final = A.count[0];
+        if (V) LAUNCH(ctx, slab_expand_count0_kernel, grid_for(V, 256), 256, 0, A, ctx->slab_cur, cnt_final);
+    }
+    F3PS_CUDA_OK(cudaMemsetAsync(SC(xctl.cursor), 0, 4, ctx->stream));
+    if (V && S0) {
+        LAUNCH(ctx, slab_expand_alloc_kernel, grid_for(S0, 256), 256, 0, A, cnt_final);
+        LAUNCH(ctx, slab_expand_fill_kernel, grid_for(V, 256), 256, 0, A, ctx->slab_cur, ctx->slab_k);
+        LAUNCH(ctx, slab_expand_fold_kernel, grid_for((int64_t)S0 * 32, kExpandThreads, kSMs * 2), kExpandThreads, 0, A, cnt_final);
+    }
+    ctx->slab_round++;
+    return F3PS_OK;
+}
+
+// after the last round (F3PS_SLAB_DIST slices exchanged): clean labels, surviving helpers (makeSupervoxels)
+int f3ps_slab_expand_end(f3ps_ctx* ctx) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    if (!ctx->slab_expanding) return ctx_fail(ctx, F3PS_ERR_LOGIC, "f3ps_slab_expand_end: f3ps_slab_expand_begin has not run");
+    cudaSetDevice(ctx->device);
+    const ExpandArgs& A = ctx->slab_A;
+    const unsigned* cnt_final = ctx->rounds > 0 ? A.count[(ctx->slab_k + 1) & 1] : A.count[0];
+    if (ctx->V) LAUNCH(ctx, slab_expand_tail_kernel, 1 + grid_for(ctx->V, 1024, kSMs * 2), 1024, 0, A, ctx->slab_cur, cnt_final);
+    F3PS_CUDA_OK(cudaMemcpyAsync(SC(xctl.sweeps_total), &ctx->slab_sweeps, 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->slab_expanding = false;
+    return expand_finish(ctx);
 }
 
 int f3ps_merge_profile(f3ps_ctx* ctx, uint64_t cycles[32]) {

@@ -79,6 +79,179 @@ __device__ __forceinline__ void grid_barrier(ExpandCtl* ctl, unsigned nblocks, u
 __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define XPHASE(i) do { if (tid == 0) { const unsigned long long t_now = globaltimer_ns(); ctl->t_phase[i] += t_now - t_prev; t_prev = t_now; } } while (0)
 
+// One voxel of one sweep: fold, in ascending label order, every helper that holds a leaf adjacent to n at its turn
+// (SupervoxelHelper::expand restated per voxel).  Reads the round-start owners / distances and the previous
+// sweep's steal table, writes this voxel's entries of the next ones.
+__device__ __forceinline__ void expand_sweep_voxel(const ExpandArgs& A, const unsigned n, const unsigned* own0, const float* dst0,
+        unsigned* own1, float* dst1, const unsigned* st_in, unsigned* st_out, unsigned* cnt, unsigned& any_change) {
+    const unsigned w0 = own0[n];
+    float D = dst0[n];
+    const unsigned st_n = st_in[n];
+    const int cnt_n = A.nbr_row[(size_t)n * kNbrStride + 27];
+    unsigned cur_l = w0 & kOwnMask;
+    unsigned idx[27], hu[27];
+    unsigned any_ph = w0 & kOwnPhantom;
+#pragma unroll
+    for (int r = 0; r < 27; ++r) idx[r] = r < cnt_n ? (unsigned)A.nbr_col[(size_t)r * A.V_cap + n] : n;
+#pragma unroll
+    for (int r = 0; r < 27; ++r) hu[r] = idx[r] != n ? own0[idx[r]] : 0u;
+#pragma unroll
+    for (int r = 0; r < 27; ++r) {
+        any_ph |= hu[r] & kOwnPhantom;
+        const unsigned h = hu[r] & kOwnMask;
+        const unsigned stv = h != 0u ? st_in[idx[r]] : 0u;
+        hu[r] = stv > h ? h : 0u;                 // still h's leaf at h's turn
+    }
+    unsigned first = kNoSteal, won = 0u, ph_n = 0u;
+    const float4 vx = A.vox_xyz[n], vc = A.vox_rgb[n], vn = A.vox_nrm[n];
+    if (!any_ph) {
+        unsigned last = 0u;
+        while (true) {                            // distinct candidate labels in ascending order
+            unsigned m = 0xffffffffu;
+#pragma unroll
+            for (int r = 0; r < 27; ++r) { const unsigned h = hu[r]; if (h > last && h < m) m = h; }
+            if (m == 0xffffffffu) break;
+            last = m;
+            if (m == cur_l) continue;
+            const float d = voxel_data_distance(A.cen.xyz[m], A.cen.rgb[m], A.cen.nrm[m], vx, vc, vn, A.P);
+            if (d < D) { if (first == kNoSteal) first = m; D = d; cur_l = m; }
+        }
+    } else {
+        // a phantom leaf somewhere in the neighbourhood: it supports all its neighbours, itself included
+        ph_n = (w0 & kOwnPhantom) ? A.phantom[n] : 0u;
+        unsigned cand[kMaxCand]; int nc = 0; bool overflow = false;
+        auto insert = [&](unsigned h) {           // sorted, distinct
+            int p = nc;
+            while (p > 0 && cand[p - 1] >= h) { if (cand[p - 1] == h) return; --p; }
+            if (nc == kMaxCand) { overflow = true; return; }
+            for (int q = nc; q > p; --q) cand[q] = cand[q - 1];
+            cand[p] = h; ++nc;
+        };
+        for (int r = 0; r < cnt_n; ++r) {
+            const unsigned u = (unsigned)A.nbr_col[(size_t)r * A.V_cap + n];
+            const unsigned wu = (u == n) ? w0 : own0[u];
+            if (u != n) {
+                const unsigned h = wu & kOwnMask;
+                if (h != 0u && st_in[u] > h) insert(h);
+            }
+            if (wu & kOwnPhantom) insert(A.phantom[u]);
+        }
+        if (overflow) atomicOr(&A.ctl->error, (unsigned)EXPAND_ERR_CAND);
+        for (int q = 0; q < nc; ++q) {
+            const unsigned h = cand[q];
+            if (h == cur_l) continue;
+            const float d = voxel_data_distance(A.cen.xyz[h], A.cen.rgb[h], A.cen.nrm[h], vx, vc, vn, A.P);
+            if (d < D) { if (first == kNoSteal) first = h; D = d; cur_l = h; if (h == ph_n) won = kOwnWon; }
+        }
+    }
+    own1[n] = cur_l | (w0 & kOwnPhantom) | won; dst1[n] = D; st_out[n] = first;
+    if (first != st_n) any_change = 1;
+    if (cur_l) atomicAdd(&cnt[cur_l], 1u);
+    if (ph_n && !won) atomicAdd(&cnt[ph_n], 1u);   // the holder still lists its phantom leaf
+}
+
+// one contiguous leaf list per helper: 32 helpers per warp, warp-aggregated bump allocation (helper order is irrelevant)
+__device__ __forceinline__ void expand_alloc_warp(const ExpandArgs& A, const unsigned* cnt_final, const unsigned base, const int lane) {
+    const unsigned l = base + lane + 1u;
+    const unsigned c = l <= A.S0 ? cnt_final[l] : 0u;
+    unsigned incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+    unsigned start = 0u;
+    if (lane == 31 && incl) start = atomicAdd(&A.ctl->cursor, incl);
+    start = __shfl_sync(kFull, start, 31);
+    if (l <= A.S0) { A.off[l] = start + incl - c; A.fill[l] = 0u; }
+}
+
+// commit the round for voxel n (a phantom leaf its holder stole becomes a regular leaf) and append it to its helpers' lists
+__device__ __forceinline__ void expand_fill_voxel(const ExpandArgs& A, unsigned* own, const unsigned n) {
+    unsigned w = own[n];
+    if (w & kOwnWon) {                       // the holder owns it now (or lost it for good to a later thief)
+        const unsigned ph = A.phantom[n];
+        A.phantom_leaf[ph] = -1; A.phantom[n] = 0u;
+        w &= kOwnMask; own[n] = w;
+    }
+    const unsigned l = w & kOwnMask;
+    if (l) A.list_raw[A.off[l] + atomicAdd(&A.fill[l], 1u)] = n;
+    if (w & kOwnPhantom) { const unsigned ph = A.phantom[n]; A.list_raw[A.off[ph] + atomicAdd(&A.fill[ph], 1u)] = n; }
+}
+
+// one helper, one warp: leaves in idx order (ranks by counting), then SupervoxelHelper::updateCentroid -- the leaves' data are
+// staged 32 at a time in shared memory, lanes 0..9 each run one ordered accumulator chain (n0..n3, x,y,z, r,g,b)
+__device__ __forceinline__ void expand_fold_helper(const ExpandArgs& A, const unsigned* cnt_final, const unsigned l, const int lane,
+                                                   unsigned* s_sorted, float* stage) {
+    const unsigned s = A.off[l], c = cnt_final[l];
+    if (c == 0) { if (lane == 0 && A.rounds > 0) A.cen.xyz[l].w = 0.0f; return; }   // helper erased (no leaves)
+    // ranks by counting (leaf sets are small; values are distinct)
+    unsigned sorted_mine = 0u;
+    for (unsigned ib = 0; ib < c; ib += 32) {
+        const unsigned i = ib + lane;
+        const unsigned v = i < c ? A.list_raw[s + i] : 0xffffffffu;
+        unsigned rank = 0;
+        for (unsigned jb = 0; jb < c; jb += 32) {
+            const unsigned x = (c <= 32) ? v : (jb + lane < c ? A.list_raw[s + jb + lane] : 0xffffffffu);
+            const unsigned m = min(32u, c - jb);
+            for (unsigned t = 0; t < m; ++t) rank += __shfl_sync(kFull, x, t) < v ? 1u : 0u;
+        }
+        if (i < c) {
+            A.list_sorted[s + rank] = v; A.pos_label[s + rank] = l;
+            if (c <= 32) s_sorted[rank] = v;
+        }
+    }
+    __syncwarp();
+    if (A.rounds == 0) return;
+    float acc = 0.0f;
+    for (unsigned base = 0; base < c; base += 32) {
+        const unsigned m = min(32u, c - base);
+        if (base + lane < c) {
+            sorted_mine = c <= 32 ? s_sorted[lane] : ldcg_u(A.list_sorted + s + base + lane);   // same-phase data: L2
+            const float4 vn = A.vox_nrm[sorted_mine], vx = A.vox_xyz[sorted_mine], vc = A.vox_rgb[sorted_mine];
+            float* row = stage + lane * 12;
+            row[0] = vn.x; row[1] = vn.y; row[2] = vn.z; row[3] = vn.w;
+            row[4] = vx.x; row[5] = vx.y; row[6] = vx.z; row[7] = vc.x; row[8] = vc.y; row[9] = vc.z;
+        }
+        __syncwarp();
+        if (lane < 10) for (unsigned j = 0; j < m; ++j) acc += stage[j * 12 + lane];
+        __syncwarp();
+    }
+    float n0 = __shfl_sync(kFull, acc, 0), n1 = __shfl_sync(kFull, acc, 1), n2 = __shfl_sync(kFull, acc, 2), n3 = __shfl_sync(kFull, acc, 3);
+    float x = __shfl_sync(kFull, acc, 4), y = __shfl_sync(kFull, acc, 5), z = __shfl_sync(kFull, acc, 6);
+    float r = __shfl_sync(kFull, acc, 7), g = __shfl_sync(kFull, acc, 8), b = __shfl_sync(kFull, acc, 9);
+    if (lane == 0) {
+        float zz = sum4(n0 * n0, n1 * n1, n2 * n2, n3 * n3);
+        if (zz > 0.0f) { float sq = sqrtf(zz); n0 /= sq; n1 /= sq; n2 /= sq; n3 /= sq; }
+        const float cf = (float)c;
+        A.cen.nrm[l] = make_float4(n0, n1, n2, n3);
+        A.cen.xyz[l] = make_float4(x / cf, y / cf, z / cf, cf);
+        A.cen.rgb[l] = make_float4(r / cf, g / cf, b / cf, 0.0f);
+    }
+    __syncwarp();
+}
+
+// surviving helpers in label order (makeSupervoxels): exclusive scan of (count > 0) by ONE block
+__device__ __forceinline__ void expand_alive_scan(const ExpandArgs& A, const unsigned* cnt_final, unsigned* s_warp, unsigned* s_carry) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { (*s_carry) = 0; A.ctl->n_pos = ldcg_u(&A.ctl->cursor); }
+    __syncthreads();
+    for (unsigned base = 1; base <= A.S0; base += blockDim.x) {      // alive ranks: exclusive scan of (count > 0)
+        const unsigned l = base + threadIdx.x;
+        const unsigned a = (l <= A.S0 && ldcg_u(cnt_final + l) > 0u) ? 1u : 0u;
+        unsigned v = a;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(kFull, v, o); if (lane >= o) v += t; }
+        if (lane == 31) s_warp[warp] = v;
+        __syncthreads();
+        unsigned wb = 0;
+        for (int w = 0; w < warp; ++w) wb += s_warp[w];
+        const unsigned carry = (*s_carry);
+        if (a) { const unsigned rank = carry + wb + v - 1u; A.sv_label[rank] = l; A.rank_of_label[l] = rank; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) (*s_carry) = carry + wb + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) A.ctl->n_sv = (*s_carry);
+}
+
 __global__ void __launch_bounds__(kExpandThreads) expand_persistent_kernel(ExpandArgs A) {
     __shared__ unsigned s_warp[32];
     __shared__ unsigned s_carry;
@@ -130,72 +303,7 @@ __global__ void __launch_bounds__(kExpandThreads) expand_persistent_kernel(Expan
                 unsigned any_change = 0;
                 for (unsigned l = tid; l < S0 + 2; l += nthreads) cnt_next[l] = 0u;
                 if (tid == 0) { ctl->changed[(k + 2u) & 63u] = 0u; ctl->cursor = 0u; }
-                for (unsigned n = tid; n < V; n += nthreads) {
-                    const unsigned w0 = own0[n];
-                    float D = dst0[n];
-                    const unsigned st_n = st_in[n];
-                    const int cnt_n = A.nbr_row[(size_t)n * kNbrStride + 27];
-                    unsigned cur_l = w0 & kOwnMask;
-                    unsigned idx[27], hu[27];
-                    unsigned any_ph = w0 & kOwnPhantom;
-#pragma unroll
-                    for (int r = 0; r < 27; ++r) idx[r] = r < cnt_n ? (unsigned)A.nbr_col[(size_t)r * A.V_cap + n] : n;
-#pragma unroll
-                    for (int r = 0; r < 27; ++r) hu[r] = idx[r] != n ? own0[idx[r]] : 0u;
-#pragma unroll
-                    for (int r = 0; r < 27; ++r) {
-                        any_ph |= hu[r] & kOwnPhantom;
-                        const unsigned h = hu[r] & kOwnMask;
-                        const unsigned stv = h != 0u ? st_in[idx[r]] : 0u;
-                        hu[r] = stv > h ? h : 0u;                 // still h's leaf at h's turn
-                    }
-                    unsigned first = kNoSteal, won = 0u, ph_n = 0u;
-                    const float4 vx = A.vox_xyz[n], vc = A.vox_rgb[n], vn = A.vox_nrm[n];
-                    if (!any_ph) {
-                        unsigned last = 0u;
-                        while (true) {                            // distinct candidate labels in ascending order
-                            unsigned m = 0xffffffffu;
-#pragma unroll
-                            for (int r = 0; r < 27; ++r) { const unsigned h = hu[r]; if (h > last && h < m) m = h; }
-                            if (m == 0xffffffffu) break;
-                            last = m;
-                            if (m == cur_l) continue;
-                            const float d = voxel_data_distance(A.cen.xyz[m], A.cen.rgb[m], A.cen.nrm[m], vx, vc, vn, A.P);
-                            if (d < D) { if (first == kNoSteal) first = m; D = d; cur_l = m; }
-                        }
-                    } else {
-                        // a phantom leaf somewhere in the neighbourhood: it supports all its neighbours, itself included
-                        ph_n = (w0 & kOwnPhantom) ? A.phantom[n] : 0u;
-                        unsigned cand[kMaxCand]; int nc = 0; bool overflow = false;
-                        auto insert = [&](unsigned h) {           // sorted, distinct
-                            int p = nc;
-                            while (p > 0 && cand[p - 1] >= h) { if (cand[p - 1] == h) return; --p; }
-                            if (nc == kMaxCand) { overflow = true; return; }
-                            for (int q = nc; q > p; --q) cand[q] = cand[q - 1];
-                            cand[p] = h; ++nc;
-                        };
-                        for (int r = 0; r < cnt_n; ++r) {
-                            const unsigned u = (unsigned)A.nbr_col[(size_t)r * A.V_cap + n];
-                            const unsigned wu = (u == n) ? w0 : own0[u];
-                            if (u != n) {
-                                const unsigned h = wu & kOwnMask;
-                                if (h != 0u && st_in[u] > h) insert(h);
-                            }
-                            if (wu & kOwnPhantom) insert(A.phantom[u]);
-                        }
-                        if (overflow) atomicOr(&ctl->error, (unsigned)EXPAND_ERR_CAND);
-                        for (int q = 0; q < nc; ++q) {
-                            const unsigned h = cand[q];
-                            if (h == cur_l) continue;
-                            const float d = voxel_data_distance(A.cen.xyz[h], A.cen.rgb[h], A.cen.nrm[h], vx, vc, vn, A.P);
-                            if (d < D) { if (first == kNoSteal) first = h; D = d; cur_l = h; if (h == ph_n) won = kOwnWon; }
-                        }
-                    }
-                    own1[n] = cur_l | (w0 & kOwnPhantom) | won; dst1[n] = D; st_out[n] = first;
-                    if (first != st_n) any_change = 1;
-                    if (cur_l) atomicAdd(&cnt[cur_l], 1u);
-                    if (ph_n && !won) atomicAdd(&cnt[ph_n], 1u);   // the holder still lists its phantom leaf
-                }
+                for (unsigned n = tid; n < V; n += nthreads) expand_sweep_voxel(A, n, own0, dst0, own1, dst1, st_in, st_out, cnt, any_change);
                 if (__syncthreads_or(any_change) && threadIdx.x == 0) atomicOr(&ctl->changed[k & 63u], 1u);
                 grid_barrier(ctl, nblocks, phase);
                 converged = ldcg_u(&ctl->changed[k & 63u]) == 0u;
@@ -217,17 +325,7 @@ __global__ void __launch_bounds__(kExpandThreads) expand_persistent_kernel(Expan
             XPHASE(2);
         }
         // ---- alloc: one contiguous leaf list per helper (warp-aggregated bump allocation; helper order is irrelevant) ----
-        for (unsigned base = gwarp * 32u; base < S0; base += nwarps * 32u) {
-            const unsigned l = base + lane + 1u;
-            const unsigned c = l <= S0 ? cnt_final[l] : 0u;
-            unsigned incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
-            unsigned start = 0u;
-            if (lane == 31 && incl) start = atomicAdd(&ctl->cursor, incl);
-            start = __shfl_sync(kFull, start, 31);
-            if (l <= S0) { A.off[l] = start + incl - c; A.fill[l] = 0u; }
-        }
+        for (unsigned base = gwarp * 32u; base < S0; base += nwarps * 32u) expand_alloc_warp(A, cnt_final, base, lane);
         grid_barrier(ctl, nblocks, phase);
         XPHASE(3);
         // ---- fill: commit the round (a phantom leaf its holder stole becomes a regular leaf), unordered member lists ----
@@ -235,15 +333,7 @@ __global__ void __launch_bounds__(kExpandThreads) expand_persistent_kernel(Expan
             unsigned* own = A.owner[cur];
             unsigned* st_next = A.st[k & 1];
             for (unsigned n = tid; n < V; n += nthreads) {
-                unsigned w = own[n];
-                if (w & kOwnWon) {                       // the holder owns it now (or lost it for good to a later thief)
-                    const unsigned ph = A.phantom[n];
-                    A.phantom_leaf[ph] = -1; A.phantom[n] = 0u;
-                    w &= kOwnMask; own[n] = w;
-                }
-                const unsigned l = w & kOwnMask;
-                if (l) A.list_raw[A.off[l] + atomicAdd(&A.fill[l], 1u)] = n;
-                if (w & kOwnPhantom) { const unsigned ph = A.phantom[n]; A.list_raw[A.off[ph] + atomicAdd(&A.fill[ph], 1u)] = n; }
+                expand_fill_voxel(A, own, n);
                 st_next[n] = kNoSteal;
             }
         }
@@ -254,52 +344,7 @@ __global__ void __launch_bounds__(kExpandThreads) expand_persistent_kernel(Expan
         {
             float* stage = &s_stage[wib][0][0];
             for (unsigned l = 1 + gwarp; l <= S0; l += nwarps) {
-                const unsigned s = A.off[l], c = cnt_final[l];
-                if (c == 0) { if (lane == 0 && A.rounds > 0) A.cen.xyz[l].w = 0.0f; continue; }   // helper erased (no leaves)
-                // ranks by counting (leaf sets are small; values are distinct)
-                unsigned sorted_mine = 0u;
-                for (unsigned ib = 0; ib < c; ib += 32) {
-                    const unsigned i = ib + lane;
-                    const unsigned v = i < c ? A.list_raw[s + i] : 0xffffffffu;
-                    unsigned rank = 0;
-                    for (unsigned jb = 0; jb < c; jb += 32) {
-                        const unsigned x = (c <= 32) ? v : (jb + lane < c ? A.list_raw[s + jb + lane] : 0xffffffffu);
-                        const unsigned m = min(32u, c - jb);
-                        for (unsigned t = 0; t < m; ++t) rank += __shfl_sync(kFull, x, t) < v ? 1u : 0u;
-                    }
-                    if (i < c) {
-                        A.list_sorted[s + rank] = v; A.pos_label[s + rank] = l;
-                        if (c <= 32) s_sorted[wib][rank] = v;
-                    }
-                }
-                __syncwarp();
-                if (A.rounds == 0) continue;
-                float acc = 0.0f;
-                for (unsigned base = 0; base < c; base += 32) {
-                    const unsigned m = min(32u, c - base);
-                    if (base + lane < c) {
-                        sorted_mine = c <= 32 ? s_sorted[wib][lane] : ldcg_u(A.list_sorted + s + base + lane);   // same-phase data: L2
-                        const float4 vn = A.vox_nrm[sorted_mine], vx = A.vox_xyz[sorted_mine], vc = A.vox_rgb[sorted_mine];
-                        float* row = stage + lane * 12;
-                        row[0] = vn.x; row[1] = vn.y; row[2] = vn.z; row[3] = vn.w;
-                        row[4] = vx.x; row[5] = vx.y; row[6] = vx.z; row[7] = vc.x; row[8] = vc.y; row[9] = vc.z;
-                    }
-                    __syncwarp();
-                    if (lane < 10) for (unsigned j = 0; j < m; ++j) acc += stage[j * 12 + lane];
-                    __syncwarp();
-                }
-                float n0 = __shfl_sync(kFull, acc, 0), n1 = __shfl_sync(kFull, acc, 1), n2 = __shfl_sync(kFull, acc, 2), n3 = __shfl_sync(kFull, acc, 3);
-                float x = __shfl_sync(kFull, acc, 4), y = __shfl_sync(kFull, acc, 5), z = __shfl_sync(kFull, acc, 6);
-                float r = __shfl_sync(kFull, acc, 7), g = __shfl_sync(kFull, acc, 8), b = __shfl_sync(kFull, acc, 9);
-                if (lane == 0) {
-                    float zz = sum4(n0 * n0, n1 * n1, n2 * n2, n3 * n3);
-                    if (zz > 0.0f) { float sq = sqrtf(zz); n0 /= sq; n1 /= sq; n2 /= sq; n3 /= sq; }
-                    const float cf = (float)c;
-                    A.cen.nrm[l] = make_float4(n0, n1, n2, n3);
-                    A.cen.xyz[l] = make_float4(x / cf, y / cf, z / cf, cf);
-                    A.cen.rgb[l] = make_float4(r / cf, g / cf, b / cf, 0.0f);
-                }
-                __syncwarp();
+                expand_fold_helper(A, cnt_final, l, lane, &s_sorted[wib][0], stage);
             }
         }
         grid_barrier(ctl, nblocks, phase);
@@ -310,26 +355,7 @@ __global__ void __launch_bounds__(kExpandThreads) expand_persistent_kernel(Expan
             for (unsigned n = tid; n < V; n += nthreads) { A.labels_out[n] = ldcg_u(own + n) & kOwnMask; A.dist_out[n] = ldcg_f(dst + n); }
             for (unsigned l = tid; l < S0 + 2; l += nthreads) A.seg_end[l] = (l >= 1 && l <= S0) ? ldcg_u(A.off + l) + ldcg_u(cnt_final + l) : 0u;
             if (blockIdx.x == 0) {
-                const int warp = threadIdx.x >> 5;
-                if (threadIdx.x == 0) { s_carry = 0; ctl->n_pos = ldcg_u(&ctl->cursor); }
-                __syncthreads();
-                for (unsigned base = 1; base <= S0; base += blockDim.x) {      // alive ranks: exclusive scan of (count > 0)
-                    const unsigned l = base + threadIdx.x;
-                    const unsigned a = (l <= S0 && ldcg_u(cnt_final + l) > 0u) ? 1u : 0u;
-                    unsigned v = a;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(kFull, v, o); if (lane >= o) v += t; }
-                    if (lane == 31) s_warp[warp] = v;
-                    __syncthreads();
-                    unsigned wb = 0;
-                    for (int w = 0; w < warp; ++w) wb += s_warp[w];
-                    const unsigned carry = s_carry;
-                    if (a) { const unsigned rank = carry + wb + v - 1u; A.sv_label[rank] = l; A.rank_of_label[l] = rank; }
-                    __syncthreads();
-                    if (threadIdx.x == blockDim.x - 1) s_carry = carry + wb + v;
-                    __syncthreads();
-                }
-                if (threadIdx.x == 0) ctl->n_sv = s_carry;
+                expand_alive_scan(A, cnt_final, s_warp, &s_carry);
             }
             XPHASE(6);
         }

@@ -304,9 +304,10 @@ struct Accu9 {
 };
 
 __global__ void __launch_bounds__(128) voxel_normals_kernel(const float4* __restrict__ vox_xyz, const int* __restrict__ nbr_row,
-        const unsigned* __restrict__ n_vox_ptr, float4* __restrict__ vox_normal, float* __restrict__ vox_curv) {
-    const unsigned V = *n_vox_ptr;
-    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        const unsigned* __restrict__ n_vox_ptr, float4* __restrict__ vox_normal, float* __restrict__ vox_curv,
+        unsigned v_begin, unsigned v_end) {          // [v_begin, v_end): the voxels this handle owns (slab mode), else everything
+    const unsigned V = min(*n_vox_ptr, v_end);
+    for (unsigned v = v_begin + blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
         Accu9 A; A.clear();
         int total = 1;
         const float4 pv = vox_xyz[v];

@@ -100,6 +100,17 @@ def lib():
         "f3ps_test_lab_ciede00": (C.c_int, [vp, vp, vp, vp, i64]),
         "f3ps_test_rgb_eucl": (C.c_int, [vp, vp, vp, vp, i64]),
         "f3ps_test_sort_pairs": (C.c_int, [vp, vp, vp, i64, C.c_int]),
+        "f3ps_slab_reset": (C.c_int, [vp]),
+        "f3ps_slab_bbox": (C.c_int, [vp, vp]),
+        "f3ps_slab_set_frame": (C.c_int, [vp, vp]),
+        "f3ps_slab_keys": (C.c_int, [vp, C.c_int, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "f3ps_slab_route": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+        "f3ps_slab_array": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int)]),
+        "f3ps_slab_set_voxels": (C.c_int, [vp, vp, vp, vp, i64, i64, i64]),
+        "f3ps_slab_expand_begin": (C.c_int, [vp]),
+        "f3ps_slab_expand_sweep": (C.c_int, [vp, vp]),
+        "f3ps_slab_expand_round_end": (C.c_int, [vp]),
+        "f3ps_slab_expand_end": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -117,7 +128,10 @@ EXPORTED = ["f3ps_create", "f3ps_destroy", "f3ps_last_error", "f3ps_version", "f
             "f3ps_get_supervoxels", "f3ps_get_supervoxel_voxels", "f3ps_get_adjacency", "f3ps_get_edges", "f3ps_get_cdf",
             "f3ps_get_merge_log", "f3ps_get_state_regions", "f3ps_get_state_edges", "f3ps_get_labeled_cloud", "f3ps_get_region_mean_color",
             "f3ps_get_voxel_segments_device", "f3ps_stage_ms", "f3ps_launch_count", "f3ps_merge_profile", "f3ps_expand_profile", "f3ps_test_rgb2lab",
-            "f3ps_test_lab_ciede00", "f3ps_test_rgb_eucl", "f3ps_test_sort_pairs"]
+            "f3ps_test_lab_ciede00", "f3ps_test_rgb_eucl", "f3ps_test_sort_pairs",
+            "f3ps_slab_reset", "f3ps_slab_bbox", "f3ps_slab_set_frame", "f3ps_slab_keys", "f3ps_slab_route", "f3ps_slab_array",
+            "f3ps_slab_set_voxels", "f3ps_slab_expand_begin", "f3ps_slab_expand_sweep", "f3ps_slab_expand_round_end",
+            "f3ps_slab_expand_end"]
 
 
 def _p(a):
@@ -309,6 +323,39 @@ class Segmenter:
         idx = np.zeros(cap, np.int32); off = np.zeros(c.n_supervoxels + 1, np.int64)
         self._chk(self.L.f3ps_get_supervoxel_voxels(self.h, _p(idx), _p(off), cap, c.n_supervoxels))
         return idx[:off[-1]], off
+
+    # ---- slab mode (per-rank pieces; f3ps/slab.py issues the exchanges between them) ----
+    SLAB_ARRAYS = {"vox_xyz": 0, "vox_rgb": 1, "vox_key": 2, "vox_normal": 3, "vox_curv": 4, "steal": 5, "owner_next": 6,
+                   "dist": 7, "count": 8}
+
+    def slab_reset(self): self._chk(self.L.f3ps_slab_reset(self.h))
+    def slab_bbox(self, d_box8): self._chk(self.L.f3ps_slab_bbox(self.h, C.c_void_p(d_box8)))
+    def slab_set_frame(self, d_box8): self._chk(self.L.f3ps_slab_set_frame(self.h, C.c_void_p(d_box8)))
+
+    def slab_keys(self, top_bits, d_hist):
+        used, shift = C.c_int(), C.c_int()
+        self._chk(self.L.f3ps_slab_keys(self.h, top_bits, C.c_void_p(d_hist), C.byref(used), C.byref(shift)))
+        return used.value, shift.value
+
+    def slab_route(self, world, splitters, d_send):
+        sp = np.ascontiguousarray(splitters, np.uint64)
+        counts = np.zeros(world, np.int64)
+        self._chk(self.L.f3ps_slab_route(self.h, world, _p(sp) if world > 1 else None, C.c_void_p(d_send), _p(counts)))
+        return counts
+
+    def slab_array(self, name):
+        """(device pointer, elements, bytes per element) of an array the slab driver exchanges in place."""
+        ptr, n, eb = C.c_void_p(), C.c_int64(), C.c_int()
+        self._chk(self.L.f3ps_slab_array(self.h, self.SLAB_ARRAYS[name], C.byref(ptr), C.byref(n), C.byref(eb)))
+        return (ptr.value or 0), n.value, eb.value
+
+    def slab_set_voxels(self, d_xyz, d_rgb, d_key, n_voxels, own_begin, own_end):
+        self._chk(self.L.f3ps_slab_set_voxels(self.h, C.c_void_p(d_xyz), C.c_void_p(d_rgb), C.c_void_p(d_key), n_voxels, own_begin, own_end))
+
+    def slab_expand_begin(self): self._chk(self.L.f3ps_slab_expand_begin(self.h))
+    def slab_expand_sweep(self, d_changed): self._chk(self.L.f3ps_slab_expand_sweep(self.h, C.c_void_p(d_changed)))
+    def slab_expand_round_end(self): self._chk(self.L.f3ps_slab_expand_round_end(self.h))
+    def slab_expand_end(self): self._chk(self.L.f3ps_slab_expand_end(self.h))
 
     # ---- device self tests ----
     def test_rgb2lab(self, rgb255):

@@ -159,6 +159,40 @@ int f3ps_get_labeled_cloud(f3ps_ctx* ctx, float* xyz /*[n][3]*/, uint32_t* label
 /* per-voxel final segment label (dense, 0xffffffff = unowned) resident on the device; for device consumers */
 int f3ps_get_voxel_segments_device(f3ps_ctx* ctx, const uint32_t** device_ptr, int64_t* n);
 
+/* ---- slab mode: one very large cloud cut into spatial slabs, one per GPU (BASELINE config 5) ----
+ * Replaces, for one scan too large or too slow for one device, the same calls as above
+ * (pcl::SupervoxelClustering::extract, supervoxel_clustering.cpp:357).  A slab is a contiguous range of the x-major
+ * Morton key, i.e. of PCL's leaf index, so every rank's voxels are a contiguous slice of the single-GPU voxel table and
+ * all ordered sums keep their order: results are bit-identical to one handle processing the whole cloud.
+ * These entry points are the per-rank pieces; the caller issues the exchanges between them on the handle's stream
+ * (f3ps/slab.py does it with torch.distributed / NCCL):
+ *   f3ps_set_input(local points) -> f3ps_slab_bbox -> [all-reduce MIN/MAX] -> f3ps_slab_set_frame -> f3ps_slab_keys
+ *   -> [all-reduce SUM histogram; choose splitters] -> f3ps_slab_route -> [all-to-all points] -> f3ps_set_input(received,
+ *   stride 16, on device) -> f3ps_voxelize -> [all-gather voxel slices] -> f3ps_slab_set_voxels -> f3ps_neighbors ->
+ *   f3ps_normals (owned slice) -> [all-gather normal slices] -> f3ps_seeds -> f3ps_slab_expand_begin -> per round {
+ *   f3ps_slab_expand_sweep -> [all-gather steal slices, all-reduce MAX flag] until 0; [all-gather owner slices, all-reduce SUM
+ *   counts]; f3ps_slab_expand_round_end } -> [all-gather distance slices] -> f3ps_slab_expand_end -> f3ps_graph -> f3ps_merge.
+ * K7 does not shard (strictly serial order over one graph): every rank replays it on the gathered graph. */
+enum f3ps_slab_array_id {
+    F3PS_SLAB_VOX_XYZ = 0, F3PS_SLAB_VOX_RGB = 1, F3PS_SLAB_VOX_KEY = 2, F3PS_SLAB_VOX_NORMAL = 3, F3PS_SLAB_VOX_CURV = 4,
+    F3PS_SLAB_STEAL = 5,       /* steal table written by the last sweep [V] u32 */
+    F3PS_SLAB_OWNER_NEXT = 6,  /* owner words the converged sweep wrote [V] u32 */
+    F3PS_SLAB_DIST = 7,        /* stored distances of the current round state [V] f32 */
+    F3PS_SLAB_COUNT = 8        /* helper sizes tallied by the last sweep over the owned slice [S0 + 2] u32 */
+};
+int f3ps_slab_reset(f3ps_ctx* ctx);
+int f3ps_slab_bbox(f3ps_ctx* ctx, uint32_t* d_box8);
+int f3ps_slab_set_frame(f3ps_ctx* ctx, const uint32_t* d_box8);
+int f3ps_slab_keys(f3ps_ctx* ctx, int top_bits, uint32_t* d_hist, int* used_bits, int* shift);
+int f3ps_slab_route(f3ps_ctx* ctx, int world, const uint64_t* splitters, void* d_send, int64_t* counts);
+int f3ps_slab_array(f3ps_ctx* ctx, int which, void** ptr, int64_t* n, int* elem_bytes);
+int f3ps_slab_set_voxels(f3ps_ctx* ctx, const void* d_xyz, const void* d_rgb, const void* d_key, int64_t n_voxels,
+                         int64_t own_begin, int64_t own_end);
+int f3ps_slab_expand_begin(f3ps_ctx* ctx);
+int f3ps_slab_expand_sweep(f3ps_ctx* ctx, uint32_t* d_changed);
+int f3ps_slab_expand_round_end(f3ps_ctx* ctx);
+int f3ps_slab_expand_end(f3ps_ctx* ctx);
+
 /* CUDA-event time of the last run of a stage, ms (valid after f3ps_sync) */
 int f3ps_stage_ms(f3ps_ctx* ctx, int stage, float* ms);
 /* Profiling aid: SM cycles (clock64) the last f3ps_merge spent per phase, and event counts.
