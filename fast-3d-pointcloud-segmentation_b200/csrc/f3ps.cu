@@ -749,14 +749,18 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
                 }
             } else {
                 const size_t per = ((size_t)Ec * 4 + 255) & ~(size_t)255, per8 = ((size_t)Ec * 8 + 255) & ~(size_t)255;
-                F3PS_CUDA_OK(ctx->merge_scratch.ensure(6 * per + 2 * per8 + per));
+                F3PS_CUDA_OK(ctx->merge_scratch.ensure(6 * per + 2 * per8 + per + per8));
                 char* sp = (char*)ctx->merge_scratch.p;
                 MergeScratch scr;
                 scr.st[0] = (long long*)sp; sp += per8; scr.st[1] = (long long*)sp; sp += per8;
                 scr.e[0] = (int*)sp; sp += per; scr.e[1] = (int*)sp; sp += per; scr.w[0] = (float*)sp; sp += per; scr.w[1] = (float*)sp; sp += per;
-                scr.x[0] = (unsigned*)sp; sp += per; scr.x[1] = (unsigned*)sp; sp += per; scr.cls = (unsigned char*)sp;
-                LAUNCH(ctx, merge_kernel, 1, kMergeThreads, 0, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
-                       ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr);
+                scr.x[0] = (unsigned*)sp; sp += per; scr.x[1] = (unsigned*)sp; sp += per; scr.cls = (unsigned char*)sp; sp += per;
+                if (S < 65536u)
+                    LAUNCH(ctx, merge_kernel<unsigned>, 1, kMergeThreads, 0, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
+                           ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr, (unsigned*)sp, ctx->pos_data);
+                else
+                    LAUNCH(ctx, merge_kernel<unsigned long long>, 1, kMergeThreads, 0, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
+                           ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr, (unsigned long long*)sp, ctx->pos_data);
                 ctx->merge_path = 2;
             }
             rc = mark(ctx, 10); if (rc) return rc;

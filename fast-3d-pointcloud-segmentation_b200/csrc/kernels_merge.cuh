@@ -28,37 +28,117 @@ __device__ __forceinline__ bool key_less(float w1, long long s1, float w2, long 
     return w1 < w2 || (w1 == w2 && s1 < s2);
 }
 
+// Ordered fold of the voxels pos_data[s..e) onto a region, one accumulator chain per lane (same scalar sequence as
+// stats_step, src/color_utilities.cpp:130-134 + computeMeanAndCovarianceMatrix): lanes 0..8 the nine raw sums, lanes 9..11 the
+// running colour mean; the 32 voxels of a batch are loaded, squared and their reciprocals 1/k prepared by all lanes at once.
+// `v` is this lane's chain value, `cnt` the (uniform) voxel count as float.  Requires cnt + 64 < 2^24 (exact integer floats).
+__device__ __forceinline__ void fold_run_lanes(float& v, float& cnt, const float4* __restrict__ pos_data, unsigned s, unsigned e,
+                                               float* __restrict__ stage, int lane) {
+    for (unsigned base = s; base < e; base += 64) {                 // two batches of 32 voxels in flight
+        const unsigned m = min(64u, e - base);
+        float4 p[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) if (base + 32u * h + lane < e) p[h] = __ldcg(pos_data + base + 32u * h + lane);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (base + 32u * h + lane < e) {
+                const uint32_t c = __float_as_uint(p[h].w);
+                float* row = stage + (32 * h + lane) * 13;
+                row[0] = p[h].x * p[h].x; row[1] = p[h].x * p[h].y; row[2] = p[h].x * p[h].z; row[3] = p[h].y * p[h].y; row[4] = p[h].y * p[h].z; row[5] = p[h].z * p[h].z;
+                row[6] = p[h].x; row[7] = p[h].y; row[8] = p[h].z;
+                row[9] = (float)((c >> 16) & 255u); row[10] = (float)((c >> 8) & 255u); row[11] = (float)(c & 255u);
+                row[12] = 1 / (cnt + (float)(32 * h + lane + 1));
+            }
+        }
+        __syncwarp();
+        if (lane < 9) { for (unsigned j = 0; j < m; ++j) v += stage[j * 13 + lane]; }
+        else if (lane < 12) { for (unsigned j = 0; j < m; ++j) v = v + stage[j * 13 + 12] * (stage[j * 13 + lane] - v); }
+        cnt += (float)m;
+        __syncwarp();
+    }
+}
+
+// packed endpoints of an edge for the incidence scan: 16 + 16 bits when the graph has < 65,536 regions, else 32 + 32
+template <typename PK> struct PkOps;
+template <> struct PkOps<unsigned> {
+    static constexpr unsigned kDead = 0xffffffffu;
+    static __device__ __forceinline__ unsigned pack(unsigned a, unsigned b) { return (a << 16) | b; }
+    static __device__ __forceinline__ unsigned lo(unsigned p) { return p >> 16; }
+    static __device__ __forceinline__ unsigned hi(unsigned p) { return p & 0xffffu; }
+};
+template <> struct PkOps<unsigned long long> {
+    static constexpr unsigned long long kDead = ~0ull;
+    static __device__ __forceinline__ unsigned long long pack(unsigned a, unsigned b) { return ((unsigned long long)a << 32) | b; }
+    static __device__ __forceinline__ unsigned lo(unsigned long long p) { return (unsigned)(p >> 32); }
+    static __device__ __forceinline__ unsigned hi(unsigned long long p) { return (unsigned)p; }
+};
+
+constexpr int kMergeTcap = 1024;       // touched edges of one merge handled in shared memory; more go through the global scratch
+
+// The general kernel: any S, E, T; everything in global memory (L2-resident), one CTA.
+//   head      : every thread caches the minimum of its own contiguous strip of edges and rescans the strip only after one of
+//               its edges was re-weighted or died ("dirty"), so a merge costs O(T * E / 1024) loads instead of O(E)
+//   incidence : one packed word per edge (16 + 16 or 32 + 32 bits), eight independent loads in flight per thread
+//   ordering / dedupe / tie stamps of the <= 1024 touched edges in shared memory (ballot prefix counts for the stamps)
+template <typename PK>
 __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R, EdgeArrays E, const unsigned* __restrict__ n_edges_ptr,
         const unsigned* __restrict__ n_sv_ptr, EdgeParams ep, const float* __restrict__ lambda_dev, float threshold,
         const unsigned* __restrict__ run_start, const unsigned* __restrict__ run_end, const unsigned* __restrict__ order,
-        const float4* __restrict__ vox_xyz, const unsigned* __restrict__ sv_label, MergeLog mlog, unsigned log_cap, MergeCtl* ctl, MergeScratch scr) {
+        const float4* __restrict__ vox_xyz, const unsigned* __restrict__ sv_label, MergeLog mlog, unsigned log_cap, MergeCtl* ctl, MergeScratch scr,
+        PK* __restrict__ pk, const float4* __restrict__ pos_data) {
+    typedef PkOps<PK> P;
     __shared__ float s_rw[32]; __shared__ long long s_rs[32]; __shared__ int s_ri[32];
     __shared__ int s_head; __shared__ float s_head_w;
     __shared__ int s_tcount;
-    int* const s_e[2] = {scr.e[0], scr.e[1]}; float* const s_w[2] = {scr.w[0], scr.w[1]}; long long* const s_st[2] = {scr.st[0], scr.st[1]};
-    unsigned* const s_x[2] = {scr.x[0], scr.x[1]}; unsigned char* const s_class = scr.cls;     // global scratch, capacity = E
+    __shared__ int sm_e[2][kMergeTcap]; __shared__ float sm_w[2][kMergeTcap]; __shared__ long long sm_st[2][kMergeTcap];
+    __shared__ unsigned sm_x[2][kMergeTcap]; __shared__ unsigned char sm_cls[kMergeTcap];
+    __shared__ unsigned char s_dirty[kMergeThreads];
+    __shared__ unsigned s_wb[32], s_wf[32], s_wd[32];
+    __shared__ float s_stage[64 * 13];
     __shared__ unsigned s_nm, s_ealive, s_ralive; __shared__ long long s_counter;
     __shared__ unsigned long long s_fold;
+    __shared__ unsigned s_maxT;
     unsigned long long pc[6] = {0, 0, 0, 0, 0, 0};
     long long t_prev = clock64();
+#undef PHASE
 #define PHASE(i) do { if (tid == 0) { long long t_now = clock64(); pc[i] += (unsigned long long)(t_now - t_prev); t_prev = t_now; } } while (0)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned nE = *n_edges_ptr;
     if (lambda_dev) ep.lambda = *lambda_dev;
-    if (tid == 0) { s_nm = 0; s_ealive = nE; s_ralive = *n_sv_ptr; s_counter = (long long)nE; s_fold = 0; }
-    __syncthreads();
+    if (tid == 0) { s_nm = 0; s_ealive = nE; s_ralive = *n_sv_ptr; s_counter = (long long)nE; s_fold = 0; s_maxT = 0; }
     const float INF = __int_as_float(0x7f800000);
     enum { C_KEEP = 0, C_FRONT = 1, C_BACK = 2, C_DUP = 3 };
+    // strip of this thread and its cached minimum
+    // thread (warp w, lane l) owns the edges w * 32 K + 32 j + l, j < K: a warp's strips interleave, so its rescans coalesce
+    const unsigned K = max(1u, (nE + kMergeThreads - 1) / kMergeThreads), W = 32u * K;
+    const unsigned my_base = (unsigned)warp * W + (unsigned)lane;
+#define F3PS_OWNER(e) ((((unsigned)(e)) / W) * 32u + (((unsigned)(e)) & 31u))
+    float cw = INF; long long cs = kDeadStamp; int ci = -1;
+    s_dirty[tid] = 1;
+    for (unsigned e = tid; e < nE; e += kMergeThreads) pk[e] = E.stamp[e] == kDeadStamp ? P::kDead : P::pack(E.a[e], E.b[e]);
+    __threadfence();
+    __syncthreads();
 
     while (true) {
         // ---- A: head of the weight map = argmin (w, stamp) -------------------------------
-        float bw = INF; long long bs = kDeadStamp; int bi = -1;
-        for (unsigned e = tid; e < nE; e += kMergeThreads) {
-            const long long st = E.stamp[e];
-            if (st == kDeadStamp) continue;
-            const float w = E.w[e];
-            if (bi < 0 || key_less(w, st, bw, bs)) { bw = w; bs = st; bi = (int)e; }
+        if (s_dirty[tid]) {
+            s_dirty[tid] = 0;
+            cw = INF; cs = kDeadStamp; ci = -1;
+            for (unsigned j0 = 0; j0 < K; j0 += 8) {
+                long long st[8]; float w[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const unsigned e = my_base + (j0 + k) * 32u;
+                    const bool in = j0 + k < K && e < nE;
+                    st[k] = in ? __ldcg(E.stamp + e) : kDeadStamp;
+                    w[k] = in ? __ldcg(E.w + e) : INF;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (st[k] != kDeadStamp && (ci < 0 || key_less(w[k], st[k], cw, cs))) { cw = w[k]; cs = st[k]; ci = (int)(my_base + (j0 + k) * 32u); }
+            }
         }
+        float bw = cw; long long bs = cs; int bi = ci;
 #pragma unroll
         for (int off = 16; off; off >>= 1) {
             const float ow = __shfl_xor_sync(kFull, bw, off); const long long os = __shfl_xor_sync(kFull, bs, off);
@@ -89,16 +169,37 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R,
                 mlog.a[m] = sv_label[a]; mlog.b[m] = sv_label[b]; mlog.w[m] = s_head_w;
                 mlog.edges_left[m] = s_ealive; mlog.regions_left[m] = s_ralive;
             }
-            E.stamp[head] = kDeadStamp;
+            E.stamp[head] = kDeadStamp; pk[head] = P::kDead;
+            s_dirty[F3PS_OWNER(head)] = 1;
         }
         // ---- B: fold (warp 0)  ||  touched-edge scan (warps 1..31) -----------------------
         if (warp == 0) {
             RegionStats st; load_stats(R, (int)a, st);
             unsigned long long steps = 0;
-            for (int run = R.head[b]; run >= 0; run = R.next_run[run]) {
-                const unsigned rs = run_start[run], re = run_end[run];
-                fold_run(st, order, rs, re, vox_xyz, lane);       // voxels_ = a ++ b  (:408)
-                steps += re - rs;
+            if (pos_data && st.cnt + (float)R.n[b] < 16000000.0f) {     // one chain per lane
+                float v = lane < 9 ? st.accu[lane] : (lane == 9 ? st.r : (lane == 10 ? st.g : st.b));
+                float cnt = st.cnt;
+                int run = R.head[b];
+                unsigned rs = run_start[run], re = run_end[run];
+                int nxt = R.next_run[run];
+                while (true) {                                                 // the next run's bounds travel while this one folds
+                    unsigned nrs = 0, nre = 0; int nnxt = -1;
+                    if (nxt >= 0) { nrs = run_start[nxt]; nre = run_end[nxt]; nnxt = R.next_run[nxt]; }
+                    fold_run_lanes(v, cnt, pos_data, rs, re, s_stage, lane);       // voxels_ = a ++ b  (:408)
+                    steps += re - rs;
+                    if (nxt < 0) break;
+                    rs = nrs; re = nre; nxt = nnxt;
+                }
+#pragma unroll
+                for (int k = 0; k < 9; ++k) st.accu[k] = __shfl_sync(kFull, v, k);
+                st.r = __shfl_sync(kFull, v, 9); st.g = __shfl_sync(kFull, v, 10); st.b = __shfl_sync(kFull, v, 11);
+                st.cnt = cnt; st.n += (int)steps;
+            } else {
+                for (int run = R.head[b]; run >= 0; run = R.next_run[run]) {
+                    const unsigned rs = run_start[run], re = run_end[run];
+                    fold_run(st, order, rs, re, vox_xyz, lane);       // voxels_ = a ++ b  (:408)
+                    steps += re - rs;
+                }
             }
             if (lane == 0) {
                 store_stats(R, (int)a, st);
@@ -117,27 +218,42 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R,
                 s_fold += steps;
             }
         } else {
-            for (unsigned e = tid - 32; e < nE; e += kMergeThreads - 32) {
-                if (E.stamp[e] == kDeadStamp || (int)e == head) continue;
-                const unsigned ea = E.a[e], eb = E.b[e];
-                if (ea == a || eb == a || ea == b || eb == b) {
-                    const int slot = atomicAdd(&s_tcount, 1);
-                    s_e[0][slot] = (int)e;
+            constexpr unsigned kScan = kMergeThreads - 32;
+            for (unsigned base = tid - 32; base < nE; base += kScan * 8) {
+                PK p[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const unsigned e = base + k * kScan; p[k] = e < nE ? __ldcg(pk + e) : P::kDead; }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (p[k] == P::kDead) continue;
+                    const unsigned e = base + k * kScan;
+                    const unsigned ea = P::lo(p[k]), eb = P::hi(p[k]);
+                    if ((int)e != head && (ea == a || eb == a || ea == b || eb == b)) {
+                        const int slot = atomicAdd(&s_tcount, 1);
+                        const unsigned x = (ea == a || ea == b) ? eb : ea;
+                        if (slot < kMergeTcap) { sm_e[0][slot] = (int)e; sm_x[0][slot] = x; } else { scr.e[0][slot] = (int)e; scr.x[0][slot] = x; }
+                    }
                 }
             }
         }
-        __threadfence();
         __syncthreads();
         PHASE(1);
         const int T = s_tcount;
+        const bool big = T > kMergeTcap;
+        if (big) {                                                   // rare: continue in the global scratch
+            for (int i = tid; i < kMergeTcap; i += kMergeThreads) { scr.e[0][i] = sm_e[0][i]; scr.x[0][i] = sm_x[0][i]; }
+            __syncthreads();
+        }
+        int* const s_e[2] = {big ? scr.e[0] : sm_e[0], big ? scr.e[1] : sm_e[1]};
+        float* const s_w[2] = {big ? scr.w[0] : sm_w[0], big ? scr.w[1] : sm_w[1]};
+        long long* const s_st[2] = {big ? scr.st[0] : sm_st[0], big ? scr.st[1] : sm_st[1]};
+        unsigned* const s_x[2] = {big ? scr.x[0] : sm_x[0], big ? scr.x[1] : sm_x[1]};
+        unsigned char* const s_class = big ? scr.cls : sm_cls;
         // ---- C: order the touched edges by their old key ---------------------------------
         for (int i = tid; i < T; i += kMergeThreads) {
             const int e = s_e[0][i];
             s_w[0][i] = E.w[e]; s_st[0][i] = E.stamp[e];
-            const unsigned ea = E.a[e], eb = E.b[e];
-            s_x[0][i] = (ea == a || ea == b) ? eb : ea;
         }
-        __threadfence();
         __syncthreads();
         for (int i = tid; i < T; i += kMergeThreads) {
             const float w = s_w[0][i]; const long long st = s_st[0][i];
@@ -145,7 +261,6 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R,
             for (int j = 0; j < T; ++j) r += key_less(s_w[0][j], s_st[0][j], w, st) ? 1 : 0;
             s_e[1][r] = s_e[0][i]; s_w[1][r] = w; s_st[1][r] = st; s_x[1][r] = s_x[0][i];
         }
-        __threadfence();
         __syncthreads();
         PHASE(2);
         // ---- D: dedupe (earlier survives), recompute, classify ---------------------------
@@ -167,45 +282,80 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R,
                 s_w[0][i] = w_new;                                 // slot 0 of the scratch is free again: new weights
             }
         }
-        __threadfence();
         __syncthreads();
         PHASE(3);
         // ---- E: tie stamps (C.2) and write back -------------------------------------------
-        for (int i = tid; i < T; i += kMergeThreads) {
-            const int cls = s_class[i];
-            const int e = s_e[1][i];
-            if (cls == C_DUP) E.stamp[e] = kDeadStamp;
-            else {
-                int nb = 0, nf = 0, rb = 0, rf = 0;
-                for (int q = 0; q < T; ++q) {
-                    const int c = s_class[q];
-                    nb += (c == C_BACK); nf += (c == C_FRONT);
-                    if (q < i) { rb += (c == C_BACK); rf += (c == C_FRONT); }
+        if (!big) {
+            // one entry per thread: ranks among the BACK / FRONT classes from ballots
+            const int cls = tid < T ? (int)s_class[tid] : -1;
+            const unsigned mb = __ballot_sync(kFull, cls == C_BACK), mf = __ballot_sync(kFull, cls == C_FRONT), md = __ballot_sync(kFull, cls == C_DUP);
+            if (lane == 0) { s_wb[warp] = __popc(mb); s_wf[warp] = __popc(mf); s_wd[warp] = __popc(md); }
+            __syncthreads();
+            int nb = 0, nf = 0, nd = 0, rb = 0, rf = 0;
+#pragma unroll
+            for (int w = 0; w < 32; ++w) {
+                const int wb = (int)s_wb[w], wf = (int)s_wf[w];
+                nb += wb; nf += wf; nd += (int)s_wd[w];
+                if (w < warp) { rb += wb; rf += wf; }
+            }
+            const unsigned lt = (1u << lane) - 1u;
+            rb += __popc(mb & lt); rf += __popc(mf & lt);
+            if (tid < T) {
+                const int e = s_e[1][tid];
+                if (cls == C_DUP) { E.stamp[e] = kDeadStamp; pk[e] = P::kDead; }
+                else {
+                    long long st = s_st[1][tid];
+                    if (cls == C_BACK) st = s_counter + rb;
+                    else if (cls == C_FRONT) st = -(s_counter + nb + (nf - 1 - rf));
+                    const unsigned x = s_x[1][tid];
+                    E.a[e] = min(a, x); E.b[e] = max(a, x); E.w[e] = s_w[0][tid]; E.stamp[e] = st;
+                    pk[e] = P::pack(min(a, x), max(a, x));
                 }
-                long long st = s_st[1][i];
-                if (cls == C_BACK) st = s_counter + rb;
-                else if (cls == C_FRONT) st = -(s_counter + nb + (nf - 1 - rf));
-                const unsigned x = s_x[1][i];
-                E.a[e] = min(a, x); E.b[e] = max(a, x); E.w[e] = s_w[0][i]; E.stamp[e] = st;
+                s_dirty[F3PS_OWNER(e)] = 1;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                s_counter += nb + nf;
+                s_ealive -= 1 + nd; s_ralive -= 1; s_nm += 1;
+                if ((unsigned)T > s_maxT) s_maxT = (unsigned)T;
+            }
+        } else {
+            for (int i = tid; i < T; i += kMergeThreads) {
+                const int cls = s_class[i];
+                const int e = s_e[1][i];
+                if (cls == C_DUP) { E.stamp[e] = kDeadStamp; pk[e] = P::kDead; }
+                else {
+                    int nb = 0, nf = 0, rb = 0, rf = 0;
+                    for (int q = 0; q < T; ++q) {
+                        const int c = s_class[q];
+                        nb += (c == C_BACK); nf += (c == C_FRONT);
+                        if (q < i) { rb += (c == C_BACK); rf += (c == C_FRONT); }
+                    }
+                    long long st = s_st[1][i];
+                    if (cls == C_BACK) st = s_counter + rb;
+                    else if (cls == C_FRONT) st = -(s_counter + nb + (nf - 1 - rf));
+                    const unsigned x = s_x[1][i];
+                    E.a[e] = min(a, x); E.b[e] = max(a, x); E.w[e] = s_w[0][i]; E.stamp[e] = st;
+                    pk[e] = P::pack(min(a, x), max(a, x));
+                }
+                s_dirty[F3PS_OWNER(e)] = 1;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int nb = 0, nf = 0, nd = 0;
+                for (int q = 0; q < T; ++q) { const int c = s_class[q]; nb += (c == C_BACK); nf += (c == C_FRONT); nd += (c == C_DUP); }
+                s_counter += nb + nf;
+                s_ealive -= 1 + nd; s_ralive -= 1; s_nm += 1;
+                if ((unsigned)T > s_maxT) s_maxT = (unsigned)T;
             }
         }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            int nb = 0, nf = 0, nd = 0;
-            for (int q = 0; q < T; ++q) { const int c = s_class[q]; nb += (c == C_BACK); nf += (c == C_FRONT); nd += (c == C_DUP); }
-            s_counter += nb + nf;
-            s_ealive -= 1 + nd; s_ralive -= 1; s_nm += 1;
-            if ((unsigned)T > ctl->max_touched) ctl->max_touched = (unsigned)T;
-        }
-        __threadfence();
         __syncthreads();
         PHASE(4);
     }
     if (tid == 0) {
         for (int i = 0; i < 6; ++i) ctl->phase_cycles[i] = pc[i];
         ctl->n_merges = s_nm; ctl->edges_alive = s_ealive; ctl->regions_alive = s_ralive; ctl->counter = s_counter;
-        ctl->fold_steps = s_fold;
+        ctl->fold_steps = s_fold; ctl->max_touched = s_maxT;
     }
 }
 

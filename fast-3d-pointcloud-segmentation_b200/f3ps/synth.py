@@ -128,3 +128,74 @@ def pack_points(xyz, rgba):
 def make_dense_scene(seed=40000, width=3652, height=2740):
     """C4: the same scene family at ~10 M rays, z in [0.5, 4] m."""
     return make_frame(seed=seed, width=width, height=height, zmin=0.5, zmax=4.0)
+
+
+# ---- C5: merged room scan (SURVEY.md section 8d) ------------------------------------------------------------
+ROOM_SCANS = 40
+
+
+def _room_surfaces(rng):
+    """Axis-aligned rectangles (origin, edge u, edge v, colour) of a 6 x 3 x 8 m room (x, y, z) translated so that
+    z stays in [1, 9] m (main() folds z < 0 and the VCCS transform takes ln z), plus box-shaped furniture."""
+    x0, x1, y0, y1, z0, z1 = -3.0, 3.0, -1.5, 1.5, 1.0, 9.0
+    S = []
+
+    def rect(o, u, v, col):
+        S.append((np.array(o, float), np.array(u, float), np.array(v, float), np.array(col, float)))
+
+    rect((x0, y1, z0), (x1 - x0, 0, 0), (0, 0, z1 - z0), rng.integers(60, 200, 3))          # floor
+    rect((x0, y0, z0), (x1 - x0, 0, 0), (0, 0, z1 - z0), rng.integers(180, 250, 3))         # ceiling
+    rect((x0, y0, z0), (0, y1 - y0, 0), (0, 0, z1 - z0), rng.integers(100, 230, 3))         # walls
+    rect((x1, y0, z0), (0, y1 - y0, 0), (0, 0, z1 - z0), rng.integers(100, 230, 3))
+    rect((x0, y0, z1), (x1 - x0, 0, 0), (0, y1 - y0, 0), rng.integers(100, 230, 3))
+    rect((x0, y0, z0), (x1 - x0, 0, 0), (0, y1 - y0, 0), rng.integers(100, 230, 3))
+    for _ in range(18):                                                                     # furniture: boxes on the floor
+        hx, hy, hz = rng.uniform(0.2, 0.7), rng.uniform(0.2, 0.9), rng.uniform(0.2, 0.7)
+        cx, cz = rng.uniform(x0 + 0.8, x1 - 0.8), rng.uniform(z0 + 0.8, z1 - 0.8)
+        lo = np.array([cx - hx, y1 - 2 * hy, cz - hz]); hi = np.array([cx + hx, y1, cz + hz])
+        col = rng.integers(20, 236, 3)
+        d = hi - lo
+        rect(lo, (d[0], 0, 0), (0, 0, d[2]), col)                                           # top
+        rect(lo, (d[0], 0, 0), (0, d[1], 0), col); rect((lo[0], lo[1], hi[2]), (d[0], 0, 0), (0, d[1], 0), col)
+        rect(lo, (0, d[1], 0), (0, 0, d[2]), col); rect((hi[0], lo[1], lo[2]), (0, d[1], 0), (0, 0, d[2]), col)
+    return S
+
+
+def make_room_scan(seed=50000, n_points=50_000_000, scans=None):
+    """C5: a room scanned from ROOM_SCANS positions and merged; `scans` (an iterable of scan numbers) selects the
+    share of one rank -- the cloud of all scans in ascending order is the concatenation of the shares.
+    Every scan samples the surfaces with a density falling off with the distance from its position, adds 2 mm range
+    noise and per-point colour noise.  Returns POINT_DTYPE records (no NaNs: merged scans are unorganised)."""
+    rng0 = np.random.default_rng(seed)
+    S = _room_surfaces(rng0)
+    area = np.array([np.linalg.norm(np.cross(u, v)) for _, u, v, _ in S])
+    pos = np.stack([rng0.uniform(-2.2, 2.2, ROOM_SCANS), rng0.uniform(-0.3, 0.6, ROOM_SCANS), rng0.uniform(1.8, 8.2, ROOM_SCANS)], 1)
+    per_scan = n_points // ROOM_SCANS
+    scans = range(ROOM_SCANS) if scans is None else scans
+    out = []
+    for s in scans:
+        rng = np.random.default_rng(seed + 1 + s)
+        n = per_scan + (n_points - per_scan * ROOM_SCANS if s == ROOM_SCANS - 1 else 0)
+        # importance: surface area / squared distance of its centre from the scanner
+        ctr = np.stack([o + 0.5 * u + 0.5 * v for o, u, v, _ in S])
+        w = area / np.maximum(0.25, ((ctr - pos[s]) ** 2).sum(1))
+        which = rng.choice(len(S), size=n, p=w / w.sum())
+        O = np.stack([q[0] for q in S])[which]; U = np.stack([q[1] for q in S])[which]; Vv = np.stack([q[2] for q in S])[which]
+        a = rng.random((n, 1)); b = rng.random((n, 1))
+        p = O + a * U + b * Vv
+        ray = p - pos[s]
+        rl = np.linalg.norm(ray, axis=1, keepdims=True)
+        p = p + ray / np.maximum(rl, 1e-6) * rng.normal(0.0, 0.002, (n, 1))
+        p[:, 2] = np.clip(p[:, 2], 0.9, 9.2)
+        col = np.stack([q[3] for q in S])[which]
+        col = np.clip(np.rint(col + rng.normal(0.0, 4.0, col.shape)), 0, 255).astype(np.uint32)
+        rgba = (np.uint32(255) << np.uint32(24)) | (col[:, 0] << np.uint32(16)) | (col[:, 1] << np.uint32(8)) | col[:, 2]
+        out.append(pack_points(p.astype(np.float32), rgba.astype(np.uint32)))
+    if not out:
+        return np.zeros(0, POINT_DTYPE)
+    return np.concatenate(out)
+
+
+def room_scan_share(rank, world):
+    """Scan numbers of rank `rank`: contiguous, so that the shares concatenate to the full cloud in scan order."""
+    return range(ROOM_SCANS * rank // world, ROOM_SCANS * (rank + 1) // world)
