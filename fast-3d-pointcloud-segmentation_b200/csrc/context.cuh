@@ -14,6 +14,7 @@
 #include "kernels_merge.cuh"
 #include "kernels_merge_fast.cuh"
 #include "kernels_merge_cluster.cuh"
+#include "kernels_eval.cuh"
 
 namespace f3ps {
 
@@ -116,6 +117,8 @@ struct f3ps_ctx {
     bool slab_frame = false; f3ps::FrameParams slab_fp{};
     bool slab_range = false; unsigned own_begin = 0, own_end = 0;
     f3ps::DevBuf slab_dest, slab_tot;
+    f3ps::DevBuf ev_parent, ev_when, ev_dense, ev_truth, ev_table;   // f3ps_eval_thresholds
     f3ps::ExpandArgs slab_A{}; int slab_cur = 0; unsigned slab_k = 0; unsigned slab_sweeps = 0; int slab_round = 0; bool slab_expanding = false;
+    bool general_attr_set = false;
     bool lambda_attr_set = false, fast_attr_set[4] = {false, false, false, false};
 };

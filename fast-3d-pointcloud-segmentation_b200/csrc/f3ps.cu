@@ -749,17 +749,27 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
                 }
             } else {
                 const size_t per = ((size_t)Ec * 4 + 255) & ~(size_t)255, per8 = ((size_t)Ec * 8 + 255) & ~(size_t)255;
-                F3PS_CUDA_OK(ctx->merge_scratch.ensure(6 * per + 2 * per8 + per + per8));
+                unsigned n2 = 2048; while (n2 < Ec) n2 <<= 1;
+                const size_t perS = ((size_t)Sc * 4 + 255) & ~(size_t)255, sortb = (size_t)n2 * sizeof(MergeSortRec);
+                F3PS_CUDA_OK(ctx->merge_scratch.ensure(6 * per + 2 * per8 + per + per8 + perS + sortb));
                 char* sp = (char*)ctx->merge_scratch.p;
                 MergeScratch scr;
                 scr.st[0] = (long long*)sp; sp += per8; scr.st[1] = (long long*)sp; sp += per8;
+                scr.sortbuf = (MergeSortRec*)sp; sp += sortb;
                 scr.e[0] = (int*)sp; sp += per; scr.e[1] = (int*)sp; sp += per; scr.w[0] = (float*)sp; sp += per; scr.w[1] = (float*)sp; sp += per;
                 scr.x[0] = (unsigned*)sp; sp += per; scr.x[1] = (unsigned*)sp; sp += per; scr.cls = (unsigned char*)sp; sp += per;
+                scr.mark = (unsigned*)sp; sp += perS;
+                const size_t dyn = (size_t)kMergeSortSmem * sizeof(MergeSortRec);
+                if (!ctx->general_attr_set) {
+                    F3PS_CUDA_OK(cudaFuncSetAttribute(merge_kernel<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                    F3PS_CUDA_OK(cudaFuncSetAttribute(merge_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                    ctx->general_attr_set = true;
+                }
                 if (S < 65536u)
-                    LAUNCH(ctx, merge_kernel<unsigned>, 1, kMergeThreads, 0, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
+                    LAUNCH(ctx, merge_kernel<unsigned>, 1, kMergeThreads, dyn, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
                            ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr, (unsigned*)sp, ctx->pos_data);
                 else
-                    LAUNCH(ctx, merge_kernel<unsigned long long>, 1, kMergeThreads, 0, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
+                    LAUNCH(ctx, merge_kernel<unsigned long long>, 1, kMergeThreads, dyn, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
                            ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr, (unsigned long long*)sp, ctx->pos_data);
                 ctx->merge_path = 2;
             }
@@ -1050,6 +1060,7 @@ int f3ps_slab_expand_end(f3ps_ctx* ctx) {
     ctx->slab_expanding = false;
     return expand_finish(ctx);
 }
+
 
 int f3ps_merge_profile(f3ps_ctx* ctx, uint64_t cycles[32]) {
     if (!ctx || !cycles) return F3PS_ERR_INVALID_ARGUMENT;
@@ -1387,6 +1398,144 @@ int f3ps_get_voxel_segments_device(f3ps_ctx* ctx, const uint32_t** device_ptr, i
 }
 
 // ---- device self tests ------------------------------------------------------------------------------
+// =====================================================================================================
+// "next" row f1: Clustering::all_thresh (src/clustering.cpp:691-729) + Testing::eval_performance (src/testing.cpp:239-362).
+extern "C++" {
+namespace {
+// Testing::compute_intersections' best matches + the seven scores, in the reference's float order.
+// table[n_seg][n_truth] = inter_matrix; g[j] = truth segment sizes; N = truth->size().
+f3ps_performance testing_scores(const std::vector<unsigned>& table, unsigned n_seg, unsigned n_truth, const std::vector<size_t>& g, size_t N) {
+    auto inter = [&](unsigned i, unsigned j) -> size_t { return table[(size_t)i * n_truth + j]; };
+    std::vector<size_t> ssz(n_seg, 0);
+    for (unsigned i = 0; i < n_seg; ++i) for (unsigned j = 0; j < n_truth; ++j) ssz[i] += inter(i, j);
+    // t_sizes: std::map<size_t, uint32_t>, insert keeps the FIRST truth segment of every size (testing.cpp:97-110)
+    std::map<size_t, unsigned> t_sizes;
+    if (n_seg) for (unsigned j = 0; j < n_truth; ++j) t_sizes.insert(std::make_pair(g[j], j));
+    std::vector<long long> matches(n_truth, -1);
+    for (auto it = t_sizes.rbegin(); it != t_sizes.rend(); ++it) {           // largest truth segment first (:112-137)
+        const unsigned j = it->second;
+        std::vector<size_t> col(n_seg);
+        for (unsigned i = 0; i < n_seg; ++i) col[i] = inter(i, j);
+        auto argmax = [&]() { long long r = 0; for (unsigned i = 1; i < n_seg; ++i) if (col[i] > col[(size_t)r]) r = i; return r; };   // Eigen maxCoeff: first maximum
+        long long row = argmax();
+        auto taken = [&](long long r) { for (long long m : matches) if (m == r) return true; return false; };
+        while (taken(row)) {
+            col[(size_t)row] = 0;
+            bool any = false; for (size_t c : col) any = any || c != 0;
+            if (any) row = argmax(); else { row = -1; break; }
+        }
+        matches[j] = row;
+    }
+    f3ps_performance pf;
+    const float n = (float)N;
+    {   // eval_voi (:305-335)
+        float h_s = 0, h_t = 0, mi = 0;
+        for (unsigned i = 0; i < n_seg; ++i) {
+            const float p = (float)ssz[i];
+            h_s -= std::log(p / n) * p / n;
+            for (unsigned j = 0; j < n_truth; ++j) {
+                const float q = (float)g[j];
+                if (i == 0) h_t -= std::log(q / n) * q / n;
+                const float r = (float)inter(i, j);
+                if (r != 0) mi += std::log(((n * r) / (p * q))) * r / n;
+            }
+        }
+        pf.voi = h_s + h_t - 2 * mi;
+    }
+    {   // eval_precision (:239-268)
+        float p = 0, r = 0, fp = 0, fn = 0;
+        for (unsigned j = 0; j < n_truth; ++j) {
+            const long long i = matches[j];
+            if (i != -1) {
+                const float in = (float)inter((unsigned)i, j), sz = (float)ssz[(size_t)i], gg = (float)g[j];
+                p += in * gg / sz; r += in; fp += (sz - in); fn += (gg - in);
+            } else fn += (float)g[j];
+        }
+        pf.precision = p / n; pf.recall = r / n; pf.fpr = fp / n; pf.fnr = fn / n;
+    }
+    if (pf.precision == 0 && pf.recall == 0) pf.fscore = 0;                 // eval_fscore (:287-299)
+    else pf.fscore = 2 * (pf.precision * pf.recall) / (pf.precision + pf.recall);
+    {   // eval_wov (:342-357): count_union of two point sets = |s| + |t| - |s ^ t|
+        float w = 0;
+        for (unsigned j = 0; j < n_truth; ++j) {
+            const long long i = matches[j];
+            if (i != -1) {
+                const float in = (float)inter((unsigned)i, j);
+                const float un = (float)(ssz[(size_t)i] + g[j] - inter((unsigned)i, j));
+                w += in * (float)g[j] / un;
+            }
+        }
+        pf.wov = w / n;
+    }
+    return pf;
+}
+} // namespace
+} // extern "C++"
+
+int f3ps_eval_thresholds(f3ps_ctx* ctx, const uint32_t* truth_label, int64_t n_voxels, const float* thresholds, int n_thresholds,
+                         f3ps_performance* perf, int32_t* n_segments, int32_t* n_merges_at) {
+    if (!ctx || !truth_label || !thresholds || !perf || n_thresholds < 1) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_GRAPH, "f3ps_eval_thresholds"); if (rc) return rc;
+    if (n_voxels != (int64_t)ctx->V) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "one ground-truth label per voxel is required");
+    if (n_voxels == 0) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "The pointcloud to be set as 'truth' cannot be empty");   // testing.cpp:430-433
+    for (int k = 1; k < n_thresholds; ++k) if (!(thresholds[k] >= thresholds[k - 1])) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "thresholds must ascend");
+    cudaSetDevice(ctx->device);
+    rc = f3ps_merge(ctx, thresholds[n_thresholds - 1]); if (rc) return rc;      // ONE replay; every threshold is a prefix of it
+    const unsigned S = ctx->S, V = ctx->V, P = ctx->n_pos;
+    const unsigned M = ctx->h_sc->mctl.n_merges;
+    if (ctx->n_out == 0) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "The pointcloud to be set as 'segm' cannot be empty");  // testing.cpp:413-416
+    // merge forest on the host (M, S are small): label -> rank, parent / time per initial supervoxel
+    std::vector<unsigned> la(M), lb(M), svl(S); std::vector<float> lw(M);
+    if (M) {
+        if ((rc = d2h(ctx, la.data(), ctx->ML.a, (size_t)M * 4))) return rc;
+        if ((rc = d2h(ctx, lb.data(), ctx->ML.b, (size_t)M * 4))) return rc;
+        if ((rc = d2h(ctx, lw.data(), ctx->ML.w, (size_t)M * 4))) return rc;
+    }
+    if ((rc = d2h(ctx, svl.data(), ctx->sv_label.p, (size_t)S * 4))) return rc;
+    if ((rc = fin(ctx))) return rc;
+    std::map<unsigned, unsigned> rank_of;
+    for (unsigned s = 0; s < S; ++s) rank_of[svl[s]] = s;
+    std::vector<unsigned> parent(S), when(S, 0xffffffffu);
+    for (unsigned s = 0; s < S; ++s) parent[s] = s;
+    for (unsigned i = 0; i < M; ++i) { const unsigned ra = rank_of[la[i]], rb = rank_of[lb[i]]; parent[rb] = ra; when[rb] = i; }
+    // Testing::label_map on the truth: dense labels in ascending label order, segment sizes
+    std::map<unsigned, unsigned> tmap;
+    for (int64_t v = 0; v < n_voxels; ++v) tmap[truth_label[v]] = 0;
+    unsigned Kt = 0; for (auto& kv : tmap) kv.second = Kt++;
+    std::vector<unsigned> tdense((size_t)V); std::vector<size_t> g(Kt, 0);
+    for (unsigned v = 0; v < V; ++v) { tdense[v] = tmap[truth_label[v]]; g[tdense[v]]++; }
+    if ((size_t)S * Kt > ((size_t)1 << 28)) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "contingency table above 2^28 cells");
+    const size_t Sc = std::max(1u, S);
+    F3PS_CUDA_OK(ctx->ev_parent.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->ev_when.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->ev_dense.ensure(Sc * 4 + 4));
+    F3PS_CUDA_OK(ctx->ev_truth.ensure((size_t)V * 4)); F3PS_CUDA_OK(ctx->ev_table.ensure(std::max<size_t>(1, (size_t)S * Kt) * 4));
+    F3PS_CUDA_OK(cudaMemcpyAsync(ctx->ev_parent.p, parent.data(), (size_t)S * 4, cudaMemcpyHostToDevice, ctx->stream));
+    F3PS_CUDA_OK(cudaMemcpyAsync(ctx->ev_when.p, when.data(), (size_t)S * 4, cudaMemcpyHostToDevice, ctx->stream));
+    F3PS_CUDA_OK(cudaMemcpyAsync(ctx->ev_truth.p, tdense.data(), (size_t)V * 4, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned* d_nseg = ctx->ev_dense.as<unsigned>() + Sc;
+    std::vector<unsigned> table;
+    unsigned m_prev = 0xffffffffu;
+    for (int k = 0; k < n_thresholds; ++k) {
+        unsigned m = M;                                                       // first step whose head weight is >= t (strict <, :388-389)
+        for (unsigned i = 0; i < M; ++i) if (!(lw[i] < thresholds[k])) { m = i; break; }
+        if (n_merges_at) n_merges_at[k] = (int32_t)m;
+        if (m == m_prev) { perf[k] = perf[k - 1]; if (n_segments) n_segments[k] = n_segments[k - 1]; continue; }
+        m_prev = m;
+        LAUNCH(ctx, eval_dense_kernel, 1, 1024, 0, ctx->ev_when.as<unsigned>(), S, m, ctx->ev_dense.as<unsigned>(), d_nseg);
+        F3PS_CUDA_OK(cudaMemsetAsync(ctx->ev_table.p, 0, std::max<size_t>(1, (size_t)S * Kt) * 4, ctx->stream));
+        if (P) LAUNCH(ctx, eval_table_kernel, grid_for(P, 256), 256, 0, ctx->pos_run.as<unsigned>(), ctx->order, P, ctx->ev_parent.as<unsigned>(),
+                      ctx->ev_when.as<unsigned>(), ctx->ev_dense.as<unsigned>(), m, ctx->ev_truth.as<unsigned>(), Kt, ctx->ev_table.as<unsigned>());
+        unsigned n_seg = 0;
+        if ((rc = d2h(ctx, &n_seg, d_nseg, 4))) return rc;
+        if ((rc = fin(ctx))) return rc;
+        table.resize((size_t)n_seg * Kt);
+        if (n_seg) { if ((rc = d2h(ctx, table.data(), ctx->ev_table.p, (size_t)n_seg * Kt * 4))) return rc; if ((rc = fin(ctx))) return rc; }
+        perf[k] = testing_scores(table, n_seg, Kt, g, (size_t)V);
+        if (n_segments) n_segments[k] = (int32_t)n_seg;
+    }
+    return F3PS_OK;
+}
+
+
 static int test_map3(f3ps_ctx* ctx, int which, const float* in1, const float* in2, float* out, int64_t n) {
     if (!ctx || n < 0) return F3PS_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);

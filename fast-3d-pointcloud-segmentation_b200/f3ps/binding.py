@@ -100,6 +100,7 @@ def lib():
         "f3ps_test_lab_ciede00": (C.c_int, [vp, vp, vp, vp, i64]),
         "f3ps_test_rgb_eucl": (C.c_int, [vp, vp, vp, vp, i64]),
         "f3ps_test_sort_pairs": (C.c_int, [vp, vp, vp, i64, C.c_int]),
+        "f3ps_eval_thresholds": (C.c_int, [vp, vp, i64, vp, C.c_int, vp, vp, vp]),
         "f3ps_slab_reset": (C.c_int, [vp]),
         "f3ps_slab_bbox": (C.c_int, [vp, vp]),
         "f3ps_slab_set_frame": (C.c_int, [vp, vp]),
@@ -129,7 +130,7 @@ EXPORTED = ["f3ps_create", "f3ps_destroy", "f3ps_last_error", "f3ps_version", "f
             "f3ps_get_merge_log", "f3ps_get_state_regions", "f3ps_get_state_edges", "f3ps_get_labeled_cloud", "f3ps_get_region_mean_color",
             "f3ps_get_voxel_segments_device", "f3ps_stage_ms", "f3ps_launch_count", "f3ps_merge_profile", "f3ps_expand_profile", "f3ps_test_rgb2lab",
             "f3ps_test_lab_ciede00", "f3ps_test_rgb_eucl", "f3ps_test_sort_pairs",
-            "f3ps_slab_reset", "f3ps_slab_bbox", "f3ps_slab_set_frame", "f3ps_slab_keys", "f3ps_slab_route", "f3ps_slab_array",
+            "f3ps_eval_thresholds", "f3ps_slab_reset", "f3ps_slab_bbox", "f3ps_slab_set_frame", "f3ps_slab_keys", "f3ps_slab_route", "f3ps_slab_array",
             "f3ps_slab_set_voxels", "f3ps_slab_expand_begin", "f3ps_slab_expand_sweep", "f3ps_slab_expand_round_end",
             "f3ps_slab_expand_end"]
 
@@ -247,7 +248,7 @@ class Segmenter:
                     "cov": dict(zip(["wait_voxels", "fold", "eigen_publish", "wait_b1"], v[16:20])),
                     "loader": {"issue": v[29], "wait_fold_splice": v[30], "wait_head": v[8], "bulk_copies": v[31]},
                     "guess_misses": v[24], "ciede_evals": v[25], "merges_T_gt_32": v[26], "sum_T": v[27]}
-        return dict(zip(["argmin", "fold_scan", "order", "delta", "stamps"], v[:5]))
+        return dict(zip(["argmin", "fold", "order", "delta", "stamps", "wait_scan", "sum_T", "fold_tail"], v[:8]))
 
     def expand_profile(self):
         a = (C.c_uint64 * 8)()
@@ -323,6 +324,44 @@ class Segmenter:
         idx = np.zeros(cap, np.int32); off = np.zeros(c.n_supervoxels + 1, np.int64)
         self._chk(self.L.f3ps_get_supervoxel_voxels(self.h, _p(idx), _p(off), cap, c.n_supervoxels))
         return idx[:off[-1]], off
+
+    # ---- auto-threshold sweep: Clustering::all_thresh / best_thresh (src/clustering.cpp:691-774) ----
+    PERF_FIELDS = ("voi", "precision", "recall", "fscore", "wov", "fpr", "fnr")
+
+    @staticmethod
+    def sweep_thresholds(start=0.8, end=1.0, step=0.005):
+        """The thresholds all_thresh visits: start, then `t += step` in float while t <= end (:711-718)."""
+        start, end, step = np.float32(start), np.float32(end), np.float32(step)
+        if start > end:
+            start, end = end, start
+        out = [start]
+        t = np.float32(start + step)
+        while t <= end:
+            out.append(t)
+            t = np.float32(t + step)
+        return np.array(out, np.float32)
+
+    def all_thresh(self, truth_label, start=0.8, end=1.0, step=0.005):
+        """{threshold: performanceSet dict} for every threshold of the sweep, from one merge replay on the device."""
+        for v in (start, end, step):
+            if v < 0 or v > 1:
+                raise IndexError("start_thresh, end_thresh and/or step_thresh outside of range [0, 1]")   # std::out_of_range (:694-698)
+        thr = self.sweep_thresholds(start, end, step)
+        truth = np.ascontiguousarray(truth_label, np.uint32)
+        perf = np.zeros((len(thr), 7), np.float32)
+        nseg = np.zeros(len(thr), np.int32); nm = np.zeros(len(thr), np.int32)
+        self._chk(self.L.f3ps_eval_thresholds(self.h, _p(truth), truth.shape[0], _p(thr), len(thr), _p(perf), _p(nseg), _p(nm)))
+        self.last_sweep = {"thresholds": thr, "perf": perf, "n_segments": nseg, "n_merges": nm}
+        return {float(t): dict(zip(self.PERF_FIELDS, map(float, perf[k]))) for k, t in enumerate(thr)}
+
+    def best_thresh(self, truth_label, start=0.8, end=1.0, step=0.005):
+        """(threshold, performanceSet) with the largest F-score; the first one wins ties, 0 / zeros if none is positive (:759-774)."""
+        res = self.all_thresh(truth_label, start, end, step)
+        best_t, best = 0.0, dict.fromkeys(self.PERF_FIELDS, 0.0)
+        for t in sorted(res):
+            if res[t]["fscore"] > best["fscore"]:
+                best_t, best = t, res[t]
+        return best_t, best
 
     # ---- slab mode (per-rank pieces; f3ps/slab.py issues the exchanges between them) ----
     SLAB_ARRAYS = {"vox_xyz": 0, "vox_rgb": 1, "vox_key": 2, "vox_normal": 3, "vox_curv": 4, "steal": 5, "owner_next": 6,

@@ -193,6 +193,16 @@ int f3ps_slab_expand_sweep(f3ps_ctx* ctx, uint32_t* d_changed);
 int f3ps_slab_expand_round_end(f3ps_ctx* ctx);
 int f3ps_slab_expand_end(f3ps_ctx* ctx);
 
+/* ---- "next" row f1: the auto-threshold sweep ------------------------------------------------------------------------
+ * Clustering::all_thresh (clustering.cpp:691-729) with Testing::eval_performance (testing.cpp:239-362) from ONE merge replay:
+ * truth_label[V] = ground-truth label of every voxel (the labelled voxel cloud main() builds, supervoxel_clustering.cpp:387-400),
+ * thresholds[n] ascending (main(): 0.8 .. 1 in float steps of 0.005); perf[n] = performanceSet (testing.h:68-75) per threshold,
+ * n_segments[n] / n_merges_at[n] (optional) = regions left / merges done at each threshold.  Leaves the handle in the state
+ * of f3ps_merge(thresholds[n-1]).  Intersections by exact xyz become equality of the voxel index. */
+typedef struct f3ps_performance { float voi, precision, recall, fscore, wov, fpr, fnr; } f3ps_performance;
+int f3ps_eval_thresholds(f3ps_ctx* ctx, const uint32_t* truth_label, int64_t n_voxels, const float* thresholds, int n_thresholds,
+                         f3ps_performance* perf, int32_t* n_segments, int32_t* n_merges_at);
+
 /* CUDA-event time of the last run of a stage, ms (valid after f3ps_sync) */
 int f3ps_stage_ms(f3ps_ctx* ctx, int stage, float* ms);
 /* Profiling aid: SM cycles (clock64) the last f3ps_merge spent per phase, and event counts.

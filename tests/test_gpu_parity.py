@@ -384,3 +384,50 @@ def test_full_size_properties_config4(gpu):
     assert np.array_equal(g.array("merges_ab"), m1)
     out = g.array("out_label")
     assert len(out) == int((labels > 0).sum()) and out.max() + 1 == g.counts().n_segments
+
+
+@pytest.mark.parametrize("n_leaves,mode", [(1500, "lab_al"), (3000, "rgb_eq"), (9000, "rgb_ml")])
+def test_general_merge_kernel_hub_graph(gpu, oracle_mod, n_leaves, mode):
+    """Merges that touch thousands of edges (a region with thousands of neighbours, as floors and walls of dense scenes
+    have): the general kernel's sorted path (bitonic sort in shared / global memory, mark-based dedupe, ballot-scan tie
+    stamps) must replay the oracle's sequence exactly.  Hub + ring graph injected through set_graph."""
+    rng = np.random.default_rng(n_leaves)
+    S = n_leaves + 2
+    sizes = rng.integers(3, 7, S)
+    sizes[0] = 40; sizes[1] = 25                      # two hubs
+    V = int(sizes.sum())
+    vxyz = (rng.normal(0, 1, (V, 3)) + 3).astype(np.float32)
+    base = rng.integers(0, 6, S)                      # few colours -> many similar weights, and exact ties under EQ
+    vrgba = np.repeat((base * 40 + 20).astype(np.uint32), sizes) * np.uint32(0x010101) + rng.integers(0, 3, V).astype(np.uint32)
+    labels = np.arange(1, S + 1, dtype=np.uint32)
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    lists = [np.arange(off[i], off[i + 1]) for i in range(S)]
+    cen = np.stack([vxyz[l].mean(0) for l in lists]).astype(np.float32)
+    nrm = rng.normal(0, 1, (S, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    pairs = {(0, 1)}
+    for i in range(2, S):
+        pairs.add((0, i))                             # hub 0 touches everything
+        if i % 2:
+            pairs.add((1, i))                         # hub 1 touches half: duplicates (a,x)/(b,x) when the hubs merge
+        if i + 1 < S:
+            pairs.add((i, i + 1))
+    adj = []
+    for i, j in sorted(pairs):
+        adj += [(labels[i], labels[j]), (labels[j], labels[i])]
+    adj = np.array(sorted(adj), np.uint32)
+    flags = {"lab_al": dict(color_mode=0, geom_mode=1, merge_mode=1), "rgb_eq": dict(color_mode=1, geom_mode=0, merge_mode=2, bins=7),
+             "rgb_ml": dict(color_mode=1, geom_mode=1, merge_mode=0, lam=0.5)}[mode]
+    thr = 0.95 if mode == "rgb_eq" else 0.3
+    o = oracle_mod.Oracle(); o.set_merge_params(merge_impl=1, **flags)
+    o.set_graph(vxyz, vrgba, labels, lists, cen, nrm, adj); o.run(7, thr)
+    g = gpu.Segmenter(); g.set_merge_params(**flags)
+    g.set_graph(vxyz, vrgba, labels, lists, cen, nrm, adj)
+    g.merge(thr)
+    c = g.counts()
+    assert c.merge_path == 2 and c.max_touched > 1024 and c.n_merges > 100, (c.merge_path, c.max_touched, c.n_merges)
+    if n_leaves >= 9000:
+        assert c.max_touched > 8192                  # the global-memory sort as well
+    assert np.array_equal(g.array("merges_ab"), o.array("merges_ab"))
+    assert same(g.array("merges_w"), o.array("merges_w"))
+    assert np.array_equal(g.array("out_label"), o.array("out_label"))

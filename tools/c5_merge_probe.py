@@ -21,5 +21,5 @@ for rep in range(2):
           "merge_ms", round(ms["merge"], 2), "kernel_ms", round(ms["merge_kernel"], 2), "us/merge", round(1e3 * ms["merge_kernel"] / max(1, c.n_merges), 2))
     if isinstance(prof, dict):
         tot = sum(v for v in prof.values() if isinstance(v, int)) or 1
-        print({k: (round(v / 1.965e3 / max(1, c.n_merges), 2) if isinstance(v, int) else v) for k, v in prof.items()}, "(us per merge)")
+        print({k: (round(v / 1.965e3 / max(1, c.n_merges), 2) if isinstance(v, int) else v) for k, v in prof.items()}, "(us per merge)", "avg T", round(prof.get("sum_T", 0) / max(1, c.n_merges), 1))
 print(g.stage_ms())
