@@ -1405,9 +1405,10 @@ namespace {
 // Testing::compute_intersections' best matches + the seven scores, in the reference's float order.
 // table[n_seg][n_truth] = inter_matrix; g[j] = truth segment sizes; N = truth->size().
 f3ps_performance testing_scores(const std::vector<unsigned>& table, unsigned n_seg, unsigned n_truth, const std::vector<size_t>& g, size_t N) {
-    auto inter = [&](unsigned i, unsigned j) -> size_t { return table[(size_t)i * n_truth + j]; };
+    // table has n_truth + 1 columns: the last one counts segmentation points without a ground-truth point at the same xyz
+    auto inter = [&](unsigned i, unsigned j) -> size_t { return table[(size_t)i * (n_truth + 1) + j]; };
     std::vector<size_t> ssz(n_seg, 0);
-    for (unsigned i = 0; i < n_seg; ++i) for (unsigned j = 0; j < n_truth; ++j) ssz[i] += inter(i, j);
+    for (unsigned i = 0; i < n_seg; ++i) for (unsigned j = 0; j <= n_truth; ++j) ssz[i] += inter(i, j);
     // t_sizes: std::map<size_t, uint32_t>, insert keeps the FIRST truth segment of every size (testing.cpp:97-110)
     std::map<size_t, unsigned> t_sizes;
     if (n_seg) for (unsigned j = 0; j < n_truth; ++j) t_sizes.insert(std::make_pair(g[j], j));
@@ -1472,12 +1473,11 @@ f3ps_performance testing_scores(const std::vector<unsigned>& table, unsigned n_s
 } // namespace
 } // extern "C++"
 
-int f3ps_eval_thresholds(f3ps_ctx* ctx, const uint32_t* truth_label, int64_t n_voxels, const float* thresholds, int n_thresholds,
-                         f3ps_performance* perf, int32_t* n_segments, int32_t* n_merges_at) {
-    if (!ctx || !truth_label || !thresholds || !perf || n_thresholds < 1) return F3PS_ERR_INVALID_ARGUMENT;
+int f3ps_eval_thresholds(f3ps_ctx* ctx, const uint32_t* truth_label, int64_t n_voxels, const uint32_t* extra_truth_label, int64_t n_extra,
+                         const float* thresholds, int n_thresholds, f3ps_performance* perf, int32_t* n_segments, int32_t* n_merges_at) {
+    if (!ctx || !truth_label || !thresholds || !perf || n_thresholds < 1 || n_extra < 0 || (n_extra > 0 && !extra_truth_label)) return F3PS_ERR_INVALID_ARGUMENT;
     int rc = need(ctx, P_GRAPH, "f3ps_eval_thresholds"); if (rc) return rc;
     if (n_voxels != (int64_t)ctx->V) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "one ground-truth label per voxel is required");
-    if (n_voxels == 0) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "The pointcloud to be set as 'truth' cannot be empty");   // testing.cpp:430-433
     for (int k = 1; k < n_thresholds; ++k) if (!(thresholds[k] >= thresholds[k - 1])) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "thresholds must ascend");
     cudaSetDevice(ctx->device);
     rc = f3ps_merge(ctx, thresholds[n_thresholds - 1]); if (rc) return rc;      // ONE replay; every threshold is a prefix of it
@@ -1500,14 +1500,22 @@ int f3ps_eval_thresholds(f3ps_ctx* ctx, const uint32_t* truth_label, int64_t n_v
     for (unsigned i = 0; i < M; ++i) { const unsigned ra = rank_of[la[i]], rb = rank_of[lb[i]]; parent[rb] = ra; when[rb] = i; }
     // Testing::label_map on the truth: dense labels in ascending label order, segment sizes
     std::map<unsigned, unsigned> tmap;
-    for (int64_t v = 0; v < n_voxels; ++v) tmap[truth_label[v]] = 0;
+    size_t n_truth_points = 0;
+    for (int64_t v = 0; v < n_voxels; ++v) if (truth_label[v] != 0xffffffffu) { tmap[truth_label[v]] = 0; ++n_truth_points; }
+    for (int64_t v = 0; v < n_extra; ++v) { tmap[extra_truth_label[v]] = 0; ++n_truth_points; }
+    if (n_truth_points == 0) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "The pointcloud to be set as 'truth' cannot be empty");
     unsigned Kt = 0; for (auto& kv : tmap) kv.second = Kt++;
     std::vector<unsigned> tdense((size_t)V); std::vector<size_t> g(Kt, 0);
-    for (unsigned v = 0; v < V; ++v) { tdense[v] = tmap[truth_label[v]]; g[tdense[v]]++; }
-    if ((size_t)S * Kt > ((size_t)1 << 28)) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "contingency table above 2^28 cells");
+    for (unsigned v = 0; v < V; ++v) {
+        if (truth_label[v] == 0xffffffffu) { tdense[v] = Kt; continue; }     // no ground-truth point at this voxel's xyz
+        tdense[v] = tmap[truth_label[v]]; g[tdense[v]]++;
+    }
+    for (int64_t v = 0; v < n_extra; ++v) g[tmap[extra_truth_label[v]]]++;    // truth points outside the segmentation's voxels
+    const unsigned Kc = Kt + 1;
+    if ((size_t)S * Kc > ((size_t)1 << 28)) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "contingency table above 2^28 cells");
     const size_t Sc = std::max(1u, S);
     F3PS_CUDA_OK(ctx->ev_parent.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->ev_when.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->ev_dense.ensure(Sc * 4 + 4));
-    F3PS_CUDA_OK(ctx->ev_truth.ensure((size_t)V * 4)); F3PS_CUDA_OK(ctx->ev_table.ensure(std::max<size_t>(1, (size_t)S * Kt) * 4));
+    F3PS_CUDA_OK(ctx->ev_truth.ensure((size_t)V * 4)); F3PS_CUDA_OK(ctx->ev_table.ensure(std::max<size_t>(1, (size_t)S * Kc) * 4));
     F3PS_CUDA_OK(cudaMemcpyAsync(ctx->ev_parent.p, parent.data(), (size_t)S * 4, cudaMemcpyHostToDevice, ctx->stream));
     F3PS_CUDA_OK(cudaMemcpyAsync(ctx->ev_when.p, when.data(), (size_t)S * 4, cudaMemcpyHostToDevice, ctx->stream));
     F3PS_CUDA_OK(cudaMemcpyAsync(ctx->ev_truth.p, tdense.data(), (size_t)V * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1521,15 +1529,15 @@ int f3ps_eval_thresholds(f3ps_ctx* ctx, const uint32_t* truth_label, int64_t n_v
         if (m == m_prev) { perf[k] = perf[k - 1]; if (n_segments) n_segments[k] = n_segments[k - 1]; continue; }
         m_prev = m;
         LAUNCH(ctx, eval_dense_kernel, 1, 1024, 0, ctx->ev_when.as<unsigned>(), S, m, ctx->ev_dense.as<unsigned>(), d_nseg);
-        F3PS_CUDA_OK(cudaMemsetAsync(ctx->ev_table.p, 0, std::max<size_t>(1, (size_t)S * Kt) * 4, ctx->stream));
+        F3PS_CUDA_OK(cudaMemsetAsync(ctx->ev_table.p, 0, std::max<size_t>(1, (size_t)S * Kc) * 4, ctx->stream));
         if (P) LAUNCH(ctx, eval_table_kernel, grid_for(P, 256), 256, 0, ctx->pos_run.as<unsigned>(), ctx->order, P, ctx->ev_parent.as<unsigned>(),
-                      ctx->ev_when.as<unsigned>(), ctx->ev_dense.as<unsigned>(), m, ctx->ev_truth.as<unsigned>(), Kt, ctx->ev_table.as<unsigned>());
+                      ctx->ev_when.as<unsigned>(), ctx->ev_dense.as<unsigned>(), m, ctx->ev_truth.as<unsigned>(), Kc, ctx->ev_table.as<unsigned>());
         unsigned n_seg = 0;
         if ((rc = d2h(ctx, &n_seg, d_nseg, 4))) return rc;
         if ((rc = fin(ctx))) return rc;
-        table.resize((size_t)n_seg * Kt);
-        if (n_seg) { if ((rc = d2h(ctx, table.data(), ctx->ev_table.p, (size_t)n_seg * Kt * 4))) return rc; if ((rc = fin(ctx))) return rc; }
-        perf[k] = testing_scores(table, n_seg, Kt, g, (size_t)V);
+        table.resize((size_t)n_seg * Kc);
+        if (n_seg) { if ((rc = d2h(ctx, table.data(), ctx->ev_table.p, (size_t)n_seg * Kc * 4))) return rc; if ((rc = fin(ctx))) return rc; }
+        perf[k] = testing_scores(table, n_seg, Kt, g, n_truth_points);
         if (n_segments) n_segments[k] = (int32_t)n_seg;
     }
     return F3PS_OK;

@@ -100,7 +100,7 @@ def lib():
         "f3ps_test_lab_ciede00": (C.c_int, [vp, vp, vp, vp, i64]),
         "f3ps_test_rgb_eucl": (C.c_int, [vp, vp, vp, vp, i64]),
         "f3ps_test_sort_pairs": (C.c_int, [vp, vp, vp, i64, C.c_int]),
-        "f3ps_eval_thresholds": (C.c_int, [vp, vp, i64, vp, C.c_int, vp, vp, vp]),
+        "f3ps_eval_thresholds": (C.c_int, [vp, vp, i64, vp, i64, vp, C.c_int, vp, vp, vp]),
         "f3ps_slab_reset": (C.c_int, [vp]),
         "f3ps_slab_bbox": (C.c_int, [vp, vp]),
         "f3ps_slab_set_frame": (C.c_int, [vp, vp]),
@@ -341,7 +341,7 @@ class Segmenter:
             t = np.float32(t + step)
         return np.array(out, np.float32)
 
-    def all_thresh(self, truth_label, start=0.8, end=1.0, step=0.005):
+    def all_thresh(self, truth_label, start=0.8, end=1.0, step=0.005, extra_truth=None):
         """{threshold: performanceSet dict} for every threshold of the sweep, from one merge replay on the device."""
         for v in (start, end, step):
             if v < 0 or v > 1:
@@ -350,7 +350,9 @@ class Segmenter:
         truth = np.ascontiguousarray(truth_label, np.uint32)
         perf = np.zeros((len(thr), 7), np.float32)
         nseg = np.zeros(len(thr), np.int32); nm = np.zeros(len(thr), np.int32)
-        self._chk(self.L.f3ps_eval_thresholds(self.h, _p(truth), truth.shape[0], _p(thr), len(thr), _p(perf), _p(nseg), _p(nm)))
+        extra = None if extra_truth is None else np.ascontiguousarray(extra_truth, np.uint32)
+        self._chk(self.L.f3ps_eval_thresholds(self.h, _p(truth), truth.shape[0], _p(extra), 0 if extra is None else extra.shape[0],
+                                              _p(thr), len(thr), _p(perf), _p(nseg), _p(nm)))
         self.last_sweep = {"thresholds": thr, "perf": perf, "n_segments": nseg, "n_merges": nm}
         return {float(t): dict(zip(self.PERF_FIELDS, map(float, perf[k]))) for k, t in enumerate(thr)}
 

@@ -334,6 +334,56 @@ std::pair<ClusteringT, AdjacencyMapT> Clustering::get_currentstate() const {
     return ret;
 }
 
+// ---- Clustering::all_thresh / best_thresh (src/clustering.cpp:691-774) ---------------------------------------------
+std::map<float, performanceSet> Clustering::all_thresh(PointLCloudT::Ptr ground_truth, float start_thresh, float end_thresh, float step_thresh) {
+    if (start_thresh < 0 || start_thresh > 1 || end_thresh < 0 || end_thresh > 1 || step_thresh < 0 || step_thresh > 1)
+        throw std::out_of_range("start_thresh, end_thresh and/or step_thresh outside of range [0, 1]");
+    if (start_thresh > end_thresh) std::swap(start_thresh, end_thresh);            // "inverting" (:699-704)
+    if (!set_initial_state)
+        throw std::logic_error("Cannot call 'cluster' before setting an initial state with 'set_initialstate'");
+    if (!ground_truth || ground_truth->empty())
+        throw std::invalid_argument("The pointcloud to be set as 'truth' cannot be empty");     // Testing::set_truth (testing.cpp:430-433)
+    if (!init_initial_weights) { push_params(); h_->check(f3ps_graph(h_->get())); init_initial_weights = true; }
+    std::vector<float> thr(1, start_thresh);
+    for (float t = start_thresh + step_thresh; t <= end_thresh; t += step_thresh) thr.push_back(t);
+    // Testing::count_intersect matches points by exact xyz (compareXYZ): ground-truth label of every voxel of the graph
+    struct Key { uint32_t k[3]; bool operator<(const Key& o) const { return std::lexicographical_compare(k, k + 3, o.k, o.k + 3); } };
+    auto key_of = [](float x, float y, float z) { Key q; float v[3] = {x == 0 ? 0.0f : x, y == 0 ? 0.0f : y, z == 0 ? 0.0f : z}; memcpy(q.k, v, 12); return q; };
+    std::map<Key, size_t> where;
+    for (size_t i = 0; i < ground_truth->size(); ++i) { const PointLT& p = ground_truth->points[i]; where.insert(std::make_pair(key_of(p.x, p.y, p.z), i)); }
+    std::vector<char> used(ground_truth->size(), 0);
+    std::vector<uint32_t> truth(flat_voxels_.size(), 0xffffffffu), extra;
+    for (size_t v = 0; v < flat_voxels_.size(); ++v) {
+        auto it = where.find(key_of(flat_voxels_[v].x, flat_voxels_[v].y, flat_voxels_[v].z));
+        if (it != where.end()) { truth[v] = ground_truth->points[it->second].label; used[it->second] = 1; }
+    }
+    for (size_t i = 0; i < ground_truth->size(); ++i) if (!used[i]) extra.push_back(ground_truth->points[i].label);
+    std::vector<f3ps_performance> perf(thr.size());
+    h_->check(f3ps_eval_thresholds(h_->get(), truth.data(), (int64_t)truth.size(), extra.empty() ? nullptr : extra.data(), (int64_t)extra.size(),
+                                   thr.data(), (int)thr.size(), perf.data(), nullptr, nullptr));
+    pull_state(true);                                                               // `state` = clustering at the last threshold
+    std::map<float, performanceSet> out;
+    for (size_t k = 0; k < thr.size(); ++k) {
+        performanceSet p;
+        p.voi = perf[k].voi; p.precision = perf[k].precision; p.recall = perf[k].recall; p.fscore = perf[k].fscore;
+        p.wov = perf[k].wov; p.fpr = perf[k].fpr; p.fnr = perf[k].fnr;
+        out.insert(std::make_pair(thr[k], p));
+    }
+    return out;
+}
+
+std::pair<float, performanceSet> Clustering::best_thresh(PointLCloudT::Ptr ground_truth, float start_thresh, float end_thresh, float step_thresh) {
+    return best_thresh(all_thresh(ground_truth, start_thresh, end_thresh, step_thresh));
+}
+
+std::pair<float, performanceSet> Clustering::best_thresh(std::map<float, performanceSet> all_thresh) {
+    float best_t = 0;
+    performanceSet best_performance;
+    for (auto it = all_thresh.begin(); it != all_thresh.end(); ++it)
+        if (it->second.fscore > best_performance.fscore) { best_performance = it->second; best_t = it->first; }
+    return std::pair<float, performanceSet>(best_t, best_performance);
+}
+
 PointLCloudT::Ptr Clustering::get_labeled_cloud() const {
     PointLCloudT::Ptr out(new PointLCloudT());
     uint32_t dense = 0;

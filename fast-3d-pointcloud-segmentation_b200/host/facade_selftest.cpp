@@ -87,6 +87,33 @@ int main(int argc, char** argv) {
     const std::vector<MergeStep>& log2 = segmentation.get_merge_log();
     CHECK(log2.size() <= (size_t)n.n_merges, "prefix length");
     for (size_t m = 0; m < log2.size(); ++m) CHECK(log2[m].a == ab[2 * m] && log2[m].b == ab[2 * m + 1], "prefix differs");
+    // threshold sweep: Clustering::all_thresh on a ground-truth voxel cloud == f3ps_eval_thresholds on the fused handle
+    {
+        PointLCloudT::Ptr truth(new PointLCloudT());
+        pcl::PointCloud<pcl::PointXYZRGBA>::Ptr vc = super.getVoxelCentroidCloud();
+        std::vector<uint32_t> tl(vc->size());
+        for (size_t v = 0; v < vc->size(); ++v) {                       // three bands along x as a stand-in ground truth
+            PointLT p; p.x = vc->points[v].x; p.y = vc->points[v].y; p.z = vc->points[v].z;
+            p.label = tl[v] = vc->points[v].x < -0.3f ? 4u : (vc->points[v].x < 0.4f ? 9u : 2u);
+            truth->push_back(p);
+        }
+        std::map<float, performanceSet> all = segmentation.all_thresh(truth, 0.05f, 0.5f, 0.05f);
+        std::vector<float> tv; for (auto& kv : all) tv.push_back(kv.first);
+        std::vector<f3ps_performance> perf(tv.size());
+        h.check(f3ps_eval_thresholds(h.get(), tl.data(), (int64_t)tl.size(), nullptr, 0, tv.data(), (int)tv.size(), perf.data(), nullptr, nullptr));
+        size_t k = 0;
+        for (auto& kv : all) {
+            CHECK(kv.second.fscore == perf[k].fscore && kv.second.voi == perf[k].voi && kv.second.wov == perf[k].wov && kv.second.fnr == perf[k].fnr,
+                  "all_thresh differs between the class path and the fused path");
+            ++k;
+        }
+        std::pair<float, performanceSet> best = segmentation.best_thresh(all);
+        for (auto& kv : all) CHECK(kv.second.fscore <= best.second.fscore, "best_thresh is not the maximum F-score");
+        CHECK(best.second.fscore > 0.0f && all.size() == tv.size() && tv.size() >= 9, "sweep size / positive F-score");
+        bool threw = false;
+        try { segmentation.all_thresh(truth, 0.5f, 1.5f, 0.1f); } catch (const std::out_of_range&) { threw = true; }
+        CHECK(threw, "all_thresh outside [0,1] must throw std::out_of_range (src/clustering.cpp:694-698)");
+    }
     printf("FACADE OK: N=%zu V=%lld S=%d E=%d M=%d segments=%d\n", cloud->size(), (long long)n.n_voxels, n.n_supervoxels, n.n_edges, n.n_merges, n.n_segments);
     return 0;
 }

@@ -35,7 +35,7 @@ bool parse(int argc, char** argv, const char* name, std::string& v) { int i = fi
 
 struct Options {
     float voxel_resolution = 0.008f, seed_resolution = 0.08f, color_importance = 0.2f, spatial_importance = 0.4f, normal_importance = 1.0f;
-    float thresh = 0; bool rgb = false, cvx = false, ml = false, al = false, eq = false, disable_transform = false, verbose = false, facade = false;
+    float thresh = 0; bool thresh_specified = true; bool rgb = false, cvx = false, ml = false, al = false, eq = false, disable_transform = false, verbose = false, facade = false;
     float lambda = 0; int bin_num = 0; std::string out;
 };
 
@@ -60,6 +60,47 @@ void usage(const char* a0) {
            "\t --facade                       (runs through the Clustering / SupervoxelClustering classes) \n"
            "\t --gpus <N>                     (shards the files of -d over N GPUs) \n"
            "\t --inflight <K>                 (frames in flight per GPU during a -d sweep, default 8) \n", a0);
+}
+
+// Ground-truth voxelisation (src/supervoxel_clustering.cpp:387-400): the reference colours the truth cloud with the Glasbey
+// table, runs VCCS on it and maps the voxel colours back to labels (color2label: labels by first occurrence in voxel order,
+// src/clustering.cpp:823-846).  A voxel whose points share one label keeps that label's colour; a mixed voxel gets the mean
+// colour, i.e. a class of its own shared with the voxels of the same label mixture.  PCL's Glasbey table is not in the
+// reference tree, so mixtures are keyed by their label proportions instead of the blended colour (equal unless two
+// different mixtures happen to blend to the same 8-bit colour).
+std::vector<uint32_t> voxelise_truth(const std::vector<int32_t>& point_voxel, const pcl::PointCloud<pcl::PointXYZRGBL>& input, size_t V) {
+    std::vector<std::map<uint32_t, uint32_t>> mix(V);
+    for (size_t i = 0; i < point_voxel.size(); ++i) if (point_voxel[i] >= 0) mix[(size_t)point_voxel[i]][input.points[i].label]++;
+    std::map<std::vector<std::pair<uint32_t, uint32_t>>, uint32_t> classes;      // color2label's std::map<float, uint32_t>
+    std::vector<uint32_t> truth(V, 0);
+    for (size_t v = 0; v < V; ++v) {
+        std::vector<std::pair<uint32_t, uint32_t>> key(mix[v].begin(), mix[v].end());
+        uint32_t g = 0;
+        for (auto& kv : key) { uint32_t a = kv.second, b = g; while (b) { uint32_t t = a % b; a = b; b = t; } g = a; }
+        if (key.size() == 1) key[0].second = 1; else for (auto& kv : key) kv.second /= std::max(1u, g);
+        auto it = classes.find(key);
+        if (it == classes.end()) it = classes.insert(std::make_pair(key, (uint32_t)classes.size())).first;
+        truth[v] = it->second;
+    }
+    return truth;
+}
+
+// Clustering::all_thresh + best_thresh (src/clustering.cpp:691-774) as main() uses them (:428-438): one merge replay on the device
+float auto_threshold(f3ps::Handle& h, const std::vector<uint32_t>& truth, std::string& report) {
+    const float start_thresh = 0.8f, end_thresh = 1.0f, step_thresh = 0.005f;   // globals of the reference (:76-78)
+    std::vector<float> thr(1, start_thresh);
+    for (float t = start_thresh + step_thresh; t <= end_thresh; t += step_thresh) thr.push_back(t);
+    std::vector<f3ps_performance> perf(thr.size());
+    h.check(f3ps_eval_thresholds(h.get(), truth.data(), (int64_t)truth.size(), nullptr, 0, thr.data(), (int)thr.size(), perf.data(), nullptr, nullptr));
+    char buf[256];
+    snprintf(buf, sizeof buf, "Testing thresholds from %f to %f (step %f)\n", start_thresh, end_thresh, step_thresh); report += buf;
+    float best_t = 0; f3ps_performance best{0, 0, 0, 0, 0, 0, 0};
+    for (size_t k = 0; k < thr.size(); ++k) {
+        snprintf(buf, sizeof buf, "<T, Fscore, voi, wov> = <%f, %f, %f, %f>\n", thr[k], perf[k].fscore, perf[k].voi, perf[k].wov); report += buf;
+        if (perf[k].fscore > best.fscore) { best = perf[k]; best_t = thr[k]; }
+    }
+    snprintf(buf, sizeof buf, "Using best threshold: %f (F-score %f, voi %f)\n", best_t, best.fscore, best.voi); report += buf;
+    return best_t;
 }
 
 int process_file(const std::string& file, const Options& o, int device, std::string& report, f3ps::Handle* worker) {
@@ -102,7 +143,16 @@ int process_file(const std::string& file, const Options& o, int device, std::str
                                      o.normal_importance, o.disable_transform ? 0 : 1, 0));
         h.check(f3ps_set_merge_params(h.get(), o.rgb ? F3PS_RGB_EUCL : F3PS_LAB_CIEDE00, o.cvx ? F3PS_CONVEX_NORMALS_DIFF : F3PS_NORMALS_DIFF, merging, lam, bins));
         h.check(f3ps_set_input(h.get(), cloud->points.data(), (int64_t)cloud->size(), 32, 0));
-        h.check(f3ps_run(h.get(), o.thresh));
+        float thresh = o.thresh;
+        if (o.thresh_specified) h.check(f3ps_run(h.get(), thresh));
+        else {                                                              // no -t: the reference's threshold sweep (:428-438)
+            h.check(f3ps_extract(h.get())); h.check(f3ps_graph(h.get()));
+            f3ps_counts n0; h.check(f3ps_get_counts(h.get(), &n0));
+            std::vector<int32_t> pv((size_t)n0.n_points);
+            h.check(f3ps_get_point_voxel(h.get(), pv.data(), n0.n_points));
+            thresh = auto_threshold(h, voxelise_truth(pv, input, (size_t)n0.n_voxels), report);
+            h.check(f3ps_merge(h.get(), thresh));                           // main() re-clusters at the chosen threshold (:443)
+        }
         f3ps_counts n; h.check(f3ps_get_counts(h.get(), &n));
         n_sv = n.n_supervoxels; n_seg = n.n_segments; n_merges = n.n_merges;
         std::vector<float> xyz(3 * (size_t)n.n_labeled); std::vector<uint32_t> lab(n.n_labeled), vox(n.n_labeled);
@@ -144,11 +194,9 @@ int main(int argc, char** argv) {
         printf("Found %zu files\n", file_list.size());
     } else if (find_switch(argc, argv, "-p")) { parse(argc, argv, "-p", path); file_list.push_back(path); }
     else { fprintf(stderr, "No input file or directory specified\n"); return 1; }
-    if (!find_switch(argc, argv, "-t")) {
-        fprintf(stderr, "Automatic threshold selection needs the evaluation module (Testing), which is outside this build's scope: pass -t <threshold>\n");
-        return 1;
-    }
-    parse(argc, argv, "-t", o.thresh);
+    o.thresh_specified = find_switch(argc, argv, "-t");
+    if (o.thresh_specified) parse(argc, argv, "-t", o.thresh);
+    else if (find_switch(argc, argv, "--facade")) { fprintf(stderr, "the threshold sweep runs on the direct path: drop --facade or pass -t <threshold>\n"); return 1; }
     parse(argc, argv, "-v", o.voxel_resolution); parse(argc, argv, "-s", o.seed_resolution);
     parse(argc, argv, "-c", o.color_importance); parse(argc, argv, "-z", o.spatial_importance); parse(argc, argv, "-n", o.normal_importance);
     o.rgb = find_switch(argc, argv, "--RGB"); o.cvx = find_switch(argc, argv, "--CVX");

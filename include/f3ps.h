@@ -198,10 +198,12 @@ int f3ps_slab_expand_end(f3ps_ctx* ctx);
  * truth_label[V] = ground-truth label of every voxel (the labelled voxel cloud main() builds, supervoxel_clustering.cpp:387-400),
  * thresholds[n] ascending (main(): 0.8 .. 1 in float steps of 0.005); perf[n] = performanceSet (testing.h:68-75) per threshold,
  * n_segments[n] / n_merges_at[n] (optional) = regions left / merges done at each threshold.  Leaves the handle in the state
- * of f3ps_merge(thresholds[n-1]).  Intersections by exact xyz become equality of the voxel index. */
+ * of f3ps_merge(thresholds[n-1]).  Intersections by exact xyz become equality of the voxel index: truth_label[v] = 0xffffffff
+ * marks a voxel without a ground-truth point at its xyz, extra_truth_label[n_extra] lists the labels of ground-truth points
+ * that are not voxels of the segmentation (after f3ps_set_graph only owned voxels are known to the handle). */
 typedef struct f3ps_performance { float voi, precision, recall, fscore, wov, fpr, fnr; } f3ps_performance;
-int f3ps_eval_thresholds(f3ps_ctx* ctx, const uint32_t* truth_label, int64_t n_voxels, const float* thresholds, int n_thresholds,
-                         f3ps_performance* perf, int32_t* n_segments, int32_t* n_merges_at);
+int f3ps_eval_thresholds(f3ps_ctx* ctx, const uint32_t* truth_label, int64_t n_voxels, const uint32_t* extra_truth_label, int64_t n_extra,
+                         const float* thresholds, int n_thresholds, f3ps_performance* perf, int32_t* n_segments, int32_t* n_merges_at);
 
 /* CUDA-event time of the last run of a stage, ms (valid after f3ps_sync) */
 int f3ps_stage_ms(f3ps_ctx* ctx, int stage, float* ms);

@@ -16,6 +16,7 @@
 #include "pcl_shim.h"
 #include "color_utilities.h"
 #include "clustering_state.h"
+#include "testing.h"
 
 typedef pcl::Normal Normal;
 typedef pcl::PointXYZL PointLT;
@@ -69,6 +70,12 @@ public:
     PointLCloudT::Ptr get_labeled_cloud() const;
 
     void cluster(float threshold);
+
+    /* threshold sweep of src/clustering.cpp:691-774: every threshold is a prefix of ONE merge replay on the device;
+     * ground_truth = labelled voxel cloud (points matched to the segmentation's voxels by exact xyz, as Testing does) */
+    std::map<float, performanceSet> all_thresh(PointLCloudT::Ptr ground_truth, float start_thresh, float end_thresh, float step_thresh);
+    std::pair<float, performanceSet> best_thresh(PointLCloudT::Ptr ground_truth, float start_thresh, float end_thresh, float step_thresh);
+    std::pair<float, performanceSet> best_thresh(std::map<float, performanceSet> all_thresh);
 
     /* the reference's --V trace "left: %de/%dp - w: %f - [%d, %d]" (src/clustering.cpp:390-392), as data */
     const std::vector<MergeStep>& get_merge_log() const { return merge_log_; }

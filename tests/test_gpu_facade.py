@@ -31,7 +31,7 @@ def test_facade_matches_fused_path(pcd_file):
 def test_cli_flags_and_merge_trace(pcd_file, oracle_mod, small_frame, tmp_path):
     cli = os.path.join(HOST, "supervoxel_clustering")
     assert subprocess.run([cli], capture_output=True).returncode == 1                        # argc < 3 -> usage, exit 1
-    assert subprocess.run([cli, "-p", pcd_file], capture_output=True).returncode == 1        # no -t: auto threshold not built
+    assert subprocess.run([cli, "-p", pcd_file, "--facade"], capture_output=True).returncode == 1   # the sweep runs on the direct path
     bad = subprocess.run([cli, "-p", pcd_file, "-t", "0.2", "--ML", "--AL"], capture_output=True, text=True)
     assert bad.returncode == 1 and "Only one parameter" in bad.stderr
     outp = str(tmp_path / "labels.pcd")
@@ -79,3 +79,24 @@ def test_cli_directory_sweep_frames_in_flight(tmp_path, oracle_mod):
     for f, l in zip(files, done):
         tok = l.split()
         assert int(tok[5]) == want[f][0] and int(tok[11]) == want[f][1], (f, l, want[f])
+
+
+def test_cli_auto_threshold_like_the_reference_default(pcd_file, small_frame):
+    """No -t: main() sweeps 41 thresholds 0.8 .. 1 (src/supervoxel_clustering.cpp:428-438) against the ground truth and
+    re-clusters at the best F-score.  The file has no label field -> one truth segment, as the reference's bundled cloud."""
+    import f3ps
+    cli = os.path.join(HOST, "supervoxel_clustering")
+    run = subprocess.run([cli, "-p", pcd_file, "--CVX", "--AL"], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    lines = run.stdout.splitlines()
+    sweep = [l for l in lines if l.startswith("<T, Fscore, voi, wov>")]
+    assert len(sweep) == 41 and sweep[0].startswith("<T, Fscore, voi, wov> = <0.800000,")
+    best = [l for l in lines if l.startswith("Using best threshold:")]
+    assert len(best) == 1
+    g = f3ps.Segmenter(); g.set_vccs_params(); g.set_merge_params(color_mode=0, geom_mode=1, merge_mode=1)
+    g.set_input(small_frame); g.extract(); g.graph()
+    bt, bp = g.best_thresh(np.zeros(g.counts().n_voxels, np.uint32))
+    assert best[0].startswith("Using best threshold: %f (F-score %f" % (bt, bp["fscore"]))
+    g.merge(bt)
+    done = [l for l in lines if l.startswith("Clustering complete")][0].split()
+    assert int(done[5]) == g.counts().n_merges and int(done[8]) == g.counts().n_segments
