@@ -237,6 +237,7 @@ int f3ps_create(int device, void* stream, f3ps_ctx** out) {
          cudaMemcpy(ctx->d_lab_lut, f3ps_lab_lut_begin, lut_bytes, cudaMemcpyHostToDevice) == cudaSuccess;
     for (int i = 0; i < f3ps_ctx::kEvents && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_batch, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { f3ps_destroy(ctx); return F3PS_ERR_CUDA; }
     // the handle's stream is non-blocking: it does not wait for the legacy stream the two copies above ran on
     cudaMemsetAsync(ctx->d_sc, 0, sizeof(DevScalars), ctx->stream);
@@ -266,6 +267,7 @@ void f3ps_destroy(f3ps_ctx* ctx) {
     if (ctx->d_lab_lut) cudaFree(ctx->d_lab_lut);
     for (int i = 0; i < f3ps_ctx::kEvents; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->ev_wait) cudaEventDestroy(ctx->ev_wait);
+    if (ctx->ev_batch) cudaEventDestroy(ctx->ev_batch);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -791,6 +793,121 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
     if (ctx->h_sc->mctl.error) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "merge kernel reported an internal capacity error");
     ctx->n_out = ctx->h_sc->n_out;
     ctx->progress = P_MERGED;
+    return F3PS_OK;
+}
+
+// Clustering::cluster(threshold) for MANY frames with ONE launch of the resident merge kernel: CTA i of the grid replays frame i.
+// A sweep that keeps frames in flight on independent streams is capped by the 32 hardware queues of a context (at most 32
+// single-CTA merge kernels overlap); one grid of n CTAs runs n frames side by side.  Every handle must be on the same device,
+// with its graph built (f3ps_graph); handles whose graph does not fit the resident kernel run f3ps_merge on their own.
+// Results per handle are exactly those of f3ps_merge(handle, threshold).
+int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
+    if (!ctxs || n < 1) return F3PS_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < n; ++i) {
+        if (!ctxs[i]) return F3PS_ERR_INVALID_ARGUMENT;
+        if (ctxs[i]->device != ctxs[0]->device) return ctx_fail(ctxs[i], F3PS_ERR_INVALID_ARGUMENT, "f3ps_merge_batch: handles on different devices");
+        if (ctxs[i]->progress < P_EXPANDED)
+            return ctx_fail(ctxs[i], F3PS_ERR_LOGIC, "Cannot call 'cluster' before setting an initial state with 'set_initialstate'");
+    }
+    cudaSetDevice(ctxs[0]->device);
+    int rc;
+    std::vector<int> batch, solo;
+    std::vector<int> slots_of(n, 0);
+    for (int i = 0; i < n; ++i) {
+        f3ps_ctx* ctx = ctxs[i];
+        if (ctx->progress < P_GRAPH) { rc = f3ps_graph(ctx); if (rc) return rc; }
+        const unsigned S = ctx->S, E = ctx->E, P = ctx->n_pos;
+        int slots = 0;
+        for (int sl : {4, 8, 12, 16}) if (!slots && (size_t)E <= (size_t)sl * kFastOwners) slots = sl;
+        const bool ok = S > 0 && slots && S < 65535u && P > 0 && !ctx->force_general_merge && ctx->merge_kernel_choice != 3;
+        slots_of[i] = slots;
+        (ok ? batch : solo).push_back(i);
+    }
+    int slots = 4;
+    for (int i : batch) slots = std::max(slots, slots_of[i]);
+    const unsigned E_cap = (unsigned)slots * kFastOwners;
+    {   // the shared-memory layout must fit with the batch's edge capacity
+        std::vector<int> keep;
+        for (int i : batch) {
+            const unsigned S_cap = (ctxs[i]->S + 7u) & ~7u;
+            if (FastSmem(nullptr, S_cap, E_cap).bytes <= 227u * 1024u) keep.push_back(i); else solo.push_back(i);
+        }
+        batch.swap(keep);
+    }
+    for (int i : solo) { rc = f3ps_merge(ctxs[i], threshold); if (rc) return rc; }
+    for (size_t g0 = 0; g0 < batch.size(); g0 += kFastBatchMax) {
+        const size_t g1 = std::min(batch.size(), g0 + (size_t)kFastBatchMax);
+        static thread_local FastBatch B;                     // 32 KB: not on the stack
+        size_t bytes = 0;
+        f3ps_ctx* lead = ctxs[batch[g0]];
+        for (size_t k = g0; k < g1; ++k) {
+            f3ps_ctx* ctx = ctxs[batch[k]];
+            rc = mark(ctx, 7); if (rc) return rc;
+            const unsigned S = ctx->S, P = ctx->n_pos; const size_t Sc = std::max(1u, S), Pc = std::max(1u, P);
+            F3PS_CUDA_OK(cudaMemcpyAsync(ctx->reg_work.p, ctx->reg_init.p, region_bytes(Sc), cudaMemcpyDeviceToDevice, ctx->stream));   // cluster(float) restarts (:678)
+            const size_t eb = std::min(ctx->edge_init.cap, ctx->edge_work.cap);
+            F3PS_CUDA_OK(cudaMemcpyAsync(ctx->edge_work.p, ctx->edge_init.p, eb, cudaMemcpyDeviceToDevice, ctx->stream));
+            F3PS_CUDA_OK(cudaMemsetAsync(SC(mctl), 0, sizeof(MergeCtl), ctx->stream));
+            F3PS_CUDA_OK(ctx->mlog.ensure(Sc * 20));
+            char* lp = (char*)ctx->mlog.p;
+            ctx->ML.a = (unsigned*)lp; ctx->ML.b = (unsigned*)(lp + Sc * 4); ctx->ML.w = (float*)(lp + Sc * 8);
+            ctx->ML.edges_left = (unsigned*)(lp + Sc * 12); ctx->ML.regions_left = (unsigned*)(lp + Sc * 16);
+            F3PS_CUDA_OK(ctx->run_out_off.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->run_dense.ensure(Sc * 4)); F3PS_CUDA_OK(ctx->region_dense.ensure(Sc * 4));
+            F3PS_CUDA_OK(ctx->out_xyz.ensure(Pc * 12)); F3PS_CUDA_OK(ctx->out_label.ensure(Pc * 4)); F3PS_CUDA_OK(ctx->out_voxel.ensure(Pc * 4));
+            F3PS_CUDA_OK(ctx->vox_segment.ensure(Pc * 4));
+            F3PS_CUDA_OK(cudaMemsetAsync(ctx->vox_segment.p, 0xff, Pc * 4, ctx->stream));
+            F3PS_CUDA_OK(cudaMemsetAsync(SC(n_out), 0, 4, ctx->stream));
+            FastArgs& A = B.a[k - g0];
+            A.R = ctx->R1; A.E = ctx->E1; A.n_edges_ptr = SC(n_edges); A.n_sv_ptr = SC(xctl.n_sv); A.ep = edge_params(ctx); A.lambda_dev = SC(lambda);
+            A.threshold = threshold; A.run_start = ctx->run_start.as<unsigned>(); A.run_end = ctx->run_end.as<unsigned>();
+            A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
+            A.ctl = SC(mctl); A.S_cap = (S + 7u) & ~7u; A.E_cap = E_cap;
+            bytes = std::max(bytes, FastSmem(nullptr, A.S_cap, E_cap).bytes);
+            rc = mark(ctx, 9); if (rc) return rc;
+            if (ctx != lead) {                               // the lead's stream runs the grid: it waits for everybody's set-up
+                F3PS_CUDA_OK(cudaEventRecord(ctx->ev_batch, ctx->stream));
+                F3PS_CUDA_OK(cudaStreamWaitEvent(lead->stream, ctx->ev_batch, 0));
+            }
+        }
+        {
+            f3ps_ctx* ctx = lead;
+            void (*kern)(const FastBatch) = slots == 4 ? merge_fast_batch_kernel<4> : slots == 8 ? merge_fast_batch_kernel<8> : slots == 12 ? merge_fast_batch_kernel<12> : merge_fast_batch_kernel<16>;
+            static bool attr_set[4] = {false, false, false, false};
+            if (!attr_set[slots / 4 - 1]) { F3PS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set[slots / 4 - 1] = true; }
+            kern<<<(unsigned)(g1 - g0), kFastThreads, bytes, ctx->stream>>>(B);
+            ctx->launches++;
+            F3PS_CUDA_OK(cudaPeekAtLastError());
+            F3PS_CUDA_OK(cudaEventRecord(ctx->ev_batch, ctx->stream));
+        }
+        for (size_t k = g0; k < g1; ++k) {                   // every handle continues on its own stream after the grid
+            f3ps_ctx* ctx = ctxs[batch[k]];
+            if (ctx != lead) F3PS_CUDA_OK(cudaStreamWaitEvent(ctx->stream, lead->ev_batch, 0));
+            ctx->merge_path = 1;
+            rc = mark(ctx, 10); if (rc) return rc;
+            const unsigned P = ctx->n_pos;
+            LAUNCH(ctx, dense_label_kernel, 1, 1024, 0, ctx->R1, SC(xctl.n_sv), ctx->run_start.as<unsigned>(), ctx->run_end.as<unsigned>(), ctx->run_out_off.as<unsigned>(),
+                   ctx->run_dense.as<unsigned>(), ctx->region_dense.as<unsigned>(), SC(n_out));
+            if (P) LAUNCH(ctx, labeled_cloud_kernel, grid_for(P, 256), 256, 0, ctx->pos_run.as<unsigned>(), P, ctx->order, ctx->run_start.as<unsigned>(),
+                          ctx->run_out_off.as<unsigned>(), ctx->run_dense.as<unsigned>(), ctx->gxyz, ctx->out_xyz.as<float>(), ctx->out_label.as<unsigned>(),
+                          ctx->out_voxel.as<unsigned>(), ctx->vox_segment.as<unsigned>(), ctx->graph_from_host ? nullptr : ctx->sorted_label,
+                          ctx->graph_from_host ? nullptr : ctx->owner0.as<unsigned>());
+            rc = mark(ctx, 8); if (rc) return rc;
+        }
+        for (size_t k = g0; k < g1; ++k) {
+            f3ps_ctx* ctx = ctxs[batch[k]];
+            rc = pull_scalars(ctx); if (rc) return rc;
+            if (ctx->h_sc->mctl.error) {                     // a merge overflowed the resident kernel's touched list: this frame alone, general kernel
+                const bool was = ctx->force_general_merge;
+                ctx->force_general_merge = true;
+                rc = f3ps_merge(ctx, threshold);
+                ctx->force_general_merge = was;
+                if (rc) return rc;
+                continue;
+            }
+            ctx->n_out = ctx->h_sc->n_out;
+            ctx->progress = P_MERGED;
+        }
+    }
     return F3PS_OK;
 }
 

@@ -201,7 +201,7 @@ __device__ __noinline__ float geom_delta(int geom_mode, float4 n_lo, float4 c_lo
 }
 
 template <int SLOTS>
-__global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(FastArgs A) {
+__device__ __forceinline__ void merge_fast_body(const FastArgs& A) {
     extern __shared__ __align__(128) char smem_raw[];
     const FastSmem sm(smem_raw, A.S_cap, A.E_cap);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -764,5 +764,18 @@ __global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(FastArgs A)
         ctl->max_touched = (unsigned)sm.misc[FM_MAXT]; ctl->nan_weights = (unsigned)sm.misc[FM_NANW]; ctl->error = (unsigned)sm.misc[FM_ERROR];
     }
 }
+
+// one frame: one CTA
+template <int SLOTS>
+__global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(const __grid_constant__ FastArgs A) { merge_fast_body<SLOTS>(A); }
+
+// A batch of frames in ONE launch, CTA i replays frame i (f3ps_merge_batch).  Independent streams share at most 32 hardware
+// queues (CUDA_DEVICE_MAX_CONNECTIONS), so at most 32 single-CTA merge kernels ever overlap; one grid has no such limit.
+// The per-frame arguments travel in the kernel parameter space (<= 32,764 bytes on sm_70+ with CUDA >= 12.1).
+constexpr int kFastBatchMax = 32764 / (int)sizeof(FastArgs) < 96 ? 32764 / (int)sizeof(FastArgs) : 96;
+struct FastBatch { FastArgs a[kFastBatchMax]; };
+static_assert(sizeof(FastBatch) <= 32764, "kernel parameter space");
+template <int SLOTS>
+__global__ void __launch_bounds__(kFastThreads, 1) merge_fast_batch_kernel(const __grid_constant__ FastBatch B) { merge_fast_body<SLOTS>(B.a[blockIdx.x]); }
 
 } // namespace f3ps

@@ -100,6 +100,7 @@ def lib():
         "f3ps_test_lab_ciede00": (C.c_int, [vp, vp, vp, vp, i64]),
         "f3ps_test_rgb_eucl": (C.c_int, [vp, vp, vp, vp, i64]),
         "f3ps_test_sort_pairs": (C.c_int, [vp, vp, vp, i64, C.c_int]),
+        "f3ps_merge_batch": (C.c_int, [C.POINTER(vp), C.c_int, f32]),
         "f3ps_eval_thresholds": (C.c_int, [vp, vp, i64, vp, i64, vp, C.c_int, vp, vp, vp]),
         "f3ps_slab_reset": (C.c_int, [vp]),
         "f3ps_slab_bbox": (C.c_int, [vp, vp]),
@@ -130,13 +131,27 @@ EXPORTED = ["f3ps_create", "f3ps_destroy", "f3ps_last_error", "f3ps_version", "f
             "f3ps_get_merge_log", "f3ps_get_state_regions", "f3ps_get_state_edges", "f3ps_get_labeled_cloud", "f3ps_get_region_mean_color",
             "f3ps_get_voxel_segments_device", "f3ps_stage_ms", "f3ps_launch_count", "f3ps_merge_profile", "f3ps_expand_profile", "f3ps_test_rgb2lab",
             "f3ps_test_lab_ciede00", "f3ps_test_rgb_eucl", "f3ps_test_sort_pairs",
-            "f3ps_eval_thresholds", "f3ps_slab_reset", "f3ps_slab_bbox", "f3ps_slab_set_frame", "f3ps_slab_keys", "f3ps_slab_route", "f3ps_slab_array",
+            "f3ps_merge_batch", "f3ps_eval_thresholds", "f3ps_slab_reset", "f3ps_slab_bbox", "f3ps_slab_set_frame", "f3ps_slab_keys", "f3ps_slab_route", "f3ps_slab_array",
             "f3ps_slab_set_voxels", "f3ps_slab_expand_begin", "f3ps_slab_expand_sweep", "f3ps_slab_expand_round_end",
             "f3ps_slab_expand_end"]
 
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def merge_batch(segs, threshold):
+    """Clustering::cluster(threshold) for many handles with one launch of the resident merge kernel (f3ps_merge_batch)."""
+    if not segs:
+        return
+    arr = (C.c_void_p * len(segs))(*[s.h for s in segs])
+    rc = lib().f3ps_merge_batch(arr, len(segs), threshold)
+    if rc:
+        for s in segs:
+            msg = s.L.f3ps_last_error(s.h).decode()
+            if msg:
+                s._chk(rc)
+        raise F3psError("f3ps_merge_batch failed with status %d" % rc)
 
 
 class Segmenter:

@@ -82,3 +82,89 @@ class FramePool:
         if errors:
             raise errors[0]
         return results
+
+
+class BatchPool:
+    """Frames in flight on ONE GPU with the merge stage batched: groups of `batch` frames run K1..K6 on their own handles /
+    streams (`workers` host threads), then ONE launch of the resident merge kernel replays the whole group, CTA i = frame i
+    (f3ps_merge_batch).  Independent streams share at most 32 hardware queues, which caps FramePool at 32 overlapping merge
+    kernels; a grid has no such cap.  Two handle sets alternate, so the front stages of group g+1 overlap the merge of group g.
+    Results are those of Segmenter.run on every frame, in frame order."""
+
+    def __init__(self, batch=64, workers=None, device=0, vccs=None, merge=None, threshold=0.2):
+        from . import binding
+        import os
+        import threading
+        self.binding = binding
+        self.batch = batch
+        self.workers = workers or max(2, min(batch, (os.cpu_count() or 4)))
+        self.sets = [[binding.Segmenter(device=device) for _ in range(batch)] for _ in range(2)]
+        for st in self.sets:
+            for s in st:
+                s.set_vccs_params(**(vccs or {}))
+                s.set_merge_params(**(merge or {}))
+                s.set_blocking_wait(True)
+        self.segs = self.sets[0] + self.sets[1]
+        self.threshold = threshold
+        self._threading = threading
+
+    def close(self):
+        for s in self.segs:
+            s.close()
+        self.sets, self.segs = [], []
+
+    def run(self, frames, on_device=False, npts=None, collect=None):
+        n = len(frames)
+        results = [None] * n
+        errors = []
+        groups = [list(range(g, min(n, g + self.batch))) for g in range(0, n, self.batch)]
+
+        def front(gi):
+            st = self.sets[gi % 2]
+            idx = groups[gi]
+
+            def worker(w):
+                try:
+                    for j in range(w, len(idx), self.workers):
+                        seg = st[j]
+                        if on_device:
+                            seg.set_input_device(frames[idx[j]], npts, 32)
+                        else:
+                            seg.set_input(frames[idx[j]])
+                        seg.extract()
+                        seg.graph()
+                except Exception as e:
+                    errors.append(e)
+            th = [self._threading.Thread(target=worker, args=(w,)) for w in range(min(self.workers, len(idx)))]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+
+        def back(gi):
+            try:
+                st = self.sets[gi % 2]
+                idx = groups[gi]
+                self.binding.merge_batch(st[:len(idx)], self.threshold)
+                if collect is not None:
+                    for j, k in enumerate(idx):
+                        results[k] = collect(st[j], k)
+            except Exception as e:
+                errors.append(e)
+
+        prev = None
+        for gi in range(len(groups)):
+            f = self._threading.Thread(target=front, args=(gi,))
+            f.start()
+            if prev is not None:
+                prev.join()                      # the set this front stage is about to reuse was merged two groups ago
+            f.join()
+            if errors:
+                raise errors[0]
+            prev = self._threading.Thread(target=back, args=(gi,))
+            prev.start()
+        if prev is not None:
+            prev.join()
+        if errors:
+            raise errors[0]
+        return results

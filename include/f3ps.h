@@ -105,6 +105,11 @@ int f3ps_seeds(f3ps_ctx* ctx);      /* K4 selectInitialSupervoxelSeeds */
 int f3ps_expand(f3ps_ctx* ctx);     /* K5 expandSupervoxels */
 int f3ps_graph(f3ps_ctx* ctx);      /* K6 makeSupervoxels + getSupervoxelAdjacency + set_initialstate + init_weights */
 int f3ps_merge(f3ps_ctx* ctx, float threshold); /* K7 Clustering::cluster(threshold): restarts from the initial state */
+/* Clustering::cluster(threshold) for n handles (same device, graphs built) with ONE launch of the resident merge kernel:
+ * CTA i replays frame i.  Independent streams share at most 32 hardware queues per context, so a sweep with one merge
+ * kernel per stream never overlaps more than 32 of them; a grid has no such limit.  Same results per handle as f3ps_merge;
+ * handles whose graph does not fit the resident kernel are clustered by f3ps_merge individually. */
+int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold);
 /* How the host waits where it needs a size from the device: 0 = spin (lowest latency, the default), 1 = sleep on a
  * blocking event.  Sweeps that keep more frames in flight than there are host cores must use 1. */
 int f3ps_set_blocking_wait(f3ps_ctx* ctx, int blocking);

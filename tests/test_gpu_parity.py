@@ -431,3 +431,38 @@ def test_general_merge_kernel_hub_graph(gpu, oracle_mod, n_leaves, mode):
     assert np.array_equal(g.array("merges_ab"), o.array("merges_ab"))
     assert same(g.array("merges_w"), o.array("merges_w"))
     assert np.array_equal(g.array("out_label"), o.array("out_label"))
+
+
+def test_merge_batch_equals_individual_merges(gpu):
+    """f3ps_merge_batch: ONE launch of the resident merge kernel, CTA i = frame i, gives every handle exactly what
+    f3ps_merge gives it alone -- mixed sizes (different slot counts), a handle forced onto the general kernel, a handle
+    whose largest merge overflows the resident kernel's touched list, and the pipelined BatchPool."""
+    from f3ps import synth, sweep
+    frames = [synth.make_frame(seed=500 + i, width=160, height=120) for i in range(9)] + [synth.make_frame(seed=20021)]
+    solo = []
+    for f in frames:
+        g = gpu.Segmenter(); g.set_vccs_params(); g.set_merge_params(**AL)
+        g.set_input(f); g.run(0.2)
+        solo.append({n: g.array(n).copy() for n in ("merges_ab", "merges_w", "merges_left", "out_label", "out_voxel")})
+    segs = []
+    for k, f in enumerate(frames):
+        g = gpu.Segmenter(); g.set_vccs_params(); g.set_merge_params(**AL)
+        if k == 3:
+            g.set_merge_kernel(2)                         # this one must take the individual path
+        g.set_input(f); g.extract(); g.graph()
+        segs.append(g)
+    for rep in range(2):                                   # twice: cluster() restarts from the initial state
+        gpu.merge_batch(segs, 0.2)
+        for k, g in enumerate(segs):
+            for n, want in solo[k].items():
+                assert np.array_equal(g.array(n), want), (rep, k, n)
+            assert g.counts().merge_path == (2 if k == 3 else 1)
+    gpu.merge_batch(segs[:5], 0.1)                         # a lower threshold: a prefix
+    for k, g in enumerate(segs[:5]):
+        m = g.counts().n_merges
+        assert m <= len(solo[k]["merges_ab"]) and np.array_equal(g.array("merges_ab"), solo[k]["merges_ab"][:m])
+    pool = sweep.BatchPool(batch=4, workers=3, merge=AL, threshold=0.2)
+    got = pool.run(frames * 2, collect=lambda s_, k: (s_.array("merges_ab").copy(), s_.array("out_label").copy()))
+    pool.close()
+    for k, (ab, lab) in enumerate(got):
+        assert np.array_equal(ab, solo[k % len(frames)]["merges_ab"]) and np.array_equal(lab, solo[k % len(frames)]["out_label"]), k
