@@ -207,7 +207,11 @@ def run_ours(args):
     host_views = [pinned[i % F].numpy().view(f3ps.synth.POINT_DTYPE).reshape(-1) for i in range(F * R)]
     ptrs = [d_frames[i % F].data_ptr() for i in range(F * R)]
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    pool = sweep.FramePool(F, device=local_rank, merge=FLAGS, threshold=THRESHOLD)
+    if args.pool == "batch":
+        # groups of F frames: K1..K6 per frame on its own handle / stream, ONE merge launch per group (CTA i = frame i)
+        pool = sweep.BatchPool(batch=F, workers=args.workers or None, device=local_rank, merge=FLAGS, threshold=THRESHOLD)
+    else:
+        pool = sweep.FramePool(F, device=local_rank, merge=FLAGS, threshold=THRESHOLD)
     stream = torch.cuda.current_stream()
 
     out_bytes = [0]
@@ -286,7 +290,7 @@ def run_ours(args):
         value = npts * n_frames * world / t_dev_max / 1e6
         e2e = npts * n_frames * world / t_e2e_max / 1e6
         V, M = counts.n_voxels, counts.n_merges
-        stage_ms = {k: v / (F * args.steps) for k, v in stage_acc.items()}     # one sample per handle per step (its last frame)
+        stage_ms = {k: v / (len(pool.segs) * args.steps) for k, v in stage_acc.items()}     # one sample per handle per step (its last frame)
         # dominant kernel = the persistent merge kernel (K7); algorithmic bytes per launch:
         # 12 E (edge list) + 40 S (region statistics) + 12 M (merge log) + 16 * fold_steps (voxels streamed by the folds)
         merge_ms = stage_ms.get("merge_kernel", stage_ms.get("merge", 0.0))
@@ -299,8 +303,12 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_dev_max / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD,
-                       "step": "%d frames per GPU, %d in flight (one handle + stream each, %d frames back to back per handle; "
-                               "the reference's -d loop processes independent files)" % (F * R, F, R),
+                       "step": ("%d frames per GPU in groups of %d: K1..K6 of a frame on its own handle + stream, ONE resident-merge launch "
+                                "per group (CTA i = frame i), the next group's front stages overlap it (BatchPool); the reference's -d loop "
+                                "processes independent files" % (F * R, F)) if args.pool == "batch" else
+                               ("%d frames per GPU, %d in flight (one handle + stream each, %d frames back to back per handle; "
+                                "the reference's -d loop processes independent files)" % (F * R, F, R)),
+                       "pool": args.pool,
                        "frames_per_step_per_gpu": F * R, "frames_in_flight_per_gpu": F, "distinct_frames": N_POOL,
                        "l2": "L2 flushed (512 MB write) between timed steps; a step streams %d MB of input" % (F * R * npts * 32 >> 20),
                        "sharding": "frames per GPU, no collective",
@@ -437,9 +445,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--inflight", type=int, default=32, help="frames in flight per GPU (handles / streams)")
-    ap.add_argument("--rounds", type=int, default=4, help="frames each handle runs back to back inside one step")
+    ap.add_argument("--inflight", type=int, default=96, help="frames per merge grid (batch pool) / frames in flight per GPU (streams pool)")
+    ap.add_argument("--rounds", type=int, default=3, help="groups per step (batch pool) / frames each handle runs back to back inside one step (streams pool)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (development)")
+    ap.add_argument("--pool", default="batch", choices=["batch", "streams"], help="batch: one merge launch per group of --inflight frames; streams: one merge kernel per stream")
+    ap.add_argument("--workers", type=int, default=0, help="host threads for the front stages of a group (batch pool)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: frames in flight (the headline); c5: one large cloud in slab mode")
     ap.add_argument("--points", type=int, default=50_000_000, help="c5: points of the merged scan")
     ap.add_argument("--verify", action="store_true", help="c5: compare the slab result with one handle processing the whole cloud")

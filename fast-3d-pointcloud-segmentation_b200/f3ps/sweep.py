@@ -146,9 +146,19 @@ class BatchPool:
                 st = self.sets[gi % 2]
                 idx = groups[gi]
                 self.binding.merge_batch(st[:len(idx)], self.threshold)
-                if collect is not None:
-                    for j, k in enumerate(idx):
-                        results[k] = collect(st[j], k)
+                if collect is not None:                  # result read-back of the group, a few host threads
+                    def reader(w):
+                        try:
+                            for j in range(w, len(idx), nread):
+                                results[idx[j]] = collect(st[j], idx[j])
+                        except Exception as e:
+                            errors.append(e)
+                    nread = max(1, min(8, len(idx)))
+                    th = [self._threading.Thread(target=reader, args=(w,)) for w in range(nread)]
+                    for t in th:
+                        t.start()
+                    for t in th:
+                        t.join()
             except Exception as e:
                 errors.append(e)
 
