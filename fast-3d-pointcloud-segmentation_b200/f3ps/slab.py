@@ -129,6 +129,37 @@ class Comm:
                 self.dist.broadcast(part, src=r)
         return full
 
+    def gather_slices_flag(self, full, bounds, flag):
+        """gather_slices(full) + all-reduce MAX of the one-element `flag` in ONE collective: every rank contributes its
+        slice padded to the longest one with the flag appended (all-gather), the slices are copied into place.
+        Returns the reduced flag on the host."""
+        if not self.on or self.world == 1:
+            return int(flag.item())
+        if self.staged:
+            self.gather_slices(full, bounds)
+            self.all_reduce(flag, "max")
+            return int(flag.item())
+        torch = self.torch
+        width = full.shape[1]
+        lens = [int(bounds[r + 1] - bounds[r]) for r in range(self.world)]
+        cap = max(lens) * width + 1
+        key = (full.dtype, cap, full.device)
+        if getattr(self, "_gs_key", None) != key:
+            self._gs_send = torch.empty(cap, dtype=full.dtype, device=full.device)
+            self._gs_recv = torch.empty((self.world, cap), dtype=full.dtype, device=full.device)
+            self._gs_key = key
+        send, recv = self._gs_send, self._gs_recv
+        lo, hi = int(bounds[self.rank]), int(bounds[self.rank + 1])
+        if hi > lo:
+            send[:(hi - lo) * width].copy_(full[lo:hi].reshape(-1))
+        send[cap - 1:cap].copy_(flag.view(full.dtype))
+        self.dist.all_gather_into_tensor(recv, send)
+        self.bytes_moved += cap * full.element_size() * (self.world - 1)
+        for r in range(self.world):
+            if r != self.rank and lens[r]:
+                full[int(bounds[r]):int(bounds[r + 1])].copy_(recv[r, :lens[r] * width].view(lens[r], width))
+        return int(recv[:, cap - 1].max().item())
+
     def all_to_all_rows(self, send, send_counts, recv_counts):
         """send: [n, k] rows grouped by destination; returns [sum(recv_counts), k] rows grouped by source rank."""
         torch = self.torch
@@ -184,13 +215,20 @@ class SlabSegmenter:
         self.seg.set_vccs_params(**(vccs or {}))
         self.seg.set_merge_params(**(merge or {}))
         self.info = {}
+        self._views = {}
 
     def close(self):
         self.seg.close()
 
     def _view(self, name, dtype):
         ptr, n, eb = self.seg.slab_array(name)
-        return device_view(self.torch, ptr, n, eb, dtype, self.device)
+        key = (ptr, n, eb, dtype)                     # the handle's buffers alternate between a few addresses: wrap each once
+        v = self._views.get(key)
+        if v is None:
+            if len(self._views) > 64:
+                self._views.clear()
+            v = self._views[key] = device_view(self.torch, ptr, n, eb, dtype, self.device)
+        return v
 
     def run(self, points, threshold=0.2, merge=True):
         torch, comm, seg = self.torch, self.comm, self.seg
@@ -201,6 +239,7 @@ class SlabSegmenter:
             e.record(self.stream)
             ev.append((name, e))
 
+        self._views.clear()
         with torch.cuda.stream(self.stream):
             tick("start")
             seg.slab_reset()
@@ -276,10 +315,9 @@ class SlabSegmenter:
                         raise binding.F3psError("expansion fixed point not reached within 32 sweeps")
                     seg.slab_expand_sweep(flag.data_ptr())
                     sweeps += 1
-                    if V:
-                        comm.gather_slices(self._view("steal", torch.int32), vb)
-                    comm.all_reduce(flag, "max")
-                    if int(flag.item()) == 0:
+                    # the slices of the steal table this sweep wrote + the convergence flag, one collective
+                    changed = comm.gather_slices_flag(self._view("steal", torch.int32), vb, flag) if V else 0
+                    if changed == 0:
                         break
                 if V:
                     comm.gather_slices(self._view("owner_next", torch.int32), vb)
