@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <new>
 
 #include "context.cuh"
@@ -436,6 +438,21 @@ int f3ps_seeds(f3ps_ctx* ctx) {
 // ---- K5 -------------------------------------------------------------------------------------------
 // One cooperative launch runs createSupervoxelHelpers, every expansion round and makeSupervoxels' lists
 // (kernels_expand.cuh); the host only learns the number of surviving helpers afterwards.
+// Sweeps: cooperative launches run ONE AT A TIME on a device (measured: K5 of concurrent frames serialises at its solo
+// duration, 0.74 ms per frame, while K1..K4 and K6 scale with the streams), so a sweep may instead launch the expansion
+// kernel as an ordinary small grid (f3ps_set_expand_sharing).  Its software grid barrier needs all CTAs of a launch resident:
+// that holds as long as the CTAs of all expansion kernels in flight fit the SMs no long-running kernel occupies, which the
+// per-device counting semaphore below enforces (the caller states the bound).
+namespace {
+struct ExpandGate { std::mutex m; std::condition_variable cv; int in_flight = 0; int limit = 1; };
+ExpandGate g_expand_gate[16];
+struct ExpandTicket {
+    ExpandGate* g = nullptr;
+    explicit ExpandTicket(ExpandGate* gate) : g(gate) { std::unique_lock<std::mutex> l(g->m); g->cv.wait(l, [&] { return g->in_flight < g->limit; }); ++g->in_flight; }
+    ~ExpandTicket() { { std::lock_guard<std::mutex> l(g->m); --g->in_flight; } g->cv.notify_one(); }
+};
+}
+
 static int expand_prepare(f3ps_ctx* ctx, ExpandArgs& A) {
     const unsigned V = ctx->V, S0 = ctx->S0; const size_t Vc = std::max(1u, V), Sc = (size_t)S0 + 2, Lc = Vc + Sc;
     DevBuf* bv[] = {&ctx->own_a, &ctx->own_b, &ctx->dst_a, &ctx->dst_b, &ctx->st0, &ctx->st1, &ctx->phantom, &ctx->owner0, &ctx->dist0};
@@ -483,6 +500,16 @@ int f3ps_expand(f3ps_ctx* ctx) {
     const unsigned V = ctx->V;
     ExpandArgs A;
     rc = expand_prepare(ctx, A); if (rc) return rc;
+    if (V && ctx->expand_ctas > 0) {
+        // shared mode: a small ordinary grid, bounded concurrency (see ExpandGate); held until the kernel has finished
+        ExpandTicket ticket(&g_expand_gate[ctx->device & 15]);
+        const int64_t want = ((int64_t)V + kExpandThreads - 1) / kExpandThreads;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, ctx->expand_ctas));
+        expand_persistent_kernel<<<grid, kExpandThreads, 0, ctx->stream>>>(A);
+        ctx->launches++;
+        F3PS_CUDA_OK(cudaPeekAtLastError());
+        return expand_finish(ctx);
+    }
     if (V) {
         if (!ctx->expand_blocks_per_sm) {
             int nb = 0;
@@ -907,6 +934,21 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
             ctx->n_out = ctx->h_sc->n_out;
             ctx->progress = P_MERGED;
         }
+    }
+    return F3PS_OK;
+}
+
+// ctas_per_frame = 0: K5 is one cooperative launch over the whole GPU (lowest latency for a single frame, the default).
+// ctas_per_frame > 0: K5 is an ordinary grid of that many CTAs and at most max_concurrent such kernels are in flight on the
+// device (process-wide); the caller guarantees ctas_per_frame * max_concurrent <= SMs not held by long-running kernels.
+int f3ps_set_expand_sharing(f3ps_ctx* ctx, int ctas_per_frame, int max_concurrent) {
+    if (!ctx || ctas_per_frame < 0 || ctas_per_frame > kSMs || (ctas_per_frame > 0 && (max_concurrent < 1 || (int64_t)ctas_per_frame * max_concurrent > kSMs)))
+        return F3PS_ERR_INVALID_ARGUMENT;
+    ctx->expand_ctas = ctas_per_frame;
+    if (ctas_per_frame > 0) {
+        ExpandGate& g = g_expand_gate[ctx->device & 15];
+        { std::lock_guard<std::mutex> l(g.m); g.limit = max_concurrent; }
+        g.cv.notify_all();
     }
     return F3PS_OK;
 }

@@ -91,7 +91,7 @@ class BatchPool:
     kernels; a grid has no such cap.  Two handle sets alternate, so the front stages of group g+1 overlap the merge of group g.
     Results are those of Segmenter.run on every frame, in frame order."""
 
-    def __init__(self, batch=64, workers=None, device=0, vccs=None, merge=None, threshold=0.2):
+    def __init__(self, batch=64, workers=None, device=0, vccs=None, merge=None, threshold=0.2, expand_ctas=0, sms=148):
         from . import binding
         import os
         import threading
@@ -104,6 +104,10 @@ class BatchPool:
                 s.set_vccs_params(**(vccs or {}))
                 s.set_merge_params(**(merge or {}))
                 s.set_blocking_wait(True)
+                if expand_ctas:
+                    # optional (measured: no gain, K5 costs ~60 SM-ms per VGA frame either way): K5 as small ordinary grids: the merge grid of a group holds `batch` SMs for its whole duration, the
+                    # expansion kernels in flight must fit the rest (their software barrier needs co-residency)
+                    s.set_expand_sharing(expand_ctas, max(1, (sms - min(batch, sms - expand_ctas)) // expand_ctas))
         self.segs = self.sets[0] + self.sets[1]
         self.threshold = threshold
         self._threading = threading
