@@ -209,7 +209,7 @@ def run_ours(args):
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     if args.pool == "batch":
         # groups of F frames: K1..K6 per frame on its own handle / stream, ONE merge launch per group (CTA i = frame i)
-        pool = sweep.BatchPool(batch=F, workers=args.workers or None, device=local_rank, merge=FLAGS, threshold=THRESHOLD)
+        pool = sweep.BatchPool(batch=F, workers=args.workers or None, device=local_rank, merge=FLAGS, threshold=THRESHOLD, expand_ctas=-args.expand_ctas)
     else:
         pool = sweep.FramePool(F, device=local_rank, merge=FLAGS, threshold=THRESHOLD)
     stream = torch.cuda.current_stream()
@@ -217,9 +217,9 @@ def run_ours(args):
     out_bytes = [0]
 
     def collect(seg, k):
-        x = seg.array("out_xyz"); l = seg.array("out_label"); m = seg.array("merges_ab"); w = seg.array("merges_w")
-        out_bytes[0] = x.nbytes + l.nbytes + x.shape[0] * 4 + m.nbytes + w.nbytes + m.nbytes
-        return int(l.shape[0])
+        r = seg.fetch_result()                       # labelled voxel cloud (xyz, label, voxel index) + merge log (a, b, w, left)
+        out_bytes[0] = sum(a.nbytes for a in r.values())
+        return int(r["out_label"].shape[0])
 
     for _ in range(max(args.warmup, 3)):
         pool.run(ptrs, on_device=True, npts=npts)
@@ -449,7 +449,8 @@ def main():
     ap.add_argument("--rounds", type=int, default=3, help="groups per step (batch pool) / frames each handle runs back to back inside one step (streams pool)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (development)")
     ap.add_argument("--pool", default="batch", choices=["batch", "streams"], help="batch: one merge launch per group of --inflight frames; streams: one merge kernel per stream")
-    ap.add_argument("--workers", type=int, default=0, help="host threads for the front stages of a group (batch pool)")
+    ap.add_argument("--expand-ctas", type=int, default=24, help="batch pool: cap of the cooperative K5 grid per frame (0 = one voxel per thread)")
+    ap.add_argument("--workers", type=int, default=32, help="host threads for the front stages of a group (batch pool)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: frames in flight (the headline); c5: one large cloud in slab mode")
     ap.add_argument("--points", type=int, default=50_000_000, help="c5: points of the merged scan")
     ap.add_argument("--verify", action="store_true", help="c5: compare the slab result with one handle processing the whole cloud")

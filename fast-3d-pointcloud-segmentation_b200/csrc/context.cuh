@@ -88,6 +88,7 @@ struct f3ps_ctx {
     f3ps::DevBuf own_a, own_b, dst_a, dst_b, st0, st1, phantom, phantom_leaf, lab_count, lab_count2, lab_fill;
     f3ps::DevBuf cen_xyz, cen_rgb, cen_nrm, lab_keys_a, lab_keys_b, lab_vals_a, lab_vals_b, seg_start, seg_end;
     int expand_blocks_per_sm = 0, sm_count = 0;
+    bool expand_coop_cap = false;       // expand_ctas caps the grid of the cooperative launch instead
     int expand_ctas = 0;                // > 0: K5 as an ordinary grid of this many CTAs (f3ps_set_expand_sharing)
     unsigned* sorted_label = nullptr; unsigned* sorted_vox = nullptr;
     // K6

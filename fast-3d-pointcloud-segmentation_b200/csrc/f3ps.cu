@@ -500,7 +500,7 @@ int f3ps_expand(f3ps_ctx* ctx) {
     const unsigned V = ctx->V;
     ExpandArgs A;
     rc = expand_prepare(ctx, A); if (rc) return rc;
-    if (V && ctx->expand_ctas > 0) {
+    if (V && ctx->expand_ctas > 0 && !ctx->expand_coop_cap) {
         // shared mode: a small ordinary grid, bounded concurrency (see ExpandGate); held until the kernel has finished
         ExpandTicket ticket(&g_expand_gate[ctx->device & 15]);
         const int64_t want = ((int64_t)V + kExpandThreads - 1) / kExpandThreads;
@@ -519,7 +519,8 @@ int f3ps_expand(f3ps_ctx* ctx) {
             ctx->expand_blocks_per_sm = std::max(1, nb); ctx->sm_count = std::max(1, sms);
         }
         const int64_t want = ((int64_t)V + kExpandThreads - 1) / kExpandThreads;
-        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)std::min(ctx->expand_blocks_per_sm, 2) * ctx->sm_count));
+        int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)std::min(ctx->expand_blocks_per_sm, 2) * ctx->sm_count));
+        if (ctx->expand_coop_cap && ctx->expand_ctas > 0) grid = std::min(grid, ctx->expand_ctas);   // sweeps: fewer CTAs per frame, more frames side by side
         void* args[] = {&A};
         F3PS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)expand_persistent_kernel, dim3(grid), dim3(kExpandThreads), args, 0, ctx->stream));
         ctx->launches++;
@@ -942,10 +943,12 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
 // ctas_per_frame > 0: K5 is an ordinary grid of that many CTAs and at most max_concurrent such kernels are in flight on the
 // device (process-wide); the caller guarantees ctas_per_frame * max_concurrent <= SMs not held by long-running kernels.
 int f3ps_set_expand_sharing(f3ps_ctx* ctx, int ctas_per_frame, int max_concurrent) {
-    if (!ctx || ctas_per_frame < 0 || ctas_per_frame > kSMs || (ctas_per_frame > 0 && (max_concurrent < 1 || (int64_t)ctas_per_frame * max_concurrent > kSMs)))
+    if (!ctx || ctas_per_frame < 0 || ctas_per_frame > 2 * kSMs || max_concurrent < 0 ||
+        (ctas_per_frame > 0 && max_concurrent > 0 && (int64_t)ctas_per_frame * max_concurrent > kSMs))
         return F3PS_ERR_INVALID_ARGUMENT;
     ctx->expand_ctas = ctas_per_frame;
-    if (ctas_per_frame > 0) {
+    ctx->expand_coop_cap = ctas_per_frame > 0 && max_concurrent == 0;       // still a cooperative launch, only a smaller grid
+    if (ctas_per_frame > 0 && max_concurrent > 0) {
         ExpandGate& g = g_expand_gate[ctx->device & 15];
         { std::lock_guard<std::mutex> l(g.m); g.limit = max_concurrent; }
         g.cv.notify_all();

@@ -22,6 +22,9 @@ constexpr unsigned kOwnMask = 0x3fffffffu;      // label bits of an owner word
 constexpr unsigned kOwnPhantom = 0x80000000u;   // voxel is held as a phantom leaf by phantom[v]
 constexpr unsigned kOwnWon = 0x40000000u;       // its holder stole it in the round being evaluated
 constexpr int kExpandThreads = 512;
+#ifndef F3PS_EXPAND_MIN_BLOCKS
+#define F3PS_EXPAND_MIN_BLOCKS 2          // 64 registers per thread: two CTAs per SM hide the latency of the neighbour probes
+#endif
 constexpr int kExpandMaxSweeps = 32;
 constexpr int kMaxCand = 32;
 
@@ -252,7 +255,7 @@ __device__ __forceinline__ void expand_alive_scan(const ExpandArgs& A, const uns
     if (threadIdx.x == 0) A.ctl->n_sv = (*s_carry);
 }
 
-__global__ void __launch_bounds__(kExpandThreads) expand_persistent_kernel(ExpandArgs A) {
+__global__ void __launch_bounds__(kExpandThreads, F3PS_EXPAND_MIN_BLOCKS) expand_persistent_kernel(ExpandArgs A) {
     __shared__ unsigned s_warp[32];
     __shared__ unsigned s_carry;
     __shared__ unsigned s_sorted[kExpandThreads / 32][32];

@@ -329,6 +329,16 @@ class Segmenter:
             return {"out_xyz": x, "out_label": l, "out_voxel": v}[name]
         raise KeyError(name)
 
+    def fetch_result(self):
+        """The result of a frame in one go: labelled voxel cloud (Clustering::get_labeled_cloud) + merge log, one size query."""
+        c = self.counts()
+        n, M = c.n_labeled, c.n_merges
+        x = np.empty((n, 3), np.float32); l = np.empty(n, np.uint32); v = np.empty(n, np.uint32)
+        self._chk(self.L.f3ps_get_labeled_cloud(self.h, _p(x), _p(l), _p(v), n))
+        ab = np.empty((M, 2), np.uint32); w = np.empty(M, np.float32); left = np.empty((M, 2), np.uint32)
+        self._chk(self.L.f3ps_get_merge_log(self.h, _p(ab), _p(w), _p(left), M))
+        return {"out_xyz": x, "out_label": l, "out_voxel": v, "merges_ab": ab, "merges_w": w, "merges_left": left}
+
     def state_regions(self):
         n = self.counts().n_segments
         l = np.zeros(n, np.uint32); x = np.zeros((n, 3), np.float32); nn = np.zeros((n, 3), np.float32); k = np.zeros(n, np.int32)

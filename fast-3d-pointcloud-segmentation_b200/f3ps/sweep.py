@@ -104,7 +104,9 @@ class BatchPool:
                 s.set_vccs_params(**(vccs or {}))
                 s.set_merge_params(**(merge or {}))
                 s.set_blocking_wait(True)
-                if expand_ctas:
+                if expand_ctas and expand_ctas < 0:
+                    s.set_expand_sharing(-expand_ctas, 0)            # cooperative launch, grid capped: more frames side by side
+                elif expand_ctas:
                     # optional (measured: no gain, K5 costs ~60 SM-ms per VGA frame either way): K5 as small ordinary grids: the merge grid of a group holds `batch` SMs for its whole duration, the
                     # expansion kernels in flight must fit the rest (their software barrier needs co-residency)
                     s.set_expand_sharing(expand_ctas, max(1, (sms - min(batch, sms - expand_ctas)) // expand_ctas))

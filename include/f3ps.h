@@ -108,7 +108,9 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold); /* K7 Clustering::cluster(thresh
 /* K5 launch mode.  ctas_per_frame = 0 (default): one cooperative launch over the whole GPU -- lowest latency for one frame, but
  * cooperative launches of concurrent frames run one at a time.  ctas_per_frame > 0: an ordinary grid of that many CTAs, at most
  * max_concurrent of them in flight on the device (process-wide gate); the caller guarantees that ctas_per_frame * max_concurrent
- * CTAs fit the SMs no long-running kernel occupies (the software grid barrier needs a launch's CTAs co-resident). */
+ * CTAs fit the SMs no long-running kernel occupies (the software grid barrier needs a launch's CTAs co-resident).
+ * max_concurrent = 0 with ctas_per_frame > 0: still a cooperative launch, its grid capped at ctas_per_frame (a sweep trades the
+ * latency of one frame for more frames side by side; the driver keeps guaranteeing co-residency). */
 int f3ps_set_expand_sharing(f3ps_ctx* ctx, int ctas_per_frame, int max_concurrent);
 /* Clustering::cluster(threshold) for n handles (same device, graphs built) with ONE launch of the resident merge kernel:
  * CTA i replays frame i.  Independent streams share at most 32 hardware queues per context, so a sweep with one merge
