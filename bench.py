@@ -274,6 +274,7 @@ def run_ours(args):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         solo.set_blocking_wait(False)
+        solo.set_expand_sharing(0, 0)                  # one frame alone: K5 over the whole GPU again (the pool caps its grid)
         solo.set_input_device(ptrs[k % F], npts, 32); solo.run(THRESHOLD)
         e1.record(stream); torch.cuda.synchronize()
         lat.append(e0.elapsed_time(e1))
