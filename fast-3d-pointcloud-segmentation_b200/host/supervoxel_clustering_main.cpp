@@ -1,11 +1,12 @@
 // supervoxel_clustering -- the reference's CLI (src/supervoxel_clustering.cpp:136-476) over the f3ps CUDA path.
 // Same flags, same defaults, same quirks for the hot path:
 //   {-d <dir> | -p <file>}  -v -s -c -z -n  -t  --RGB --CVX --ML [l] --AL --EQ [bins]  --NT --V
-// Not built here (out of the hot-path scope): the auto-threshold sweep (needs the
-// evaluation module, so -t is required), -r / -f, the viewer.  Additions: -o <file.pcd> writes the labelled voxel
-// cloud, --facade routes through the Clustering / SupervoxelClustering classes instead of the fused f3ps_run,
-// --gpus N shards the files of a -d sweep over N GPUs, --inflight K keeps K frames in flight per GPU (one host thread +
-// handle + stream each, no collective).
+// Without -t the threshold sweep of the reference runs (41 thresholds against the ground truth, best F-score, :428-438).
+// Not built here (out of the hot-path scope): -r / -f, the CSV writers, the viewer.
+// Additions: -o <file.pcd> writes the labelled voxel cloud, --facade routes through the Clustering / SupervoxelClustering
+// classes instead of the fused path, --gpus N shards the files of a -d sweep over N GPUs (no collective), --inflight K =
+// files per group of a sweep: K1..K6 of a file on its own handle + stream, ONE merge launch per group (f3ps_merge_batch),
+// the next group's front stages overlapping it.
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -101,6 +102,86 @@ float auto_threshold(f3ps::Handle& h, const std::vector<uint32_t>& truth, std::s
     }
     snprintf(buf, sizeof buf, "Using best threshold: %f (F-score %f, voi %f)\n", best_t, best.fscore, best.voi); report += buf;
     return best_t;
+}
+
+// ---- a -d sweep with -t: front stages per file, one merge launch per group ---------------------------------------
+struct SweepJob {
+    std::string file; pcl::PointCloud<pcl::PointXYZRGBA>::Ptr cloud; std::chrono::steady_clock::time_point t0;
+};
+void sweep_front(SweepJob& j, const Options& o, f3ps::Handle& h) {
+    pcl::PointCloud<pcl::PointXYZRGBL> input;
+    f3ps::loadPCDFile(j.file, input);                                    // return value ignored, as in the reference (:313)
+    j.cloud.reset(new pcl::PointCloud<pcl::PointXYZRGBA>());
+    for (auto& p : input.points) if (p.z < 0) p.z = std::abs(p.z);       // :317-321
+    pcl::copyPointCloud(input, *j.cloud);
+    const int merging = o.ml ? F3PS_MANUAL_LAMBDA : (o.eq ? F3PS_EQUALIZATION : F3PS_ADAPTIVE_LAMBDA);
+    const float lam = (o.ml && o.lambda != 0) ? o.lambda : 0.5f;
+    const int bins = (o.eq && o.bin_num != 0) ? o.bin_num : 500;
+    j.t0 = std::chrono::steady_clock::now();
+    h.check(f3ps_set_vccs_params(h.get(), o.voxel_resolution, o.seed_resolution, o.color_importance, o.spatial_importance,
+                                 o.normal_importance, o.disable_transform ? 0 : 1, 0));
+    h.check(f3ps_set_merge_params(h.get(), o.rgb ? F3PS_RGB_EUCL : F3PS_LAB_CIEDE00, o.cvx ? F3PS_CONVEX_NORMALS_DIFF : F3PS_NORMALS_DIFF, merging, lam, bins));
+    h.check(f3ps_set_input(h.get(), j.cloud->points.data(), (int64_t)j.cloud->size(), 32, 0));
+    h.check(f3ps_extract(h.get()));
+    h.check(f3ps_graph(h.get()));
+}
+void sweep_back(SweepJob& j, const Options& o, f3ps::Handle& h, int device, std::string& report) {
+    f3ps_counts n; h.check(f3ps_get_counts(h.get(), &n));
+    float stage[9] = {0};
+    for (int s = 0; s < 9; ++s) f3ps_stage_ms(h.get(), s, &stage[s]);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - j.t0).count();
+    char buf[512];
+    snprintf(buf, sizeof buf, "Loading pointcloud from PCD file '%s'...\nFound %d supervoxels\n", j.file.c_str(), n.n_supervoxels); report += buf;
+    if (o.verbose) {
+        std::vector<uint32_t> ab(2 * (size_t)n.n_merges), left(2 * (size_t)n.n_merges); std::vector<float> w(n.n_merges);
+        h.check(f3ps_get_merge_log(h.get(), ab.data(), w.data(), left.data(), (int64_t)n.n_merges));
+        for (int m = 0; m < n.n_merges; ++m) { snprintf(buf, sizeof buf, "left: %de/%dp - w: %f - [%d, %d]...OK\n", left[2 * m], left[2 * m + 1], w[m], ab[2 * m], ab[2 * m + 1]); report += buf; }
+    }
+    snprintf(buf, sizeof buf, "Clustering complete: %zu points -> %d merges -> %d segments over %d voxels in %.3f ms (GPU %d)\n",
+             j.cloud->size(), n.n_merges, n.n_segments, n.n_labeled, ms, device); report += buf;
+    snprintf(buf, sizeof buf, "  stage ms: voxelize %.3f neighbors %.3f normals %.3f seeds %.3f expand %.3f graph %.3f merge %.3f total %.3f\n",
+             stage[0], stage[1], stage[2], stage[3], stage[4], stage[5], stage[6], stage[7]); report += buf;
+    j.cloud.reset();
+}
+// one GPU's share of the files: groups of `group` files, two handle sets alternate
+void sweep_device(const std::vector<size_t>& mine, const std::vector<std::string>& files, const Options& o, int device, int group,
+                  std::vector<std::string>& reports, std::string& first_error, std::mutex& emu) {
+    auto fail = [&](const std::exception& e) { std::lock_guard<std::mutex> g(emu); if (first_error.empty()) first_error = e.what(); };
+    try {
+        const int threads = (int)std::max(2u, std::min<unsigned>((unsigned)group, std::thread::hardware_concurrency()));
+        std::vector<std::unique_ptr<f3ps::Handle>> sets[2];
+        for (int s = 0; s < 2; ++s) for (int k = 0; k < group; ++k) {
+            sets[s].emplace_back(new f3ps::Handle(device));
+            f3ps_set_blocking_wait(sets[s].back()->get(), 1);
+            f3ps_set_expand_sharing(sets[s].back()->get(), 24, 0);        // sweeps: smaller cooperative K5 grids, more files side by side
+        }
+        std::vector<SweepJob> jobs[2];
+        std::thread back;
+        for (size_t g0 = 0, gi = 0; g0 < mine.size(); g0 += (size_t)group, ++gi) {
+            const size_t g1 = std::min(mine.size(), g0 + (size_t)group);
+            const int si = (int)(gi & 1);
+            // the set this group is about to use was merged two groups ago; the previous group's merge is still running
+            jobs[si].assign(g1 - g0, SweepJob());
+            for (size_t k = g0; k < g1; ++k) jobs[si][k - g0].file = files[mine[k]];
+            std::vector<std::thread> th;
+            for (int w = 0; w < threads; ++w) th.emplace_back([&, w]() {
+                try { for (size_t k = (size_t)w; k < g1 - g0; k += (size_t)threads) sweep_front(jobs[si][k], o, *sets[si][k]); }
+                catch (const std::exception& e) { fail(e); }
+            });
+            for (auto& t : th) t.join();
+            if (back.joinable()) back.join();
+            { std::lock_guard<std::mutex> g(emu); if (!first_error.empty()) return; }
+            back = std::thread([&, si, g0, g1]() {
+                try {
+                    std::vector<f3ps_ctx*> ctxs;
+                    for (size_t k = 0; k < g1 - g0; ++k) ctxs.push_back(sets[si][k]->get());
+                    sets[si][0]->check(f3ps_merge_batch(ctxs.data(), (int)ctxs.size(), o.thresh));   // Clustering::cluster of every file of the group (:443)
+                    for (size_t k = 0; k < g1 - g0; ++k) sweep_back(jobs[si][k], o, *sets[si][k], device, reports[mine[g0 + k]]);
+                } catch (const std::exception& e) { fail(e); }
+            });
+        }
+        if (back.joinable()) back.join();
+    } catch (const std::exception& e) { fail(e); }
 }
 
 int process_file(const std::string& file, const Options& o, int device, std::string& report, f3ps::Handle* worker) {
@@ -216,17 +297,28 @@ int main(int argc, char** argv) {
         else {
             // -d sweep: files are independent (fresh SupervoxelClustering + Clustering per file in the reference, :348,408).
             // `inflight` frames per GPU, each on its own handle / stream / host thread; reports are printed in file order.
-            const int workers = (int)std::min<size_t>((size_t)gpus * inflight, file_list.size());
-            const bool blocking = workers > (int)std::max(1u, std::thread::hardware_concurrency() / 2);
-            std::vector<std::thread> th; std::mutex emu; std::string first_error;
-            for (int w = 0; w < workers; ++w) th.emplace_back([&, w]() {
-                try {
-                    f3ps::Handle h(w % gpus);
-                    f3ps_set_blocking_wait(h.get(), blocking ? 1 : 0);
-                    for (size_t i = w; i < file_list.size(); i += workers) process_file(file_list[i], o, w % gpus, reports[i], &h);
-                } catch (const std::exception& e) { std::lock_guard<std::mutex> g(emu); if (first_error.empty()) first_error = e.what(); }
-            });
-            for (auto& t : th) t.join();
+            std::mutex emu; std::string first_error;
+            if (o.thresh_specified && o.out.empty()) {
+                // groups of `inflight` files per GPU: front stages per file, ONE merge launch per group
+                std::vector<std::vector<size_t>> share((size_t)gpus);
+                for (size_t i = 0; i < file_list.size(); ++i) share[i % (size_t)gpus].push_back(i);
+                std::vector<std::thread> th;
+                for (int gdev = 0; gdev < gpus; ++gdev)
+                    th.emplace_back([&, gdev]() { sweep_device(share[(size_t)gdev], file_list, o, gdev, std::min(inflight, 96), reports, first_error, emu); });
+                for (auto& t : th) t.join();
+            } else {
+                const int workers = (int)std::min<size_t>((size_t)gpus * inflight, file_list.size());
+                const bool blocking = workers > (int)std::max(1u, std::thread::hardware_concurrency() / 2);
+                std::vector<std::thread> th;
+                for (int w = 0; w < workers; ++w) th.emplace_back([&, w]() {
+                    try {
+                        f3ps::Handle h(w % gpus);
+                        f3ps_set_blocking_wait(h.get(), blocking ? 1 : 0);
+                        for (size_t i = w; i < file_list.size(); i += workers) process_file(file_list[i], o, w % gpus, reports[i], &h);
+                    } catch (const std::exception& e) { std::lock_guard<std::mutex> g(emu); if (first_error.empty()) first_error = e.what(); }
+                });
+                for (auto& t : th) t.join();
+            }
             if (!first_error.empty()) throw std::runtime_error(first_error);
         }
         for (auto& r : reports) fputs(r.c_str(), stdout);
