@@ -3,19 +3,22 @@
 
 Metric: Mpoints/s end-to-end segmentation (voxelize -> VCCS -> edge weights -> merge) on the
 C2 workload: synthetic 640x480 RGB-D frames (307,200 points each, seed 20020 + k), flags
---CVX --AL -t 0.2.  A "step" is one batch of F frames (--inflight, default 32), each through f3ps_run on its
-own handle + stream: frames are independent (the reference's -d loop), and the serial merge stage of one frame
-occupies one SM, so a sweep keeps many frames in flight.  The latency of one frame alone is reported beside it
-(`single_frame_latency_ms`, the figure BASELINE.json's 2 ms target refers to).
+--CVX --AL -t 0.2.  Frames are independent (the reference's -d loop), and the serial merge stage of one frame
+occupies one SM, so a sweep keeps many frames in flight.  A "step" is --rounds groups of --inflight frames through
+f3ps/sweep.py: BatchPool -- K1..K6 of a frame on its own handle + stream, ONE launch of the resident merge kernel per
+group (CTA i = frame i, f3ps_merge_batch), the next group's front stages overlapping it (--pool streams: one merge
+kernel per stream instead).  The latency of one frame alone is reported beside it (`single_frame_latency_ms`, the
+figure BASELINE.json's 2 ms target refers to).
 
   python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K --warmup W   (CPU oracle port, rank 0 only)
+  python bench.py --workload c5 [--points P] [--verify]    (BASELINE config 5: one cloud in slab mode, torchrun for N > 1)
 
 `value`  : frames resident in HBM before the timed region; CUDA events around each step (recorded after every
            handle's stream has drained), per-stage times from each handle's own events on its own stream.
 `e2e`    : the same frames through the public API with HOST buffers (H2D of the points and D2H of the
            labelled voxel cloud + merge log inside the timed region).
-Frames are sharded one stream per GPU with no collective: every rank runs K
+Frames are sharded per GPU with no collective: every rank runs K
 steps on its own frames ("weak" scaling); the time is the max over ranks.
 """
 import argparse
