@@ -85,6 +85,7 @@ struct f3ps_ctx {
     f3ps::DevBuf cell_code, cell_code_b, cell_vox, cell_vox_b, vox_cell, cell_start, cell_codes, cell_nn, cell_keep, seeds;
     // K5
     f3ps::DevBuf owner0, dist0;                       // results: clean label / stored distance per voxel
+    f3ps::DevBuf chg_a, chg_b;                        // active-set flags of the sweeps
     f3ps::DevBuf own_a, own_b, dst_a, dst_b, st0, st1, phantom, phantom_leaf, lab_count, lab_count2, lab_fill;
     f3ps::DevBuf cen_xyz, cen_rgb, cen_nrm, lab_keys_a, lab_keys_b, lab_vals_a, lab_vals_b, seg_start, seg_end;
     int expand_blocks_per_sm = 0, sm_count = 0;

@@ -256,7 +256,7 @@ void f3ps_destroy(f3ps_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->in_buf, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->starts, &ctx->point_voxel, &ctx->sort_scratch,
         &ctx->compact_scratch, &ctx->vox_xyz, &ctx->vox_rgb, &ctx->vox_key, &ctx->hash_slots, &ctx->hash_vals, &ctx->nbr_row, &ctx->nbr_col,
         &ctx->vox_normal, &ctx->vox_curv, &ctx->cell_code, &ctx->cell_code_b, &ctx->cell_vox, &ctx->cell_vox_b, &ctx->vox_cell, &ctx->cell_start,
-        &ctx->cell_codes, &ctx->cell_nn, &ctx->cell_keep, &ctx->seeds, &ctx->owner0, &ctx->dist0, &ctx->own_a, &ctx->own_b, &ctx->dst_a, &ctx->dst_b, &ctx->st0, &ctx->st1, &ctx->phantom, &ctx->phantom_leaf,
+        &ctx->cell_codes, &ctx->cell_nn, &ctx->cell_keep, &ctx->seeds, &ctx->owner0, &ctx->dist0, &ctx->chg_a, &ctx->chg_b, &ctx->own_a, &ctx->own_b, &ctx->dst_a, &ctx->dst_b, &ctx->st0, &ctx->st1, &ctx->phantom, &ctx->phantom_leaf,
         &ctx->lab_count, &ctx->lab_count2, &ctx->lab_fill, &ctx->lab_keys_a,
         &ctx->cen_xyz, &ctx->cen_rgb, &ctx->cen_nrm, &ctx->lab_keys_b, &ctx->lab_vals_a, &ctx->lab_vals_b, &ctx->seg_start, &ctx->seg_end,
         &ctx->sv_label, &ctx->rank_of_label, &ctx->run_start, &ctx->run_end, &ctx->pos_run, &ctx->edge_set, &ctx->edge_keys_a, &ctx->edge_keys_b,
@@ -459,6 +459,7 @@ static int expand_prepare(f3ps_ctx* ctx, ExpandArgs& A) {
     for (DevBuf* b : bv) F3PS_CUDA_OK(b->ensure(Vc * 4));
     DevBuf* bl[] = {&ctx->lab_keys_a, &ctx->lab_vals_a, &ctx->lab_vals_b};
     for (DevBuf* b : bl) F3PS_CUDA_OK(b->ensure(Lc * 4));
+    F3PS_CUDA_OK(ctx->chg_a.ensure(Vc)); F3PS_CUDA_OK(ctx->chg_b.ensure(Vc));
     DevBuf* bs[] = {&ctx->seg_start, &ctx->seg_end, &ctx->lab_count, &ctx->lab_count2, &ctx->lab_fill, &ctx->phantom_leaf, &ctx->sv_label, &ctx->rank_of_label};
     for (DevBuf* b : bs) F3PS_CUDA_OK(b->ensure(Sc * 4));
     F3PS_CUDA_OK(ctx->cen_xyz.ensure(Sc * 16)); F3PS_CUDA_OK(ctx->cen_rgb.ensure(Sc * 16)); F3PS_CUDA_OK(ctx->cen_nrm.ensure(Sc * 16));
@@ -472,6 +473,7 @@ static int expand_prepare(f3ps_ctx* ctx, ExpandArgs& A) {
     A.owner[0] = ctx->own_a.as<unsigned>(); A.owner[1] = ctx->own_b.as<unsigned>();
     A.dist[0] = ctx->dst_a.as<float>(); A.dist[1] = ctx->dst_b.as<float>();
     A.st[0] = ctx->st0.as<unsigned>(); A.st[1] = ctx->st1.as<unsigned>();
+    A.chg[0] = ctx->chg_a.as<unsigned char>(); A.chg[1] = ctx->chg_b.as<unsigned char>();
     A.phantom = ctx->phantom.as<unsigned>(); A.phantom_leaf = ctx->phantom_leaf.as<int>();
     A.cen = Centroids{ctx->cen_xyz.as<float4>(), ctx->cen_rgb.as<float4>(), ctx->cen_nrm.as<float4>()};
     A.count[0] = ctx->lab_count.as<unsigned>(); A.count[1] = ctx->lab_count2.as<unsigned>(); A.fill = ctx->lab_fill.as<unsigned>(); A.off = ctx->seg_start.as<unsigned>();

@@ -49,6 +49,7 @@ struct ExpandArgs {
     VccsParams P;
     // mutable state
     unsigned* owner[2]; float* dist[2]; unsigned* st[2];
+    unsigned char* chg[2];            // per voxel: did its steal-table entry move in the sweep that wrote it (active-set sweeps)
     unsigned* phantom; int* phantom_leaf;
     Centroids cen;
     unsigned* count[2]; unsigned* fill; unsigned* off;         // per label [S0 + 2]
@@ -85,8 +86,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long l
 // One voxel of one sweep: fold, in ascending label order, every helper that holds a leaf adjacent to n at its turn
 // (SupervoxelHelper::expand restated per voxel).  Reads the round-start owners / distances and the previous
 // sweep's steal table, writes this voxel's entries of the next ones.
+//
+// Active set: the result for n is a pure function of the round-start state and of the steal-table entries of its
+// NEIGHBOURS; when none of them moved in the previous sweep (chg_in), this sweep reproduces the previous one, whose owner /
+// distance are still in own1 / dst1 (same buffers for every sweep of a round) -- only the entry is carried over and the
+// helper sizes are tallied.  chg_in == nullptr (first sweep of a round, slab mode): everything is evaluated.
 __device__ __forceinline__ void expand_sweep_voxel(const ExpandArgs& A, const unsigned n, const unsigned* own0, const float* dst0,
-        unsigned* own1, float* dst1, const unsigned* st_in, unsigned* st_out, unsigned* cnt, unsigned& any_change) {
+        unsigned* own1, float* dst1, const unsigned* st_in, unsigned* st_out, unsigned* cnt, unsigned& any_change,
+        const unsigned char* chg_in = nullptr, unsigned char* chg_out = nullptr) {
     const unsigned w0 = own0[n];
     float D = dst0[n];
     const unsigned st_n = st_in[n];
@@ -96,6 +103,20 @@ __device__ __forceinline__ void expand_sweep_voxel(const ExpandArgs& A, const un
     unsigned any_ph = w0 & kOwnPhantom;
 #pragma unroll
     for (int r = 0; r < 27; ++r) idx[r] = r < cnt_n ? (unsigned)A.nbr_col[(size_t)r * A.V_cap + n] : n;
+    if (chg_in) {
+        unsigned moved = 0;
+#pragma unroll
+        for (int r = 0; r < 27; ++r) moved |= idx[r] != n ? (unsigned)chg_in[idx[r]] : 0u;
+        if (!moved) {
+            const unsigned w1 = own1[n];                       // what the previous sweep decided
+            st_out[n] = st_n;
+            chg_out[n] = 0;
+            const unsigned l1 = w1 & kOwnMask;
+            if (l1) atomicAdd(&cnt[l1], 1u);
+            if ((w0 & kOwnPhantom) && !(w1 & kOwnWon)) atomicAdd(&cnt[A.phantom[n]], 1u);
+            return;
+        }
+    }
 #pragma unroll
     for (int r = 0; r < 27; ++r) hu[r] = idx[r] != n ? own0[idx[r]] : 0u;
 #pragma unroll
@@ -148,6 +169,7 @@ __device__ __forceinline__ void expand_sweep_voxel(const ExpandArgs& A, const un
         }
     }
     own1[n] = cur_l | (w0 & kOwnPhantom) | won; dst1[n] = D; st_out[n] = first;
+    if (chg_out) chg_out[n] = first != st_n ? 1 : 0;
     if (first != st_n) any_change = 1;
     if (cur_l) atomicAdd(&cnt[cur_l], 1u);
     if (ph_n && !won) atomicAdd(&cnt[ph_n], 1u);   // the holder still lists its phantom leaf
@@ -306,7 +328,9 @@ __global__ void __launch_bounds__(kExpandThreads, F3PS_EXPAND_MIN_BLOCKS) expand
                 unsigned any_change = 0;
                 for (unsigned l = tid; l < S0 + 2; l += nthreads) cnt_next[l] = 0u;
                 if (tid == 0) { ctl->changed[(k + 2u) & 63u] = 0u; ctl->cursor = 0u; }
-                for (unsigned n = tid; n < V; n += nthreads) expand_sweep_voxel(A, n, own0, dst0, own1, dst1, st_in, st_out, cnt, any_change);
+                const unsigned char* chg_in = s > 0 ? A.chg[k & 1] : nullptr;     // the first sweep of a round evaluates everything
+                unsigned char* chg_out = A.chg[(k + 1) & 1];
+                for (unsigned n = tid; n < V; n += nthreads) expand_sweep_voxel(A, n, own0, dst0, own1, dst1, st_in, st_out, cnt, any_change, chg_in, chg_out);
                 if (__syncthreads_or(any_change) && threadIdx.x == 0) atomicOr(&ctl->changed[k & 63u], 1u);
                 grid_barrier(ctl, nblocks, phase);
                 converged = ldcg_u(&ctl->changed[k & 63u]) == 0u;
