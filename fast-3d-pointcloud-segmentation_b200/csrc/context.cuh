@@ -12,8 +12,7 @@
 
 #define F3PS_MERGE_ERR_TOUCHED 4u
 #include "kernels_merge.cuh"
-#include "kernels_merge_fast.cuh"
-#include "kernels_merge_cluster.cuh"
+#include "kernels_merge_lean.cuh"
 #include "kernels_eval.cuh"
 
 namespace f3ps {
@@ -105,7 +104,7 @@ struct f3ps_ctx {
     const float4* pos_data = nullptr;   // voxel (x,y,z,rgba) in position order (what the merge folds stream)
     int merge_path = 0;                 // 1 = resident kernel, 2 = general kernel (last f3ps_merge)
     bool force_general_merge = false;   // f3ps_set_merge_kernel(ctx, 2)
-    int merge_kernel_choice = 0;        // 0 auto, 1 resident single CTA, 2 general, 3 four-CTA cluster
+    int merge_kernel_choice = 0;        // 0 auto, 1 resident single CTA, 2 general, 4 resident with phase counters
     f3ps::MergeLog ML{};
     unsigned n_pos = 0;           // positions of the label-ordered voxel list
     const unsigned* order = nullptr;
@@ -124,5 +123,5 @@ struct f3ps_ctx {
     f3ps::DevBuf ev_parent, ev_when, ev_dense, ev_truth, ev_table;   // f3ps_eval_thresholds
     f3ps::ExpandArgs slab_A{}; int slab_cur = 0; unsigned slab_k = 0; unsigned slab_sweeps = 0; int slab_round = 0; bool slab_expanding = false;
     bool general_attr_set = false;
-    bool lambda_attr_set = false, fast_attr_set[4] = {false, false, false, false};
+    bool lambda_attr_set = false;
 };

@@ -10,6 +10,8 @@
 #include <map>
 #include <mutex>
 #include <new>
+#include <set>
+#include <utility>
 
 #include "context.cuh"
 
@@ -707,6 +709,29 @@ int f3ps_set_graph(f3ps_ctx* ctx, int64_t n_voxels, const float* voxel_xyz, cons
 }
 
 // ---- K7 -------------------------------------------------------------------------------------------
+extern "C++" {
+namespace {
+// edge slots per worker thread of the resident kernel (0 = the graph does not fit)
+int lean_slots_for(unsigned E) {
+    for (int sl : {4, 8, 10, 12}) if ((size_t)E <= (size_t)sl * kFastOwners) return sl;
+    return 0;
+}
+void (*lean_kernel_for(int slots, bool prof))(FastArgs) {
+    if (prof) return slots == 4 ? merge_fast_kernel<4, true> : slots == 8 ? merge_fast_kernel<8, true> : slots == 10 ? merge_fast_kernel<10, true> : merge_fast_kernel<12, true>;
+    return slots == 4 ? merge_fast_kernel<4, false> : slots == 8 ? merge_fast_kernel<8, false> : slots == 10 ? merge_fast_kernel<10, false> : merge_fast_kernel<12, false>;
+}
+// The opt-in to > 48 KB of dynamic shared memory is per function AND per device: remember it per (device, function).
+int lean_attr(f3ps_ctx* ctx, const void* kern) {
+    static std::mutex m;
+    static std::set<std::pair<int, const void*>> done;
+    std::lock_guard<std::mutex> l(m);
+    if (done.count({ctx->device, kern})) return F3PS_OK;
+    F3PS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    done.insert({ctx->device, kern});
+    return F3PS_OK;
+}
+}
+}
 int f3ps_merge(f3ps_ctx* ctx, float threshold) {
     if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
     if (ctx->progress < P_EXPANDED)                            // std::logic_error of Clustering::cluster (src/clustering.cpp:671-673)
@@ -732,19 +757,13 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
     F3PS_CUDA_OK(cudaMemsetAsync(SC(n_out), 0, 4, ctx->stream));
     if (S) {
         EdgeParams ep = edge_params(ctx);
-        // resident kernel when the graph fits one SM (kernels_merge_fast.cuh), else the general one
+        // resident kernel when the graph fits one SM (kernels_merge_lean.cuh), else the general one
         const unsigned S_cap = (S + 7u) & ~7u;
-        int slots = 0;
-        for (int sl : {4, 8, 12, 16}) if (!slots && (size_t)E <= (size_t)sl * kFastOwners) slots = sl;
+        const int slots = lean_slots_for(E);
         const unsigned E_cap = (unsigned)std::max(slots, 4) * kFastOwners;
         const size_t fast_bytes = FastSmem(nullptr, S_cap, E_cap).bytes;
-        int cl_slots = 0;
-        for (int sl : {2, 4, 6, 8}) if (!cl_slots && (size_t)E <= (size_t)sl * 2048u) cl_slots = sl;
-        const size_t cl_bytes = ClusterSmem(nullptr, S_cap, (unsigned)std::max(cl_slots, 2) * 1024u).bytes;
-        const bool cluster_ok = cl_slots && S < 65535u && cl_bytes <= 227u * 1024u && P > 0;
         const bool single_ok = slots && S < 65535u && fast_bytes <= 227u * 1024u && P > 0;
-        const bool use_cluster = cluster_ok && ctx->merge_kernel_choice == 3;
-        bool fast = !ctx->force_general_merge && (use_cluster || single_ok);
+        bool fast = !ctx->force_general_merge && single_ok;
         for (int attempt = 0; attempt < 2; ++attempt) {
             if (attempt == 1) {                                    // a merge overflowed the resident kernel's touched list: start over
                 F3PS_CUDA_OK(cudaMemcpyAsync(ctx->reg_work.p, ctx->reg_init.p, region_bytes(Sc), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -758,27 +777,13 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
                 A.threshold = threshold; A.run_start = ctx->run_start.as<unsigned>(); A.run_end = ctx->run_end.as<unsigned>();
                 A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
                 A.ctl = SC(mctl); A.S_cap = S_cap;
-                if (use_cluster) {
-                    A.E_cap = (unsigned)cl_slots * 2048u;
-                    void (*kern)(FastArgs) = cl_slots == 2 ? merge_cluster_kernel<2> : cl_slots == 4 ? merge_cluster_kernel<4> : cl_slots == 6 ? merge_cluster_kernel<6> : merge_cluster_kernel<8>;
-                    F3PS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                    cudaLaunchConfig_t cfg = {};
-                    cfg.gridDim = dim3(4); cfg.blockDim = dim3(kClThreads); cfg.dynamicSmemBytes = cl_bytes; cfg.stream = ctx->stream;
-                    cudaLaunchAttribute attr[1];
-                    attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-                    cfg.attrs = attr; cfg.numAttrs = 1;
-                    F3PS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, A));
-                    ctx->launches++;
-                    ctx->merge_path = 3;
-                } else {
-                    A.E_cap = E_cap;
-                    void (*kern)(FastArgs) = slots == 4 ? merge_fast_kernel<4> : slots == 8 ? merge_fast_kernel<8> : slots == 12 ? merge_fast_kernel<12> : merge_fast_kernel<16>;
-                    if (!ctx->fast_attr_set[slots / 4 - 1]) { F3PS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); ctx->fast_attr_set[slots / 4 - 1] = true; }   // same value from every handle / thread
-                    kern<<<1, kFastThreads, fast_bytes, ctx->stream>>>(A);
-                    ctx->launches++;
-                    F3PS_CUDA_OK(cudaPeekAtLastError());
-                    ctx->merge_path = 1;
-                }
+                A.E_cap = E_cap;
+                void (*kern)(FastArgs) = lean_kernel_for(slots, ctx->merge_kernel_choice == 4);
+                rc = lean_attr(ctx, (const void*)kern); if (rc) return rc;
+                kern<<<1, kFastThreads, fast_bytes, ctx->stream>>>(A);
+                ctx->launches++;
+                F3PS_CUDA_OK(cudaPeekAtLastError());
+                ctx->merge_path = 1;
             } else {
                 const size_t per = ((size_t)Ec * 4 + 255) & ~(size_t)255, per8 = ((size_t)Ec * 8 + 255) & ~(size_t)255;
                 unsigned n2 = 2048; while (n2 < Ec) n2 <<= 1;
@@ -847,9 +852,8 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
         f3ps_ctx* ctx = ctxs[i];
         if (ctx->progress < P_GRAPH) { rc = f3ps_graph(ctx); if (rc) return rc; }
         const unsigned S = ctx->S, E = ctx->E, P = ctx->n_pos;
-        int slots = 0;
-        for (int sl : {4, 8, 12, 16}) if (!slots && (size_t)E <= (size_t)sl * kFastOwners) slots = sl;
-        const bool ok = S > 0 && slots && S < 65535u && P > 0 && !ctx->force_general_merge && ctx->merge_kernel_choice != 3;
+        const int slots = lean_slots_for(E);
+        const bool ok = S > 0 && slots && S < 65535u && P > 0 && !ctx->force_general_merge;
         slots_of[i] = slots;
         (ok ? batch : solo).push_back(i);
     }
@@ -901,9 +905,8 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
         }
         {
             f3ps_ctx* ctx = lead;
-            void (*kern)(const FastBatch) = slots == 4 ? merge_fast_batch_kernel<4> : slots == 8 ? merge_fast_batch_kernel<8> : slots == 12 ? merge_fast_batch_kernel<12> : merge_fast_batch_kernel<16>;
-            static bool attr_set[4] = {false, false, false, false};
-            if (!attr_set[slots / 4 - 1]) { F3PS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set[slots / 4 - 1] = true; }
+            void (*kern)(const FastBatch) = slots == 4 ? merge_fast_batch_kernel<4> : slots == 8 ? merge_fast_batch_kernel<8> : slots == 10 ? merge_fast_batch_kernel<10> : merge_fast_batch_kernel<12>;
+            rc = lean_attr(ctx, (const void*)kern); if (rc) return rc;
             kern<<<(unsigned)(g1 - g0), kFastThreads, bytes, ctx->stream>>>(B);
             ctx->launches++;
             F3PS_CUDA_OK(cudaPeekAtLastError());
@@ -965,7 +968,7 @@ int f3ps_set_blocking_wait(f3ps_ctx* ctx, int blocking) {
 }
 
 int f3ps_set_merge_kernel(f3ps_ctx* ctx, int which) {
-    if (!ctx || which < 0 || which > 3) return F3PS_ERR_INVALID_ARGUMENT;
+    if (!ctx || which < 0 || which > 4 || which == 3) return F3PS_ERR_INVALID_ARGUMENT;
     ctx->force_general_merge = which == 2;
     ctx->merge_kernel_choice = which;
     return F3PS_OK;

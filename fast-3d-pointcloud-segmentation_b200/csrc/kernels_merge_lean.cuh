@@ -1,0 +1,596 @@
+// kernels_merge_lean.cuh -- K7, the resident kernel: Clustering::cluster / merge / contains
+// (/root/reference/src/clustering.cpp:384-469, 497-506) replayed by ONE persistent CTA whose working set lives on the SM
+// (SURVEY.md Appendix C for the replay rules).  Round 2 rewrite of the round-1 resident kernel: that one spent its time
+// refetching instructions (8.9 k SASS instructions against a 32 KB instruction cache, 75 % hit rate) and ran CIEDE2000 on
+// 128 of its 1024 threads.  This one keeps the per-merge code small and flat:
+//
+//   edges         shared memory: 64-bit order key (weight bits : biased tie stamp) + packed (a,b); worker thread t owns the
+//                 edges t + 928 j and rescans its slots every merge (no cached minima, no pending lists)
+//   ropes / sizes shared memory (per region: head / tail / next run, run bounds, voxel count)
+//   voxels        position-ordered float4 (x,y,z,rgba) in HBM/L2; region b's runs stream through a four-slot ring of
+//                 512 voxels filled by cp.async.bulk (loader warp, full/empty mbarriers), so long folds never wait for a copy
+//   touched edges ONE worker thread per touched edge (up to 928): duplicates through a per-region mark, CIEDE2000 in every
+//                 thread that needs it (the round-1 kernel looped 128 threads over up to 600 edges), tie stamps through a hash
+//
+// Roles: warp 0 covariance / xyz sums + eigen-solve, warp 1 running colour mean + Lab, warp 2 loader, warps 3..31 workers.
+// Barriers per merge: S1 (all: partial minima published), W1 (workers: touched list complete), WB1 / WB2 (workers, or one
+// warp when <= 32 edges are touched), F (all: new geometry published), W4 (workers: new keys written).
+//
+// Limits (the host falls back to merge_kernel of kernels_merge.cuh beyond them): S < 65535, tables within 227 KB,
+// E <= 928 * SLOTS, at most 928 edges touched by one merge.
+#pragma once
+#include "kernels_merge.cuh"
+
+namespace f3ps {
+
+constexpr int kFastThreads = 1024;
+constexpr int kLeanRoleWarps = 3;
+constexpr int kFastOwners = kFastThreads - 32 * kLeanRoleWarps;     // 928 worker threads
+constexpr int kLeanWorkerWarps = kFastOwners / 32;                  // 29
+constexpr int kLeanMaxTouched = kFastOwners;
+constexpr int kLeanHash = 2048;
+constexpr int kLeanRing = 4, kLeanSlotVox = 512;
+constexpr unsigned kDeadKey = 0xffffffffu;
+constexpr unsigned long long kDeadKey64 = ~0ull;
+constexpr unsigned kNil16 = 0xffffu;
+constexpr unsigned kFastErrTouched = 4u;      // == F3PS_MERGE_ERR_TOUCHED
+constexpr unsigned kFastErrStamp = 8u;
+
+struct FastArgs {
+    RegionArrays R; EdgeArrays E;
+    const unsigned* n_edges_ptr; const unsigned* n_sv_ptr;
+    EdgeParams ep; const float* lambda_dev; float threshold;
+    const unsigned* run_start; const unsigned* run_end;
+    const float4* pos_data;                  // voxel (x,y,z,rgba) by position of the label-ordered list
+    const unsigned* sv_label;
+    MergeLog mlog; unsigned log_cap;
+    MergeCtl* ctl;
+    unsigned S_cap, E_cap;                   // table capacities the shared-memory layout was sized for
+};
+
+// shared-memory layout, shared by host (size) and device (pointers)
+struct FastSmem {
+    unsigned long long* key; unsigned* ab;
+    float4* stage; unsigned long long* mbar;                        // full[kLeanRing], empty[kLeanRing]
+    unsigned short *te_e, *partner; unsigned* res_w; unsigned char* cls; unsigned long long* te_key;
+    unsigned *hkey, *hcnt;
+    unsigned long long* wm_key; unsigned *wm_e, *wm_ab;
+    float* newgeo; int* misc; float* inv;
+    unsigned *rs, *re; int* n;
+    unsigned short *head, *tail, *next, *mark;
+    size_t bytes;
+    __host__ __device__ FastSmem(char* base, unsigned S, unsigned E_cap) {
+        size_t o = 0;
+        auto take = [&](size_t b) { char* p = base + o; o += (b + 15) & ~(size_t)15; return p; };
+        stage = (float4*)take((size_t)kLeanRing * kLeanSlotVox * 16); mbar = (unsigned long long*)take(2 * kLeanRing * 8);
+        key = (unsigned long long*)take((size_t)E_cap * 8); te_key = (unsigned long long*)take(kLeanMaxTouched * 8); ab = (unsigned*)take((size_t)E_cap * 4);
+        te_e = (unsigned short*)take(kLeanMaxTouched * 2); partner = (unsigned short*)take(kLeanMaxTouched * 2);
+        res_w = (unsigned*)take(kLeanMaxTouched * 4); cls = (unsigned char*)take(kLeanMaxTouched);
+        hkey = (unsigned*)take(kLeanHash * 4); hcnt = (unsigned*)take(kLeanHash * 4);
+        wm_key = (unsigned long long*)take(32 * 8); wm_e = (unsigned*)take(32 * 4); wm_ab = (unsigned*)take(32 * 4);
+        newgeo = (float*)take(16 * 4); misc = (int*)take(16 * 4); inv = (float*)take(64 * 4);
+        rs = (unsigned*)take((size_t)S * 4); re = (unsigned*)take((size_t)S * 4); n = (int*)take((size_t)S * 4);
+        head = (unsigned short*)take((size_t)S * 2); tail = (unsigned short*)take((size_t)S * 2); next = (unsigned short*)take((size_t)S * 2);
+        mark = (unsigned short*)take((size_t)S * 2);
+        bytes = o;
+    }
+};
+enum { FM_TCOUNT = 0, FM_EALIVE, FM_RALIVE, FM_COUNTER, FM_ND, FM_NANW, FM_ERROR, FM_MAXT, FM_SUMT, FM_MISS, FM_EVALS, FM_NMERGES };
+
+// ---- PTX helpers: mbarrier + 1-D bulk copy (TMA engine, no tensor map), named barriers ------------------------
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(unsigned mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// OpenCV's LUT interpolation spread over 8 lanes (one lattice corner each); result valid in every lane of the warp
+__device__ __forceinline__ void rgb2lab_lanes(const short* __restrict__ lut, float r255, float g255, float b255, int lane, float lab[3]) {
+    const float in[3] = {r255, g255, b255};
+    int t[3], f[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = in[k] / 255;
+        v = fminf(fmaxf(v, 0.0f), 1.0f);
+        const int c = (int)rintf(v * 16384.0f);
+        t[k] = c >> 9; f[k] = (c >> 5) & 15;
+    }
+    int out[3] = {0, 0, 0};
+    if (lane < 8) {
+        const int dr = lane >> 2, dg = (lane >> 1) & 1, db = lane & 1;
+        const int w = (dr ? f[0] : 16 - f[0]) * (dg ? f[1] : 16 - f[1]) * (db ? f[2] : 16 - f[2]);
+        const int ir = min(t[0] + dr, 32), ig = min(t[1] + dg, 32), ib = min(t[2] + db, 32);
+        const short* e = lut + ((ir * 33 + ig) * 33 + ib) * 3;
+        out[0] = w * (int)e[0]; out[1] = w * (int)e[1]; out[2] = w * (int)e[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int v = out[k];
+        v += __shfl_xor_sync(kFull, v, 4); v += __shfl_xor_sync(kFull, v, 2); v += __shfl_xor_sync(kFull, v, 1);
+        out[k] = (__shfl_sync(kFull, v, 0) + 2048) >> 12;
+    }
+    lab[0] = ((float)out[0] / 16384.0f) * 100.0f;
+    lab[1] = ((float)out[1] / 16384.0f) * 256.0f - 128.0f;
+    lab[2] = ((float)out[2] / 16384.0f) * 256.0f - 128.0f;
+}
+
+// delta_c of Clustering::delta_c_g (src/clustering.cpp:113-122) on two colour vectors, first argument = smaller label.
+// One copy of the FP64 code in the kernel (the instruction cache, not the FP64 pipe, bounds a replicated version).
+__device__ __noinline__ float colour_delta(int color_mode, float4 lo, float4 hi) {
+    const float c1[3] = {lo.x, lo.y, lo.z}, c2[3] = {hi.x, hi.y, hi.z};
+    float dc;
+    if (color_mode == 0) { dc = lab_ciede00(c1, c2); dc /= F3PS_LAB_RANGE; }
+    else { dc = rgb_eucl(c1, c2); dc /= F3PS_RGB_RANGE; }
+    return dc;
+}
+
+// delta_g of Clustering::delta_c_g (src/clustering.cpp:126-138), first argument = smaller label
+__device__ __forceinline__ float geom_delta(int geom_mode, float4 n_lo, float4 c_lo, float4 n_hi, float4 c_hi) {
+    const float n1[3] = {n_lo.x, n_lo.y, n_lo.z}, c1[3] = {c_lo.x, c_lo.y, c_lo.z}, n2[3] = {n_hi.x, n_hi.y, n_hi.z}, c2[3] = {c_hi.x, c_hi.y, c_hi.z};
+    float dg = normals_diff(n1, c1, n2, c2);
+    if (geom_mode == 1 && is_convex(n1, c1, n2, c2)) dg *= 0.5f;
+    return dg;
+}
+
+struct FastHead { unsigned hi, lo, e, ab; };
+// every warp derives the head of the weight map from the worker warps' partial minima (after S1)
+__device__ __forceinline__ FastHead lean_head(const FastSmem& sm, int lane) {
+    FastHead h;
+    const unsigned long long k = lane < kLeanWorkerWarps ? sm.wm_key[lane] : kDeadKey64;
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    h.hi = __reduce_min_sync(kFull, hi);
+    h.lo = __reduce_min_sync(kFull, hi == h.hi ? lo : kDeadKey);
+    const int win = __ffs(__ballot_sync(kFull, hi == h.hi && lo == h.lo)) - 1;
+    h.e = sm.wm_e[win]; h.ab = sm.wm_ab[win];
+    return h;
+}
+
+enum { FC_KEEP = 0, FC_FRONT = 1, FC_BACK = 2, FC_DUP = 3 };
+enum { BAR_W1 = 1, BAR_WB = 2, BAR_F = 3, BAR_W4 = 4 };
+
+#define LPROF_DECL unsigned pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned t_prev = PROF ? (unsigned)clock() : 0u
+#define LPROF(cond, i) do { if (PROF && (cond)) { const unsigned t_now = (unsigned)clock(); pc[i] += t_now - t_prev; t_prev = t_now; } } while (0)
+#define LPROF_STORE(cond, base, n) do { if (PROF && (cond)) for (int i_ = 0; i_ < (n); ++i_) A.ctl->phase_cycles[(base) + i_] = pc[i_]; } while (0)
+
+template <int SLOTS, bool PROF>
+__device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
+    extern __shared__ __align__(128) char smem_raw[];
+    const FastSmem sm(smem_raw, A.S_cap, A.E_cap);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned nE = *A.n_edges_ptr, S = *A.n_sv_ptr;
+    const RegionArrays R = A.R;
+    const unsigned mbar_full = smem_addr(sm.mbar), mbar_empty = mbar_full + 8u * kLeanRing;
+    int* const newgeo_i = reinterpret_cast<int*>(sm.newgeo);
+
+    // ---- set-up: ropes and edges -> shared memory -----------------------------------------------------------------
+    for (unsigned s = tid; s < S; s += kFastThreads) {
+        sm.rs[s] = A.run_start[s]; sm.re[s] = A.run_end[s]; sm.n[s] = R.n[s];
+        const int h = R.head[s], t = R.tail[s], nx = R.next_run[s];
+        sm.head[s] = (unsigned short)(h < 0 ? kNil16 : (unsigned)h); sm.tail[s] = (unsigned short)(t < 0 ? kNil16 : (unsigned)t);
+        sm.next[s] = (unsigned short)(nx < 0 ? kNil16 : (unsigned)nx); sm.mark[s] = (unsigned short)kNil16;
+    }
+    for (unsigned e = tid; e < A.E_cap; e += kFastThreads) {
+        unsigned long long k = kDeadKey64; unsigned ab = kDeadKey;
+        if (e < nE && A.E.stamp[e] != kDeadStamp) {
+            const float w = A.E.w[e];
+            const unsigned hi = isnan(w) ? 0x7f800000u : __float_as_uint(w);
+            k = ((unsigned long long)hi << 32) | ((unsigned)(int)A.E.stamp[e] ^ 0x80000000u);
+            ab = (A.E.a[e] << 16) | A.E.b[e];
+        }
+        sm.key[e] = k; sm.ab[e] = ab;
+    }
+    for (int i = tid; i < kLeanHash; i += kFastThreads) { sm.hkey[i] = kDeadKey; sm.hcnt[i] = 0u; }
+    if (tid == 0) {
+        for (int i = 0; i < 16; ++i) sm.misc[i] = 0;
+        sm.misc[FM_EALIVE] = (int)nE; sm.misc[FM_RALIVE] = (int)S; sm.misc[FM_COUNTER] = (int)nE;
+        for (int i = 0; i < kLeanRing; ++i) { mbar_init(mbar_full + 8u * i, 1u); mbar_init(mbar_empty + 8u * i, 2u); }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // =========== covariance sums + xyz sums: lanes 0..8 each continue one accumulator of region a over b's voxels =====
+        const float* stage_f = reinterpret_cast<const float*>(sm.stage);
+        const int pi = lane < 3 ? 0 : (lane < 5 ? 1 : (lane == 5 ? 2 : (lane < 9 ? lane - 6 : 0)));
+        const int qi = lane < 3 ? lane : (lane < 5 ? lane - 2 : 2);
+        const bool prod = lane < 6;
+        unsigned chunk = 0;
+        LPROF_DECL;
+        while (true) {
+            __syncthreads();                                                                   // S1
+            const FastHead hd = lean_head(sm, lane);
+            LPROF(lane == 0, 3);
+            if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
+            const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
+            const int na = sm.n[a], nb = sm.n[b];
+            float acc = 0.0f;
+            if (lane < 9) {
+                const float* src = lane < 4 ? reinterpret_cast<const float*>(R.accu0 + a) + lane
+                                 : (lane < 8 ? reinterpret_cast<const float*>(R.accu1 + a) + (lane - 4) : reinterpret_cast<const float*>(R.accu2 + a));
+                acc = __ldcg(src);
+            }
+            for (int done = 0; done < nb; done += kLeanSlotVox, ++chunk) {
+                const int cn = min(nb - done, kLeanSlotVox);
+                const unsigned slot = chunk & (kLeanRing - 1);
+                mbar_wait(mbar_full + 8u * slot, (chunk / kLeanRing) & 1u);
+                LPROF(lane == 0, 0);
+                const float* sf = stage_f + slot * (kLeanSlotVox * 4);
+                int j = 0;
+                for (; j + 8 <= cn; j += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float p = sf[4 * (j + u) + pi];
+                        const float q = prod ? sf[4 * (j + u) + qi] : 1.0f;
+                        acc = acc + p * q;
+                    }
+                }
+                for (; j < cn; ++j) {
+                    const float p = sf[4 * j + pi];
+                    const float q = prod ? sf[4 * j + qi] : 1.0f;
+                    acc = acc + p * q;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(mbar_empty + 8u * slot);
+            }
+            LPROF(lane == 0, 1);
+            float ac[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) ac[k] = __shfl_sync(kFull, acc, k);
+            float cx = 0, cy = 0, cz = 0, curv = 0; float nv[3] = {0, 0, 0};
+            if (lane == 0) {
+                const int nn = na + nb;
+                const float fn = (float)nn;
+                cx = ac[6] / fn; cy = ac[7] / fn; cz = ac[8] / fn;                              // computeCentroid (:411-413)
+                if (nn < 3) { nv[0] = nv[1] = nv[2] = nanf(""); curv = nv[0]; }
+                else plane_from_accu(ac, nn, nv, curv);                                         // computePointNormal (:415-417)
+                flip_and_normalize(cx, cy, cz, nv);                                             // :418-420
+                sm.newgeo[3] = cx; sm.newgeo[4] = cy; sm.newgeo[5] = cz;
+                sm.newgeo[6] = nv[0]; sm.newgeo[7] = nv[1]; sm.newgeo[8] = nv[2];
+            }
+            __syncwarp();
+            LPROF(lane == 0, 2);
+            named_bar(BAR_F, kFastThreads);                                                     // F: workers read x's old state before this
+            if (lane == 0) {
+                R.centroid[a] = make_float4(cx, cy, cz, 0.0f);
+                R.normal[a] = make_float4(nv[0], nv[1], nv[2], curv);
+                R.accu0[a] = make_float4(ac[0], ac[1], ac[2], ac[3]);
+                R.accu1[a] = make_float4(ac[4], ac[5], ac[6], ac[7]);
+                R.accu2[a] = make_float4(ac[8], 0.0f, 0.0f, 0.0f);
+            }
+        }
+        LPROF_STORE(lane == 0, 16, 4);
+    } else if (warp == 1) {
+        // =========== ColorUtilities::mean_color continued: lanes 0..2 carry r, g, b; every lane prepares one reciprocal =====
+        const unsigned* stage_u = reinterpret_cast<const unsigned*>(sm.stage);
+        const int shift = lane < 3 ? 16 - 8 * lane : 0;
+        const EdgeParams ep = A.ep;
+        float* const inv_s = sm.inv;
+        unsigned chunk = 0;
+        unsigned long long fold_steps = 0;
+        LPROF_DECL;
+        while (true) {
+            __syncthreads();                                                                   // S1
+            const FastHead hd = lean_head(sm, lane);
+            LPROF(lane == 0, 3);
+            if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
+            const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
+            const int na = sm.n[a], nb = sm.n[b];
+            float m = 0.0f;
+            if (lane < 3) m = __ldcg(reinterpret_cast<const float*>(R.mean + a) + 1 + lane);
+            const float4 guess = __ldcg(R.cvec + (na >= nb ? a : b));                          // the workers' guess for the new colour vector
+            const float cnt0 = (float)na;
+            for (int done = 0; done < nb; done += kLeanSlotVox, ++chunk) {
+                const int cn = min(nb - done, kLeanSlotVox);
+                const unsigned slot = chunk & (kLeanRing - 1);
+                float inv_next = 1 / (cnt0 + (float)(done + lane + 1));
+                mbar_wait(mbar_full + 8u * slot, (chunk / kLeanRing) & 1u);
+                LPROF(lane == 0, 0);
+                const unsigned* su = stage_u + slot * (kLeanSlotVox * 4);
+                for (int base = 0, g = 0; base < cn; base += 32, g ^= 1) {
+                    inv_s[g * 32 + lane] = inv_next;                       // 1/k of the next 32 voxels, one division per lane
+                    inv_next = 1 / (cnt0 + (float)(done + base + 32 + lane + 1));
+                    __syncwarp();
+                    const int mcount = min(32, cn - base);
+                    const float* iv = inv_s + g * 32;
+                    const unsigned* sv = su + 4 * base + 3;
+#pragma unroll 8
+                    for (int j = 0; j < mcount; ++j) {
+                        const float x = (float)((sv[4 * j] >> shift) & 255u);
+                        m = m + iv[j] * (x - m);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_local(mbar_empty + 8u * slot);
+            }
+            LPROF(lane == 0, 1);
+            const float mr = __shfl_sync(kFull, m, 0), mg = __shfl_sync(kFull, m, 1), mb = __shfl_sync(kFull, m, 2);
+            float cv[3];
+            if (ep.color_mode == 0) rgb2lab_lanes(ep.lab_lut, mr, mg, mb, lane, cv);
+            else { cv[0] = mr; cv[1] = mg; cv[2] = mb; }
+            if (lane == 0) {
+                sm.newgeo[0] = cv[0]; sm.newgeo[1] = cv[1]; sm.newgeo[2] = cv[2];
+                newgeo_i[9] = (__float_as_uint(cv[0]) == __float_as_uint(guess.x) && __float_as_uint(cv[1]) == __float_as_uint(guess.y) &&
+                               __float_as_uint(cv[2]) == __float_as_uint(guess.z)) ? 1 : 0;
+            }
+            __syncwarp();
+            LPROF(lane == 0, 2);
+            named_bar(BAR_F, kFastThreads);                                                     // F: the workers read the guess before this
+            if (lane == 0) {
+                R.mean[a] = make_float4((float)(na + nb), mr, mg, mb);
+                R.cvec[a] = make_float4(cv[0], cv[1], cv[2], 0.0f);
+            }
+            fold_steps += (unsigned long long)nb;
+        }
+        if (lane == 0) A.ctl->fold_steps = fold_steps;
+        LPROF_STORE(lane == 0, 12, 4);
+    } else if (warp == 2) {
+        // =========== loader: walk b's rope, one bulk copy per run (or part of a run) into the ring; splice the ropes =====
+        const unsigned stage_addr = smem_addr(sm.stage);
+        unsigned chunk = 0;
+        while (true) {
+            __syncthreads();                                                                   // S1
+            const FastHead hd = lean_head(sm, lane);
+            if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
+            const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
+            const int na = sm.n[a], nb = sm.n[b];
+            if (lane == 0) {
+                unsigned run = sm.head[b];
+                unsigned pos = run != kNil16 ? sm.rs[run] : 0u;
+                for (int done = 0; done < nb; done += kLeanSlotVox, ++chunk) {
+                    const int cn = min(nb - done, kLeanSlotVox);
+                    const unsigned slot = chunk & (kLeanRing - 1);
+                    mbar_wait(mbar_empty + 8u * slot, ((chunk / kLeanRing) & 1u) ^ 1u);           // both fold warps are done with the slot
+                    mbar_arrive_expect_tx(mbar_full + 8u * slot, (unsigned)cn * 16u);
+                    const unsigned dst = stage_addr + slot * (kLeanSlotVox * 16u);
+                    int off = 0;
+                    while (off < cn) {
+                        const unsigned end = sm.re[run];
+                        const int take = min((int)(end - pos), cn - off);
+                        if (take > 0) bulk_g2s(dst + (unsigned)off * 16u, A.pos_data + pos, (unsigned)take * 16u, mbar_full + 8u * slot);
+                        off += take; pos += (unsigned)take;
+                        if (pos == end) { run = sm.next[run]; if (run != kNil16) pos = sm.rs[run]; else break; }
+                    }
+                }
+            } else {
+                chunk += (unsigned)((nb + kLeanSlotVox - 1) / kLeanSlotVox);
+            }
+            chunk = __shfl_sync(kFull, chunk, 0);
+            named_bar(BAR_F, kFastThreads);                                                     // F
+            // rope splice and sizes (voxels_ = a ++ b, :406-409, :426-429) once nobody reads the old ones any more
+            if (lane == 0) {
+                sm.next[sm.tail[a]] = sm.head[b]; sm.tail[a] = sm.tail[b];
+                sm.n[a] = na + nb; sm.n[b] = 0;
+            }
+        }
+    } else {
+        // =========== workers: the weight map (argmin, incidence) and one touched edge per thread =====
+        EdgeParams ep = A.ep;
+        if (A.lambda_dev) ep.lambda = *A.lambda_dev;
+        const int wtid = tid - 32 * kLeanRoleWarps;                                            // 0..927
+        const int ww = warp - kLeanRoleWarps;                                                  // 0..28
+        unsigned my_hs = kNil16;                                                               // tie-hash slot to clear after the next S1
+        unsigned n_merges = 0;
+        LPROF_DECL;
+#define WPROF(i) LPROF(wtid == 0, i)
+        while (true) {
+            // ---- A: local minimum over my slots, warp minimum, publish ----
+            unsigned long long best = sm.key[wtid]; int bj = 0;
+#pragma unroll
+            for (int j = 1; j < SLOTS; ++j) { const unsigned long long k = sm.key[j * kFastOwners + wtid]; if (k < best) { best = k; bj = j; } }
+            {
+                const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
+                const unsigned m_hi = __reduce_min_sync(kFull, hi);
+                const unsigned m_lo = __reduce_min_sync(kFull, hi == m_hi ? lo : kDeadKey);
+                const int win = __ffs(__ballot_sync(kFull, hi == m_hi && lo == m_lo)) - 1;
+                if (lane == win) { const unsigned e = (unsigned)(bj * kFastOwners + wtid); sm.wm_key[ww] = best; sm.wm_e[ww] = e; sm.wm_ab[ww] = sm.ab[e]; }
+            }
+            WPROF(0);
+            __syncthreads();                                                                   // S1
+            const FastHead hd = lean_head(sm, lane);
+            if (my_hs != kNil16) { sm.hkey[my_hs] = kDeadKey; sm.hcnt[my_hs] = 0u; my_hs = kNil16; }
+            if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;   // strict <, src/clustering.cpp:388-389
+            const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
+            const int na_ = sm.n[a], nb_ = sm.n[b];
+            const int counter = sm.misc[FM_COUNTER];
+            WPROF(1);
+            // ---- B: the head edge leaves the map; edges incident to a or b -> touched list ----
+            if (hd.e % kFastOwners == (unsigned)wtid) { sm.key[hd.e] = kDeadKey64; sm.ab[hd.e] = kDeadKey; }
+            {
+                const unsigned aa = a * 0x10001u, bb = b * 0x10001u;
+                unsigned hits = 0;
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    const unsigned v = sm.ab[j * kFastOwners + wtid];
+                    hits |= ((__vcmpeq2(v, aa) | __vcmpeq2(v, bb)) != 0u ? 1u : 0u) << j;
+                }
+                if (__any_sync(kFull, hits != 0u)) {
+                    const int cnt = __popc(hits);
+                    int incl = cnt;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(kFull, incl, off); if (lane >= off) incl += t; }
+                    int base = 0;
+                    if (lane == 31) base = atomicAdd(&sm.misc[FM_TCOUNT], incl);
+                    int p = __shfl_sync(kFull, base, 31) + incl - cnt;
+                    while (hits) {
+                        const int j = __ffs(hits) - 1; hits &= hits - 1u;
+                        if (p < kLeanMaxTouched) { sm.te_e[p] = (unsigned short)(j * kFastOwners + wtid); sm.partner[p] = (unsigned short)kNil16; }
+                        ++p;
+                    }
+                }
+            }
+            if (wtid == 0 && n_merges < A.log_cap) {                                           // debug line of :390-392 (ranks; labels at the end)
+                A.mlog.a[n_merges] = a; A.mlog.b[n_merges] = b; A.mlog.w[n_merges] = __uint_as_float(hd.hi);
+                A.mlog.edges_left[n_merges] = (unsigned)sm.misc[FM_EALIVE]; A.mlog.regions_left[n_merges] = (unsigned)sm.misc[FM_RALIVE];
+            }
+            named_bar(BAR_W1, kFastOwners);                                                    // W1: touched list complete
+            const int T = sm.misc[FM_TCOUNT];
+            WPROF(2);
+            const bool overflow = T > kLeanMaxTouched;
+            const bool wide = T > 32;                                                          // more than one warp of touched edges
+            const bool mine = !overflow && wtid < T;
+            // ---- C: duplicates (a,x)/(b,x) through a per-region mark; x's geometry; speculative colour deltas ----
+            // Colour deltas are memoised per edge and speculated: while the fold runs, the edges that cannot reuse their stored
+            // delta get CIEDE2000 against a GUESS of the merged region's colour vector (that of the larger side; the Lab lattice
+            // quantises the mean colour, so absorbing a small region usually leaves it bit-identical).  A wrong guess re-evaluates.
+            const bool big_is_a = na_ >= nb_;
+            const bool speculate = max(na_, nb_) >= 4 * min(na_, nb_);
+            unsigned e = 0, x = 0; bool side_a = false; unsigned long long okey = kDeadKey64;
+            bool live = false, need = false;
+            float dc = 0.0f; float4 xcv, c4, n4, guess;
+            if (ww == 0 || wide) {
+                if (mine) {
+                    e = sm.te_e[wtid]; okey = sm.key[e]; sm.te_key[wtid] = okey;
+                    const unsigned eab = sm.ab[e], ea = eab >> 16, eb = eab & 0xffffu;
+                    side_a = ea == a || eb == a;
+                    x = (ea == a || ea == b) ? eb : ea;
+                    const unsigned short old = atomicCAS(&sm.mark[x], (unsigned short)kNil16, (unsigned short)wtid);
+                    if (old != (unsigned short)kNil16) { sm.partner[wtid] = old; sm.partner[old] = (unsigned short)wtid; }
+                    xcv = __ldcg(R.cvec + x); c4 = __ldcg(R.centroid + x); n4 = __ldcg(R.normal + x); dc = __ldcg(A.E.dc + e);
+                    guess = __ldcg(R.cvec + (big_is_a ? a : b));
+                }
+                if (wide) named_bar(BAR_WB, kFastOwners); else __syncwarp();                   // WB1
+                if (mine) {
+                    const unsigned q = sm.partner[wtid];
+                    const bool dup = q != kNil16 && sm.te_key[q] < okey;                       // the earlier of (a,x), (b,x) survives
+                    sm.mark[x] = (unsigned short)kNil16;
+                    live = !dup;
+                    const bool reuse = side_a ? big_is_a : (!big_is_a && ((b < x) == (a < x)));   // same ends' colours, same argument order
+                    need = live && !reuse;
+                    if (speculate && need) dc = a < x ? colour_delta(ep.color_mode, guess, xcv) : colour_delta(ep.color_mode, xcv, guess);
+                }
+            }
+            WPROF(3);
+            named_bar(BAR_F, kFastThreads);                                                    // F: region a's new colour vector / centroid / normal
+            WPROF(4);
+            // ---- D: colour delta after a wrong guess, geometry delta, weight, classification, tie stamps ----
+            if (ww == 0 || wide) {
+                unsigned wbits = kDeadKey, nab = kDeadKey; int cls = FC_DUP; unsigned hs = kNil16;
+                const bool hit = newgeo_i[9] != 0;
+                if (mine) {
+                    const bool redo = hit ? (need && !speculate) : live;                       // wrong guess: every survivor; no guess made: the ones that cannot reuse
+                    if (redo) {
+                        const float4 acv = make_float4(sm.newgeo[0], sm.newgeo[1], sm.newgeo[2], 0.0f);
+                        dc = a < x ? colour_delta(ep.color_mode, acv, xcv) : colour_delta(ep.color_mode, xcv, acv);
+                    }
+                    if (PROF && (redo || (speculate && need))) atomicAdd(&sm.misc[FM_EVALS], (redo ? 1 : 0) + ((speculate && need) ? 1 : 0));
+                    if (live) {
+                        const float4 ace = make_float4(sm.newgeo[3], sm.newgeo[4], sm.newgeo[5], 0.0f), anr = make_float4(sm.newgeo[6], sm.newgeo[7], sm.newgeo[8], 0.0f);
+                        const bool a_first = a < x;
+                        const float dg = geom_delta(ep.geom_mode, a_first ? anr : n4, a_first ? ace : c4, a_first ? n4 : anr, a_first ? c4 : ace);
+                        nab = a_first ? (a << 16) | x : (x << 16) | a;
+                        float w_new = unify(ep, dc, dg);
+                        if (isnan(w_new)) { atomicAdd(&sm.misc[FM_NANW], 1); w_new = __int_as_float(0x7f800000); }
+                        wbits = __float_as_uint(w_new);
+                        const unsigned old_hi = (unsigned)(okey >> 32);
+                        cls = wbits == old_hi ? FC_KEEP : (wbits > old_hi ? FC_FRONT : FC_BACK);
+                        if (cls != FC_KEEP) {                                                  // tie groups: same new weight, same side
+                            const unsigned hk = wbits | (cls == FC_FRONT ? 0x80000000u : 0u);
+                            unsigned h = (hk * 2654435761u) >> 21;
+                            while (true) {
+                                const unsigned prev = atomicCAS(&sm.hkey[h], kDeadKey, hk);
+                                if (prev == kDeadKey || prev == hk) break;
+                                h = (h + 1) & (kLeanHash - 1);
+                            }
+                            atomicAdd(&sm.hcnt[h], 1u);
+                            hs = h;
+                        }
+                        A.E.dc[e] = dc;
+                    } else atomicAdd(&sm.misc[FM_ND], 1);
+                    sm.res_w[wtid] = wbits; sm.cls[wtid] = (unsigned char)cls;
+                }
+                if (wide) named_bar(BAR_WB, kFastOwners); else __syncwarp();                   // WB2
+                if (mine) {
+                    unsigned lo = (unsigned)okey;
+                    if (hs != kNil16) {
+                        const unsigned gsz = sm.hcnt[hs];
+                        unsigned rank = 0;
+                        if (gsz > 1)                                                           // new arrivals keep their old relative order inside a tie group
+#pragma unroll 1
+                            for (int q = 0; q < T; ++q)
+                                if (sm.cls[q] == cls && sm.res_w[q] == wbits && sm.te_key[q] < okey) ++rank;
+                        const int st = cls == FC_BACK ? counter + (int)rank : -(counter + (int)(gsz - 1 - rank));
+                        lo = (unsigned)st ^ 0x80000000u;
+                        my_hs = hs;
+                    }
+                    sm.key[e] = live ? ((unsigned long long)wbits << 32) | lo : kDeadKey64;
+                    sm.ab[e] = nab;
+                }
+            }
+            if (wtid == 0) {
+                if (overflow) sm.misc[FM_ERROR] = (int)kFastErrTouched;                        // the host falls back to merge_kernel
+                else {
+                    if (counter > 0x7f000000 - T) sm.misc[FM_ERROR] = (int)kFastErrStamp;
+                    sm.misc[FM_COUNTER] = counter + T;
+                    sm.misc[FM_EALIVE] -= 1 + sm.misc[FM_ND]; sm.misc[FM_ND] = 0; sm.misc[FM_RALIVE] -= 1;
+                    if (T > sm.misc[FM_MAXT]) sm.misc[FM_MAXT] = T;
+                    sm.misc[FM_SUMT] += T; sm.misc[FM_MISS] += newgeo_i[9] ? 0 : 1;
+                }
+                sm.misc[FM_TCOUNT] = 0;
+            }
+            WPROF(5);
+            named_bar(BAR_W4, kFastOwners);                                                    // W4: new keys written
+            WPROF(6);
+            ++n_merges;
+        }
+#undef WPROF
+        LPROF_STORE(wtid == 0, 0, 8);
+        if (wtid == 0) sm.misc[FM_NMERGES] = (int)n_merges;
+    }
+
+    // ---- write back: weight map, ropes, log labels, counters ---------------------------------------------------------
+    __syncthreads();
+    const unsigned n_merges = (unsigned)sm.misc[FM_NMERGES];
+    for (unsigned e = tid; e < nE; e += kFastThreads) {
+        const unsigned long long k = sm.key[e];
+        if (k == kDeadKey64) A.E.stamp[e] = kDeadStamp;
+        else {
+            const unsigned ab = sm.ab[e];
+            A.E.a[e] = ab >> 16; A.E.b[e] = ab & 0xffffu; A.E.w[e] = __uint_as_float((unsigned)(k >> 32));
+            A.E.stamp[e] = (long long)(int)((unsigned)k ^ 0x80000000u);
+        }
+    }
+    for (unsigned s = tid; s < S; s += kFastThreads) {
+        R.n[s] = sm.n[s];
+        R.head[s] = sm.head[s] == kNil16 ? -1 : (int)sm.head[s]; R.tail[s] = sm.tail[s] == kNil16 ? -1 : (int)sm.tail[s];
+        R.next_run[s] = sm.next[s] == kNil16 ? -1 : (int)sm.next[s];
+    }
+    for (unsigned m = tid; m < n_merges && m < A.log_cap; m += kFastThreads) { A.mlog.a[m] = A.sv_label[A.mlog.a[m]]; A.mlog.b[m] = A.sv_label[A.mlog.b[m]]; }
+    if (tid == 0) {
+        MergeCtl* ctl = A.ctl;
+        ctl->phase_cycles[24] = (unsigned long long)sm.misc[FM_MISS]; ctl->phase_cycles[25] = (unsigned long long)sm.misc[FM_EVALS];
+        ctl->phase_cycles[27] = (unsigned long long)sm.misc[FM_SUMT];
+        ctl->n_merges = n_merges; ctl->edges_alive = (unsigned)sm.misc[FM_EALIVE]; ctl->regions_alive = (unsigned)sm.misc[FM_RALIVE];
+        ctl->counter = (long long)sm.misc[FM_COUNTER];
+        ctl->max_touched = (unsigned)sm.misc[FM_MAXT]; ctl->nan_weights = (unsigned)sm.misc[FM_NANW]; ctl->error = (unsigned)sm.misc[FM_ERROR];
+    }
+}
+
+// one frame: one CTA
+template <int SLOTS, bool PROF>
+__global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(const __grid_constant__ FastArgs A) { merge_lean_body<SLOTS, PROF>(A); }
+
+// A batch of frames in ONE launch, CTA i replays frame i (f3ps_merge_batch).  Independent streams share at most 32 hardware
+// queues (CUDA_DEVICE_MAX_CONNECTIONS), so at most 32 single-CTA merge kernels ever overlap; one grid has no such limit.
+// The per-frame arguments travel in the kernel parameter space (<= 32,764 bytes on sm_70+ with CUDA >= 12.1).
+constexpr int kFastBatchMax = 32764 / (int)sizeof(FastArgs) < 96 ? 32764 / (int)sizeof(FastArgs) : 96;
+struct FastBatch { FastArgs a[kFastBatchMax]; };
+static_assert(sizeof(FastBatch) <= 32764, "kernel parameter space");
+template <int SLOTS>
+__global__ void __launch_bounds__(kFastThreads, 1) merge_fast_batch_kernel(const __grid_constant__ FastBatch B) { merge_lean_body<SLOTS, false>(B.a[blockIdx.x]); }
+
+} // namespace f3ps

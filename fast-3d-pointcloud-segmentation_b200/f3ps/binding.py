@@ -258,13 +258,11 @@ class Segmenter:
         a = (C.c_uint64 * 32)()
         self._chk(self.L.f3ps_merge_profile(self.h, C.byref(a)))
         v = list(a)
-        if self.counts().merge_path in (1, 3):  # resident kernels (see include/f3ps.h)
-            return {"delta": dict(zip(["head", "wait_touched", "order_dedupe_small", "spec_ciede", "wait_fold", "miss_ciede", "weights_stamps", "order_dedupe_big"], v[0:8])),
-                    "owner": dict(zip(["apply_argmin", "wait_b1", "head", "scan_publish", "wait_results"], v[20:24] + [v[28]])),
-                    "mean": dict(zip(["wait_voxels", "fold", "lab_publish", "wait_b1"], v[12:16])),
-                    "cov": dict(zip(["wait_voxels", "fold", "eigen_publish", "wait_b1"], v[16:20])),
-                    "loader": {"issue": v[29], "wait_fold_splice": v[30], "wait_head": v[8], "bulk_copies": v[31]},
-                    "guess_misses": v[24], "ciede_evals": v[25], "merges_T_gt_32": v[26], "sum_T": v[27]}
+        if self.counts().merge_path == 1:       # resident kernel; cycle counters only after set_merge_kernel(4)
+            return {"worker": dict(zip(["scan_publish", "wait_s1_head", "incidence_w1", "dedupe_spec_ciede", "wait_fold", "weights_stamps", "wait_w4"], v[0:7])),
+                    "mean": dict(zip(["wait_voxels", "fold", "lab_publish", "wait_s1"], v[12:16])),
+                    "cov": dict(zip(["wait_voxels", "fold", "eigen_publish", "wait_s1"], v[16:20])),
+                    "guess_misses": v[24], "ciede_evals": v[25], "sum_T": v[27]}
         return dict(zip(["argmin", "fold", "order", "delta", "stamps", "wait_scan", "sum_T", "fold_tail"], v[:8]))
 
     def expand_profile(self):

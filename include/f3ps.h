@@ -71,7 +71,7 @@ typedef struct f3ps_counts {
     int32_t max_touched;   /* largest number of edges re-weighted by one merge */
     int64_t fold_steps;    /* voxel steps folded by the merge loop (sum of |b|) */
     int32_t nan_weights;   /* edge weights that evaluated to NaN (regions with < 3 voxels) */
-    int32_t merge_path;    /* kernel the last f3ps_merge ran: 1 = resident (one SM, edges in registers), 2 = general, 3 = cluster */
+    int32_t merge_path;    /* kernel the last f3ps_merge ran: 1 = resident (one SM, weight map in shared memory), 2 = general */
 } f3ps_counts;
 
 /* ---- life cycle ------------------------------------------------------------ */
@@ -121,7 +121,7 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold);
  * blocking event.  Sweeps that keep more frames in flight than there are host cores must use 1. */
 int f3ps_set_blocking_wait(f3ps_ctx* ctx, int blocking);
 /* which K7 kernel f3ps_merge uses: 0 = automatic (resident single-CTA kernel when the graph fits one SM, else general),
- * 1 = same as 0, 2 = always general, 3 = four-CTA thread-block cluster (one role per SM, distributed shared memory).
+ * 1 = same as 0, 2 = always general, 4 = resident kernel compiled with per-phase cycle counters (f3ps_merge_profile).
  * All replay the same merge sequence; the switch exists for tests and profiling. */
 int f3ps_set_merge_kernel(f3ps_ctx* ctx, int which);
 /* SupervoxelClustering::extract + getSupervoxelAdjacency = K1..K5 + supervoxel tables */

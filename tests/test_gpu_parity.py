@@ -231,8 +231,8 @@ def test_threshold_prefix_property_and_restart(gpu, oracle_mod, small_frame):
 
 @pytest.mark.parametrize("mp", [AL, EQ, RGB_ML], ids=["cvx_al", "eq200", "rgb_ml"])
 def test_resident_and_general_merge_kernels_agree(gpu, vga_frame, small_frame, mp):
-    """K7 has three kernels (one SM with the weight map in registers / a four-SM cluster with one role per SM /
-    everything in global memory); all replay the same sequence.  f3ps_set_merge_kernel selects."""
+    """K7 has two kernels (resident: one SM with the weight map in shared memory / general: everything in global
+    memory); both replay the same sequence.  f3ps_set_merge_kernel selects (4 = resident with phase counters)."""
     for pts, thr in ((small_frame, 0.2), (vga_frame, 0.2), (small_frame, 1.0)):
         g = gpu.Segmenter(); g.set_vccs_params(); g.set_merge_params(**mp); g.set_input(pts); g.run(thr)
         assert g.counts().merge_path == 1
@@ -241,8 +241,8 @@ def test_resident_and_general_merge_kernels_agree(gpu, vga_frame, small_frame, m
         assert g.counts().merge_path == 2
         for n in MERGE_ARRAYS:
             assert same(fast[n], g.array(n)), n
-        g.set_merge_kernel(3); g.merge(thr)                 # four-CTA cluster variant (one role per SM)
-        assert g.counts().merge_path == 3
+        g.set_merge_kernel(4); g.merge(thr)                 # resident kernel compiled with its phase counters
+        assert g.counts().merge_path == 1 and g.merge_profile()["sum_T"] > 0
         for n in MERGE_ARRAYS:
             assert same(fast[n], g.array(n)), n
         g.set_merge_kernel(0); g.merge(thr)
