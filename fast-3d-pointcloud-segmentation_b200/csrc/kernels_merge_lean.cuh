@@ -29,7 +29,7 @@ constexpr int kFastOwners = kFastThreads - 32 * kLeanRoleWarps;     // 928 worke
 constexpr int kLeanWorkerWarps = kFastOwners / 32;                  // 29
 constexpr int kLeanMaxTouched = kFastOwners;
 constexpr int kLeanHash = 2048;
-constexpr int kLeanRing = 4, kLeanSlotVox = 512;
+constexpr int kLeanRing = 4, kLeanSlotVox = 256;
 constexpr unsigned kDeadKey = 0xffffffffu;
 constexpr unsigned long long kDeadKey64 = ~0ull;
 constexpr unsigned kNil16 = 0xffffu;
@@ -52,10 +52,11 @@ struct FastArgs {
 struct FastSmem {
     unsigned long long* key; unsigned* ab;
     float4* stage; unsigned long long* mbar;                        // full[kLeanRing], empty[kLeanRing]
+    float4* priv;                                                   // one private stage per fold warp: regions of <= kLeanSlotVox voxels skip the loader
     unsigned short *te_e, *partner; unsigned* res_w; unsigned char* cls; unsigned long long* te_key;
     unsigned *hkey, *hcnt;
     unsigned long long* wm_key; unsigned *wm_e, *wm_ab;
-    float* newgeo; int* misc; float* inv;
+    float* newgeo; int* misc; float* inv; int* wdirty; unsigned* wmask;
     unsigned *rs, *re; int* n;
     unsigned short *head, *tail, *next, *mark;
     size_t bytes;
@@ -63,12 +64,14 @@ struct FastSmem {
         size_t o = 0;
         auto take = [&](size_t b) { char* p = base + o; o += (b + 15) & ~(size_t)15; return p; };
         stage = (float4*)take((size_t)kLeanRing * kLeanSlotVox * 16); mbar = (unsigned long long*)take(2 * kLeanRing * 8);
+        priv = (float4*)take((size_t)2 * kLeanSlotVox * 16);
         key = (unsigned long long*)take((size_t)E_cap * 8); te_key = (unsigned long long*)take(kLeanMaxTouched * 8); ab = (unsigned*)take((size_t)E_cap * 4);
         te_e = (unsigned short*)take(kLeanMaxTouched * 2); partner = (unsigned short*)take(kLeanMaxTouched * 2);
         res_w = (unsigned*)take(kLeanMaxTouched * 4); cls = (unsigned char*)take(kLeanMaxTouched);
         hkey = (unsigned*)take(kLeanHash * 4); hcnt = (unsigned*)take(kLeanHash * 4);
         wm_key = (unsigned long long*)take(32 * 8); wm_e = (unsigned*)take(32 * 4); wm_ab = (unsigned*)take(32 * 4);
-        newgeo = (float*)take(16 * 4); misc = (int*)take(16 * 4); inv = (float*)take(64 * 4);
+        newgeo = (float*)take(16 * 4); misc = (int*)take(16 * 4); inv = (float*)take(64 * 4); wdirty = (int*)take(32 * 4);
+        wmask = (unsigned*)take((size_t)S * 4);
         rs = (unsigned*)take((size_t)S * 4); re = (unsigned*)take((size_t)S * 4); n = (int*)take((size_t)S * 4);
         head = (unsigned short*)take((size_t)S * 2); tail = (unsigned short*)take((size_t)S * 2); next = (unsigned short*)take((size_t)S * 2);
         mark = (unsigned short*)take((size_t)S * 2);
@@ -96,6 +99,23 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
     } while (!ok);
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// A region of at most kLeanSlotVox voxels: the fold warp copies its runs itself (one 16-byte cp.async per lane and voxel,
+// every run in flight at once) -- one L2 round trip instead of the loader hand-over plus a bulk copy per run.
+__device__ __forceinline__ void lean_fetch_small(const unsigned short* head, const unsigned short* next, const unsigned* rs, const unsigned* re,
+                                                 const float4* __restrict__ pos_data, unsigned b, int nb, float4* dst, int lane) {
+    unsigned run = head[b]; int filled = 0;
+    while (filled < nb && run != kNil16) {
+        const unsigned r0 = rs[run]; const int len = (int)(re[run] - r0);
+        for (int j = lane; j < len; j += 32) cp_async16(smem_addr(dst + filled + j), pos_data + r0 + j);
+        filled += len; run = next[run];
+    }
+    cp_async_wait_all();
+    __syncwarp();
 }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -139,12 +159,70 @@ __device__ __noinline__ float colour_delta(int color_mode, float4 lo, float4 hi)
     return dc;
 }
 
-// delta_g of Clustering::delta_c_g (src/clustering.cpp:126-138), first argument = smaller label
-__device__ __forceinline__ float geom_delta(int geom_mode, float4 n_lo, float4 c_lo, float4 n_hi, float4 c_hi) {
-    const float n1[3] = {n_lo.x, n_lo.y, n_lo.z}, c1[3] = {c_lo.x, c_lo.y, c_lo.z}, n2[3] = {n_hi.x, n_hi.y, n_hi.z}, c2[3] = {c_hi.x, c_hi.y, c_hi.z};
-    float dg = normals_diff(n1, c1, n2, c2);
-    if (geom_mode == 1 && is_convex(n1, c1, n2, c2)) dg *= 0.5f;
+// delta_g of Clustering::delta_c_g (src/clustering.cpp:126-138), first argument = smaller label: normals_diff (:79-96) and
+// is_convex (:53-67) share the unit centroid difference and the two projections (the same float expressions in both).
+__device__ __forceinline__ float geom_delta(int geom_mode, float4 n1, float4 c1, float4 n2, float4 c2) {
+    float C0 = c1.x - c2.x, C1 = c1.y - c2.y, C2 = c1.z - c2.z;
+    const float nrm = sqrtf(sum3(C0 * C0, C1 * C1, C2 * C2));
+    C0 /= nrm; C1 /= nrm; C2 /= nrm;
+    const float x0 = n1.y * n2.z - n1.z * n2.y, x1 = n1.z * n2.x - n1.x * n2.z, x2 = n1.x * n2.y - n1.y * n2.x;
+    const float N1xN2 = sqrtf(sum3(x0 * x0, x1 * x1, x2 * x2));
+    const float cos1 = sum3(n1.x * C0, n1.y * C1, n1.z * C2), cos2 = sum3(n2.x * C0, n2.y * C1, n2.z * C2);
+    float dg = (N1xN2 + fabsf(cos1) + fabsf(cos2)) / 3;
+    if (geom_mode == 1 && cos1 >= cos2) dg *= 0.5f;
     return dg;
+}
+
+// computeCentroid + computePointNormal + flipNormalTowardsViewpoint of Clustering::merge (src/clustering.cpp:411-424) on the nine
+// raw sums held one per lane (lane k < 9: accu[k] of plane_from_accu), spread over the lanes of one warp: every group of
+// independent IEEE divisions (9 by n, 6 by the scale, 3 + 3 normalisations) and the three cross products run once, side by
+// side, instead of back to back in one thread.  Same float expressions in the same association order as plane_from_accu /
+// eigen33_smallest / flip_and_normalize (kernels_vccs.cuh): bit-identical results, valid in every lane.
+__device__ __forceinline__ void plane_from_accu_warp(float acc, int nn, int lane, int pi, int qi, float cen[3], float nv[3], float& curv) {
+    const float fn = (float)nn;
+    const float am = acc / fn;                                                                // accu[k] / n  (k = lane)
+    cen[0] = __shfl_sync(kFull, am, 6); cen[1] = __shfl_sync(kFull, am, 7); cen[2] = __shfl_sync(kFull, am, 8);
+    if (nn < 3) { nv[0] = nv[1] = nv[2] = nanf(""); curv = nv[0]; }
+    else {
+        const float ap = __shfl_sync(kFull, am, 6 + pi), aq = __shfl_sync(kFull, am, 6 + qi);
+        const float cov = am - ap * aq;                                                       // lanes 0..5: xx xy xz yy yz zz
+        float sc = lane < 6 ? fabsf(cov) : 0.0f;
+        sc = fmaxf(sc, __shfl_xor_sync(kFull, sc, 4)); sc = fmaxf(sc, __shfl_xor_sync(kFull, sc, 2)); sc = fmaxf(sc, __shfl_xor_sync(kFull, sc, 1));
+        sc = __shfl_sync(kFull, sc, 0);
+        if (sc <= FLT_MIN) sc = 1.0f;
+        const float smk = cov / sc;
+        const float m00 = __shfl_sync(kFull, smk, 0), m01 = __shfl_sync(kFull, smk, 1), m02 = __shfl_sync(kFull, smk, 2);
+        const float m11 = __shfl_sync(kFull, smk, 3), m12 = __shfl_sync(kFull, smk, 4), m22 = __shfl_sync(kFull, smk, 5);
+        const float mm[9] = {m00, m01, m02, m01, m11, m12, m02, m12, m22};
+        float roots[3];
+        compute_roots(mm, roots);
+        const float ev = roots[0] * sc;
+        const float d00 = m00 - roots[0], d11 = m11 - roots[0], d22 = m22 - roots[0];
+        // lane 0: row0 x row1, lane 1: row0 x row2, lane 2: row1 x row2
+        const bool second = lane == 2, first = lane == 0;
+        const float a0 = second ? m01 : d00, a1 = second ? d11 : m01, a2 = second ? m12 : m02;
+        const float b0 = first ? m01 : m02, b1 = first ? d11 : m12, b2 = first ? m12 : d22;
+        const float v0 = a1 * b2 - a2 * b1, v1 = a2 * b0 - a0 * b2, v2 = a0 * b1 - a1 * b0;
+        const float l = sum3(v0 * v0, v1 * v1, v2 * v2);
+        const float l1 = __shfl_sync(kFull, l, 0), l2 = __shfl_sync(kFull, l, 1), l3 = __shfl_sync(kFull, l, 2);
+        const int which = (l1 >= l2 && l1 >= l3) ? 0 : ((l2 >= l1 && l2 >= l3) ? 1 : 2);
+        const float s = sqrtf(which == 0 ? l1 : (which == 1 ? l2 : l3));
+        const float w0 = __shfl_sync(kFull, v0, which), w1 = __shfl_sync(kFull, v1, which), w2 = __shfl_sync(kFull, v2, which);
+        const float comp = (lane == 0 ? w0 : (lane == 1 ? w1 : w2)) / s;                       // lanes 0..2: one component each
+        nv[0] = __shfl_sync(kFull, comp, 0); nv[1] = __shfl_sync(kFull, comp, 1); nv[2] = __shfl_sync(kFull, comp, 2);
+        const float c0 = __shfl_sync(kFull, cov, 0), c3 = __shfl_sync(kFull, cov, 3), c5 = __shfl_sync(kFull, cov, 5);
+        const float eig_sum = c0 + c3 + c5;
+        curv = (eig_sum != 0) ? fabsf(ev / eig_sum) : 0.0f;
+    }
+    // flipNormalTowardsViewpoint(p, 0,0,0, n) ; n[3]=0 ; normalize()
+    const float cos_theta = sum4((0.0f - cen[0]) * nv[0], (0.0f - cen[1]) * nv[1], (0.0f - cen[2]) * nv[2], 0.0f);
+    if (cos_theta < 0) { nv[0] *= -1; nv[1] *= -1; nv[2] *= -1; }
+    const float z = sum4(nv[0] * nv[0], nv[1] * nv[1], nv[2] * nv[2], 0.0f);
+    if (z > 0.0f) {
+        const float sz = sqrtf(z);
+        const float comp = (lane == 0 ? nv[0] : (lane == 1 ? nv[1] : nv[2])) / sz;
+        nv[0] = __shfl_sync(kFull, comp, 0); nv[1] = __shfl_sync(kFull, comp, 1); nv[2] = __shfl_sync(kFull, comp, 2);
+    }
 }
 
 struct FastHead { unsigned hi, lo, e, ab; };
@@ -161,7 +239,8 @@ __device__ __forceinline__ FastHead lean_head(const FastSmem& sm, int lane) {
 }
 
 enum { FC_KEEP = 0, FC_FRONT = 1, FC_BACK = 2, FC_DUP = 3 };
-enum { BAR_W1 = 1, BAR_WB = 2, BAR_F = 3, BAR_W4 = 4 };
+enum { BAR_W1 = 1, BAR_WB = 2, BAR_F = 3, BAR_W4 = 4, BAR_G = 5 };
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 #define LPROF_DECL unsigned pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned t_prev = PROF ? (unsigned)clock() : 0u
 #define LPROF(cond, i) do { if (PROF && (cond)) { const unsigned t_now = (unsigned)clock(); pc[i] += t_now - t_prev; t_prev = t_now; } } while (0)
@@ -182,8 +261,10 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
         sm.rs[s] = A.run_start[s]; sm.re[s] = A.run_end[s]; sm.n[s] = R.n[s];
         const int h = R.head[s], t = R.tail[s], nx = R.next_run[s];
         sm.head[s] = (unsigned short)(h < 0 ? kNil16 : (unsigned)h); sm.tail[s] = (unsigned short)(t < 0 ? kNil16 : (unsigned)t);
-        sm.next[s] = (unsigned short)(nx < 0 ? kNil16 : (unsigned)nx); sm.mark[s] = (unsigned short)kNil16;
+        sm.next[s] = (unsigned short)(nx < 0 ? kNil16 : (unsigned)nx); sm.mark[s] = (unsigned short)kNil16; sm.wmask[s] = 0u;
     }
+    if (tid < 32) sm.wdirty[tid] = 1;
+    __syncthreads();
     for (unsigned e = tid; e < A.E_cap; e += kFastThreads) {
         unsigned long long k = kDeadKey64; unsigned ab = kDeadKey;
         if (e < nE && A.E.stamp[e] != kDeadStamp) {
@@ -191,6 +272,8 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             const unsigned hi = isnan(w) ? 0x7f800000u : __float_as_uint(w);
             k = ((unsigned long long)hi << 32) | ((unsigned)(int)A.E.stamp[e] ^ 0x80000000u);
             ab = (A.E.a[e] << 16) | A.E.b[e];
+            const unsigned wbit = 1u << ((e % kFastOwners) >> 5);             // the worker warp that owns this slot
+            atomicOr(&sm.wmask[ab >> 16], wbit); atomicOr(&sm.wmask[ab & 0xffffu], wbit);
         }
         sm.key[e] = k; sm.ab[e] = ab;
     }
@@ -224,12 +307,14 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                                  : (lane < 8 ? reinterpret_cast<const float*>(R.accu1 + a) + (lane - 4) : reinterpret_cast<const float*>(R.accu2 + a));
                 acc = __ldcg(src);
             }
-            for (int done = 0; done < nb; done += kLeanSlotVox, ++chunk) {
+            const bool direct = nb <= kLeanSlotVox;
+            if (direct) lean_fetch_small(sm.head, sm.next, sm.rs, sm.re, A.pos_data, b, nb, sm.priv, lane);
+            for (int done = 0; done < nb; done += kLeanSlotVox) {
                 const int cn = min(nb - done, kLeanSlotVox);
                 const unsigned slot = chunk & (kLeanRing - 1);
-                mbar_wait(mbar_full + 8u * slot, (chunk / kLeanRing) & 1u);
+                if (!direct) mbar_wait(mbar_full + 8u * slot, (chunk / kLeanRing) & 1u);
                 LPROF(lane == 0, 0);
-                const float* sf = stage_f + slot * (kLeanSlotVox * 4);
+                const float* sf = direct ? reinterpret_cast<const float*>(sm.priv) : stage_f + slot * (kLeanSlotVox * 4);
                 int j = 0;
                 for (; j + 8 <= cn; j += 8) {
 #pragma unroll
@@ -244,33 +329,28 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                     const float q = prod ? sf[4 * j + qi] : 1.0f;
                     acc = acc + p * q;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive_local(mbar_empty + 8u * slot);
+                if (!direct) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_local(mbar_empty + 8u * slot);
+                    ++chunk;
+                }
             }
             LPROF(lane == 0, 1);
-            float ac[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) ac[k] = __shfl_sync(kFull, acc, k);
-            float cx = 0, cy = 0, cz = 0, curv = 0; float nv[3] = {0, 0, 0};
+            float cen[3], nv[3], curv;
+            plane_from_accu_warp(acc, na + nb, lane, pi, qi, cen, nv, curv);                   // :411-420, spread over the lanes
+            const float cx = cen[0], cy = cen[1], cz = cen[2];
             if (lane == 0) {
-                const int nn = na + nb;
-                const float fn = (float)nn;
-                cx = ac[6] / fn; cy = ac[7] / fn; cz = ac[8] / fn;                              // computeCentroid (:411-413)
-                if (nn < 3) { nv[0] = nv[1] = nv[2] = nanf(""); curv = nv[0]; }
-                else plane_from_accu(ac, nn, nv, curv);                                         // computePointNormal (:415-417)
-                flip_and_normalize(cx, cy, cz, nv);                                             // :418-420
                 sm.newgeo[3] = cx; sm.newgeo[4] = cy; sm.newgeo[5] = cz;
                 sm.newgeo[6] = nv[0]; sm.newgeo[7] = nv[1]; sm.newgeo[8] = nv[2];
             }
             __syncwarp();
             LPROF(lane == 0, 2);
             named_bar(BAR_F, kFastThreads);                                                     // F: workers read x's old state before this
-            if (lane == 0) {
-                R.centroid[a] = make_float4(cx, cy, cz, 0.0f);
-                R.normal[a] = make_float4(nv[0], nv[1], nv[2], curv);
-                R.accu0[a] = make_float4(ac[0], ac[1], ac[2], ac[3]);
-                R.accu1[a] = make_float4(ac[4], ac[5], ac[6], ac[7]);
-                R.accu2[a] = make_float4(ac[8], 0.0f, 0.0f, 0.0f);
+            if (lane == 0) { R.centroid[a] = make_float4(cx, cy, cz, 0.0f); R.normal[a] = make_float4(nv[0], nv[1], nv[2], curv); }
+            if (lane < 9) {                                                                     // every lane stores its own raw sum
+                float* dst = lane < 4 ? reinterpret_cast<float*>(R.accu0 + a) + lane
+                           : (lane < 8 ? reinterpret_cast<float*>(R.accu1 + a) + (lane - 4) : reinterpret_cast<float*>(R.accu2 + a));
+                *dst = acc;
             }
         }
         LPROF_STORE(lane == 0, 16, 4);
@@ -290,17 +370,33 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
             const int na = sm.n[a], nb = sm.n[b];
-            float m = 0.0f;
-            if (lane < 3) m = __ldcg(reinterpret_cast<const float*>(R.mean + a) + 1 + lane);
-            const float4 guess = __ldcg(R.cvec + (na >= nb ? a : b));                          // the workers' guess for the new colour vector
+            float m = 0.0f, mb_ = 0.0f;
+            if (lane < 3) { m = __ldcg(reinterpret_cast<const float*>(R.mean + a) + 1 + lane); mb_ = __ldcg(reinterpret_cast<const float*>(R.mean + b) + 1 + lane); }
+            // GUESS of the merged region's colour vector for the workers' speculative colour deltas: the Lab lattice point of the
+            // size-weighted mean of the two running means.  It differs from the exact continued running mean by rounding noise
+            // only, and OpenCV's LUT quantises its input to 9 bits per channel, so the guess is wrong about once in 10^3 merges
+            // (checked against the exact result below; a wrong guess costs a re-evaluation, never a wrong result).
+            float guess[3];
+            {
+                const float gm = (m * (float)na + mb_ * (float)nb) / (float)(na + nb);
+                const float gr = __shfl_sync(kFull, gm, 0), gg = __shfl_sync(kFull, gm, 1), gb = __shfl_sync(kFull, gm, 2);
+                if (ep.color_mode == 0) rgb2lab_lanes(ep.lab_lut, gr, gg, gb, lane, guess);
+                else { guess[0] = gr; guess[1] = gg; guess[2] = gb; }
+                if (lane == 0) { sm.newgeo[10] = guess[0]; sm.newgeo[11] = guess[1]; sm.newgeo[12] = guess[2]; }
+                __syncwarp();
+                bar_arrive(BAR_G, 32 + kFastOwners);                                            // G: guess published
+            }
+            LPROF(lane == 0, 3);
             const float cnt0 = (float)na;
-            for (int done = 0; done < nb; done += kLeanSlotVox, ++chunk) {
+            const bool direct = nb <= kLeanSlotVox;
+            if (direct) lean_fetch_small(sm.head, sm.next, sm.rs, sm.re, A.pos_data, b, nb, sm.priv + kLeanSlotVox, lane);
+            for (int done = 0; done < nb; done += kLeanSlotVox) {
                 const int cn = min(nb - done, kLeanSlotVox);
                 const unsigned slot = chunk & (kLeanRing - 1);
                 float inv_next = 1 / (cnt0 + (float)(done + lane + 1));
-                mbar_wait(mbar_full + 8u * slot, (chunk / kLeanRing) & 1u);
+                if (!direct) mbar_wait(mbar_full + 8u * slot, (chunk / kLeanRing) & 1u);
                 LPROF(lane == 0, 0);
-                const unsigned* su = stage_u + slot * (kLeanSlotVox * 4);
+                const unsigned* su = direct ? reinterpret_cast<const unsigned*>(sm.priv + kLeanSlotVox) : stage_u + slot * (kLeanSlotVox * 4);
                 for (int base = 0, g = 0; base < cn; base += 32, g ^= 1) {
                     inv_s[g * 32 + lane] = inv_next;                       // 1/k of the next 32 voxels, one division per lane
                     inv_next = 1 / (cnt0 + (float)(done + base + 32 + lane + 1));
@@ -314,8 +410,11 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                         m = m + iv[j] * (x - m);
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive_local(mbar_empty + 8u * slot);
+                if (!direct) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_local(mbar_empty + 8u * slot);
+                    ++chunk;
+                }
             }
             LPROF(lane == 0, 1);
             const float mr = __shfl_sync(kFull, m, 0), mg = __shfl_sync(kFull, m, 1), mb = __shfl_sync(kFull, m, 2);
@@ -324,8 +423,8 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             else { cv[0] = mr; cv[1] = mg; cv[2] = mb; }
             if (lane == 0) {
                 sm.newgeo[0] = cv[0]; sm.newgeo[1] = cv[1]; sm.newgeo[2] = cv[2];
-                newgeo_i[9] = (__float_as_uint(cv[0]) == __float_as_uint(guess.x) && __float_as_uint(cv[1]) == __float_as_uint(guess.y) &&
-                               __float_as_uint(cv[2]) == __float_as_uint(guess.z)) ? 1 : 0;
+                newgeo_i[9] = (__float_as_uint(cv[0]) == __float_as_uint(guess[0]) && __float_as_uint(cv[1]) == __float_as_uint(guess[1]) &&
+                               __float_as_uint(cv[2]) == __float_as_uint(guess[2])) ? 1 : 0;
             }
             __syncwarp();
             LPROF(lane == 0, 2);
@@ -348,7 +447,9 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
             const int na = sm.n[a], nb = sm.n[b];
-            if (lane == 0) {
+            if (nb <= kLeanSlotVox) {
+                // the fold warps fetch a small region themselves (lean_fetch_small)
+            } else if (lane == 0) {
                 unsigned run = sm.head[b];
                 unsigned pos = run != kNil16 ? sm.rs[run] : 0u;
                 for (int done = 0; done < nb; done += kLeanSlotVox, ++chunk) {
@@ -375,6 +476,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             if (lane == 0) {
                 sm.next[sm.tail[a]] = sm.head[b]; sm.tail[a] = sm.tail[b];
                 sm.n[a] = na + nb; sm.n[b] = 0;
+                sm.wmask[a] |= sm.wmask[b];                    // b's edges now name a (every worker read the masks before F)
             }
         }
     } else {
@@ -386,18 +488,20 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
         unsigned my_hs = kNil16;                                                               // tie-hash slot to clear after the next S1
         unsigned n_merges = 0;
         LPROF_DECL;
+        unsigned long long cls_cyc[3] = {0, 0, 0}; unsigned cls_cnt[3] = {0, 0, 0}; unsigned t_top = 0;   // PROF: merges by touched-edge class
 #define WPROF(i) LPROF(wtid == 0, i)
         while (true) {
-            // ---- A: local minimum over my slots, warp minimum, publish ----
-            unsigned long long best = sm.key[wtid]; int bj = 0;
+            if (PROF) t_top = (unsigned)clock();
+            // ---- A: warps that hold a re-weighted (or removed) edge rescan their slots and republish their minimum ----
+            if (sm.wdirty[ww]) {
+                unsigned long long best = sm.key[wtid]; int bj = 0;
 #pragma unroll
-            for (int j = 1; j < SLOTS; ++j) { const unsigned long long k = sm.key[j * kFastOwners + wtid]; if (k < best) { best = k; bj = j; } }
-            {
+                for (int j = 1; j < SLOTS; ++j) { const unsigned long long k = sm.key[j * kFastOwners + wtid]; if (k < best) { best = k; bj = j; } }
                 const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
                 const unsigned m_hi = __reduce_min_sync(kFull, hi);
                 const unsigned m_lo = __reduce_min_sync(kFull, hi == m_hi ? lo : kDeadKey);
                 const int win = __ffs(__ballot_sync(kFull, hi == m_hi && lo == m_lo)) - 1;
-                if (lane == win) { const unsigned e = (unsigned)(bj * kFastOwners + wtid); sm.wm_key[ww] = best; sm.wm_e[ww] = e; sm.wm_ab[ww] = sm.ab[e]; }
+                if (lane == win) { const unsigned e = (unsigned)(bj * kFastOwners + wtid); sm.wm_key[ww] = best; sm.wm_e[ww] = e; sm.wm_ab[ww] = sm.ab[e]; sm.wdirty[ww] = 0; }
             }
             WPROF(0);
             __syncthreads();                                                                   // S1
@@ -405,12 +509,11 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             if (my_hs != kNil16) { sm.hkey[my_hs] = kDeadKey; sm.hcnt[my_hs] = 0u; my_hs = kNil16; }
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;   // strict <, src/clustering.cpp:388-389
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
-            const int na_ = sm.n[a], nb_ = sm.n[b];
             const int counter = sm.misc[FM_COUNTER];
             WPROF(1);
             // ---- B: the head edge leaves the map; edges incident to a or b -> touched list ----
-            if (hd.e % kFastOwners == (unsigned)wtid) { sm.key[hd.e] = kDeadKey64; sm.ab[hd.e] = kDeadKey; }
-            {
+            if (hd.e % kFastOwners == (unsigned)wtid) { sm.key[hd.e] = kDeadKey64; sm.ab[hd.e] = kDeadKey; sm.wdirty[ww] = 1; }
+            if (((sm.wmask[a] | sm.wmask[b]) >> ww) & 1u) {                                    // warp-uniform: does this warp hold an incident edge?
                 const unsigned aa = a * 0x10001u, bb = b * 0x10001u;
                 unsigned hits = 0;
 #pragma unroll
@@ -444,14 +547,12 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             const bool wide = T > 32;                                                          // more than one warp of touched edges
             const bool mine = !overflow && wtid < T;
             // ---- C: duplicates (a,x)/(b,x) through a per-region mark; x's geometry; speculative colour deltas ----
-            // Colour deltas are memoised per edge and speculated: while the fold runs, the edges that cannot reuse their stored
-            // delta get CIEDE2000 against a GUESS of the merged region's colour vector (that of the larger side; the Lab lattice
-            // quantises the mean colour, so absorbing a small region usually leaves it bit-identical).  A wrong guess re-evaluates.
-            const bool big_is_a = na_ >= nb_;
-            const bool speculate = max(na_, nb_) >= 4 * min(na_, nb_);
+            // Colour deltas are memoised per edge and speculated: while the fold runs, the edges whose stored delta does not
+            // fit the GUESS of the merged region's colour vector (warp 1: Lab lattice point of the size-weighted mean) get
+            // CIEDE2000 against the guess.  A wrong guess (about 1 merge in 10^3) re-evaluates after the fold.
             unsigned e = 0, x = 0; bool side_a = false; unsigned long long okey = kDeadKey64;
             bool live = false, need = false;
-            float dc = 0.0f; float4 xcv, c4, n4, guess;
+            float dc = 0.0f; float4 xcv, c4, n4, ocv;
             if (ww == 0 || wide) {
                 if (mine) {
                     e = sm.te_e[wtid]; okey = sm.key[e]; sm.te_key[wtid] = okey;
@@ -461,18 +562,23 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                     const unsigned short old = atomicCAS(&sm.mark[x], (unsigned short)kNil16, (unsigned short)wtid);
                     if (old != (unsigned short)kNil16) { sm.partner[wtid] = old; sm.partner[old] = (unsigned short)wtid; }
                     xcv = __ldcg(R.cvec + x); c4 = __ldcg(R.centroid + x); n4 = __ldcg(R.normal + x); dc = __ldcg(A.E.dc + e);
-                    guess = __ldcg(R.cvec + (big_is_a ? a : b));
+                    ocv = __ldcg(R.cvec + (side_a ? a : b));                                   // the colour vector the stored delta was computed with
                 }
                 if (wide) named_bar(BAR_WB, kFastOwners); else __syncwarp();                   // WB1
-                if (mine) {
-                    const unsigned q = sm.partner[wtid];
-                    const bool dup = q != kNil16 && sm.te_key[q] < okey;                       // the earlier of (a,x), (b,x) survives
-                    sm.mark[x] = (unsigned short)kNil16;
-                    live = !dup;
-                    const bool reuse = side_a ? big_is_a : (!big_is_a && ((b < x) == (a < x)));   // same ends' colours, same argument order
-                    need = live && !reuse;
-                    if (speculate && need) dc = a < x ? colour_delta(ep.color_mode, guess, xcv) : colour_delta(ep.color_mode, xcv, guess);
-                }
+            }
+            named_bar(BAR_G, 32 + kFastOwners);                                                // G: the guess of a's new colour vector
+            const float4 guess = make_float4(sm.newgeo[10], sm.newgeo[11], sm.newgeo[12], 0.0f);
+            if (mine && (ww == 0 || wide)) {
+                const unsigned q = sm.partner[wtid];
+                const bool dup = q != kNil16 && sm.te_key[q] < okey;                           // the earlier of (a,x), (b,x) survives
+                sm.mark[x] = (unsigned short)kNil16;
+                live = !dup;
+                // the stored delta stays valid when the end that changes keeps its colour vector and the argument order
+                const bool same_cv = __float_as_uint(ocv.x) == __float_as_uint(guess.x) && __float_as_uint(ocv.y) == __float_as_uint(guess.y) &&
+                                     __float_as_uint(ocv.z) == __float_as_uint(guess.z);
+                const bool reuse = same_cv && (side_a || ((b < x) == (a < x)));
+                need = live && !reuse;
+                if (need) dc = a < x ? colour_delta(ep.color_mode, guess, xcv) : colour_delta(ep.color_mode, xcv, guess);
             }
             WPROF(3);
             named_bar(BAR_F, kFastThreads);                                                    // F: region a's new colour vector / centroid / normal
@@ -482,12 +588,12 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                 unsigned wbits = kDeadKey, nab = kDeadKey; int cls = FC_DUP; unsigned hs = kNil16;
                 const bool hit = newgeo_i[9] != 0;
                 if (mine) {
-                    const bool redo = hit ? (need && !speculate) : live;                       // wrong guess: every survivor; no guess made: the ones that cannot reuse
+                    const bool redo = !hit && live;                                            // wrong guess (rare): every survivor re-evaluates
                     if (redo) {
                         const float4 acv = make_float4(sm.newgeo[0], sm.newgeo[1], sm.newgeo[2], 0.0f);
                         dc = a < x ? colour_delta(ep.color_mode, acv, xcv) : colour_delta(ep.color_mode, xcv, acv);
                     }
-                    if (PROF && (redo || (speculate && need))) atomicAdd(&sm.misc[FM_EVALS], (redo ? 1 : 0) + ((speculate && need) ? 1 : 0));
+                    if (PROF && (redo || need)) atomicAdd(&sm.misc[FM_EVALS], (redo ? 1 : 0) + (need ? 1 : 0));
                     if (live) {
                         const float4 ace = make_float4(sm.newgeo[3], sm.newgeo[4], sm.newgeo[5], 0.0f), anr = make_float4(sm.newgeo[6], sm.newgeo[7], sm.newgeo[8], 0.0f);
                         const bool a_first = a < x;
@@ -529,6 +635,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                     }
                     sm.key[e] = live ? ((unsigned long long)wbits << 32) | lo : kDeadKey64;
                     sm.ab[e] = nab;
+                    sm.wdirty[(e % kFastOwners) >> 5] = 1;
                 }
             }
             if (wtid == 0) {
@@ -545,10 +652,12 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             WPROF(5);
             named_bar(BAR_W4, kFastOwners);                                                    // W4: new keys written
             WPROF(6);
+            if (PROF && wtid == 0) { const int c_ = T <= 32 ? 0 : (T <= 128 ? 1 : 2); cls_cyc[c_] += (unsigned)clock() - t_top; cls_cnt[c_]++; }
             ++n_merges;
         }
 #undef WPROF
         LPROF_STORE(wtid == 0, 0, 8);
+        if (PROF && wtid == 0) for (int i = 0; i < 3; ++i) { A.ctl->phase_cycles[8 + i] = cls_cyc[i]; A.ctl->phase_cycles[28 + i] = cls_cnt[i]; }
         if (wtid == 0) sm.misc[FM_NMERGES] = (int)n_merges;
     }
 

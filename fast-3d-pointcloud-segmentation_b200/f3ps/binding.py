@@ -262,6 +262,8 @@ class Segmenter:
             return {"worker": dict(zip(["scan_publish", "wait_s1_head", "incidence_w1", "dedupe_spec_ciede", "wait_fold", "weights_stamps", "wait_w4"], v[0:7])),
                     "mean": dict(zip(["wait_voxels", "fold", "lab_publish", "wait_s1"], v[12:16])),
                     "cov": dict(zip(["wait_voxels", "fold", "eigen_publish", "wait_s1"], v[16:20])),
+                    "by_touched": {k: {"merges": v[28 + i], "cycles_per_merge": (v[8 + i] // v[28 + i]) if v[28 + i] else 0}
+                                   for i, k in enumerate(["T<=32", "T<=128", "T>128"])},
                     "guess_misses": v[24], "ciede_evals": v[25], "sum_T": v[27]}
         return dict(zip(["argmin", "fold", "order", "delta", "stamps", "wait_scan", "sum_T", "fold_tail"], v[:8]))
 

@@ -104,3 +104,49 @@ def write_pcd_binary(path, pts):
     with open(path, "wb") as f:
         f.write(hdr.encode("ascii"))
         f.write(rec.tobytes())
+
+
+def _lzf_compress_literal(data):
+    """A valid LZF stream that uses literal runs only (no back-references): what a decoder must accept, no more."""
+    out = bytearray()
+    for i in range(0, len(data), 32):
+        chunk = data[i:i + 32]
+        out.append(len(chunk) - 1)
+        out += chunk
+    return bytes(out)
+
+
+def write_pcd(path, pts, label=None, mode="binary", rgb_as_float=False):
+    """Test / tooling writer: FIELDS x y z rgba|rgb [label] in DATA ascii | binary | binary_compressed.
+    rgb_as_float: declare the colour field as `rgb`, TYPE F (PCL's PointXYZRGB); in ascii it is then printed the way
+    PCL >= 1.8 prints it, as the uint32 reinterpretation of the packed colour."""
+    n = len(pts)
+    cname, ctype = ("rgb", "F") if rgb_as_float else ("rgba", "U")
+    names = ["x", "y", "z", cname] + (["label"] if label is not None else [])
+    types = ["F", "F", "F", ctype] + (["U"] if label is not None else [])
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS %s\nSIZE %s\nTYPE %s\nCOUNT %s\n"
+           "WIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA %s\n" % (
+               " ".join(names), " ".join(["4"] * len(names)), " ".join(types), " ".join(["1"] * len(names)), n, n, mode))
+    cols = [np.ascontiguousarray(pts[k], "<f4") for k in ("x", "y", "z")] + [np.ascontiguousarray(pts["rgba"], "<u4")]
+    if label is not None:
+        cols.append(np.ascontiguousarray(label, "<u4"))
+    with open(path, "wb") as f:
+        f.write(hdr.encode("ascii"))
+        if mode == "ascii":
+            lines = []
+            for i in range(n):
+                t = ["nan" if np.isnan(c[i]) else repr(float(c[i])) for c in cols[:3]] + [str(int(c[i])) for c in cols[3:]]
+                lines.append(" ".join(t))
+            f.write(("\n".join(lines) + "\n").encode("ascii"))
+        elif mode == "binary":
+            rec = np.zeros(n, dtype=np.dtype([(nm, "<u4") for nm in names]))
+            for nm, c in zip(names, cols):
+                rec[nm] = c.view("<u4")
+            f.write(rec.tobytes())
+        elif mode == "binary_compressed":
+            soa = b"".join(c.tobytes() for c in cols)
+            comp = _lzf_compress_literal(soa)
+            f.write(struct.pack("<II", len(comp), len(soa)))
+            f.write(comp)
+        else:
+            raise ValueError(mode)

@@ -1,7 +1,10 @@
 #include "pcd_io.h"
 
+#include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <limits>
 #include <sstream>
@@ -65,6 +68,7 @@ int loadPCDFile(const std::string& path, pcl::PointCloud<pcl::PointXYZRGBL>& clo
     }
     if (!npts) npts = width * height;
     if (fields.empty() || mode.empty()) return -1;
+    if (npts > raw.size()) return -1;                      // every encoding spends at least one byte per point
     size_t rec = 0;
     for (auto& fd : fields) { fd.offset = rec; rec += (size_t)fd.size * fd.count; }
     int ix = -1, iy = -1, iz = -1, ic = -1, il = -1;
@@ -81,9 +85,16 @@ int loadPCDFile(const std::string& path, pcl::PointCloud<pcl::PointXYZRGBL>& clo
             pcl::PointXYZRGBL& p = cloud.points[i];
             for (size_t k = 0; k < fields.size(); ++k) for (int c = 0; c < fields[k].count; ++c) {
                 std::string tok; ss >> tok;
-                double v = (tok == "nan" || tok == "NaN") ? std::numeric_limits<double>::quiet_NaN() : atof(tok.c_str());
+                const bool is_nan = tok == "nan" || tok == "NaN" || tok == "-nan";
+                double v = is_nan ? std::numeric_limits<double>::quiet_NaN() : atof(tok.c_str());
                 if ((int)k == ix) p.x = (float)v; else if ((int)k == iy) p.y = (float)v; else if ((int)k == iz) p.z = (float)v;
-                else if ((int)k == ic) { if (fields[k].type == 'F') { float fv = (float)v; memcpy(&p.rgba, &fv, 4); } else p.rgba = (uint32_t)v; }
+                else if ((int)k == ic) {
+                    // PCL >= 1.8 writes an ascii rgb field of TYPE F as the uint32 reinterpretation of the packed colour
+                    // (e.g. 4285098345); older files carry the float's decimal form
+                    const bool as_int = !is_nan && tok.find_first_of(".eEnN") == std::string::npos;
+                    if (fields[k].type == 'F' && !as_int) { float fv = (float)v; memcpy(&p.rgba, &fv, 4); }
+                    else p.rgba = (uint32_t)strtoul(tok.c_str(), nullptr, 10);
+                }
                 else if ((int)k == il) p.label = (uint32_t)v;
             }
         }

@@ -176,11 +176,11 @@ def test_float_libm_model_matches_glibc_mostly(oracle_mod):
     assert np.max(np.abs(ours.astype(np.float64) - glibc.astype(np.float64)) / ulp) <= 1.0
 
 
-@pytest.mark.skipif(not os.path.exists("/root/reference/pcd/milk_cartoon_all_small_clorox.pcd"), reason="reference checkout not present")
 def test_bundled_frame_config1(oracle_mod):
-    """C1: the reference's sample cloud at defaults; sizes recorded by the survey probes."""
+    """C1: the reference's sample cloud (tests/fixtures/, a copy of /root/reference/pcd/) at defaults; sizes recorded by
+    the survey probes."""
     from f3ps import pcd
-    pts, label, hdr = pcd.read_pcd("/root/reference/pcd/milk_cartoon_all_small_clorox.pcd")
+    pts, label, hdr = pcd.read_pcd(os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures", "milk_cartoon_all_small_clorox.pcd"))
     assert len(pts) == 307200 and int(np.isfinite(pts["z"]).sum()) == 241407
     o = run_oracle(oracle_mod, pts, dict(color_mode=0, geom_mode=1, merge_mode=1), 0.2, merge_impl=1)
     assert len(o.array("keys")) == 34211 and int(o.scalars()["depth"]) == 8

@@ -38,6 +38,7 @@ def main():
             p = g.merge_profile(); M = max(1, c.n_merges)
             for role in ("worker", "mean", "cov"):
                 print("   %-6s cycles/merge:" % role, {k: round(v / M) for k, v in p[role].items()})
+            print("   by touched-edge class:", p["by_touched"])
             print("   guess_misses %d  ciede_evals %d  sum_T %d  fold_steps %d" % (p["guess_misses"], p["ciede_evals"], p["sum_T"], c.fold_steps))
     g.set_merge_kernel(0)
     for i in range(3):
