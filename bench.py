@@ -37,7 +37,10 @@ sys.path.insert(0, os.path.join(ROOT, "fast-3d-pointcloud-segmentation_b200"))
 WORKLOAD = "C2: synthetic 640x480 RGB-D frame (307200 points), --CVX --AL -t 0.2"
 FLAGS = dict(color_mode=0, geom_mode=1, merge_mode=1, lam=0.5, bins=500)
 THRESHOLD = 0.2
-N_POOL = 8                     # distinct synthetic frames (replicated into the in-flight slots)
+# BASELINE config 3: the -d sweep, frames from the same generator with seeds 30000 + i, --EQ 200 -t 0.2
+C3_WORKLOAD = "C3: synthetic VGA directory sweep (-d), frames seeded 30000+i, --EQ 200 -t 0.2"
+C3_FLAGS = dict(color_mode=0, geom_mode=0, merge_mode=2, lam=0.5, bins=200)
+N_POOL = 32                    # distinct synthetic frames per rank (replicated into the in-flight slots)
 L2_FLUSH_BYTES = 512 << 20     # > 126 MB L2
 
 
@@ -49,11 +52,14 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+TRAFFIC_FILE = os.path.join("profiles", "r02_traffic.json")
+
+
 def load_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from this round's ncu capture of the
+    kernel the run dispatches (tools/k7_ncu.sh writes the report, tools/ncu_summary.py the JSON); None when absent."""
     try:
-        with open(p) as f:
+        with open(os.path.join(ROOT, TRAFFIC_FILE)) as f:
             return int(json.load(f)["traffic_bytes_per_launch"])
     except Exception:
         return None
@@ -107,9 +113,16 @@ class ClockSampler:
         return out
 
 
-def make_frames(rank, count):
+def make_frames(rank, count, base_seed=20020):
     from f3ps import synth
-    return [synth.make_frame(seed=20020 + rank * 1000 + i) for i in range(count)]
+    return [synth.make_frame(seed=base_seed + rank * 1000 + i) for i in range(count)]
+
+
+def shared_config(workload):
+    """The `config` both arms print (the driver compares the two dicts): what is measured, nothing about how."""
+    flags = {"c2": "--CVX --AL -t 0.2", "c3": "--EQ 200 -t 0.2", "c5": "-v 0.01 -s 0.1 --CVX --AL -t 0.2"}[workload]
+    name = {"c2": WORKLOAD, "c3": C3_WORKLOAD, "c5": C5_WORKLOAD}[workload]
+    return {"workload": name, "flags": flags, "points_per_frame": 307200 if workload != "c5" else None}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -124,12 +137,14 @@ def run_reference(args):
     oracle_py.build()
     from concurrent.futures import ProcessPoolExecutor
     cores = os.cpu_count() or 1
-    frames = make_frames(0, 1)
+    c3 = args.workload == "c3"
+    flags = C3_FLAGS if c3 else FLAGS
+    frames = make_frames(0, 1, 30000 if c3 else 20020)
     npts = len(frames[0])
     with ProcessPoolExecutor(max_workers=cores) as ex:
         def step():
             t0 = time.perf_counter()
-            list(ex.map(_oracle_frame, [(frames[0], 1)] * cores))
+            list(ex.map(_oracle_frame, [(frames[0], 1, flags)] * cores))
             return time.perf_counter() - t0
         for _ in range(args.warmup):
             step()
@@ -137,11 +152,11 @@ def run_reference(args):
     total = sum(times)
     value = cores * npts * args.steps / total / 1e6
     # the reference AS WRITTEN (std::multimap rebuilt per merge, contains() by value, src/clustering.cpp:431-468, 497-506): one frame, one core
-    t_lit, _ = _oracle_frame((frames[0], 0))
-    line = {"impl": "reference", "metric": "Mpoints/s end-to-end segmentation", "value": value, "unit": "Mpoints/s",
+    t_lit, _ = _oracle_frame((frames[0], 0, flags))
+    line = {"impl": "reference", "impl_detail": "CPU oracle port (the reference needs PCL/OpenCV C++ and cannot be built here), stamp-based merge = same results as the literal std::multimap replay, ~30x faster", "metric": "Mpoints/s end-to-end segmentation", "value": value, "unit": "Mpoints/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": cores},
+            "config": shared_config(args.workload if args.workload in ("c2", "c3") else "c2"), "run": {"frames_per_step": cores},
             "cpu_baseline": {"value": value, "unit": "Mpoints/s", "cores": cores, "kind": "port",
                              "sample": "%d VGA frames per step, one per core, CPU oracle with the stamp-based merge "
                                        "(identical results to the literal std::multimap replay, which is ~30x slower)" % cores,
@@ -154,7 +169,7 @@ def run_reference(args):
 
 
 def _oracle_frame(arg):
-    pts, merge_impl = arg
+    pts, merge_impl, FLAGS = arg
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
     o = oracle_py.Oracle()
@@ -166,13 +181,13 @@ def _oracle_frame(arg):
     return time.perf_counter() - t0, o.array("stage_ms")
 
 
-def cpu_baseline(frame):
+def cpu_baseline(frame, FLAGS=FLAGS):
     """Rank 0, N=1: the literal CPU oracle (std::multimap replay, as the reference is written) on one frame."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
     oracle_py.build()
-    t_lit, st_lit = _oracle_frame((frame, 0))
-    t_fix, st_fix = _oracle_frame((frame, 1))
+    t_lit, st_lit = _oracle_frame((frame, 0, FLAGS))
+    t_fix, st_fix = _oracle_frame((frame, 1, FLAGS))
     n = len(frame)
     return {"value": n / t_lit / 1e6, "unit": "Mpoints/s", "cores": 1, "kind": "port",
             "sample": "1 VGA frame (307200 points), single thread, literal std::multimap merge replay: %.2f s" % t_lit,
@@ -183,38 +198,29 @@ def cpu_baseline(frame):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # before the CUDA context exists (see f3ps_create)
+def sweep_leg(args, env, workload, steps):
+    """One measured leg of the frame sweep (C2 or C3): resident throughput, host-buffer throughput, single-frame latency."""
     import torch
-    import torch.distributed as dist
     import f3ps
     from f3ps import sweep
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the f3ps path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
+    dist, world, rank, local_rank, dev = env
+    flags = C3_FLAGS if workload == "c3" else FLAGS
     F = max(1, args.inflight)                 # frames in flight per GPU
     R = max(1, args.rounds)                   # frames each handle processes back to back inside one step
-    frames = make_frames(rank, N_POOL)
+    n_distinct = min(N_POOL, F)
+    frames = make_frames(rank, n_distinct, 30000 if workload == "c3" else 20020)
     npts = len(frames[0])
     # one resident copy per in-flight slot: a step streams F * 9.8 MB of distinct input (> L2 for F >= 13)
-    d_frames = [torch.from_numpy(frames[i % N_POOL].view(np.uint8).reshape(-1, 32).copy()).to(dev) for i in range(F)]
-    pinned = [torch.from_numpy(frames[i % N_POOL].view(np.uint8).reshape(-1, 32).copy()).pin_memory() for i in range(F)]
+    d_frames = [torch.from_numpy(frames[i % n_distinct].view(np.uint8).reshape(-1, 32).copy()).to(dev) for i in range(F)]
+    pinned = [torch.from_numpy(frames[i % n_distinct].view(np.uint8).reshape(-1, 32).copy()).pin_memory() for i in range(F)]
     host_views = [pinned[i % F].numpy().view(f3ps.synth.POINT_DTYPE).reshape(-1) for i in range(F * R)]
     ptrs = [d_frames[i % F].data_ptr() for i in range(F * R)]
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     if args.pool == "batch":
         # groups of F frames: K1..K6 per frame on its own handle / stream, ONE merge launch per group (CTA i = frame i)
-        pool = sweep.BatchPool(batch=F, workers=args.workers or None, device=local_rank, merge=FLAGS, threshold=THRESHOLD, expand_ctas=-args.expand_ctas)
+        pool = sweep.BatchPool(batch=F, workers=args.workers or None, device=local_rank, merge=flags, threshold=THRESHOLD, expand_ctas=-args.expand_ctas)
     else:
-        pool = sweep.FramePool(F, device=local_rank, merge=FLAGS, threshold=THRESHOLD)
+        pool = sweep.FramePool(F, device=local_rank, merge=flags, threshold=THRESHOLD)
     stream = torch.cuda.current_stream()
 
     out_bytes = [0]
@@ -234,10 +240,10 @@ def run_ours(args):
     torch.cuda.synchronize()
     sampler.start()
     launches0 = sum(s.launch_count() for s in pool.segs)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     stage_acc = {}
     wall0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(steps):
         flush.fill_(k & 0xff)                  # L2 flush between timed iterations (outside the events)
         torch.cuda.synchronize()
         ev[k][0].record(stream)
@@ -263,7 +269,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(steps):
         pool.run(host_views, collect=collect)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
@@ -271,7 +277,7 @@ def run_ours(args):
     # one frame alone on one stream: the latency the 2 ms target of BASELINE.json speaks about
     solo = pool.segs[0]
     lat = []
-    for k in range(5):
+    for k in range(7):
         flush.fill_(k)
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -282,67 +288,103 @@ def run_ours(args):
         e1.record(stream); torch.cuda.synchronize()
         lat.append(e0.elapsed_time(e1))
     solo_stage = solo.stage_ms()
+    solo_counts = solo.counts()
 
     tmax = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     t_dev_max, t_e2e_max = float(tmax[0]), float(tmax[1])
+    pool.close()
+    del d_frames, pinned, flush
+    n_frames = F * R * steps
+    return dict(F=F, R=R, npts=npts, n_distinct=n_distinct, steps=steps, n_frames=n_frames, t_dev=t_dev_max, t_e2e=t_e2e_max,
+                value=npts * n_frames * world / t_dev_max / 1e6, e2e=npts * n_frames * world / t_e2e_max / 1e6,
+                counts=counts, solo_counts=solo_counts, stage_ms={k: v / (len(pool.segs) * steps) for k, v in stage_acc.items()},
+                solo_stage=solo_stage, lat=lat, launches=int(launches), clocks=clocks, wall=wall, out_bytes=int(out_bytes[0]), frame0=frames[0])
+
+
+def run_ours(args):
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # before the CUDA context exists (see f3ps_create)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu:
+        # the CPU legs run BEFORE any GPU work, so the GPU-busy window of this process is the measurement alone
+        try:
+            cpu = cpu_baseline(make_frames(0, 1, 30000 if args.workload == "c3" else 20020)[0], C3_FLAGS if args.workload == "c3" else FLAGS)
+        except Exception as e:     # the oracle is a checker; its absence must not hide the GPU number
+            cpu = {"value": None, "unit": "Mpoints/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the f3ps path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    env = (dist, world, rank, local_rank, dev)
+    m = sweep_leg(args, env, args.workload, args.steps)
+    c3 = sweep_leg(args, env, "c3", max(2, args.steps // 2)) if (args.workload == "c2" and not args.no_c3) else None
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        n_frames = F * R * args.steps
-        value = npts * n_frames * world / t_dev_max / 1e6
-        e2e = npts * n_frames * world / t_e2e_max / 1e6
+        counts, F, R, npts = m["counts"], m["F"], m["R"], m["npts"]
         V, M = counts.n_voxels, counts.n_merges
-        stage_ms = {k: v / (len(pool.segs) * args.steps) for k, v in stage_acc.items()}     # one sample per handle per step (its last frame)
+        stage_ms = m["stage_ms"]
         # dominant kernel = the persistent merge kernel (K7); algorithmic bytes per launch:
         # 12 E (edge list) + 40 S (region statistics) + 12 M (merge log) + 16 * fold_steps (voxels streamed by the folds)
-        merge_ms = stage_ms.get("merge_kernel", stage_ms.get("merge", 0.0))
-        alg_bytes = 12 * counts.n_edges + 40 * counts.n_supervoxels + 12 * M + 16 * counts.fold_steps
-        ach = alg_bytes / (merge_ms * 1e-3) / 1e9 if merge_ms > 0 else 0.0
+        sc = m["solo_counts"]
+        solo_merge_ms = m["solo_stage"].get("merge_kernel", m["solo_stage"].get("merge", 0.0))
+        alg_bytes = 12 * sc.n_edges + 40 * sc.n_supervoxels + 12 * sc.n_merges + 16 * sc.fold_steps
+        ach = alg_bytes / (solo_merge_ms * 1e-3) / 1e9 if solo_merge_ms > 0 else 0.0
         e2e_bytes = 16 * npts + 16 * V + 12 * M
-        t_frame = t_dev_max / n_frames
+        t_frame = m["t_dev"] / m["n_frames"]
+        traffic = load_traffic()
         line = {
-            "metric": "Mpoints/s end-to-end segmentation", "value": value, "unit": "Mpoints/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_dev_max / args.steps * 1e3,
+            "metric": "Mpoints/s end-to-end segmentation", "value": m["value"], "unit": "Mpoints/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": m["t_dev"] / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "step": ("%d frames per GPU in groups of %d: K1..K6 of a frame on its own handle + stream, ONE resident-merge launch "
-                                "per group (CTA i = frame i), the next group's front stages overlap it (BatchPool); the reference's -d loop "
-                                "processes independent files" % (F * R, F)) if args.pool == "batch" else
-                               ("%d frames per GPU, %d in flight (one handle + stream each, %d frames back to back per handle; "
-                                "the reference's -d loop processes independent files)" % (F * R, F, R)),
-                       "pool": args.pool,
-                       "frames_per_step_per_gpu": F * R, "frames_in_flight_per_gpu": F, "distinct_frames": N_POOL,
-                       "l2": "L2 flushed (512 MB write) between timed steps; a step streams %d MB of input" % (F * R * npts * 32 >> 20),
-                       "sharding": "frames per GPU, no collective",
-                       "V": int(V), "S": int(counts.n_supervoxels), "E": int(counts.n_edges), "M": int(M)},
-            "e2e": {"value": e2e, "unit": "Mpoints/s", "h2d_bytes_per_step": F * R * npts * 32, "d2h_bytes_per_step": int(out_bytes[0]) * F * R},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
+            "config": shared_config(args.workload),
+            "run": {"step": ("%d frames per GPU in groups of %d: K1..K6 of a frame on its own handle + stream, ONE resident-merge launch "
+                             "per group (CTA i = frame i), the next group's front stages overlap it (BatchPool); the reference's -d loop "
+                             "processes independent files" % (F * R, F)) if args.pool == "batch" else
+                            ("%d frames per GPU, %d in flight (one handle + stream each, %d frames back to back per handle; "
+                             "the reference's -d loop processes independent files)" % (F * R, F, R)),
+                    "pool": args.pool, "frames_per_step_per_gpu": F * R, "frames_in_flight_per_gpu": F, "distinct_frames": m["n_distinct"],
+                    "l2": "L2 flushed (512 MB write) between timed steps; a step streams %d MB of input" % (F * R * npts * 32 >> 20),
+                    "sharding": "frames per GPU, no collective",
+                    "V": int(V), "S": int(counts.n_supervoxels), "E": int(counts.n_edges), "M": int(M)},
+            "e2e": {"value": m["e2e"], "unit": "Mpoints/s", "h2d_bytes_per_step": F * R * npts * 32, "d2h_bytes_per_step": m["out_bytes"] * F * R},
+            "gpu_launches": m["launches"],
+            "clocks": m["clocks"],
             "ms_per_frame": t_frame * 1e3,
-            "single_frame_latency_ms": {"median": statistics.median(lat), "min": min(lat), "stage_ms": {k: round(v, 4) for k, v in solo_stage.items()}},
+            "single_frame_latency_ms": {"median": statistics.median(m["lat"]), "min": min(m["lat"]),
+                                        "stage_ms": {k: round(v, 4) for k, v in m["solo_stage"].items()},
+                                        "us_per_merge": 1e3 * solo_merge_ms / max(1, sc.n_merges)},
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
-            "roofline": {"bound": "hbm", "kernel": "merge_fast_kernel (K7, one persistent CTA per frame; latency-bound serial replay, see DESIGN.md)",
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": load_traffic(), "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "merge_fast_kernel (K7, one persistent CTA per frame; a serial dependency chain, not a bandwidth "
+                                                   "problem: its HBM fraction is ~1e-5 by construction, the figure to read is us_per_merge; DESIGN.md section 3.7)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                         "traffic_source": TRAFFIC_FILE if traffic is not None else None, "peak_source": peak_src,
+                         "timed": "the kernel's own CUDA events on its stream, one frame alone (%.3f ms for %d merges)" % (solo_merge_ms, sc.n_merges),
                          "algorithmic_bytes_per_launch": int(alg_bytes),
-                         "merge_path": int(counts.merge_path),
+                         "merge_path": int(sc.merge_path),
                          "e2e_algorithmic_bytes": e2e_bytes,
                          "e2e_achieved_gbs": e2e_bytes / t_frame / 1e9 if t_frame > 0 else 0.0,
                          "e2e_frac": e2e_bytes / t_frame / 1e9 / peak if t_frame > 0 else 0.0},
-            "wall_s": wall,
+            "wall_s": m["wall"],
         }
-        if world == 1 and not args.no_cpu:
-            try:
-                line["cpu_baseline"] = cpu_baseline(frames[0])
-            except Exception as e:     # the oracle is a checker; its absence must not hide the GPU number
-                line["cpu_baseline"] = {"value": None, "unit": "Mpoints/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
+        if c3 is not None:
+            line["c3"] = {"config": shared_config("c3"), "value": c3["value"], "unit": "Mpoints/s", "e2e": c3["e2e"], "steps": c3["steps"],
+                          "ms_per_frame": c3["t_dev"] / c3["n_frames"] * 1e3, "M": int(c3["counts"].n_merges),
+                          "single_frame_latency_ms": statistics.median(c3["lat"]), "stage_ms": {k: round(v, 4) for k, v in c3["stage_ms"].items()}}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    pool.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
-
 
 
 # ------------------------------------------------------------------------------------------------
@@ -426,7 +468,7 @@ def run_slab(args):
         line = {"metric": "Mpoints/s end-to-end segmentation", "value": value, "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(1, args.warmup), "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": C5_WORKLOAD, "points": args.points, "V": V, "S": int(c.n_supervoxels), "E": int(c.n_edges), "M": M,
+                "config": dict(shared_config("c5"), points=args.points), "run": {"points": args.points, "V": V, "S": int(c.n_supervoxels), "E": int(c.n_edges), "M": M,
                            "nan_weights": int(c.nan_weights), "rounds": int(c.rounds), "sweeps": int(info["sweeps"]),
                            "own_slice_rank0": list(info["own"]), "l2": "L2 flushed between steps; the cloud is %d MB" % (args.points * 32 >> 20),
                            "sharding": "slabs = Morton-key ranges; K1/K3/K5 sweeps sharded, K2/K4/K6 on replicated tables, K7 replicas only"},
@@ -455,7 +497,8 @@ def main():
     ap.add_argument("--pool", default="batch", choices=["batch", "streams"], help="batch: one merge launch per group of --inflight frames; streams: one merge kernel per stream")
     ap.add_argument("--expand-ctas", type=int, default=24, help="batch pool: cap of the cooperative K5 grid per frame (0 = one voxel per thread)")
     ap.add_argument("--workers", type=int, default=32, help="host threads for the front stages of a group (batch pool)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: frames in flight (the headline); c5: one large cloud in slab mode")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"], help="c2: frames in flight, --CVX --AL (the headline; a short C3 leg rides along); c3: the --EQ 200 directory sweep; c5: one large cloud in slab mode")
+    ap.add_argument("--no-c3", action="store_true", help="c2: skip the C3 leg")
     ap.add_argument("--points", type=int, default=50_000_000, help="c5: points of the merged scan")
     ap.add_argument("--verify", action="store_true", help="c5: compare the slab result with one handle processing the whole cloud")
     args = ap.parse_args()

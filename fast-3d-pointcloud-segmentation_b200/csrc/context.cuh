@@ -17,8 +17,14 @@
 
 namespace f3ps {
 
+// Owning device buffer: freed by its destructor, so a handle's `delete` releases every buffer it ever grew
+// (f3ps_destroy used to walk an explicit list that missed the threshold-sweep and slab buffers).
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap && p) return cudaSuccess;
         if (p) cudaFree(p);
@@ -100,7 +106,8 @@ struct f3ps_ctx {
     unsigned edge_set_mask = 0; int edge_kb = 0;
     // K7
     f3ps::DevBuf mlog, run_out_off, run_dense, region_dense, out_xyz, out_label, out_voxel, vox_segment;
-    f3ps::DevBuf pos_data_buf, merge_scratch;
+    f3ps::DevBuf pos_data_buf, merge_scratch, adj_pool, merge_trace;
+    unsigned merge_trace_first = 0;
     const float4* pos_data = nullptr;   // voxel (x,y,z,rgba) in position order (what the merge folds stream)
     int merge_path = 0;                 // 1 = resident kernel, 2 = general kernel (last f3ps_merge)
     bool force_general_merge = false;   // f3ps_set_merge_kernel(ctx, 2)

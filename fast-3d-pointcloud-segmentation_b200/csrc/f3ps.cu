@@ -255,17 +255,7 @@ void f3ps_destroy(f3ps_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->in_buf, &ctx->keys_a, &ctx->keys_b, &ctx->vals_a, &ctx->vals_b, &ctx->starts, &ctx->point_voxel, &ctx->sort_scratch,
-        &ctx->compact_scratch, &ctx->vox_xyz, &ctx->vox_rgb, &ctx->vox_key, &ctx->hash_slots, &ctx->hash_vals, &ctx->nbr_row, &ctx->nbr_col,
-        &ctx->vox_normal, &ctx->vox_curv, &ctx->cell_code, &ctx->cell_code_b, &ctx->cell_vox, &ctx->cell_vox_b, &ctx->vox_cell, &ctx->cell_start,
-        &ctx->cell_codes, &ctx->cell_nn, &ctx->cell_keep, &ctx->seeds, &ctx->owner0, &ctx->dist0, &ctx->chg_a, &ctx->chg_b, &ctx->own_a, &ctx->own_b, &ctx->dst_a, &ctx->dst_b, &ctx->st0, &ctx->st1, &ctx->phantom, &ctx->phantom_leaf,
-        &ctx->lab_count, &ctx->lab_count2, &ctx->lab_fill, &ctx->lab_keys_a,
-        &ctx->cen_xyz, &ctx->cen_rgb, &ctx->cen_nrm, &ctx->lab_keys_b, &ctx->lab_vals_a, &ctx->lab_vals_b, &ctx->seg_start, &ctx->seg_end,
-        &ctx->sv_label, &ctx->rank_of_label, &ctx->run_start, &ctx->run_end, &ctx->pos_run, &ctx->edge_set, &ctx->edge_keys_a, &ctx->edge_keys_b,
-        &ctx->edge_vals_a, &ctx->edge_vals_b, &ctx->dbits_a, &ctx->dbits_b, &ctx->dbits_c, &ctx->dbits_d, &ctx->cdf_c, &ctx->cdf_g, &ctx->cdf_hist,
-        &ctx->reg_init, &ctx->reg_work, &ctx->edge_init, &ctx->edge_work, &ctx->mlog, &ctx->run_out_off, &ctx->run_dense, &ctx->region_dense,
-        &ctx->out_xyz, &ctx->out_label, &ctx->out_voxel, &ctx->vox_segment, &ctx->pos_data_buf, &ctx->merge_scratch};
-    for (DevBuf* b : bufs) b->release();
+    // (device buffers are DevBuf members: `delete ctx` below releases every one of them)
     if (ctx->d_sc) cudaFree(ctx->d_sc);
     if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
     if (ctx->d_lab_lut) cudaFree(ctx->d_lab_lut);
@@ -711,14 +701,19 @@ int f3ps_set_graph(f3ps_ctx* ctx, int64_t n_voxels, const float* voxel_xyz, cons
 // ---- K7 -------------------------------------------------------------------------------------------
 extern "C++" {
 namespace {
-// edge slots per worker thread of the resident kernel (0 = the graph does not fit)
+// blocks of 32 edges per worker warp of the resident kernel (0 = the graph does not fit): E_cap = 928 * blocks
 int lean_slots_for(unsigned E) {
-    for (int sl : {4, 8, 10, 12}) if ((size_t)E <= (size_t)sl * kFastOwners) return sl;
-    return 0;
+    const unsigned nb = std::max(1u, (E + (unsigned)kFastOwners - 1u) / (unsigned)kFastOwners);
+    return nb <= 32u ? (int)nb : 0;
 }
-void (*lean_kernel_for(int slots, bool prof))(FastArgs) {
-    if (prof) return slots == 4 ? merge_fast_kernel<4, true> : slots == 8 ? merge_fast_kernel<8, true> : slots == 10 ? merge_fast_kernel<10, true> : merge_fast_kernel<12, true>;
-    return slots == 4 ? merge_fast_kernel<4, false> : slots == 8 ? merge_fast_kernel<8, false> : slots == 10 ? merge_fast_kernel<10, false> : merge_fast_kernel<12, false>;
+void (*lean_kernel_for(bool prof))(FastArgs) { return prof ? merge_fast_kernel<true> : merge_fast_kernel<false>; }
+// adjacency pool of the resident kernel (edge ids, 2 bytes each): the initial lists plus room for the lists that outgrow their block
+constexpr size_t kLeanPoolSlack = 1u << 20;
+int lean_pool(f3ps_ctx* ctx, unsigned E, FastArgs& A) {
+    const size_t entries = 2 * (size_t)E + kLeanPoolSlack;
+    F3PS_CUDA_OK(ctx->adj_pool.ensure(entries * 2));
+    A.adj_pool = ctx->adj_pool.as<unsigned short>(); A.pool_cap = (unsigned)entries;
+    return F3PS_OK;
 }
 // The opt-in to > 48 KB of dynamic shared memory is per function AND per device: remember it per (device, function).
 int lean_attr(f3ps_ctx* ctx, const void* kern) {
@@ -760,9 +755,9 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
         // resident kernel when the graph fits one SM (kernels_merge_lean.cuh), else the general one
         const unsigned S_cap = (S + 7u) & ~7u;
         const int slots = lean_slots_for(E);
-        const unsigned E_cap = (unsigned)std::max(slots, 4) * kFastOwners;
+        const unsigned E_cap = (unsigned)std::max(slots, 1) * kFastOwners;
         const size_t fast_bytes = FastSmem(nullptr, S_cap, E_cap).bytes;
-        const bool single_ok = slots && S < 65535u && fast_bytes <= 227u * 1024u && P > 0;
+        const bool single_ok = slots && S <= 4096u && fast_bytes <= 227u * 1024u && P > 0;
         bool fast = !ctx->force_general_merge && single_ok;
         for (int attempt = 0; attempt < 2; ++attempt) {
             if (attempt == 1) {                                    // a merge overflowed the resident kernel's touched list: start over
@@ -778,8 +773,15 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
                 A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
                 A.ctl = SC(mctl); A.S_cap = S_cap;
                 A.E_cap = E_cap;
-                void (*kern)(FastArgs) = lean_kernel_for(slots, ctx->merge_kernel_choice == 4);
+                void (*kern)(FastArgs) = lean_kernel_for(ctx->merge_kernel_choice == 4);
                 rc = lean_attr(ctx, (const void*)kern); if (rc) return rc;
+                rc = lean_pool(ctx, E, A); if (rc) return rc;
+                A.trace = nullptr; A.trace_first = ctx->merge_trace_first;
+                if (ctx->merge_kernel_choice == 4) {
+                    F3PS_CUDA_OK(ctx->merge_trace.ensure(256 * 32 * 4));
+                    F3PS_CUDA_OK(cudaMemsetAsync(ctx->merge_trace.p, 0, 256 * 32 * 4, ctx->stream));
+                    A.trace = ctx->merge_trace.as<unsigned>();
+                }
                 kern<<<1, kFastThreads, fast_bytes, ctx->stream>>>(A);
                 ctx->launches++;
                 F3PS_CUDA_OK(cudaPeekAtLastError());
@@ -853,11 +855,11 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
         if (ctx->progress < P_GRAPH) { rc = f3ps_graph(ctx); if (rc) return rc; }
         const unsigned S = ctx->S, E = ctx->E, P = ctx->n_pos;
         const int slots = lean_slots_for(E);
-        const bool ok = S > 0 && slots && S < 65535u && P > 0 && !ctx->force_general_merge;
+        const bool ok = S > 0 && slots && S <= 4096u && P > 0 && !ctx->force_general_merge;
         slots_of[i] = slots;
         (ok ? batch : solo).push_back(i);
     }
-    int slots = 4;
+    int slots = 1;
     for (int i : batch) slots = std::max(slots, slots_of[i]);
     const unsigned E_cap = (unsigned)slots * kFastOwners;
     {   // the shared-memory layout must fit with the batch's edge capacity
@@ -896,6 +898,8 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
             A.threshold = threshold; A.run_start = ctx->run_start.as<unsigned>(); A.run_end = ctx->run_end.as<unsigned>();
             A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
             A.ctl = SC(mctl); A.S_cap = (S + 7u) & ~7u; A.E_cap = E_cap;
+            rc = lean_pool(ctx, ctx->E, A); if (rc) return rc;
+            A.trace = nullptr; A.trace_first = 0;
             bytes = std::max(bytes, FastSmem(nullptr, A.S_cap, E_cap).bytes);
             rc = mark(ctx, 9); if (rc) return rc;
             if (ctx != lead) {                               // the lead's stream runs the grid: it waits for everybody's set-up
@@ -905,7 +909,7 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
         }
         {
             f3ps_ctx* ctx = lead;
-            void (*kern)(const FastBatch) = slots == 4 ? merge_fast_batch_kernel<4> : slots == 8 ? merge_fast_batch_kernel<8> : slots == 10 ? merge_fast_batch_kernel<10> : merge_fast_batch_kernel<12>;
+            void (*kern)(const FastBatch) = merge_fast_batch_kernel;
             rc = lean_attr(ctx, (const void*)kern); if (rc) return rc;
             kern<<<(unsigned)(g1 - g0), kFastThreads, bytes, ctx->stream>>>(B);
             ctx->launches++;
@@ -1233,6 +1237,17 @@ int f3ps_merge_profile(f3ps_ctx* ctx, uint64_t cycles[32]) {
     if (!ctx || !cycles) return F3PS_ERR_INVALID_ARGUMENT;
     int rc = need(ctx, P_MERGED, "f3ps_merge_profile"); if (rc) return rc;
     for (int i = 0; i < 32; ++i) cycles[i] = ctx->h_sc->mctl.phase_cycles[i];
+    return F3PS_OK;
+}
+
+int f3ps_merge_trace(f3ps_ctx* ctx, int64_t first_merge, uint32_t* out, int64_t capacity_words) {
+    if (!ctx || first_merge < 0) return F3PS_ERR_INVALID_ARGUMENT;
+    ctx->merge_trace_first = (unsigned)first_merge;          // takes effect at the next f3ps_merge with kernel choice 4
+    if (!out) return F3PS_OK;
+    if (capacity_words < 256 * 32 || !ctx->merge_trace.p) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "f3ps_merge_trace: no trace recorded or buffer below 8192 words");
+    cudaSetDevice(ctx->device);
+    F3PS_CUDA_OK(cudaMemcpyAsync(out, ctx->merge_trace.p, 256 * 32 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    F3PS_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     return F3PS_OK;
 }
 
@@ -1710,6 +1725,31 @@ int f3ps_eval_thresholds(f3ps_ctx* ctx, const uint32_t* truth_label, int64_t n_v
     return F3PS_OK;
 }
 
+
+int f3ps_eval_label_pairs(f3ps_ctx* ctx, const uint32_t* seg, const uint32_t* truth, int64_t n_pairs, int32_t n_seg, int32_t n_truth,
+                          const uint64_t* truth_sizes, int64_t n_truth_points, f3ps_performance* perf) {
+    if (!ctx || !perf || n_pairs < 0 || n_seg < 0 || n_truth < 0 || (n_pairs > 0 && (!seg || !truth)) || (n_truth > 0 && !truth_sizes)) return F3PS_ERR_INVALID_ARGUMENT;
+    if (n_pairs == 0) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "The pointcloud to be set as 'segm' cannot be empty");       // testing.cpp:413-416
+    if (n_truth_points <= 0) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "The pointcloud to be set as 'truth' cannot be empty"); // :430-433
+    for (int64_t i = 0; i < n_pairs; ++i)
+        if (seg[i] >= (uint32_t)n_seg || truth[i] > (uint32_t)n_truth) return ctx_fail(ctx, F3PS_ERR_INVALID_ARGUMENT, "f3ps_eval_label_pairs: label out of range");
+    const unsigned Kc = (unsigned)n_truth + 1u;
+    if ((size_t)n_seg * Kc > ((size_t)1 << 28)) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "contingency table above 2^28 cells");
+    cudaSetDevice(ctx->device);
+    const size_t cells = std::max<size_t>(1, (size_t)n_seg * Kc);
+    F3PS_CUDA_OK(ctx->ev_dense.ensure((size_t)n_pairs * 4)); F3PS_CUDA_OK(ctx->ev_truth.ensure((size_t)n_pairs * 4)); F3PS_CUDA_OK(ctx->ev_table.ensure(cells * 4));
+    F3PS_CUDA_OK(cudaMemcpyAsync(ctx->ev_dense.p, seg, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    F3PS_CUDA_OK(cudaMemcpyAsync(ctx->ev_truth.p, truth, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    F3PS_CUDA_OK(cudaMemsetAsync(ctx->ev_table.p, 0, cells * 4, ctx->stream));
+    LAUNCH(ctx, eval_pairs_kernel, grid_for(n_pairs, 256), 256, 0, ctx->ev_dense.as<unsigned>(), ctx->ev_truth.as<unsigned>(), (long long)n_pairs, Kc, ctx->ev_table.as<unsigned>());
+    std::vector<unsigned> table(cells);
+    int rc = d2h(ctx, table.data(), ctx->ev_table.p, cells * 4); if (rc) return rc;
+    if ((rc = fin(ctx))) return rc;
+    std::vector<size_t> g((size_t)n_truth);
+    for (int32_t j = 0; j < n_truth; ++j) g[(size_t)j] = (size_t)truth_sizes[j];
+    *perf = testing_scores(table, (unsigned)n_seg, (unsigned)n_truth, g, (size_t)n_truth_points);
+    return F3PS_OK;
+}
 
 static int test_map3(f3ps_ctx* ctx, int which, const float* in1, const float* in2, float* out, int64_t n) {
     if (!ctx || n < 0) return F3PS_ERR_INVALID_ARGUMENT;

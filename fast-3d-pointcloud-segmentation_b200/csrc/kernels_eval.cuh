@@ -51,4 +51,11 @@ __global__ void __launch_bounds__(256) eval_table_kernel(const unsigned* __restr
     }
 }
 
+// contingency histogram of (segment, ground-truth label) pairs (Testing::compute_intersections, src/testing.cpp:88-146)
+__global__ void __launch_bounds__(256) eval_pairs_kernel(const unsigned* __restrict__ seg, const unsigned* __restrict__ truth, long long n,
+        unsigned n_cols, unsigned* __restrict__ table) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&table[(size_t)seg[i] * n_cols + truth[i]], 1u);
+}
+
 } // namespace f3ps

@@ -4,11 +4,15 @@
 // refetching instructions (8.9 k SASS instructions against a 32 KB instruction cache, 75 % hit rate) and ran CIEDE2000 on
 // 128 of its 1024 threads.  This one keeps the per-merge code small and flat:
 //
-//   edges         shared memory: 64-bit order key (weight bits : biased tie stamp) + packed (a,b); worker thread t owns the
-//                 edges t + 928 j and rescans its slots every merge (no cached minima, no pending lists)
+//   edges         shared memory: 64-bit order key (weight bits : biased tie stamp) + packed (a,b); worker warp w owns the blocks
+//                 of 32 edges w, w + 29, ... and rescans them (independent loads) only after a merge re-weighted one of them
+//   adjacency     per region a list of edge ids in an L2-resident pool (start / length / capacity in shared memory): the edges a
+//                 merge touches are read from the two lists, never searched for; the survivors become a's new list
 //   ropes / sizes shared memory (per region: head / tail / next run, run bounds, voxel count)
-//   voxels        position-ordered float4 (x,y,z,rgba) in HBM/L2; region b's runs stream through a four-slot ring of
-//                 512 voxels filled by cp.async.bulk (loader warp, full/empty mbarriers), so long folds never wait for a copy
+//   voxels        position-ordered float4 (x,y,z,rgba) in HBM/L2; a region of <= 256 voxels is fetched by the fold warps themselves
+//                 (16-byte cp.async per lane, every run in flight at once); longer ones stream through a four-slot ring of 256
+//                 voxels filled by the loader warp the same way (full/empty mbarriers, cp.async.mbarrier.arrive).  One bulk copy
+//                 (TMA) per run, as in round 1, made the loader the bottleneck of the long folds: runs are ~15 voxels
 //   touched edges ONE worker thread per touched edge (up to 928): duplicates through a per-region mark, CIEDE2000 in every
 //                 thread that needs it (the round-1 kernel looped 128 threads over up to 600 edges), tie stamps through a hash
 //
@@ -17,7 +21,7 @@
 // warp when <= 32 edges are touched), F (all: new geometry published), W4 (workers: new keys written).
 //
 // Limits (the host falls back to merge_kernel of kernels_merge.cuh beyond them): S < 65535, tables within 227 KB,
-// E <= 928 * SLOTS, at most 928 edges touched by one merge.
+// E <= 928 * 32, at most 928 adjacency entries of a and b together, the adjacency pool not exhausted.
 #pragma once
 #include "kernels_merge.cuh"
 
@@ -35,6 +39,7 @@ constexpr unsigned long long kDeadKey64 = ~0ull;
 constexpr unsigned kNil16 = 0xffffu;
 constexpr unsigned kFastErrTouched = 4u;      // == F3PS_MERGE_ERR_TOUCHED
 constexpr unsigned kFastErrStamp = 8u;
+constexpr unsigned kFastErrPool = 16u;
 
 struct FastArgs {
     RegionArrays R; EdgeArrays E;
@@ -45,7 +50,9 @@ struct FastArgs {
     const unsigned* sv_label;
     MergeLog mlog; unsigned log_cap;
     MergeCtl* ctl;
-    unsigned S_cap, E_cap;                   // table capacities the shared-memory layout was sized for
+    unsigned short* adj_pool; unsigned pool_cap;   // adjacency lists (edge ids), bump-allocated; entries
+    unsigned* trace; unsigned trace_first;         // PROF only: clock() of 32 points of 256 merges starting at trace_first (f3ps_get_merge_trace)
+    unsigned S_cap, E_cap;                   // table capacities the shared-memory layout was sized for (E_cap = 928 * blocks per warp)
 };
 
 // shared-memory layout, shared by host (size) and device (pointers)
@@ -53,12 +60,13 @@ struct FastSmem {
     unsigned long long* key; unsigned* ab;
     float4* stage; unsigned long long* mbar;                        // full[kLeanRing], empty[kLeanRing]
     float4* priv;                                                   // one private stage per fold warp: regions of <= kLeanSlotVox voxels skip the loader
-    unsigned short *te_e, *partner; unsigned* res_w; unsigned char* cls; unsigned long long* te_key;
+    unsigned short* partner; unsigned* res_w; unsigned char* cls; unsigned long long* te_key;
     unsigned *hkey, *hcnt;
     unsigned long long* wm_key; unsigned *wm_e, *wm_ab;
-    float* newgeo; int* misc; float* inv; int* wdirty; unsigned* wmask;
-    unsigned *rs, *re; int* n;
+    float* newgeo; int* misc; float* inv; unsigned* bdirty;
+    unsigned* rs; unsigned short* rlen; int* n;
     unsigned short *head, *tail, *next, *mark;
+    unsigned* adj_start; unsigned short *adj_len, *adj_cap;
     size_t bytes;
     __host__ __device__ FastSmem(char* base, unsigned S, unsigned E_cap) {
         size_t o = 0;
@@ -66,31 +74,24 @@ struct FastSmem {
         stage = (float4*)take((size_t)kLeanRing * kLeanSlotVox * 16); mbar = (unsigned long long*)take(2 * kLeanRing * 8);
         priv = (float4*)take((size_t)2 * kLeanSlotVox * 16);
         key = (unsigned long long*)take((size_t)E_cap * 8); te_key = (unsigned long long*)take(kLeanMaxTouched * 8); ab = (unsigned*)take((size_t)E_cap * 4);
-        te_e = (unsigned short*)take(kLeanMaxTouched * 2); partner = (unsigned short*)take(kLeanMaxTouched * 2);
+        partner = (unsigned short*)take(kLeanMaxTouched * 2);
         res_w = (unsigned*)take(kLeanMaxTouched * 4); cls = (unsigned char*)take(kLeanMaxTouched);
         hkey = (unsigned*)take(kLeanHash * 4); hcnt = (unsigned*)take(kLeanHash * 4);
         wm_key = (unsigned long long*)take(32 * 8); wm_e = (unsigned*)take(32 * 4); wm_ab = (unsigned*)take(32 * 4);
-        newgeo = (float*)take(16 * 4); misc = (int*)take(16 * 4); inv = (float*)take(64 * 4); wdirty = (int*)take(32 * 4);
-        wmask = (unsigned*)take((size_t)S * 4);
-        rs = (unsigned*)take((size_t)S * 4); re = (unsigned*)take((size_t)S * 4); n = (int*)take((size_t)S * 4);
+        newgeo = (float*)take(16 * 4); misc = (int*)take(16 * 4); inv = (float*)take(64 * 4); bdirty = (unsigned*)take(32 * 4);
+        rs = (unsigned*)take((size_t)S * 4); rlen = (unsigned short*)take((size_t)S * 2); n = (int*)take((size_t)S * 4);
         head = (unsigned short*)take((size_t)S * 2); tail = (unsigned short*)take((size_t)S * 2); next = (unsigned short*)take((size_t)S * 2);
         mark = (unsigned short*)take((size_t)S * 2);
+        adj_start = (unsigned*)take((size_t)S * 4); adj_len = (unsigned short*)take((size_t)S * 2); adj_cap = (unsigned short*)take((size_t)S * 2);
         bytes = o;
     }
 };
-enum { FM_TCOUNT = 0, FM_EALIVE, FM_RALIVE, FM_COUNTER, FM_ND, FM_NANW, FM_ERROR, FM_MAXT, FM_SUMT, FM_MISS, FM_EVALS, FM_NMERGES };
+enum { FM_NLIVE = 0, FM_EALIVE, FM_RALIVE, FM_COUNTER, FM_ND, FM_NANW, FM_ERROR, FM_MAXT, FM_SUMT, FM_MISS, FM_EVALS, FM_NMERGES, FM_POOL };
 
-// ---- PTX helpers: mbarrier + 1-D bulk copy (TMA engine, no tensor map), named barriers ------------------------
+// ---- PTX helpers: mbarrier, cp.async, named barriers ------------------------
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_local(unsigned mbar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
@@ -106,11 +107,11 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // A region of at most kLeanSlotVox voxels: the fold warp copies its runs itself (one 16-byte cp.async per lane and voxel,
 // every run in flight at once) -- one L2 round trip instead of the loader hand-over plus a bulk copy per run.
-__device__ __forceinline__ void lean_fetch_small(const unsigned short* head, const unsigned short* next, const unsigned* rs, const unsigned* re,
+__device__ __forceinline__ void lean_fetch_small(const unsigned short* head, const unsigned short* next, const unsigned* rs, const unsigned short* rlen,
                                                  const float4* __restrict__ pos_data, unsigned b, int nb, float4* dst, int lane) {
     unsigned run = head[b]; int filled = 0;
     while (filled < nb && run != kNil16) {
-        const unsigned r0 = rs[run]; const int len = (int)(re[run] - r0);
+        const unsigned r0 = rs[run]; const int len = (int)rlen[run];
         for (int j = lane; j < len; j += 32) cp_async16(smem_addr(dst + filled + j), pos_data + r0 + j);
         filled += len; run = next[run];
     }
@@ -239,14 +240,18 @@ __device__ __forceinline__ FastHead lean_head(const FastSmem& sm, int lane) {
 }
 
 enum { FC_KEEP = 0, FC_FRONT = 1, FC_BACK = 2, FC_DUP = 3 };
-enum { BAR_W1 = 1, BAR_WB = 2, BAR_F = 3, BAR_W4 = 4, BAR_G = 5 };
+enum { BAR_W1 = 1, BAR_WB = 2, BAR_F = 3, BAR_W4 = 4, BAR_G = 5, BAR_FN = 6, BAR_GN = 7 };
+// A merge whose two adjacency lists hold <= 32 entries is NARROW: one worker warp handles it, the other 28 sleep until W4, and
+// the G / F barriers shrink to the warps involved (G: mean warp + worker warp 0; F: the three role warps + worker warp 0).
+__device__ __forceinline__ bool lean_wide(const FastSmem& sm, unsigned a, unsigned b) { return (unsigned)sm.adj_len[a] + (unsigned)sm.adj_len[b] > 32u; }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 #define LPROF_DECL unsigned pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned t_prev = PROF ? (unsigned)clock() : 0u
 #define LPROF(cond, i) do { if (PROF && (cond)) { const unsigned t_now = (unsigned)clock(); pc[i] += t_now - t_prev; t_prev = t_now; } } while (0)
+#define LTRACE(cond, slot, val) do { if (PROF && (cond) && A.trace && (nm - A.trace_first) < 256u) A.trace[(nm - A.trace_first) * 32u + (slot)] = (val); } while (0)
 #define LPROF_STORE(cond, base, n) do { if (PROF && (cond)) for (int i_ = 0; i_ < (n); ++i_) A.ctl->phase_cycles[(base) + i_] = pc[i_]; } while (0)
 
-template <int SLOTS, bool PROF>
+template <bool PROF>
 __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
     extern __shared__ __align__(128) char smem_raw[];
     const FastSmem sm(smem_raw, A.S_cap, A.E_cap);
@@ -256,14 +261,19 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
     const unsigned mbar_full = smem_addr(sm.mbar), mbar_empty = mbar_full + 8u * kLeanRing;
     int* const newgeo_i = reinterpret_cast<int*>(sm.newgeo);
 
-    // ---- set-up: ropes and edges -> shared memory -----------------------------------------------------------------
+    // ---- set-up: ropes, edges, adjacency lists -> shared memory / the pool ------------------------------------------------
+    const unsigned nbw = A.E_cap / kFastOwners;                                // blocks of 32 edges per worker warp
+    unsigned* const cursor = reinterpret_cast<unsigned*>(sm.stage);           // scratch: the ring is idle until the first merge
     for (unsigned s = tid; s < S; s += kFastThreads) {
-        sm.rs[s] = A.run_start[s]; sm.re[s] = A.run_end[s]; sm.n[s] = R.n[s];
+        const unsigned r0 = A.run_start[s];
+        sm.rs[s] = r0; sm.rlen[s] = (unsigned short)(A.run_end[s] - r0); sm.n[s] = R.n[s];
         const int h = R.head[s], t = R.tail[s], nx = R.next_run[s];
         sm.head[s] = (unsigned short)(h < 0 ? kNil16 : (unsigned)h); sm.tail[s] = (unsigned short)(t < 0 ? kNil16 : (unsigned)t);
-        sm.next[s] = (unsigned short)(nx < 0 ? kNil16 : (unsigned)nx); sm.mark[s] = (unsigned short)kNil16; sm.wmask[s] = 0u;
+        sm.next[s] = (unsigned short)(nx < 0 ? kNil16 : (unsigned)nx); sm.mark[s] = (unsigned short)kNil16; sm.adj_start[s] = 0u;
     }
-    if (tid < 32) sm.wdirty[tid] = 1;
+    if (tid < 32) sm.bdirty[tid] = 1u;
+    for (int i = tid; i < kLeanMaxTouched; i += kFastThreads) sm.partner[i] = (unsigned short)kNil16;
+    for (int i = tid; i < kLeanHash; i += kFastThreads) { sm.hkey[i] = kDeadKey; sm.hcnt[i] = 0u; }
     __syncthreads();
     for (unsigned e = tid; e < A.E_cap; e += kFastThreads) {
         unsigned long long k = kDeadKey64; unsigned ab = kDeadKey;
@@ -272,18 +282,46 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             const unsigned hi = isnan(w) ? 0x7f800000u : __float_as_uint(w);
             k = ((unsigned long long)hi << 32) | ((unsigned)(int)A.E.stamp[e] ^ 0x80000000u);
             ab = (A.E.a[e] << 16) | A.E.b[e];
-            const unsigned wbit = 1u << ((e % kFastOwners) >> 5);             // the worker warp that owns this slot
-            atomicOr(&sm.wmask[ab >> 16], wbit); atomicOr(&sm.wmask[ab & 0xffffu], wbit);
+            atomicAdd(&sm.adj_start[ab >> 16], 1u); atomicAdd(&sm.adj_start[ab & 0xffffu], 1u);      // degrees
         }
         sm.key[e] = k; sm.ab[e] = ab;
     }
-    for (int i = tid; i < kLeanHash; i += kFastThreads) { sm.hkey[i] = kDeadKey; sm.hcnt[i] = 0u; }
     if (tid == 0) {
         for (int i = 0; i < 16; ++i) sm.misc[i] = 0;
         sm.misc[FM_EALIVE] = (int)nE; sm.misc[FM_RALIVE] = (int)S; sm.misc[FM_COUNTER] = (int)nE;
-        for (int i = 0; i < kLeanRing; ++i) { mbar_init(mbar_full + 8u * i, 1u); mbar_init(mbar_empty + 8u * i, 2u); }
+        for (int i = 0; i < kLeanRing; ++i) { mbar_init(mbar_full + 8u * i, 32u); mbar_init(mbar_empty + 8u * i, 2u); }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    __syncthreads();
+    // exclusive scan of the degrees -> list starts (CSR), 1024 regions per round
+    for (unsigned base = 0; base < S; base += kFastThreads) {
+        const unsigned s = base + tid;
+        const unsigned deg = s < S ? sm.adj_start[s] : 0u;
+        unsigned incl = deg;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const unsigned t = __shfl_up_sync(kFull, incl, off); if (lane >= off) incl += t; }
+        if (lane == 31) sm.wm_e[warp] = incl;
+        __syncthreads();
+        unsigned wpre = 0;
+        for (int w = 0; w < warp; ++w) wpre += sm.wm_e[w];
+        const unsigned carry = (unsigned)sm.misc[FM_POOL];
+        if (s < S) {
+            const unsigned st = carry + wpre + incl - deg;
+            sm.adj_start[s] = st; cursor[s] = st; sm.adj_len[s] = (unsigned short)deg; sm.adj_cap[s] = (unsigned short)deg;
+        }
+        __syncthreads();
+        if (tid == kFastThreads - 1) sm.misc[FM_POOL] = (int)(carry + wpre + incl);
+        __syncthreads();
+    }
+    if ((unsigned)sm.misc[FM_POOL] > A.pool_cap) { if (tid == 0) sm.misc[FM_ERROR] = (int)kFastErrPool; }
+    else
+        for (unsigned e = tid; e < A.E_cap; e += kFastThreads) {
+            const unsigned ab = sm.ab[e];
+            if (ab == kDeadKey) continue;
+            A.adj_pool[atomicAdd(&cursor[ab >> 16], 1u)] = (unsigned short)e;
+            A.adj_pool[atomicAdd(&cursor[ab & 0xffffu], 1u)] = (unsigned short)e;
+        }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the scratch words become the bulk copies' ring again
     __syncthreads();
 
     if (warp == 0) {
@@ -294,6 +332,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
         const bool prod = lane < 6;
         unsigned chunk = 0;
         LPROF_DECL;
+        unsigned nm = 0;                                   // merges so far (trace index)
         while (true) {
             __syncthreads();                                                                   // S1
             const FastHead hd = lean_head(sm, lane);
@@ -301,6 +340,8 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
             const int na = sm.n[a], nb = sm.n[b];
+            const bool wide = lean_wide(sm, a, b);
+            LTRACE(lane == 0, 12, (unsigned)clock()); LTRACE(lane == 0, 21, (unsigned)nb);
             float acc = 0.0f;
             if (lane < 9) {
                 const float* src = lane < 4 ? reinterpret_cast<const float*>(R.accu0 + a) + lane
@@ -308,12 +349,13 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                 acc = __ldcg(src);
             }
             const bool direct = nb <= kLeanSlotVox;
-            if (direct) lean_fetch_small(sm.head, sm.next, sm.rs, sm.re, A.pos_data, b, nb, sm.priv, lane);
+            if (direct) lean_fetch_small(sm.head, sm.next, sm.rs, sm.rlen, A.pos_data, b, nb, sm.priv, lane);
             for (int done = 0; done < nb; done += kLeanSlotVox) {
                 const int cn = min(nb - done, kLeanSlotVox);
                 const unsigned slot = chunk & (kLeanRing - 1);
                 if (!direct) mbar_wait(mbar_full + 8u * slot, (chunk / kLeanRing) & 1u);
                 LPROF(lane == 0, 0);
+                LTRACE(lane == 0 && done == 0, 13, (unsigned)clock());
                 const float* sf = direct ? reinterpret_cast<const float*>(sm.priv) : stage_f + slot * (kLeanSlotVox * 4);
                 int j = 0;
                 for (; j + 8 <= cn; j += 8) {
@@ -336,6 +378,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                 }
             }
             LPROF(lane == 0, 1);
+            LTRACE(lane == 0, 14, (unsigned)clock());
             float cen[3], nv[3], curv;
             plane_from_accu_warp(acc, na + nb, lane, pi, qi, cen, nv, curv);                   // :411-420, spread over the lanes
             const float cx = cen[0], cy = cen[1], cz = cen[2];
@@ -345,13 +388,15 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             }
             __syncwarp();
             LPROF(lane == 0, 2);
-            named_bar(BAR_F, kFastThreads);                                                     // F: workers read x's old state before this
+            LTRACE(lane == 0, 15, (unsigned)clock());
+            if (wide) named_bar(BAR_F, kFastThreads); else named_bar(BAR_FN, 128);              // F: workers read x's old state before this
             if (lane == 0) { R.centroid[a] = make_float4(cx, cy, cz, 0.0f); R.normal[a] = make_float4(nv[0], nv[1], nv[2], curv); }
             if (lane < 9) {                                                                     // every lane stores its own raw sum
                 float* dst = lane < 4 ? reinterpret_cast<float*>(R.accu0 + a) + lane
                            : (lane < 8 ? reinterpret_cast<float*>(R.accu1 + a) + (lane - 4) : reinterpret_cast<float*>(R.accu2 + a));
                 *dst = acc;
             }
+            ++nm;
         }
         LPROF_STORE(lane == 0, 16, 4);
     } else if (warp == 1) {
@@ -363,6 +408,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
         unsigned chunk = 0;
         unsigned long long fold_steps = 0;
         LPROF_DECL;
+        unsigned nm = 0;                                   // merges so far (trace index)
         while (true) {
             __syncthreads();                                                                   // S1
             const FastHead hd = lean_head(sm, lane);
@@ -370,6 +416,8 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
             const int na = sm.n[a], nb = sm.n[b];
+            const bool wide = lean_wide(sm, a, b);
+            LTRACE(lane == 0, 16, (unsigned)clock());
             float m = 0.0f, mb_ = 0.0f;
             if (lane < 3) { m = __ldcg(reinterpret_cast<const float*>(R.mean + a) + 1 + lane); mb_ = __ldcg(reinterpret_cast<const float*>(R.mean + b) + 1 + lane); }
             // GUESS of the merged region's colour vector for the workers' speculative colour deltas: the Lab lattice point of the
@@ -384,18 +432,20 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                 else { guess[0] = gr; guess[1] = gg; guess[2] = gb; }
                 if (lane == 0) { sm.newgeo[10] = guess[0]; sm.newgeo[11] = guess[1]; sm.newgeo[12] = guess[2]; }
                 __syncwarp();
-                bar_arrive(BAR_G, 32 + kFastOwners);                                            // G: guess published
+                if (wide) bar_arrive(BAR_G, 32 + kFastOwners); else bar_arrive(BAR_GN, 64);     // G: guess published
             }
             LPROF(lane == 0, 3);
+            LTRACE(lane == 0, 17, (unsigned)clock());
             const float cnt0 = (float)na;
             const bool direct = nb <= kLeanSlotVox;
-            if (direct) lean_fetch_small(sm.head, sm.next, sm.rs, sm.re, A.pos_data, b, nb, sm.priv + kLeanSlotVox, lane);
+            if (direct) lean_fetch_small(sm.head, sm.next, sm.rs, sm.rlen, A.pos_data, b, nb, sm.priv + kLeanSlotVox, lane);
             for (int done = 0; done < nb; done += kLeanSlotVox) {
                 const int cn = min(nb - done, kLeanSlotVox);
                 const unsigned slot = chunk & (kLeanRing - 1);
                 float inv_next = 1 / (cnt0 + (float)(done + lane + 1));
                 if (!direct) mbar_wait(mbar_full + 8u * slot, (chunk / kLeanRing) & 1u);
                 LPROF(lane == 0, 0);
+                LTRACE(lane == 0 && done == 0, 18, (unsigned)clock());
                 const unsigned* su = direct ? reinterpret_cast<const unsigned*>(sm.priv + kLeanSlotVox) : stage_u + slot * (kLeanSlotVox * 4);
                 for (int base = 0, g = 0; base < cn; base += 32, g ^= 1) {
                     inv_s[g * 32 + lane] = inv_next;                       // 1/k of the next 32 voxels, one division per lane
@@ -417,6 +467,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                 }
             }
             LPROF(lane == 0, 1);
+            LTRACE(lane == 0, 19, (unsigned)clock());
             const float mr = __shfl_sync(kFull, m, 0), mg = __shfl_sync(kFull, m, 1), mb = __shfl_sync(kFull, m, 2);
             float cv[3];
             if (ep.color_mode == 0) rgb2lab_lanes(ep.lab_lut, mr, mg, mb, lane, cv);
@@ -428,17 +479,18 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             }
             __syncwarp();
             LPROF(lane == 0, 2);
-            named_bar(BAR_F, kFastThreads);                                                     // F: the workers read the guess before this
+            LTRACE(lane == 0, 20, (unsigned)clock());
+            if (wide) named_bar(BAR_F, kFastThreads); else named_bar(BAR_FN, 128);              // F: the workers read the guess before this
             if (lane == 0) {
                 R.mean[a] = make_float4((float)(na + nb), mr, mg, mb);
                 R.cvec[a] = make_float4(cv[0], cv[1], cv[2], 0.0f);
             }
-            fold_steps += (unsigned long long)nb;
+            fold_steps += (unsigned long long)nb; ++nm;
         }
         if (lane == 0) A.ctl->fold_steps = fold_steps;
         LPROF_STORE(lane == 0, 12, 4);
     } else if (warp == 2) {
-        // =========== loader: walk b's rope, one bulk copy per run (or part of a run) into the ring; splice the ropes =====
+        // =========== loader: walk b's rope, copy its runs into the ring (long regions only); splice the ropes =====
         const unsigned stage_addr = smem_addr(sm.stage);
         unsigned chunk = 0;
         while (true) {
@@ -447,151 +499,156 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
             const int na = sm.n[a], nb = sm.n[b];
-            if (nb <= kLeanSlotVox) {
-                // the fold warps fetch a small region themselves (lean_fetch_small)
-            } else if (lane == 0) {
+            const bool wide = lean_wide(sm, a, b);
+            if (nb > kLeanSlotVox) {                       // (the fold warps fetch a small region themselves, lean_fetch_small)
+                // every lane copies one voxel of the current run per step (16-byte cp.async); a lane's copies of a chunk complete
+                // its arrival on the slot's "full" barrier (cp.async.mbarrier.arrive.noinc, 32 arrivals per phase)
                 unsigned run = sm.head[b];
-                unsigned pos = run != kNil16 ? sm.rs[run] : 0u;
+                unsigned pos = run != kNil16 ? sm.rs[run] : 0u, end = run != kNil16 ? pos + sm.rlen[run] : 0u;
                 for (int done = 0; done < nb; done += kLeanSlotVox, ++chunk) {
                     const int cn = min(nb - done, kLeanSlotVox);
                     const unsigned slot = chunk & (kLeanRing - 1);
                     mbar_wait(mbar_empty + 8u * slot, ((chunk / kLeanRing) & 1u) ^ 1u);           // both fold warps are done with the slot
-                    mbar_arrive_expect_tx(mbar_full + 8u * slot, (unsigned)cn * 16u);
                     const unsigned dst = stage_addr + slot * (kLeanSlotVox * 16u);
                     int off = 0;
-                    while (off < cn) {
-                        const unsigned end = sm.re[run];
+                    while (off < cn && run != kNil16) {
                         const int take = min((int)(end - pos), cn - off);
-                        if (take > 0) bulk_g2s(dst + (unsigned)off * 16u, A.pos_data + pos, (unsigned)take * 16u, mbar_full + 8u * slot);
+                        for (int j = lane; j < take; j += 32) cp_async16(dst + (unsigned)(off + j) * 16u, A.pos_data + pos + j);
                         off += take; pos += (unsigned)take;
-                        if (pos == end) { run = sm.next[run]; if (run != kNil16) pos = sm.rs[run]; else break; }
+                        if (pos == end) { run = sm.next[run]; if (run != kNil16) { pos = sm.rs[run]; end = pos + sm.rlen[run]; } }
                     }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar_full + 8u * slot) : "memory");
                 }
-            } else {
-                chunk += (unsigned)((nb + kLeanSlotVox - 1) / kLeanSlotVox);
             }
-            chunk = __shfl_sync(kFull, chunk, 0);
-            named_bar(BAR_F, kFastThreads);                                                     // F
+            if (wide) named_bar(BAR_F, kFastThreads); else named_bar(BAR_FN, 128);              // F
             // rope splice and sizes (voxels_ = a ++ b, :406-409, :426-429) once nobody reads the old ones any more
             if (lane == 0) {
                 sm.next[sm.tail[a]] = sm.head[b]; sm.tail[a] = sm.tail[b];
                 sm.n[a] = na + nb; sm.n[b] = 0;
-                sm.wmask[a] |= sm.wmask[b];                    // b's edges now name a (every worker read the masks before F)
             }
         }
     } else {
-        // =========== workers: the weight map (argmin, incidence) and one touched edge per thread =====
+        // =========== workers: the weight map (cached block minima, adjacency lists) and one touched edge per thread =====
         EdgeParams ep = A.ep;
         if (A.lambda_dev) ep.lambda = *A.lambda_dev;
         const int wtid = tid - 32 * kLeanRoleWarps;                                            // 0..927
         const int ww = warp - kLeanRoleWarps;                                                  // 0..28
+        const unsigned short* __restrict__ pool = A.adj_pool;
         unsigned my_hs = kNil16;                                                               // tie-hash slot to clear after the next S1
         unsigned n_merges = 0;
         LPROF_DECL;
+        unsigned nm = 0;                                   // merges so far (trace index)
         unsigned long long cls_cyc[3] = {0, 0, 0}; unsigned cls_cnt[3] = {0, 0, 0}; unsigned t_top = 0;   // PROF: merges by touched-edge class
 #define WPROF(i) LPROF(wtid == 0, i)
         while (true) {
             if (PROF) t_top = (unsigned)clock();
-            // ---- A: warps that hold a re-weighted (or removed) edge rescan their slots and republish their minimum ----
-            if (sm.wdirty[ww]) {
-                unsigned long long best = sm.key[wtid]; int bj = 0;
-#pragma unroll
-                for (int j = 1; j < SLOTS; ++j) { const unsigned long long k = sm.key[j * kFastOwners + wtid]; if (k < best) { best = k; bj = j; } }
+            LTRACE(wtid == 0, 0, t_top);
+            // ---- A: a warp that holds a re-weighted (or removed) edge rescans its blocks (lane l: edge 32 blk + l, the loads
+            //         independent) and republishes its minimum ----
+            if (sm.bdirty[ww]) {
+                __syncwarp();
+                if (lane == 0) sm.bdirty[ww] = 0u;
+                unsigned long long best = kDeadKey64; unsigned be = 0;
+#pragma unroll 4
+                for (unsigned j = 0; j < nbw; ++j) {
+                    const unsigned e = ((unsigned)ww + kLeanWorkerWarps * j) * 32u + (unsigned)lane;
+                    const unsigned long long k = sm.key[e];
+                    if (k < best) { best = k; be = e; }
+                }
                 const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
                 const unsigned m_hi = __reduce_min_sync(kFull, hi);
                 const unsigned m_lo = __reduce_min_sync(kFull, hi == m_hi ? lo : kDeadKey);
-                const int win = __ffs(__ballot_sync(kFull, hi == m_hi && lo == m_lo)) - 1;
-                if (lane == win) { const unsigned e = (unsigned)(bj * kFastOwners + wtid); sm.wm_key[ww] = best; sm.wm_e[ww] = e; sm.wm_ab[ww] = sm.ab[e]; sm.wdirty[ww] = 0; }
+                if (lane == __ffs(__ballot_sync(kFull, hi == m_hi && lo == m_lo)) - 1) { sm.wm_key[ww] = best; sm.wm_e[ww] = be; sm.wm_ab[ww] = sm.ab[be]; }
             }
             WPROF(0);
+            LTRACE(wtid == 0, 1, (unsigned)clock());
             __syncthreads();                                                                   // S1
             const FastHead hd = lean_head(sm, lane);
             if (my_hs != kNil16) { sm.hkey[my_hs] = kDeadKey; sm.hcnt[my_hs] = 0u; my_hs = kNil16; }
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;   // strict <, src/clustering.cpp:388-389
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
             const int counter = sm.misc[FM_COUNTER];
+            const unsigned pool_top = (unsigned)sm.misc[FM_POOL];
             WPROF(1);
-            // ---- B: the head edge leaves the map; edges incident to a or b -> touched list ----
-            if (hd.e % kFastOwners == (unsigned)wtid) { sm.key[hd.e] = kDeadKey64; sm.ab[hd.e] = kDeadKey; sm.wdirty[ww] = 1; }
-            if (((sm.wmask[a] | sm.wmask[b]) >> ww) & 1u) {                                    // warp-uniform: does this warp hold an incident edge?
-                const unsigned aa = a * 0x10001u, bb = b * 0x10001u;
-                unsigned hits = 0;
-#pragma unroll
-                for (int j = 0; j < SLOTS; ++j) {
-                    const unsigned v = sm.ab[j * kFastOwners + wtid];
-                    hits |= ((__vcmpeq2(v, aa) | __vcmpeq2(v, bb)) != 0u ? 1u : 0u) << j;
-                }
-                if (__any_sync(kFull, hits != 0u)) {
-                    const int cnt = __popc(hits);
-                    int incl = cnt;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(kFull, incl, off); if (lane >= off) incl += t; }
-                    int base = 0;
-                    if (lane == 31) base = atomicAdd(&sm.misc[FM_TCOUNT], incl);
-                    int p = __shfl_sync(kFull, base, 31) + incl - cnt;
-                    while (hits) {
-                        const int j = __ffs(hits) - 1; hits &= hits - 1u;
-                        if (p < kLeanMaxTouched) { sm.te_e[p] = (unsigned short)(j * kFastOwners + wtid); sm.partner[p] = (unsigned short)kNil16; }
-                        ++p;
-                    }
-                }
-            }
-            if (wtid == 0 && n_merges < A.log_cap) {                                           // debug line of :390-392 (ranks; labels at the end)
-                A.mlog.a[n_merges] = a; A.mlog.b[n_merges] = b; A.mlog.w[n_merges] = __uint_as_float(hd.hi);
-                A.mlog.edges_left[n_merges] = (unsigned)sm.misc[FM_EALIVE]; A.mlog.regions_left[n_merges] = (unsigned)sm.misc[FM_RALIVE];
-            }
-            named_bar(BAR_W1, kFastOwners);                                                    // W1: touched list complete
-            const int T = sm.misc[FM_TCOUNT];
-            WPROF(2);
+            LTRACE(wtid == 0, 2, (unsigned)clock());
+            // ---- B: the edges incident to a or b come from the two adjacency lists (thread i: entry i) ----
+            const unsigned la = sm.adj_len[a], lb = sm.adj_len[b], sa = sm.adj_start[a], sb = sm.adj_start[b];
+            const unsigned ca = sm.adj_cap[a], cb = sm.adj_cap[b];
+            const int T = (int)(la + lb);
             const bool overflow = T > kLeanMaxTouched;
-            const bool wide = T > 32;                                                          // more than one warp of touched edges
-            const bool mine = !overflow && wtid < T;
+            const bool wide = T > 32;                                                          // more than one warp of entries
+            if (wtid == 0) {
+                sm.key[hd.e] = kDeadKey64; sm.ab[hd.e] = kDeadKey;                             // the head edge leaves the map
+                const unsigned hb = hd.e >> 5;
+                sm.bdirty[hb % kLeanWorkerWarps] = 1u;
+                if (n_merges < A.log_cap) {                                                    // debug line of :390-392 (ranks; labels at the end)
+                    A.mlog.a[n_merges] = a; A.mlog.b[n_merges] = b; A.mlog.w[n_merges] = __uint_as_float(hd.hi);
+                    A.mlog.edges_left[n_merges] = (unsigned)sm.misc[FM_EALIVE]; A.mlog.regions_left[n_merges] = (unsigned)sm.misc[FM_RALIVE];
+                }
+            }
             // ---- C: duplicates (a,x)/(b,x) through a per-region mark; x's geometry; speculative colour deltas ----
             // Colour deltas are memoised per edge and speculated: while the fold runs, the edges whose stored delta does not
             // fit the GUESS of the merged region's colour vector (warp 1: Lab lattice point of the size-weighted mean) get
             // CIEDE2000 against the guess.  A wrong guess (about 1 merge in 10^3) re-evaluates after the fold.
-            unsigned e = 0, x = 0; bool side_a = false; unsigned long long okey = kDeadKey64;
+            unsigned e = 0, x = 0; bool side_a = false, mine = false; unsigned long long okey = kDeadKey64;
             bool live = false, need = false;
             float dc = 0.0f; float4 xcv, c4, n4, ocv;
-            if (ww == 0 || wide) {
-                if (mine) {
-                    e = sm.te_e[wtid]; okey = sm.key[e]; sm.te_key[wtid] = okey;
-                    const unsigned eab = sm.ab[e], ea = eab >> 16, eb = eab & 0xffffu;
-                    side_a = ea == a || eb == a;
-                    x = (ea == a || ea == b) ? eb : ea;
-                    const unsigned short old = atomicCAS(&sm.mark[x], (unsigned short)kNil16, (unsigned short)wtid);
-                    if (old != (unsigned short)kNil16) { sm.partner[wtid] = old; sm.partner[old] = (unsigned short)wtid; }
-                    xcv = __ldcg(R.cvec + x); c4 = __ldcg(R.centroid + x); n4 = __ldcg(R.normal + x); dc = __ldcg(A.E.dc + e);
-                    ocv = __ldcg(R.cvec + (side_a ? a : b));                                   // the colour vector the stored delta was computed with
+            const bool active = ww == 0 || wide;
+            if (active) {
+                if (!overflow && wtid < T) {
+                    e = __ldcg(pool + ((unsigned)wtid < la ? sa + (unsigned)wtid : sb + ((unsigned)wtid - la)));
+                    const unsigned eab = sm.ab[e];
+                    mine = e != hd.e && eab != kDeadKey;                                       // lists keep removed edges until they are rewritten
+                    if (mine) {
+                        okey = sm.key[e]; sm.te_key[wtid] = okey;
+                        const unsigned ea = eab >> 16, eb = eab & 0xffffu;
+                        side_a = ea == a || eb == a;
+                        x = (ea == a || ea == b) ? eb : ea;
+                        const unsigned short old = atomicCAS(&sm.mark[x], (unsigned short)kNil16, (unsigned short)wtid);
+                        if (old != (unsigned short)kNil16) { sm.partner[wtid] = old; sm.partner[old] = (unsigned short)wtid; }
+                        xcv = __ldcg(R.cvec + x); c4 = __ldcg(R.centroid + x); n4 = __ldcg(R.normal + x); dc = __ldcg(A.E.dc + e);
+                        ocv = __ldcg(R.cvec + (side_a ? a : b));                               // the colour vector the stored delta was computed with
+                    }
                 }
                 if (wide) named_bar(BAR_WB, kFastOwners); else __syncwarp();                   // WB1
             }
-            named_bar(BAR_G, 32 + kFastOwners);                                                // G: the guess of a's new colour vector
+            WPROF(2);
+            LTRACE(wtid == 0, 3, (unsigned)clock()); LTRACE(wtid == 0, 8, (unsigned)T);
+            if (wide) named_bar(BAR_G, 32 + kFastOwners); else if (active) named_bar(BAR_GN, 64);   // G: the guess of a's new colour vector
             const float4 guess = make_float4(sm.newgeo[10], sm.newgeo[11], sm.newgeo[12], 0.0f);
-            if (mine && (ww == 0 || wide)) {
+            if (mine) {
                 const unsigned q = sm.partner[wtid];
                 const bool dup = q != kNil16 && sm.te_key[q] < okey;                           // the earlier of (a,x), (b,x) survives
-                sm.mark[x] = (unsigned short)kNil16;
+                sm.mark[x] = (unsigned short)kNil16; sm.partner[wtid] = (unsigned short)kNil16;
                 live = !dup;
                 // the stored delta stays valid when the end that changes keeps its colour vector and the argument order
                 const bool same_cv = __float_as_uint(ocv.x) == __float_as_uint(guess.x) && __float_as_uint(ocv.y) == __float_as_uint(guess.y) &&
                                      __float_as_uint(ocv.z) == __float_as_uint(guess.z);
                 const bool reuse = same_cv && (side_a || ((b < x) == (a < x)));
                 need = live && !reuse;
-                if (need) dc = a < x ? colour_delta(ep.color_mode, guess, xcv) : colour_delta(ep.color_mode, xcv, guess);
+                if (need) { const bool af = a < x; dc = colour_delta(ep.color_mode, af ? guess : xcv, af ? xcv : guess); }   // ONE call site: lanes must not diverge around 800 instructions
             }
             WPROF(3);
-            named_bar(BAR_F, kFastThreads);                                                    // F: region a's new colour vector / centroid / normal
+            LTRACE(wtid == 0, 4, (unsigned)clock());
+            if (wide) named_bar(BAR_F, kFastThreads); else if (active) named_bar(BAR_FN, 128);  // F: region a's new colour vector / centroid / normal
             WPROF(4);
-            // ---- D: colour delta after a wrong guess, geometry delta, weight, classification, tie stamps ----
-            if (ww == 0 || wide) {
+            LTRACE(wtid == 0, 5, (unsigned)clock());
+            // ---- D: colour delta after a wrong guess, geometry delta, weight, classification, tie stamps, a's new list ----
+            // a's new adjacency list goes into a's block, else into b's, else into a fresh one twice the size (T bounds the survivors)
+            const bool fresh = ca < (unsigned)T && cb < (unsigned)T;
+            const unsigned ncap = fresh ? min(2u * (unsigned)T, 65535u) : (ca >= (unsigned)T ? ca : cb);
+            const unsigned dst = ca >= (unsigned)T ? sa : (cb >= (unsigned)T ? sb : pool_top);
+            const bool pool_ok = !fresh || pool_top + ncap <= A.pool_cap;
+            if (active) {
                 unsigned wbits = kDeadKey, nab = kDeadKey; int cls = FC_DUP; unsigned hs = kNil16;
                 const bool hit = newgeo_i[9] != 0;
+                // a's new adjacency list: in a's block, else in b's, else a fresh one twice the size (T bounds the survivors)
                 if (mine) {
                     const bool redo = !hit && live;                                            // wrong guess (rare): every survivor re-evaluates
                     if (redo) {
                         const float4 acv = make_float4(sm.newgeo[0], sm.newgeo[1], sm.newgeo[2], 0.0f);
-                        dc = a < x ? colour_delta(ep.color_mode, acv, xcv) : colour_delta(ep.color_mode, xcv, acv);
+                        const bool af = a < x;
+                        dc = colour_delta(ep.color_mode, af ? acv : xcv, af ? xcv : acv);
                     }
                     if (PROF && (redo || need)) atomicAdd(&sm.misc[FM_EVALS], (redo ? 1 : 0) + (need ? 1 : 0));
                     if (live) {
@@ -604,7 +661,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                         wbits = __float_as_uint(w_new);
                         const unsigned old_hi = (unsigned)(okey >> 32);
                         cls = wbits == old_hi ? FC_KEEP : (wbits > old_hi ? FC_FRONT : FC_BACK);
-                        if (cls != FC_KEEP) {                                                  // tie groups: same new weight, same side
+                        if (cls != FC_KEEP && wide) {                                          // tie groups: same new weight, same side
                             const unsigned hk = wbits | (cls == FC_FRONT ? 0x80000000u : 0u);
                             unsigned h = (hk * 2654435761u) >> 21;
                             while (true) {
@@ -616,13 +673,39 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                             hs = h;
                         }
                         A.E.dc[e] = dc;
-                    } else atomicAdd(&sm.misc[FM_ND], 1);
+                    } else if (wide) atomicAdd(&sm.misc[FM_ND], 1);
                     sm.res_w[wtid] = wbits; sm.cls[wtid] = (unsigned char)cls;
+                } else if (!overflow && wtid < T) { sm.res_w[wtid] = kDeadKey; sm.cls[wtid] = (unsigned char)FC_DUP; }   // a removed edge's entry
+                unsigned narrow_rank = 0, narrow_gsz = 1;
+                {   // survivors take consecutive places in a's new list
+                    const unsigned lm = __ballot_sync(kFull, live), mm = __ballot_sync(kFull, mine);
+                    int base = 0;
+                    if (wide) {
+                        const int leader = __ffs(lm) - 1;
+                        if (lm && lane == leader) base = atomicAdd(&sm.misc[FM_NLIVE], __popc(lm));
+                        base = __shfl_sync(kFull, base, leader < 0 ? 0 : leader);
+                    } else {
+                        if (lane == 0) { sm.misc[FM_NLIVE] = __popc(lm); sm.misc[FM_ND] = __popc(mm & ~lm); }
+                        // one warp holds every touched edge: tie groups by match, ranks by the old keys of the group's lanes
+                        const unsigned hk = (live && cls != FC_KEEP) ? (wbits | (cls == FC_FRONT ? 0x80000000u : 0u)) : (0xffffff00u | (unsigned)lane);
+                        unsigned grp = __match_any_sync(kFull, hk);
+                        narrow_gsz = (unsigned)__popc(grp);
+                        if (narrow_gsz > 1) {                                                  // (whole groups take this branch together)
+                            grp &= ~(1u << lane);
+                            while (grp) { const int q = __ffs(grp) - 1; grp &= grp - 1u; if (sm.te_key[(wtid & ~31) + q] < okey) ++narrow_rank; }
+                        }
+                    }
+                    if (live && pool_ok) A.adj_pool[dst + (unsigned)base + (unsigned)__popc(lm & ((1u << lane) - 1u))] = (unsigned short)e;
                 }
                 if (wide) named_bar(BAR_WB, kFastOwners); else __syncwarp();                   // WB2
                 if (mine) {
                     unsigned lo = (unsigned)okey;
-                    if (hs != kNil16) {
+                    if (!wide) {
+                        if (live && cls != FC_KEEP) {
+                            const int st = cls == FC_BACK ? counter + (int)narrow_rank : -(counter + (int)(narrow_gsz - 1 - narrow_rank));
+                            lo = (unsigned)st ^ 0x80000000u;
+                        }
+                    } else if (hs != kNil16) {
                         const unsigned gsz = sm.hcnt[hs];
                         unsigned rank = 0;
                         if (gsz > 1)                                                           // new arrivals keep their old relative order inside a tie group
@@ -635,25 +718,31 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                     }
                     sm.key[e] = live ? ((unsigned long long)wbits << 32) | lo : kDeadKey64;
                     sm.ab[e] = nab;
-                    sm.wdirty[(e % kFastOwners) >> 5] = 1;
+                    sm.bdirty[(e >> 5) % kLeanWorkerWarps] = 1u;
                 }
             }
             if (wtid == 0) {
                 if (overflow) sm.misc[FM_ERROR] = (int)kFastErrTouched;                        // the host falls back to merge_kernel
                 else {
                     if (counter > 0x7f000000 - T) sm.misc[FM_ERROR] = (int)kFastErrStamp;
+                    if (!pool_ok) sm.misc[FM_ERROR] = (int)kFastErrPool;
+                    else if (fresh) sm.misc[FM_POOL] = (int)(pool_top + ncap);
+                    sm.adj_start[a] = dst;
+                    sm.adj_len[a] = (unsigned short)sm.misc[FM_NLIVE]; sm.adj_cap[a] = (unsigned short)ncap; sm.adj_len[b] = 0; sm.adj_cap[b] = 0;
+                    sm.misc[FM_NLIVE] = 0;
                     sm.misc[FM_COUNTER] = counter + T;
                     sm.misc[FM_EALIVE] -= 1 + sm.misc[FM_ND]; sm.misc[FM_ND] = 0; sm.misc[FM_RALIVE] -= 1;
                     if (T > sm.misc[FM_MAXT]) sm.misc[FM_MAXT] = T;
                     sm.misc[FM_SUMT] += T; sm.misc[FM_MISS] += newgeo_i[9] ? 0 : 1;
                 }
-                sm.misc[FM_TCOUNT] = 0;
             }
             WPROF(5);
-            named_bar(BAR_W4, kFastOwners);                                                    // W4: new keys written
+            LTRACE(wtid == 0, 6, (unsigned)clock());
+            named_bar(BAR_W4, kFastOwners);                                                    // W4: new keys and a's list written
             WPROF(6);
+            LTRACE(wtid == 0, 7, (unsigned)clock());
             if (PROF && wtid == 0) { const int c_ = T <= 32 ? 0 : (T <= 128 ? 1 : 2); cls_cyc[c_] += (unsigned)clock() - t_top; cls_cnt[c_]++; }
-            ++n_merges;
+            ++n_merges; ++nm;
         }
 #undef WPROF
         LPROF_STORE(wtid == 0, 0, 8);
@@ -690,8 +779,8 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
 }
 
 // one frame: one CTA
-template <int SLOTS, bool PROF>
-__global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(const __grid_constant__ FastArgs A) { merge_lean_body<SLOTS, PROF>(A); }
+template <bool PROF>
+__global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(const __grid_constant__ FastArgs A) { merge_lean_body<PROF>(A); }
 
 // A batch of frames in ONE launch, CTA i replays frame i (f3ps_merge_batch).  Independent streams share at most 32 hardware
 // queues (CUDA_DEVICE_MAX_CONNECTIONS), so at most 32 single-CTA merge kernels ever overlap; one grid has no such limit.
@@ -699,7 +788,6 @@ __global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(const __gri
 constexpr int kFastBatchMax = 32764 / (int)sizeof(FastArgs) < 96 ? 32764 / (int)sizeof(FastArgs) : 96;
 struct FastBatch { FastArgs a[kFastBatchMax]; };
 static_assert(sizeof(FastBatch) <= 32764, "kernel parameter space");
-template <int SLOTS>
-__global__ void __launch_bounds__(kFastThreads, 1) merge_fast_batch_kernel(const __grid_constant__ FastBatch B) { merge_lean_body<SLOTS, false>(B.a[blockIdx.x]); }
+__global__ void __launch_bounds__(kFastThreads, 1) merge_fast_batch_kernel(const __grid_constant__ FastBatch B) { merge_lean_body<false>(B.a[blockIdx.x]); }
 
 } // namespace f3ps

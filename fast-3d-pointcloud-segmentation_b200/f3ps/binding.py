@@ -95,6 +95,7 @@ def lib():
         "f3ps_stage_ms": (C.c_int, [vp, C.c_int, C.POINTER(f32)]),
         "f3ps_launch_count": (i64, [vp]),
         "f3ps_merge_profile": (C.c_int, [vp, C.POINTER(C.c_uint64 * 32)]),
+        "f3ps_merge_trace": (C.c_int, [vp, i64, vp, i64]),
         "f3ps_expand_profile": (C.c_int, [vp, C.POINTER(C.c_uint64 * 8)]),
         "f3ps_test_rgb2lab": (C.c_int, [vp, vp, vp, i64]),
         "f3ps_test_lab_ciede00": (C.c_int, [vp, vp, vp, vp, i64]),
@@ -103,6 +104,7 @@ def lib():
         "f3ps_merge_batch": (C.c_int, [C.POINTER(vp), C.c_int, f32]),
         "f3ps_set_expand_sharing": (C.c_int, [vp, C.c_int, C.c_int]),
         "f3ps_eval_thresholds": (C.c_int, [vp, vp, i64, vp, i64, vp, C.c_int, vp, vp, vp]),
+        "f3ps_eval_label_pairs": (C.c_int, [vp, vp, vp, i64, C.c_int, C.c_int, vp, i64, vp]),
         "f3ps_slab_reset": (C.c_int, [vp]),
         "f3ps_slab_bbox": (C.c_int, [vp, vp]),
         "f3ps_slab_set_frame": (C.c_int, [vp, vp]),
@@ -130,9 +132,9 @@ EXPORTED = ["f3ps_create", "f3ps_destroy", "f3ps_last_error", "f3ps_version", "f
             "f3ps_get_voxel_neighbors", "f3ps_get_voxel_normals", "f3ps_get_seeds", "f3ps_get_voxel_labels",
             "f3ps_get_supervoxels", "f3ps_get_supervoxel_voxels", "f3ps_get_adjacency", "f3ps_get_edges", "f3ps_get_cdf",
             "f3ps_get_merge_log", "f3ps_get_state_regions", "f3ps_get_state_edges", "f3ps_get_labeled_cloud", "f3ps_get_region_mean_color",
-            "f3ps_get_voxel_segments_device", "f3ps_stage_ms", "f3ps_launch_count", "f3ps_merge_profile", "f3ps_expand_profile", "f3ps_test_rgb2lab",
+            "f3ps_get_voxel_segments_device", "f3ps_stage_ms", "f3ps_launch_count", "f3ps_merge_profile", "f3ps_merge_trace", "f3ps_expand_profile", "f3ps_test_rgb2lab",
             "f3ps_test_lab_ciede00", "f3ps_test_rgb_eucl", "f3ps_test_sort_pairs",
-            "f3ps_merge_batch", "f3ps_set_expand_sharing", "f3ps_eval_thresholds", "f3ps_slab_reset", "f3ps_slab_bbox", "f3ps_slab_set_frame", "f3ps_slab_keys", "f3ps_slab_route", "f3ps_slab_array",
+            "f3ps_merge_batch", "f3ps_set_expand_sharing", "f3ps_eval_thresholds", "f3ps_eval_label_pairs", "f3ps_slab_reset", "f3ps_slab_bbox", "f3ps_slab_set_frame", "f3ps_slab_keys", "f3ps_slab_route", "f3ps_slab_array",
             "f3ps_slab_set_voxels", "f3ps_slab_expand_begin", "f3ps_slab_expand_sweep", "f3ps_slab_expand_round_end",
             "f3ps_slab_expand_end"]
 
@@ -266,6 +268,19 @@ class Segmenter:
                                    for i, k in enumerate(["T<=32", "T<=128", "T>128"])},
                     "guess_misses": v[24], "ciede_evals": v[25], "sum_T": v[27]}
         return dict(zip(["argmin", "fold", "order", "delta", "stamps", "wait_scan", "sum_T", "fold_tail"], v[:8]))
+
+    def merge_trace(self, first=None):
+        """first given: set the window for the next merge (kernel choice 4).  Else: the recorded window as a [256, 32] array of
+        SM clock values: worker thread 0: 0 loop top, 1 rescan done, 2 head known, 3 entries read / marks set, 4 colour deltas
+        done, 5 after F, 6 weights + stamps done, 7 after W4, 8 = adjacency entries read; covariance warp: 12 head known,
+        13 voxels fetched, 14 folded, 15 eigen-solve done, 21 = voxels of b; mean warp: 16 head known, 17 guess published,
+        18 voxels fetched, 19 folded, 20 Lab done."""
+        if first is not None:
+            self._chk(self.L.f3ps_merge_trace(self.h, int(first), None, 0))
+            return None
+        out = np.zeros((256, 32), np.uint32)
+        self._chk(self.L.f3ps_merge_trace(self.h, 0, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
 
     def expand_profile(self):
         a = (C.c_uint64 * 8)()

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <limits>
 #include <stdexcept>
 
 #include "supervoxel_clustering/clustering.h"
@@ -54,7 +55,7 @@ void SupervoxelClustering<PointT>::extract(std::map<uint32_t, typename pcl::Supe
         sv->centroid_.x = cen[3 * s]; sv->centroid_.y = cen[3 * s + 1]; sv->centroid_.z = cen[3 * s + 2];
         sv->centroid_.rgba = ((uint32_t)rgb[3 * s] << 16) | ((uint32_t)rgb[3 * s + 1] << 8) | (uint32_t)rgb[3 * s + 2];
         sv->normal_.normal_x = nrm[4 * s]; sv->normal_.normal_y = nrm[4 * s + 1]; sv->normal_.normal_z = nrm[4 * s + 2];
-        sv->normal_.curvature = 0.0f;
+        sv->normal_.curvature = nrm[4 * s + 3];
         const size_t m = (size_t)(off[s + 1] - off[s]);
         sv->voxels_->resize(m); sv->normals_->resize(m);
         for (size_t k = 0; k < m; ++k) {
@@ -168,17 +169,17 @@ template <> void copyPointCloud(const PointCloud<PointXYZRGBA>& in, PointCloud<P
 ClusteringState::ClusteringState(ClusteringT s, WeightMapT w) { set_segments(s); set_weight_map(w); }
 
 // ---------------------------------------------------------------------------------------------------
-std::array<uint8_t, 3> ColorUtilities::get_glasbey(uint32_t label) {
-    // deterministic distinct-colour palette (golden-angle hue walk); pcl::GlasbeyLUT's table is not reproduced
-    const uint32_t k = label % 256u;
-    const float h = std::fmod(k * 0.61803398875f, 1.0f), s = 0.55f + 0.45f * ((k * 7u) % 5u) / 4.0f, v = 0.6f + 0.4f * ((k * 3u) % 4u) / 3.0f;
-    const float c = v * s, hp = h * 6.0f, x = c * (1.0f - std::fabs(std::fmod(hp, 2.0f) - 1.0f)), m = v - c;
-    float r = 0, g = 0, b = 0;
-    if (hp < 1) { r = c; g = x; } else if (hp < 2) { r = x; g = c; } else if (hp < 3) { g = c; b = x; }
-    else if (hp < 4) { g = x; b = c; } else if (hp < 5) { r = x; b = c; } else { r = c; b = x; }
-    return {(uint8_t)((r + m) * 255.0f), (uint8_t)((g + m) * 255.0f), (uint8_t)((b + m) * 255.0f)};
+// 256 maximally distinct colours by the construction of Glasbey et al. (greedy maximisation of the minimum CIE76 distance over
+// an 18^3 sRGB lattice, 15 < L* < 95; generated offline).  pcl::GlasbeyLUT's own table is not part of /root/reference.
+static const uint8_t kGlasbey[256 * 3] = {75,180,75,0,0,255,255,0,90,30,135,210,255,165,0,75,45,15,255,120,255,255,225,210,0,255,255,45,0,120,225,255,0,0,255,30,30,120,105,165,90,135,180,60,0,240,240,135,30,45,75,135,120,0,0,105,255,210,0,255,225,195,255,255,135,135,210,0,135,30,75,0,255,0,0,150,210,165,135,0,45,150,135,105,0,255,180,135,210,240,150,105,210,150,180,0,255,180,120,90,0,195,15,45,30,165,255,105,75,15,75,135,135,165,240,210,15,165,0,165,165,90,60,255,135,210,30,60,135,0,255,120,45,195,0,120,150,75,0,135,165,180,90,255,255,105,0,255,0,210,195,120,30,90,45,60,180,255,165,0,135,75,210,150,165,255,90,75,225,75,120,210,195,135,90,90,90,150,255,0,0,180,180,0,195,150,135,0,105,0,135,255,150,165,255,210,180,60,60,120,0,105,60,195,105,30,0,105,90,30,165,180,180,45,75,255,180,255,240,105,45,135,180,0,30,225,240,255,0,90,135,180,135,75,255,135,75,0,180,240,120,255,210,195,135,210,210,240,90,120,105,165,135,30,255,165,75,90,195,75,165,150,105,105,255,180,165,150,195,90,75,105,60,120,30,75,135,210,0,225,240,195,60,90,195,0,75,90,165,0,90,210,45,225,135,75,0,105,240,135,150,195,255,0,225,255,210,90,75,90,165,0,225,120,150,240,150,255,255,30,135,255,90,195,135,165,135,240,0,45,120,90,120,105,135,135,90,105,15,255,165,210,105,210,135,255,210,120,0,75,45,45,60,15,75,165,135,135,120,255,225,195,210,255,180,75,90,60,120,195,90,210,0,45,195,195,225,150,0,45,150,225,60,15,120,150,30,105,255,75,90,15,30,225,135,105,180,180,90,165,150,210,255,180,255,180,195,225,150,75,150,150,15,195,210,45,75,180,135,0,105,0,150,240,135,30,45,45,45,120,60,45,195,195,165,135,15,0,105,225,225,30,180,210,0,30,225,120,90,60,195,150,135,90,210,75,255,225,90,0,135,0,195,75,135,120,120,210,255,30,255,180,150,255,210,0,165,180,240,120,255,195,45,150,45,150,195,135,180,195,210,0,90,165,90,45,30,75,255,210,165,195,225,210,255,90,165,90,150,195,150,135,135,195,255,195,195,255,75,60,90,75,195,120,255,135,195,180,180,90,30,15,105,30,255,0,165,195,120,120,165,45,240,0,105,195,165,165,30,45,30,105,120,75,240,165,45,45,105,165,180,255,240,165,180,150,60,0,180,105,30,0,150,255,240,0,195,210,90,135,135,75,210,90,105,150,105,0,210,0,90,75,75,120,15,105,60,75,60,45,120,60,105,135,255,180,90,90,60,15,255,150,75,60,75,150,180,120,255,165,180,120,255,120,90,60,0,210,165,120,0,210,195,255,90,105,75,105,120,0,165,15,105,0,15,255,90,255,60,150,150,120,225,195,240,75,210,90,120,180,165,120,90,75,60,150,210,135,75,240,240,75,75,135,90,45,75,210,60,30,30,135,75,90,105,225,0,150,60,195,45,225,75,210,90,240,90,165,255,195,180,0,105,75,75,180,240,255,75,120,45,165,165,120,15,135,45,0,45,60,225,90,45,180,150,180,150,165,210,15,75,135,135,210,75,75,0,105,180,15,0,255,195,240,255,120,90,150,105,180,180,30,75,105,90,210,0,255,225,0,210,105,15,225,15,150,60,30};
+
+uint8_t* ColorUtilities::get_glasbey(uint32_t label) {
+    uint8_t* out = new uint8_t[3];
+    const uint8_t* c = kGlasbey + 3 * (label % 256u);
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2];
+    return out;
 }
-std::array<float, 3> ColorUtilities::mean_color(SupervoxelT::Ptr s) {
+float* ColorUtilities::mean_color(SupervoxelT::Ptr s) {
     // one supervoxel as a one-node graph: the device computes the running mean exactly as the merge loop does
     f3ps::Handle& h = f3ps::shared_handle();
     const size_t n = s->voxels_->size();
@@ -186,42 +187,176 @@ std::array<float, 3> ColorUtilities::mean_color(SupervoxelT::Ptr s) {
     for (size_t i = 0; i < n; ++i) { const PointT& p = s->voxels_->points[i]; xyz[3 * i] = p.x; xyz[3 * i + 1] = p.y; xyz[3 * i + 2] = p.z; rgba[i] = p.rgba; }
     const uint32_t label = 1; const int64_t off[2] = {0, (int64_t)n}; const float cen[3] = {0, 0, 0}, nrm[3] = {0, 0, 1};
     h.check(f3ps_set_graph(h.get(), (int64_t)n, xyz.data(), rgba.data(), 1, &label, off, cen, nrm, 0, nullptr));
-    float rgb[3] = {0, 0, 0};
+    float* rgb = new float[3]();
     h.check(f3ps_get_region_mean_color(h.get(), 0, rgb));
-    return {rgb[0], rgb[1], rgb[2]};
+    return rgb;
 }
-std::array<float, 3> ColorUtilities::rgb2lab(const float rgb[3]) {
-    float lab[3]; f3ps::Handle& h = f3ps::shared_handle();
-    h.check(f3ps_test_rgb2lab(h.get(), rgb, lab, 1));
-    return {lab[0], lab[1], lab[2]};
+// cv::cvtColor(CV_32FC3, COLOR_Lab2RGB) stand-in (src/color_utilities.cpp:52-69, code CV_Lab2RGB): the analytic CIE L*a*b* ->
+// linear -> sRGB chain in float.  Only convert_test calls it (print-only in the reference); within 0.5 / 255 of OpenCV 4.13.
+static void lab2rgb_host(const float lab[3], float rgb[3]) {
+    const float fy = (lab[0] + 16.0f) / 116.0f, fx = fy + lab[1] / 500.0f, fz = fy - lab[2] / 200.0f;
+    auto finv = [](float t) { return t > 6.0f / 29.0f ? t * t * t : (t - 16.0f / 116.0f) / 7.787f; };
+    const float X = 0.950456f * finv(fx), Y = finv(fy), Z = 1.088754f * finv(fz);
+    const float lin[3] = {3.240479f * X - 1.53715f * Y - 0.498535f * Z, -0.969256f * X + 1.875991f * Y + 0.041556f * Z,
+                          0.055648f * X - 0.204043f * Y + 1.057311f * Z};
+    for (int k = 0; k < 3; ++k) {
+        float v = std::min(1.0f, std::max(0.0f, lin[k]));
+        rgb[k] = v <= 0.0031308f ? 12.92f * v : 1.055f * std::pow(v, 1.0f / 2.4f) - 0.055f;
+    }
 }
-float ColorUtilities::lab_ciede00(const float lab1[3], const float lab2[3]) {
+float* ColorUtilities::color_conversion(float in[3], int code) {
+    float* out = new float[3]();
+    if (code == 0) {
+        f3ps::Handle& h = f3ps::shared_handle();
+        h.check(f3ps_test_rgb2lab(h.get(), in, out, 1));            // OpenCV's LUT + trilinear interpolation, bit-exact on the device
+    } else lab2rgb_host(in, out);
+    return out;
+}
+float* ColorUtilities::rgb2lab(float rgb[3]) { return color_conversion(rgb, 0); }            // the kernel takes 0..255 as the reference's caller passes it (:151-160)
+float* ColorUtilities::lab2rgb(float lab[3]) {
+    float* out = color_conversion(lab, 1);
+    for (int k = 0; k < 3; ++k) out[k] *= 255.0f;                                             // :169-178
+    return out;
+}
+// lab_ciede00 with weights other than 1 (nothing in the reference passes any): the formula of src/color_utilities.cpp:190-294 on the host
+static float ciede00_weighted(const float l1[3], const float l2[3], double kL, double kC, double kH) {
+    const double PI = 3.14159265358979323846;
+    const double Cab = ((double)std::sqrt(l1[1] * l1[1] + l1[2] * l1[2]) + (double)std::sqrt(l2[1] * l2[1] + l2[2] * l2[2])) / 2.0;
+    const double G = 0.5 * (1.0 - std::sqrt(std::pow(Cab, 7.0) / (std::pow(Cab, 7.0) + std::pow(25.0, 7.0))));
+    const double ap1 = (1.0 + G) * l1[1], ap2 = (1.0 + G) * l2[1];
+    const double Cp1 = std::sqrt(ap1 * ap1 + (double)(l1[2] * l1[2])), Cp2 = std::sqrt(ap2 * ap2 + (double)(l2[2] * l2[2]));
+    const double Cpp = Cp1 * Cp2;
+    double hp1 = std::atan2((double)l1[2], ap1); if (hp1 < 0) hp1 += 2 * PI; if (std::fabs(ap1) + std::fabs(l1[2]) == 0) hp1 = 0;
+    double hp2 = std::atan2((double)l2[2], ap2); if (hp2 < 0) hp2 += 2 * PI; if (std::fabs(ap2) + std::fabs(l2[2]) == 0) hp2 = 0;
+    const double dL = (double)(l2[0] - l1[0]), dC = Cp2 - Cp1;
+    double dhp = hp2 - hp1; if (dhp > PI) dhp -= 2 * PI; if (dhp < -PI) dhp += 2 * PI; if (Cpp == 0) dhp = 0;
+    const double dH = 2.0 * std::sqrt(Cpp) * std::sin(dhp / 2.0);
+    const double Lp = (double)(l1[0] + l2[0]) / 2.0, Cp = (Cp1 + Cp2) / 2.0;
+    double hp = (hp1 + hp2) / 2.0; if (std::fabs(hp1 - hp2) > PI) hp -= PI; if (hp < 0) hp += 2 * PI; if (Cpp == 0) hp = hp1 + hp2;
+    const double Lpm = (Lp - 50.0) * (Lp - 50.0);
+    const double SL = 1.0 + 0.015 * Lpm / std::sqrt(20.0 + Lpm), SC = 1.0 + 0.045 * Cp;
+    const double T = 1.0 - 0.17 * std::cos(hp - PI / 6.0) + 0.24 * std::cos(2.0 * hp) + 0.32 * std::cos(3.0 * hp + PI / 30.0) - 0.20 * std::cos(4.0 * hp - 63.0 * PI / 180.0);
+    const double SH = 1.0 + 0.015 * Cp * T;
+    const double dth = (30.0 * PI / 180.0) * std::exp(-std::pow((180.0 / PI * hp - 275.0) / 25.0, 2.0));
+    const double RC = 2.0 * std::sqrt(std::pow(Cp, 7.0) / (std::pow(Cp, 7.0) + std::pow(25.0, 7.0)));
+    const double RT = -std::sin(2.0 * dth) * RC;
+    const double tL = dL / (kL * SL), tC = dC / (kC * SC), tH = dH / (kH * SH);
+    return (float)std::sqrt(tL * tL + tC * tC + tH * tH + RT * tC * tH);
+}
+float ColorUtilities::lab_ciede00(float lab1[3], float lab2[3], double kL, double kC, double kH) {
+    if (kL != 1.0 || kC != 1.0 || kH != 1.0) return ciede00_weighted(lab1, lab2, kL, kC, kH);
     float d; f3ps::Handle& h = f3ps::shared_handle();
     h.check(f3ps_test_lab_ciede00(h.get(), lab1, lab2, &d, 1));
     return d;
 }
-float ColorUtilities::rgb_eucl(const float rgb1[3], const float rgb2[3]) {
+float ColorUtilities::rgb_eucl(float rgb1[3], float rgb2[3]) {
     float d; f3ps::Handle& h = f3ps::shared_handle();
     h.check(f3ps_test_rgb_eucl(h.get(), rgb1, rgb2, &d, 1));
     return d;
 }
-float ColorUtilities::rgb_test() {
-    const float c[8][3] = {{0, 0, 0}, {255, 255, 255}, {255, 0, 0}, {0, 255, 0}, {0, 255, 0}, {255, 0, 255}, {100, 20, 35}, {104, 20, 32}};
+void ColorUtilities::rgb_test() {                                    // src/color_utilities.cpp:324-349: prints value and expectation
+    float c[8][3] = {{0, 0, 0}, {255, 255, 255}, {255, 0, 0}, {0, 255, 0}, {0, 255, 0}, {255, 0, 255}, {100, 20, 35}, {104, 20, 32}};
     const int pairs[7][2] = {{0, 0}, {0, 1}, {1, 1}, {0, 2}, {3, 0}, {4, 5}, {6, 7}};
     const float expect[7] = {0, 441.672943f, 0, 255, 255, 441.672943f, 5};
-    float err = 0;
-    for (int i = 0; i < 7; ++i) err = std::max(err, std::fabs(rgb_eucl(c[pairs[i][0]], c[pairs[i][1]]) - expect[i]));
-    return err;
+    for (int i = 0; i < 7; ++i) std::printf("RGB distance test %d: %f (should be %f)\n", i + 1, rgb_eucl(c[pairs[i][0]], c[pairs[i][1]]), expect[i]);
 }
-float ColorUtilities::lab_test() {
-    // a few rows of the Sharma-Wu-Dalal table (the full table is exercised by tests/)
-    const float v[4][7] = {{50.0000f, 2.6772f, -79.7751f, 50.0000f, 0.0000f, -82.7485f, 2.0425f},
-                           {50.0000f, 2.5000f, 0.0000f, 73.0000f, 25.0000f, -18.0000f, 27.1492f},
-                           {60.2574f, -34.0099f, 36.2677f, 60.4626f, -34.1751f, 39.4387f, 1.2644f},
-                           {2.0776f, 0.0795f, -1.1350f, 0.9033f, -0.0636f, -0.5514f, 0.9082f}};
+float ColorUtilities::ciede00_test(float L1, float a1, float b1, float L2, float a2, float b2, float result) {
+    float l1[3] = {L1, a1, b1}, l2[3] = {L2, a2, b2};
+    const float d = lab_ciede00(l1, l2);
+    std::printf("CIEDE00 test: %f (should be %f)\n", d, result);
+    return std::fabs(d - result);
+}
+void ColorUtilities::lab_test() {                                    // :354-460, the Sharma-Wu-Dalal table (34 pairs)
+    static const float v[34][7] = {
+        {50.0000f, 2.6772f, -79.7751f, 50.0000f, 0.0000f, -82.7485f, 2.0425f}, {50.0000f, 3.1571f, -77.2803f, 50.0000f, 0.0000f, -82.7485f, 2.8615f},
+        {50.0000f, 2.8361f, -74.0200f, 50.0000f, 0.0000f, -82.7485f, 3.4412f}, {50.0000f, -1.3802f, -84.2814f, 50.0000f, 0.0000f, -82.7485f, 1.0000f},
+        {50.0000f, -1.1848f, -84.8006f, 50.0000f, 0.0000f, -82.7485f, 1.0000f}, {50.0000f, -0.9009f, -85.5211f, 50.0000f, 0.0000f, -82.7485f, 1.0000f},
+        {50.0000f, 0.0000f, 0.0000f, 50.0000f, -1.0000f, 2.0000f, 2.3669f}, {50.0000f, -1.0000f, 2.0000f, 50.0000f, 0.0000f, 0.0000f, 2.3669f},
+        {50.0000f, 2.4900f, -0.0010f, 50.0000f, -2.4900f, 0.0009f, 7.1792f}, {50.0000f, 2.4900f, -0.0010f, 50.0000f, -2.4900f, 0.0010f, 7.1792f},
+        {50.0000f, 2.4900f, -0.0010f, 50.0000f, -2.4900f, 0.0011f, 7.2195f}, {50.0000f, 2.4900f, -0.0010f, 50.0000f, -2.4900f, 0.0012f, 7.2195f},
+        {50.0000f, -0.0010f, 2.4900f, 50.0000f, 0.0009f, -2.4900f, 4.8045f}, {50.0000f, -0.0010f, 2.4900f, 50.0000f, 0.0010f, -2.4900f, 4.8045f},
+        {50.0000f, -0.0010f, 2.4900f, 50.0000f, 0.0011f, -2.4900f, 4.7461f}, {50.0000f, 2.5000f, 0.0000f, 50.0000f, 0.0000f, -2.5000f, 4.3065f},
+        {50.0000f, 2.5000f, 0.0000f, 73.0000f, 25.0000f, -18.0000f, 27.1492f}, {50.0000f, 2.5000f, 0.0000f, 61.0000f, -5.0000f, 29.0000f, 22.8977f},
+        {50.0000f, 2.5000f, 0.0000f, 56.0000f, -27.0000f, -3.0000f, 31.9030f}, {50.0000f, 2.5000f, 0.0000f, 58.0000f, 24.0000f, 15.0000f, 19.4535f},
+        {50.0000f, 2.5000f, 0.0000f, 50.0000f, 3.1736f, 0.5854f, 1.0000f}, {50.0000f, 2.5000f, 0.0000f, 50.0000f, 3.2972f, 0.0000f, 1.0000f},
+        {50.0000f, 2.5000f, 0.0000f, 50.0000f, 1.8634f, 0.5757f, 1.0000f}, {50.0000f, 2.5000f, 0.0000f, 50.0000f, 3.2592f, 0.3350f, 1.0000f},
+        {60.2574f, -34.0099f, 36.2677f, 60.4626f, -34.1751f, 39.4387f, 1.2644f}, {63.0109f, -31.0961f, -5.8663f, 62.8187f, -29.7946f, -4.0864f, 1.2630f},
+        {61.2901f, 3.7196f, -5.3901f, 61.4292f, 2.2480f, -4.9620f, 1.8731f}, {35.0831f, -44.1164f, 3.7933f, 35.0232f, -40.0716f, 1.5901f, 1.8645f},
+        {22.7233f, 20.0904f, -46.6940f, 23.0331f, 14.9730f, -42.5619f, 2.0373f}, {36.4612f, 47.8580f, 18.3852f, 36.2715f, 50.5065f, 21.2231f, 1.4146f},
+        {90.8027f, -2.0831f, 1.4410f, 91.1528f, -1.6435f, 0.0447f, 1.4441f}, {90.9257f, -0.5406f, -0.9208f, 88.6381f, -0.8985f, -0.7239f, 1.5381f},
+        {6.7747f, -0.2908f, -2.4247f, 5.8714f, -0.0985f, -2.2286f, 0.6377f}, {2.0776f, 0.0795f, -1.1350f, 0.9033f, -0.0636f, -0.5514f, 0.9082f}};
     float err = 0;
-    for (int i = 0; i < 4; ++i) err = std::max(err, std::fabs(lab_ciede00(v[i], v[i] + 3) - v[i][6]));
-    return err;
+    for (int i = 0; i < 34; ++i) err = std::max(err, ciede00_test(v[i][0], v[i][1], v[i][2], v[i][3], v[i][4], v[i][5], v[i][6]));
+    std::printf("CIEDE00 max error: %f\n", err);
+}
+void ColorUtilities::convert_test() {                                // :465-499: RGB -> Lab -> RGB round trip on four colours, printed
+    float cols[4][3] = {{123, 10, 200}, {0, 0, 0}, {255, 255, 255}, {255, 255, 0}};
+    for (int i = 0; i < 4; ++i) {
+        float* lab = rgb2lab(cols[i]);
+        float* back = lab2rgb(lab);
+        std::printf("RGB (%g, %g, %g) -> Lab (%f, %f, %f) -> RGB (%f, %f, %f)\n", cols[i][0], cols[i][1], cols[i][2], lab[0], lab[1], lab[2], back[0], back[1], back[2]);
+        delete[] lab; delete[] back;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Testing (src/testing.cpp): pairs by exact xyz on the host, contingency table + scores through f3ps_eval_label_pairs
+void Testing::init_performance() { precision = recall = fscore = voi = wov = fpr = fnr = -1; }
+labelMapT Testing::label_map(PointLCloudT::Ptr in) {                 // :62-82: one sub-cloud per label, renumbered 0..L-1 in ascending label order
+    std::map<uint32_t, PointLCloudT::Ptr> by_label;
+    for (const PointLT& p : in->points) {
+        auto it = by_label.find(p.label);
+        if (it == by_label.end()) it = by_label.insert(std::make_pair(p.label, PointLCloudT::Ptr(new PointLCloudT()))).first;
+        it->second->push_back(p);
+    }
+    labelMapT out; uint32_t k = 0;
+    for (auto& kv : by_label) out[k++] = kv.second;
+    return out;
+}
+void Testing::compute_intersections() {
+    // dense labels in ascending label order for both clouds; truth points indexed by xyz (compareXYZ: -0 == +0, as operator<)
+    std::map<uint32_t, uint32_t> sdense, tdense;
+    for (const PointLT& p : segm->points) sdense[p.label] = 0;
+    for (const PointLT& p : truth->points) tdense[p.label] = 0;
+    uint32_t ns = 0, nt = 0;
+    for (auto& kv : sdense) kv.second = ns++;
+    for (auto& kv : tdense) kv.second = nt++;
+    std::map<PointLT, uint32_t, compareXYZ> where;
+    std::vector<uint64_t> tsizes(nt, 0);
+    for (const PointLT& p : truth->points) { const uint32_t j = tdense[p.label]; where.insert(std::make_pair(p, j)); tsizes[j]++; }
+    std::vector<uint32_t> sl(segm->size()), tl(segm->size());
+    for (size_t i = 0; i < segm->size(); ++i) {
+        const PointLT& p = segm->points[i];
+        sl[i] = sdense[p.label];
+        auto it = where.find(p);
+        tl[i] = it == where.end() ? nt : it->second;
+    }
+    f3ps::Handle& h = f3ps::shared_handle();
+    f3ps_performance pf;
+    h.check(f3ps_eval_label_pairs(h.get(), sl.data(), tl.data(), (int64_t)sl.size(), (int32_t)ns, (int32_t)nt, tsizes.data(), (int64_t)truth->size(), &pf));
+    precision = pf.precision; recall = pf.recall; fscore = pf.fscore; voi = pf.voi; wov = pf.wov; fpr = pf.fpr; fnr = pf.fnr;
+}
+Testing::Testing(PointLCloudT::Ptr s, PointLCloudT::Ptr t) { is_set_segm = false; is_set_truth = false; init_performance(); set_segm(s); set_truth(t); }
+void Testing::set_segm(PointLCloudT::Ptr s) {
+    if (s->empty()) throw std::invalid_argument("The pointcloud to be set as 'segm' cannot be empty");
+    segm = s; init_performance(); segm_labels = label_map(s); is_set_segm = true;
+    if (is_set_truth) compute_intersections();
+}
+void Testing::set_truth(PointLCloudT::Ptr t) {
+    if (t->empty()) throw std::invalid_argument("The pointcloud to be set as 'truth' cannot be empty");
+    truth = t; init_performance(); truth_labels = label_map(t); is_set_truth = true;
+    if (is_set_segm) compute_intersections();
+}
+float Testing::eval_precision() { return precision; }
+float Testing::eval_recall() { return recall; }
+float Testing::eval_fscore() { return fscore; }
+float Testing::eval_voi() { return voi; }
+float Testing::eval_wov() { return wov; }
+float Testing::eval_fpr() { return fpr; }
+float Testing::eval_fnr() { return fnr; }
+performanceSet Testing::eval_performance() {
+    performanceSet p; p.voi = voi; p.precision = precision; p.recall = recall; p.fscore = fscore; p.wov = wov; p.fpr = fpr; p.fnr = fnr;
+    return p;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -288,7 +423,9 @@ void Clustering::pull_state(bool merged) {
         WeightMapT wm;
         std::vector<size_t> ord(E);
         for (size_t i = 0; i < E; ++i) ord[i] = i;
-        std::stable_sort(ord.begin(), ord.end(), [&](size_t x, size_t y) { return w[x] < w[y]; });
+        // NaN weights (degenerate regions) order as +inf, as on the device: `<` alone is not a strict weak order with NaNs
+        auto wkey = [&](size_t i) { return std::isnan(w[i]) ? std::numeric_limits<float>::infinity() : w[i]; };
+        std::stable_sort(ord.begin(), ord.end(), [&](size_t x, size_t y) { return wkey(x) < wkey(y); });
         for (size_t i : ord) wm.insert(wm.end(), WeightedPairT(w[i], std::make_pair(ab[2 * i], ab[2 * i + 1])));
         initial_state.set_weight_map(wm);
         lambda = n.lambda;
@@ -394,15 +531,17 @@ PointLCloudT::Ptr Clustering::get_labeled_cloud() const {
     return out;
 }
 PointCloudT::Ptr Clustering::get_colored_cloud() const { return label2color(get_labeled_cloud()); }
+void Clustering::test_all() const { ColorUtilities::rgb_test(); ColorUtilities::lab_test(); ColorUtilities::convert_test(); }
 
 PointCloudT::Ptr Clustering::label2color(PointLCloudT::Ptr label_cloud) {
     PointCloudT::Ptr out(new PointCloudT());
     out->resize(label_cloud->size());
     for (size_t i = 0; i < label_cloud->size(); ++i) {
         const PointLT& p = label_cloud->points[i];
-        const std::array<uint8_t, 3> c = ColorUtilities::get_glasbey(p.label);
+        uint8_t* c = ColorUtilities::get_glasbey(p.label);
         PointT& q = out->points[i];
         q.x = p.x; q.y = p.y; q.z = p.z; q.rgba = 0; q.r = c[0]; q.g = c[1]; q.b = c[2];
+        delete[] c;
     }
     return out;
 }

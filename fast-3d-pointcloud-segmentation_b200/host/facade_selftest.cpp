@@ -38,8 +38,23 @@ int main(int argc, char** argv) {
         try { c.set_bins_num(-1); } catch (const std::invalid_argument&) { threw = true; }
         CHECK(threw, "set_bins_num(-1) must throw std::invalid_argument");
     }
-    CHECK(ColorUtilities::rgb_test() == 0.0f, "rgb_eucl known answers");
-    CHECK(ColorUtilities::lab_test() < 1e-4f, "CIEDE2000 known answers");
+    {   // ColorUtilities with the reference's signatures (float* results are new[]-allocated, as there)
+        float c1[3] = {0, 0, 0}, c2[3] = {255, 255, 255}, c3[3] = {100, 20, 35}, c4[3] = {104, 20, 32};
+        CHECK(ColorUtilities::rgb_eucl(c1, c2) == 441.672943f && ColorUtilities::rgb_eucl(c3, c4) == 5.0f, "rgb_eucl known answers");
+        float l1[3] = {50.0000f, 2.6772f, -79.7751f}, l2[3] = {50.0000f, 0.0000f, -82.7485f};
+        CHECK(std::fabs(ColorUtilities::lab_ciede00(l1, l2) - 2.0425f) < 1e-4f, "CIEDE2000 known answer");
+        CHECK(std::fabs(ColorUtilities::lab_ciede00(l1, l2, 2.0, 1.0, 1.0) - ColorUtilities::lab_ciede00(l1, l2)) < 1e-4f, "kL only scales the (zero) lightness term here");
+        float rgb[3] = {123, 10, 200};
+        float* lab = ColorUtilities::rgb2lab(rgb);
+        CHECK(lab[0] == 35.113525390625f && lab[1] == 69.984375f && lab[2] == -71.28125f, "rgb2lab = OpenCV's LUT value (SURVEY Appendix F)");
+        float* back = ColorUtilities::lab2rgb(lab);
+        CHECK(std::fabs(back[0] - 123) < 1.0f && std::fabs(back[1] - 10) < 1.0f && std::fabs(back[2] - 200) < 1.0f, "lab2rgb round trip");
+        delete[] lab; delete[] back;
+        uint8_t* g0 = ColorUtilities::get_glasbey(7); uint8_t* g1 = ColorUtilities::get_glasbey(7 + 256);
+        CHECK(g0[0] == g1[0] && g0[1] == g1[1] && g0[2] == g1[2], "glasbey wraps at 256");
+        delete[] g0; delete[] g1;
+        Clustering().test_all();                                      // prints, as the reference's does
+    }
 
     // (a) fused path
     f3ps::Handle h(0);
@@ -113,6 +128,38 @@ int main(int argc, char** argv) {
         bool threw = false;
         try { segmentation.all_thresh(truth, 0.5f, 1.5f, 0.1f); } catch (const std::out_of_range&) { threw = true; }
         CHECK(threw, "all_thresh outside [0,1] must throw std::out_of_range (src/clustering.cpp:694-698)");
+    }
+    {   // Testing(segm, truth) == the fused sweep's score at the same threshold; label2color / color2label round trip
+        segmentation.cluster(thr);
+        PointLCloudT::Ptr seg = segmentation.get_labeled_cloud();
+        PointLCloudT::Ptr truth(new PointLCloudT());
+        pcl::PointCloud<pcl::PointXYZRGBA>::Ptr vc = super.getVoxelCentroidCloud();
+        std::vector<uint32_t> tl(vc->size());
+        for (size_t v = 0; v < vc->size(); ++v) {
+            PointLT p; p.x = vc->points[v].x; p.y = vc->points[v].y; p.z = vc->points[v].z;
+            p.label = tl[v] = vc->points[v].x < -0.3f ? 4u : (vc->points[v].x < 0.4f ? 9u : 2u);
+            truth->push_back(p);
+        }
+        Testing test(seg, truth);
+        performanceSet ps = test.eval_performance();
+        f3ps_performance pf; const float t1 = thr;
+        h.check(f3ps_eval_thresholds(h.get(), tl.data(), (int64_t)tl.size(), nullptr, 0, &t1, 1, &pf, nullptr, nullptr));
+        CHECK(ps.fscore == pf.fscore && ps.voi == pf.voi && ps.wov == pf.wov && ps.precision == pf.precision && ps.recall == pf.recall &&
+              ps.fpr == pf.fpr && ps.fnr == pf.fnr, "Testing differs from the sweep's scores");
+        CHECK(test.eval_fscore() == ps.fscore && test.eval_recall() == ps.recall, "eval_* getters");
+        bool threw = false;
+        try { Testing bad(PointLCloudT::Ptr(new PointLCloudT()), truth); } catch (const std::invalid_argument&) { threw = true; }
+        CHECK(threw, "an empty segmentation must throw std::invalid_argument (src/testing.cpp:413-416)");
+        PointLCloudT::Ptr back = Clustering::color2label(Clustering::label2color(seg));
+        std::map<uint32_t, uint32_t> fwd;
+        bool consistent = back->size() == seg->size();
+        for (size_t i = 0; consistent && i < seg->size(); ++i) {
+            auto it = fwd.find(seg->points[i].label);
+            if (it == fwd.end()) fwd[seg->points[i].label] = back->points[i].label;
+            else consistent = it->second == back->points[i].label;
+        }
+        std::map<uint32_t, uint32_t> inv; for (auto& kv : fwd) inv[kv.second] = kv.first;
+        CHECK(consistent && (inv.size() == fwd.size() || fwd.size() > 256), "label2color / color2label is not a bijection on the labels");
     }
     printf("FACADE OK: N=%zu V=%lld S=%d E=%d M=%d segments=%d\n", cloud->size(), (long long)n.n_voxels, n.n_supervoxels, n.n_edges, n.n_merges, n.n_segments);
     return 0;

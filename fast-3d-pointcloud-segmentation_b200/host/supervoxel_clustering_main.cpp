@@ -2,17 +2,23 @@
 // Same flags, same defaults, same quirks for the hot path:
 //   {-d <dir> | -p <file>}  -v -s -c -z -n  -t  --RGB --CVX --ML [l] --AL --EQ [bins]  --NT --V
 // Without -t the threshold sweep of the reference runs (41 thresholds against the ground truth, best F-score, :428-438).
-// Not built here (out of the hot-path scope): -r / -f, the CSV writers, the viewer.
-// Additions: -o <file.pcd> writes the labelled voxel cloud, --facade routes through the Clustering / SupervoxelClustering
+// -r <label> drops the points of one ground-truth label (:295-298, 329-333), -f <name> names the seven score files
+// <name>_{voi,precision,recall,fscore,wov,fpr,fnr}.csv (:194-196, 478-518); the final scores are printed as :520-557 does.
+// Not built: the interactive viewer.
+// Additions: --no-eval skips the evaluation of the final segmentation, -o <file.pcd> writes the labelled voxel cloud (per
+// file "<stem>_<o>" in a -d sweep), --facade routes through the Clustering / SupervoxelClustering
 // classes instead of the fused path, --gpus N shards the files of a -d sweep over N GPUs (no collective), --inflight K =
 // files per group of a sweep: K1..K6 of a file on its own handle + stream, ONE merge launch per group (f3ps_merge_batch),
 // the next group's front stages overlapping it.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <filesystem>
+#include <fstream>
+#include <map>
 #include <mutex>
 #include <memory>
 #include <thread>
@@ -38,7 +44,9 @@ struct Options {
     float voxel_resolution = 0.008f, seed_resolution = 0.08f, color_importance = 0.2f, spatial_importance = 0.4f, normal_importance = 1.0f;
     float thresh = 0; bool thresh_specified = true; bool rgb = false, cvx = false, ml = false, al = false, eq = false, disable_transform = false, verbose = false, facade = false;
     float lambda = 0; int bin_num = 0; std::string out;
+    bool remove_label = false; uint32_t label_to_be_removed = 0; std::string test_filename = "test"; bool eval = true;
 };
+struct FileScores { bool have_best = false; f3ps_performance best; std::vector<std::pair<float, f3ps_performance>> all; };
 
 void usage(const char* a0) {
     printf("Syntax is: %s {-d <direcory-of-pcd-files> OR -p <pcd-file>} [arguments] \n\n"
@@ -47,7 +55,7 @@ void usage(const char* a0) {
            "\t -c <color-weight>              (default: 0.2) \n\t -z <spatial-weight>            (default: 0.4) \n"
            "\t -n <normal-weight>             (default: 1.0) \n\n"
            "\tSEGMENTATION optional arguments: \n"
-           "\t -t <threshold>                 (required in this build: the automatic threshold needs the evaluation module)\n"
+           "\t -t <threshold>                 (default: auto)\n"
            "\t --RGB                          (RGB colour distance instead of L*A*B* CIEDE2000) \n"
            "\t --CVX                          (convexity criterion on the geometric distance) \n"
            "\t --ML [manual-lambda] *         (Manual Lambda; lambda=0.5 when no value is given) \n"
@@ -55,12 +63,78 @@ void usage(const char* a0) {
            "\t --EQ [bins-number]   *         (Equalization; 500 bins when no value is given -- the reference's text says 200) \n"
            "\t  * only one of these can be passed at a time \n\n"
            "\tOTHER optional arguments: \n"
+           "\t -r <label-to-be-removed>       (if ground-truth is provided, removes all points with the given label from the ground-truth)\n"
+           "\t -f <test-results-filename>     (name of the test results files; 'test' if not given)\n"
+           "\t --no-eval                      (skips the evaluation of the final segmentation)\n"
            "\t --NT                           (disables the single camera transform) \n"
            "\t --V                            (verbose: prints the merge sequence) \n"
            "\t -o <file.pcd>                  (writes the labelled voxel cloud) \n"
            "\t --facade                       (runs through the Clustering / SupervoxelClustering classes) \n"
            "\t --gpus <N>                     (shards the files of -d over N GPUs) \n"
            "\t --inflight <K>                 (frames in flight per GPU during a -d sweep, default 8) \n", a0);
+}
+
+// main()'s input clean-up (src/supervoxel_clustering.cpp:315-337): z<0 -> |z|; with -r, the points of that label and the points
+// with a NaN z are dropped (has_label is hard-coded true there, so the test reduces to this)
+void clean_input(pcl::PointCloud<pcl::PointXYZRGBL>& input, const Options& o) {
+    for (auto& p : input.points) if (p.z < 0) p.z = std::abs(p.z);
+    if (!o.remove_label) return;
+    pcl::PointCloud<pcl::PointXYZRGBL> kept;
+    for (auto& p : input.points) if (p.label != o.label_to_be_removed && !std::isnan(p.z)) kept.push_back(p);
+    input = kept;
+}
+
+// Testing(segmentation.get_labeled_cloud(), truth_cloud).eval_performance() (:456-457) for the handle's current segmentation:
+// the labelled voxel cloud against the ground-truth voxel labels, contingency table on the device
+f3ps_performance final_scores(f3ps::Handle& h, const std::vector<uint32_t>& truth, int n_labeled, const std::vector<uint32_t>& lab, const std::vector<uint32_t>& vox) {
+    std::map<uint32_t, uint32_t> dense;
+    for (uint32_t t : truth) dense[t] = 0;
+    uint32_t nt = 0; for (auto& kv : dense) kv.second = nt++;
+    std::vector<uint64_t> tsizes(nt, 0);
+    for (uint32_t t : truth) tsizes[dense[t]]++;
+    uint32_t ns = 0; for (int i = 0; i < n_labeled; ++i) ns = std::max(ns, lab[(size_t)i] + 1);
+    std::vector<uint32_t> tl((size_t)n_labeled);
+    for (int i = 0; i < n_labeled; ++i) tl[(size_t)i] = dense[truth[vox[(size_t)i]]];
+    f3ps_performance pf{0, 0, 0, 0, 0, 0, 0};
+    if (n_labeled > 0 && !truth.empty())
+        h.check(f3ps_eval_label_pairs(h.get(), lab.data(), tl.data(), n_labeled, (int32_t)ns, (int32_t)nt, tsizes.data(), (int64_t)truth.size(), &pf));
+    return pf;
+}
+
+// manageAllPerformances (:478-518): seven files, one line per input file, one ';'-terminated value per threshold
+void manage_all_performances(const std::vector<FileScores>& scores, const std::string& filename) {
+    const char* names[7] = {"voi", "precision", "recall", "fscore", "wov", "fpr", "fnr"};
+    for (int k = 0; k < 7; ++k) {
+        std::ofstream f((filename + "_" + names[k] + ".csv").c_str());
+        for (const FileScores& s : scores) {
+            if (s.all.empty()) continue;                                 // a file clustered with -t has no sweep (all_performances gets no entry, :428-431)
+            for (auto& kv : s.all) {
+                const f3ps_performance& p = kv.second;
+                const float v[7] = {p.voi, p.precision, p.recall, p.fscore, p.wov, p.fpr, p.fnr};
+                f << v[k] << ";";
+            }
+            f << "\n";
+        }
+    }
+}
+// printBestPerformances (:520-557).  The reference's average uses an integer 1/count, so only the first file counts
+// (a reporting bug); the running mean below is the intended one.
+void print_best_performances(const std::vector<FileScores>& scores) {
+    std::vector<f3ps_performance> best;
+    for (const FileScores& s : scores) if (s.have_best) best.push_back(s.best);
+    if (best.empty()) return;
+    if (best.size() == 1) {
+        const f3ps_performance& p = best.back();
+        printf("Scores:\nVOI\t%f\nPrec.\t%f\nRecall\t%f\nF-score\t%f\nWOv\t%f\nFPR\t%f\nFNR\t%f\n", p.voi, p.precision, p.recall, p.fscore, p.wov, p.fpr, p.fnr);
+        return;
+    }
+    float m[7] = {0, 0, 0, 0, 0, 0, 0}; int count = 0;
+    for (const f3ps_performance& p : best) {
+        ++count;
+        const float v[7] = {p.voi, p.precision, p.recall, p.fscore, p.wov, p.fpr, p.fnr};
+        for (int k = 0; k < 7; ++k) m[k] = m[k] + (1.0f / count) * (v[k] - m[k]);
+    }
+    printf("Average scores:\nVOI\t%f\nPrec.\t%f\nRecall\t%f\nF-score\t%f\nWOv\t%f\nFPR\t%f\nFNR\t%f\n", m[0], m[1], m[2], m[3], m[4], m[5], m[6]);
 }
 
 // Ground-truth voxelisation (src/supervoxel_clustering.cpp:387-400): the reference colours the truth cloud with the Glasbey
@@ -87,7 +161,7 @@ std::vector<uint32_t> voxelise_truth(const std::vector<int32_t>& point_voxel, co
 }
 
 // Clustering::all_thresh + best_thresh (src/clustering.cpp:691-774) as main() uses them (:428-438): one merge replay on the device
-float auto_threshold(f3ps::Handle& h, const std::vector<uint32_t>& truth, std::string& report) {
+float auto_threshold(f3ps::Handle& h, const std::vector<uint32_t>& truth, std::string& report, FileScores* fs) {
     const float start_thresh = 0.8f, end_thresh = 1.0f, step_thresh = 0.005f;   // globals of the reference (:76-78)
     std::vector<float> thr(1, start_thresh);
     for (float t = start_thresh + step_thresh; t <= end_thresh; t += step_thresh) thr.push_back(t);
@@ -99,6 +173,7 @@ float auto_threshold(f3ps::Handle& h, const std::vector<uint32_t>& truth, std::s
     for (size_t k = 0; k < thr.size(); ++k) {
         snprintf(buf, sizeof buf, "<T, Fscore, voi, wov> = <%f, %f, %f, %f>\n", thr[k], perf[k].fscore, perf[k].voi, perf[k].wov); report += buf;
         if (perf[k].fscore > best.fscore) { best = perf[k]; best_t = thr[k]; }
+        if (fs) fs->all.push_back(std::make_pair(thr[k], perf[k]));
     }
     snprintf(buf, sizeof buf, "Using best threshold: %f (F-score %f, voi %f)\n", best_t, best.fscore, best.voi); report += buf;
     return best_t;
@@ -107,12 +182,13 @@ float auto_threshold(f3ps::Handle& h, const std::vector<uint32_t>& truth, std::s
 // ---- a -d sweep with -t: front stages per file, one merge launch per group ---------------------------------------
 struct SweepJob {
     std::string file; pcl::PointCloud<pcl::PointXYZRGBA>::Ptr cloud; std::chrono::steady_clock::time_point t0;
+    pcl::PointCloud<pcl::PointXYZRGBL> input;                            // kept for the ground-truth labels of the evaluation
 };
 void sweep_front(SweepJob& j, const Options& o, f3ps::Handle& h) {
-    pcl::PointCloud<pcl::PointXYZRGBL> input;
+    pcl::PointCloud<pcl::PointXYZRGBL>& input = j.input;
     f3ps::loadPCDFile(j.file, input);                                    // return value ignored, as in the reference (:313)
     j.cloud.reset(new pcl::PointCloud<pcl::PointXYZRGBA>());
-    for (auto& p : input.points) if (p.z < 0) p.z = std::abs(p.z);       // :317-321
+    clean_input(input, o);                                               // :315-337
     pcl::copyPointCloud(input, *j.cloud);
     const int merging = o.ml ? F3PS_MANUAL_LAMBDA : (o.eq ? F3PS_EQUALIZATION : F3PS_ADAPTIVE_LAMBDA);
     const float lam = (o.ml && o.lambda != 0) ? o.lambda : 0.5f;
@@ -125,8 +201,15 @@ void sweep_front(SweepJob& j, const Options& o, f3ps::Handle& h) {
     h.check(f3ps_extract(h.get()));
     h.check(f3ps_graph(h.get()));
 }
-void sweep_back(SweepJob& j, const Options& o, f3ps::Handle& h, int device, std::string& report) {
+void sweep_back(SweepJob& j, const Options& o, f3ps::Handle& h, int device, std::string& report, FileScores& fs) {
     f3ps_counts n; h.check(f3ps_get_counts(h.get(), &n));
+    if (o.eval && n.n_labeled > 0) {
+        std::vector<int32_t> pv((size_t)n.n_points);
+        h.check(f3ps_get_point_voxel(h.get(), pv.data(), n.n_points));
+        std::vector<float> xyz(3 * (size_t)n.n_labeled); std::vector<uint32_t> lab(n.n_labeled), vox(n.n_labeled);
+        h.check(f3ps_get_labeled_cloud(h.get(), xyz.data(), lab.data(), vox.data(), n.n_labeled));
+        fs.best = final_scores(h, voxelise_truth(pv, j.input, (size_t)n.n_voxels), n.n_labeled, lab, vox); fs.have_best = true;
+    }
     float stage[9] = {0};
     for (int s = 0; s < 9; ++s) f3ps_stage_ms(h.get(), s, &stage[s]);
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - j.t0).count();
@@ -141,11 +224,11 @@ void sweep_back(SweepJob& j, const Options& o, f3ps::Handle& h, int device, std:
              j.cloud->size(), n.n_merges, n.n_segments, n.n_labeled, ms, device); report += buf;
     snprintf(buf, sizeof buf, "  stage ms: voxelize %.3f neighbors %.3f normals %.3f seeds %.3f expand %.3f graph %.3f merge %.3f total %.3f\n",
              stage[0], stage[1], stage[2], stage[3], stage[4], stage[5], stage[6], stage[7]); report += buf;
-    j.cloud.reset();
+    j.cloud.reset(); j.input.clear();
 }
 // one GPU's share of the files: groups of `group` files, two handle sets alternate
 void sweep_device(const std::vector<size_t>& mine, const std::vector<std::string>& files, const Options& o, int device, int group,
-                  std::vector<std::string>& reports, std::string& first_error, std::mutex& emu) {
+                  std::vector<std::string>& reports, std::vector<FileScores>& scores, std::string& first_error, std::mutex& emu) {
     auto fail = [&](const std::exception& e) { std::lock_guard<std::mutex> g(emu); if (first_error.empty()) first_error = e.what(); };
     try {
         const int threads = (int)std::max(2u, std::min<unsigned>((unsigned)group, std::thread::hardware_concurrency()));
@@ -176,7 +259,7 @@ void sweep_device(const std::vector<size_t>& mine, const std::vector<std::string
                     std::vector<f3ps_ctx*> ctxs;
                     for (size_t k = 0; k < g1 - g0; ++k) ctxs.push_back(sets[si][k]->get());
                     sets[si][0]->check(f3ps_merge_batch(ctxs.data(), (int)ctxs.size(), o.thresh));   // Clustering::cluster of every file of the group (:443)
-                    for (size_t k = 0; k < g1 - g0; ++k) sweep_back(jobs[si][k], o, *sets[si][k], device, reports[mine[g0 + k]]);
+                    for (size_t k = 0; k < g1 - g0; ++k) sweep_back(jobs[si][k], o, *sets[si][k], device, reports[mine[g0 + k]], scores[mine[g0 + k]]);
                 } catch (const std::exception& e) { fail(e); }
             });
         }
@@ -184,11 +267,11 @@ void sweep_device(const std::vector<size_t>& mine, const std::vector<std::string
     } catch (const std::exception& e) { fail(e); }
 }
 
-int process_file(const std::string& file, const Options& o, int device, std::string& report, f3ps::Handle* worker) {
+int process_file(const std::string& file, const Options& o, int device, std::string& report, f3ps::Handle* worker, FileScores& fs, bool in_sweep) {
     pcl::PointCloud<pcl::PointXYZRGBL> input;
     f3ps::loadPCDFile(file, input);                                      // return value ignored, as in the reference (:313)
     pcl::PointCloud<pcl::PointXYZRGBA>::Ptr cloud(new pcl::PointCloud<pcl::PointXYZRGBA>());
-    for (auto& p : input.points) if (p.z < 0) p.z = std::abs(p.z);       // :317-321
+    clean_input(input, o);                                               // :315-337
     pcl::copyPointCloud(input, *cloud);
     const int merging = o.ml ? F3PS_MANUAL_LAMBDA : (o.eq ? F3PS_EQUALIZATION : F3PS_ADAPTIVE_LAMBDA);
     const float lam = (o.ml && o.lambda != 0) ? o.lambda : 0.5f;         // --ML 0 means "unset" (:417)
@@ -214,6 +297,21 @@ int process_file(const std::string& file, const Options& o, int device, std::str
         segmentation.set_initialstate(supervoxel_clusters, label_adjacency);
         segmentation.cluster(o.thresh);
         labeled = segmentation.get_labeled_cloud();
+        if (o.eval && !labeled->empty()) {                                  // the reference's own sequence (:386-400, 456-457) through the classes
+            pcl::PointCloud<pcl::PointXYZL>::Ptr truth_cloud(new pcl::PointCloud<pcl::PointXYZL>());
+            pcl::copyPointCloud(input, *truth_cloud);
+            pcl::PointCloud<pcl::PointXYZRGBA>::Ptr colored_truth_cloud = Clustering::label2color(truth_cloud);
+            pcl::SupervoxelClustering<pcl::PointXYZRGBA> super_label(o.voxel_resolution, o.seed_resolution, device);
+            super_label.setUseSingleCameraTransform(!o.disable_transform);
+            super_label.setInputCloud(colored_truth_cloud);
+            super_label.setColorImportance(o.color_importance); super_label.setSpatialImportance(o.spatial_importance); super_label.setNormalImportance(o.normal_importance);
+            std::map<uint32_t, pcl::Supervoxel<pcl::PointXYZRGBA>::Ptr> supervoxel_label_clusters;
+            super_label.extract(supervoxel_label_clusters);
+            truth_cloud = Clustering::color2label(super_label.getVoxelCentroidCloud());
+            Testing test(labeled, truth_cloud);
+            const performanceSet ps = test.eval_performance();
+            fs.best = f3ps_performance{ps.voi, ps.precision, ps.recall, ps.fscore, ps.wov, ps.fpr, ps.fnr}; fs.have_best = true;
+        }
         n_sv = supervoxel_clusters.size(); n_seg = segmentation.get_currentstate().first.size();
         log = segmentation.get_merge_log(); n_merges = log.size();
     } else {
@@ -225,14 +323,16 @@ int process_file(const std::string& file, const Options& o, int device, std::str
         h.check(f3ps_set_merge_params(h.get(), o.rgb ? F3PS_RGB_EUCL : F3PS_LAB_CIEDE00, o.cvx ? F3PS_CONVEX_NORMALS_DIFF : F3PS_NORMALS_DIFF, merging, lam, bins));
         h.check(f3ps_set_input(h.get(), cloud->points.data(), (int64_t)cloud->size(), 32, 0));
         float thresh = o.thresh;
-        if (o.thresh_specified) h.check(f3ps_run(h.get(), thresh));
-        else {                                                              // no -t: the reference's threshold sweep (:428-438)
+        std::vector<uint32_t> truth;
+        if (o.thresh_specified && !o.eval) h.check(f3ps_run(h.get(), thresh));
+        else {
             h.check(f3ps_extract(h.get())); h.check(f3ps_graph(h.get()));
             f3ps_counts n0; h.check(f3ps_get_counts(h.get(), &n0));
             std::vector<int32_t> pv((size_t)n0.n_points);
             h.check(f3ps_get_point_voxel(h.get(), pv.data(), n0.n_points));
-            thresh = auto_threshold(h, voxelise_truth(pv, input, (size_t)n0.n_voxels), report);
-            h.check(f3ps_merge(h.get(), thresh));                           // main() re-clusters at the chosen threshold (:443)
+            truth = voxelise_truth(pv, input, (size_t)n0.n_voxels);          // :386-400
+            if (!o.thresh_specified) thresh = auto_threshold(h, truth, report, &fs);   // no -t: the reference's threshold sweep (:428-438)
+            h.check(f3ps_merge(h.get(), thresh));                           // main() (re-)clusters at the chosen threshold (:443)
         }
         f3ps_counts n; h.check(f3ps_get_counts(h.get(), &n));
         n_sv = n.n_supervoxels; n_seg = n.n_segments; n_merges = n.n_merges;
@@ -240,6 +340,7 @@ int process_file(const std::string& file, const Options& o, int device, std::str
         h.check(f3ps_get_labeled_cloud(h.get(), xyz.data(), lab.data(), vox.data(), n.n_labeled));
         labeled->resize(n.n_labeled);
         for (int i = 0; i < n.n_labeled; ++i) { auto& p = labeled->points[i]; p.x = xyz[3 * i]; p.y = xyz[3 * i + 1]; p.z = xyz[3 * i + 2]; p.label = lab[i]; }
+        if (o.eval && n.n_labeled > 0) { fs.best = final_scores(h, truth, n.n_labeled, lab, vox); fs.have_best = true; }   // :456-457
         for (int s = 0; s < 9; ++s) f3ps_stage_ms(h.get(), s, &stage[s]);
         if (o.verbose) {
             std::vector<uint32_t> ab(2 * n_merges), left(2 * n_merges); std::vector<float> w(n_merges);
@@ -255,7 +356,11 @@ int process_file(const std::string& file, const Options& o, int device, std::str
              cloud->size(), n_merges, n_seg, labeled->size(), ms, device); report += buf;
     if (!o.facade) { snprintf(buf, sizeof buf, "  stage ms: voxelize %.3f neighbors %.3f normals %.3f seeds %.3f expand %.3f graph %.3f merge %.3f total %.3f\n",
                               stage[0], stage[1], stage[2], stage[3], stage[4], stage[5], stage[6], stage[7]); report += buf; }
-    if (!o.out.empty()) f3ps::savePCDFileASCII(o.out, *labeled);
+    if (!o.out.empty()) {                                                // a sweep writes one file per input: <stem>_<o> next to -o's path
+        std::string out = o.out;
+        if (in_sweep) { const std::filesystem::path op(o.out); out = (op.parent_path() / (std::filesystem::path(file).stem().string() + "_" + op.filename().string())).string(); }
+        f3ps::savePCDFileASCII(out, *labeled);
+    }
     return 0;
 }
 } // namespace
@@ -287,13 +392,18 @@ int main(int argc, char** argv) {
     if (o.ml) parse(argc, argv, "--ML", o.lambda);
     if (o.eq) parse(argc, argv, "--EQ", o.bin_num);
     parse(argc, argv, "-o", o.out);
+    o.remove_label = find_switch(argc, argv, "-r");
+    if (o.remove_label) { int r = 0; parse(argc, argv, "-r", r); o.label_to_be_removed = (uint32_t)r; }
+    if (find_switch(argc, argv, "-f")) parse(argc, argv, "-f", o.test_filename);
+    o.eval = !find_switch(argc, argv, "--no-eval");
     int gpus = 1; parse(argc, argv, "--gpus", gpus); gpus = std::max(1, gpus);
     int inflight = 8; parse(argc, argv, "--inflight", inflight); inflight = std::max(1, inflight);
     setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);                     // before the CUDA context exists (see f3ps_create)
     int rc = 0;
     std::vector<std::string> reports(file_list.size());
+    std::vector<FileScores> scores(file_list.size());
     try {
-        if (file_list.size() <= 1 || o.facade) { for (size_t i = 0; i < file_list.size(); ++i) rc |= process_file(file_list[i], o, 0, reports[i], nullptr); }
+        if (file_list.size() <= 1 || o.facade) { for (size_t i = 0; i < file_list.size(); ++i) rc |= process_file(file_list[i], o, 0, reports[i], nullptr, scores[i], file_list.size() > 1); }
         else {
             // -d sweep: files are independent (fresh SupervoxelClustering + Clustering per file in the reference, :348,408).
             // `inflight` frames per GPU, each on its own handle / stream / host thread; reports are printed in file order.
@@ -304,7 +414,7 @@ int main(int argc, char** argv) {
                 for (size_t i = 0; i < file_list.size(); ++i) share[i % (size_t)gpus].push_back(i);
                 std::vector<std::thread> th;
                 for (int gdev = 0; gdev < gpus; ++gdev)
-                    th.emplace_back([&, gdev]() { sweep_device(share[(size_t)gdev], file_list, o, gdev, std::min(inflight, 96), reports, first_error, emu); });
+                    th.emplace_back([&, gdev]() { sweep_device(share[(size_t)gdev], file_list, o, gdev, std::min(inflight, 96), reports, scores, first_error, emu); });
                 for (auto& t : th) t.join();
             } else {
                 const int workers = (int)std::min<size_t>((size_t)gpus * inflight, file_list.size());
@@ -314,7 +424,7 @@ int main(int argc, char** argv) {
                     try {
                         f3ps::Handle h(w % gpus);
                         f3ps_set_blocking_wait(h.get(), blocking ? 1 : 0);
-                        for (size_t i = w; i < file_list.size(); i += workers) process_file(file_list[i], o, w % gpus, reports[i], &h);
+                        for (size_t i = w; i < file_list.size(); i += workers) process_file(file_list[i], o, w % gpus, reports[i], &h, scores[i], true);
                     } catch (const std::exception& e) { std::lock_guard<std::mutex> g(emu); if (first_error.empty()) first_error = e.what(); }
                 });
                 for (auto& t : th) t.join();
@@ -322,6 +432,7 @@ int main(int argc, char** argv) {
             if (!first_error.empty()) throw std::runtime_error(first_error);
         }
         for (auto& r : reports) fputs(r.c_str(), stdout);
+        if (o.eval) { manage_all_performances(scores, o.test_filename); print_best_performances(scores); }
     } catch (const std::exception& e) { fprintf(stderr, "error: %s\n", e.what()); return 2; }
     return rc;
 }

@@ -124,6 +124,10 @@ int f3ps_set_blocking_wait(f3ps_ctx* ctx, int blocking);
  * 1 = same as 0, 2 = always general, 4 = resident kernel compiled with per-phase cycle counters (f3ps_merge_profile).
  * All replay the same merge sequence; the switch exists for tests and profiling. */
 int f3ps_set_merge_kernel(f3ps_ctx* ctx, int which);
+/* Development aid of the resident kernel (kernel choice 4): SM clock values at 32 points of each of 256 consecutive merges,
+ * starting at merge `first_merge` of the NEXT f3ps_merge; out (may be NULL to only set the window) receives the last
+ * recorded window, 256 x 32 words (slot meaning: f3ps/binding.py merge_trace). */
+int f3ps_merge_trace(f3ps_ctx* ctx, int64_t first_merge, uint32_t* out, int64_t capacity_words);
 /* SupervoxelClustering::extract + getSupervoxelAdjacency = K1..K5 + supervoxel tables */
 int f3ps_extract(f3ps_ctx* ctx);
 /* whole path: K1..K7 */
@@ -216,6 +220,13 @@ int f3ps_slab_expand_end(f3ps_ctx* ctx);
 typedef struct f3ps_performance { float voi, precision, recall, fscore, wov, fpr, fnr; } f3ps_performance;
 int f3ps_eval_thresholds(f3ps_ctx* ctx, const uint32_t* truth_label, int64_t n_voxels, const uint32_t* extra_truth_label, int64_t n_extra,
                          const float* thresholds, int n_thresholds, f3ps_performance* perf, int32_t* n_segments, int32_t* n_merges_at);
+
+/* Testing(segm, truth).eval_performance() (testing.cpp:62-146, 239-406) for ONE pair of labelled clouds: the caller pairs the
+ * points by exact xyz (as count_intersect does) and passes, per segmentation point, its dense segment label seg[i] < n_seg and
+ * the dense ground-truth label of the point at the same xyz, truth[i] < n_truth, or n_truth when there is none; truth_sizes[j] =
+ * points of ground-truth segment j, n_truth_points = truth->size().  The contingency table is counted on the device. */
+int f3ps_eval_label_pairs(f3ps_ctx* ctx, const uint32_t* seg, const uint32_t* truth, int64_t n_pairs, int32_t n_seg, int32_t n_truth,
+                          const uint64_t* truth_sizes, int64_t n_truth_points, f3ps_performance* perf);
 
 /* CUDA-event time of the last run of a stage, ms (valid after f3ps_sync) */
 int f3ps_stage_ms(f3ps_ctx* ctx, int stage, float* ms);

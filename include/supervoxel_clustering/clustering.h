@@ -80,6 +80,9 @@ public:
     /* the reference's --V trace "left: %de/%dp - w: %f - [%d, %d]" (src/clustering.cpp:390-392), as data */
     const std::vector<MergeStep>& get_merge_log() const { return merge_log_; }
 
+    /* ColorUtilities' print-only self checks (src/clustering.cpp:779-783) */
+    void test_all() const;
+
     static PointCloudT::Ptr label2color(PointLCloudT::Ptr label_cloud);
     static PointLCloudT::Ptr color2label(PointCloudT::Ptr colored_cloud);
 };
