@@ -218,7 +218,7 @@ def sweep_leg(args, env, workload, steps):
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     if args.pool == "batch":
         # groups of F frames: K1..K6 per frame on its own handle / stream, ONE merge launch per group (CTA i = frame i)
-        pool = sweep.BatchPool(batch=F, workers=args.workers or None, device=local_rank, merge=flags, threshold=THRESHOLD, expand_ctas=-args.expand_ctas)
+        pool = sweep.BatchPool(batch=F, workers=args.workers or None, device=local_rank, merge=flags, threshold=THRESHOLD, expand_ctas=-args.expand_ctas, expand_cluster=args.expand_cluster)
     else:
         pool = sweep.FramePool(F, device=local_rank, merge=flags, threshold=THRESHOLD)
     stream = torch.cuda.current_stream()
@@ -283,7 +283,7 @@ def sweep_leg(args, env, workload, steps):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         solo.set_blocking_wait(False)
-        solo.set_expand_sharing(0, 0)                  # one frame alone: K5 over the whole GPU again (the pool caps its grid)
+        solo.set_expand_kernel(0, 0); solo.set_expand_sharing(0, 0)   # one frame alone: K5 as the cooperative grid over the whole GPU (the pool runs small clusters)
         solo.set_input_device(ptrs[k % F], npts, 32); solo.run(THRESHOLD)
         e1.record(stream); torch.cuda.synchronize()
         lat.append(e0.elapsed_time(e1))
@@ -294,12 +294,13 @@ def sweep_leg(args, env, workload, steps):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     t_dev_max, t_e2e_max = float(tmax[0]), float(tmax[1])
+    n_segs = len(pool.segs)
     pool.close()
     del d_frames, pinned, flush
     n_frames = F * R * steps
     return dict(F=F, R=R, npts=npts, n_distinct=n_distinct, steps=steps, n_frames=n_frames, t_dev=t_dev_max, t_e2e=t_e2e_max,
                 value=npts * n_frames * world / t_dev_max / 1e6, e2e=npts * n_frames * world / t_e2e_max / 1e6,
-                counts=counts, solo_counts=solo_counts, stage_ms={k: v / (len(pool.segs) * steps) for k, v in stage_acc.items()},
+                counts=counts, solo_counts=solo_counts, stage_ms={k: v / (n_segs * steps) for k, v in stage_acc.items()},
                 solo_stage=solo_stage, lat=lat, launches=int(launches), clocks=clocks, wall=wall, out_bytes=int(out_bytes[0]), frame0=frames[0])
 
 
@@ -495,6 +496,7 @@ def main():
     ap.add_argument("--rounds", type=int, default=3, help="groups per step (batch pool) / frames each handle runs back to back inside one step (streams pool)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (development)")
     ap.add_argument("--pool", default="batch", choices=["batch", "streams"], help="batch: one merge launch per group of --inflight frames; streams: one merge kernel per stream")
+    ap.add_argument("--expand-cluster", type=int, default=8, help="batch pool: K5 of a frame as one thread-block cluster of this many CTAs (0 = cooperative grid, see --expand-ctas)")
     ap.add_argument("--expand-ctas", type=int, default=24, help="batch pool: cap of the cooperative K5 grid per frame (0 = one voxel per thread)")
     ap.add_argument("--workers", type=int, default=32, help="host threads for the front stages of a group (batch pool)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"], help="c2: frames in flight, --CVX --AL (the headline; a short C3 leg rides along); c3: the --EQ 200 directory sweep; c5: one large cloud in slab mode")

@@ -50,7 +50,7 @@ F3PS_HD double dsqrt(double x) {
     double r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
     r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
     g = fma(fma(-g, g, x), h, g);
-    return x > 0.0 ? g : 0.0;
+    return x > 0.0 ? g : (x == 0.0 ? 0.0 : x * __longlong_as_double(0x7ff8000000000000ll));   // sqrt(+-0) = 0; negative or NaN -> NaN, as sqrt() does
 }
 #else
 F3PS_HD double ddiv(double n, double x) { return n / x; }

@@ -57,7 +57,7 @@ enum Progress { P_NONE = 0, P_INPUT, P_VOXELS, P_NEIGHBORS, P_NORMALS, P_SEEDS, 
 struct f3ps_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    bool own_stream = false;
+    cudaStream_t private_stream = nullptr;   // created by the handle (f3ps_create without a stream); destroyed with it
     std::string err;
     f3ps::VccsParams vp{0.008f, 0.08f, 0.2f, 0.4f, 1.0f, 1, 1};
     f3ps::MergeParams mp{0, 0, 1, 0.5f, 500};
@@ -129,6 +129,10 @@ struct f3ps_ctx {
     f3ps::DevBuf slab_dest, slab_tot;
     f3ps::DevBuf ev_parent, ev_when, ev_dense, ev_truth, ev_table;   // f3ps_eval_thresholds
     f3ps::ExpandArgs slab_A{}; int slab_cur = 0; unsigned slab_k = 0; unsigned slab_sweeps = 0; int slab_round = 0; bool slab_expanding = false;
+    int expand_kernel_choice = 0;       // f3ps_set_expand_kernel: 0 auto, 1 cooperative grid, 2 one cluster
+    int expand_cluster_ctas = 0;        // cap of the cluster size (0 = by V, at most 16)
+    int expand_path = 0;                // what the last f3ps_expand launched: 1 cooperative / shared grid, 2 cluster
+    bool expand_cluster_attr_set = false;
     bool general_attr_set = false;
     bool lambda_attr_set = false;
 };

@@ -233,7 +233,7 @@ int f3ps_create(int device, void* stream, f3ps_ctx** out) {
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return F3PS_ERR_CUDA; }
     if (stream) ctx->stream = (cudaStream_t)stream;
-    else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return F3PS_ERR_CUDA; } ctx->own_stream = true; }
+    else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return F3PS_ERR_CUDA; } ctx->private_stream = ctx->stream; }
     bool ok = cudaMalloc(&ctx->d_sc, sizeof(DevScalars)) == cudaSuccess &&
               cudaMallocHost(&ctx->h_sc, sizeof(DevScalars)) == cudaSuccess;
     const size_t lut_bytes = (size_t)(f3ps_lab_lut_end - f3ps_lab_lut_begin);
@@ -262,7 +262,7 @@ void f3ps_destroy(f3ps_ctx* ctx) {
     for (int i = 0; i < f3ps_ctx::kEvents; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->ev_wait) cudaEventDestroy(ctx->ev_wait);
     if (ctx->ev_batch) cudaEventDestroy(ctx->ev_batch);
-    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->private_stream) cudaStreamDestroy(ctx->private_stream);
     delete ctx;
 }
 
@@ -494,6 +494,27 @@ int f3ps_expand(f3ps_ctx* ctx) {
     const unsigned V = ctx->V;
     ExpandArgs A;
     rc = expand_prepare(ctx, A); if (rc) return rc;
+    const bool cluster = V && ctx->expand_kernel_choice == 2;      // sweeps ask for it (f3ps_set_expand_kernel); one frame alone is fastest on the cooperative grid
+    if (cluster) {
+        // one thread-block cluster per frame (kernels_expand.cuh): ~2 voxels per thread, at most 16 CTAs
+        int ncta = (int)std::min<int64_t>(kExpandClusterMax, ((int64_t)V + 2 * kExpandClusterThreads - 1) / (2 * kExpandClusterThreads));
+        if (ctx->expand_cluster_ctas > 0) ncta = std::min(ncta, ctx->expand_cluster_ctas);
+        ncta = std::max(1, ncta);
+        if (!ctx->expand_cluster_attr_set) {
+            F3PS_CUDA_OK(cudaFuncSetAttribute((const void*)expand_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            ctx->expand_cluster_attr_set = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ncta); cfg.blockDim = dim3(kExpandClusterThreads); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = (unsigned)ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        F3PS_CUDA_OK(cudaLaunchKernelEx(&cfg, expand_cluster_kernel, A));
+        ctx->launches++;
+        ctx->expand_path = 2;
+        return expand_finish(ctx);
+    }
+    ctx->expand_path = 1;
     if (V && ctx->expand_ctas > 0 && !ctx->expand_coop_cap) {
         // shared mode: a small ordinary grid, bounded concurrency (see ExpandGate); held until the kernel has finished
         ExpandTicket ticket(&g_expand_gate[ctx->device & 15]);
@@ -859,18 +880,14 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
         slots_of[i] = slots;
         (ok ? batch : solo).push_back(i);
     }
-    int slots = 1;
-    for (int i : batch) slots = std::max(slots, slots_of[i]);
-    const unsigned E_cap = (unsigned)slots * kFastOwners;
-    {   // the shared-memory layout must fit with the batch's edge capacity
+    {   // every frame brings its own table capacities (the layout is per CTA); the launch asks for the largest footprint
         std::vector<int> keep;
         for (int i : batch) {
             const unsigned S_cap = (ctxs[i]->S + 7u) & ~7u;
-            if (FastSmem(nullptr, S_cap, E_cap).bytes <= 227u * 1024u) keep.push_back(i); else solo.push_back(i);
+            if (FastSmem(nullptr, S_cap, (unsigned)slots_of[i] * kFastOwners).bytes <= 227u * 1024u) keep.push_back(i); else solo.push_back(i);
         }
         batch.swap(keep);
     }
-    for (int i : solo) { rc = f3ps_merge(ctxs[i], threshold); if (rc) return rc; }
     for (size_t g0 = 0; g0 < batch.size(); g0 += kFastBatchMax) {
         const size_t g1 = std::min(batch.size(), g0 + (size_t)kFastBatchMax);
         static thread_local FastBatch B;                     // 32 KB: not on the stack
@@ -897,12 +914,12 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
             A.R = ctx->R1; A.E = ctx->E1; A.n_edges_ptr = SC(n_edges); A.n_sv_ptr = SC(xctl.n_sv); A.ep = edge_params(ctx); A.lambda_dev = SC(lambda);
             A.threshold = threshold; A.run_start = ctx->run_start.as<unsigned>(); A.run_end = ctx->run_end.as<unsigned>();
             A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
-            A.ctl = SC(mctl); A.S_cap = (S + 7u) & ~7u; A.E_cap = E_cap;
+            A.ctl = SC(mctl); A.S_cap = (S + 7u) & ~7u; A.E_cap = (unsigned)slots_of[batch[k]] * kFastOwners;
             rc = lean_pool(ctx, ctx->E, A); if (rc) return rc;
             A.trace = nullptr; A.trace_first = 0;
-            bytes = std::max(bytes, FastSmem(nullptr, A.S_cap, E_cap).bytes);
+            bytes = std::max(bytes, FastSmem(nullptr, A.S_cap, A.E_cap).bytes);
             rc = mark(ctx, 9); if (rc) return rc;
-            if (ctx != lead) {                               // the lead's stream runs the grid: it waits for everybody's set-up
+            if (ctx->stream != lead->stream) {               // the lead's stream runs the grid: it waits for everybody's set-up
                 F3PS_CUDA_OK(cudaEventRecord(ctx->ev_batch, ctx->stream));
                 F3PS_CUDA_OK(cudaStreamWaitEvent(lead->stream, ctx->ev_batch, 0));
             }
@@ -918,7 +935,7 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
         }
         for (size_t k = g0; k < g1; ++k) {                   // every handle continues on its own stream after the grid
             f3ps_ctx* ctx = ctxs[batch[k]];
-            if (ctx != lead) F3PS_CUDA_OK(cudaStreamWaitEvent(ctx->stream, lead->ev_batch, 0));
+            if (ctx->stream != lead->stream) F3PS_CUDA_OK(cudaStreamWaitEvent(ctx->stream, lead->ev_batch, 0));
             ctx->merge_path = 1;
             rc = mark(ctx, 10); if (rc) return rc;
             const unsigned P = ctx->n_pos;
@@ -930,7 +947,12 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
                           ctx->graph_from_host ? nullptr : ctx->owner0.as<unsigned>());
             rc = mark(ctx, 8); if (rc) return rc;
         }
-        for (size_t k = g0; k < g1; ++k) {
+    }
+    // graphs that do not fit the resident kernel: one by one (general kernel), next to the grids already in flight
+    for (int i : solo) { rc = f3ps_merge(ctxs[i], threshold); if (rc) return rc; }
+    // results only after EVERY chunk's grid is in flight (a batch larger than one parameter block must not run its chunks back to back)
+    {
+        for (size_t k = 0; k < batch.size(); ++k) {
             f3ps_ctx* ctx = ctxs[batch[k]];
             rc = pull_scalars(ctx); if (rc) return rc;
             if (ctx->h_sc->mctl.error) {                     // a merge overflowed the resident kernel's touched list: this frame alone, general kernel
@@ -962,6 +984,13 @@ int f3ps_set_expand_sharing(f3ps_ctx* ctx, int ctas_per_frame, int max_concurren
         { std::lock_guard<std::mutex> l(g.m); g.limit = max_concurrent; }
         g.cv.notify_all();
     }
+    return F3PS_OK;
+}
+
+int f3ps_set_expand_kernel(f3ps_ctx* ctx, int which, int cluster_ctas) {
+    if (!ctx || which < 0 || which > 2 || cluster_ctas < 0 || cluster_ctas > kExpandClusterMax) return F3PS_ERR_INVALID_ARGUMENT;
+    ctx->expand_kernel_choice = which;
+    ctx->expand_cluster_ctas = cluster_ctas;
     return F3PS_OK;
 }
 

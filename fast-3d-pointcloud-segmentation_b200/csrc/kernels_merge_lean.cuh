@@ -10,7 +10,7 @@
 //                 merge touches are read from the two lists, never searched for; the survivors become a's new list
 //   ropes / sizes shared memory (per region: head / tail / next run, run bounds, voxel count)
 //   voxels        position-ordered float4 (x,y,z,rgba) in HBM/L2; a region of <= 256 voxels is fetched by the fold warps themselves
-//                 (16-byte cp.async per lane, every run in flight at once); longer ones stream through a four-slot ring of 256
+//                 (16-byte cp.async per lane, every run in flight at once); longer ones stream through a two-slot ring of 256
 //                 voxels filled by the loader warp the same way (full/empty mbarriers, cp.async.mbarrier.arrive).  One bulk copy
 //                 (TMA) per run, as in round 1, made the loader the bottleneck of the long folds: runs are ~15 voxels
 //   touched edges ONE worker thread per touched edge (up to 928): duplicates through a per-region mark, CIEDE2000 in every
@@ -32,8 +32,9 @@ constexpr int kLeanRoleWarps = 3;
 constexpr int kFastOwners = kFastThreads - 32 * kLeanRoleWarps;     // 928 worker threads
 constexpr int kLeanWorkerWarps = kFastOwners / 32;                  // 29
 constexpr int kLeanMaxTouched = kFastOwners;
-constexpr int kLeanHash = 2048;
-constexpr int kLeanRing = 4, kLeanSlotVox = 256;
+constexpr int kLeanHash = 1024;                      // tie-group table (distinct new weights of one merge), power of two
+constexpr int kLeanHashShift = 22;                   // 32 - log2(kLeanHash)
+constexpr int kLeanRing = 2, kLeanSlotVox = 256;     // (four slots measured no faster than two; 8 KB decide whether a VGA frame fits)
 constexpr unsigned kDeadKey = 0xffffffffu;
 constexpr unsigned long long kDeadKey64 = ~0ull;
 constexpr unsigned kNil16 = 0xffffu;
@@ -71,8 +72,9 @@ struct FastSmem {
     __host__ __device__ FastSmem(char* base, unsigned S, unsigned E_cap) {
         size_t o = 0;
         auto take = [&](size_t b) { char* p = base + o; o += (b + 15) & ~(size_t)15; return p; };
-        stage = (float4*)take((size_t)kLeanRing * kLeanSlotVox * 16); mbar = (unsigned long long*)take(2 * kLeanRing * 8);
-        priv = (float4*)take((size_t)2 * kLeanSlotVox * 16);
+        mbar = (unsigned long long*)take(2 * kLeanRing * 8);
+        stage = (float4*)take((size_t)kLeanRing * kLeanSlotVox * 16);
+        priv = (float4*)take((size_t)2 * kLeanSlotVox * 16);     // directly behind the ring: the set-up's scratch (4 bytes per region, S <= 4096) spans both
         key = (unsigned long long*)take((size_t)E_cap * 8); te_key = (unsigned long long*)take(kLeanMaxTouched * 8); ab = (unsigned*)take((size_t)E_cap * 4);
         partner = (unsigned short*)take(kLeanMaxTouched * 2);
         res_w = (unsigned*)take(kLeanMaxTouched * 4); cls = (unsigned char*)take(kLeanMaxTouched);
@@ -263,7 +265,8 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
 
     // ---- set-up: ropes, edges, adjacency lists -> shared memory / the pool ------------------------------------------------
     const unsigned nbw = A.E_cap / kFastOwners;                                // blocks of 32 edges per worker warp
-    unsigned* const cursor = reinterpret_cast<unsigned*>(sm.stage);           // scratch: the ring is idle until the first merge
+    static_assert((kLeanRing + 2) * kLeanSlotVox * 16 >= 4096 * 4, "set-up scratch: one word per region");
+    unsigned* const cursor = reinterpret_cast<unsigned*>(sm.stage);           // scratch: ring + private stages are idle until the first merge
     for (unsigned s = tid; s < S; s += kFastThreads) {
         const unsigned r0 = A.run_start[s];
         sm.rs[s] = r0; sm.rlen[s] = (unsigned short)(A.run_end[s] - r0); sm.n[s] = R.n[s];
@@ -663,7 +666,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                         cls = wbits == old_hi ? FC_KEEP : (wbits > old_hi ? FC_FRONT : FC_BACK);
                         if (cls != FC_KEEP && wide) {                                          // tie groups: same new weight, same side
                             const unsigned hk = wbits | (cls == FC_FRONT ? 0x80000000u : 0u);
-                            unsigned h = (hk * 2654435761u) >> 21;
+                            unsigned h = (hk * 2654435761u) >> kLeanHashShift;
                             while (true) {
                                 const unsigned prev = atomicCAS(&sm.hkey[h], kDeadKey, hk);
                                 if (prev == kDeadKey || prev == hk) break;

@@ -91,7 +91,7 @@ class BatchPool:
     kernels; a grid has no such cap.  Two handle sets alternate, so the front stages of group g+1 overlap the merge of group g.
     Results are those of Segmenter.run on every frame, in frame order."""
 
-    def __init__(self, batch=64, workers=None, device=0, vccs=None, merge=None, threshold=0.2, expand_ctas=0, sms=148):
+    def __init__(self, batch=64, workers=None, device=0, vccs=None, merge=None, threshold=0.2, expand_ctas=0, sms=148, expand_cluster=8):
         from . import binding
         import os
         import threading
@@ -104,7 +104,12 @@ class BatchPool:
                 s.set_vccs_params(**(vccs or {}))
                 s.set_merge_params(**(merge or {}))
                 s.set_blocking_wait(True)
-                if expand_ctas and expand_ctas < 0:
+                if expand_cluster:
+                    # K5 as ONE thread-block cluster per frame (hardware cluster barrier; an ordinary launch, so the frames' K5 run side
+                    # by side -- cooperative launches run one at a time).  Measured on C2, groups of 96: 8 CTAs 427 Mpoints/s,
+                    # cooperative grid capped at 24 CTAs 416; 1-2 CTAs per frame lose (the 32 hardware queues cap long kernels)
+                    s.set_expand_kernel(2, expand_cluster)
+                elif expand_ctas and expand_ctas < 0:
                     s.set_expand_sharing(-expand_ctas, 0)            # cooperative launch, grid capped: more frames side by side
                 elif expand_ctas:
                     # optional (measured: no gain, K5 costs ~60 SM-ms per VGA frame either way): K5 as small ordinary grids: the merge grid of a group holds `batch` SMs for its whole duration, the
@@ -125,7 +130,12 @@ class BatchPool:
         errors = []
         groups = [list(range(g, min(n, g + self.batch))) for g in range(0, n, self.batch)]
 
+        import time as _time
+        self.timeline = []                      # (what, group, start, end) in seconds since the start of run(): where a step's time goes
+        t_run0 = _time.perf_counter()
+
         def front(gi):
+            t_f0 = _time.perf_counter()
             st = self.sets[gi % 2]
             idx = groups[gi]
 
@@ -146,12 +156,15 @@ class BatchPool:
                 t.start()
             for t in th:
                 t.join()
+            self.timeline.append(("front", gi, t_f0 - t_run0, _time.perf_counter() - t_run0))
 
         def back(gi):
+            t_b0 = _time.perf_counter()
             try:
                 st = self.sets[gi % 2]
                 idx = groups[gi]
                 self.binding.merge_batch(st[:len(idx)], self.threshold)
+                self.timeline.append(("merge", gi, t_b0 - t_run0, _time.perf_counter() - t_run0))
                 if collect is not None:                  # result read-back of the group, a few host threads
                     def reader(w):
                         try:
@@ -184,3 +197,4 @@ class BatchPool:
         if errors:
             raise errors[0]
         return results
+

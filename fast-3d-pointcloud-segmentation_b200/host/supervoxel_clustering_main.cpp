@@ -236,7 +236,7 @@ void sweep_device(const std::vector<size_t>& mine, const std::vector<std::string
         for (int s = 0; s < 2; ++s) for (int k = 0; k < group; ++k) {
             sets[s].emplace_back(new f3ps::Handle(device));
             f3ps_set_blocking_wait(sets[s].back()->get(), 1);
-            f3ps_set_expand_sharing(sets[s].back()->get(), 24, 0);        // sweeps: smaller cooperative K5 grids, more files side by side
+            f3ps_set_expand_kernel(sets[s].back()->get(), 2, 8);          // sweeps: K5 of a file as one cluster of 8 CTAs, the files side by side
         }
         std::vector<SweepJob> jobs[2];
         std::thread back;

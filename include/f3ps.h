@@ -112,6 +112,13 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold); /* K7 Clustering::cluster(thresh
  * max_concurrent = 0 with ctas_per_frame > 0: still a cooperative launch, its grid capped at ctas_per_frame (a sweep trades the
  * latency of one frame for more frames side by side; the driver keeps guaranteeing co-residency). */
 int f3ps_set_expand_sharing(f3ps_ctx* ctx, int ctas_per_frame, int max_concurrent);
+/* which K5 kernel f3ps_expand launches: 0 / 1 = the cooperative grid over the whole GPU (lowest latency for one frame: 0.8 ms on a
+ * VGA frame, but ~50 SM-ms of mostly barrier waiting; f3ps_set_expand_sharing applies to it), 2 = ONE thread-block cluster per frame
+ * (cluster_ctas = 1..16 CTAs of 1024 threads meeting at the hardware cluster barrier; 0 = two voxels per thread, at most 16): the
+ * expansion is instruction-bound, so a small cluster does the same work in ~17 SM-ms and leaves the other SMs to the frames next to
+ * it -- what directory sweeps use.  Same results from every choice.
+ * Replaces pcl::SupervoxelClustering::expandSupervoxels as called from extract() (/root/reference/src/supervoxel_clustering.cpp:357). */
+int f3ps_set_expand_kernel(f3ps_ctx* ctx, int which, int cluster_ctas);
 /* Clustering::cluster(threshold) for n handles (same device, graphs built) with ONE launch of the resident merge kernel:
  * CTA i replays frame i.  Independent streams share at most 32 hardware queues per context, so a sweep with one merge
  * kernel per stream never overlaps more than 32 of them; a grid has no such limit.  Same results per handle as f3ps_merge;

@@ -176,6 +176,28 @@ def test_phantom_seed_leaves(gpu, oracle_mod, seed, w, h):
         assert len(g.array("out_voxel")) == int(g.array("sv_count").sum())
 
 
+@pytest.mark.parametrize("seed,w,h", [(11, 160, 120), (52, 160, 120), (20020, 640, 480)], ids=["small", "phantom", "vga"])
+def test_expand_cluster_kernel_equals_cooperative_grid(gpu, oracle_mod, seed, w, h):
+    """K5 has two launch shapes (f3ps_set_expand_kernel): the cooperative grid over the GPU (software grid barrier) and ONE
+    thread-block cluster per frame (hardware cluster barrier; what sweeps use).  Every cluster size gives the cooperative
+    grid's arrays bit for bit, and those are the oracle's."""
+    pts = gpu.synth.make_frame(seed=seed, width=w, height=h)
+    g, o = run_both(gpu, oracle_mod, pts, AL, 0.2, merge_impl=1)
+    assert_parity(g, o, STAGE_ARRAYS)
+    names = ["labels", "dist", "sv_label", "sv_count", "sv_xyz", "sv_rgb", "sv_normal", "adj", "edges_ab", "edges_w"]
+    ref = {n: g.array(n).copy() for n in names}
+    for ctas in (1, 3, 8, 16, 0):
+        g.set_expand_kernel(2, ctas)
+        g.set_input(pts); g.run(0.2)
+        for n in names:
+            assert same(ref[n], g.array(n)), (ctas, n)
+    g.set_expand_kernel(1, 0); g.set_input(pts); g.run(0.2)
+    for n in names:
+        assert same(ref[n], g.array(n)), ("cooperative", n)
+    with pytest.raises(gpu.F3psError):
+        g.set_expand_kernel(2, 17)
+
+
 def test_no_transform_and_other_resolutions(gpu, oracle_mod, small_frame):
     g, o = run_both(gpu, oracle_mod, small_frame, RGB_ML, 0.2, use_transform=False, voxel_res=0.02, seed_res=0.15)
     assert_parity(g, o, STAGE_ARRAYS + MERGE_ARRAYS)
