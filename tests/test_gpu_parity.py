@@ -194,7 +194,7 @@ def test_expand_cluster_kernel_equals_cooperative_grid(gpu, oracle_mod, seed, w,
     g.set_expand_kernel(1, 0); g.set_input(pts); g.run(0.2)
     for n in names:
         assert same(ref[n], g.array(n)), ("cooperative", n)
-    with pytest.raises(gpu.F3psError):
+    with pytest.raises(ValueError):                      # F3PS_ERR_INVALID_ARGUMENT
         g.set_expand_kernel(2, 17)
 
 
