@@ -461,7 +461,7 @@ static int expand_prepare(f3ps_ctx* ctx, ExpandArgs& A) {
     ctx->sorted_label = ctx->lab_keys_a.as<unsigned>(); ctx->sorted_vox = ctx->lab_vals_b.as<unsigned>();
     A.nbr_col = ctx->nbr_col.as<int>(); A.nbr_row = ctx->nbr_row.as<int>(); A.V_cap = V;
     A.vox_xyz = ctx->vox_xyz.as<float4>(); A.vox_rgb = ctx->vox_rgb.as<float4>(); A.vox_nrm = ctx->vox_normal.as<float4>();
-    A.seeds = ctx->seeds.as<int>(); A.V = V; A.S0 = S0; A.rounds = ctx->rounds; A.P = ctx->vp;
+    A.seeds = ctx->seeds.as<int>(); A.V = V; A.S0 = S0; A.rounds = ctx->rounds; A.P = ctx->vp; A.keep_centroids = 0;
     A.owner[0] = ctx->own_a.as<unsigned>(); A.owner[1] = ctx->own_b.as<unsigned>();
     A.dist[0] = ctx->dst_a.as<float>(); A.dist[1] = ctx->dst_b.as<float>();
     A.st[0] = ctx->st0.as<unsigned>(); A.st[1] = ctx->st1.as<unsigned>();
@@ -487,13 +487,12 @@ static int expand_finish(f3ps_ctx* ctx) {
     return mark(ctx, 5);
 }
 
-int f3ps_expand(f3ps_ctx* ctx) {
-    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
-    int rc = need(ctx, P_SEEDS, "f3ps_expand"); if (rc) return rc;
-    cudaSetDevice(ctx->device);
+static int expand_launch(f3ps_ctx* ctx, bool keep_centroids) {
     const unsigned V = ctx->V;
     ExpandArgs A;
-    rc = expand_prepare(ctx, A); if (rc) return rc;
+    int rc = expand_prepare(ctx, A); if (rc) return rc;
+    A.keep_centroids = keep_centroids ? 1 : 0;
+    if (keep_centroids) A.seeds = ctx->seeds_refine.as<int>();      // the seed voxels of f3ps_seeds stay what f3ps_get_seeds returns
     const bool cluster = V && ctx->expand_kernel_choice == 2;      // sweeps ask for it (f3ps_set_expand_kernel); one frame alone is fastest on the cooperative grid
     if (cluster) {
         // one thread-block cluster per frame (kernels_expand.cuh): ~2 voxels per thread, at most 16 CTAs
@@ -541,6 +540,36 @@ int f3ps_expand(f3ps_ctx* ctx) {
         ctx->launches++;
     }
     return expand_finish(ctx);
+}
+
+int f3ps_expand(f3ps_ctx* ctx) {
+    if (!ctx) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_SEEDS, "f3ps_expand"); if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    return expand_launch(ctx, false);
+}
+
+// pcl::SupervoxelClustering::refineSupervoxels(num_itr, ...): per iteration refineNormals, reseedSupervoxels and the expansion
+// rounds again, starting from the helpers' current centroids (kernels_vccs.cuh, kernels_expand.cuh).  Leaves the handle where
+// f3ps_expand leaves it: labels, distances, voxel normals and the supervoxels are the refined ones, the graph has to be rebuilt.
+int f3ps_refine(f3ps_ctx* ctx, int num_itr) {
+    if (!ctx || num_itr < 0) return F3PS_ERR_INVALID_ARGUMENT;
+    int rc = need(ctx, P_EXPANDED, "f3ps_refine"); if (rc) return rc;          // PCL: "Supervoxels must be extracted before they can be refined"
+    if (ctx->graph_from_host) return ctx_fail(ctx, F3PS_ERR_LOGIC, "f3ps_refine needs the voxels of f3ps_extract, not a graph set with f3ps_set_graph");
+    if (ctx->slab_range) return ctx_fail(ctx, F3PS_ERR_LOGIC, "f3ps_refine is not available in slab mode");
+    cudaSetDevice(ctx->device);
+    const unsigned V = ctx->V, S0 = ctx->S0;
+    F3PS_CUDA_OK(ctx->seeds_refine.ensure(((size_t)S0 + 1) * 4));
+    for (int it = 0; it < num_itr && V && S0; ++it) {
+        LAUNCH(ctx, refine_normals_kernel, grid_for(V, 128), 128, 0, ctx->vox_xyz.as<float4>(), ctx->nbr_row.as<int>(), SC(n_voxels),
+               ctx->owner0.as<unsigned>(), ctx->phantom.as<unsigned>(), ctx->vox_normal.as<float4>(), ctx->vox_curv.as<float>());
+        LAUNCH(ctx, reseed_kernel, (int)std::min<unsigned>(S0, 4u * kSMs), 256, 0, ctx->cen_xyz.as<float4>(), S0, ctx->vox_xyz.as<float4>(), SC(n_voxels),
+               ctx->seeds_refine.as<int>());
+        ctx->progress = P_SEEDS;
+        rc = expand_launch(ctx, true); if (rc) return rc;
+    }
+    ctx->progress = P_EXPANDED;
+    return F3PS_OK;
 }
 
 // ---- K6 -------------------------------------------------------------------------------------------

@@ -46,6 +46,7 @@ struct ExpandArgs {
     const float4* vox_xyz; const float4* vox_rgb; const float4* vox_nrm;
     const int* seeds;
     unsigned V, S0; int rounds;
+    int keep_centroids;               // refineSupervoxels: the helpers keep their centroids, seeds[i] < 0 = helper i + 1 was erased
     VccsParams P;
     // mutable state
     unsigned* owner[2]; float* dist[2]; unsigned* st[2];
@@ -318,14 +319,17 @@ __device__ __forceinline__ void expand_body(const ExpandArgs& A, ExpandSmem<THRE
     // ---- createSupervoxelHelpers -------------------------------------------------------------------
     for (unsigned v = tid; v < V; v += nthreads) { A.owner[0][v] = 0u; A.dist[0][v] = FLT_MAX; A.st[0][v] = kNoSteal; A.phantom[v] = 0u; }
     for (unsigned l = tid; l < S0 + 2; l += nthreads) {
-        A.cen.xyz[l] = make_float4(0, 0, 0, l >= 1 && l <= S0 ? 1.0f : 0.0f);   // SupervoxelHelper::centroid_ starts at zero (literal)
-        A.cen.rgb[l] = make_float4(0, 0, 0, 0); A.cen.nrm[l] = make_float4(0, 0, 0, 0);
+        if (!A.keep_centroids) {
+            A.cen.xyz[l] = make_float4(0, 0, 0, l >= 1 && l <= S0 ? 1.0f : 0.0f);   // SupervoxelHelper::centroid_ starts at zero (literal)
+            A.cen.rgb[l] = make_float4(0, 0, 0, 0); A.cen.nrm[l] = make_float4(0, 0, 0, 0);
+        }
         A.phantom_leaf[l] = -1; A.count[0][l] = 0u; A.count[1][l] = 0u; A.off[l] = 0u;
     }
     expand_barrier<CLUSTER>(ctl, nblocks, phase);
-    for (unsigned i = tid; i < S0; i += nthreads) atomicMax(&A.owner[0][A.seeds[i]], i + 1u);      // addLeaf: the last helper owns
+    for (unsigned i = tid; i < S0; i += nthreads) if (A.seeds[i] >= 0) atomicMax(&A.owner[0][A.seeds[i]], i + 1u);      // addLeaf: the last helper owns
     expand_barrier<CLUSTER>(ctl, nblocks, phase);
     for (unsigned i = tid; i < S0; i += nthreads) {
+        if (A.seeds[i] < 0) continue;
         const unsigned u = (unsigned)A.seeds[i];
         if ((ldcg_u(A.owner[0] + u) & kOwnMask) == i + 1u) continue;
         if (atomicCAS(&A.phantom[u], 0u, i + 1u) != 0u) atomicOr(&ctl->error, (unsigned)EXPAND_ERR_TRIPLE);   // not modelled

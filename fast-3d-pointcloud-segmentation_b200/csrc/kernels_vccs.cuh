@@ -338,6 +338,78 @@ __global__ void __launch_bounds__(128) voxel_normals_kernel(const float4* __rest
     }
 }
 
+// ---- refineSupervoxels, part 1: SupervoxelHelper::refineNormals (pcl supervoxel_clustering.hpp; call site
+// /root/reference/src/supervoxel_clustering.cpp:369-371).  A voxel's normal is recomputed from the index list
+// [u + N(u) for u in N(v)], every entry only when its owner is v's owner (N includes the voxel itself; duplicates kept).
+// Reads centroids and owners only, so the voxels are independent; unowned voxels keep their normal.  A phantom leaf (held by
+// helper `phantom[v]` without being owned by it) is recomputed twice in PCL, by its owner and by its holder, each with its own
+// filter; the helpers run in label order, so the later of the two decides -- the holder when a third helper with a smaller
+// label has stolen the voxel from its first owner.
+__global__ void __launch_bounds__(128) refine_normals_kernel(const float4* __restrict__ vox_xyz, const int* __restrict__ nbr_row,
+        const unsigned* __restrict__ n_vox_ptr, const unsigned* __restrict__ label, const unsigned* __restrict__ phantom,
+        float4* __restrict__ vox_normal, float* __restrict__ vox_curv) {
+    const unsigned V = *n_vox_ptr;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        unsigned L = label[v];
+        if (L == 0u) continue;
+        const unsigned ph = phantom[v];
+        if (ph > L) L = ph;
+        Accu9 A; A.clear();
+        int total = 0;
+        const float4 pv = vox_xyz[v];
+        const int* row = nbr_row + (size_t)v * kNbrStride;
+        const int cnt = row[27];
+        for (int a = 0; a < cnt; ++a) {
+            const int nb = row[a];
+            if (label[nb] != L) continue;
+            const float4 pn = vox_xyz[nb];
+            A.add(pn.x, pn.y, pn.z); ++total;
+            const int* rown = nbr_row + (size_t)nb * kNbrStride;
+            const int cn = rown[27];
+            for (int b = 0; b < cn; ++b) {
+                const int w = rown[b];
+                if (label[w] == L) { const float4 p2 = vox_xyz[w]; A.add(p2.x, p2.y, p2.z); ++total; }
+            }
+        }
+        float n[3]; float curv;
+        if (total < 3) { n[0] = n[1] = n[2] = nanf(""); curv = n[0]; }
+        else plane_from_accu(A.a, total, n, curv);
+        flip_and_normalize(pv.x, pv.y, pv.z, n);
+        vox_normal[v] = make_float4(n[0], n[1], n[2], 0.0f);
+        vox_curv[v] = curv;
+    }
+}
+
+// ---- refineSupervoxels, part 2: reseedSupervoxels.  Every surviving helper (centroid count > 0) takes the voxel nearest to its
+// centroid as its only leaf (voxel_kdtree_->nearestKSearch(point, 1): exact 1-NN under flann::L2_Simple, ties to the lowest
+// index); an erased helper gets -1.  One block per helper, brute force over the voxel centroids (S x V distance evaluations).
+__global__ void __launch_bounds__(256) reseed_kernel(const float4* __restrict__ cen_xyz, unsigned S0, const float4* __restrict__ vox_xyz,
+        const unsigned* __restrict__ n_vox_ptr, int* __restrict__ seeds) {
+    __shared__ unsigned long long s_best[8];
+    const unsigned V = *n_vox_ptr;
+    for (unsigned i = blockIdx.x; i < S0; i += gridDim.x) {
+        const float4 c = cen_xyz[i + 1];
+        if (!(c.w > 0.0f)) { if (threadIdx.x == 0) seeds[i] = -1; continue; }
+        unsigned long long best = ~0ull;                                   // (distance bits : voxel index), distances are >= 0
+        for (unsigned u = threadIdx.x; u < V; u += blockDim.x) {
+            const float4 p = vox_xyz[u];
+            float r = 0.0f;
+            { const float d0 = c.x - p.x; r += d0 * d0; const float d1 = c.y - p.y; r += d1 * d1; const float d2 = c.z - p.z; r += d2 * d2; }
+            const unsigned long long k = ((unsigned long long)__float_as_uint(r) << 32) | u;
+            if (!(r != r) && k < best) best = k;
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) { const unsigned long long o = __shfl_xor_sync(kFull, best, off); if (o < best) best = o; }
+        if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) if (s_best[w] < best) best = s_best[w];
+            seeds[i] = best == ~0ull ? -1 : (int)(unsigned)best;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- K4: seed selection (A.4) ---------------------------------------------------------------
 // Seed octree box growth (OctreePointCloud::adoptBoundingBoxToPoint) over the voxel centroids in
 // idx order.  One block; the cursor only moves forward, so the centroids are read once.

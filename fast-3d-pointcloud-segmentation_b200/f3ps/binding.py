@@ -104,6 +104,7 @@ def lib():
         "f3ps_merge_batch": (C.c_int, [C.POINTER(vp), C.c_int, f32]),
         "f3ps_set_expand_sharing": (C.c_int, [vp, C.c_int, C.c_int]),
         "f3ps_set_expand_kernel": (C.c_int, [vp, C.c_int, C.c_int]),
+        "f3ps_refine": (C.c_int, [vp, C.c_int]),
 
         "f3ps_eval_thresholds": (C.c_int, [vp, vp, i64, vp, i64, vp, C.c_int, vp, vp, vp]),
         "f3ps_eval_label_pairs": (C.c_int, [vp, vp, vp, i64, C.c_int, C.c_int, vp, i64, vp]),
@@ -136,7 +137,7 @@ EXPORTED = ["f3ps_create", "f3ps_destroy", "f3ps_last_error", "f3ps_version", "f
             "f3ps_get_merge_log", "f3ps_get_state_regions", "f3ps_get_state_edges", "f3ps_get_labeled_cloud", "f3ps_get_region_mean_color",
             "f3ps_get_voxel_segments_device", "f3ps_stage_ms", "f3ps_launch_count", "f3ps_merge_profile", "f3ps_merge_trace", "f3ps_expand_profile", "f3ps_test_rgb2lab",
             "f3ps_test_lab_ciede00", "f3ps_test_rgb_eucl", "f3ps_test_sort_pairs",
-            "f3ps_merge_batch", "f3ps_set_expand_sharing", "f3ps_set_expand_kernel", "f3ps_eval_thresholds", "f3ps_eval_label_pairs", "f3ps_slab_reset", "f3ps_slab_bbox", "f3ps_slab_set_frame", "f3ps_slab_keys", "f3ps_slab_route", "f3ps_slab_array",
+            "f3ps_merge_batch", "f3ps_set_expand_sharing", "f3ps_set_expand_kernel", "f3ps_refine", "f3ps_eval_thresholds", "f3ps_eval_label_pairs", "f3ps_slab_reset", "f3ps_slab_bbox", "f3ps_slab_set_frame", "f3ps_slab_keys", "f3ps_slab_route", "f3ps_slab_array",
             "f3ps_slab_set_voxels", "f3ps_slab_expand_begin", "f3ps_slab_expand_sweep", "f3ps_slab_expand_round_end",
             "f3ps_slab_expand_end"]
 
@@ -218,6 +219,7 @@ class Segmenter:
     def normals(self): self._chk(self.L.f3ps_normals(self.h))
     def seeds(self): self._chk(self.L.f3ps_seeds(self.h))
     def expand(self): self._chk(self.L.f3ps_expand(self.h))
+    def refine(self, num_itr=3): self._chk(self.L.f3ps_refine(self.h, num_itr))
     def graph(self): self._chk(self.L.f3ps_graph(self.h))
     def merge(self, threshold): self._chk(self.L.f3ps_merge(self.h, threshold))
     def set_merge_kernel(self, which): self._chk(self.L.f3ps_set_merge_kernel(self.h, which))

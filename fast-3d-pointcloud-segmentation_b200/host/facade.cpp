@@ -40,6 +40,47 @@ void SupervoxelClustering<PointT>::extract(std::map<uint32_t, typename pcl::Supe
     h_->check(f3ps_set_input(c, input_->points.data(), (int64_t)input_->points.size(), (int)sizeof(PointT), 0));
     h_->check(f3ps_extract(c));
     extracted_ = true;
+    collect(out);
+}
+
+// pcl::SupervoxelClustering::refineSupervoxels (src/supervoxel_clustering.cpp:369-371): num_itr rounds of refineNormals /
+// reseedSupervoxels / expandSupervoxels on the device (f3ps_refine), then makeSupervoxels into `out`.  As in PCL, the labelled
+// clouds and the adjacency the object returns afterwards are those of the refined supervoxels.
+template <typename PointT>
+void SupervoxelClustering<PointT>::refineSupervoxels(int num_itr, std::map<uint32_t, typename pcl::Supervoxel<PointT>::Ptr>& out) {
+    if (!extracted_) { fprintf(stderr, "Supervoxels must be extracted before they can be refined\n"); return; }   // PCL_FATAL + return
+    f3ps_ctx* c = h_->get();
+    h_->check(f3ps_refine(c, num_itr));
+    h_->check(f3ps_graph(c));
+    collect(out);
+}
+
+// getSupervoxelAdjacencyList: vertices = supervoxel labels, one undirected edge per adjacent pair, edge weight = distance between
+// the two centroids (PCL builds a boost::adjacency_list<setS, setS, undirectedS, uint32_t, float>; Boost is not a dependency here).
+template <typename PointT>
+void SupervoxelClustering<PointT>::getSupervoxelAdjacencyList(VoxelAdjacencyList& g) const {
+    g.vertices.clear(); g.edges.clear();
+    if (!extracted_) return;
+    f3ps_ctx* c = h_->get();
+    f3ps_counts n; h_->check(f3ps_get_counts(c, &n));
+    const size_t S = (size_t)n.n_supervoxels;
+    std::vector<uint32_t> label(S); std::vector<float> cen(3 * S);
+    h_->check(f3ps_get_supervoxels(c, label.data(), cen.data(), nullptr, nullptr, nullptr, (int64_t)S));
+    std::map<uint32_t, size_t> at;
+    for (size_t s = 0; s < S; ++s) { g.vertices.insert(label[s]); at[label[s]] = s; }
+    std::multimap<uint32_t, uint32_t> adj; getSupervoxelAdjacency(adj);
+    for (auto& kv : adj) {
+        if (kv.first >= kv.second) continue;
+        const float* a = &cen[3 * at[kv.first]]; const float* b = &cen[3 * at[kv.second]];
+        const float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+        g.edges[std::make_pair(kv.first, kv.second)] = std::sqrt(dx * dx + dy * dy + dz * dz);
+    }
+}
+
+template <typename PointT>
+void SupervoxelClustering<PointT>::collect(std::map<uint32_t, typename pcl::Supervoxel<PointT>::Ptr>& out) {
+    out.clear();
+    f3ps_ctx* c = h_->get();
     f3ps_counts n; h_->check(f3ps_get_counts(c, &n));
     const size_t V = (size_t)n.n_voxels, S = (size_t)n.n_supervoxels;
     std::vector<float> vxyz(3 * V), vn(4 * V), vcurv(V);

@@ -129,6 +129,37 @@ int main(int argc, char** argv) {
         try { segmentation.all_thresh(truth, 0.5f, 1.5f, 0.1f); } catch (const std::out_of_range&) { threw = true; }
         CHECK(threw, "all_thresh outside [0,1] must throw std::out_of_range (src/clustering.cpp:694-698)");
     }
+    {   // refineSupervoxels + getSupervoxelAdjacencyList (src/supervoxel_clustering.cpp:367-384) == f3ps_refine on the fused handle
+        pcl::SupervoxelClustering<pcl::PointXYZRGBA> sup2(0.008f, 0.08f);
+        sup2.setUseSingleCameraTransform(true); sup2.setInputCloud(cloud);
+        sup2.setColorImportance(0.2f); sup2.setSpatialImportance(0.4f); sup2.setNormalImportance(1.0f);
+        std::map<uint32_t, pcl::Supervoxel<pcl::PointXYZRGBA>::Ptr> first, refined;
+        sup2.extract(first);
+        f3ps::VoxelAdjacencyList gl; sup2.getSupervoxelAdjacencyList(gl);
+        CHECK(gl.vertices.size() == first.size() && (int)gl.edges.size() == n.n_edges, "adjacency list size");
+        for (auto& e : gl.edges) CHECK(e.first.first < e.first.second && e.second > 0.0f && gl.vertices.count(e.first.first) && gl.vertices.count(e.first.second), "adjacency list edge");
+        sup2.refineSupervoxels(3, refined);
+        f3ps::Handle h2(0);
+        h2.check(f3ps_set_vccs_params(h2.get(), 0.008f, 0.08f, 0.2f, 0.4f, 1.0f, 1, 0));
+        h2.check(f3ps_set_input(h2.get(), cloud->points.data(), (int64_t)cloud->points.size(), (int)sizeof(pcl::PointXYZRGBA), 0));
+        h2.check(f3ps_extract(h2.get())); h2.check(f3ps_refine(h2.get(), 3)); h2.check(f3ps_graph(h2.get()));
+        f3ps_counts n2; h2.check(f3ps_get_counts(h2.get(), &n2));
+        CHECK((int)refined.size() == n2.n_supervoxels && refined.size() > 0 && refined.size() <= first.size(), "refined supervoxel count");
+        std::vector<uint32_t> l2((size_t)n2.n_supervoxels); std::vector<float> c2(3 * (size_t)n2.n_supervoxels); std::vector<int32_t> k2((size_t)n2.n_supervoxels);
+        h2.check(f3ps_get_supervoxels(h2.get(), l2.data(), c2.data(), nullptr, nullptr, k2.data(), (int64_t)n2.n_supervoxels));
+        size_t s2 = 0;
+        for (auto& kv : refined) {
+            CHECK(kv.first == l2[s2] && kv.second->centroid_.x == c2[3 * s2] && kv.second->centroid_.z == c2[3 * s2 + 2] &&
+                  (int)kv.second->voxels_->size() == k2[s2], "refined supervoxel differs from f3ps_refine");
+            ++s2;
+        }
+        std::multimap<uint32_t, uint32_t> adj2; sup2.getSupervoxelAdjacency(adj2);
+        CHECK((int)adj2.size() == 2 * n2.n_edges, "adjacency after refinement");
+        pcl::SupervoxelClustering<pcl::PointXYZRGBA> sup3(0.008f, 0.08f);
+        std::map<uint32_t, pcl::Supervoxel<pcl::PointXYZRGBA>::Ptr> none;
+        sup3.refineSupervoxels(3, none);                                 // before extract(): PCL_FATAL + return, nothing happens
+        CHECK(none.empty(), "refine before extract");
+    }
     {   // Testing(segm, truth) == the fused sweep's score at the same threshold; label2color / color2label round trip
         segmentation.cluster(thr);
         PointLCloudT::Ptr seg = segmentation.get_labeled_cloud();

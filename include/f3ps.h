@@ -112,6 +112,13 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold); /* K7 Clustering::cluster(thresh
  * max_concurrent = 0 with ctas_per_frame > 0: still a cooperative launch, its grid capped at ctas_per_frame (a sweep trades the
  * latency of one frame for more frames side by side; the driver keeps guaranteeing co-residency). */
 int f3ps_set_expand_sharing(f3ps_ctx* ctx, int ctas_per_frame, int max_concurrent);
+/* pcl::SupervoxelClustering::refineSupervoxels(num_itr, clusters) (/root/reference/src/supervoxel_clustering.cpp:369-371) on the
+ * result of f3ps_expand / f3ps_extract: per iteration SupervoxelHelper::refineNormals (voxel normals from the neighbours of the
+ * same supervoxel), reseedSupervoxels (every helper restarts from the voxel nearest to its centroid) and the expansion rounds
+ * again from the helpers' current centroids.  Afterwards the per-voxel labels / distances / normals and the supervoxel getters
+ * return the refined state; the supervoxel graph is rebuilt by the next f3ps_graph / f3ps_merge.  Calling it before f3ps_expand
+ * is F3PS_ERR_LOGIC (PCL: "Supervoxels must be extracted before they can be refined"). */
+int f3ps_refine(f3ps_ctx* ctx, int num_itr);
 /* which K5 kernel f3ps_expand launches: 0 / 1 = the cooperative grid over the whole GPU (lowest latency for one frame: 0.8 ms on a
  * VGA frame, but ~50 SM-ms of mostly barrier waiting; f3ps_set_expand_sharing applies to it), 2 = ONE thread-block cluster per frame
  * (cluster_ctas = 1..16 CTAs of 1024 threads meeting at the hardware cluster barrier; 0 = two voxels per thread, at most 16): the

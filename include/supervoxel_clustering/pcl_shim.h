@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstring>
 #include <map>
+#include <set>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -119,6 +120,12 @@ private:
     f3ps_ctx* ctx_ = nullptr;
 };
 
+/* what pcl::SupervoxelClustering::getSupervoxelAdjacencyList fills (there a boost::adjacency_list<setS, setS, undirectedS, uint32_t, float>) */
+struct VoxelAdjacencyList {
+    std::set<uint32_t> vertices;                                  /* supervoxel labels */
+    std::map<std::pair<uint32_t, uint32_t>, float> edges;         /* (a < b) -> distance between the two centroids */
+};
+
 /* Drop-in for pcl::SupervoxelClustering<pcl::PointXYZRGBA> over the CUDA path (K1..K5 + supervoxel tables).
  * Same method names and semantics as the calls at src/supervoxel_clustering.cpp:348-367. */
 template <typename PointT>
@@ -135,12 +142,18 @@ public:
     pcl::PointCloud<pcl::PointXYZL>::Ptr getLabeledCloud() const;           /* input points with their supervoxel label */
     pcl::PointCloud<pcl::PointXYZL>::Ptr getLabeledVoxelCloud() const;
     void getSupervoxelAdjacency(std::multimap<uint32_t, uint32_t>& label_adjacency) const;
+    /* refineSupervoxels(num_itr, clusters), src/supervoxel_clustering.cpp:369-371: the labelled clouds / adjacency returned
+     * afterwards are the refined ones, as in PCL */
+    void refineSupervoxels(int num_itr, std::map<uint32_t, typename pcl::Supervoxel<PointT>::Ptr>& supervoxel_clusters);
+    /* getSupervoxelAdjacencyList, :376-384: labels as vertices, centroid distance as edge weight (a plain struct, not a BGL graph) */
+    void getSupervoxelAdjacencyList(VoxelAdjacencyList& adjacency_list_arg) const;
     static pcl::PointCloud<pcl::PointNormal>::Ptr makeSupervoxelNormalCloud(
         std::map<uint32_t, typename pcl::Supervoxel<PointT>::Ptr>& supervoxel_clusters);
     float getVoxelResolution() const { return resolution_; }
     float getSeedResolution() const { return seed_resolution_; }
     Handle& handle() { return *h_; }
 private:
+    void collect(std::map<uint32_t, typename pcl::Supervoxel<PointT>::Ptr>& supervoxel_clusters);   /* makeSupervoxels from the device tables */
     std::shared_ptr<Handle> h_;
     float resolution_, seed_resolution_;
     float color_importance_ = 0.1f, spatial_importance_ = 0.4f, normal_importance_ = 1.0f;   /* PCL defaults */

@@ -132,6 +132,7 @@ struct Oracle {
     void expand();              // K5  (A.5)
     void expand_fixed_point();  // K5, restated as the per-voxel fold + steal-table fixed point
     int sweeps_total = 0;
+    void refine(int num_itr);   // refineSupervoxels (supervoxel_clustering.cpp:369-371) on the result of expand()
     void make_supervoxels();    // K6a (A.6)
     void set_initialstate();    // clustering.cpp:605-612 on the VCCS output
     void init_weights();        // clustering.cpp:212-251

@@ -69,6 +69,13 @@ int orc_run(void* hv, int stage, float thr) {
     return 0;
 }
 
+// refineSupervoxels(num_itr) on the result of stage 5 (K5); stage 6 afterwards rebuilds the graph from the refined supervoxels
+int orc_refine(void* hv, int num_itr) {
+    Handle* h = (Handle*)hv;
+    try { h->O.refine(num_itr); } catch (const std::exception& e) { h->err = e.what(); return 2; }
+    return 0;
+}
+
 // Inject a graph directly (Clustering facade tests): regions given as voxel lists over
 // caller-provided voxel arrays.
 int orc_set_graph(void* hv, long V, const float* vxyz, const uint32_t* vrgba,

@@ -125,6 +125,13 @@ class Oracle:
         if rc:
             raise RuntimeError(self.L.orc_last_error(self.h).decode())
 
+    def refine(self, num_itr=3):
+        """pcl::SupervoxelClustering::refineSupervoxels on the result of run(5); run(6) afterwards rebuilds the graph"""
+        self.L.orc_refine.argtypes = [C.c_void_p, C.c_int]
+        rc = self.L.orc_refine(self.h, num_itr)
+        if rc:
+            raise RuntimeError(self.L.orc_last_error(self.h).decode())
+
     def set_graph(self, vxyz, vrgba, labels, vox_lists, centroids, normals, adj_pairs):
         vxyz = np.ascontiguousarray(vxyz, np.float32)
         vrgba = np.ascontiguousarray(vrgba, np.uint32)

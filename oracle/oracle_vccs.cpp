@@ -610,6 +610,125 @@ void Oracle::expand_fixed_point() {
     stage_ms[4] = now_ms() - t0;
 }
 
+// ---------------------------------------------------------------------------------
+// pcl::SupervoxelClustering::refineSupervoxels(num_itr, clusters) (call site /root/reference/src/supervoxel_clustering.cpp:369-371),
+// PCL 1.10 semantics restated (supervoxel_clustering.hpp): per iteration
+//   SupervoxelHelper::refineNormals   every leaf's normal / curvature from computePointNormal over the index list
+//                                     [neighbour u + u's neighbours, both only when owned by this helper] (duplicates kept,
+//                                     the leaf itself comes in as its own neighbour), flipped towards the origin, normalised
+//   reseedSupervoxels                 every helper drops its leaves (owner_ = 0, distance_ = max), then takes the voxel nearest
+//                                     to its centroid (kd-tree 1-NN) as its only leaf -- centroids are NOT reset
+//   expandSupervoxels(max_depth)      the rounds of extract(), starting from those centroids
+// and makeSupervoxels at the end.  Works on the surviving helpers of expand() (sv_* arrays) and leaves the same arrays behind.
+void Oracle::refine(int num_itr) {
+    const int V = (int)morton.size();
+    const int S = (int)sv_label.size();
+    std::vector<Helper> H(S);
+    std::vector<int> owner(V, -1);
+    for (int s = 0; s < S; ++s) {
+        H[s].label = sv_label[s];
+        H[s].leaves.insert(sv_leaves[s].begin(), sv_leaves[s].end());
+        for (int k = 0; k < 3; ++k) { H[s].xyz[k] = sv_xyz[3 * s + k]; H[s].rgb[k] = sv_rgb[3 * s + k]; }
+        for (int k = 0; k < 4; ++k) H[s].nrm[k] = sv_normal[4 * s + k];
+    }
+    std::map<uint32_t, int> helper_of;
+    for (int s = 0; s < S; ++s) helper_of[sv_label[s]] = s;
+    for (int v = 0; v < V; ++v) if (labels[v]) owner[v] = helper_of[labels[v]];
+    const float qnan = std::numeric_limits<float>::quiet_NaN();
+    auto update_centroid = [&](Helper& h) {
+        float n[4] = {0, 0, 0, 0}, x[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+        for (int u : h.leaves) {
+            for (int k = 0; k < 4; ++k) n[k] += normals[(size_t)u * 4 + k];
+            for (int k = 0; k < 3; ++k) { x[k] += vxyz[3 * u + k]; c[k] += vrgb[3 * u + k]; }
+        }
+        float z = sum4(n[0] * n[0], n[1] * n[1], n[2] * n[2], n[3] * n[3]);
+        if (z > 0.0f) { float sq = std::sqrt(z); for (int k = 0; k < 4; ++k) n[k] /= sq; }
+        float cnt = (float)h.leaves.size();
+        for (int k = 0; k < 3; ++k) { h.xyz[k] = x[k] / cnt; h.rgb[k] = c[k] / cnt; }
+        for (int k = 0; k < 4; ++k) h.nrm[k] = n[k];
+    };
+    auto vdist = [&](const Helper& h, int u) {
+        float dx[3], dc[3];
+        for (int k = 0; k < 3; ++k) { dx[k] = h.xyz[k] - vxyz[3 * u + k]; dc[k] = h.rgb[k] - vrgb[3 * u + k]; }
+        float spatial = std::sqrt(dot3(dx, dx)) / P.seed_res;
+        float color = std::sqrt(dot3(dc, dc)) / 255.0f;
+        const float* m = &normals[(size_t)u * 4];
+        float cosang = 1.0f - std::abs(sum4(h.nrm[0] * m[0], h.nrm[1] * m[1], h.nrm[2] * m[2], h.nrm[3] * m[3]));
+        return cosang * P.normal_imp + color * P.color_imp + spatial * P.spatial_imp;
+    };
+    const int max_depth = (int)(1.8f * P.seed_res / P.voxel_res);
+    for (int itr = 0; itr < num_itr; ++itr) {
+        // ---- refineNormals (helpers in list order; reads only centroids and owners, so the last writer of a voxel decides) ----
+        std::vector<float> nn = normals, cc = curvature;
+        for (int hi = 0; hi < (int)H.size(); ++hi) {
+            if (!H[hi].alive) continue;
+            for (int v : H[hi].leaves) {
+                float accu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; int cnt = 0;
+                auto add = [&](int i) {
+                    const float x = vxyz[3 * i], y = vxyz[3 * i + 1], z = vxyz[3 * i + 2];
+                    accu[0] += x * x; accu[1] += x * y; accu[2] += x * z; accu[3] += y * y; accu[4] += y * z; accu[5] += z * z;
+                    accu[6] += x; accu[7] += y; accu[8] += z; ++cnt; };
+                for (int a = 0; a < nbr_count[v]; ++a) {
+                    const int u = nbr[(size_t)v * 27 + a];
+                    if (owner[u] != hi) continue;
+                    add(u);
+                    for (int b = 0; b < nbr_count[u]; ++b) { const int w = nbr[(size_t)u * 27 + b]; if (owner[w] == hi) add(w); }
+                }
+                float n4[4]; float curv;
+                if (cnt < 3) { n4[0] = n4[1] = n4[2] = n4[3] = qnan; curv = qnan; }
+                else plane_from_accu(accu, cnt, n4, &curv);
+                flip_and_normalize(&vxyz[3 * v], n4);
+                for (int k = 0; k < 4; ++k) nn[(size_t)v * 4 + k] = n4[k];
+                cc[v] = curv;
+            }
+        }
+        normals.swap(nn); curvature.swap(cc);
+        // ---- reseedSupervoxels ----
+        for (auto& h : H) { for (int u : h.leaves) { owner[u] = -1; dist[u] = std::numeric_limits<float>::max(); } h.leaves.clear(); }
+        for (int hi = 0; hi < (int)H.size(); ++hi) {
+            if (!H[hi].alive) continue;
+            int best = -1; float bd = 0;
+            for (int u = 0; u < V; ++u) {                       // exact 1-NN (flann::L2_Simple), ties to the lowest index
+                float r = 0.0f; for (int k = 0; k < 3; ++k) { const float df = H[hi].xyz[k] - vxyz[3 * u + k]; r += df * df; }
+                if (best < 0 || r < bd) { best = u; bd = r; }
+            }
+            if (best >= 0) { H[hi].leaves.insert(best); owner[best] = hi; }
+        }
+        // ---- expandSupervoxels ----
+        for (int it = 1; it < max_depth; ++it) {
+            for (int hi = 0; hi < (int)H.size(); ++hi) {
+                Helper& h = H[hi];
+                if (!h.alive) continue;
+                std::vector<int> new_owned;
+                for (int u : h.leaves)
+                    for (int a = 0; a < nbr_count[u]; ++a) {
+                        const int nb = nbr[(size_t)u * 27 + a];
+                        if (owner[nb] == hi) continue;
+                        const float dd = vdist(h, nb);
+                        if (dd < dist[nb]) {
+                            dist[nb] = dd;
+                            if (owner[nb] >= 0) H[owner[nb]].leaves.erase(nb);
+                            owner[nb] = hi;
+                            new_owned.push_back(nb);
+                        }
+                    }
+                for (int u : new_owned) h.leaves.insert(u);
+            }
+            for (auto& h : H) { if (!h.alive) continue; if (h.leaves.empty()) h.alive = false; else update_centroid(h); }
+        }
+    }
+    for (int v = 0; v < V; ++v) labels[v] = owner[v] >= 0 ? H[owner[v]].label : 0;
+    sv_label.clear(); sv_xyz.clear(); sv_rgb.clear(); sv_normal.clear(); sv_count.clear(); sv_leaves.clear();
+    for (auto& h : H) {
+        if (!h.alive) continue;
+        sv_leaves.push_back(std::vector<int>(h.leaves.begin(), h.leaves.end()));
+        sv_label.push_back(h.label);
+        for (int k = 0; k < 3; ++k) { sv_xyz.push_back(h.xyz[k]); sv_rgb.push_back(h.rgb[k]); }
+        for (int k = 0; k < 4; ++k) sv_normal.push_back(h.nrm[k]);
+        sv_count.push_back((int)h.leaves.size());
+    }
+}
+
 // K6a: makeSupervoxels + getSupervoxelAdjacency (A.6): both walk the helpers' LEAF SETS (getVoxels,
 // getNeighborLabels), so a phantom leaf (see expand_fixed_point) is listed by its holder as well.
 void Oracle::make_supervoxels() {

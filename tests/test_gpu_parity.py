@@ -198,6 +198,28 @@ def test_expand_cluster_kernel_equals_cooperative_grid(gpu, oracle_mod, seed, w,
         g.set_expand_kernel(2, 17)
 
 
+@pytest.mark.parametrize("seed,w,h,itr", [(11, 160, 120, 3), (52, 160, 120, 2), (20020, 640, 480, 3)], ids=["small", "phantom", "vga"])
+def test_refine_supervoxels_matches_oracle(gpu, oracle_mod, seed, w, h, itr):
+    """pcl::SupervoxelClustering::refineSupervoxels (src/supervoxel_clustering.cpp:369-371): refineNormals, reseedSupervoxels and
+    the expansion rounds from the helpers' current centroids, num_itr times.  f3ps_refine against the oracle's literal sequential
+    restatement: refined voxel normals, labels, distances, supervoxels, and everything rebuilt on top (graph, weights, merges)."""
+    pts = gpu.synth.make_frame(seed=seed, width=w, height=h)
+    o = oracle_mod.Oracle(); o.set_vccs_params(); o.set_merge_params(merge_impl=1, **AL); o.set_input(pts)
+    for st in (1, 2, 3, 4, 5):
+        o.run(st)
+    s_before = len(o.array("sv_label")); labels_before = o.array("labels").copy()
+    o.refine(itr); o.run(6); o.run(7, 0.2)
+    g = gpu.Segmenter(); g.set_vccs_params(); g.set_merge_params(**AL); g.set_input(pts)
+    with pytest.raises(gpu.LogicError):
+        g.refine(itr)                                       # "Supervoxels must be extracted before they can be refined"
+    g.extract(); g.refine(itr); g.graph(); g.merge(0.2)
+    assert_parity(g, o, ["normals", "curvature", "labels", "dist", "sv_label", "sv_xyz", "sv_rgb", "sv_normal", "sv_count", "adj",
+                         "edges_ab", "edges_dc", "edges_dg", "edges_w", "seeds"] + MERGE_ARRAYS)
+    assert len(g.array("sv_label")) <= s_before and np.mean(g.array("labels") != labels_before) > 0.01    # it did something
+    g.refine(0)                                             # zero iterations: makeSupervoxels only, nothing moves
+    assert same(g.array("labels"), o.array("labels"))
+
+
 def test_no_transform_and_other_resolutions(gpu, oracle_mod, small_frame):
     g, o = run_both(gpu, oracle_mod, small_frame, RGB_ML, 0.2, use_transform=False, voxel_res=0.02, seed_res=0.15)
     assert_parity(g, o, STAGE_ARRAYS + MERGE_ARRAYS)

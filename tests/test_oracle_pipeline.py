@@ -211,3 +211,28 @@ def test_expansion_fixed_point_equals_literal_sequential(oracle_mod, seed, w, h)
         assert np.array_equal(bits(lit.array(n)), bits(fp.array(n))), n
     if seed in (16, 52, 127):
         assert int(lit.array("sv_count").sum()) > int((lit.array("labels") > 0).sum())      # a phantom leaf survived
+
+
+def test_refine_supervoxels_oracle_invariants(oracle_mod):
+    """Oracle::refine (pcl refineSupervoxels restated): labels stay a partition into the surviving helpers, every helper's
+    leaf list is its label's voxels (+ at most one phantom leaf), the helper count never grows, zero iterations change nothing."""
+    from f3ps import synth
+    pts = synth.make_frame(seed=11, width=160, height=120)
+    o = oracle_mod.Oracle(); o.set_vccs_params(); o.set_merge_params(merge_impl=1, **AL); o.set_input(pts)
+    for st in (1, 2, 3, 4, 5):
+        o.run(st)
+    l0 = o.array("labels").copy(); s0 = o.array("sv_label").copy(); n0 = o.array("normals").copy()
+    o.refine(0)
+    assert np.array_equal(o.array("labels"), l0) and np.array_equal(o.array("sv_label"), s0)
+    o.refine(2)
+    l1 = o.array("labels"); s1 = o.array("sv_label"); c1 = o.array("sv_count")
+    assert set(s1.tolist()) <= set(s0.tolist()) and len(s1) <= len(s0)
+    assert set(np.unique(l1[l1 > 0]).tolist()) == set(s1.tolist())
+    owned = np.bincount(l1, minlength=int(s0.max()) + 1)[s1]
+    assert np.all((c1 == owned) | (c1 == owned + 1))
+    n1 = o.array("normals")
+    assert not np.array_equal(n0, n1, equal_nan=True)
+    nn = np.linalg.norm(n1[:, :3][np.isfinite(n1[:, 0])], axis=1)
+    assert np.allclose(nn, 1.0, atol=1e-4)
+    o.run(6); o.run(7, 0.2)
+    assert len(o.array("merges_ab")) > 0
