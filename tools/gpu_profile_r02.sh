@@ -28,5 +28,5 @@ c = g.counts(); print(c.n_points, c.n_voxels, c.n_seeds, c.n_supervoxels, c.n_ed
 PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r02.csv python /tmp/one.py > gpurun_out/r02_ncu_launch.log 2>&1; echo "launch list rc=$?"
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:merge_fast --launch-skip 1 --launch-count 1 -o gpurun_out/prof_merge_lean_r02 -f python /tmp/one.py > gpurun_out/r02_ncu_merge.log 2>&1; echo "merge rc=$?"
-timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --launch-skip 70 -c 200 --csv --log-file gpurun_out/c4_dram_r02.csv python /tmp/c4.py > gpurun_out/r02_ncu_c4.log 2>&1; echo "c4 rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 300 --csv --log-file gpurun_out/c4_dram_r02.csv python /tmp/c4.py > gpurun_out/r02_ncu_c4.log 2>&1; echo "c4 rc=$?"
 tail -2 gpurun_out/r02_ncu_c4.log

@@ -1,5 +1,5 @@
 """Executed warp instructions per CUDA source line: joins `ncu --page source --csv` (SASS rows in order) with `nvdisasm -g` of the
-same kernel.  usage: ncu_lines.py <source.csv> <nvdisasm.txt> [top]"""
+same kernel.  usage: ncu_lines.py <source.csv> <nvdisasm.txt> [top] [source dir of the profiled build]"""
 import csv, re, collections, sys, os
 dis = open(sys.argv[2]).read().splitlines()
 cur = None; seq = []
@@ -16,7 +16,7 @@ by = collections.Counter(); bys = collections.Counter()
 for i in range(len(seq)):
     by[seq[i]] += int(data[i][ie]); bys[seq[i]] += int(data[i][ist])
 tot = sum(by.values()); print("total warp instructions", tot, " samples", sum(bys.values()))
-root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fast-3d-pointcloud-segmentation_b200", "csrc")
+root = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fast-3d-pointcloud-segmentation_b200", "csrc")
 src = {}
 for k, v in by.most_common(int(sys.argv[3]) if len(sys.argv) > 3 else 30):
     line = ""
