@@ -751,10 +751,10 @@ int f3ps_set_graph(f3ps_ctx* ctx, int64_t n_voxels, const float* voxel_xyz, cons
 // ---- K7 -------------------------------------------------------------------------------------------
 extern "C++" {
 namespace {
-// blocks of 32 edges per worker warp of the resident kernel (0 = the graph does not fit): E_cap = 928 * blocks
-int lean_slots_for(unsigned E) {
+// edge capacity of the resident kernel's tables: E rounded up to whole blocks of 32 edges (0 = more than 32 blocks per worker warp)
+unsigned lean_ecap_for(unsigned E) {
     const unsigned nb = std::max(1u, (E + (unsigned)kFastOwners - 1u) / (unsigned)kFastOwners);
-    return nb <= 32u ? (int)nb : 0;
+    return nb <= 32u ? std::max(32u, (E + 31u) & ~31u) : 0u;
 }
 void (*lean_kernel_for(bool prof))(FastArgs) { return prof ? merge_fast_kernel<true> : merge_fast_kernel<false>; }
 // adjacency pool of the resident kernel (edge ids, 2 bytes each): the initial lists plus room for the lists that outgrow their block
@@ -804,10 +804,9 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
         EdgeParams ep = edge_params(ctx);
         // resident kernel when the graph fits one SM (kernels_merge_lean.cuh), else the general one
         const unsigned S_cap = (S + 7u) & ~7u;
-        const int slots = lean_slots_for(E);
-        const unsigned E_cap = (unsigned)std::max(slots, 1) * kFastOwners;
+        const unsigned E_cap = std::max(32u, lean_ecap_for(E));
         const size_t fast_bytes = FastSmem(nullptr, S_cap, E_cap).bytes;
-        const bool single_ok = slots && S <= 4096u && fast_bytes <= 227u * 1024u && P > 0;
+        const bool single_ok = lean_ecap_for(E) && S <= 4096u && fast_bytes <= 227u * 1024u && P > 0;
         bool fast = !ctx->force_general_merge && single_ok;
         for (int attempt = 0; attempt < 2; ++attempt) {
             if (attempt == 1) {                                    // a merge overflowed the resident kernel's touched list: start over
@@ -899,21 +898,21 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
     cudaSetDevice(ctxs[0]->device);
     int rc;
     std::vector<int> batch, solo;
-    std::vector<int> slots_of(n, 0);
+    std::vector<int> slots_of(n, 0);                         // per handle: edge capacity of its tables
     for (int i = 0; i < n; ++i) {
         f3ps_ctx* ctx = ctxs[i];
         if (ctx->progress < P_GRAPH) { rc = f3ps_graph(ctx); if (rc) return rc; }
         const unsigned S = ctx->S, E = ctx->E, P = ctx->n_pos;
-        const int slots = lean_slots_for(E);
-        const bool ok = S > 0 && slots && S <= 4096u && P > 0 && !ctx->force_general_merge;
-        slots_of[i] = slots;
+        const unsigned ecap = lean_ecap_for(E);
+        const bool ok = S > 0 && ecap && S <= 4096u && P > 0 && !ctx->force_general_merge;
+        slots_of[i] = (int)ecap;
         (ok ? batch : solo).push_back(i);
     }
     {   // every frame brings its own table capacities (the layout is per CTA); the launch asks for the largest footprint
         std::vector<int> keep;
         for (int i : batch) {
             const unsigned S_cap = (ctxs[i]->S + 7u) & ~7u;
-            if (FastSmem(nullptr, S_cap, (unsigned)slots_of[i] * kFastOwners).bytes <= 227u * 1024u) keep.push_back(i); else solo.push_back(i);
+            if (FastSmem(nullptr, S_cap, (unsigned)slots_of[i]).bytes <= 227u * 1024u) keep.push_back(i); else solo.push_back(i);
         }
         batch.swap(keep);
     }
@@ -943,7 +942,7 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
             A.R = ctx->R1; A.E = ctx->E1; A.n_edges_ptr = SC(n_edges); A.n_sv_ptr = SC(xctl.n_sv); A.ep = edge_params(ctx); A.lambda_dev = SC(lambda);
             A.threshold = threshold; A.run_start = ctx->run_start.as<unsigned>(); A.run_end = ctx->run_end.as<unsigned>();
             A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
-            A.ctl = SC(mctl); A.S_cap = (S + 7u) & ~7u; A.E_cap = (unsigned)slots_of[batch[k]] * kFastOwners;
+            A.ctl = SC(mctl); A.S_cap = (S + 7u) & ~7u; A.E_cap = (unsigned)slots_of[batch[k]];
             rc = lean_pool(ctx, ctx->E, A); if (rc) return rc;
             A.trace = nullptr; A.trace_first = 0;
             bytes = std::max(bytes, FastSmem(nullptr, A.S_cap, A.E_cap).bytes);

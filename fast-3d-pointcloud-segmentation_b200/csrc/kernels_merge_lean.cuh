@@ -53,7 +53,7 @@ struct FastArgs {
     MergeCtl* ctl;
     unsigned short* adj_pool; unsigned pool_cap;   // adjacency lists (edge ids), bump-allocated; entries
     unsigned* trace; unsigned trace_first;         // PROF only: clock() of 32 points of 256 merges starting at trace_first (f3ps_get_merge_trace)
-    unsigned S_cap, E_cap;                   // table capacities the shared-memory layout was sized for (E_cap = 928 * blocks per warp)
+    unsigned S_cap, E_cap;                   // table capacities the shared-memory layout was sized for (E_cap = E rounded up to whole blocks of 32 edges)
 };
 
 // shared-memory layout, shared by host (size) and device (pointers)
@@ -70,7 +70,7 @@ struct FastSmem {
     unsigned* adj_start; unsigned short *adj_len, *adj_cap;
     size_t bytes;
     // Fixed-size tables first (compile-time offsets), then the two per-edge tables, then the per-region ones: every pointer is
-    // base + constant (+ k * E_cap) (+ k * S) with S a multiple of 8 and E_cap a multiple of 928, so no alignment rounding depends
+    // base + constant (+ k * E_cap) (+ k * S) with S a multiple of 8 and E_cap a multiple of 32, so no alignment rounding depends
     // on a run-time value.  (ncu, round 2: the generic bump allocator this replaces cost 8 % of the kernel's instructions --
     // the 30 pointers do not fit the 64 registers and were re-derived through its dependent additions all over the merge loop.)
     __host__ __device__ FastSmem(char* base, unsigned S, unsigned E_cap) {
@@ -271,7 +271,8 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
     int* const newgeo_i = reinterpret_cast<int*>(sm.newgeo);
 
     // ---- set-up: ropes, edges, adjacency lists -> shared memory / the pool ------------------------------------------------
-    const unsigned nbw = A.E_cap / kFastOwners;                                // blocks of 32 edges per worker warp
+    const unsigned nblk = A.E_cap / 32u;                                       // blocks of 32 edges; warp w owns w, w + 29, ...
+    const unsigned nbw = (nblk + kLeanWorkerWarps - 1u) / kLeanWorkerWarps;   // (the last row of blocks may be partial)
     static_assert((kLeanRing + 2) * kLeanSlotVox * 16 >= 4096 * 4, "set-up scratch: one word per region");
     unsigned* const cursor = reinterpret_cast<unsigned*>(sm.stage);           // scratch: ring + private stages are idle until the first merge
     for (unsigned s = tid; s < S; s += kFastThreads) {
@@ -561,8 +562,9 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                 unsigned long long best = kDeadKey64; unsigned be = 0;
 #pragma unroll 4
                 for (unsigned j = 0; j < nbw; ++j) {
-                    const unsigned e = ((unsigned)ww + kLeanWorkerWarps * j) * 32u + (unsigned)lane;
-                    const unsigned long long k = sm.key[e];
+                    const unsigned blk = (unsigned)ww + kLeanWorkerWarps * j;
+                    const unsigned e = blk * 32u + (unsigned)lane;
+                    const unsigned long long k = blk < nblk ? sm.key[e] : kDeadKey64;
                     if (k < best) { best = k; be = e; }
                 }
                 const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
