@@ -88,6 +88,7 @@ struct f3ps_ctx {
     f3ps::DevBuf vox_normal, vox_curv;
     // K4
     f3ps::DevBuf cell_code, cell_code_b, cell_vox, cell_vox_b, vox_cell, cell_start, cell_codes, cell_nn, cell_keep, seeds;
+    f3ps::DevBuf lean_big;                    // K7 resident kernel, BIG variant: per-edge / per-region tables + set-up scratch in global memory
     f3ps::DevBuf seeds_refine;                // reseedSupervoxels: one voxel per helper, -1 = erased (f3ps_refine)
     // K5
     f3ps::DevBuf owner0, dist0;                       // results: clean label / stored distance per voxel

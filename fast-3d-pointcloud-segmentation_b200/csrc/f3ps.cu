@@ -806,10 +806,19 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
         const unsigned S_cap = (S + 7u) & ~7u;
         const unsigned E_cap = std::max(32u, lean_ecap_for(E));
         const size_t fast_bytes = FastSmem(nullptr, S_cap, E_cap).bytes;
-        const bool single_ok = lean_ecap_for(E) && S <= 4096u && fast_bytes <= 227u * 1024u && P > 0;
-        bool fast = !ctx->force_general_merge && single_ok;
+        const bool single_ok = lean_ecap_for(E) && S <= 4096u && fast_bytes <= 227u * 1024u && P > 0 && ctx->merge_kernel_choice != 3;
+        // graphs that do not fit an SM: the same kernel with its big tables in global memory (16-bit region / edge ids)
+        const unsigned E_big = (E + 31u) & ~31u;
+        const bool big_ok = !single_ok && P > 0 && S < 65535u && E_big <= 65504u && ctx->merge_kernel_choice != 1 &&
+                            FastSmem(nullptr, S_cap, E_big, (char*)16).bytes <= 227u * 1024u;
+        bool fast = !ctx->force_general_merge && (single_ok || big_ok);
+        bool resume = false;
         for (int attempt = 0; attempt < 2; ++attempt) {
-            if (attempt == 1) {                                    // a merge overflowed the resident kernel's touched list: start over
+            if (attempt == 1 && resume) {
+                // the resident kernel stopped in front of a merge that touches more edges than it has worker threads; its state
+                // (regions, edges, stamps, ropes, log, counters) is that after n_merges merges: the general kernel continues from it
+                F3PS_CUDA_OK(cudaMemsetAsync(SC(mctl.error), 0, 4, ctx->stream));
+            } else if (attempt == 1) {                             // adjacency pool / stamp range exhausted: start over
                 F3PS_CUDA_OK(cudaMemcpyAsync(ctx->reg_work.p, ctx->reg_init.p, region_bytes(Sc), cudaMemcpyDeviceToDevice, ctx->stream));
                 F3PS_CUDA_OK(cudaMemcpyAsync(ctx->edge_work.p, ctx->edge_init.p, eb, cudaMemcpyDeviceToDevice, ctx->stream));
                 F3PS_CUDA_OK(cudaMemsetAsync(SC(mctl), 0, sizeof(MergeCtl), ctx->stream));
@@ -821,8 +830,16 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
                 A.threshold = threshold; A.run_start = ctx->run_start.as<unsigned>(); A.run_end = ctx->run_end.as<unsigned>();
                 A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
                 A.ctl = SC(mctl); A.S_cap = S_cap;
-                A.E_cap = E_cap;
-                void (*kern)(FastArgs) = lean_kernel_for(ctx->merge_kernel_choice == 4);
+                A.E_cap = single_ok ? E_cap : E_big;
+                A.big = nullptr; A.big_cursor = nullptr;
+                void (*kern)(FastArgs) = single_ok ? lean_kernel_for(ctx->merge_kernel_choice == 4) : merge_fast_big_kernel;
+                size_t launch_bytes = fast_bytes;
+                if (!single_ok) {
+                    const size_t bb = (FastSmem::big_bytes(S_cap, E_big) + 255) & ~(size_t)255;
+                    F3PS_CUDA_OK(ctx->lean_big.ensure(bb + (size_t)S_cap * 4));
+                    A.big = (char*)ctx->lean_big.p; A.big_cursor = (unsigned*)((char*)ctx->lean_big.p + bb);
+                    launch_bytes = FastSmem(nullptr, S_cap, E_big, A.big).bytes;
+                }
                 rc = lean_attr(ctx, (const void*)kern); if (rc) return rc;
                 rc = lean_pool(ctx, E, A); if (rc) return rc;
                 A.trace = nullptr; A.trace_first = ctx->merge_trace_first;
@@ -831,10 +848,10 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
                     F3PS_CUDA_OK(cudaMemsetAsync(ctx->merge_trace.p, 0, 256 * 32 * 4, ctx->stream));
                     A.trace = ctx->merge_trace.as<unsigned>();
                 }
-                kern<<<1, kFastThreads, fast_bytes, ctx->stream>>>(A);
+                kern<<<1, kFastThreads, launch_bytes, ctx->stream>>>(A);
                 ctx->launches++;
                 F3PS_CUDA_OK(cudaPeekAtLastError());
-                ctx->merge_path = 1;
+                ctx->merge_path = single_ok ? 1 : 3;
             } else {
                 const size_t per = ((size_t)Ec * 4 + 255) & ~(size_t)255, per8 = ((size_t)Ec * 8 + 255) & ~(size_t)255;
                 unsigned n2 = 2048; while (n2 < Ec) n2 <<= 1;
@@ -855,16 +872,17 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
                 }
                 if (S < 65536u)
                     LAUNCH(ctx, merge_kernel<unsigned>, 1, kMergeThreads, dyn, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
-                           ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr, (unsigned*)sp, ctx->pos_data);
+                           ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr, (unsigned*)sp, ctx->pos_data, resume ? 1 : 0);
                 else
                     LAUNCH(ctx, merge_kernel<unsigned long long>, 1, kMergeThreads, dyn, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
-                           ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr, (unsigned long long*)sp, ctx->pos_data);
-                ctx->merge_path = 2;
+                           ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr, (unsigned long long*)sp, ctx->pos_data, resume ? 1 : 0);
+                ctx->merge_path = resume ? (ctx->merge_path == 3 ? 5 : 4) : 2;
             }
             rc = mark(ctx, 10); if (rc) return rc;
             if (!fast) break;
             rc = pull_scalars(ctx); if (rc) return rc;           // did the resident kernel finish?
             if (ctx->h_sc->mctl.error == 0) break;
+            resume = ctx->h_sc->mctl.error == kFastErrTouched;
             fast = false;
         }
         LAUNCH(ctx, dense_label_kernel, 1, 1024, 0, ctx->R1, SC(xctl.n_sv), ctx->run_start.as<unsigned>(), ctx->run_end.as<unsigned>(), ctx->run_out_off.as<unsigned>(),
@@ -944,7 +962,7 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
             A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
             A.ctl = SC(mctl); A.S_cap = (S + 7u) & ~7u; A.E_cap = (unsigned)slots_of[batch[k]];
             rc = lean_pool(ctx, ctx->E, A); if (rc) return rc;
-            A.trace = nullptr; A.trace_first = 0;
+            A.trace = nullptr; A.trace_first = 0; A.big = nullptr; A.big_cursor = nullptr;
             bytes = std::max(bytes, FastSmem(nullptr, A.S_cap, A.E_cap).bytes);
             rc = mark(ctx, 9); if (rc) return rc;
             if (ctx->stream != lead->stream) {               // the lead's stream runs the grid: it waits for everybody's set-up
@@ -1029,7 +1047,7 @@ int f3ps_set_blocking_wait(f3ps_ctx* ctx, int blocking) {
 }
 
 int f3ps_set_merge_kernel(f3ps_ctx* ctx, int which) {
-    if (!ctx || which < 0 || which > 4 || which == 3) return F3PS_ERR_INVALID_ARGUMENT;
+    if (!ctx || which < 0 || which > 4) return F3PS_ERR_INVALID_ARGUMENT;
     ctx->force_general_merge = which == 2;
     ctx->merge_kernel_choice = which;
     return F3PS_OK;

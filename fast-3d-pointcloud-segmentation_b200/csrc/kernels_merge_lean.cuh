@@ -53,6 +53,7 @@ struct FastArgs {
     MergeCtl* ctl;
     unsigned short* adj_pool; unsigned pool_cap;   // adjacency lists (edge ids), bump-allocated; entries
     unsigned* trace; unsigned trace_first;         // PROF only: clock() of 32 points of 256 merges starting at trace_first (f3ps_get_merge_trace)
+    char* big; unsigned* big_cursor;         // BIG variant only: the per-edge / per-region tables (12 E_cap + 26 S_cap bytes) and the set-up scratch (4 S_cap) in global memory
     unsigned S_cap, E_cap;                   // table capacities the shared-memory layout was sized for (E_cap = E rounded up to whole blocks of 32 edges)
 };
 
@@ -73,7 +74,11 @@ struct FastSmem {
     // base + constant (+ k * E_cap) (+ k * S) with S a multiple of 8 and E_cap a multiple of 32, so no alignment rounding depends
     // on a run-time value.  (ncu, round 2: the generic bump allocator this replaces cost 8 % of the kernel's instructions --
     // the 30 pointers do not fit the 64 registers and were re-derived through its dependent additions all over the merge loop.)
-    __host__ __device__ FastSmem(char* base, unsigned S, unsigned E_cap) {
+    // BIG variant (graphs that do not fit an SM: S up to 65,534, E up to 65,504): the per-edge and per-region tables live in global
+    // memory (`big`, L2-resident) and shared memory keeps, per block of 32 edges, the block's minimum key with its edge and end
+    // points (bm_*) and a dirty bit -- a re-weighted edge costs its block one coalesced 256-byte reload, never a scan of the map.
+    unsigned long long* bm_key; unsigned *bm_e, *bm_ab, *blkdirty;
+    __host__ __device__ FastSmem(char* base, unsigned S, unsigned E_cap, char* big = nullptr) {
         size_t o = 0;
         auto take = [&](size_t b) { char* p = base + o; o += (b + 15) & ~(size_t)15; return p; };
         mbar = (unsigned long long*)take(2 * kLeanRing * 8);
@@ -85,15 +90,24 @@ struct FastSmem {
         hkey = (unsigned*)take(kLeanHash * 4); hcnt = (unsigned*)take(kLeanHash * 4);
         wm_key = (unsigned long long*)take(32 * 8); wm_e = (unsigned*)take(32 * 4); wm_ab = (unsigned*)take(32 * 4);
         newgeo = (float*)take(16 * 4); misc = (int*)take(16 * 4); inv = (float*)take(64 * 4); bdirty = (unsigned*)take(32 * 4);
-        char* const eb = base + o;                                // o is a compile-time constant up to here
+        char* eb = base + o;                                      // o is a compile-time constant up to here
+        bm_key = nullptr; bm_e = bm_ab = blkdirty = nullptr;
+        if (big) {
+            const size_t nblk = E_cap / 32u;
+            bm_key = (unsigned long long*)eb; bm_e = (unsigned*)(eb + nblk * 8); bm_ab = (unsigned*)(eb + nblk * 12);
+            blkdirty = (unsigned*)(eb + nblk * 16);
+            o += nblk * 16 + ((nblk + 31) / 32) * 4;
+            eb = big;
+        }
         key = (unsigned long long*)eb; ab = (unsigned*)(eb + (size_t)E_cap * 8);
         char* const sb = eb + (size_t)E_cap * 12;
         rs = (unsigned*)sb; n = (int*)(sb + (size_t)S * 4); adj_start = (unsigned*)(sb + (size_t)S * 8);
         rlen = (unsigned short*)(sb + (size_t)S * 12); head = (unsigned short*)(sb + (size_t)S * 14); tail = (unsigned short*)(sb + (size_t)S * 16);
         next = (unsigned short*)(sb + (size_t)S * 18); mark = (unsigned short*)(sb + (size_t)S * 20);
         adj_len = (unsigned short*)(sb + (size_t)S * 22); adj_cap = (unsigned short*)(sb + (size_t)S * 24);
-        bytes = o + (size_t)E_cap * 12 + (size_t)S * 26;
+        bytes = big ? o : o + (size_t)E_cap * 12 + (size_t)S * 26;
     }
+    static __host__ __device__ size_t big_bytes(unsigned S, unsigned E_cap) { return (size_t)E_cap * 12 + (size_t)S * 26 + 256; }
 };
 enum { FM_NLIVE = 0, FM_EALIVE, FM_RALIVE, FM_COUNTER, FM_ND, FM_NANW, FM_ERROR, FM_MAXT, FM_SUMT, FM_MISS, FM_EVALS, FM_NMERGES, FM_POOL };
 
@@ -252,6 +266,7 @@ enum { FC_KEEP = 0, FC_FRONT = 1, FC_BACK = 2, FC_DUP = 3 };
 enum { BAR_W1 = 1, BAR_WB = 2, BAR_F = 3, BAR_W4 = 4, BAR_G = 5, BAR_FN = 6, BAR_GN = 7 };
 // A merge whose two adjacency lists hold <= 32 entries is NARROW: one worker warp handles it, the other 28 sleep until W4, and
 // the G / F barriers shrink to the warps involved (G: mean warp + worker warp 0; F: the three role warps + worker warp 0).
+__device__ __forceinline__ bool lean_too_wide(const FastSmem& sm, unsigned a, unsigned b) { return (unsigned)sm.adj_len[a] + (unsigned)sm.adj_len[b] > (unsigned)kLeanMaxTouched; }
 __device__ __forceinline__ bool lean_wide(const FastSmem& sm, unsigned a, unsigned b) { return (unsigned)sm.adj_len[a] + (unsigned)sm.adj_len[b] > 32u; }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -260,10 +275,10 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile(
 #define LTRACE(cond, slot, val) do { if (PROF && (cond) && A.trace && (nm - A.trace_first) < 256u) A.trace[(nm - A.trace_first) * 32u + (slot)] = (val); } while (0)
 #define LPROF_STORE(cond, base, n) do { if (PROF && (cond)) for (int i_ = 0; i_ < (n); ++i_) A.ctl->phase_cycles[(base) + i_] = pc[i_]; } while (0)
 
-template <bool PROF>
+template <bool PROF, bool BIG = false>
 __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
     extern __shared__ __align__(128) char smem_raw[];
-    const FastSmem sm(smem_raw, A.S_cap, A.E_cap);
+    const FastSmem sm(smem_raw, A.S_cap, A.E_cap, BIG ? A.big : nullptr);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned nE = *A.n_edges_ptr, S = *A.n_sv_ptr;
     const RegionArrays R = A.R;
@@ -274,7 +289,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
     const unsigned nblk = A.E_cap / 32u;                                       // blocks of 32 edges; warp w owns w, w + 29, ...
     const unsigned nbw = (nblk + kLeanWorkerWarps - 1u) / kLeanWorkerWarps;   // (the last row of blocks may be partial)
     static_assert((kLeanRing + 2) * kLeanSlotVox * 16 >= 4096 * 4, "set-up scratch: one word per region");
-    unsigned* const cursor = reinterpret_cast<unsigned*>(sm.stage);           // scratch: ring + private stages are idle until the first merge
+    unsigned* const cursor = BIG ? A.big_cursor : reinterpret_cast<unsigned*>(sm.stage);   // scratch: ring + private stages are idle until the first merge
     for (unsigned s = tid; s < S; s += kFastThreads) {
         const unsigned r0 = A.run_start[s];
         sm.rs[s] = r0; sm.rlen[s] = (unsigned short)(A.run_end[s] - r0); sm.n[s] = R.n[s];
@@ -283,6 +298,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
         sm.next[s] = (unsigned short)(nx < 0 ? kNil16 : (unsigned)nx); sm.mark[s] = (unsigned short)kNil16; sm.adj_start[s] = 0u;
     }
     if (tid < 32) sm.bdirty[tid] = 1u;
+    if constexpr (BIG) for (unsigned i = tid; i < (nblk + 31u) / 32u; i += kFastThreads) sm.blkdirty[i] = 0xffffffffu;
     for (int i = tid; i < kLeanMaxTouched; i += kFastThreads) sm.partner[i] = (unsigned short)kNil16;
     for (int i = tid; i < kLeanHash; i += kFastThreads) { sm.hkey[i] = kDeadKey; sm.hcnt[i] = 0u; }
     __syncthreads();
@@ -350,6 +366,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             LPROF(lane == 0, 3);
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
+            if (lean_too_wide(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
             const int na = sm.n[a], nb = sm.n[b];
             const bool wide = lean_wide(sm, a, b);
             LTRACE(lane == 0, 12, (unsigned)clock()); LTRACE(lane == 0, 21, (unsigned)nb);
@@ -426,6 +443,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             LPROF(lane == 0, 3);
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
+            if (lean_too_wide(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
             const int na = sm.n[a], nb = sm.n[b];
             const bool wide = lean_wide(sm, a, b);
             LTRACE(lane == 0, 16, (unsigned)clock());
@@ -509,6 +527,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             const FastHead hd = lean_head(sm, lane);
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
+            if (lean_too_wide(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
             const int na = sm.n[a], nb = sm.n[b];
             const bool wide = lean_wide(sm, a, b);
             if (nb > kLeanSlotVox) {                       // (the fold warps fetch a small region themselves, lean_fetch_small)
@@ -559,6 +578,40 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             if (sm.bdirty[ww]) {
                 __syncwarp();
                 if (lane == 0) sm.bdirty[ww] = 0u;
+                if constexpr (BIG) {
+                    // blocks of this warp with a re-weighted / removed edge: one coalesced reload each (four in flight), new block minimum
+                    for (unsigned j0 = 0; j0 < nbw; j0 += 4u) {
+                        unsigned long long k4[4]; unsigned b4[4]; bool d4[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            b4[u] = (unsigned)ww + kLeanWorkerWarps * (j0 + (unsigned)u);
+                            d4[u] = j0 + (unsigned)u < nbw && b4[u] < nblk && ((sm.blkdirty[b4[u] >> 5] >> (b4[u] & 31u)) & 1u);
+                            k4[u] = d4[u] ? __ldcg(sm.key + b4[u] * 32u + (unsigned)lane) : kDeadKey64;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (!d4[u]) continue;                                           // (warp-uniform)
+                            const unsigned hi = (unsigned)(k4[u] >> 32), lo = (unsigned)k4[u];
+                            const unsigned m_hi = __reduce_min_sync(kFull, hi);
+                            const unsigned m_lo = __reduce_min_sync(kFull, hi == m_hi ? lo : kDeadKey);
+                            if (lane == __ffs(__ballot_sync(kFull, hi == m_hi && lo == m_lo)) - 1) {
+                                const unsigned e = b4[u] * 32u + (unsigned)lane;
+                                sm.bm_key[b4[u]] = k4[u]; sm.bm_e[b4[u]] = e; sm.bm_ab[b4[u]] = __ldcg(sm.ab + e);
+                                atomicAnd(&sm.blkdirty[b4[u] >> 5], ~(1u << (b4[u] & 31u)));
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    unsigned long long best = kDeadKey64; unsigned bb = 0;
+                    for (unsigned j = (unsigned)lane; j < nbw; j += 32u) {
+                        const unsigned blk = (unsigned)ww + kLeanWorkerWarps * j;
+                        if (blk < nblk) { const unsigned long long k = sm.bm_key[blk]; if (k < best) { best = k; bb = blk; } }
+                    }
+                    const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
+                    const unsigned m_hi = __reduce_min_sync(kFull, hi);
+                    const unsigned m_lo = __reduce_min_sync(kFull, hi == m_hi ? lo : kDeadKey);
+                    if (lane == __ffs(__ballot_sync(kFull, hi == m_hi && lo == m_lo)) - 1) { sm.wm_key[ww] = best; sm.wm_e[ww] = sm.bm_e[bb]; sm.wm_ab[ww] = sm.bm_ab[bb]; }
+                } else {
                 unsigned long long best = kDeadKey64; unsigned be = 0;
 #pragma unroll 4
                 for (unsigned j = 0; j < nbw; ++j) {
@@ -571,6 +624,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                 const unsigned m_hi = __reduce_min_sync(kFull, hi);
                 const unsigned m_lo = __reduce_min_sync(kFull, hi == m_hi ? lo : kDeadKey);
                 if (lane == __ffs(__ballot_sync(kFull, hi == m_hi && lo == m_lo)) - 1) { sm.wm_key[ww] = best; sm.wm_e[ww] = be; sm.wm_ab[ww] = sm.ab[be]; }
+                }
             }
             WPROF(0);
             LTRACE(wtid == 0, 1, (unsigned)clock());
@@ -579,6 +633,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             if (my_hs != kNil16) { sm.hkey[my_hs] = kDeadKey; sm.hcnt[my_hs] = 0u; my_hs = kNil16; }
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;   // strict <, src/clustering.cpp:388-389
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
+            if (lean_too_wide(sm, a, b)) { if (wtid == 0) sm.misc[FM_ERROR] = (int)kFastErrTouched; break; }   // nothing of this merge has happened yet
             const int counter = sm.misc[FM_COUNTER];
             const unsigned pool_top = (unsigned)sm.misc[FM_POOL];
             WPROF(1);
@@ -593,6 +648,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                 sm.key[hd.e] = kDeadKey64; sm.ab[hd.e] = kDeadKey;                             // the head edge leaves the map
                 const unsigned hb = hd.e >> 5;
                 sm.bdirty[hb % kLeanWorkerWarps] = 1u;
+                if constexpr (BIG) atomicOr(&sm.blkdirty[hb >> 5], 1u << (hb & 31u));
                 if (n_merges < A.log_cap) {                                                    // debug line of :390-392 (ranks; labels at the end)
                     A.mlog.a[n_merges] = a; A.mlog.b[n_merges] = b; A.mlog.w[n_merges] = __uint_as_float(hd.hi);
                     A.mlog.edges_left[n_merges] = (unsigned)sm.misc[FM_EALIVE]; A.mlog.regions_left[n_merges] = (unsigned)sm.misc[FM_RALIVE];
@@ -731,6 +787,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                     sm.key[e] = live ? ((unsigned long long)wbits << 32) | lo : kDeadKey64;
                     sm.ab[e] = nab;
                     sm.bdirty[(e >> 5) % kLeanWorkerWarps] = 1u;
+                    if constexpr (BIG) atomicOr(&sm.blkdirty[e >> 10], 1u << ((e >> 5) & 31u));
                 }
             }
             if (wtid == 0) {
@@ -793,6 +850,9 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
 // one frame: one CTA
 template <bool PROF>
 __global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(const __grid_constant__ FastArgs A) { merge_lean_body<PROF>(A); }
+
+// graphs too large for an SM's shared memory (C5-size scenes): the same loop with the big tables in global memory
+__global__ void __launch_bounds__(kFastThreads, 1) merge_fast_big_kernel(const __grid_constant__ FastArgs A) { merge_lean_body<false, true>(A); }
 
 // A batch of frames in ONE launch, CTA i replays frame i (f3ps_merge_batch).  Independent streams share at most 32 hardware
 // queues (CUDA_DEVICE_MAX_CONNECTIONS), so at most 32 single-CTA merge kernels ever overlap; one grid has no such limit.

@@ -275,24 +275,20 @@ def test_threshold_prefix_property_and_restart(gpu, oracle_mod, small_frame):
 
 @pytest.mark.parametrize("mp", [AL, EQ, RGB_ML], ids=["cvx_al", "eq200", "rgb_ml"])
 def test_resident_and_general_merge_kernels_agree(gpu, vga_frame, small_frame, mp):
-    """K7 has two kernels (resident: one SM with the weight map in shared memory / general: everything in global
-    memory); both replay the same sequence.  f3ps_set_merge_kernel selects (4 = resident with phase counters)."""
+    """K7 has three kernels (resident: one SM with the weight map in shared memory / the same loop with its tables in L2, for
+    graphs too large for an SM / general: everything in global memory); all replay the same sequence.
+    f3ps_set_merge_kernel selects (4 = resident with phase counters)."""
     for pts, thr in ((small_frame, 0.2), (vga_frame, 0.2), (small_frame, 1.0)):
         g = gpu.Segmenter(); g.set_vccs_params(); g.set_merge_params(**mp); g.set_input(pts); g.run(thr)
         assert g.counts().merge_path == 1
         fast = {n: g.array(n).copy() for n in MERGE_ARRAYS}
-        g.set_merge_kernel(2); g.merge(thr)
-        assert g.counts().merge_path == 2
-        for n in MERGE_ARRAYS:
-            assert same(fast[n], g.array(n)), n
-        g.set_merge_kernel(4); g.merge(thr)                 # resident kernel compiled with its phase counters
-        assert g.counts().merge_path == 1 and (g.merge_profile()["sum_T"] > 0 or g.counts().n_merges < 2)
-        for n in MERGE_ARRAYS:
-            assert same(fast[n], g.array(n)), n
-        g.set_merge_kernel(0); g.merge(thr)
-        assert g.counts().merge_path == 1
-        for n in MERGE_ARRAYS:
-            assert same(fast[n], g.array(n)), n
+        for which, path in ((2, 2), (3, 3), (4, 1), (0, 1)):
+            g.set_merge_kernel(which); g.merge(thr)
+            assert g.counts().merge_path == path, (which, g.counts().merge_path)
+            for n in MERGE_ARRAYS:
+                assert same(fast[n], g.array(n)), (which, n)
+            if which == 4:
+                assert g.merge_profile()["sum_T"] > 0 or g.counts().n_merges < 2
 
 
 def test_frames_in_flight_pool(gpu, oracle_mod, small_frame):
@@ -469,7 +465,13 @@ def test_general_merge_kernel_hub_graph(gpu, oracle_mod, n_leaves, mode):
     g.set_graph(vxyz, vrgba, labels, lists, cen, nrm, adj)
     g.merge(thr)
     c = g.counts()
-    assert c.merge_path == 2 and c.max_touched > 1024 and c.n_merges > 100, (c.merge_path, c.max_touched, c.n_merges)
+    # (2: general kernel from the start; 4 / 5: the resident kernel up to the first merge that touches more edges than it has worker
+    # threads, then the general kernel continues from its state -- the hand-over is part of what this test pins against the oracle)
+    assert c.merge_path in (2, 4, 5) and c.max_touched > 1024 and c.n_merges > 100, (c.merge_path, c.max_touched, c.n_merges)
+    first = (c.merge_path, g.array("merges_ab").copy(), g.array("final_ab").copy())
+    g.set_merge_kernel(2); g.merge(thr)                  # the general kernel alone replays the same sequence
+    assert g.counts().merge_path == 2 and np.array_equal(g.array("merges_ab"), first[1]) and np.array_equal(g.array("final_ab"), first[2])
+    g.set_merge_kernel(0); g.merge(thr)
     if n_leaves >= 9000:
         assert c.max_touched > 8192                  # the global-memory sort as well
     assert np.array_equal(g.array("merges_ab"), o.array("merges_ab"))

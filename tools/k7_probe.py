@@ -22,7 +22,7 @@ def main():
     g = f3ps.Segmenter(); g.set_vccs_params(); g.set_merge_params(**mp); g.set_input(pts)
     g.extract(); g.graph(); g.sync()
     ok = True
-    for kern in (0, 4, 2):
+    for kern in (0, 3, 2):
         g.set_merge_kernel(kern)
         ms = []
         for r in range(reps):
