@@ -69,16 +69,19 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
         self.index = index
         self.proc = None
+        self.enabled = enabled          # one sampler per job (rank 0): eight nvidia-smi loops only perturb the launches they watch
         self.path = "/tmp/f3ps_clocks_%d.csv" % os.getpid()
 
     def start(self):
+        if not self.enabled:
+            return
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -234,7 +237,7 @@ def sweep_leg(args, env, workload, steps):
         pool.run(ptrs, on_device=True, npts=npts)
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, enabled=rank == 0)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -421,7 +424,7 @@ def run_slab(args):
     for _ in range(max(1, args.warmup)):
         ss.run((d_pts.data_ptr(), n_local, 32), THRESHOLD)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, enabled=rank == 0)
     if world > 1:
         dist.barrier()
     sampler.start()

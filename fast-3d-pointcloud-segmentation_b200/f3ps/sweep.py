@@ -97,7 +97,9 @@ class BatchPool:
         import threading
         self.binding = binding
         self.batch = batch
-        self.workers = workers or max(2, min(batch, (os.cpu_count() or 4)))
+        # front-stage host threads: they sleep on blocking events most of the time, and what they are for is keeping ~16 frames in
+        # flight (measured: 8, 16, 32 give the same throughput on 16 cores) -- not one per core: 8 ranks x 32 threads only contend
+        self.workers = workers or max(2, min(batch, 16))
         self.sets = [[binding.Segmenter(device=device) for _ in range(batch)] for _ in range(2)]
         for st in self.sets:
             for s in st:
