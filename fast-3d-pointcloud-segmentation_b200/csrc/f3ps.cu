@@ -447,8 +447,9 @@ struct ExpandTicket {
 
 static int expand_prepare(f3ps_ctx* ctx, ExpandArgs& A) {
     const unsigned V = ctx->V, S0 = ctx->S0; const size_t Vc = std::max(1u, V), Sc = (size_t)S0 + 2, Lc = Vc + Sc;
-    DevBuf* bv[] = {&ctx->own_a, &ctx->own_b, &ctx->dst_a, &ctx->dst_b, &ctx->st0, &ctx->st1, &ctx->phantom, &ctx->owner0, &ctx->dist0};
+    DevBuf* bv[] = {&ctx->own_a, &ctx->own_b, &ctx->dst_a, &ctx->dst_b, &ctx->st0, &ctx->st1, &ctx->owner0, &ctx->dist0};
     for (DevBuf* b : bv) F3PS_CUDA_OK(b->ensure(Vc * 4));
+    F3PS_CUDA_OK(ctx->phantom.ensure(Vc * 4 * kPhSlots));
     DevBuf* bl[] = {&ctx->lab_keys_a, &ctx->lab_vals_a, &ctx->lab_vals_b};
     for (DevBuf* b : bl) F3PS_CUDA_OK(b->ensure(Lc * 4));
     F3PS_CUDA_OK(ctx->chg_a.ensure(Vc)); F3PS_CUDA_OK(ctx->chg_b.ensure(Vc));
@@ -479,7 +480,7 @@ static int expand_prepare(f3ps_ctx* ctx, ExpandArgs& A) {
 static int expand_finish(f3ps_ctx* ctx) {
     int rc = pull_scalars(ctx); if (rc) return rc;
     const ExpandCtl& x = ctx->h_sc->xctl;
-    if (x.error & EXPAND_ERR_TRIPLE) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "three seed cells elected the same voxel (not modelled)");
+    if (x.error & EXPAND_ERR_TRIPLE) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "more than four seed cells elected the same voxel (not modelled)");
     if (x.error & EXPAND_ERR_CAND) return ctx_fail(ctx, F3PS_ERR_CAPACITY, "more than 32 candidate helpers around one voxel");
     if (x.error & EXPAND_ERR_SWEEPS) return ctx_fail(ctx, F3PS_ERR_NOT_CONVERGED, "expansion fixed point not reached within 32 sweeps");
     ctx->S = ctx->V ? x.n_sv : 0; ctx->n_pos = ctx->V ? x.n_pos : 0;

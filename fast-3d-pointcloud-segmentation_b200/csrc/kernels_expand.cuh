@@ -8,8 +8,8 @@
 // The sweep is the exact data-parallel restatement of PCL's sequential helper loop (oracle:
 // Oracle::expand_fixed_point): voxel n folds, in ascending label order, every helper that holds a leaf
 // adjacent to n at its turn.  "Phantom" leaves (two seed cells elected the same voxel; the earlier helper
-// keeps the leaf in its set without owning it) are modelled exactly; three helpers on one voxel are
-// reported as F3PS_ERR_CAPACITY.
+// keeps the leaf in its set without owning it) are modelled exactly for up to four seed cells on one voxel
+// (three holders + the owner); more are reported as F3PS_ERR_CAPACITY.
 //
 // Cross-CTA mutable state (owner / dist / steal table / centroids / lists) is read with ld.global.cg
 // (L2 is the coherence point) and published with a fence before every barrier arrival.
@@ -18,9 +18,11 @@
 
 namespace f3ps {
 
-constexpr unsigned kOwnMask = 0x3fffffffu;      // label bits of an owner word
-constexpr unsigned kOwnPhantom = 0x80000000u;   // voxel is held as a phantom leaf by phantom[v]
-constexpr unsigned kOwnWon = 0x40000000u;       // its holder stole it in the round being evaluated
+constexpr int kPhSlots = 3;                     // helpers that can hold one voxel as a phantom leaf (four seed cells electing one voxel)
+constexpr unsigned kOwnMask = 0x0fffffffu;      // label bits of an owner word
+constexpr unsigned kOwnPhantom = 0x80000000u;   // voxel is held as a phantom leaf by the helpers phantom[kPhSlots * v + s]
+constexpr unsigned kOwnWon = 0x70000000u;       // bit 28 + s: the holder in slot s stole it in the round being evaluated
+__device__ __forceinline__ unsigned own_won_bit(int s) { return 0x10000000u << s; }
 constexpr int kExpandThreads = 512;
 #ifndef F3PS_EXPAND_MIN_BLOCKS
 #define F3PS_EXPAND_MIN_BLOCKS 2          // 64 registers per thread: two CTAs per SM hide the latency of the neighbour probes
@@ -125,7 +127,8 @@ __device__ __forceinline__ void expand_sweep_voxel(const ExpandArgs& A, const un
             chg_out[n] = 0;
             const unsigned l1 = w1 & kOwnMask;
             if (l1) atomicAdd(&cnt[l1], 1u);
-            if ((w0 & kOwnPhantom) && !(w1 & kOwnWon)) atomicAdd(&cnt[A.phantom[n]], 1u);
+            if (w0 & kOwnPhantom)
+                for (int s = 0; s < kPhSlots; ++s) { const unsigned h = A.phantom[(size_t)kPhSlots * n + s]; if (h && !(w1 & own_won_bit(s))) atomicAdd(&cnt[h], 1u); }
             return;
         }
     }
@@ -138,7 +141,7 @@ __device__ __forceinline__ void expand_sweep_voxel(const ExpandArgs& A, const un
         const unsigned stv = h != 0u ? st_in[idx[r]] : 0u;
         hu[r] = stv > h ? h : 0u;                 // still h's leaf at h's turn
     }
-    unsigned first = kNoSteal, won = 0u, ph_n = 0u;
+    unsigned first = kNoSteal, won = 0u, ph_n[kPhSlots] = {0u, 0u, 0u};
     const float4 vx = A.vox_xyz[n], vc = A.vox_rgb[n], vn = A.vox_nrm[n];
     if (!any_ph) {
         unsigned last = 0u;
@@ -154,7 +157,7 @@ __device__ __forceinline__ void expand_sweep_voxel(const ExpandArgs& A, const un
         }
     } else {
         // a phantom leaf somewhere in the neighbourhood: it supports all its neighbours, itself included
-        ph_n = (w0 & kOwnPhantom) ? A.phantom[n] : 0u;
+        if (w0 & kOwnPhantom) for (int s = 0; s < kPhSlots; ++s) ph_n[s] = A.phantom[(size_t)kPhSlots * n + s];
         unsigned cand[kMaxCand]; int nc = 0; bool overflow = false;
         auto insert = [&](unsigned h) {           // sorted, distinct
             int p = nc;
@@ -170,21 +173,25 @@ __device__ __forceinline__ void expand_sweep_voxel(const ExpandArgs& A, const un
                 const unsigned h = wu & kOwnMask;
                 if (h != 0u && st_in[u] > h) insert(h);
             }
-            if (wu & kOwnPhantom) insert(A.phantom[u]);
+            if (wu & kOwnPhantom) for (int s = 0; s < kPhSlots; ++s) { const unsigned h = A.phantom[(size_t)kPhSlots * u + s]; if (h) insert(h); }
         }
         if (overflow) atomicOr(&A.ctl->error, (unsigned)EXPAND_ERR_CAND);
         for (int q = 0; q < nc; ++q) {
             const unsigned h = cand[q];
             if (h == cur_l) continue;
             const float d = voxel_data_distance(A.cen.xyz[h], A.cen.rgb[h], A.cen.nrm[h], vx, vc, vn, A.P);
-            if (d < D) { if (first == kNoSteal) first = h; D = d; cur_l = h; if (h == ph_n) won = kOwnWon; }
+            if (d < D) {
+                if (first == kNoSteal) first = h;
+                D = d; cur_l = h;
+                for (int s = 0; s < kPhSlots; ++s) if (h == ph_n[s]) won |= own_won_bit(s);
+            }
         }
     }
     own1[n] = cur_l | (w0 & kOwnPhantom) | won; dst1[n] = D; st_out[n] = first;
     if (chg_out) chg_out[n] = first != st_n ? 1 : 0;
     if (first != st_n) any_change = 1;
     if (cur_l) atomicAdd(&cnt[cur_l], 1u);
-    if (ph_n && !won) atomicAdd(&cnt[ph_n], 1u);   // the holder still lists its phantom leaf
+    for (int s = 0; s < kPhSlots; ++s) if (ph_n[s] && !(won & own_won_bit(s))) atomicAdd(&cnt[ph_n[s]], 1u);   // a holder that did not steal it still lists its phantom leaf
 }
 
 // one contiguous leaf list per helper: 32 helpers per warp, warp-aggregated bump allocation (helper order is irrelevant)
@@ -203,14 +210,22 @@ __device__ __forceinline__ void expand_alloc_warp(const ExpandArgs& A, const uns
 // commit the round for voxel n (a phantom leaf its holder stole becomes a regular leaf) and append it to its helpers' lists
 __device__ __forceinline__ void expand_fill_voxel(const ExpandArgs& A, unsigned* own, const unsigned n) {
     unsigned w = own[n];
-    if (w & kOwnWon) {                       // the holder owns it now (or lost it for good to a later thief)
-        const unsigned ph = A.phantom[n];
-        A.phantom_leaf[ph] = -1; A.phantom[n] = 0u;
-        w &= kOwnMask; own[n] = w;
+    if (w & kOwnPhantom) {
+        bool held = false;
+        for (int s = 0; s < kPhSlots; ++s) {
+            const unsigned ph = A.phantom[(size_t)kPhSlots * n + s];
+            if (!ph) continue;
+            if (w & own_won_bit(s)) { A.phantom_leaf[ph] = -1; A.phantom[(size_t)kPhSlots * n + s] = 0u; }   // the holder owns it now (or lost it for good to a later thief)
+            else held = true;
+        }
+        w &= ~kOwnWon;
+        if (!held) w &= ~kOwnPhantom;
+        own[n] = w;
     }
     const unsigned l = w & kOwnMask;
     if (l) A.list_raw[A.off[l] + atomicAdd(&A.fill[l], 1u)] = n;
-    if (w & kOwnPhantom) { const unsigned ph = A.phantom[n]; A.list_raw[A.off[ph] + atomicAdd(&A.fill[ph], 1u)] = n; }
+    if (w & kOwnPhantom)
+        for (int s = 0; s < kPhSlots; ++s) { const unsigned ph = A.phantom[(size_t)kPhSlots * n + s]; if (ph) A.list_raw[A.off[ph] + atomicAdd(&A.fill[ph], 1u)] = n; }
 }
 
 // one helper, one warp: leaves in idx order (ranks by counting), then SupervoxelHelper::updateCentroid -- the leaves' data are
@@ -317,7 +332,7 @@ __device__ __forceinline__ void expand_body(const ExpandArgs& A, ExpandSmem<THRE
     unsigned long long t_prev = globaltimer_ns();
 
     // ---- createSupervoxelHelpers -------------------------------------------------------------------
-    for (unsigned v = tid; v < V; v += nthreads) { A.owner[0][v] = 0u; A.dist[0][v] = FLT_MAX; A.st[0][v] = kNoSteal; A.phantom[v] = 0u; }
+    for (unsigned v = tid; v < V; v += nthreads) { A.owner[0][v] = 0u; A.dist[0][v] = FLT_MAX; A.st[0][v] = kNoSteal; for (int s = 0; s < kPhSlots; ++s) A.phantom[(size_t)kPhSlots * v + s] = 0u; }
     for (unsigned l = tid; l < S0 + 2; l += nthreads) {
         if (!A.keep_centroids) {
             A.cen.xyz[l] = make_float4(0, 0, 0, l >= 1 && l <= S0 ? 1.0f : 0.0f);   // SupervoxelHelper::centroid_ starts at zero (literal)
@@ -332,7 +347,9 @@ __device__ __forceinline__ void expand_body(const ExpandArgs& A, ExpandSmem<THRE
         if (A.seeds[i] < 0) continue;
         const unsigned u = (unsigned)A.seeds[i];
         if ((ldcg_u(A.owner[0] + u) & kOwnMask) == i + 1u) continue;
-        if (atomicCAS(&A.phantom[u], 0u, i + 1u) != 0u) atomicOr(&ctl->error, (unsigned)EXPAND_ERR_TRIPLE);   // not modelled
+        bool placed = false;
+        for (int s = 0; s < kPhSlots && !placed; ++s) placed = atomicCAS(&A.phantom[(size_t)kPhSlots * u + s], 0u, i + 1u) == 0u;
+        if (!placed) atomicOr(&ctl->error, (unsigned)EXPAND_ERR_TRIPLE);        // more than kPhSlots + 1 seed cells on one voxel: not modelled
         A.phantom_leaf[i + 1] = (int)u;
         atomicOr(&A.owner[0][u], kOwnPhantom);
     }
@@ -374,7 +391,7 @@ __device__ __forceinline__ void expand_body(const ExpandArgs& A, ExpandSmem<THRE
             for (unsigned n = tid; n < V; n += nthreads) {
                 const unsigned w = ldcg_u(own + n);
                 if (w & kOwnMask) atomicAdd(&cnt_final[w & kOwnMask], 1u);
-                if (w & kOwnPhantom) atomicAdd(&cnt_final[ldcg_u(A.phantom + n)], 1u);
+                if (w & kOwnPhantom) for (int s = 0; s < kPhSlots; ++s) { const unsigned h = ldcg_u(A.phantom + (size_t)kPhSlots * n + s); if (h) atomicAdd(&cnt_final[h], 1u); }
             }
             expand_barrier<CLUSTER>(ctl, nblocks, phase);
             XPHASE(2);

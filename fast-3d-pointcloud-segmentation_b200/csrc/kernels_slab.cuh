@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(PointLoader pl, const un
 __global__ void __launch_bounds__(256) slab_expand_init_kernel(ExpandArgs A) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     for (unsigned v = tid; v < A.V; v += nthreads) {
-        A.owner[0][v] = 0u; A.dist[0][v] = FLT_MAX; A.st[0][v] = kNoSteal; A.st[1][v] = kNoSteal; A.phantom[v] = 0u;
+        A.owner[0][v] = 0u; A.dist[0][v] = FLT_MAX; A.st[0][v] = kNoSteal; A.st[1][v] = kNoSteal; for (int s = 0; s < kPhSlots; ++s) A.phantom[(size_t)kPhSlots * v + s] = 0u;
         A.owner[1][v] = 0u; A.dist[1][v] = FLT_MAX;
     }
     for (unsigned l = tid; l < A.S0 + 2; l += nthreads) {
@@ -80,7 +80,9 @@ __global__ void __launch_bounds__(256) slab_expand_phantom_kernel(ExpandArgs A) 
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < A.S0; i += gridDim.x * blockDim.x) {
         const unsigned u = (unsigned)A.seeds[i];
         if ((A.owner[0][u] & kOwnMask) == i + 1u) continue;
-        if (atomicCAS(&A.phantom[u], 0u, i + 1u) != 0u) atomicOr(&A.ctl->error, (unsigned)EXPAND_ERR_TRIPLE);
+        bool placed = false;
+        for (int s = 0; s < kPhSlots && !placed; ++s) placed = atomicCAS(&A.phantom[(size_t)kPhSlots * u + s], 0u, i + 1u) == 0u;
+        if (!placed) atomicOr(&A.ctl->error, (unsigned)EXPAND_ERR_TRIPLE);
         A.phantom_leaf[i + 1] = (int)u;
         atomicOr(&A.owner[0][u], kOwnPhantom);
     }
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(256) slab_expand_count0_kernel(ExpandArgs A, i
     for (unsigned n = blockIdx.x * blockDim.x + threadIdx.x; n < A.V; n += gridDim.x * blockDim.x) {
         const unsigned w = own[n];
         if (w & kOwnMask) atomicAdd(&cnt[w & kOwnMask], 1u);
-        if (w & kOwnPhantom) atomicAdd(&cnt[A.phantom[n]], 1u);
+        if (w & kOwnPhantom) for (int s = 0; s < kPhSlots; ++s) { const unsigned h = A.phantom[(size_t)kPhSlots * n + s]; if (h) atomicAdd(&cnt[h], 1u); }
     }
 }
 

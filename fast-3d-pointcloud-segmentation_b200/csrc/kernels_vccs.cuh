@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(128) voxel_normals_kernel(const float4* __rest
 // /root/reference/src/supervoxel_clustering.cpp:369-371).  A voxel's normal is recomputed from the index list
 // [u + N(u) for u in N(v)], every entry only when its owner is v's owner (N includes the voxel itself; duplicates kept).
 // Reads centroids and owners only, so the voxels are independent; unowned voxels keep their normal.  A phantom leaf (held by
-// helper `phantom[v]` without being owned by it) is recomputed twice in PCL, by its owner and by its holder, each with its own
+// helpers `phantom[3 v + s]` without being owned by them) is recomputed by its owner and by every holder in PCL, each with its own
 // filter; the helpers run in label order, so the later of the two decides -- the holder when a third helper with a smaller
 // label has stolen the voxel from its first owner.
 __global__ void __launch_bounds__(128) refine_normals_kernel(const float4* __restrict__ vox_xyz, const int* __restrict__ nbr_row,
@@ -352,8 +352,7 @@ __global__ void __launch_bounds__(128) refine_normals_kernel(const float4* __res
     for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
         unsigned L = label[v];
         if (L == 0u) continue;
-        const unsigned ph = phantom[v];
-        if (ph > L) L = ph;
+        for (int s = 0; s < 3; ++s) { const unsigned ph = phantom[(size_t)3 * v + s]; if (ph > L) L = ph; }   // kPhSlots holders (kernels_expand.cuh)
         Accu9 A; A.clear();
         int total = 0;
         const float4 pv = vox_xyz[v];
