@@ -813,79 +813,95 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
         const bool big_ok = !single_ok && P > 0 && S < 65535u && E_big <= 65504u && ctx->merge_kernel_choice != 1 &&
                             FastSmem(nullptr, S_cap, E_big, (char*)16).bytes <= 227u * 1024u;
         bool fast = !ctx->force_general_merge && (single_ok || big_ok);
-        bool resume = false;
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            if (attempt == 1 && resume) {
-                // the resident kernel stopped in front of a merge that touches more edges than it has worker threads; its state
-                // (regions, edges, stamps, ropes, log, counters) is that after n_merges merges: the general kernel continues from it
-                F3PS_CUDA_OK(cudaMemsetAsync(SC(mctl.error), 0, 4, ctx->stream));
-            } else if (attempt == 1) {                             // adjacency pool / stamp range exhausted: start over
+        // general kernel (any graph); resume: continue from the state the resident kernel left; stop_after: hand back after that many merges
+        auto launch_general = [&](bool resume, unsigned stop_after) -> int {
+            const size_t per = ((size_t)Ec * 4 + 255) & ~(size_t)255, per8 = ((size_t)Ec * 8 + 255) & ~(size_t)255;
+            unsigned n2 = 2048; while (n2 < Ec) n2 <<= 1;
+            const size_t perS = ((size_t)Sc * 4 + 255) & ~(size_t)255, sortb = (size_t)n2 * sizeof(MergeSortRec);
+            F3PS_CUDA_OK(ctx->merge_scratch.ensure(6 * per + 2 * per8 + per + per8 + perS + sortb));
+            char* sp = (char*)ctx->merge_scratch.p;
+            MergeScratch scr;
+            scr.st[0] = (long long*)sp; sp += per8; scr.st[1] = (long long*)sp; sp += per8;
+            scr.sortbuf = (MergeSortRec*)sp; sp += sortb;
+            scr.e[0] = (int*)sp; sp += per; scr.e[1] = (int*)sp; sp += per; scr.w[0] = (float*)sp; sp += per; scr.w[1] = (float*)sp; sp += per;
+            scr.x[0] = (unsigned*)sp; sp += per; scr.x[1] = (unsigned*)sp; sp += per; scr.cls = (unsigned char*)sp; sp += per;
+            scr.mark = (unsigned*)sp; sp += perS;
+            const size_t dyn = (size_t)kMergeSortSmem * sizeof(MergeSortRec);
+            if (!ctx->general_attr_set) {
+                F3PS_CUDA_OK(cudaFuncSetAttribute(merge_kernel<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                F3PS_CUDA_OK(cudaFuncSetAttribute(merge_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                ctx->general_attr_set = true;
+            }
+            if (S < 65536u)
+                LAUNCH(ctx, merge_kernel<unsigned>, 1, kMergeThreads, dyn, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
+                       ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr, (unsigned*)sp, ctx->pos_data, resume ? 1 : 0, stop_after);
+            else
+                LAUNCH(ctx, merge_kernel<unsigned long long>, 1, kMergeThreads, dyn, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
+                       ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr, (unsigned long long*)sp, ctx->pos_data, resume ? 1 : 0, stop_after);
+            return F3PS_OK;
+        };
+        // resident kernel (shared-memory tables, or the BIG variant with its tables in L2)
+        auto launch_resident = [&](bool resume) -> int {
+            FastArgs A;
+            A.R = ctx->R1; A.E = ctx->E1; A.n_edges_ptr = SC(n_edges); A.n_sv_ptr = SC(xctl.n_sv); A.ep = ep; A.lambda_dev = SC(lambda);
+            A.threshold = threshold; A.run_start = ctx->run_start.as<unsigned>(); A.run_end = ctx->run_end.as<unsigned>();
+            A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
+            A.ctl = SC(mctl); A.S_cap = S_cap;
+            A.E_cap = single_ok ? E_cap : E_big;
+            A.big = nullptr; A.big_cursor = nullptr; A.resume = resume ? 1 : 0;
+            void (*kern)(FastArgs) = single_ok ? lean_kernel_for(ctx->merge_kernel_choice == 4) : merge_fast_big_kernel;
+            size_t launch_bytes = fast_bytes;
+            if (!single_ok) {
+                const size_t bb = (FastSmem::big_bytes(S_cap, E_big) + 255) & ~(size_t)255;
+                F3PS_CUDA_OK(ctx->lean_big.ensure(bb + (size_t)S_cap * 4));
+                A.big = (char*)ctx->lean_big.p; A.big_cursor = (unsigned*)((char*)ctx->lean_big.p + bb);
+                launch_bytes = FastSmem(nullptr, S_cap, E_big, A.big).bytes;
+            }
+            int r = lean_attr(ctx, (const void*)kern); if (r) return r;
+            r = lean_pool(ctx, E, A); if (r) return r;
+            A.trace = nullptr; A.trace_first = ctx->merge_trace_first;
+            if (ctx->merge_kernel_choice == 4 && single_ok && !resume) {
+                F3PS_CUDA_OK(ctx->merge_trace.ensure(256 * 32 * 4));
+                F3PS_CUDA_OK(cudaMemsetAsync(ctx->merge_trace.p, 0, 256 * 32 * 4, ctx->stream));
+                A.trace = ctx->merge_trace.as<unsigned>();
+            }
+            kern<<<1, kFastThreads, launch_bytes, ctx->stream>>>(A);
+            ctx->launches++;
+            F3PS_CUDA_OK(cudaPeekAtLastError());
+            return F3PS_OK;
+        };
+        rc = mark(ctx, 9); if (rc) return rc;
+        if (!fast) { rc = launch_general(false, 0); if (rc) return rc; ctx->merge_path = 2; }
+        else {
+            // The resident kernel stops IN FRONT of a merge whose two adjacency lists hold more entries than it has worker threads
+            // (nothing of that merge has happened; its state is that after n merges).  The general kernel then replays exactly that
+            // merge from the same state and hands back; after kHandOvers such hand-overs (a scene full of hubs) it keeps the rest.
+            constexpr int kHandOvers = 16;
+            ctx->merge_path = single_ok ? 1 : 3;
+            bool resume = false;
+            for (int hand = 0;; ++hand) {
+                rc = launch_resident(resume); if (rc) return rc;
+                rc = pull_scalars(ctx); if (rc) return rc;       // did the resident kernel finish?
+                const unsigned err = ctx->h_sc->mctl.error;
+                if (err == 0) break;
+                if (err == kFastErrTouched) {
+                    F3PS_CUDA_OK(cudaMemsetAsync(SC(mctl.error), 0, 4, ctx->stream));
+                    ctx->merge_path = single_ok ? 4 : 5;
+                    rc = launch_general(true, hand < kHandOvers ? 1u : 0u); if (rc) return rc;
+                    if (hand >= kHandOvers) break;
+                    resume = true;
+                    continue;
+                }
+                // adjacency pool / stamp range exhausted: start over on the general kernel
                 F3PS_CUDA_OK(cudaMemcpyAsync(ctx->reg_work.p, ctx->reg_init.p, region_bytes(Sc), cudaMemcpyDeviceToDevice, ctx->stream));
                 F3PS_CUDA_OK(cudaMemcpyAsync(ctx->edge_work.p, ctx->edge_init.p, eb, cudaMemcpyDeviceToDevice, ctx->stream));
                 F3PS_CUDA_OK(cudaMemsetAsync(SC(mctl), 0, sizeof(MergeCtl), ctx->stream));
+                rc = launch_general(false, 0); if (rc) return rc;
+                ctx->merge_path = 2;
+                break;
             }
-            rc = mark(ctx, 9); if (rc) return rc;
-            if (fast) {
-                FastArgs A;
-                A.R = ctx->R1; A.E = ctx->E1; A.n_edges_ptr = SC(n_edges); A.n_sv_ptr = SC(xctl.n_sv); A.ep = ep; A.lambda_dev = SC(lambda);
-                A.threshold = threshold; A.run_start = ctx->run_start.as<unsigned>(); A.run_end = ctx->run_end.as<unsigned>();
-                A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
-                A.ctl = SC(mctl); A.S_cap = S_cap;
-                A.E_cap = single_ok ? E_cap : E_big;
-                A.big = nullptr; A.big_cursor = nullptr;
-                void (*kern)(FastArgs) = single_ok ? lean_kernel_for(ctx->merge_kernel_choice == 4) : merge_fast_big_kernel;
-                size_t launch_bytes = fast_bytes;
-                if (!single_ok) {
-                    const size_t bb = (FastSmem::big_bytes(S_cap, E_big) + 255) & ~(size_t)255;
-                    F3PS_CUDA_OK(ctx->lean_big.ensure(bb + (size_t)S_cap * 4));
-                    A.big = (char*)ctx->lean_big.p; A.big_cursor = (unsigned*)((char*)ctx->lean_big.p + bb);
-                    launch_bytes = FastSmem(nullptr, S_cap, E_big, A.big).bytes;
-                }
-                rc = lean_attr(ctx, (const void*)kern); if (rc) return rc;
-                rc = lean_pool(ctx, E, A); if (rc) return rc;
-                A.trace = nullptr; A.trace_first = ctx->merge_trace_first;
-                if (ctx->merge_kernel_choice == 4) {
-                    F3PS_CUDA_OK(ctx->merge_trace.ensure(256 * 32 * 4));
-                    F3PS_CUDA_OK(cudaMemsetAsync(ctx->merge_trace.p, 0, 256 * 32 * 4, ctx->stream));
-                    A.trace = ctx->merge_trace.as<unsigned>();
-                }
-                kern<<<1, kFastThreads, launch_bytes, ctx->stream>>>(A);
-                ctx->launches++;
-                F3PS_CUDA_OK(cudaPeekAtLastError());
-                ctx->merge_path = single_ok ? 1 : 3;
-            } else {
-                const size_t per = ((size_t)Ec * 4 + 255) & ~(size_t)255, per8 = ((size_t)Ec * 8 + 255) & ~(size_t)255;
-                unsigned n2 = 2048; while (n2 < Ec) n2 <<= 1;
-                const size_t perS = ((size_t)Sc * 4 + 255) & ~(size_t)255, sortb = (size_t)n2 * sizeof(MergeSortRec);
-                F3PS_CUDA_OK(ctx->merge_scratch.ensure(6 * per + 2 * per8 + per + per8 + perS + sortb));
-                char* sp = (char*)ctx->merge_scratch.p;
-                MergeScratch scr;
-                scr.st[0] = (long long*)sp; sp += per8; scr.st[1] = (long long*)sp; sp += per8;
-                scr.sortbuf = (MergeSortRec*)sp; sp += sortb;
-                scr.e[0] = (int*)sp; sp += per; scr.e[1] = (int*)sp; sp += per; scr.w[0] = (float*)sp; sp += per; scr.w[1] = (float*)sp; sp += per;
-                scr.x[0] = (unsigned*)sp; sp += per; scr.x[1] = (unsigned*)sp; sp += per; scr.cls = (unsigned char*)sp; sp += per;
-                scr.mark = (unsigned*)sp; sp += perS;
-                const size_t dyn = (size_t)kMergeSortSmem * sizeof(MergeSortRec);
-                if (!ctx->general_attr_set) {
-                    F3PS_CUDA_OK(cudaFuncSetAttribute(merge_kernel<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                    F3PS_CUDA_OK(cudaFuncSetAttribute(merge_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                    ctx->general_attr_set = true;
-                }
-                if (S < 65536u)
-                    LAUNCH(ctx, merge_kernel<unsigned>, 1, kMergeThreads, dyn, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
-                           ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr, (unsigned*)sp, ctx->pos_data, resume ? 1 : 0);
-                else
-                    LAUNCH(ctx, merge_kernel<unsigned long long>, 1, kMergeThreads, dyn, ctx->R1, ctx->E1, SC(n_edges), SC(xctl.n_sv), ep, SC(lambda), threshold, ctx->run_start.as<unsigned>(),
-                           ctx->run_end.as<unsigned>(), ctx->order, ctx->gxyz, ctx->sv_label.as<unsigned>(), ctx->ML, (unsigned)Sc, SC(mctl), scr, (unsigned long long*)sp, ctx->pos_data, resume ? 1 : 0);
-                ctx->merge_path = resume ? (ctx->merge_path == 3 ? 5 : 4) : 2;
-            }
-            rc = mark(ctx, 10); if (rc) return rc;
-            if (!fast) break;
-            rc = pull_scalars(ctx); if (rc) return rc;           // did the resident kernel finish?
-            if (ctx->h_sc->mctl.error == 0) break;
-            resume = ctx->h_sc->mctl.error == kFastErrTouched;
-            fast = false;
         }
+        rc = mark(ctx, 10); if (rc) return rc;
         LAUNCH(ctx, dense_label_kernel, 1, 1024, 0, ctx->R1, SC(xctl.n_sv), ctx->run_start.as<unsigned>(), ctx->run_end.as<unsigned>(), ctx->run_out_off.as<unsigned>(),
                ctx->run_dense.as<unsigned>(), ctx->region_dense.as<unsigned>(), SC(n_out));
         if (P) LAUNCH(ctx, labeled_cloud_kernel, grid_for(P, 256), 256, 0, ctx->pos_run.as<unsigned>(), P, ctx->order, ctx->run_start.as<unsigned>(),
@@ -963,7 +979,7 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
             A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
             A.ctl = SC(mctl); A.S_cap = (S + 7u) & ~7u; A.E_cap = (unsigned)slots_of[batch[k]];
             rc = lean_pool(ctx, ctx->E, A); if (rc) return rc;
-            A.trace = nullptr; A.trace_first = 0; A.big = nullptr; A.big_cursor = nullptr;
+            A.trace = nullptr; A.trace_first = 0; A.big = nullptr; A.big_cursor = nullptr; A.resume = 0;
             bytes = std::max(bytes, FastSmem(nullptr, A.S_cap, A.E_cap).bytes);
             rc = mark(ctx, 9); if (rc) return rc;
             if (ctx->stream != lead->stream) {               // the lead's stream runs the grid: it waits for everybody's set-up

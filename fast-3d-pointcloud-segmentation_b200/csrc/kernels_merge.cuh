@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R,
         const unsigned* __restrict__ n_sv_ptr, EdgeParams ep, const float* __restrict__ lambda_dev, float threshold,
         const unsigned* __restrict__ run_start, const unsigned* __restrict__ run_end, const unsigned* __restrict__ order,
         const float4* __restrict__ vox_xyz, const unsigned* __restrict__ sv_label, MergeLog mlog, unsigned log_cap, MergeCtl* ctl, MergeScratch scr,
-        PK* __restrict__ pk, const float4* __restrict__ pos_data, int resume) {   // resume: continue a replay the resident kernel handed over (ctl holds its counters)
+        PK* __restrict__ pk, const float4* __restrict__ pos_data, int resume, unsigned stop_after) {   // resume: continue a replay the resident kernel handed over (ctl holds its counters); stop_after > 0: hand back after that many merges
     typedef PkOps<PK> P;
     extern __shared__ __align__(16) unsigned char dyn_smem[];     // kMergeSortSmem sort records
     __shared__ float s_rw[32]; __shared__ long long s_rs[32]; __shared__ int s_ri[32];
@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R,
             s_counter = ctl->counter > (long long)nE ? ctl->counter : (long long)nE; s_fold = ctl->fold_steps; s_maxT = ctl->max_touched;
         }
     }
+    const unsigned nm0 = resume ? ctl->n_merges : 0u;
     const float INF = __int_as_float(0x7f800000);
     enum { C_KEEP = 0, C_FRONT = 1, C_BACK = 2, C_DUP = 3 };
     // strip of this thread and its cached minimum
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R,
         const int head = s_head;
         PHASE(0);
         if (head < 0 || !(s_head_w < threshold)) break;          // strict <, src/clustering.cpp:388-389
+        if (stop_after && s_nm - nm0 >= stop_after) break;        // (s_nm is stable here: written before the barriers above)
         const unsigned a = E.a[head], b = E.b[head];
         __syncthreads();
         if (tid == 0) {
@@ -405,6 +407,7 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_kernel(RegionArrays R,
                 float dc, dg;
                 delta_cached(ep, rgb1, rgb2, n1, c1, n2, c2, dc, dg);
                 float w_new = unify(ep, dc, dg);
+                E.dc[s_e[1][i]] = dc;                              // the resident kernel memoises delta_c per edge: keep its copy current
                 if (isnan(w_new)) { atomicAdd(&ctl->nan_weights, 1u); w_new = INF; }
                 const float w_old = s_w[1][i];
                 s_class[i] = (w_new == w_old) ? C_KEEP : (w_new > w_old ? C_FRONT : C_BACK);

@@ -53,6 +53,7 @@ struct FastArgs {
     MergeCtl* ctl;
     unsigned short* adj_pool; unsigned pool_cap;   // adjacency lists (edge ids), bump-allocated; entries
     unsigned* trace; unsigned trace_first;         // PROF only: clock() of 32 points of 256 merges starting at trace_first (f3ps_get_merge_trace)
+    int resume;                              // continue a replay from the state in the edge / region arrays (counters in *ctl): set after the general kernel took one merge this kernel could not
     char* big; unsigned* big_cursor;         // BIG variant only: the per-edge / per-region tables (12 E_cap + 26 S_cap bytes) and the set-up scratch (4 S_cap) in global memory
     unsigned S_cap, E_cap;                   // table capacities the shared-memory layout was sized for (E_cap = E rounded up to whole blocks of 32 edges)
 };
@@ -281,6 +282,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
     const FastSmem sm(smem_raw, A.S_cap, A.E_cap, BIG ? A.big : nullptr);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned nE = *A.n_edges_ptr, S = *A.n_sv_ptr;
+    const unsigned nm_first = A.resume ? A.ctl->n_merges : 0u;
     const RegionArrays R = A.R;
     const unsigned mbar_full = smem_addr(sm.mbar), mbar_empty = mbar_full + 8u * kLeanRing;
     int* const newgeo_i = reinterpret_cast<int*>(sm.newgeo);
@@ -316,6 +318,12 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
     if (tid == 0) {
         for (int i = 0; i < 16; ++i) sm.misc[i] = 0;
         sm.misc[FM_EALIVE] = (int)nE; sm.misc[FM_RALIVE] = (int)S; sm.misc[FM_COUNTER] = (int)nE;
+        if (A.resume) {
+            const MergeCtl* c = A.ctl;
+            sm.misc[FM_EALIVE] = (int)c->edges_alive; sm.misc[FM_RALIVE] = (int)c->regions_alive;
+            sm.misc[FM_COUNTER] = (int)(c->counter > (long long)nE ? c->counter : (long long)nE);
+            sm.misc[FM_NANW] = (int)c->nan_weights; sm.misc[FM_MAXT] = (int)c->max_touched; sm.misc[FM_NMERGES] = (int)c->n_merges;
+        }
         for (int i = 0; i < kLeanRing; ++i) { mbar_init(mbar_full + 8u * i, 32u); mbar_init(mbar_empty + 8u * i, 2u); }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -434,7 +442,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
         const EdgeParams ep = A.ep;
         float* const inv_s = sm.inv;
         unsigned chunk = 0;
-        unsigned long long fold_steps = 0;
+        unsigned long long fold_steps = A.resume ? A.ctl->fold_steps : 0ull;
         LPROF_DECL;
         unsigned nm = 0;                                   // merges so far (trace index)
         while (true) {
@@ -565,7 +573,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
         const int ww = warp - kLeanRoleWarps;                                                  // 0..28
         const unsigned short* __restrict__ pool = A.adj_pool;
         unsigned my_hs = kNil16;                                                               // tie-hash slot to clear after the next S1
-        unsigned n_merges = 0;
+        unsigned n_merges = A.resume ? A.ctl->n_merges : 0u;          // (the log continues behind the merges already replayed)
         LPROF_DECL;
         unsigned nm = 0;                                   // merges so far (trace index)
         unsigned long long cls_cyc[3] = {0, 0, 0}; unsigned cls_cnt[3] = {0, 0, 0}; unsigned t_top = 0;   // PROF: merges by touched-edge class
@@ -836,7 +844,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
         R.head[s] = sm.head[s] == kNil16 ? -1 : (int)sm.head[s]; R.tail[s] = sm.tail[s] == kNil16 ? -1 : (int)sm.tail[s];
         R.next_run[s] = sm.next[s] == kNil16 ? -1 : (int)sm.next[s];
     }
-    for (unsigned m = tid; m < n_merges && m < A.log_cap; m += kFastThreads) { A.mlog.a[m] = A.sv_label[A.mlog.a[m]]; A.mlog.b[m] = A.sv_label[A.mlog.b[m]]; }
+    for (unsigned m = nm_first + tid; m < n_merges && m < A.log_cap; m += kFastThreads) { A.mlog.a[m] = A.sv_label[A.mlog.a[m]]; A.mlog.b[m] = A.sv_label[A.mlog.b[m]]; }   // ranks -> labels, this launch's entries
     if (tid == 0) {
         MergeCtl* ctl = A.ctl;
         ctl->phase_cycles[24] = (unsigned long long)sm.misc[FM_MISS]; ctl->phase_cycles[25] = (unsigned long long)sm.misc[FM_EVALS];
