@@ -145,8 +145,16 @@ public:
     /* refineSupervoxels(num_itr, clusters), src/supervoxel_clustering.cpp:369-371: the labelled clouds / adjacency returned
      * afterwards are the refined ones, as in PCL */
     void refineSupervoxels(int num_itr, std::map<uint32_t, typename pcl::Supervoxel<PointT>::Ptr>& supervoxel_clusters);
-    /* getSupervoxelAdjacencyList, :376-384: labels as vertices, centroid distance as edge weight (a plain struct, not a BGL graph) */
+    /* getSupervoxelAdjacencyList, :376-384: labels as vertices, centroid distance as edge weight.  The library fills the plain
+     * struct above; any other graph type (the reference passes a boost::adjacency_list<setS, setS, undirectedS, uint32_t, float>)
+     * goes through the caller's f3ps_copy_adjacency_list(const f3ps::VoxelAdjacencyList&, GraphT&) -- INTEGRATION.md shows the BGL one. */
     void getSupervoxelAdjacencyList(VoxelAdjacencyList& adjacency_list_arg) const;
+    template <typename GraphT>
+    void getSupervoxelAdjacencyList(GraphT& adjacency_list_arg) const {
+        VoxelAdjacencyList plain;
+        getSupervoxelAdjacencyList(plain);
+        f3ps_copy_adjacency_list(plain, adjacency_list_arg);
+    }
     static pcl::PointCloud<pcl::PointNormal>::Ptr makeSupervoxelNormalCloud(
         std::map<uint32_t, typename pcl::Supervoxel<PointT>::Ptr>& supervoxel_clusters);
     float getVoxelResolution() const { return resolution_; }
