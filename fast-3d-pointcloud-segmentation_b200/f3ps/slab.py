@@ -204,7 +204,9 @@ class SlabSegmenter:
 
     TOP_BITS = 12
 
-    def __init__(self, comm, device=0, vccs=None, merge=None):
+    SHARD_EXPAND_MIN_V = 4_000_000      # voxels: below this the per-sweep exchange costs more than sharding the sweeps saves
+
+    def __init__(self, comm, device=0, vccs=None, merge=None, shard_expand=None):
         import torch
         self.torch = torch
         self.comm = comm
@@ -216,6 +218,10 @@ class SlabSegmenter:
         self.seg.set_merge_params(**(merge or {}))
         self.info = {}
         self._views = {}
+        # K5: None = by size (sweeps sharded over the slabs with a steal-table exchange per sweep when V >= SHARD_EXPAND_MIN_V, else
+        # every rank runs the persistent expansion kernel on the replicated voxel table: measured on the 50 M-point scan, V = 0.6 M:
+        # 8.8 ms replicated against 13.9 / 18.0 / 37.6 ms sharded over 2 / 4 / 8 GPUs); True / False force it (tests run both)
+        self.shard_expand = shard_expand
 
     def close(self):
         self.seg.close()
@@ -304,11 +310,18 @@ class SlabSegmenter:
             tick("normals")
             seg.seeds()
             tick("seeds")
-            # ---- K5: sweeps over the owned slice, steal table exchanged after every sweep ----
-            seg.slab_expand_begin()
-            rounds = int(seg.counts().rounds)
-            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            # ---- K5: sweeps over the owned slice, steal table exchanged after every sweep -- or, for a voxel table too small for
+            #      that to pay, the single-GPU persistent kernel on the replicated table (identical results, no exchange) ----
+            shard = self.shard_expand if self.shard_expand is not None else (comm.world > 1 and V >= self.SHARD_EXPAND_MIN_V)
             sweeps = 0
+            rounds = 0
+            if not shard:
+                seg.expand()
+                sweeps = int(seg.counts().sweeps)
+            else:
+                seg.slab_expand_begin()
+                rounds = int(seg.counts().rounds)
+            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
             for _ in range(rounds):
                 for s in range(33):
                     if s == 32:
@@ -323,11 +336,12 @@ class SlabSegmenter:
                     comm.gather_slices(self._view("owner_next", torch.int32), vb)
                 comm.all_reduce(self._view("count", torch.int32), "sum")
                 seg.slab_expand_round_end()
-            if rounds == 0:
-                seg.slab_expand_round_end()
-            elif V:
-                comm.gather_slices(self._view("dist", torch.float32), vb)
-            seg.slab_expand_end()
+            if shard:
+                if rounds == 0:
+                    seg.slab_expand_round_end()
+                elif V:
+                    comm.gather_slices(self._view("dist", torch.float32), vb)
+                seg.slab_expand_end()
             tick("expand")
             # ---- K6, K7 on the replicated tables ----
             seg.graph()
