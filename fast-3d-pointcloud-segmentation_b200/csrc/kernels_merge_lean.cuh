@@ -20,8 +20,12 @@
 // Barriers per merge: S1 (all: partial minima published), W1 (workers: touched list complete), WB1 / WB2 (workers, or one
 // warp when <= 32 edges are touched), F (all: new geometry published), W4 (workers: new keys written).
 //
-// Limits (the host falls back to merge_kernel of kernels_merge.cuh beyond them): S < 65535, tables within 227 KB,
-// E <= 928 * 32, at most 928 adjacency entries of a and b together, the adjacency pool not exhausted.
+// Two instantiations: tables in shared memory (S <= 4096, E <= 928 * 32, 12 E + 26 S + 40 KB within 227 KB: a VGA frame), or --
+// BIG -- the per-edge / per-region tables in global memory with per-block minima in shared memory (S < 65535, E <= 65504:
+// C5-size scenes).  A merge whose two adjacency lists hold more than 928 entries is not started: every role stops in front
+// of it, the state written back is that after n merges, and the host lets merge_kernel (kernels_merge.cuh) replay that one
+// merge from the same state and relaunches this kernel with A.resume (f3ps.cu: f3ps_merge).  An exhausted adjacency pool or
+// stamp range restarts the replay on merge_kernel.
 #pragma once
 #include "kernels_merge.cuh"
 
