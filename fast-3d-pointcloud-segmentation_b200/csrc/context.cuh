@@ -113,6 +113,7 @@ struct f3ps_ctx {
     const float4* pos_data = nullptr;   // voxel (x,y,z,rgba) in position order (what the merge folds stream)
     int merge_path = 0;                 // 1 = resident kernel, 2 = general kernel (last f3ps_merge)
     bool force_general_merge = false;   // f3ps_set_merge_kernel(ctx, 2)
+    bool merge_take_over = false;       // f3ps_merge_batch -> f3ps_merge: continue the replay the batch grid stopped (state after n merges), do not restart
     int merge_kernel_choice = 0;        // 0 auto, 1 resident single CTA, 2 general, 4 resident with phase counters
     f3ps::MergeLog ML{};
     unsigned n_pos = 0;           // positions of the label-ordered voxel list

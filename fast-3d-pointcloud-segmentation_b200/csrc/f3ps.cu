@@ -787,11 +787,16 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
     if (ctx->progress < P_GRAPH) { rc = f3ps_graph(ctx); if (rc) return rc; }   // if (!init_initial_weights) init_weights()  (:675-676)
     rc = mark(ctx, 7); if (rc) return rc;
     const unsigned S = ctx->S, E = ctx->E, P = ctx->n_pos; const size_t Sc = std::max(1u, S), Ec = std::max(1u, E), Pc = std::max(1u, P);
-    // cluster(float) always restarts from initial_state (:678)
-    F3PS_CUDA_OK(cudaMemcpyAsync(ctx->reg_work.p, ctx->reg_init.p, region_bytes(Sc), cudaMemcpyDeviceToDevice, ctx->stream));
+    // cluster(float) always restarts from initial_state (:678) -- unless f3ps_merge_batch hands over a replay its grid stopped in front
+    // of a merge with too many adjacency entries (the working state and the counters are then those after n merges)
+    const bool take_over = ctx->merge_take_over;
+    ctx->merge_take_over = false;
     const size_t eb = std::min(ctx->edge_init.cap, ctx->edge_work.cap);
-    F3PS_CUDA_OK(cudaMemcpyAsync(ctx->edge_work.p, ctx->edge_init.p, eb, cudaMemcpyDeviceToDevice, ctx->stream));
-    F3PS_CUDA_OK(cudaMemsetAsync(SC(mctl), 0, sizeof(MergeCtl), ctx->stream));
+    if (!take_over) {
+        F3PS_CUDA_OK(cudaMemcpyAsync(ctx->reg_work.p, ctx->reg_init.p, region_bytes(Sc), cudaMemcpyDeviceToDevice, ctx->stream));
+        F3PS_CUDA_OK(cudaMemcpyAsync(ctx->edge_work.p, ctx->edge_init.p, eb, cudaMemcpyDeviceToDevice, ctx->stream));
+        F3PS_CUDA_OK(cudaMemsetAsync(SC(mctl), 0, sizeof(MergeCtl), ctx->stream));
+    }
     F3PS_CUDA_OK(ctx->mlog.ensure(Sc * 20));
     char* lp = (char*)ctx->mlog.p;
     ctx->ML.a = (unsigned*)lp; ctx->ML.b = (unsigned*)(lp + Sc * 4); ctx->ML.w = (float*)(lp + Sc * 8);
@@ -880,9 +885,12 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
             ctx->merge_path = single_ok ? 1 : 3;
             bool resume = false;
             for (int hand = 0;; ++hand) {
-                rc = launch_resident(resume); if (rc) return rc;
-                rc = pull_scalars(ctx); if (rc) return rc;       // did the resident kernel finish?
-                const unsigned err = ctx->h_sc->mctl.error;
+                unsigned err = kFastErrTouched;                  // (take-over: the batch grid already stopped in front of a wide merge)
+                if (!(take_over && hand == 0)) {
+                    rc = launch_resident(resume); if (rc) return rc;
+                    rc = pull_scalars(ctx); if (rc) return rc;   // did the resident kernel finish?
+                    err = ctx->h_sc->mctl.error;
+                }
                 if (err == 0) break;
                 if (err == kFastErrTouched) {
                     F3PS_CUDA_OK(cudaMemsetAsync(SC(mctl.error), 0, 4, ctx->stream));
@@ -1018,7 +1026,12 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold) {
         for (size_t k = 0; k < batch.size(); ++k) {
             f3ps_ctx* ctx = ctxs[batch[k]];
             rc = pull_scalars(ctx); if (rc) return rc;
-            if (ctx->h_sc->mctl.error) {                     // a merge overflowed the resident kernel's touched list: this frame alone, general kernel
+            if (ctx->h_sc->mctl.error == kFastErrTouched) {  // the frame's CTA stopped in front of a merge with more adjacency entries than worker
+                ctx->merge_take_over = true;                 // threads: this frame alone continues from that state (general kernel for that merge, then resident again)
+                rc = f3ps_merge(ctx, threshold); if (rc) return rc;
+                continue;
+            }
+            if (ctx->h_sc->mctl.error) {                     // adjacency pool / stamp range exhausted: this frame alone, general kernel, from the start
                 const bool was = ctx->force_general_merge;
                 ctx->force_general_merge = true;
                 rc = f3ps_merge(ctx, threshold);
