@@ -562,10 +562,14 @@ __global__ void __launch_bounds__(256) seed_select_kernel(const float4* __restri
 #pragma unroll
         for (int a = 0; a < 3; ++a) ctr[a] = (float)(((double)k[a] + 0.5f) * res + sb->mn_final[a]);   // genLeafNodeCenterFromOctreeKey
         float bd = FLT_MAX; unsigned best = 0xffffffffu;
+        // the 27 cell look-ups (a binary search each) run side by side, one per lane, instead of one after the other in every lane
+        int my_cc = -1;
+        if (lane < 27) {
+            const long long x = (long long)k[0] + (lane / 9 - 1), y = (long long)k[1] + ((lane / 3) % 3 - 1), z = (long long)k[2] + (lane % 3 - 1);
+            if (!(x < 0 || y < 0 || z < 0 || x >= kmax || y >= kmax || z >= kmax)) my_cc = find_cell(cell_codes, C, morton_xmajor((uint32_t)x, (uint32_t)y, (uint32_t)z));
+        }
         for (int q = 0; q < 27; ++q) {
-            long long x = (long long)k[0] + (q / 9 - 1), y = (long long)k[1] + ((q / 3) % 3 - 1), z = (long long)k[2] + (q % 3 - 1);
-            if (x < 0 || y < 0 || z < 0 || x >= kmax || y >= kmax || z >= kmax) continue;
-            int cc = find_cell(cell_codes, C, morton_xmajor((uint32_t)x, (uint32_t)y, (uint32_t)z));
+            const int cc = __shfl_sync(kFull, my_cc, q);
             if (cc < 0) continue;
             unsigned s = cell_start[cc], e = (cc + 1 < C) ? cell_start[cc + 1] : V;
             for (unsigned j = s + lane; j < e; j += 32) {
@@ -585,10 +589,13 @@ __global__ void __launch_bounds__(256) seed_select_kernel(const float4* __restri
         uint32_t kb[3];
         morton_decode(vox_cell[best], kb[0], kb[1], kb[2]);
         int num = 0;
+        my_cc = -1;
+        if (lane < 27) {
+            const long long x = (long long)kb[0] + (lane / 9 - 1), y = (long long)kb[1] + ((lane / 3) % 3 - 1), z = (long long)kb[2] + (lane % 3 - 1);
+            if (!(x < 0 || y < 0 || z < 0 || x >= kmax || y >= kmax || z >= kmax)) my_cc = find_cell(cell_codes, C, morton_xmajor((uint32_t)x, (uint32_t)y, (uint32_t)z));
+        }
         for (int q = 0; q < 27; ++q) {
-            long long x = (long long)kb[0] + (q / 9 - 1), y = (long long)kb[1] + ((q / 3) % 3 - 1), z = (long long)kb[2] + (q % 3 - 1);
-            if (x < 0 || y < 0 || z < 0 || x >= kmax || y >= kmax || z >= kmax) continue;
-            int cc = find_cell(cell_codes, C, morton_xmajor((uint32_t)x, (uint32_t)y, (uint32_t)z));
+            const int cc = __shfl_sync(kFull, my_cc, q);
             if (cc < 0) continue;
             unsigned s = cell_start[cc], e = (cc + 1 < C) ? cell_start[cc + 1] : V;
             for (unsigned j = s + lane; j < e; j += 32) {
