@@ -114,7 +114,7 @@ struct f3ps_ctx {
     int merge_path = 0;                 // 1 = resident kernel, 2 = general kernel (last f3ps_merge)
     bool force_general_merge = false;   // f3ps_set_merge_kernel(ctx, 2)
     bool merge_take_over = false;       // f3ps_merge_batch -> f3ps_merge: continue the replay the batch grid stopped (state after n merges), do not restart
-    int merge_kernel_choice = 0;        // 0 auto, 1 resident single CTA, 2 general, 4 resident with phase counters
+    int merge_kernel_choice = 0;        // 0 auto, 1 resident single CTA, 2 general, 3 resident with its tables in L2, 4 / 5 = 1 / 3 with phase counters
     f3ps::MergeLog ML{};
     unsigned n_pos = 0;           // positions of the label-ordered voxel list
     const unsigned* order = nullptr;

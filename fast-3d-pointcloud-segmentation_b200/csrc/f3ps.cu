@@ -760,9 +760,9 @@ unsigned lean_ecap_for(unsigned E) {
 void (*lean_kernel_for(bool prof))(FastArgs) { return prof ? merge_fast_kernel<true> : merge_fast_kernel<false>; }
 // adjacency pool of the resident kernel (edge ids, 2 bytes each): the initial lists plus room for the lists that outgrow their block
 constexpr size_t kLeanPoolSlack = 1u << 20;
-int lean_pool(f3ps_ctx* ctx, unsigned E, FastArgs& A) {
-    const size_t entries = 2 * (size_t)E + kLeanPoolSlack;
-    F3PS_CUDA_OK(ctx->adj_pool.ensure(entries * 2));
+int lean_pool(f3ps_ctx* ctx, unsigned E, FastArgs& A, bool big = false) {      // (edge ids: 2 bytes, BIG variant 4)
+    const size_t entries = 2 * (size_t)E + (big ? 8 : 1) * kLeanPoolSlack;
+    F3PS_CUDA_OK(ctx->adj_pool.ensure(entries * (big ? 4 : 2)));
     A.adj_pool = ctx->adj_pool.as<unsigned short>(); A.pool_cap = (unsigned)entries;
     return F3PS_OK;
 }
@@ -812,10 +812,11 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
         const unsigned S_cap = (S + 7u) & ~7u;
         const unsigned E_cap = std::max(32u, lean_ecap_for(E));
         const size_t fast_bytes = FastSmem(nullptr, S_cap, E_cap).bytes;
-        const bool single_ok = lean_ecap_for(E) && S <= 4096u && fast_bytes <= 227u * 1024u && P > 0 && ctx->merge_kernel_choice != 3;
-        // graphs that do not fit an SM: the same kernel with its big tables in global memory (16-bit region / edge ids)
+        const bool single_ok = lean_ecap_for(E) && S <= 4096u && fast_bytes <= 227u * 1024u && P > 0 && ctx->merge_kernel_choice != 3 && ctx->merge_kernel_choice != 5;
+        // graphs that do not fit an SM: the same kernel with its big tables in global memory (16-bit region ids, 32-bit edge ids;
+        // 16 bytes of shared memory per block of 32 edges bound E near 380,000)
         const unsigned E_big = (E + 31u) & ~31u;
-        const bool big_ok = !single_ok && P > 0 && S < 65535u && E_big <= 65504u && ctx->merge_kernel_choice != 1 &&
+        const bool big_ok = !single_ok && P > 0 && S < 65535u && E_big <= (1u << 20) && ctx->merge_kernel_choice != 1 &&
                             FastSmem(nullptr, S_cap, E_big, (char*)16).bytes <= 227u * 1024u;
         bool fast = !ctx->force_general_merge && (single_ok || big_ok);
         // general kernel (any graph); resume: continue from the state the resident kernel left; stop_after: hand back after that many merges
@@ -854,16 +855,16 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
             A.ctl = SC(mctl); A.S_cap = S_cap;
             A.E_cap = single_ok ? E_cap : E_big;
             A.big = nullptr; A.big_cursor = nullptr; A.resume = resume ? 1 : 0;
-            void (*kern)(FastArgs) = single_ok ? lean_kernel_for(ctx->merge_kernel_choice == 4) : merge_fast_big_kernel;
+            void (*kern)(FastArgs) = single_ok ? lean_kernel_for(ctx->merge_kernel_choice == 4) : (ctx->merge_kernel_choice == 5 ? merge_fast_big_kernel<true> : merge_fast_big_kernel<false>);
             size_t launch_bytes = fast_bytes;
             if (!single_ok) {
                 const size_t bb = (FastSmem::big_bytes(S_cap, E_big) + 255) & ~(size_t)255;
-                F3PS_CUDA_OK(ctx->lean_big.ensure(bb + (size_t)S_cap * 4));
+                F3PS_CUDA_OK(ctx->lean_big.ensure(bb + lean_cursor_bytes(S_cap) + LeanWideScratch::bytes));
                 A.big = (char*)ctx->lean_big.p; A.big_cursor = (unsigned*)((char*)ctx->lean_big.p + bb);
                 launch_bytes = FastSmem(nullptr, S_cap, E_big, A.big).bytes;
             }
             int r = lean_attr(ctx, (const void*)kern); if (r) return r;
-            r = lean_pool(ctx, E, A); if (r) return r;
+            r = lean_pool(ctx, E, A, !single_ok); if (r) return r;
             A.trace = nullptr; A.trace_first = ctx->merge_trace_first;
             if (ctx->merge_kernel_choice == 4 && single_ok && !resume) {
                 F3PS_CUDA_OK(ctx->merge_trace.ensure(256 * 32 * 4));
@@ -1077,7 +1078,7 @@ int f3ps_set_blocking_wait(f3ps_ctx* ctx, int blocking) {
 }
 
 int f3ps_set_merge_kernel(f3ps_ctx* ctx, int which) {
-    if (!ctx || which < 0 || which > 4) return F3PS_ERR_INVALID_ARGUMENT;
+    if (!ctx || which < 0 || which > 5) return F3PS_ERR_INVALID_ARGUMENT;
     ctx->force_general_merge = which == 2;
     ctx->merge_kernel_choice = which;
     return F3PS_OK;

@@ -21,11 +21,13 @@
 // warp when <= 32 edges are touched), F (all: new geometry published), W4 (workers: new keys written).
 //
 // Two instantiations: tables in shared memory (S <= 4096, E <= 928 * 32, 12 E + 26 S + 40 KB within 227 KB: a VGA frame), or --
-// BIG -- the per-edge / per-region tables in global memory with per-block minima in shared memory (S < 65535, E <= 65504:
-// C5-size scenes).  A merge whose two adjacency lists hold more than 928 entries is not started: every role stops in front
-// of it, the state written back is that after n merges, and the host lets merge_kernel (kernels_merge.cuh) replay that one
-// merge from the same state and relaunches this kernel with A.resume (f3ps.cu: f3ps_merge).  An exhausted adjacency pool or
-// stamp range restarts the replay on merge_kernel.
+// BIG -- the per-edge / per-region tables in global memory with per-block minima in shared memory (S < 65535, 32-bit edge ids,
+// E bounded by 16 bytes of shared memory per block of 32 edges: C4 / C5-size scenes).  Shared-memory variant: a merge whose two
+// adjacency lists hold more than 928 entries is not started: every role stops in front of it, the state written back is that
+// after n merges, and the host lets merge_kernel (kernels_merge.cuh) replay that one merge from the same state and relaunches
+// this kernel with A.resume (f3ps.cu: f3ps_merge).  BIG variant: such a merge runs in lean_wide_merge (every worker thread loops
+// over the entries, per-entry state in a global scratch); only beyond 65,534 entries does it hand over.  An exhausted adjacency
+// pool or stamp range restarts the replay on merge_kernel.
 #pragma once
 #include "kernels_merge.cuh"
 
@@ -45,6 +47,26 @@ constexpr unsigned kNil16 = 0xffffu;
 constexpr unsigned kFastErrTouched = 4u;      // == F3PS_MERGE_ERR_TOUCHED
 constexpr unsigned kFastErrStamp = 8u;
 constexpr unsigned kFastErrPool = 16u;
+// BIG variant: a merge whose two adjacency lists hold more entries than there are worker threads (a floor or a wall of a dense scene
+// has thousands of neighbours) keeps its per-entry state in a global scratch (L2) and every worker thread loops over the entries
+// i, i + 928, ...  Entry indices travel in the 16-bit region marks, so the limit is 65,534 entries.
+constexpr int kLeanWideMax = 65534;
+constexpr unsigned kLeanWideSlots = 65536u;
+constexpr unsigned kLeanWideHash = 1u << 17;         // tie-group table of a wide merge (distinct new weights), power of two
+constexpr int kLeanWideHashShift = 15;               // 32 - log2(kLeanWideHash)
+struct LeanWideScratch {
+    unsigned long long* te_key; unsigned *te_e, *res_w; float* dcs; unsigned* hs; unsigned short* partner; unsigned char *cls, *flags;
+    unsigned *hkey, *hcnt;
+    static constexpr size_t bytes = (size_t)kLeanWideSlots * (8 + 4 + 4 + 4 + 4 + 2 + 1 + 1) + (size_t)kLeanWideHash * 8;
+    __host__ __device__ explicit LeanWideScratch(char* p) {
+        te_key = (unsigned long long*)p; p += (size_t)kLeanWideSlots * 8;
+        te_e = (unsigned*)p; p += (size_t)kLeanWideSlots * 4; res_w = (unsigned*)p; p += (size_t)kLeanWideSlots * 4;
+        dcs = (float*)p; p += (size_t)kLeanWideSlots * 4; hs = (unsigned*)p; p += (size_t)kLeanWideSlots * 4;
+        partner = (unsigned short*)p; p += (size_t)kLeanWideSlots * 2;
+        cls = (unsigned char*)p; p += kLeanWideSlots; flags = (unsigned char*)p; p += kLeanWideSlots;
+        hkey = (unsigned*)p; p += (size_t)kLeanWideHash * 4; hcnt = (unsigned*)p;
+    }
+};
 
 struct FastArgs {
     RegionArrays R; EdgeArrays E;
@@ -55,10 +77,10 @@ struct FastArgs {
     const unsigned* sv_label;
     MergeLog mlog; unsigned log_cap;
     MergeCtl* ctl;
-    unsigned short* adj_pool; unsigned pool_cap;   // adjacency lists (edge ids), bump-allocated; entries
+    unsigned short* adj_pool; unsigned pool_cap;   // adjacency lists (edge ids: 16 bits, BIG variant 32 bits), bump-allocated; capacity in entries
     unsigned* trace; unsigned trace_first;         // PROF only: clock() of 32 points of 256 merges starting at trace_first (f3ps_get_merge_trace)
     int resume;                              // continue a replay from the state in the edge / region arrays (counters in *ctl): set after the general kernel took one merge this kernel could not
-    char* big; unsigned* big_cursor;         // BIG variant only: the per-edge / per-region tables (12 E_cap + 26 S_cap bytes) and the set-up scratch (4 S_cap) in global memory
+    char* big; unsigned* big_cursor;         // BIG variant only: the per-edge / per-region tables (12 E_cap + 26 S_cap bytes) and the set-up scratch (4 S_cap) in global memory; LeanWideScratch sits at big_cursor + lean_cursor_bytes(S_cap)
     unsigned S_cap, E_cap;                   // table capacities the shared-memory layout was sized for (E_cap = E rounded up to whole blocks of 32 edges)
 };
 
@@ -114,6 +136,7 @@ struct FastSmem {
     }
     static __host__ __device__ size_t big_bytes(unsigned S, unsigned E_cap) { return (size_t)E_cap * 12 + (size_t)S * 26 + 256; }
 };
+__host__ __device__ inline size_t lean_cursor_bytes(unsigned S_cap) { return ((size_t)S_cap * 4 + 255) & ~(size_t)255; }
 enum { FM_NLIVE = 0, FM_EALIVE, FM_RALIVE, FM_COUNTER, FM_ND, FM_NANW, FM_ERROR, FM_MAXT, FM_SUMT, FM_MISS, FM_EVALS, FM_NMERGES, FM_POOL };
 
 // ---- PTX helpers: mbarrier, cp.async, named barriers ------------------------
@@ -267,13 +290,209 @@ __device__ __forceinline__ FastHead lean_head(const FastSmem& sm, int lane) {
     return h;
 }
 
+// BIG variant, an edge of block e / 32 goes from key `okey` to `nkey` (dead = removed): a key below the block's cached minimum
+// becomes the minimum by atomicMin (its edge id / end points are written after the next worker barrier by the thread whose key
+// won); only when the block's minimum edge itself moved up or died is the block reloaded (dirty bit, phase A).
+__device__ __forceinline__ void lean_block_min_update(const FastSmem& sm, unsigned e, unsigned long long okey, unsigned long long nkey) {
+    const unsigned blk = e >> 5;
+    if (sm.bm_e[blk] == e && nkey > okey) atomicOr(&sm.blkdirty[blk >> 5], 1u << (blk & 31u));
+    else if (nkey != kDeadKey64) atomicMin(&sm.bm_key[blk], nkey);
+}
 enum { FC_KEEP = 0, FC_FRONT = 1, FC_BACK = 2, FC_DUP = 3 };
 enum { BAR_W1 = 1, BAR_WB = 2, BAR_F = 3, BAR_W4 = 4, BAR_G = 5, BAR_FN = 6, BAR_GN = 7 };
 // A merge whose two adjacency lists hold <= 32 entries is NARROW: one worker warp handles it, the other 28 sleep until W4, and
 // the G / F barriers shrink to the warps involved (G: mean warp + worker warp 0; F: the three role warps + worker warp 0).
-__device__ __forceinline__ bool lean_too_wide(const FastSmem& sm, unsigned a, unsigned b) { return (unsigned)sm.adj_len[a] + (unsigned)sm.adj_len[b] > (unsigned)kLeanMaxTouched; }
+template <bool BIG>
+__device__ __forceinline__ bool lean_too_wide(const FastSmem& sm, unsigned a, unsigned b) {
+    return (unsigned)sm.adj_len[a] + (unsigned)sm.adj_len[b] > (unsigned)(BIG ? kLeanWideMax : kLeanMaxTouched);
+}
 __device__ __forceinline__ bool lean_wide(const FastSmem& sm, unsigned a, unsigned b) { return (unsigned)sm.adj_len[a] + (unsigned)sm.adj_len[b] > 32u; }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// BIG variant, a merge with more adjacency entries than worker threads (T > 928): the same steps as the one-entry-per-thread
+// code in merge_lean_body -- C (entries, duplicates through the region marks), colour deltas against the guess, D (geometry,
+// weight, class, tie groups, a's new list), E (tie stamps, new keys) -- with every worker thread looping over the entries
+// i, i + 928, ... and the per-entry state parked in LeanWideScratch between the barriers.  Same barrier protocol as a wide
+// merge of the main loop (WB1, G, F, WB2; the caller arrives at W4).  Off the hot path of a VGA frame: never inlined.
+template <bool PROF>
+__device__ __forceinline__ void lean_wide_merge(const FastArgs& A, float lambda, unsigned head_e, unsigned a, unsigned b, int counter, unsigned pool_top, int wtid) {
+    extern __shared__ __align__(128) char smem_raw[];
+    const FastSmem sm(smem_raw, A.S_cap, A.E_cap, A.big);          // (rebuilt here: a reference would pin the caller's copy to its stack)
+    EdgeParams ep = A.ep; ep.lambda = lambda;
+    const int lane = wtid & 31;
+    const RegionArrays& R = A.R;
+    unsigned* const pool = reinterpret_cast<unsigned*>(A.adj_pool);
+    const LeanWideScratch ws(reinterpret_cast<char*>(A.big_cursor) + lean_cursor_bytes(A.S_cap));
+    const int* const newgeo_i = reinterpret_cast<const int*>(sm.newgeo);
+    const unsigned la = sm.adj_len[a], lb = sm.adj_len[b], sa = sm.adj_start[a], sb = sm.adj_start[b];
+    const unsigned ca = sm.adj_cap[a], cb = sm.adj_cap[b];
+    const unsigned T = la + lb;
+    unsigned t_prev = PROF ? (unsigned)clock() : 0u;
+#define WIDE_PROF(k) do { if (PROF && wtid == 0) { const unsigned t_now = (unsigned)clock(); A.ctl->phase_cycles[20 + (k)] += t_now - t_prev; t_prev = t_now; } } while (0)
+    // ---- C: entries, duplicates (a,x)/(b,x) through the region marks ----
+    for (unsigned i = (unsigned)wtid; i < T; i += (unsigned)kFastOwners) {
+        const unsigned e = __ldcg(pool + (i < la ? sa + i : sb + (i - la)));
+        const unsigned eab = sm.ab[e];
+        const bool mine = e != head_e && eab != kDeadKey;                                  // lists keep removed edges until they are rewritten
+        ws.te_e[i] = mine ? e : kDeadKey;
+        if (mine) {
+            ws.te_key[i] = sm.key[e];
+            const unsigned ea = eab >> 16, eb = eab & 0xffffu;
+            const unsigned x = (ea == a || ea == b) ? eb : ea;
+            const unsigned short old = atomicCAS(&sm.mark[x], (unsigned short)kNil16, (unsigned short)i);
+            if (old != (unsigned short)kNil16) { ws.partner[i] = old; ws.partner[old] = (unsigned short)i; }
+        }
+    }
+    named_bar(BAR_WB, kFastOwners);                                                        // WB1
+    named_bar(BAR_G, 32 + kFastOwners);                                                    // G: the guess of a's new colour vector
+    WIDE_PROF(0);
+    const float4 guess = make_float4(sm.newgeo[10], sm.newgeo[11], sm.newgeo[12], 0.0f);
+    for (unsigned i = (unsigned)wtid; i < T; i += (unsigned)kFastOwners) {
+        const unsigned e = __ldcg(ws.te_e + i);
+        if (e == kDeadKey) continue;
+        const unsigned eab = sm.ab[e];
+        const unsigned ea = eab >> 16, eb = eab & 0xffffu;
+        const bool side_a = ea == a || eb == a;
+        const unsigned x = (ea == a || ea == b) ? eb : ea;
+        const unsigned long long okey = __ldcg(ws.te_key + i);
+        const unsigned q = __ldcg(ws.partner + i);
+        const bool dup = q != kNil16 && __ldcg(ws.te_key + q) < okey;                       // the earlier of (a,x), (b,x) survives
+        sm.mark[x] = (unsigned short)kNil16; ws.partner[i] = (unsigned short)kNil16;
+        const bool live = !dup;
+        float dc = __ldcg(A.E.dc + e);
+        const float4 xcv = __ldcg(R.cvec + x), ocv = __ldcg(R.cvec + (side_a ? a : b));
+        const bool same_cv = __float_as_uint(ocv.x) == __float_as_uint(guess.x) && __float_as_uint(ocv.y) == __float_as_uint(guess.y) &&
+                             __float_as_uint(ocv.z) == __float_as_uint(guess.z);
+        const bool reuse = same_cv && (side_a || ((b < x) == (a < x)));
+        const bool need = live && !reuse;
+        if (need) { const bool af = a < x; dc = colour_delta(ep.color_mode, af ? guess : xcv, af ? xcv : guess); }
+        ws.dcs[i] = dc; ws.flags[i] = (unsigned char)(live ? 1 : 0);
+    }
+    named_bar(BAR_F, kFastThreads);                                                        // F: region a's new colour vector / centroid / normal
+    WIDE_PROF(1);
+    // ---- D: colour delta after a wrong guess, geometry delta, weight, class, tie groups, a's new list ----
+    const bool fresh = ca < T && cb < T;
+    const unsigned ncap = fresh ? min(2u * T, 65535u) : (ca >= T ? ca : cb);
+    const unsigned dst = ca >= T ? sa : (cb >= T ? sb : pool_top);
+    const bool pool_ok = !fresh || pool_top + ncap <= A.pool_cap;
+    const bool hit = newgeo_i[9] != 0;
+    const float4 acv = make_float4(sm.newgeo[0], sm.newgeo[1], sm.newgeo[2], 0.0f);
+    const float4 ace = make_float4(sm.newgeo[3], sm.newgeo[4], sm.newgeo[5], 0.0f), anr = make_float4(sm.newgeo[6], sm.newgeo[7], sm.newgeo[8], 0.0f);
+    for (unsigned base = 0; base < T; base += (unsigned)kFastOwners) {                      // (uniform trip count: ballots inside)
+        const unsigned i = base + (unsigned)wtid;
+        const unsigned e = i < T ? __ldcg(ws.te_e + i) : kDeadKey;
+        bool live = false;
+        if (e != kDeadKey) {
+            live = __ldcg(ws.flags + i) != 0;
+            unsigned wbits = kDeadKey, hs = kDeadKey; int cls = FC_DUP;
+            if (live) {
+                const unsigned eab = sm.ab[e];
+                const unsigned ea = eab >> 16;
+                const unsigned x = (ea == a || ea == b) ? (eab & 0xffffu) : ea;
+                const bool a_first = a < x;
+                float dc = __ldcg(ws.dcs + i);
+                if (!hit) { const float4 xcv = __ldcg(R.cvec + x); dc = colour_delta(ep.color_mode, a_first ? acv : xcv, a_first ? xcv : acv); }   // wrong guess (rare)
+                const float4 c4 = __ldcg(R.centroid + x), n4 = __ldcg(R.normal + x);
+                const float dg = geom_delta(ep.geom_mode, a_first ? anr : n4, a_first ? ace : c4, a_first ? n4 : anr, a_first ? c4 : ace);
+                float w_new = unify(ep, dc, dg);
+                if (isnan(w_new)) { atomicAdd(&sm.misc[FM_NANW], 1); w_new = __int_as_float(0x7f800000); }
+                wbits = __float_as_uint(w_new);
+                const unsigned old_hi = (unsigned)(__ldcg(ws.te_key + i) >> 32);
+                cls = wbits == old_hi ? FC_KEEP : (wbits > old_hi ? FC_FRONT : FC_BACK);
+                if (cls != FC_KEEP) {                                                      // tie groups: same new weight, same side
+                    const unsigned hk = wbits | (cls == FC_FRONT ? 0x80000000u : 0u);
+                    unsigned h = (hk * 2654435761u) >> kLeanWideHashShift;
+                    while (true) {
+                        const unsigned prev = atomicCAS(&ws.hkey[h], kDeadKey, hk);
+                        if (prev == kDeadKey || prev == hk) break;
+                        h = (h + 1) & (kLeanWideHash - 1);
+                    }
+                    atomicAdd(&ws.hcnt[h], 1u);
+                    hs = h;
+                }
+                A.E.dc[e] = dc;
+            } else atomicAdd(&sm.misc[FM_ND], 1);
+            ws.res_w[i] = wbits; ws.cls[i] = (unsigned char)cls; ws.hs[i] = hs;
+        } else if (i < T) { ws.res_w[i] = kDeadKey; ws.cls[i] = (unsigned char)FC_DUP; ws.hs[i] = kDeadKey; }   // a removed edge's entry
+        const unsigned lm = __ballot_sync(kFull, live);                                     // survivors take consecutive places in a's new list
+        const int leader = __ffs(lm) - 1;
+        int at = 0;
+        if (lm && lane == leader) at = atomicAdd(&sm.misc[FM_NLIVE], __popc(lm));
+        at = __shfl_sync(kFull, at, leader < 0 ? 0 : leader);
+        if (live && pool_ok) pool[dst + (unsigned)at + (unsigned)__popc(lm & ((1u << lane) - 1u))] = e;
+    }
+    named_bar(BAR_WB, kFastOwners);                                                        // WB2
+    WIDE_PROF(2);
+    // ---- E: tie stamps, new keys ----
+    for (unsigned base = 0; base < T; base += (unsigned)kFastOwners) {                      // (uniform trip count: the ranks are warp-wide scans)
+        const unsigned i = base + (unsigned)wtid;
+        const unsigned e = i < T ? __ldcg(ws.te_e + i) : kDeadKey;
+        const bool mine = e != kDeadKey;
+        bool live = false; unsigned long long okey = kDeadKey64; unsigned wbits = kDeadKey, hs = kDeadKey, gsz = 0; int cls = FC_DUP;
+        if (mine) {
+            live = __ldcg(ws.flags + i) != 0; okey = __ldcg(ws.te_key + i);
+            wbits = __ldcg(ws.res_w + i); hs = __ldcg(ws.hs + i); cls = (int)__ldcg(ws.cls + i);
+            if (hs != kDeadKey) gsz = __ldcg(ws.hcnt + hs);
+        }
+        // new arrivals keep their old relative order inside a tie group: rank = entries of the group (same tie slot) with a smaller
+        // old key, counted by the whole warp for one tied lane after the other
+        unsigned rank = 0;
+        unsigned tied = __ballot_sync(kFull, gsz > 1u);
+        while (tied) {
+            const int src = __ffs(tied) - 1; tied &= tied - 1u;
+            const unsigned s_hs = __shfl_sync(kFull, hs, src);
+            const unsigned long long s_key = __shfl_sync(kFull, okey, src);
+            unsigned cnt = 0;
+#pragma unroll 8
+            for (unsigned q = (unsigned)lane; q < T; q += 32u)
+                if (__ldcg(ws.hs + q) == s_hs && __ldcg(ws.te_key + q) < s_key) ++cnt;
+            cnt = __reduce_add_sync(kFull, cnt);
+            if (lane == src) rank = cnt;
+        }
+        if (!mine) continue;
+        unsigned lo = (unsigned)okey;
+        if (hs != kDeadKey) {
+            const int st = cls == FC_BACK ? counter + (int)rank : -(counter + (int)(gsz - 1 - rank));
+            lo = (unsigned)st ^ 0x80000000u;
+        }
+        unsigned nab = kDeadKey;
+        if (live) {
+            const unsigned eab = sm.ab[e];
+            const unsigned ea = eab >> 16;
+            const unsigned x = (ea == a || ea == b) ? (eab & 0xffffu) : ea;
+            nab = a < x ? (a << 16) | x : (x << 16) | a;
+        }
+        const unsigned long long nkey = live ? ((unsigned long long)wbits << 32) | lo : kDeadKey64;
+        sm.key[e] = nkey;
+        sm.ab[e] = nab;
+        sm.bdirty[(e >> 5) % kLeanWorkerWarps] = 1u;
+        lean_block_min_update(sm, e, okey, nkey);
+    }
+    if (wtid == 0) {
+        if (counter > 0x7f000000 - (int)T) sm.misc[FM_ERROR] = (int)kFastErrStamp;
+        if (!pool_ok) sm.misc[FM_ERROR] = (int)kFastErrPool;
+        else if (fresh) sm.misc[FM_POOL] = (int)(pool_top + ncap);
+        sm.adj_start[a] = dst;
+        sm.adj_len[a] = (unsigned short)sm.misc[FM_NLIVE]; sm.adj_cap[a] = (unsigned short)ncap; sm.adj_len[b] = 0; sm.adj_cap[b] = 0;
+        sm.misc[FM_NLIVE] = 0;
+        sm.misc[FM_COUNTER] = counter + (int)T;
+        sm.misc[FM_EALIVE] -= 1 + sm.misc[FM_ND]; sm.misc[FM_ND] = 0; sm.misc[FM_RALIVE] -= 1;
+        if ((int)T > sm.misc[FM_MAXT]) sm.misc[FM_MAXT] = (int)T;
+        sm.misc[FM_SUMT] += (int)T; sm.misc[FM_MISS] += newgeo_i[9] ? 0 : 1;
+    }
+    named_bar(BAR_WB, kFastOwners);                                                        // every rank scan is done with the tie table; every atomicMin has landed
+    for (unsigned i = (unsigned)wtid; i < T; i += (unsigned)kFastOwners) {
+        const unsigned hs = __ldcg(ws.hs + i);
+        if (hs != kDeadKey) { ws.hkey[hs] = kDeadKey; ws.hcnt[hs] = 0u; }
+        const unsigned e = __ldcg(ws.te_e + i);
+        if (e != kDeadKey && __ldcg(ws.flags + i) != 0) {                                   // the new block minima's edge / end points
+            const unsigned long long k = sm.key[e];
+            if (sm.bm_key[e >> 5] == k) { sm.bm_e[e >> 5] = e; sm.bm_ab[e >> 5] = sm.ab[e]; }
+        }
+    }
+    WIDE_PROF(3);
+#undef WIDE_PROF
+}
 
 #define LPROF_DECL unsigned pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned t_prev = PROF ? (unsigned)clock() : 0u
 #define LPROF(cond, i) do { if (PROF && (cond)) { const unsigned t_now = (unsigned)clock(); pc[i] += t_now - t_prev; t_prev = t_now; } } while (0)
@@ -290,6 +509,8 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
     const RegionArrays R = A.R;
     const unsigned mbar_full = smem_addr(sm.mbar), mbar_empty = mbar_full + 8u * kLeanRing;
     int* const newgeo_i = reinterpret_cast<int*>(sm.newgeo);
+    using PoolT = typename std::conditional<BIG, unsigned, unsigned short>::type;          // edge ids of the adjacency lists
+    PoolT* const adj_pool = reinterpret_cast<PoolT*>(A.adj_pool);
 
     // ---- set-up: ropes, edges, adjacency lists -> shared memory / the pool ------------------------------------------------
     const unsigned nblk = A.E_cap / 32u;                                       // blocks of 32 edges; warp w owns w, w + 29, ...
@@ -307,6 +528,11 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
     if constexpr (BIG) for (unsigned i = tid; i < (nblk + 31u) / 32u; i += kFastThreads) sm.blkdirty[i] = 0xffffffffu;
     for (int i = tid; i < kLeanMaxTouched; i += kFastThreads) sm.partner[i] = (unsigned short)kNil16;
     for (int i = tid; i < kLeanHash; i += kFastThreads) { sm.hkey[i] = kDeadKey; sm.hcnt[i] = 0u; }
+    if constexpr (BIG) {
+        const LeanWideScratch ws(reinterpret_cast<char*>(A.big_cursor) + lean_cursor_bytes(A.S_cap));
+        for (unsigned i = tid; i < kLeanWideSlots; i += kFastThreads) ws.partner[i] = (unsigned short)kNil16;
+        for (unsigned i = tid; i < kLeanWideHash; i += kFastThreads) { ws.hkey[i] = kDeadKey; ws.hcnt[i] = 0u; }
+    }
     __syncthreads();
     for (unsigned e = tid; e < A.E_cap; e += kFastThreads) {
         unsigned long long k = kDeadKey64; unsigned ab = kDeadKey;
@@ -357,8 +583,8 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
         for (unsigned e = tid; e < A.E_cap; e += kFastThreads) {
             const unsigned ab = sm.ab[e];
             if (ab == kDeadKey) continue;
-            A.adj_pool[atomicAdd(&cursor[ab >> 16], 1u)] = (unsigned short)e;
-            A.adj_pool[atomicAdd(&cursor[ab & 0xffffu], 1u)] = (unsigned short)e;
+            adj_pool[atomicAdd(&cursor[ab >> 16], 1u)] = (PoolT)e;
+            adj_pool[atomicAdd(&cursor[ab & 0xffffu], 1u)] = (PoolT)e;
         }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the scratch words become the bulk copies' ring again
     __syncthreads();
@@ -378,7 +604,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             LPROF(lane == 0, 3);
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
-            if (lean_too_wide(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
+            if (lean_too_wide<BIG>(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
             const int na = sm.n[a], nb = sm.n[b];
             const bool wide = lean_wide(sm, a, b);
             LTRACE(lane == 0, 12, (unsigned)clock()); LTRACE(lane == 0, 21, (unsigned)nb);
@@ -455,7 +681,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             LPROF(lane == 0, 3);
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
-            if (lean_too_wide(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
+            if (lean_too_wide<BIG>(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
             const int na = sm.n[a], nb = sm.n[b];
             const bool wide = lean_wide(sm, a, b);
             LTRACE(lane == 0, 16, (unsigned)clock());
@@ -539,7 +765,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             const FastHead hd = lean_head(sm, lane);
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
-            if (lean_too_wide(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
+            if (lean_too_wide<BIG>(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
             const int na = sm.n[a], nb = sm.n[b];
             const bool wide = lean_wide(sm, a, b);
             if (nb > kLeanSlotVox) {                       // (the fold warps fetch a small region themselves, lean_fetch_small)
@@ -575,12 +801,12 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
         if (A.lambda_dev) ep.lambda = *A.lambda_dev;
         const int wtid = tid - 32 * kLeanRoleWarps;                                            // 0..927
         const int ww = warp - kLeanRoleWarps;                                                  // 0..28
-        const unsigned short* __restrict__ pool = A.adj_pool;
+        const PoolT* const pool = adj_pool;
         unsigned my_hs = kNil16;                                                               // tie-hash slot to clear after the next S1
         unsigned n_merges = A.resume ? A.ctl->n_merges : 0u;          // (the log continues behind the merges already replayed)
         LPROF_DECL;
         unsigned nm = 0;                                   // merges so far (trace index)
-        unsigned long long cls_cyc[3] = {0, 0, 0}; unsigned cls_cnt[3] = {0, 0, 0}; unsigned t_top = 0;   // PROF: merges by touched-edge class
+        unsigned long long cls_cyc[4] = {0, 0, 0, 0}; unsigned cls_cnt[4] = {0, 0, 0, 0}; unsigned t_top = 0;   // PROF: merges by touched-edge class
 #define WPROF(i) LPROF(wtid == 0, i)
         while (true) {
             if (PROF) t_top = (unsigned)clock();
@@ -591,25 +817,33 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                 __syncwarp();
                 if (lane == 0) sm.bdirty[ww] = 0u;
                 if constexpr (BIG) {
-                    // blocks of this warp with a re-weighted / removed edge: one coalesced reload each (four in flight), new block minimum
-                    for (unsigned j0 = 0; j0 < nbw; j0 += 4u) {
-                        unsigned long long k4[4]; unsigned b4[4]; bool d4[4];
+                    // blocks of this warp whose MINIMUM edge was re-weighted upwards or removed (every other re-weighted edge went into
+                    // its block's cached minimum by atomicMin, phase E): the lanes test 32 blocks at a time, the dirty ones are reloaded
+                    // (one coalesced 256 + 128-byte load each, eight in flight) and reduced to a new block minimum
+                    for (unsigned jb = 0; jb < nbw; jb += 32u) {
+                        const unsigned jl = jb + (unsigned)lane, bl = (unsigned)ww + kLeanWorkerWarps * jl;
+                        unsigned m = __ballot_sync(kFull, jl < nbw && bl < nblk && ((sm.blkdirty[bl >> 5] >> (bl & 31u)) & 1u));
+                        while (m) {
+                            unsigned long long k8[8]; unsigned a8[8], b8[8]; bool d8[8];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            b4[u] = (unsigned)ww + kLeanWorkerWarps * (j0 + (unsigned)u);
-                            d4[u] = j0 + (unsigned)u < nbw && b4[u] < nblk && ((sm.blkdirty[b4[u] >> 5] >> (b4[u] & 31u)) & 1u);
-                            k4[u] = d4[u] ? __ldcg(sm.key + b4[u] * 32u + (unsigned)lane) : kDeadKey64;
-                        }
+                            for (int u = 0; u < 8; ++u) {
+                                d8[u] = m != 0u;
+                                const unsigned q = d8[u] ? (unsigned)__ffs(m) - 1u : 0u;
+                                m &= m - 1u;
+                                b8[u] = (unsigned)ww + kLeanWorkerWarps * (jb + q);
+                                k8[u] = d8[u] ? __ldcg(sm.key + b8[u] * 32u + (unsigned)lane) : kDeadKey64;
+                                a8[u] = d8[u] ? __ldcg(sm.ab + b8[u] * 32u + (unsigned)lane) : kDeadKey;
+                            }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (!d4[u]) continue;                                           // (warp-uniform)
-                            const unsigned hi = (unsigned)(k4[u] >> 32), lo = (unsigned)k4[u];
-                            const unsigned m_hi = __reduce_min_sync(kFull, hi);
-                            const unsigned m_lo = __reduce_min_sync(kFull, hi == m_hi ? lo : kDeadKey);
-                            if (lane == __ffs(__ballot_sync(kFull, hi == m_hi && lo == m_lo)) - 1) {
-                                const unsigned e = b4[u] * 32u + (unsigned)lane;
-                                sm.bm_key[b4[u]] = k4[u]; sm.bm_e[b4[u]] = e; sm.bm_ab[b4[u]] = __ldcg(sm.ab + e);
-                                atomicAnd(&sm.blkdirty[b4[u] >> 5], ~(1u << (b4[u] & 31u)));
+                            for (int u = 0; u < 8; ++u) {
+                                if (!d8[u]) continue;                                       // (warp-uniform)
+                                const unsigned hi = (unsigned)(k8[u] >> 32), lo = (unsigned)k8[u];
+                                const unsigned m_hi = __reduce_min_sync(kFull, hi);
+                                const unsigned m_lo = __reduce_min_sync(kFull, hi == m_hi ? lo : kDeadKey);
+                                if (lane == __ffs(__ballot_sync(kFull, hi == m_hi && lo == m_lo)) - 1) {
+                                    sm.bm_key[b8[u]] = k8[u]; sm.bm_e[b8[u]] = b8[u] * 32u + (unsigned)lane; sm.bm_ab[b8[u]] = a8[u];
+                                    atomicAnd(&sm.blkdirty[b8[u] >> 5], ~(1u << (b8[u] & 31u)));
+                                }
                             }
                         }
                     }
@@ -645,7 +879,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             if (my_hs != kNil16) { sm.hkey[my_hs] = kDeadKey; sm.hcnt[my_hs] = 0u; my_hs = kNil16; }
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;   // strict <, src/clustering.cpp:388-389
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
-            if (lean_too_wide(sm, a, b)) { if (wtid == 0) sm.misc[FM_ERROR] = (int)kFastErrTouched; break; }   // nothing of this merge has happened yet
+            if (lean_too_wide<BIG>(sm, a, b)) { if (wtid == 0) sm.misc[FM_ERROR] = (int)kFastErrTouched; break; }   // nothing of this merge has happened yet
             const int counter = sm.misc[FM_COUNTER];
             const unsigned pool_top = (unsigned)sm.misc[FM_POOL];
             WPROF(1);
@@ -666,11 +900,21 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                     A.mlog.edges_left[n_merges] = (unsigned)sm.misc[FM_EALIVE]; A.mlog.regions_left[n_merges] = (unsigned)sm.misc[FM_RALIVE];
                 }
             }
+            if constexpr (BIG) {
+                if (T > kLeanMaxTouched) {                 // more adjacency entries than worker threads (CTA-uniform): every thread loops
+                    lean_wide_merge<PROF>(A, ep.lambda, hd.e, a, b, counter, pool_top, wtid);
+                    named_bar(BAR_W4, kFastOwners);                                            // W4
+                    WPROF(7);
+                    if (PROF && wtid == 0) { cls_cyc[3] += (unsigned)clock() - t_top; cls_cnt[3]++; }
+                    ++n_merges; ++nm;
+                    continue;
+                }
+            }
             // ---- C: duplicates (a,x)/(b,x) through a per-region mark; x's geometry; speculative colour deltas ----
             // Colour deltas are memoised per edge and speculated: while the fold runs, the edges whose stored delta does not
             // fit the GUESS of the merged region's colour vector (warp 1: Lab lattice point of the size-weighted mean) get
             // CIEDE2000 against the guess.  A wrong guess (about 1 merge in 10^3) re-evaluates after the fold.
-            unsigned e = 0, x = 0; bool side_a = false, mine = false; unsigned long long okey = kDeadKey64;
+            unsigned e = 0, x = 0; bool side_a = false, mine = false; unsigned long long okey = kDeadKey64, nkey = kDeadKey64;
             bool live = false, need = false;
             float dc = 0.0f; float4 xcv, c4, n4, ocv;
             const bool active = ww == 0 || wide;
@@ -775,7 +1019,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                             while (grp) { const int q = __ffs(grp) - 1; grp &= grp - 1u; if (sm.te_key[(wtid & ~31) + q] < okey) ++narrow_rank; }
                         }
                     }
-                    if (live && pool_ok) A.adj_pool[dst + (unsigned)base + (unsigned)__popc(lm & ((1u << lane) - 1u))] = (unsigned short)e;
+                    if (live && pool_ok) adj_pool[dst + (unsigned)base + (unsigned)__popc(lm & ((1u << lane) - 1u))] = (PoolT)e;
                 }
                 if (wide) named_bar(BAR_WB, kFastOwners); else __syncwarp();                   // WB2
                 if (mine) {
@@ -796,10 +1040,15 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
                         lo = (unsigned)st ^ 0x80000000u;
                         my_hs = hs;
                     }
-                    sm.key[e] = live ? ((unsigned long long)wbits << 32) | lo : kDeadKey64;
+                    nkey = live ? ((unsigned long long)wbits << 32) | lo : kDeadKey64;
+                    sm.key[e] = nkey;
                     sm.ab[e] = nab;
                     sm.bdirty[(e >> 5) % kLeanWorkerWarps] = 1u;
-                    if constexpr (BIG) atomicOr(&sm.blkdirty[e >> 10], 1u << ((e >> 5) & 31u));
+                    if constexpr (BIG) lean_block_min_update(sm, e, okey, nkey);
+                }
+                if constexpr (BIG) {                                                           // the new block minima's edge / end points
+                    if (wide) named_bar(BAR_WB, kFastOwners); else __syncwarp();
+                    if (mine && live && sm.bm_key[e >> 5] == nkey) { sm.bm_e[e >> 5] = e; sm.bm_ab[e >> 5] = nab; }
                 }
             }
             if (wtid == 0) {
@@ -827,7 +1076,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
         }
 #undef WPROF
         LPROF_STORE(wtid == 0, 0, 8);
-        if (PROF && wtid == 0) for (int i = 0; i < 3; ++i) { A.ctl->phase_cycles[8 + i] = cls_cyc[i]; A.ctl->phase_cycles[28 + i] = cls_cnt[i]; }
+        if (PROF && wtid == 0) for (int i = 0; i < 4; ++i) { A.ctl->phase_cycles[8 + i] = cls_cyc[i]; A.ctl->phase_cycles[i < 3 ? 28 + i : 31] = cls_cnt[i]; }
         if (wtid == 0) sm.misc[FM_NMERGES] = (int)n_merges;
     }
 
@@ -864,7 +1113,8 @@ template <bool PROF>
 __global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(const __grid_constant__ FastArgs A) { merge_lean_body<PROF>(A); }
 
 // graphs too large for an SM's shared memory (C5-size scenes): the same loop with the big tables in global memory
-__global__ void __launch_bounds__(kFastThreads, 1) merge_fast_big_kernel(const __grid_constant__ FastArgs A) { merge_lean_body<false, true>(A); }
+template <bool PROF>
+__global__ void __launch_bounds__(kFastThreads, 1) merge_fast_big_kernel(const __grid_constant__ FastArgs A) { merge_lean_body<PROF, true>(A); }
 
 // A batch of frames in ONE launch, CTA i replays frame i (f3ps_merge_batch).  Independent streams share at most 32 hardware
 // queues (CUDA_DEVICE_MAX_CONNECTIONS), so at most 32 single-CTA merge kernels ever overlap; one grid has no such limit.

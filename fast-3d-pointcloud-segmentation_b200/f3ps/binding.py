@@ -265,12 +265,14 @@ class Segmenter:
         a = (C.c_uint64 * 32)()
         self._chk(self.L.f3ps_merge_profile(self.h, C.byref(a)))
         v = list(a)
-        if self.counts().merge_path == 1:       # resident kernel; cycle counters only after set_merge_kernel(4)
+        if self.counts().merge_path in (1, 3):  # resident kernel; cycle counters only after set_merge_kernel(4) / (5)
             return {"worker": dict(zip(["scan_publish", "wait_s1_head", "incidence_w1", "dedupe_spec_ciede", "wait_fold", "weights_stamps", "wait_w4"], v[0:7])),
                     "mean": dict(zip(["wait_voxels", "fold", "lab_publish", "wait_s1"], v[12:16])),
                     "cov": dict(zip(["wait_voxels", "fold", "eigen_publish", "wait_s1"], v[16:20])),
                     "by_touched": {k: {"merges": v[28 + i], "cycles_per_merge": (v[8 + i] // v[28 + i]) if v[28 + i] else 0}
                                    for i, k in enumerate(["T<=32", "T<=128", "T>128"])},
+                    "wide": {"merges": v[31], "cycles_per_merge": (v[11] // v[31]) if v[31] else 0, "worker_total": v[7],
+                             "phases": dict(zip(["entries_marks_guess", "dedupe_colour_wait_fold", "weights_classes_list", "stamps_keys_clear"], v[20:24]))},
                     "guess_misses": v[24], "ciede_evals": v[25], "sum_T": v[27]}
         return dict(zip(["argmin", "fold", "order", "delta", "stamps", "wait_scan", "sum_T", "fold_tail"], v[:8]))
 

@@ -71,7 +71,7 @@ typedef struct f3ps_counts {
     int32_t max_touched;   /* largest number of edges re-weighted by one merge */
     int64_t fold_steps;    /* voxel steps folded by the merge loop (sum of |b|) */
     int32_t nan_weights;   /* edge weights that evaluated to NaN (regions with < 3 voxels) */
-    int32_t merge_path;    /* kernel the last f3ps_merge ran: 1 = resident (one SM, weight map in shared memory), 2 = general, 3 = resident with its tables in L2 (graphs too large for an SM), 4 / 5 = 1 / 3 with the general kernel taking the merges whose adjacency lists hold more than 928 entries (and, after 16 such hand-overs, the rest) */
+    int32_t merge_path;    /* kernel the last f3ps_merge ran: 1 = resident (one SM, weight map in shared memory), 2 = general, 3 = resident with its tables in L2 (graphs too large for an SM), 4 / 5 = 1 / 3 with the general kernel taking the merges whose adjacency lists hold more entries than the kernel handles (1: 928, 3: 65,534) (and, after 16 such hand-overs, the rest) */
 } f3ps_counts;
 
 /* ---- life cycle ------------------------------------------------------------ */
@@ -135,10 +135,12 @@ int f3ps_merge_batch(f3ps_ctx** ctxs, int n, float threshold);
  * blocking event.  Sweeps that keep more frames in flight than there are host cores must use 1. */
 int f3ps_set_blocking_wait(f3ps_ctx* ctx, int blocking);
 /* which K7 kernel f3ps_merge uses: 0 = automatic (the resident kernel when the graph fits one SM's shared memory; the same kernel
- * with its per-edge / per-region tables in L2 when it does not but S < 65,535 and E <= 65,504; else the general kernel -- which
- * also takes over when a merge touches more than 928 edges), 1 = resident in shared memory or general, 2 = always general,
- * 3 = resident with the tables in L2 even when the graph would fit an SM, 4 = 1 compiled with per-phase cycle counters and the merge
- * trace (f3ps_merge_profile, f3ps_merge_trace).  All replay the same merge sequence; the switch exists for tests and profiling. */
+ * with its per-edge / per-region tables in L2 when it does not but S < 65,535 and E < ~380,000 (16 bytes of shared memory per
+ * 32 edges); else the general kernel -- which also takes over when a merge of the shared-memory kernel has more than 928
+ * adjacency entries, or one of the L2 variant more than 65,534), 1 = resident in shared memory or general, 2 = always general,
+ * 3 = resident with the tables in L2 even when the graph would fit an SM, 4 / 5 = 1 / 3 compiled with per-phase cycle counters
+ * (4: and the merge trace; f3ps_merge_profile, f3ps_merge_trace).  All replay the same merge sequence; the switch exists for
+ * tests and profiling. */
 int f3ps_set_merge_kernel(f3ps_ctx* ctx, int which);
 /* Development aid of the resident kernel (kernel choice 4): SM clock values at 32 points of each of 256 consecutive merges,
  * starting at merge `first_merge` of the NEXT f3ps_merge; out (may be NULL to only set the window) receives the last

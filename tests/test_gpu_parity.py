@@ -471,10 +471,16 @@ def test_general_merge_kernel_hub_graph(gpu, oracle_mod, n_leaves, mode):
     c = g.counts()
     # (2: general kernel from the start; 4 / 5: the resident kernel up to the first merge that touches more edges than it has worker
     # threads, then the general kernel continues from its state -- the hand-over is part of what this test pins against the oracle)
-    assert c.merge_path in (2, 4, 5) and c.max_touched > 1024 and c.n_merges > 100, (c.merge_path, c.max_touched, c.n_merges)
-    first = (c.merge_path, g.array("merges_ab").copy(), g.array("final_ab").copy())
+    # -- or 3: the graph does not fit an SM, the resident kernel with its tables in L2 loops over the entries of such merges itself)
+    assert c.merge_path in (2, 3, 4, 5) and c.max_touched > 1024 and c.n_merges > 100, (c.merge_path, c.max_touched, c.n_merges)
+    first = (c.merge_path, g.array("merges_ab").copy(), g.array("final_ab").copy(), g.array("final_w").copy(), g.array("merges_w").copy())
     g.set_merge_kernel(2); g.merge(thr)                  # the general kernel alone replays the same sequence
     assert g.counts().merge_path == 2 and np.array_equal(g.array("merges_ab"), first[1]) and np.array_equal(g.array("final_ab"), first[2])
+    g.set_merge_kernel(3); g.merge(thr)                  # tables in L2: merges with more than 928 adjacency entries run in lean_wide_merge, no hand-over
+    c3 = g.counts()
+    assert c3.merge_path == 3 and c3.max_touched > 1024 and c3.n_merges == c.n_merges, (c3.merge_path, c3.max_touched, c3.n_merges)
+    assert np.array_equal(g.array("merges_ab"), first[1]) and np.array_equal(g.array("final_ab"), first[2])
+    assert same(g.array("final_w"), first[3]) and same(g.array("merges_w"), first[4])
     g.set_merge_kernel(0); g.merge(thr)
     if n_leaves >= 9000:
         assert c.max_touched > 8192                  # the global-memory sort as well

@@ -27,3 +27,6 @@ for kern in (2, 0):
         kern, c.merge_path, c.n_supervoxels, c.n_edges, c.n_merges, c.max_touched, c.fold_steps, ms["merge_kernel"],
         1e3 * ms["merge_kernel"] / max(1, c.n_merges), "identical" if not bad else "DIFF " + ",".join(bad)), flush=True)
 print({k: round(v, 3) for k, v in g.stage_ms().items()})
+g.set_merge_kernel(5); g.merge(0.2); g.sync()            # the same kernel compiled with phase counters
+import json
+print("phase counters (kernel 5, %.2f ms):" % g.stage_ms()["merge_kernel"], json.dumps(g.merge_profile()))
