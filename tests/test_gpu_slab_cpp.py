@@ -1,0 +1,38 @@
+"""Slab mode driven from C++ over NCCL (host/slab_host.cpp: one thread, stream, handle and ncclComm_t per GPU) against ONE
+handle processing the whole cloud -- SURVEY.md section 8e row 2 with the host side in C++ as BASELINE's north_star asks.
+host/slab_selftest cuts a synthetic room scan (with drop-outs and negative z) into uneven shares, runs the protocol of
+f3ps/slab.py through NCCL, and compares every rank's voxel labels / distances, merge log and labelled cloud with the single
+handle bit for bit.  On a one-GPU box the world is 1 (every collective degenerates, the routing / slicing code still runs);
+with two or more visible GPUs the exchanges are real."""
+import json
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "fast-3d-pointcloud-segmentation_b200", "host")
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def selftest():
+    import f3ps
+    f3ps.build()
+    subprocess.check_call(["make", "-C", HOST, "-s"])
+    exe = os.path.join(HOST, "slab_selftest")
+    assert os.path.exists(exe)
+    return exe
+
+
+@pytest.mark.parametrize("shard", [1, 0], ids=["sharded_sweeps", "replicated_expand"])
+def test_cpp_nccl_slab_mode_equals_one_handle(selftest, shard):
+    import torch
+    gpus = min(2, torch.cuda.device_count())
+    out = subprocess.run([selftest, "--gpus", str(gpus), "--points", "400000", "--shard-expand", str(shard)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    assert rec["identical_to_one_handle"] is True and rec["gpus"] == gpus
+    assert rec["V"] > 10000 and rec["merges"] > 10 and rec["sharded_expand"] == bool(shard)
