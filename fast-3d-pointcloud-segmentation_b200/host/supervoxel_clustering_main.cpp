@@ -24,6 +24,7 @@
 #include <thread>
 
 #include "pcd_io.h"
+#include "slab_host.h"
 #include "supervoxel_clustering/clustering.h"
 
 namespace {
@@ -71,7 +72,9 @@ void usage(const char* a0) {
            "\t -o <file.pcd>                  (writes the labelled voxel cloud) \n"
            "\t --facade                       (runs through the Clustering / SupervoxelClustering classes) \n"
            "\t --gpus <N>                     (shards the files of -d over N GPUs) \n"
-           "\t --inflight <K>                 (frames in flight per GPU during a -d sweep, default 8) \n", a0);
+           "\t --inflight <K>                 (frames in flight per GPU during a -d sweep, default 8) \n"
+           "\t --slabs <N>                    (with -p and -t: ONE cloud cut into N spatial slabs, one per GPU, exchanges over NCCL;\n"
+           "\t                                 same result as one GPU; no evaluation against ground truth in this mode) \n", a0);
 }
 
 // main()'s input clean-up (src/supervoxel_clustering.cpp:315-337): z<0 -> |z|; with -r, the points of that label and the points
@@ -365,6 +368,63 @@ int process_file(const std::string& file, const Options& o, int device, std::str
 }
 } // namespace
 
+// --slabs N: one very large cloud over N GPUs (BASELINE config 5).  The reference's call sequence for the file (:313-367, 408-449)
+// with SupervoxelClustering::extract + Clustering::cluster replaced by f3ps_host::SlabRun (slab_host.h); rank 0's handle reports.
+int run_slabs(const std::string& file, const Options& o, int slabs) {
+    pcl::PointCloud<pcl::PointXYZRGBL> input;
+    f3ps::loadPCDFile(file, input);
+    clean_input(input, o);
+    pcl::PointCloud<pcl::PointXYZRGBA> cloud;
+    pcl::copyPointCloud(input, cloud);
+    std::vector<int> devs; for (int d = 0; d < slabs; ++d) devs.push_back(d);
+    f3ps_host::SlabRun run(devs);
+    if (!run.ok()) { fprintf(stderr, "error: slab mode on %d GPUs: %s\n", slabs, run.init_error().c_str()); return 2; }
+    f3ps_host::SlabParams sp;
+    sp.voxel_res = o.voxel_resolution; sp.seed_res = o.seed_resolution; sp.color_imp = o.color_importance; sp.spatial_imp = o.spatial_importance;
+    sp.normal_imp = o.normal_importance; sp.use_transform = o.disable_transform ? 0 : 1; sp.fold_negative_z = 0;
+    sp.color_distance = o.rgb ? F3PS_RGB_EUCL : F3PS_LAB_CIEDE00; sp.geometric_distance = o.cvx ? F3PS_CONVEX_NORMALS_DIFF : F3PS_NORMALS_DIFF;
+    sp.merging = o.ml ? F3PS_MANUAL_LAMBDA : (o.eq ? F3PS_EQUALIZATION : F3PS_ADAPTIVE_LAMBDA);
+    sp.lambda = (o.ml && o.lambda != 0) ? o.lambda : 0.5f; sp.bins = (o.eq && o.bin_num != 0) ? o.bin_num : 500; sp.threshold = o.thresh;
+    const int64_t n = (int64_t)cloud.size();
+    std::vector<f3ps_host::SlabShare> shares((size_t)slabs);
+    for (int r = 0; r < slabs; ++r) {
+        const int64_t lo = n * r / slabs, hi = n * (r + 1) / slabs;
+        shares[(size_t)r].points = cloud.points.data() + lo; shares[(size_t)r].n = hi - lo; shares[(size_t)r].stride = 32;
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    if (run.run(shares, sp)) {
+        for (int r = 0; r < slabs; ++r) if (!run.info(r).error.empty()) fprintf(stderr, "error: slab rank %d: %s\n", r, run.info(r).error.c_str());
+        return 2;
+    }
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    f3ps_ctx* h = run.handle(0);
+    f3ps_counts c; f3ps_get_counts(h, &c);
+    printf("Loading pointcloud from PCD file '%s'...\nFound %d supervoxels\n", file.c_str(), c.n_supervoxels);
+    if (o.verbose) {
+        std::vector<uint32_t> ab(2 * (size_t)c.n_merges), left(2 * (size_t)c.n_merges); std::vector<float> w((size_t)c.n_merges);
+        if (c.n_merges) f3ps_get_merge_log(h, ab.data(), w.data(), left.data(), (int64_t)c.n_merges);
+        for (int m = 0; m < c.n_merges; ++m) printf("left: %de/%dp - w: %f - [%d, %d]...OK\n", left[2 * m], left[2 * m + 1], w[(size_t)m], ab[2 * m], ab[2 * m + 1]);
+    }
+    printf("Clustering complete: %lld points -> %d merges -> %d segments over %d voxels in %.3f ms (%d GPUs, slab mode over NCCL)\n",
+           (long long)n, c.n_merges, c.n_segments, c.n_labeled, ms, slabs);
+    std::map<std::string, float> worst; std::vector<std::string> order;
+    for (int r = 0; r < slabs; ++r)
+        for (auto& kv : run.info(r).stage_ms) { if (!worst.count(kv.first)) order.push_back(kv.first); worst[kv.first] = std::max(worst[kv.first], kv.second); }
+    printf("  stage ms (max over ranks):");
+    for (auto& k : order) printf(" %s %.3f", k.c_str(), worst[k]);
+    printf("\n  voxels %lld, exchanged %.1f MB (rank 0)\n", (long long)run.info(0).V, (double)run.info(0).bytes_exchanged / 1e6);
+    if (!o.out.empty()) {
+        pcl::PointCloud<pcl::PointXYZL> labeled;
+        std::vector<float> xyz(3 * (size_t)c.n_labeled); std::vector<uint32_t> lab((size_t)c.n_labeled), vox((size_t)c.n_labeled);
+        if (c.n_labeled) f3ps_get_labeled_cloud(h, xyz.data(), lab.data(), vox.data(), c.n_labeled);
+        labeled.points.resize((size_t)c.n_labeled);
+        for (int i = 0; i < c.n_labeled; ++i) { auto& q = labeled.points[(size_t)i]; q.x = xyz[3 * (size_t)i]; q.y = xyz[3 * (size_t)i + 1]; q.z = xyz[3 * (size_t)i + 2]; q.label = lab[(size_t)i]; }
+        labeled.width = (uint32_t)c.n_labeled; labeled.height = 1;
+        f3ps::savePCDFileASCII(o.out, labeled);
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 3) { usage(argv[0]); return 1; }
     Options o;
@@ -399,6 +459,11 @@ int main(int argc, char** argv) {
     int gpus = 1; parse(argc, argv, "--gpus", gpus); gpus = std::max(1, gpus);
     int inflight = 8; parse(argc, argv, "--inflight", inflight); inflight = std::max(1, inflight);
     setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);                     // before the CUDA context exists (see f3ps_create)
+    int slabs = 0; parse(argc, argv, "--slabs", slabs);
+    if (slabs > 0) {
+        if (file_list.size() != 1 || !o.thresh_specified || o.facade) { fprintf(stderr, "--slabs needs one input file (-p) and a threshold (-t)\n"); return 1; }
+        try { return run_slabs(file_list[0], o, slabs); } catch (const std::exception& e) { fprintf(stderr, "error: %s\n", e.what()); return 2; }
+    }
     int rc = 0;
     std::vector<std::string> reports(file_list.size());
     std::vector<FileScores> scores(file_list.size());

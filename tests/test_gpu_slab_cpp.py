@@ -36,3 +36,26 @@ def test_cpp_nccl_slab_mode_equals_one_handle(selftest, shard):
     rec = json.loads(out.stdout.strip().splitlines()[-1])
     assert rec["identical_to_one_handle"] is True and rec["gpus"] == gpus
     assert rec["V"] > 10000 and rec["merges"] > 10 and rec["sharded_expand"] == bool(shard)
+
+
+def test_cli_slabs_prints_the_same_merge_sequence(selftest, small_frame, tmp_path):
+    """supervoxel_clustering -p cloud.pcd -t 0.2 --CVX --AL --V [--slabs N]: the reference's per-merge debug lines
+    (src/clustering.cpp:390-392) and the labelled cloud written by -o are the same with and without slab mode."""
+    import torch
+    from f3ps import pcd
+    gpus = min(2, torch.cuda.device_count())
+    cli = os.path.join(HOST, "supervoxel_clustering")
+    p = str(tmp_path / "cloud.pcd")
+    pcd.write_pcd_binary(p, small_frame)
+    outs = []
+    for extra, name in (([], "one.pcd"), (["--slabs", str(gpus)], "slabs.pcd")):
+        o = str(tmp_path / name)
+        run = subprocess.run([cli, "-p", p, "-t", "0.2", "--CVX", "--AL", "--V", "--no-eval", "-o", o] + extra, capture_output=True, text=True, timeout=300)
+        assert run.returncode == 0, run.stdout + run.stderr
+        lines = [l for l in run.stdout.splitlines() if l.startswith("left:") or l.startswith("Found ")]
+        assert len(lines) > 50
+        outs.append((lines, open(o).read()))
+    assert outs[0][0] == outs[1][0]
+    assert outs[0][1] == outs[1][1]
+    bad = subprocess.run([cli, "-p", p, "--slabs", "1"], capture_output=True, text=True)      # no -t: refused
+    assert bad.returncode == 1 and "--slabs needs" in bad.stderr
