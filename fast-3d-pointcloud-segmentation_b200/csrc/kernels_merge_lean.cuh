@@ -55,11 +55,12 @@ constexpr unsigned kLeanWideSlots = 65536u;
 constexpr unsigned kLeanWideHash = 1u << 17;         // tie-group table of a wide merge (distinct new weights), power of two
 constexpr int kLeanWideHashShift = 15;               // 32 - log2(kLeanWideHash)
 struct LeanWideScratch {
-    unsigned long long* te_key; unsigned *te_e, *res_w; float* dcs; unsigned* hs; unsigned short* partner; unsigned char *cls, *flags;
+    unsigned long long *te_key, *nkey; unsigned *te_e, *res_w, *xs; float* dcs; unsigned* hs; unsigned short* partner; unsigned char *cls, *flags;
     unsigned *hkey, *hcnt;
-    static constexpr size_t bytes = (size_t)kLeanWideSlots * (8 + 4 + 4 + 4 + 4 + 2 + 1 + 1) + (size_t)kLeanWideHash * 8;
+    static constexpr size_t bytes = (size_t)kLeanWideSlots * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 2 + 1 + 1) + (size_t)kLeanWideHash * 8;
     __host__ __device__ explicit LeanWideScratch(char* p) {
-        te_key = (unsigned long long*)p; p += (size_t)kLeanWideSlots * 8;
+        te_key = (unsigned long long*)p; p += (size_t)kLeanWideSlots * 8; nkey = (unsigned long long*)p; p += (size_t)kLeanWideSlots * 8;
+        xs = (unsigned*)p; p += (size_t)kLeanWideSlots * 4;
         te_e = (unsigned*)p; p += (size_t)kLeanWideSlots * 4; res_w = (unsigned*)p; p += (size_t)kLeanWideSlots * 4;
         dcs = (float*)p; p += (size_t)kLeanWideSlots * 4; hs = (unsigned*)p; p += (size_t)kLeanWideSlots * 4;
         partner = (unsigned short*)p; p += (size_t)kLeanWideSlots * 2;
@@ -339,6 +340,7 @@ __device__ __forceinline__ void lean_wide_merge(const FastArgs& A, float lambda,
             ws.te_key[i] = sm.key[e];
             const unsigned ea = eab >> 16, eb = eab & 0xffffu;
             const unsigned x = (ea == a || ea == b) ? eb : ea;
+            ws.xs[i] = x | ((ea == a || eb == a) ? 0x10000u : 0u);                          // far end + "this edge hangs on a": the later phases do not go back to the edge table
             const unsigned short old = atomicCAS(&sm.mark[x], (unsigned short)kNil16, (unsigned short)i);
             if (old != (unsigned short)kNil16) { ws.partner[i] = old; ws.partner[old] = (unsigned short)i; }
         }
@@ -349,11 +351,10 @@ __device__ __forceinline__ void lean_wide_merge(const FastArgs& A, float lambda,
     const float4 guess = make_float4(sm.newgeo[10], sm.newgeo[11], sm.newgeo[12], 0.0f);
     for (unsigned i = (unsigned)wtid; i < T; i += (unsigned)kFastOwners) {
         const unsigned e = __ldcg(ws.te_e + i);
+        const unsigned xw = __ldcg(ws.xs + i);
         if (e == kDeadKey) continue;
-        const unsigned eab = sm.ab[e];
-        const unsigned ea = eab >> 16, eb = eab & 0xffffu;
-        const bool side_a = ea == a || eb == a;
-        const unsigned x = (ea == a || ea == b) ? eb : ea;
+        const bool side_a = (xw & 0x10000u) != 0u;
+        const unsigned x = xw & 0xffffu;
         const unsigned long long okey = __ldcg(ws.te_key + i);
         const unsigned q = __ldcg(ws.partner + i);
         const bool dup = q != kNil16 && __ldcg(ws.te_key + q) < okey;                       // the earlier of (a,x), (b,x) survives
@@ -386,9 +387,7 @@ __device__ __forceinline__ void lean_wide_merge(const FastArgs& A, float lambda,
             live = __ldcg(ws.flags + i) != 0;
             unsigned wbits = kDeadKey, hs = kDeadKey; int cls = FC_DUP;
             if (live) {
-                const unsigned eab = sm.ab[e];
-                const unsigned ea = eab >> 16;
-                const unsigned x = (ea == a || ea == b) ? (eab & 0xffffu) : ea;
+                const unsigned x = __ldcg(ws.xs + i) & 0xffffu;
                 const bool a_first = a < x;
                 float dc = __ldcg(ws.dcs + i);
                 if (!hit) { const float4 xcv = __ldcg(R.cvec + x); dc = colour_delta(ep.color_mode, a_first ? acv : xcv, a_first ? xcv : acv); }   // wrong guess (rare)
@@ -404,10 +403,10 @@ __device__ __forceinline__ void lean_wide_merge(const FastArgs& A, float lambda,
                     unsigned h = (hk * 2654435761u) >> kLeanWideHashShift;
                     while (true) {
                         const unsigned prev = atomicCAS(&ws.hkey[h], kDeadKey, hk);
+                        if (prev == hk) ws.hcnt[h] = 1u;                                   // a second entry with this weight and side: a tie group (rare)
                         if (prev == kDeadKey || prev == hk) break;
                         h = (h + 1) & (kLeanWideHash - 1);
                     }
-                    atomicAdd(&ws.hcnt[h], 1u);
                     hs = h;
                 }
                 A.E.dc[e] = dc;
@@ -432,7 +431,7 @@ __device__ __forceinline__ void lean_wide_merge(const FastArgs& A, float lambda,
         if (mine) {
             live = __ldcg(ws.flags + i) != 0; okey = __ldcg(ws.te_key + i);
             wbits = __ldcg(ws.res_w + i); hs = __ldcg(ws.hs + i); cls = (int)__ldcg(ws.cls + i);
-            if (hs != kDeadKey) gsz = __ldcg(ws.hcnt + hs);
+            if (hs != kDeadKey) gsz = 1u + __ldcg(ws.hcnt + hs);                            // 2 = "tied" (the group's size comes out of the rank scan)
         }
         // new arrivals keep their old relative order inside a tie group: rank = entries of the group (same tie slot) with a smaller
         // old key, counted by the whole warp for one tied lane after the other
@@ -442,12 +441,12 @@ __device__ __forceinline__ void lean_wide_merge(const FastArgs& A, float lambda,
             const int src = __ffs(tied) - 1; tied &= tied - 1u;
             const unsigned s_hs = __shfl_sync(kFull, hs, src);
             const unsigned long long s_key = __shfl_sync(kFull, okey, src);
-            unsigned cnt = 0;
+            unsigned cnt = 0, grp = 0;
 #pragma unroll 8
             for (unsigned q = (unsigned)lane; q < T; q += 32u)
-                if (__ldcg(ws.hs + q) == s_hs && __ldcg(ws.te_key + q) < s_key) ++cnt;
-            cnt = __reduce_add_sync(kFull, cnt);
-            if (lane == src) rank = cnt;
+                if (__ldcg(ws.hs + q) == s_hs) { ++grp; if (__ldcg(ws.te_key + q) < s_key) ++cnt; }
+            cnt = __reduce_add_sync(kFull, cnt); grp = __reduce_add_sync(kFull, grp);
+            if (lane == src) { rank = cnt; gsz = grp; }
         }
         if (!mine) continue;
         unsigned lo = (unsigned)okey;
@@ -456,13 +455,9 @@ __device__ __forceinline__ void lean_wide_merge(const FastArgs& A, float lambda,
             lo = (unsigned)st ^ 0x80000000u;
         }
         unsigned nab = kDeadKey;
-        if (live) {
-            const unsigned eab = sm.ab[e];
-            const unsigned ea = eab >> 16;
-            const unsigned x = (ea == a || ea == b) ? (eab & 0xffffu) : ea;
-            nab = a < x ? (a << 16) | x : (x << 16) | a;
-        }
+        if (live) { const unsigned x = __ldcg(ws.xs + i) & 0xffffu; nab = a < x ? (a << 16) | x : (x << 16) | a; }
         const unsigned long long nkey = live ? ((unsigned long long)wbits << 32) | lo : kDeadKey64;
+        ws.nkey[i] = nkey;
         sm.key[e] = nkey;
         sm.ab[e] = nab;
         sm.bdirty[(e >> 5) % kLeanWorkerWarps] = 1u;
@@ -486,8 +481,10 @@ __device__ __forceinline__ void lean_wide_merge(const FastArgs& A, float lambda,
         if (hs != kDeadKey) { ws.hkey[hs] = kDeadKey; ws.hcnt[hs] = 0u; }
         const unsigned e = __ldcg(ws.te_e + i);
         if (e != kDeadKey && __ldcg(ws.flags + i) != 0) {                                   // the new block minima's edge / end points
-            const unsigned long long k = sm.key[e];
-            if (sm.bm_key[e >> 5] == k) { sm.bm_e[e >> 5] = e; sm.bm_ab[e >> 5] = sm.ab[e]; }
+            if (sm.bm_key[e >> 5] == __ldcg(ws.nkey + i)) {
+                const unsigned x = __ldcg(ws.xs + i) & 0xffffu;
+                sm.bm_e[e >> 5] = e; sm.bm_ab[e >> 5] = a < x ? (a << 16) | x : (x << 16) | a;
+            }
         }
     }
     WIDE_PROF(3);
