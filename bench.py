@@ -495,8 +495,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--inflight", type=int, default=96, help="frames per merge grid (batch pool) / frames in flight per GPU (streams pool)")
-    ap.add_argument("--rounds", type=int, default=8, help="groups per step (batch pool) / frames each handle runs back to back inside one step (streams pool)")
+    ap.add_argument("--inflight", type=int, default=80, help="frames per merge grid (batch pool) / frames in flight per GPU (streams pool); measured on one B200, C2: 48 -> 338, 64 -> 401, 72 -> 422, 80 -> 435, 96 -> 394 Mpoints/s resident (a merge CTA holds its SM for ~26 ms: 80 of them leave 68 SMs to the front stages of the next group)")
+    ap.add_argument("--rounds", type=int, default=10, help="groups per step (batch pool) / frames each handle runs back to back inside one step (streams pool)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (development)")
     ap.add_argument("--pool", default="batch", choices=["batch", "streams"], help="batch: one merge launch per group of --inflight frames; streams: one merge kernel per stream")
     ap.add_argument("--expand-cluster", type=int, default=8, help="batch pool: K5 of a frame as one thread-block cluster of this many CTAs (0 = cooperative grid, see --expand-ctas)")
