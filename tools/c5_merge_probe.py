@@ -1,5 +1,7 @@
-"""K7 on a C5-style graph (10 M-point room scan: S ~ 14 k, E ~ 50 k, M ~ 14 k): the resident kernel with its tables in L2
-(f3ps_set_merge_kernel 0 / 3) against the general kernel (2): ms, us per merge, identical merge logs."""
+"""K7 on the large scenes -- c5: 10 M-point room scan (S ~ 14 k, E ~ 50 k, M ~ 14 k); c4: the 10 M-point dense scene (S ~ 21 k,
+E ~ 134 k, M ~ 19 k, 3,430 merges with more than 928 adjacency entries): the resident kernel with its tables in L2
+(f3ps_set_merge_kernel 0 / 3) against the general kernel (2): ms, us per merge, identical merge logs; then the phase counters of
+the same kernel compiled with them (5)."""
 import os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fast-3d-pointcloud-segmentation_b200"))
 import numpy as np
