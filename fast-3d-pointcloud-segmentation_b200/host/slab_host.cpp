@@ -50,6 +50,16 @@ std::vector<uint64_t> choose_splitters(const std::vector<uint32_t>& hist, int wo
     return cuts;
 }
 
+}  // namespace f3ps_host
+// plain-C view of choose_splitters for the CPU test (tests/test_slab_host_logic.py compares it with f3ps/slab.py's)
+extern "C" int f3ps_host_choose_splitters(const uint32_t* hist, int n_bins, int world, int shift, uint64_t* out) {
+    if (!hist || n_bins < 1 || world < 1 || !out) return F3PS_ERR_INVALID_ARGUMENT;
+    const std::vector<uint64_t> cuts = f3ps_host::choose_splitters(std::vector<uint32_t>(hist, hist + n_bins), world, shift);
+    for (size_t i = 0; i < cuts.size(); ++i) out[i] = cuts[i];
+    return F3PS_OK;
+}
+namespace f3ps_host {
+
 SlabRun::SlabRun(const std::vector<int>& devices) : devices_(devices) {
     const size_t w = devices_.size();
     ctx_.assign(w, nullptr); stream_.assign(w, nullptr); comm_.assign(w, nullptr); info_.resize(w); status_.assign(w, 0);

@@ -68,3 +68,5 @@ private:
 std::vector<uint64_t> choose_splitters(const std::vector<uint32_t>& hist, int world, int shift);
 
 }  // namespace f3ps_host
+
+extern "C" int f3ps_host_choose_splitters(const uint32_t* hist, int n_bins, int world, int shift, uint64_t* out /*[world-1]*/);

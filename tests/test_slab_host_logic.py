@@ -29,6 +29,37 @@ def test_choose_splitters_equal_count():
     assert list(slab.slice_bounds([3, 0, 5])) == [0, 3, 3, 8]
 
 
+def test_cpp_choose_splitters_equals_python():
+    """host/slab_host.cpp (the C++ NCCL slab host) cuts the key space exactly where f3ps/slab.py does: the two hosts drive the same
+    protocol, so a cloud lands in the same slabs whichever one runs it."""
+    import ctypes as C
+    import os
+    import subprocess
+    from f3ps import slab
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fast-3d-pointcloud-segmentation_b200", "host")
+    subprocess.check_call(["make", "-C", os.path.dirname(host), "-s"])
+    subprocess.check_call(["make", "-C", host, "-s", "libf3ps_slab.so"])
+    lib = C.CDLL(os.path.join(host, "libf3ps_slab.so"))
+    lib.f3ps_host_choose_splitters.restype = C.c_int
+    lib.f3ps_host_choose_splitters.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(17)
+    cases = []
+    for n_bins in (1, 2, 64, 4096):
+        for _ in range(6):
+            h = rng.integers(0, 5000, n_bins).astype(np.uint32)
+            if rng.random() < 0.5:
+                h[rng.integers(0, n_bins, max(1, n_bins // 2))] = 0
+            cases.append(h)
+    cases += [np.zeros(64, np.uint32), np.eye(1, 64, 10, dtype=np.uint32)[0] * 99]
+    for h in cases:
+        for world in (1, 2, 3, 8):
+            for shift in (0, 9, 33):
+                want = slab.choose_splitters(h, world, shift)
+                got = np.zeros(max(1, world - 1), np.uint64)
+                assert lib.f3ps_host_choose_splitters(h.ctypes.data, len(h), world, shift, got.ctypes.data) == 0
+                assert np.array_equal(got[:world - 1], want), (len(h), world, shift)
+
+
 def _oracle_keys(pts):
     """Morton key of every point's voxel (x-major), from the oracle's voxelisation -- test-side stand-in for K1 keygen."""
     import oracle_py
