@@ -250,11 +250,13 @@ int f3ps_eval_label_pairs(f3ps_ctx* ctx, const uint32_t* seg, const uint32_t* tr
 int f3ps_stage_ms(f3ps_ctx* ctx, int stage, float* ms);
 /* Profiling aid: SM cycles (clock64) the last f3ps_merge spent per phase, and event counts.
  * General kernel: [0..4] argmin, fold||edge scan, ordering, re-weighting, tie stamps (thread 0).
- * Resident kernel: [0..7] delta warps: head, wait for the touched list, order/dedupe, speculative CIEDE, wait for the
- * fold, CIEDE after a wrong guess, weights + stamps, order/dedupe of the > 32-edge path;  [12..15] colour-mean warp: wait for
- * the voxels, fold, Lab + publish, wait for the next head;  [16..19] covariance warp: same with centroid + eigen-solve;
- * [20..23], [28] one owner lane: apply + local argmin, wait at the CTA barrier, head, scan + publish, wait for results;  [24] wrong colour guesses, [25] CIEDE evaluations, [26] merges touching > 32 edges,
- * [27] touched edges in total. */
+ * Resident kernel (kernel choice 4, or 5 for the variant with its tables in L2), worker thread 0: [0..6] rescan + publish, wait at
+ * S1 + head, adjacency entries + marks, dedupe + speculative colour deltas, wait for the fold, weights + stamps + keys, wait at W4;
+ * [7] cycles inside merges with more than 928 adjacency entries (choice 5), [20..23] their four looped phases (entries + marks +
+ * guess, dedupe + colour + wait for the fold, weights + classes + list, stamps + keys + clear);  [8..10] / [28..30] cycles / merges by
+ * adjacency entries (<= 32, <= 128, more), [11] / [31] the same for merges with more than 928;  [12..15] colour-mean warp: wait for the
+ * voxels, fold, Lab + publish, wait for the next head;  [16..19] covariance warp: same with centroid + eigen-solve;  [24] wrong colour
+ * guesses, [25] colour-distance evaluations, [27] adjacency entries in total.  f3ps/binding.py merge_profile() names them. */
 int f3ps_merge_profile(f3ps_ctx* ctx, uint64_t cycles[32]);
 /* nanoseconds the expansion kernel spent per phase: init, sweeps, count, scan, fill, centroid fold, tail, (spare) */
 int f3ps_expand_profile(f3ps_ctx* ctx, uint64_t ns[8]);
