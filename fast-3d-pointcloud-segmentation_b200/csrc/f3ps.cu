@@ -819,6 +819,10 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
         const bool big_ok = !single_ok && P > 0 && S < 65535u && E_big <= (1u << 20) && ctx->merge_kernel_choice != 1 &&
                             FastSmem(nullptr, S_cap, E_big, (char*)16).bytes <= 227u * 1024u;
         bool fast = !ctx->force_general_merge && (single_ok || big_ok);
+        // a graph that fits an SM but has a merge with more adjacency entries than worker threads continues on the L2 variant (which
+        // loops over the entries) instead of handing single merges to the general kernel
+        const bool can_switch = single_ok && P > 0 && ctx->merge_kernel_choice != 1 && FastSmem(nullptr, S_cap, E_big, (char*)16).bytes <= 227u * 1024u;
+        bool use_big = !single_ok;
         // general kernel (any graph); resume: continue from the state the resident kernel left; stop_after: hand back after that many merges
         auto launch_general = [&](bool resume, unsigned stop_after) -> int {
             const size_t per = ((size_t)Ec * 4 + 255) & ~(size_t)255, per8 = ((size_t)Ec * 8 + 255) & ~(size_t)255;
@@ -853,20 +857,20 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
             A.threshold = threshold; A.run_start = ctx->run_start.as<unsigned>(); A.run_end = ctx->run_end.as<unsigned>();
             A.pos_data = ctx->pos_data; A.sv_label = ctx->sv_label.as<unsigned>(); A.mlog = ctx->ML; A.log_cap = (unsigned)Sc;
             A.ctl = SC(mctl); A.S_cap = S_cap;
-            A.E_cap = single_ok ? E_cap : E_big;
+            A.E_cap = !use_big ? E_cap : E_big;
             A.big = nullptr; A.big_cursor = nullptr; A.resume = resume ? 1 : 0;
-            void (*kern)(FastArgs) = single_ok ? lean_kernel_for(ctx->merge_kernel_choice == 4) : (ctx->merge_kernel_choice == 5 ? merge_fast_big_kernel<true> : merge_fast_big_kernel<false>);
+            void (*kern)(FastArgs) = !use_big ? lean_kernel_for(ctx->merge_kernel_choice == 4) : (ctx->merge_kernel_choice == 5 ? merge_fast_big_kernel<true> : merge_fast_big_kernel<false>);
             size_t launch_bytes = fast_bytes;
-            if (!single_ok) {
+            if (use_big) {
                 const size_t bb = (FastSmem::big_bytes(S_cap, E_big) + 255) & ~(size_t)255;
                 F3PS_CUDA_OK(ctx->lean_big.ensure(bb + lean_cursor_bytes(S_cap) + LeanWideScratch::bytes));
                 A.big = (char*)ctx->lean_big.p; A.big_cursor = (unsigned*)((char*)ctx->lean_big.p + bb);
                 launch_bytes = FastSmem(nullptr, S_cap, E_big, A.big).bytes;
             }
             int r = lean_attr(ctx, (const void*)kern); if (r) return r;
-            r = lean_pool(ctx, E, A, !single_ok); if (r) return r;
+            r = lean_pool(ctx, E, A, use_big); if (r) return r;
             A.trace = nullptr; A.trace_first = ctx->merge_trace_first;
-            if (ctx->merge_kernel_choice == 4 && single_ok && !resume) {
+            if (ctx->merge_kernel_choice == 4 && !use_big && !resume) {
                 F3PS_CUDA_OK(ctx->merge_trace.ensure(256 * 32 * 4));
                 F3PS_CUDA_OK(cudaMemsetAsync(ctx->merge_trace.p, 0, 256 * 32 * 4, ctx->stream));
                 A.trace = ctx->merge_trace.as<unsigned>();
@@ -895,6 +899,7 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
                 if (err == 0) break;
                 if (err == kFastErrTouched) {
                     F3PS_CUDA_OK(cudaMemsetAsync(SC(mctl.error), 0, 4, ctx->stream));
+                    if (!use_big && can_switch) { use_big = true; resume = true; ctx->merge_path = 6; continue; }   // same state, tables in L2 from here on
                     ctx->merge_path = single_ok ? 4 : 5;
                     rc = launch_general(true, hand < kHandOvers ? 1u : 0u); if (rc) return rc;
                     if (hand >= kHandOvers) break;

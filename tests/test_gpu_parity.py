@@ -471,8 +471,9 @@ def test_general_merge_kernel_hub_graph(gpu, oracle_mod, n_leaves, mode):
     c = g.counts()
     # (2: general kernel from the start; 4 / 5: the resident kernel up to the first merge that touches more edges than it has worker
     # threads, then the general kernel continues from its state -- the hand-over is part of what this test pins against the oracle)
-    # -- or 3: the graph does not fit an SM, the resident kernel with its tables in L2 loops over the entries of such merges itself)
-    assert c.merge_path in (2, 3, 4, 5) and c.max_touched > 1024 and c.n_merges > 100, (c.merge_path, c.max_touched, c.n_merges)
+    # -- or 3: the graph does not fit an SM, the resident kernel with its tables in L2 loops over the entries of such merges itself;
+    # 6: the shared-memory kernel up to the first such merge, then the L2 variant from that state)
+    assert c.merge_path in (2, 3, 4, 5, 6) and c.max_touched > 1024 and c.n_merges > 100, (c.merge_path, c.max_touched, c.n_merges)
     first = (c.merge_path, g.array("merges_ab").copy(), g.array("final_ab").copy(), g.array("final_w").copy(), g.array("merges_w").copy())
     g.set_merge_kernel(2); g.merge(thr)                  # the general kernel alone replays the same sequence
     assert g.counts().merge_path == 2 and np.array_equal(g.array("merges_ab"), first[1]) and np.array_equal(g.array("final_ab"), first[2])
@@ -487,6 +488,13 @@ def test_general_merge_kernel_hub_graph(gpu, oracle_mod, n_leaves, mode):
     assert np.array_equal(g.array("merges_ab"), o.array("merges_ab"))
     assert same(g.array("merges_w"), o.array("merges_w"))
     assert np.array_equal(g.array("out_label"), o.array("out_label"))
+    if S <= 4096:
+        # one grid for many frames (f3ps_merge_batch): this frame's CTA stops in front of its first wide merge and the handle
+        # continues from that state on the L2 variant
+        gpu.merge_batch([g], thr)
+        assert g.counts().merge_path == 6, g.counts().merge_path
+        assert np.array_equal(g.array("merges_ab"), o.array("merges_ab")) and same(g.array("merges_w"), o.array("merges_w"))
+        assert np.array_equal(g.array("out_label"), o.array("out_label"))
 
 
 def test_merge_batch_equals_individual_merges(gpu):
