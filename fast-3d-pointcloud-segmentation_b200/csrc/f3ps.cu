@@ -753,11 +753,16 @@ int f3ps_set_graph(f3ps_ctx* ctx, int64_t n_voxels, const float* voxel_xyz, cons
 extern "C++" {
 namespace {
 // edge capacity of the resident kernel's tables: E rounded up to whole blocks of 32 edges (0 = more than 32 blocks per worker warp)
-unsigned lean_ecap_for(unsigned E) {
-    const unsigned nb = std::max(1u, (E + (unsigned)kFastOwners - 1u) / (unsigned)kFastOwners);
+unsigned lean_ecap_for(unsigned E, int threads = kFastThreads) {
+    const unsigned owners = (unsigned)(threads - 32 * kLeanRoleWarps);
+    const unsigned nb = std::max(1u, (E + owners - 1u) / owners);
     return nb <= 32u ? std::max(32u, (E + 31u) & ~31u) : 0u;
 }
-void (*lean_kernel_for(bool prof))(FastArgs) { return prof ? merge_fast_kernel<true> : merge_fast_kernel<false>; }
+// one frame alone runs the 768-thread build (80 registers) when its edges fit 21 worker warps
+void (*lean_kernel_for(bool prof, bool solo))(FastArgs) {
+    if (solo) return prof ? merge_fast_kernel<true, kFastThreadsSolo> : merge_fast_kernel<false, kFastThreadsSolo>;
+    return prof ? merge_fast_kernel<true, kFastThreads> : merge_fast_kernel<false, kFastThreads>;
+}
 // adjacency pool of the resident kernel (edge ids, 2 bytes each): the initial lists plus room for the lists that outgrow their block
 constexpr size_t kLeanPoolSlack = 1u << 20;
 int lean_pool(f3ps_ctx* ctx, unsigned E, FastArgs& A, bool big = false) {      // (edge ids: 2 bytes, BIG variant 4)
@@ -859,7 +864,8 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
             A.ctl = SC(mctl); A.S_cap = S_cap;
             A.E_cap = !use_big ? E_cap : E_big;
             A.big = nullptr; A.big_cursor = nullptr; A.resume = resume ? 1 : 0;
-            void (*kern)(FastArgs) = !use_big ? lean_kernel_for(ctx->merge_kernel_choice == 4) : (ctx->merge_kernel_choice == 5 ? merge_fast_big_kernel<true> : merge_fast_big_kernel<false>);
+            const bool solo = !use_big && lean_ecap_for(E, kFastThreadsSolo) != 0u && can_switch;      // (a wider merge than 672 entries continues on the L2 variant)
+            void (*kern)(FastArgs) = !use_big ? lean_kernel_for(ctx->merge_kernel_choice == 4, solo) : (ctx->merge_kernel_choice == 5 ? merge_fast_big_kernel<true> : merge_fast_big_kernel<false>);
             size_t launch_bytes = fast_bytes;
             if (use_big) {
                 const size_t bb = (FastSmem::big_bytes(S_cap, E_big) + 255) & ~(size_t)255;
@@ -875,7 +881,7 @@ int f3ps_merge(f3ps_ctx* ctx, float threshold) {
                 F3PS_CUDA_OK(cudaMemsetAsync(ctx->merge_trace.p, 0, 256 * 32 * 4, ctx->stream));
                 A.trace = ctx->merge_trace.as<unsigned>();
             }
-            kern<<<1, kFastThreads, launch_bytes, ctx->stream>>>(A);
+            kern<<<1, solo ? kFastThreadsSolo : kFastThreads, launch_bytes, ctx->stream>>>(A);
             ctx->launches++;
             F3PS_CUDA_OK(cudaPeekAtLastError());
             return F3PS_OK;

@@ -303,9 +303,9 @@ enum { FC_KEEP = 0, FC_FRONT = 1, FC_BACK = 2, FC_DUP = 3 };
 enum { BAR_W1 = 1, BAR_WB = 2, BAR_F = 3, BAR_W4 = 4, BAR_G = 5, BAR_FN = 6, BAR_GN = 7 };
 // A merge whose two adjacency lists hold <= 32 entries is NARROW: one worker warp handles it, the other 28 sleep until W4, and
 // the G / F barriers shrink to the warps involved (G: mean warp + worker warp 0; F: the three role warps + worker warp 0).
-template <bool BIG>
+template <bool BIG, int NT>
 __device__ __forceinline__ bool lean_too_wide(const FastSmem& sm, unsigned a, unsigned b) {
-    return (unsigned)sm.adj_len[a] + (unsigned)sm.adj_len[b] > (unsigned)(BIG ? kLeanWideMax : kLeanMaxTouched);
+    return (unsigned)sm.adj_len[a] + (unsigned)sm.adj_len[b] > (unsigned)(BIG ? kLeanWideMax : NT - 32 * kLeanRoleWarps);
 }
 __device__ __forceinline__ bool lean_wide(const FastSmem& sm, unsigned a, unsigned b) { return (unsigned)sm.adj_len[a] + (unsigned)sm.adj_len[b] > 32u; }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -496,8 +496,16 @@ __device__ __forceinline__ void lean_wide_merge(const FastArgs& A, float lambda,
 #define LTRACE(cond, slot, val) do { if (PROF && (cond) && A.trace && (nm - A.trace_first) < 256u) A.trace[(nm - A.trace_first) * 32u + (slot)] = (val); } while (0)
 #define LPROF_STORE(cond, base, n) do { if (PROF && (cond)) for (int i_ = 0; i_ < (n); ++i_) A.ctl->phase_cycles[(base) + i_] = pc[i_]; } while (0)
 
-template <bool PROF, bool BIG = false>
+// NT = threads of the CTA: 1024 (29 worker warps, merges of up to 928 adjacency entries: what a grid of many frames runs, and the L2
+// variant) or 768 (21 worker warps, 672 entries, 80 registers per thread instead of 64: a third of the spills and smaller
+// barriers -- a VGA frame alone replays 11 % faster on it; a frame with a wider merge continues on the L2 variant, merge path 6).
+template <bool PROF, bool BIG = false, int NT = 1024>
 __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
+    static_assert(!BIG || NT == 1024, "the L2 variant (lean_wide_merge) is written for 1024 threads");
+    constexpr int kFastThreads = NT;                                    // (these shadow the namespace-scope constants of the 1024-thread layout)
+    constexpr int kFastOwners = NT - 32 * kLeanRoleWarps;
+    constexpr int kLeanWorkerWarps = kFastOwners / 32;
+    constexpr int kLeanMaxTouched = kFastOwners;
     extern __shared__ __align__(128) char smem_raw[];
     const FastSmem sm(smem_raw, A.S_cap, A.E_cap, BIG ? A.big : nullptr);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -521,7 +529,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
         sm.head[s] = (unsigned short)(h < 0 ? kNil16 : (unsigned)h); sm.tail[s] = (unsigned short)(t < 0 ? kNil16 : (unsigned)t);
         sm.next[s] = (unsigned short)(nx < 0 ? kNil16 : (unsigned)nx); sm.mark[s] = (unsigned short)kNil16; sm.adj_start[s] = 0u;
     }
-    if (tid < 32) sm.bdirty[tid] = 1u;
+    if (tid < 32) { sm.bdirty[tid] = 1u; sm.wm_key[tid] = kDeadKey64; }      // (lean_head reads 29 partial minima whatever NT is)
     if constexpr (BIG) for (unsigned i = tid; i < (nblk + 31u) / 32u; i += kFastThreads) sm.blkdirty[i] = 0xffffffffu;
     for (int i = tid; i < kLeanMaxTouched; i += kFastThreads) sm.partner[i] = (unsigned short)kNil16;
     for (int i = tid; i < kLeanHash; i += kFastThreads) { sm.hkey[i] = kDeadKey; sm.hcnt[i] = 0u; }
@@ -601,7 +609,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             LPROF(lane == 0, 3);
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
-            if (lean_too_wide<BIG>(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
+            if (lean_too_wide<BIG, NT>(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
             const int na = sm.n[a], nb = sm.n[b];
             const bool wide = lean_wide(sm, a, b);
             LTRACE(lane == 0, 12, (unsigned)clock()); LTRACE(lane == 0, 21, (unsigned)nb);
@@ -678,7 +686,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             LPROF(lane == 0, 3);
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
-            if (lean_too_wide<BIG>(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
+            if (lean_too_wide<BIG, NT>(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
             const int na = sm.n[a], nb = sm.n[b];
             const bool wide = lean_wide(sm, a, b);
             LTRACE(lane == 0, 16, (unsigned)clock());
@@ -762,7 +770,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             const FastHead hd = lean_head(sm, lane);
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
-            if (lean_too_wide<BIG>(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
+            if (lean_too_wide<BIG, NT>(sm, a, b)) break;               // more touched edges than worker threads: stop BEFORE this merge (the host continues with the general kernel)
             const int na = sm.n[a], nb = sm.n[b];
             const bool wide = lean_wide(sm, a, b);
             if (nb > kLeanSlotVox) {                       // (the fold warps fetch a small region themselves, lean_fetch_small)
@@ -876,7 +884,7 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
             if (my_hs != kNil16) { sm.hkey[my_hs] = kDeadKey; sm.hcnt[my_hs] = 0u; my_hs = kNil16; }
             if (sm.misc[FM_ERROR] || hd.hi == kDeadKey || !(__uint_as_float(hd.hi) < A.threshold)) break;   // strict <, src/clustering.cpp:388-389
             const unsigned a = hd.ab >> 16, b = hd.ab & 0xffffu;
-            if (lean_too_wide<BIG>(sm, a, b)) { if (wtid == 0) sm.misc[FM_ERROR] = (int)kFastErrTouched; break; }   // nothing of this merge has happened yet
+            if (lean_too_wide<BIG, NT>(sm, a, b)) { if (wtid == 0) sm.misc[FM_ERROR] = (int)kFastErrTouched; break; }   // nothing of this merge has happened yet
             const int counter = sm.misc[FM_COUNTER];
             const unsigned pool_top = (unsigned)sm.misc[FM_POOL];
             WPROF(1);
@@ -1106,8 +1114,9 @@ __device__ __forceinline__ void merge_lean_body(const FastArgs& A) {
 }
 
 // one frame: one CTA
-template <bool PROF>
-__global__ void __launch_bounds__(kFastThreads, 1) merge_fast_kernel(const __grid_constant__ FastArgs A) { merge_lean_body<PROF>(A); }
+template <bool PROF, int NT>
+__global__ void __launch_bounds__(NT, 1) merge_fast_kernel(const __grid_constant__ FastArgs A) { merge_lean_body<PROF, false, NT>(A); }
+constexpr int kFastThreadsSolo = 768;                // one frame alone (f3ps_merge); grids of frames keep 1024
 
 // graphs too large for an SM's shared memory (C5-size scenes): the same loop with the big tables in global memory
 template <bool PROF>
