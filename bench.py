@@ -52,7 +52,7 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-TRAFFIC_FILE = os.path.join("profiles", "r02_traffic.json")
+TRAFFIC_FILE = os.path.join("profiles", "r02c_traffic.json")
 
 
 def load_traffic():
