@@ -314,7 +314,8 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile(
 // code in merge_lean_body -- C (entries, duplicates through the region marks), colour deltas against the guess, D (geometry,
 // weight, class, tie groups, a's new list), E (tie stamps, new keys) -- with every worker thread looping over the entries
 // i, i + 928, ... and the per-entry state parked in LeanWideScratch between the barriers.  Same barrier protocol as a wide
-// merge of the main loop (WB1, G, F, WB2; the caller arrives at W4).  Off the hot path of a VGA frame: never inlined.
+// merge of the main loop (WB1, G, F, WB2; the caller arrives at W4).  Only the L2 variant instantiates it (a cold branch of its worker loop;
+// inlined: as a separate function the call pinned the caller's table pointers to the stack).
 template <bool PROF>
 __device__ __forceinline__ void lean_wide_merge(const FastArgs& A, float lambda, unsigned head_e, unsigned a, unsigned b, int counter, unsigned pool_top, int wtid) {
     extern __shared__ __align__(128) char smem_raw[];
