@@ -23,7 +23,7 @@ struct Fail : std::runtime_error { int code; Fail(int c, const std::string& m) :
 void cu(cudaError_t e, const char* what) { if (e != cudaSuccess) throw Fail(F3PS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); }
 void nc(ncclResult_t r, const char* what) { if (r != ncclSuccess) throw Fail(F3PS_ERR_CUDA, std::string(what) + ": " + ncclGetErrorString(r)); }
 
-struct DevMem {                                    // cudaMalloc'ed scratch of one rank
+struct DevMem {                                    // cudaMalloc'ed buffer of one rank (grows, never shrinks)
     void* p = nullptr; size_t cap = 0;
     ~DevMem() { if (p) cudaFree(p); }
     void* ensure(size_t bytes) {
@@ -31,6 +31,7 @@ struct DevMem {                                    // cudaMalloc'ed scratch of o
         return p;
     }
 };
+struct RankMem { int device = 0; DevMem small, send, recv, fx, fr, fk; };   // exchange buffers of one rank, reused by every run
 }  // namespace
 
 std::vector<uint64_t> choose_splitters(const std::vector<uint32_t>& hist, int world, int shift) {
@@ -75,6 +76,8 @@ SlabRun::SlabRun(const std::vector<int>& devices) : devices_(devices) {
             stream_[r] = s;
             const int rc = f3ps_create(devices_[r], s, &ctx_[r]);
             if (rc) throw Fail(rc, "f3ps_create failed on device " + std::to_string(devices_[r]));
+            const int dev = devices_[r];
+            mem_.push_back(std::shared_ptr<void>(new RankMem{dev}, [](void* p) { RankMem* m = (RankMem*)p; cudaSetDevice(m->device); delete m; }));
         }
     } catch (const Fail& f) { init_error_ = f.what(); }
 }
@@ -130,7 +133,8 @@ void SlabRun::rank_main(int rank, const SlabShare& share, const SlabParams& p) {
             nc(ncclGroupEnd(), "ncclGroupEnd");
         };
         auto slab_array = [&](int which, void*& ptr, int64_t& n, int& eb) { ok(f3ps_slab_array(ctx, which, &ptr, &n, &eb), "f3ps_slab_array"); };
-        DevMem small, send, recv, fx, fr, fk;
+        RankMem& M = *(RankMem*)mem_[(size_t)rank].get();
+        DevMem &small = M.small, &send = M.send, &recv = M.recv, &fx = M.fx, &fr = M.fr, &fk = M.fk;
 
         ok(f3ps_set_vccs_params(ctx, p.voxel_res, p.seed_res, p.color_imp, p.spatial_imp, p.normal_imp, p.use_transform, p.fold_negative_z), "f3ps_set_vccs_params");
         ok(f3ps_set_merge_params(ctx, p.color_distance, p.geometric_distance, p.merging, p.lambda, p.bins), "f3ps_set_merge_params");
@@ -138,7 +142,7 @@ void SlabRun::rank_main(int rank, const SlabShare& share, const SlabParams& p) {
         ok(f3ps_slab_reset(ctx), "f3ps_slab_reset");
         const int64_t n_local = share.n;
         info.n_local = n_local;
-        ok(f3ps_set_input(ctx, share.points, n_local, share.stride, 0), "f3ps_set_input");
+        ok(f3ps_set_input(ctx, share.points, n_local, share.stride, share.on_device ? 1 : 0), "f3ps_set_input");
         // ---- K1a: the frame of the whole cloud (order-preserving encoded box: MIN of 3 words, MAX of 4) ----
         uint32_t* d_small = (uint32_t*)small.ensure(((size_t)8 + ((size_t)1 << kTopBits) + 4) * 4 + (size_t)world * (size_t)world * 8 + 64);
         uint32_t* d_box = d_small;

@@ -8,6 +8,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -26,7 +27,8 @@ struct SlabParams {
     int shard_expand = -1;            // K5: -1 = by size (sharded sweeps with a per-sweep exchange only for tables >= 4 M voxels), 0 / 1 force it
 };
 
-struct SlabShare { const void* points = nullptr; int64_t n = 0; int stride = 32; };   // one rank's share of the cloud, host memory
+// one rank's share of the cloud: host memory, or (on_device) memory of that rank's GPU -- the scans it recorded, already in HBM
+struct SlabShare { const void* points = nullptr; int64_t n = 0; int stride = 32; bool on_device = false; };
 
 struct SlabInfo {                     // per rank, after run()
     int64_t n_local = 0, n_received = 0, v_local = 0, V = 0, own_lo = 0, own_hi = 0;
@@ -58,6 +60,7 @@ private:
     std::vector<f3ps_ctx*> ctx_;
     std::vector<void*> stream_;       // cudaStream_t
     std::vector<void*> comm_;         // ncclComm_t
+    std::vector<std::shared_ptr<void>> mem_;   // per rank: the exchange buffers, kept from run to run
     std::vector<SlabInfo> info_;
     std::vector<int> status_;
     std::string init_error_;

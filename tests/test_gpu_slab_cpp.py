@@ -30,8 +30,8 @@ def selftest():
 def test_cpp_nccl_slab_mode_equals_one_handle(selftest, shard):
     import torch
     gpus = min(2, torch.cuda.device_count())
-    out = subprocess.run([selftest, "--gpus", str(gpus), "--points", "400000", "--shard-expand", str(shard)],
-                         capture_output=True, text=True, timeout=600)
+    out = subprocess.run([selftest, "--gpus", str(gpus), "--points", "400000", "--shard-expand", str(shard), "--device-shares", str(shard)],
+                         capture_output=True, text=True, timeout=600)   # (sharded sweeps from device-resident shares, the replicated expansion from host memory)
     assert out.returncode == 0, out.stdout + out.stderr
     rec = json.loads(out.stdout.strip().splitlines()[-1])
     assert rec["identical_to_one_handle"] is True and rec["gpus"] == gpus
