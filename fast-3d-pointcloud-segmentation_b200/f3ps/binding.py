@@ -414,6 +414,25 @@ class Segmenter:
                 best_t, best = t, res[t]
         return best_t, best
 
+    def eval_clouds(self, seg_xyz, seg_label, truth_xyz, truth_label):
+        """Testing(segm, truth).eval_performance() (/root/reference/src/testing.cpp:62-146, 239-406) for one pair of labelled clouds:
+        the host pairs the points by exact xyz (compareXYZ: -0 == +0; the first truth point of an xyz wins, as std::map::insert) and
+        renumbers the labels densely in ascending order -- what host/facade.cpp's Testing does --, the contingency table and the seven
+        scores come from f3ps_eval_label_pairs on the device."""
+        sx = np.ascontiguousarray(seg_xyz, np.float32) + np.float32(0); tx = np.ascontiguousarray(truth_xyz, np.float32) + np.float32(0)   # -0 -> +0
+        su, sd = np.unique(np.asarray(seg_label, np.uint32), return_inverse=True)
+        tu, td = np.unique(np.asarray(truth_label, np.uint32), return_inverse=True)
+        where = {}
+        for k, j in zip(map(bytes, tx.view(np.uint8).reshape(len(tx), 12)), td):
+            where.setdefault(k, int(j))
+        nt = len(tu)
+        tl = np.array([where.get(k, nt) for k in map(bytes, sx.view(np.uint8).reshape(len(sx), 12))], np.uint32)
+        sl = np.ascontiguousarray(sd, np.uint32)
+        tsizes = np.bincount(td, minlength=nt).astype(np.uint64)
+        perf = np.zeros(7, np.float32)
+        self._chk(self.L.f3ps_eval_label_pairs(self.h, _p(sl), _p(tl), len(sl), len(su), nt, _p(tsizes), len(tx), _p(perf)))
+        return dict(zip(self.PERF_FIELDS, map(float, perf)))
+
     # ---- slab mode (per-rank pieces; f3ps/slab.py issues the exchanges between them) ----
     SLAB_ARRAYS = {"vox_xyz": 0, "vox_rgb": 1, "vox_key": 2, "vox_normal": 3, "vox_curv": 4, "steal": 5, "owner_next": 6,
                    "dist": 7, "count": 8}

@@ -3,8 +3,10 @@ f3ps_eval_thresholds.  Literal: Testing::label_map / compute_intersections / eva
 175-219, 239-362) on two labelled point clouds, with the intersections by exact xyz (count_intersect's sort +
 set_intersection), float32 arithmetic in the reference's order, and Clustering::all_thresh / best_thresh
 (/root/reference/src/clustering.cpp:691-774) driven by re-running the oracle's cluster() per threshold.
-The reference has no fixture for this module: parity of the scores is pinned by hand-computed cases in
-tests/test_oracle_testing.py only."""
+Pinned by the reference's OWN Testing class: /root/reference/src/testing.cpp compiles where it lies against the container stand-ins
+of oracle/ref_shim/ (oracle/Makefile `ref`); its scores on 38 labelled cloud pairs are committed as tests/golden/testing_ref.json
+(tools/gen_testing_golden.py) and tests/test_oracle_testing.py compares this module with them (and with the compiled class live where
+the reference tree exists), next to hand-computed cases."""
 import numpy as np
 
 F = np.float32

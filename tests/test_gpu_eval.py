@@ -74,3 +74,18 @@ def test_eval_errors(gpu, small_frame):
         g.all_thresh(np.zeros(10, np.uint32))                   # one label per voxel
     with pytest.raises(IndexError):
         g.all_thresh(np.zeros(g.counts().n_voxels, np.uint32), 0.8, 1.5, 0.005)     # std::out_of_range (:694-698)
+
+
+def test_eval_label_pairs_equals_reference_testing_class_golden(gpu):
+    """f3ps_eval_label_pairs (what host/facade.cpp's Testing calls) against the scores of the REFERENCE's own Testing class on the
+    committed cloud pairs (tests/golden/testing_ref.json <- /root/reference/src/testing.cpp compiled against oracle/ref_shim,
+    tools/gen_testing_golden.py): float32 sums of ratios and logs, 1e-5 absolute (device logf vs libm)."""
+    import json
+    import os
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "testing_ref.json")))
+    g = gpu.Segmenter()
+    for k, c in enumerate(d["cases"]):
+        want = [float.fromhex(h) for h in c["scores_f32_hex"]]
+        got = g.eval_clouds(np.array(c["seg_xyz"], np.float32), c["seg_label"], np.array(c["truth_xyz"], np.float32), c["truth_label"])
+        for n, w in zip(d["order"], want):
+            assert abs(got[n] - w) < 1e-5, (k, n, got[n], w)

@@ -1,10 +1,69 @@
-"""The evaluation restatement (oracle/oracle_testing.py) against hand-computed cases of the reference's formulas
-(src/testing.cpp:239-362).  The reference ships no fixture for this module."""
+"""The evaluation restatement (oracle/oracle_testing.py) against (i) hand-computed cases of the reference's formulas
+(src/testing.cpp:239-362) and (ii) the REFERENCE's own Testing class: /root/reference/src/testing.cpp compiles where it lies against
+the container stand-ins of oracle/ref_shim/ (oracle/Makefile `ref` -> oracle/_ref/libref_testing.so); tools/gen_testing_golden.py ran
+it on 38 random / adversarial labelled cloud pairs and committed inputs and scores as tests/golden/testing_ref.json."""
+import ctypes as C
+import json
 import math
+import os
+import subprocess
 
 import numpy as np
+import pytest
 
 import oracle_testing as ot
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORDER = ("voi", "precision", "recall", "fscore", "wov", "fpr", "fnr")
+
+
+def _check(got, want):
+    """the scores are float32 sums in the reference's order: bit-identical except where libm's logf and numpy's log differ by an ulp"""
+    g = np.array([got[n] for n in ORDER], np.float32)
+    for n, a, b in zip(ORDER, g, want):
+        if n in ("voi",):
+            assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (n, a, b)
+        else:
+            assert a == b or abs(a - b) <= 2e-7 * max(1.0, abs(b)), (n, a, b)
+
+
+def test_restatement_equals_reference_testing_class_golden():
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", "testing_ref.json")))
+    assert list(d["order"]) == list(ORDER) and len(d["cases"]) >= 38
+    exact = 0
+    for c in d["cases"]:
+        want = np.array([float.fromhex(h) for h in c["scores_f32_hex"]], np.float32)
+        got = ot.scores(np.array(c["seg_xyz"], np.float32), np.array(c["seg_label"], np.uint32),
+                        np.array(c["truth_xyz"], np.float32), np.array(c["truth_label"], np.uint32))
+        _check(got, want)
+        exact += int(np.array_equal(np.array([got[n] for n in ORDER], np.float32), want))
+    assert exact >= len(d["cases"]) - 4                          # (36 of 38 bit-identical when the fixture was made)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/testing.cpp"), reason="the reference tree exists in the build container only")
+def test_restatement_equals_reference_testing_class_live():
+    """fresh random clouds through the compiled reference class (not only the committed ones)"""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "ref"])
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_testing.so"))
+    lib.ref_testing_eval.restype = C.c_int
+    lib.ref_testing_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    rng = np.random.default_rng(99)
+    for trial in range(25):
+        n = int(rng.integers(1, 400))
+        idx = rng.choice(20 ** 3, n, replace=False)
+        xyz = np.stack([idx % 20, (idx // 20) % 20, idx // 400], 1).astype(np.float32) - 7
+        sl = rng.integers(0, int(rng.integers(1, 9)), n).astype(np.uint32) * 13 + 5
+        tl = rng.integers(0, int(rng.integers(1, 9)), n).astype(np.uint32) * 7 + 2
+        ks = rng.random(n) < 0.9; kt = rng.random(n) < 0.9
+        ks[0] = True; kt[-1] = True
+        sx, tx = np.ascontiguousarray(xyz[ks]), np.ascontiguousarray(xyz[kt])
+        s_l, t_l = np.ascontiguousarray(sl[ks]), np.ascontiguousarray(tl[kt])
+        out = np.zeros(7, np.float32)
+        assert lib.ref_testing_eval(sx.ctypes.data, s_l.ctypes.data, len(s_l), tx.ctypes.data, t_l.ctypes.data, len(t_l), out.ctypes.data) == 0
+        _check(ot.scores(sx, s_l, tx, t_l), out)
+    # an empty cloud: the reference throws std::invalid_argument (src/testing.cpp:420-441)
+    z = np.zeros((0, 3), np.float32); zl = np.zeros(0, np.uint32); one = np.zeros((1, 3), np.float32); ol = np.zeros(1, np.uint32)
+    assert lib.ref_testing_eval(z.ctypes.data, zl.ctypes.data, 0, one.ctypes.data, ol.ctypes.data, 1, np.zeros(7, np.float32).ctypes.data) == 1
 
 
 def _cloud(n):
