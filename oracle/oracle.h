@@ -143,6 +143,7 @@ struct Oracle {
 
 // ---- metric kernels exposed for known-answer tests ----
 void rgb2lab(const int16_t* lut, const float rgb255[3], float lab[3]);     // color_utilities.cpp:151-160 + cv::cvtColor
+void rgb_unit2lab(const int16_t* lut, const float unit[3], float lab[3]);  // cv::cvtColor(COLOR_RGB2Lab) alone, channels in [0, 1]
 float lab_ciede00(const float lab1[3], const float lab2[3]);               // color_utilities.cpp:190-294
 float rgb_eucl(const float rgb1[3], const float rgb2[3]);                  // color_utilities.cpp:304-319
 float normals_diff(const float n1[3], const float c1[3], const float n2[3], const float c2[3]); // clustering.cpp:79-96

@@ -27,9 +27,14 @@ static inline float sum4(float a0, float a1, float a2, float a3) { return (a0 + 
 // point lattice + integer trilinear interpolation (pinned
 // bit-exact against cv2 4.13.0 by tests/test_oracle_color.py).
 void rgb2lab(const int16_t* lut, const float rgb[3], float lab[3]) {
+    const float unit[3] = {rgb[0] / 255, rgb[1] / 255, rgb[2] / 255};   // :153-155
+    rgb_unit2lab(lut, unit, lab);
+}
+// cv::cvtColor(CV_32FC3, COLOR_RGB2Lab) on one pixel with channels in [0, 1] (what color_conversion hands it, :57-60)
+void rgb_unit2lab(const int16_t* lut, const float unit[3], float lab[3]) {
     int c[3];
     for (int k = 0; k < 3; ++k) {
-        float v = rgb[k] / 255;                              // :153-155
+        float v = unit[k];
         v = std::min(std::max(v, 0.0f), 1.0f);
         c[k] = (int)std::nearbyint(v * 16384.0f);            // round-half-even
     }

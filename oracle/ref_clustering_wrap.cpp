@@ -1,0 +1,67 @@
+// ref_clustering_wrap.cpp -- plain-C entry to the REFERENCE's own Clustering class (/root/reference/src/clustering.cpp,
+// clustering_state.cpp, color_utilities.cpp compiled where they lie against oracle/ref_shim/): set_initialstate + cluster(threshold)
+// on caller-supplied supervoxels (what main() does at /root/reference/src/supervoxel_clustering.cpp:408-443), returning the
+// reference's per-merge debug lines (:390-392), the remaining edges, the regions and the labelled cloud.
+// Test infrastructure: built into oracle/_ref/libref_clustering.so by oracle/Makefile when /root/reference exists.
+#include <cstdint>
+#include <exception>
+
+#include "ref_capture.h"
+#include "supervoxel_clustering/clustering.h"
+
+extern "C" int ref_cluster(const int16_t* lab_lut, int32_t n_sv, const uint32_t* labels, const int64_t* vox_off, const float* vox_xyz,
+                           const uint32_t* vox_rgba, const float* centroid_xyz, const float* normal_xyz, int64_t n_adj, const uint32_t* adj_pairs,
+                           int color, int geom, int merging, float lambda, int bins, float threshold,
+                           int64_t cap_merges, uint32_t* m_ab, float* m_w, uint32_t* m_left, int64_t* n_merges,
+                           int64_t cap_edges, uint32_t* f_ab, int64_t* n_edges,
+                           uint32_t* r_label, int32_t* r_size, float* r_centroid, float* r_normal4, int32_t* n_regions,
+                           int64_t cap_points, uint32_t* out_label, float* out_xyz, int64_t* n_points, float* lambda_out) {
+    try {
+        f3ps_ref::lab_lut = lab_lut;
+        ClusteringT segm;
+        for (int32_t s = 0; s < n_sv; ++s) {
+            SupervoxelT::Ptr sv = boost::make_shared<SupervoxelT>();
+            for (int64_t v = vox_off[s]; v < vox_off[s + 1]; ++v) {
+                PointT p; p.x = vox_xyz[3 * v]; p.y = vox_xyz[3 * v + 1]; p.z = vox_xyz[3 * v + 2]; p.rgba = vox_rgba[v];
+                sv->voxels_->push_back(p);
+            }
+            sv->centroid_.x = centroid_xyz[3 * s]; sv->centroid_.y = centroid_xyz[3 * s + 1]; sv->centroid_.z = centroid_xyz[3 * s + 2];
+            sv->normal_.normal_x = normal_xyz[3 * s]; sv->normal_.normal_y = normal_xyz[3 * s + 1]; sv->normal_.normal_z = normal_xyz[3 * s + 2];
+            segm.insert(std::make_pair(labels[s], sv));
+        }
+        AdjacencyMapT adj;
+        for (int64_t k = 0; k < n_adj; ++k) adj.insert(std::make_pair(adj_pairs[2 * k], adj_pairs[2 * k + 1]));
+        Clustering c((ColorDistance)color, (GeometricDistance)geom, (MergingCriterion)merging);
+        if (merging == MANUAL_LAMBDA) c.set_lambda(lambda);
+        if (merging == EQUALIZATION) c.set_bins_num((short)bins);
+        c.set_initialstate(segm, adj);
+        std::vector<f3ps_ref::MergeLine> log;
+        f3ps_ref::sink = &log;
+        c.cluster(threshold);
+        f3ps_ref::sink = nullptr;
+        *n_merges = (int64_t)log.size();
+        for (int64_t m = 0; m < (int64_t)log.size() && m < cap_merges; ++m) {
+            m_ab[2 * m] = log[m].a; m_ab[2 * m + 1] = log[m].b; m_w[m] = log[m].w; m_left[2 * m] = log[m].edges_left; m_left[2 * m + 1] = log[m].regions_left;
+        }
+        const std::pair<ClusteringT, AdjacencyMapT> st = c.get_currentstate();
+        *n_edges = (int64_t)st.second.size();
+        int64_t e = 0;
+        for (auto& kv : st.second) { if (e < cap_edges) { f_ab[2 * e] = kv.first; f_ab[2 * e + 1] = kv.second; } ++e; }
+        *n_regions = (int32_t)st.first.size();
+        int32_t r = 0;
+        for (auto& kv : st.first) {
+            r_label[r] = kv.first; r_size[r] = (int32_t)kv.second->voxels_->size();
+            r_centroid[3 * r] = kv.second->centroid_.x; r_centroid[3 * r + 1] = kv.second->centroid_.y; r_centroid[3 * r + 2] = kv.second->centroid_.z;
+            r_normal4[4 * r] = kv.second->normal_.normal_x; r_normal4[4 * r + 1] = kv.second->normal_.normal_y; r_normal4[4 * r + 2] = kv.second->normal_.normal_z;
+            r_normal4[4 * r + 3] = kv.second->normal_.curvature;
+            ++r;
+        }
+        PointLCloudT::Ptr lc = c.get_labeled_cloud();
+        *n_points = (int64_t)lc->size();
+        for (int64_t i = 0; i < (int64_t)lc->size() && i < cap_points; ++i) {
+            out_label[i] = lc->points[(size_t)i].label; out_xyz[3 * i] = lc->points[(size_t)i].x; out_xyz[3 * i + 1] = lc->points[(size_t)i].y; out_xyz[3 * i + 2] = lc->points[(size_t)i].z;
+        }
+        *lambda_out = c.get_lambda();
+        return 0;
+    } catch (const std::exception&) { f3ps_ref::sink = nullptr; return 1; }
+}

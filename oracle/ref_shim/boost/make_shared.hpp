@@ -1,4 +1,3 @@
-// Stand-in: boost::shared_ptr / make_shared = the std ones (oracle/ref_shim/README.md).  Test infrastructure only.
+// Stand-in: see f3ps_ref_standins.h (oracle/ref_shim/README.md).  Test infrastructure only.
 #pragma once
-#include <memory>
-namespace boost { using std::shared_ptr; using std::make_shared; }
+#include "../f3ps_ref_standins.h"

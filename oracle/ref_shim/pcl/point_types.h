@@ -1,4 +1,3 @@
-// Stand-in for pcl/point_types.h: the one point type src/testing.cpp uses (oracle/ref_shim/README.md).  Test infrastructure only.
+// Stand-in: see f3ps_ref_standins.h (oracle/ref_shim/README.md).  Test infrastructure only.
 #pragma once
-#include <cstdint>
-namespace pcl { struct PointXYZL { float x, y, z; uint32_t label; }; }
+#include "../f3ps_ref_standins.h"

@@ -327,6 +327,34 @@ def test_set_graph_facade_path(gpu, oracle_mod, small_frame):
     assert np.array_equal(g._graph_order[g.array("out_voxel")], o.array("out_voxel"))
 
 
+def _reference_clustering_cases():
+    z = np.load(os.path.join(HERE, "golden", "clustering_ref.npz"))
+    return [str(n) for n in z["case_names"]]
+
+
+@pytest.mark.parametrize("name", _reference_clustering_cases())
+def test_set_graph_equals_reference_clustering_golden(gpu, name):
+    """K6 + K7 on the device against the REFERENCE's own Clustering class: /root/reference/src/clustering.cpp + color_utilities.cpp
+    compiled where they lie against the stand-ins of oracle/ref_shim/ and driven like main() (set_initialstate + cluster(threshold))
+    on hub graphs and on the supervoxels of the 160x120 frame in BASELINE's flag sets; inputs and the reference's per-merge lines
+    committed by tools/gen_clustering_golden.py as tests/golden/clustering_ref.npz.  Merge pairs, edge / region counts and the labelled
+    cloud exact; weights to 1e-6 relative with at most 0.2 % not bit-identical (FP64 libm on the host, CUDA's on the device)."""
+    from test_oracle_reference_clustering import load_case
+    z = np.load(os.path.join(HERE, "golden", "clustering_ref.npz"))
+    graph, flags, thr, want = load_case(z, name)
+    for kernel in (0, 2, 3):                                       # automatic (shared memory), general, tables in L2
+        g = gpu.Segmenter(); g.set_merge_params(**flags)
+        g.set_graph(*graph)
+        g.set_merge_kernel(kernel); g.merge(thr)
+        assert np.array_equal(g.array("merges_ab"), want["merges_ab"]), (name, kernel)
+        assert close_enough(g.array("merges_w"), want["merges_w"]), (name, kernel)
+        assert np.array_equal(g.array("merges_left"), want["merges_left"]), (name, kernel)
+        assert np.array_equal(g.array("out_label"), want["out_label"]), (name, kernel)
+        assert set(map(tuple, g.array("final_ab").tolist())) == set(map(tuple, want["final_ab"].tolist())), (name, kernel)
+        if flags["merge_mode"] == 1:
+            assert abs(g.counts().lambda_ - float(want["lam"])) <= 1e-6 * float(want["lam"]), (name, kernel)
+
+
 def test_error_behaviour_matches_reference(gpu):
     g = gpu.Segmenter()
     with pytest.raises(gpu.LogicError):          # cluster before set_initialstate (src/clustering.cpp:671-673)

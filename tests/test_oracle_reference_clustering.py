@@ -1,0 +1,76 @@
+"""The oracle's K6 / K7 half against the REFERENCE's own Clustering class.
+
+/root/reference/src/clustering.cpp, clustering_state.cpp and color_utilities.cpp compile where they lie against the stand-ins of
+oracle/ref_shim/ (containers, the few Eigen operations, PCL's centroid / plane fit as the oracle restates PCL, cv::cvtColor as the
+cv2-pinned LUT; oracle/ref_shim/README.md) into oracle/_ref/libref_clustering.so.  tools/gen_clustering_golden.py drove it the way
+main() does (set_initialstate + cluster(threshold)) on hub graphs and on the supervoxels of the 160x120 synthetic frame in the flag
+sets BASELINE.json names, and committed inputs and outputs as tests/golden/clustering_ref.npz.  Here the oracle -- the literal
+std::multimap replay AND the stamp-rule variant the GPU kernels implement -- must reproduce the reference's per-merge debug lines
+(a, b, weight bits, edges / regions left), its adaptive lambda, the edges that remain and the labelled cloud, bit for bit.
+The GPU path is compared with the same fixture in tests/test_gpu_parity.py::test_set_graph_equals_reference_clustering_golden."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "clustering_ref.npz")
+
+
+def load_case(z, name):
+    g = str(z[name + "/graph"])
+    off = z[g + "/voxel_offsets"]; order = z[g + "/voxel_order"]
+    lists = [order[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    graph = (z[g + "/vxyz"], z[g + "/vrgba"], z[g + "/labels"], lists, z[g + "/centroids"], z[g + "/normals"], z[g + "/adj"])
+    color, geom, merging, lam, bins = z[name + "/flags"]
+    flags = dict(color_mode=int(color), geom_mode=int(geom), merge_mode=int(merging), lam=float(lam), bins=int(bins))
+    want = {k: z[name + "/" + k] for k in ("merges_ab", "merges_w", "merges_left", "final_ab", "out_label", "out_xyz", "lam", "region_label", "region_size")}
+    return graph, flags, float(z[name + "/threshold"]), want
+
+
+def case_names():
+    return [str(n) for n in np.load(GOLD)["case_names"]]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("name", case_names())
+@pytest.mark.parametrize("impl", [0, 1], ids=["literal_multimap", "stamp_rule"])
+def test_oracle_reproduces_reference_clustering(oracle_mod, name, impl):
+    z = np.load(GOLD)
+    graph, flags, thr, want = load_case(z, name)
+    o = oracle_mod.Oracle(); o.set_merge_params(merge_impl=impl, **flags)
+    o.set_graph(*graph); o.run(7, thr)
+    assert np.array_equal(o.array("merges_ab"), want["merges_ab"])                 # the reference's "[a, b]" per merge
+    assert np.array_equal(bits(o.array("merges_w")), bits(want["merges_w"]))       # "w: %f" -- the float the multimap was keyed with
+    assert np.array_equal(o.array("merges_left"), want["merges_left"])             # "left: %de/%dp"
+    if flags["merge_mode"] == 1:
+        lam = np.float32(dict(zip(oracle_mod.SCALARS, o.array("scalars")))["lambda"])
+        assert bits(lam)[()] == bits(want["lam"])[()]                              # adaptive lambda (clustering.cpp:258-287)
+    got_edges = set(map(tuple, o.array("final_ab").tolist())); ref_edges = set(map(tuple, want["final_ab"].tolist()))
+    assert got_edges == ref_edges                                                   # get_currentstate(): the edges that remain
+    assert np.array_equal(o.array("out_label"), want["out_label"])                 # get_labeled_cloud(): dense labels in region order
+    assert np.array_equal(bits(o.array("out_xyz")), bits(want["out_xyz"]))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/clustering.cpp"), reason="the reference tree exists in the build container only")
+def test_oracle_reproduces_reference_clustering_live(oracle_mod):
+    """fresh hub graphs (other seeds, sizes and flag sets than the committed ones) through the compiled reference class"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_clustering_golden as gen
+    lib = gen.ref_lib()
+    lut = np.fromfile(oracle_mod.LUT_PATH, np.int16)
+    for seed, n_leaves, flags, thr in [(901, 40, (0, 0, 1, 0.5, 500), 0.4), (902, 90, (1, 1, 2, 0.5, 50), 0.7), (903, 120, (0, 1, 0, 0.3, 500), 0.35),
+                                       (904, 25, (1, 0, 0, 0.9, 500), 1.0), (905, 200, (0, 1, 1, 0.5, 500), 0.3)]:
+        graph = gen.hub_graph(n_leaves, seed)
+        want = gen.ref_cluster(lib, lut, *graph, *flags, thr)
+        for impl in (0, 1):
+            o = oracle_mod.Oracle()
+            o.set_merge_params(merge_impl=impl, color_mode=flags[0], geom_mode=flags[1], merge_mode=flags[2], lam=flags[3], bins=flags[4])
+            o.set_graph(*graph); o.run(7, thr)
+            assert np.array_equal(o.array("merges_ab"), want["merges_ab"]), (seed, impl)
+            assert np.array_equal(bits(o.array("merges_w")), bits(want["merges_w"])), (seed, impl)
+            assert np.array_equal(o.array("merges_left"), want["merges_left"]) and np.array_equal(o.array("out_label"), want["out_label"]), (seed, impl)
