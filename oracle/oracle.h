@@ -19,6 +19,14 @@
 //     known-answer vectors (src/color_utilities.cpp:324-460), see tests/.
 //   * RGB->Lab is pinned against cv2 4.13.0 in this image (tools/gen_lab_lut.py,
 //     tests/golden/lab_kat.json); the reference does not pin OpenCV's version.
+//   * The whole back half -- set_initialstate, init_weights, adaptive lambda, CDFs,
+//     mean_color, the multimap merge loop and its order, get_labeled_cloud, and the
+//     evaluation scores -- is pinned by the reference's OWN classes: clustering.cpp,
+//     clustering_state.cpp, color_utilities.cpp and testing.cpp compile where they lie
+//     against the stand-ins of oracle/ref_shim/ (Makefile target `ref` -> oracle/_ref/);
+//     their merge sequences / scores are committed as tests/golden/clustering_ref.npz and
+//     testing_ref.json and this oracle reproduces them bit for bit
+//     (tests/test_oracle_reference_clustering.py, tests/test_oracle_testing.py).
 //   * The VCCS front end (PCL) is **parity unpinned**: PCL is absent from this
 //     image and from /root/reference, the reference has no test or fixture for
 //     it, so every PCL/Eigen detail below is restated from knowledge of PCL
