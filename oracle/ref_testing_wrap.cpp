@@ -1,6 +1,6 @@
 // ref_testing_wrap.cpp -- plain-C entry to the REFERENCE's own Testing class (/root/reference/src/testing.cpp, compiled where it lies
 // against the container stand-ins of oracle/ref_shim/): Testing(segm, truth).eval_performance()
-// (/root/reference/include/supervoxel_clustering/testing.h:77-134).  Test infrastructure: built into oracle/_ref/libref_testing.so by
+// (/root/reference/include/supervoxel_clustering/testing.h:77-134).  Test infrastructure: built into oracle/_ref/libref_clustering.so by
 // oracle/Makefile when /root/reference exists; only tests/ and tools/gen_testing_golden.py load it.
 #include <cstdint>
 #include <exception>

@@ -1,6 +1,6 @@
 """The evaluation restatement (oracle/oracle_testing.py) against (i) hand-computed cases of the reference's formulas
 (src/testing.cpp:239-362) and (ii) the REFERENCE's own Testing class: /root/reference/src/testing.cpp compiles where it lies against
-the container stand-ins of oracle/ref_shim/ (oracle/Makefile `ref` -> oracle/_ref/libref_testing.so); tools/gen_testing_golden.py ran
+the container stand-ins of oracle/ref_shim/ (oracle/Makefile `ref` -> oracle/_ref/libref_clustering.so); tools/gen_testing_golden.py ran
 it on 38 random / adversarial labelled cloud pairs and committed inputs and scores as tests/golden/testing_ref.json."""
 import ctypes as C
 import json
@@ -44,7 +44,7 @@ def test_restatement_equals_reference_testing_class_golden():
 def test_restatement_equals_reference_testing_class_live():
     """fresh random clouds through the compiled reference class (not only the committed ones)"""
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "ref"])
-    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_testing.so"))
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_clustering.so"))
     lib.ref_testing_eval.restype = C.c_int
     lib.ref_testing_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     rng = np.random.default_rng(99)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Golden vectors of the REFERENCE's own Testing class: random labelled cloud pairs through
-oracle/_ref/libref_testing.so -- /root/reference/src/testing.cpp compiled where it lies against the container stand-ins of
+oracle/_ref/libref_clustering.so -- /root/reference/src/testing.cpp compiled where it lies against the container stand-ins of
 oracle/ref_shim/ (oracle/Makefile, target `ref`) -- with inputs and the seven scores committed as tests/golden/testing_ref.json.
 Runs in the build container only (the GPU box has no /root/reference); the tests read the fixture.
 Coordinates are small integers (exact in float32), unique inside a cloud; labels are arbitrary uint32 values."""
@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "oracle", "_ref", "libref_testing.so")
+LIB = os.path.join(ROOT, "oracle", "_ref", "libref_clustering.so")
 OUT = os.path.join(ROOT, "tests", "golden", "testing_ref.json")
 
 
