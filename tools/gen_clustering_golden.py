@@ -4,7 +4,8 @@
 oracle/ref_shim/ (oracle/Makefile, target `ref` -> oracle/_ref/libref_clustering.so), driven as main() drives them
 (set_initialstate + cluster(threshold), /root/reference/src/supervoxel_clustering.cpp:408-443) on
   * hub + ring graphs (a region adjacent to everything, duplicates (a,x)/(b,x), few colours -> ties) in five flag sets, and
-  * the supervoxels of the 160x120 synthetic frame (1,646 supervoxels, 4,635 edges) in the three flag sets BASELINE.json names.
+  * the supervoxels of the 160x120 synthetic frame (1,646 supervoxels, 4,635 edges) in the three flag sets BASELINE.json names, and
+  * the supervoxels of the 640x480 frame of the headline benchmark (2,274 supervoxels, 7,592 edges, --CVX --AL -t 0.2: 2,267 merges).
 Inputs and the reference's outputs -- its per-merge debug lines (a, b, weight bits, edges / regions left), the adaptive lambda, the
 regions that remain and the labelled cloud -- are committed as tests/golden/clustering_ref.npz.  Build container only."""
 import ctypes as C
@@ -78,12 +79,13 @@ def hub_graph(n_leaves, seed):
     return vxyz, vrgba, labels, lists, cen, nrm, np.array(sorted(adj), np.uint32)
 
 
-def frame_graph():
-    """the supervoxels PCL's VCCS would hand to set_initialstate, from the oracle's front half on the 160x120 synthetic frame"""
+def frame_graph(vga=False):
+    """the supervoxels PCL's VCCS would hand to set_initialstate, from the oracle's front half on the 160x120 synthetic frame
+    (vga: on the 640x480 frame bench.py's headline and the exact-merge-sequence test use, seed 20020)"""
     import oracle_py
     from f3ps import synth
     o = oracle_py.Oracle(); o.set_vccs_params(); o.set_merge_params(merge_impl=1, color_mode=0, geom_mode=1, merge_mode=1)
-    o.set_input(synth.make_frame(seed=11, width=160, height=120)); o.run(0, 0.2)
+    o.set_input(synth.make_frame(seed=20020) if vga else synth.make_frame(seed=11, width=160, height=120)); o.run(0, 0.2)
     labels = o.array("sv_label").copy(); vl = o.array("labels")
     lists = [np.nonzero(vl == l)[0] for l in labels]
     return (o.array("voxel_xyz").copy(), o.array("voxel_rgba").copy(), labels, lists, o.array("sv_xyz").copy(), o.array("sv_normal")[:, :3].copy(), o.array("adj").copy())
@@ -98,6 +100,7 @@ CASES = [   # name, graph, flags (color, geom, merging, lambda, bins), threshold
     ("frame_cvx_al", ("frame",), (0, 1, 1, 0.5, 500), 0.2),          # BASELINE configs[1]: --CVX --AL -t 0.2
     ("frame_eq200", ("frame",), (0, 0, 2, 0.5, 200), 0.5),           # configs[2]: --EQ 200 (threshold raised: under equalisation few edges are below 0.2)
     ("frame_rgb_ml", ("frame",), (1, 0, 0, 0.5, 500), 0.2),          # configs[3]: --RGB --ML 0.5
+    ("vga_cvx_al", ("vga",), (0, 1, 1, 0.5, 500), 0.2),              # configs[1] at its own size: the 640x480 frame of the headline, 2,267 merges
 ]
 
 
@@ -109,7 +112,7 @@ def main():
     graphs = {}
     for name, gsel, flags, thr in CASES:
         if gsel not in graphs:
-            graphs[gsel] = hub_graph(gsel[1], gsel[1]) if gsel[0] == "hub" else frame_graph()
+            graphs[gsel] = hub_graph(gsel[1], gsel[1]) if gsel[0] == "hub" else frame_graph(vga=gsel[0] == "vga")
         vxyz, vrgba, labels, lists, cen, nrm, adj = graphs[gsel]
         gname = "_".join(map(str, gsel))
         if gname + "/vxyz" not in out:
