@@ -9,6 +9,59 @@
 #include "ref_capture.h"
 #include "supervoxel_clustering/clustering.h"
 
+namespace {
+ClusteringT build_segments(int32_t n_sv, const uint32_t* labels, const int64_t* vox_off, const float* vox_xyz, const uint32_t* vox_rgba,
+                           const float* centroid_xyz, const float* normal_xyz) {
+    ClusteringT segm;
+    for (int32_t s = 0; s < n_sv; ++s) {
+        SupervoxelT::Ptr sv = boost::make_shared<SupervoxelT>();
+        for (int64_t v = vox_off[s]; v < vox_off[s + 1]; ++v) {
+            PointT p; p.x = vox_xyz[3 * v]; p.y = vox_xyz[3 * v + 1]; p.z = vox_xyz[3 * v + 2]; p.rgba = vox_rgba[v];
+            sv->voxels_->push_back(p);
+        }
+        sv->centroid_.x = centroid_xyz[3 * s]; sv->centroid_.y = centroid_xyz[3 * s + 1]; sv->centroid_.z = centroid_xyz[3 * s + 2];
+        sv->normal_.normal_x = normal_xyz[3 * s]; sv->normal_.normal_y = normal_xyz[3 * s + 1]; sv->normal_.normal_z = normal_xyz[3 * s + 2];
+        segm.insert(std::make_pair(labels[s], sv));
+    }
+    return segm;
+}
+}  // namespace
+
+// Clustering::all_thresh + best_thresh (/root/reference/src/clustering.cpp:691-774) as main() uses them for the automatic threshold
+// (/root/reference/src/supervoxel_clustering.cpp:428-438): truth_label[v] = ground-truth label of voxel v (same order as vox_xyz).
+// out_t[k], out_perf[k][7] = (voi, precision, recall, fscore, wov, fpr, fnr) per threshold in map order; best[8] = threshold + its scores.
+extern "C" int ref_all_thresh(const int16_t* lab_lut, int32_t n_sv, const uint32_t* labels, const int64_t* vox_off, const float* vox_xyz,
+                              const uint32_t* vox_rgba, const float* centroid_xyz, const float* normal_xyz, int64_t n_adj, const uint32_t* adj_pairs,
+                              int color, int geom, int merging, float lambda, int bins, const uint32_t* truth_label,
+                              float start, float end, float step, int32_t cap, float* out_t, float* out_perf, int32_t* n_out, float* best) {
+    try {
+        f3ps_ref::lab_lut = lab_lut;
+        ClusteringT segm = build_segments(n_sv, labels, vox_off, vox_xyz, vox_rgba, centroid_xyz, normal_xyz);
+        AdjacencyMapT adj;
+        for (int64_t k = 0; k < n_adj; ++k) adj.insert(std::make_pair(adj_pairs[2 * k], adj_pairs[2 * k + 1]));
+        PointLCloudT::Ptr truth = boost::make_shared<PointLCloudT>();
+        for (int64_t v = 0; v < vox_off[n_sv]; ++v) { PointLT p; p.x = vox_xyz[3 * v]; p.y = vox_xyz[3 * v + 1]; p.z = vox_xyz[3 * v + 2]; p.label = truth_label[v]; truth->push_back(p); }
+        Clustering c((ColorDistance)color, (GeometricDistance)geom, (MergingCriterion)merging);
+        if (merging == MANUAL_LAMBDA) c.set_lambda(lambda);
+        if (merging == EQUALIZATION) c.set_bins_num((short)bins);
+        c.set_initialstate(segm, adj);
+        const std::map<float, performanceSet> all = c.all_thresh(truth, start, end, step);
+        *n_out = (int32_t)all.size();
+        int32_t k = 0;
+        for (auto& kv : all) {
+            if (k < cap) {
+                out_t[k] = kv.first; const performanceSet& p = kv.second;
+                float* o = out_perf + 7 * k; o[0] = p.voi; o[1] = p.precision; o[2] = p.recall; o[3] = p.fscore; o[4] = p.wov; o[5] = p.fpr; o[6] = p.fnr;
+            }
+            ++k;
+        }
+        const std::pair<float, performanceSet> b = c.best_thresh(all);
+        best[0] = b.first; best[1] = b.second.voi; best[2] = b.second.precision; best[3] = b.second.recall; best[4] = b.second.fscore;
+        best[5] = b.second.wov; best[6] = b.second.fpr; best[7] = b.second.fnr;
+        return 0;
+    } catch (const std::exception&) { return 1; }
+}
+
 extern "C" int ref_cluster(const int16_t* lab_lut, int32_t n_sv, const uint32_t* labels, const int64_t* vox_off, const float* vox_xyz,
                            const uint32_t* vox_rgba, const float* centroid_xyz, const float* normal_xyz, int64_t n_adj, const uint32_t* adj_pairs,
                            int color, int geom, int merging, float lambda, int bins, float threshold,
@@ -18,17 +71,7 @@ extern "C" int ref_cluster(const int16_t* lab_lut, int32_t n_sv, const uint32_t*
                            int64_t cap_points, uint32_t* out_label, float* out_xyz, int64_t* n_points, float* lambda_out) {
     try {
         f3ps_ref::lab_lut = lab_lut;
-        ClusteringT segm;
-        for (int32_t s = 0; s < n_sv; ++s) {
-            SupervoxelT::Ptr sv = boost::make_shared<SupervoxelT>();
-            for (int64_t v = vox_off[s]; v < vox_off[s + 1]; ++v) {
-                PointT p; p.x = vox_xyz[3 * v]; p.y = vox_xyz[3 * v + 1]; p.z = vox_xyz[3 * v + 2]; p.rgba = vox_rgba[v];
-                sv->voxels_->push_back(p);
-            }
-            sv->centroid_.x = centroid_xyz[3 * s]; sv->centroid_.y = centroid_xyz[3 * s + 1]; sv->centroid_.z = centroid_xyz[3 * s + 2];
-            sv->normal_.normal_x = normal_xyz[3 * s]; sv->normal_.normal_y = normal_xyz[3 * s + 1]; sv->normal_.normal_z = normal_xyz[3 * s + 2];
-            segm.insert(std::make_pair(labels[s], sv));
-        }
+        ClusteringT segm = build_segments(n_sv, labels, vox_off, vox_xyz, vox_rgba, centroid_xyz, normal_xyz);
         AdjacencyMapT adj;
         for (int64_t k = 0; k < n_adj; ++k) adj.insert(std::make_pair(adj_pairs[2 * k], adj_pairs[2 * k + 1]));
         Clustering c((ColorDistance)color, (GeometricDistance)geom, (MergingCriterion)merging);

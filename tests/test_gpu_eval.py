@@ -89,3 +89,23 @@ def test_eval_label_pairs_equals_reference_testing_class_golden(gpu):
         got = g.eval_clouds(np.array(c["seg_xyz"], np.float32), c["seg_label"], np.array(c["truth_xyz"], np.float32), c["truth_label"])
         for n, w in zip(d["order"], want):
             assert abs(got[n] - w) < 1e-5, (k, n, got[n], w)
+
+
+@pytest.mark.parametrize("name", ["sweep_hub150_rgb_cvx_ml", "sweep_hub400_lab_cvx_al", "sweep_frame_cvx_al"])
+def test_all_thresh_equals_reference_clustering_golden(gpu, name):
+    """f3ps_eval_thresholds (one merge replay on the device) against Clustering::all_thresh / best_thresh of the REFERENCE's own classes
+    (compiled from /root/reference/src against oracle/ref_shim, tools/gen_clustering_golden.py -> tests/golden/clustering_ref.npz):
+    the same thresholds, every score within 1e-5, the same chosen threshold."""
+    import os
+    from test_oracle_reference_clustering import load_sweep
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "clustering_ref.npz"))
+    graph, flags, (t0, t1, dt), truth, thr, perf, best = load_sweep(z, name)
+    g = gpu.Segmenter(); g.set_merge_params(**flags)
+    g.set_graph(*graph)
+    got = g.all_thresh(truth[g._graph_order], t0, t1, dt)
+    assert np.array_equal(np.array(sorted(got), np.float32), thr)
+    for k, t in enumerate(thr):
+        for j, n in enumerate(gpu.Segmenter.PERF_FIELDS):
+            assert abs(got[float(t)][n] - perf[k, j]) < 1e-5, (name, float(t), n, got[float(t)][n], perf[k, j])
+    bt, bp = g.best_thresh(truth[g._graph_order], t0, t1, dt)
+    assert np.float32(bt) == best[0] and abs(bp["fscore"] - best[4]) < 1e-5

@@ -74,3 +74,48 @@ def test_oracle_reproduces_reference_clustering_live(oracle_mod):
             assert np.array_equal(o.array("merges_ab"), want["merges_ab"]), (seed, impl)
             assert np.array_equal(bits(o.array("merges_w")), bits(want["merges_w"])), (seed, impl)
             assert np.array_equal(o.array("merges_left"), want["merges_left"]) and np.array_equal(o.array("out_label"), want["out_label"]), (seed, impl)
+
+
+def sweep_names():
+    return [str(n) for n in np.load(GOLD)["sweep_names"]]
+
+
+def load_sweep(z, name):
+    g = str(z[name + "/graph"])
+    off = z[g + "/voxel_offsets"]; order = z[g + "/voxel_order"]
+    lists = [order[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    graph = (z[g + "/vxyz"], z[g + "/vrgba"], z[g + "/labels"], lists, z[g + "/centroids"], z[g + "/normals"], z[g + "/adj"])
+    color, geom, merging, lam, bins = z[name + "/flags"]
+    flags = dict(color_mode=int(color), geom_mode=int(geom), merge_mode=int(merging), lam=float(lam), bins=int(bins))
+    return graph, flags, tuple(float(x) for x in z[name + "/range"]), z[name + "/truth"], z[name + "/thresholds"], z[name + "/perf"], z[name + "/best"]
+
+
+ORDER = ("voi", "precision", "recall", "fscore", "wov", "fpr", "fnr")
+
+
+@pytest.mark.parametrize("name", sweep_names())
+def test_oracle_reproduces_reference_all_thresh(oracle_mod, name):
+    """Clustering::all_thresh / best_thresh of the compiled reference (the automatic threshold of main(),
+    /root/reference/src/supervoxel_clustering.cpp:428-438): the thresholds its float loop visits, the seven scores at each, and the
+    chosen threshold.  The reference continues clustering from the previous threshold's state; the oracle restarts per threshold --
+    the same result, now checked against the reference's own code."""
+    import oracle_testing as ot
+    z = np.load(GOLD)
+    graph, flags, (t0, t1, dt), truth, thr, perf, best = load_sweep(z, name)
+    F = np.float32
+    mine = [F(t0)]
+    t = F(F(t0) + F(dt))
+    while t <= F(t1):
+        mine.append(t); t = F(t + F(dt))
+    assert np.array_equal(np.array(mine, np.float32), thr)                          # the float loop of :711-718
+    res = {}
+    for k, t in enumerate(thr):
+        o = oracle_mod.Oracle(); o.set_merge_params(merge_impl=1, **flags); o.set_graph(*graph); o.run(7, float(t))
+        owned = np.concatenate(graph[3])                                             # the ground-truth cloud holds the voxels of the supervoxels
+        got = ot.scores(o.array("out_xyz"), o.array("out_label"), graph[0][owned], truth[owned])
+        res[float(t)] = got
+        for j, n in enumerate(ORDER):
+            tol = 1e-6 if n == "voi" else 2e-7
+            assert abs(got[n] - perf[k, j]) <= tol * max(1.0, abs(perf[k, j])), (name, float(t), n, got[n], perf[k, j])
+    bt, bp = ot.best_thresh(res)
+    assert np.float32(bt) == best[0] and abs(bp["fscore"] - best[4]) <= 2e-7

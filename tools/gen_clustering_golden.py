@@ -7,7 +7,9 @@ oracle/ref_shim/ (oracle/Makefile, target `ref` -> oracle/_ref/libref_clustering
   * the supervoxels of the 160x120 synthetic frame (1,646 supervoxels, 4,635 edges) in the three flag sets BASELINE.json names, and
   * the supervoxels of the 640x480 frame of the headline benchmark (2,274 supervoxels, 7,592 edges, --CVX --AL -t 0.2: 2,267 merges).
 Inputs and the reference's outputs -- its per-merge debug lines (a, b, weight bits, edges / regions left), the adaptive lambda, the
-regions that remain and the labelled cloud -- are committed as tests/golden/clustering_ref.npz.  Build container only."""
+regions that remain and the labelled cloud -- and, for three threshold sweeps, Clustering::all_thresh / best_thresh (the automatic
+threshold of main(), :428-438: every threshold's seven scores and the chosen one) are committed as tests/golden/clustering_ref.npz.
+Build container only."""
 import ctypes as C
 import os
 import subprocess
@@ -53,6 +55,27 @@ def ref_cluster(lib, lut, vxyz, vrgba, labels, lists, cen, nrm, adj, color, geom
                 region_label=r_label[:nr.value].copy(), region_size=r_size[:nr.value].copy(), region_centroid=r_cen[:nr.value].copy(),
                 region_normal4=r_n4[:nr.value].copy(), out_label=o_label[:npnt.value].copy(), out_xyz=o_xyz[:npnt.value].copy(),
                 lam=np.float32(lam_out.value))
+
+
+def ref_all_thresh(lib, lut, vxyz, vrgba, labels, lists, cen, nrm, adj, color, geom, merging, lam, bins, truth_per_voxel, start, end, step):
+    """Clustering::all_thresh + best_thresh of the compiled reference; truth_per_voxel is indexed like vxyz"""
+    S = len(labels)
+    order = np.concatenate(lists)
+    off = np.concatenate([[0], np.cumsum([len(l) for l in lists])]).astype(np.int64)
+    vx = np.ascontiguousarray(np.asarray(vxyz, np.float32)[order]); vc = np.ascontiguousarray(np.asarray(vrgba, np.uint32)[order])
+    tl = np.ascontiguousarray(np.asarray(truth_per_voxel, np.uint32)[order])
+    labels = np.ascontiguousarray(labels, np.uint32); cen = np.ascontiguousarray(cen, np.float32); nrm = np.ascontiguousarray(nrm, np.float32)
+    adj = np.ascontiguousarray(adj, np.uint32)
+    cap = 512
+    out_t = np.zeros(cap, np.float32); out_p = np.zeros((cap, 7), np.float32); n = C.c_int32(); best = np.zeros(8, np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.ref_all_thresh.restype = C.c_int
+    rc = lib.ref_all_thresh(p(lut), C.c_int32(S), p(labels), p(off), p(vx), p(vc), p(cen), p(nrm), C.c_int64(len(adj)), p(adj), C.c_int(color), C.c_int(geom),
+                            C.c_int(merging), C.c_float(lam), C.c_int(bins), p(tl), C.c_float(start), C.c_float(end), C.c_float(step), C.c_int32(cap),
+                            p(out_t), p(out_p), C.byref(n), p(best))
+    if rc:
+        raise RuntimeError("the reference threw")
+    return out_t[:n.value].copy(), out_p[:n.value].copy(), best
 
 
 def hub_graph(n_leaves, seed):
@@ -104,6 +127,29 @@ CASES = [   # name, graph, flags (color, geom, merging, lambda, bins), threshold
 ]
 
 
+SWEEPS = [  # name, graph, flags, (start, end, step), truth: "colour" = the hub graph's six colour classes, "coarse" = the reference's own segments at 0.35 folded to 7 classes
+    ("sweep_hub150_rgb_cvx_ml", ("hub", 150), (1, 1, 0, 0.5, 500), (0.05, 0.6, 0.05), "colour"),
+    ("sweep_hub400_lab_cvx_al", ("hub", 400), (0, 1, 1, 0.5, 500), (0.8, 1.0, 0.005), "colour"),       # main()'s own range: 41 thresholds
+    ("sweep_frame_cvx_al", ("frame",), (0, 1, 1, 0.5, 500), (0.1, 0.5, 0.1), "coarse"),
+]
+
+
+def truth_for(kind, graph, lib, lut, flags):
+    vxyz, vrgba, labels, lists, cen, nrm, adj = graph
+    t = np.zeros(len(vxyz), np.uint32)
+    if kind == "colour":
+        for l in lists:
+            t[l] = (int(vrgba[l[0]]) & 255) // 40 + 1
+        return t
+    r = ref_cluster(lib, lut, *graph, *flags, 0.35)                # labelled cloud: regions ascending, voxels in list order
+    # map the labelled cloud back to voxels by exact xyz (voxel centroids are distinct)
+    key = {tuple(np.asarray(vxyz[v], np.float32).view(np.uint32).tolist()): v for v in range(len(vxyz))}
+    for xyz, lab in zip(r["out_xyz"], r["out_label"]):
+        t[key[tuple(np.asarray(xyz, np.float32).view(np.uint32).tolist())]] = int(lab) % 7 + 1
+    t[t == 0] = 777                                                 # voxels of no region (none here)
+    return t
+
+
 def main():
     import oracle_py
     lib = ref_lib()
@@ -124,6 +170,17 @@ def main():
         for k, v in r.items():
             out[name + "/" + k] = v
         print("%-20s S %5d  adjacency %6d  -> %5d merges, %4d regions left, lambda %.6f" % (name, len(labels), len(adj), len(r["merges_w"]), len(r["region_label"]), r["lam"]))
+    out["sweep_names"] = np.array([c[0] for c in SWEEPS])
+    for name, gsel, flags, (t0, t1, dt), kind in SWEEPS:
+        if gsel not in graphs:
+            graphs[gsel] = hub_graph(gsel[1], gsel[1]) if gsel[0] == "hub" else frame_graph(vga=gsel[0] == "vga")
+        graph = graphs[gsel]
+        truth = truth_for(kind, graph, lib, lut, flags)
+        thr, perf, best = ref_all_thresh(lib, lut, *graph, *flags, truth, t0, t1, dt)
+        out[name + "/graph"] = np.array("_".join(map(str, gsel))); out[name + "/flags"] = np.array(flags, np.float64)
+        out[name + "/range"] = np.array([t0, t1, dt], np.float32); out[name + "/truth"] = truth
+        out[name + "/thresholds"] = thr; out[name + "/perf"] = perf; out[name + "/best"] = best
+        print("%-26s %3d thresholds, best %.3f (F-score %.4f)" % (name, len(thr), best[0], best[4]))
     np.savez_compressed(OUT, **out)
     print("wrote %s (%d bytes)" % (OUT, os.path.getsize(OUT)))
 
