@@ -108,3 +108,12 @@ extern "C" int ref_cluster(const int16_t* lab_lut, int32_t n_sv, const uint32_t*
         return 0;
     } catch (const std::exception&) { f3ps_ref::sink = nullptr; return 1; }
 }
+
+// ColorUtilities::lab_ciede00 / rgb_eucl (/root/reference/src/color_utilities.cpp:190-319) on n pairs; the reference returns plain floats
+extern "C" void ref_color_distances(int64_t n, const float* c1, const float* c2, float* ciede00, float* eucl) {
+    for (int64_t i = 0; i < n; ++i) {
+        float a[3] = {c1[3 * i], c1[3 * i + 1], c1[3 * i + 2]}, b[3] = {c2[3 * i], c2[3 * i + 1], c2[3 * i + 2]};
+        if (ciede00) ciede00[i] = ColorUtilities::lab_ciede00(a, b);
+        if (eucl) eucl[i] = ColorUtilities::rgb_eucl(a, b);
+    }
+}

@@ -119,3 +119,33 @@ def test_oracle_reproduces_reference_all_thresh(oracle_mod, name):
             assert abs(got[n] - perf[k, j]) <= tol * max(1.0, abs(perf[k, j])), (name, float(t), n, got[n], perf[k, j])
     bt, bp = ot.best_thresh(res)
     assert np.float32(bt) == best[0] and abs(bp["fscore"] - best[4]) <= 2e-7
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/color_utilities.cpp"), reason="the reference tree exists in the build container only")
+def test_oracle_colour_distances_equal_reference_live(oracle_mod):
+    """ColorUtilities::lab_ciede00 / rgb_eucl of the compiled reference on 200,000 random pairs (hue wrap-arounds, greys, identical
+    colours, the corners of the gamut) against the oracle's restatement: bit for bit (same libm, same float / double mix)."""
+    import ctypes as C
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_clustering.so"))
+    rng = np.random.default_rng(2000)
+    n = 200000
+    lab1 = np.stack([rng.random(n) * 100, rng.random(n) * 256 - 128, rng.random(n) * 256 - 128], 1).astype(np.float32)
+    lab2 = np.stack([rng.random(n) * 100, rng.random(n) * 256 - 128, rng.random(n) * 256 - 128], 1).astype(np.float32)
+    lab2[:1000] = lab1[:1000]                                   # identical
+    lab1[1000:3000, 1:] = 0; lab2[2000:4000, 1:] = 0            # greys (C = 0: the hue branches)
+    lab2[4000:6000, 1:] = -lab1[4000:6000, 1:]                  # opposite hues (the 180-degree branches)
+    lab1[6000:6100] = [[0, -128, -128]]; lab2[6000:6100] = [[100, 127.99, 127.99]]
+    rgb1 = (rng.random((n, 3)) * 255).astype(np.float32); rgb2 = (rng.random((n, 3)) * 255).astype(np.float32)
+    ref_de = np.zeros(n, np.float32); ref_eu = np.zeros(n, np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.ref_color_distances(C.c_int64(n), p(lab1), p(lab2), p(ref_de), None)
+    lib.ref_color_distances(C.c_int64(n), p(rgb1), p(rgb2), None, p(ref_eu))
+    o = oracle_mod.Oracle()
+    step = 40                                                    # the oracle's entry points take one pair per call
+    got_de = np.array([o.lab_ciede00(a, b) for a, b in zip(lab1[::step], lab2[::step])], np.float32)
+    got_eu = np.array([o.rgb_eucl(a, b) for a, b in zip(rgb1[::step], rgb2[::step])], np.float32)
+    assert np.array_equal(bits(got_de), bits(ref_de[::step])) and np.array_equal(bits(got_eu), bits(ref_eu[::step]))
+    head = np.array([o.lab_ciede00(a, b) for a, b in zip(lab1[:6100:7], lab2[:6100:7])], np.float32)      # the constructed cases, densely
+    assert np.array_equal(bits(head), bits(ref_de[:6100:7]))
