@@ -91,7 +91,7 @@ def test_eval_label_pairs_equals_reference_testing_class_golden(gpu):
             assert abs(got[n] - w) < 1e-5, (k, n, got[n], w)
 
 
-@pytest.mark.parametrize("name", ["sweep_hub150_rgb_cvx_ml", "sweep_hub400_lab_cvx_al", "sweep_frame_cvx_al"])
+@pytest.mark.parametrize("name", ["sweep_hub150_rgb_cvx_ml", "sweep_hub400_lab_cvx_al", "sweep_frame_cvx_al", "sweep_c1_defaults"])
 def test_all_thresh_equals_reference_clustering_golden(gpu, name):
     """f3ps_eval_thresholds (one merge replay on the device) against Clustering::all_thresh / best_thresh of the REFERENCE's own classes
     (compiled from /root/reference/src against oracle/ref_shim, tools/gen_clustering_golden.py -> tests/golden/clustering_ref.npz):

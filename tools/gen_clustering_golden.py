@@ -102,13 +102,19 @@ def hub_graph(n_leaves, seed):
     return vxyz, vrgba, labels, lists, cen, nrm, np.array(sorted(adj), np.uint32)
 
 
-def frame_graph(vga=False):
+def frame_graph(vga=False, bundled=False):
     """the supervoxels PCL's VCCS would hand to set_initialstate, from the oracle's front half on the 160x120 synthetic frame
-    (vga: on the 640x480 frame bench.py's headline and the exact-merge-sequence test use, seed 20020)"""
+    (vga: on the 640x480 frame bench.py's headline and the exact-merge-sequence test use, seed 20020; bundled: on the reference's
+    own cloud, pcd/milk_cartoon_all_small_clorox.pcd = tests/fixtures/, loaded as main() does with z < 0 folded -- BASELINE configs[0])"""
     import oracle_py
-    from f3ps import synth
-    o = oracle_py.Oracle(); o.set_vccs_params(); o.set_merge_params(merge_impl=1, color_mode=0, geom_mode=1, merge_mode=1)
-    o.set_input(synth.make_frame(seed=20020) if vga else synth.make_frame(seed=11, width=160, height=120)); o.run(0, 0.2)
+    from f3ps import pcd, synth
+    o = oracle_py.Oracle(); o.set_vccs_params(fold_negative_z=True) if bundled else o.set_vccs_params()
+    o.set_merge_params(merge_impl=1, color_mode=0, geom_mode=1, merge_mode=1)
+    if bundled:
+        pts = pcd.read_pcd(os.path.join(ROOT, "tests", "fixtures", "milk_cartoon_all_small_clorox.pcd"))[0]
+    else:
+        pts = synth.make_frame(seed=20020) if vga else synth.make_frame(seed=11, width=160, height=120)
+    o.set_input(pts); o.run(0, 0.2)
     labels = o.array("sv_label").copy(); vl = o.array("labels")
     lists = [np.nonzero(vl == l)[0] for l in labels]
     return (o.array("voxel_xyz").copy(), o.array("voxel_rgba").copy(), labels, lists, o.array("sv_xyz").copy(), o.array("sv_normal")[:, :3].copy(), o.array("adj").copy())
@@ -124,6 +130,8 @@ CASES = [   # name, graph, flags (color, geom, merging, lambda, bins), threshold
     ("frame_eq200", ("frame",), (0, 0, 2, 0.5, 200), 0.5),           # configs[2]: --EQ 200 (threshold raised: under equalisation few edges are below 0.2)
     ("frame_rgb_ml", ("frame",), (1, 0, 0, 0.5, 500), 0.2),          # configs[3]: --RGB --ML 0.5
     ("vga_cvx_al", ("vga",), (0, 1, 1, 0.5, 500), 0.2),              # configs[1] at its own size: the 640x480 frame of the headline, 2,267 merges
+    ("c1_launch_file", ("bundled",), (0, 1, 1, 0.5, 500), 0.2),      # configs[0]: the reference's bundled cloud, launch file flags --CVX --AL -t 0.2
+    ("c1_defaults", ("bundled",), (0, 0, 1, 0.5, 500), 0.2),         # ... and the CLI defaults
 ]
 
 
@@ -131,12 +139,15 @@ SWEEPS = [  # name, graph, flags, (start, end, step), truth: "colour" = the hub 
     ("sweep_hub150_rgb_cvx_ml", ("hub", 150), (1, 1, 0, 0.5, 500), (0.05, 0.6, 0.05), "colour"),
     ("sweep_hub400_lab_cvx_al", ("hub", 400), (0, 1, 1, 0.5, 500), (0.8, 1.0, 0.005), "colour"),       # main()'s own range: 41 thresholds
     ("sweep_frame_cvx_al", ("frame",), (0, 1, 1, 0.5, 500), (0.1, 0.5, 0.1), "coarse"),
+    ("sweep_c1_defaults", ("bundled",), (0, 0, 1, 0.5, 500), (0.8, 1.0, 0.005), "single"),       # configs[0] without -t: main()'s automatic threshold; the file has no label field
 ]
 
 
 def truth_for(kind, graph, lib, lut, flags):
     vxyz, vrgba, labels, lists, cen, nrm, adj = graph
     t = np.zeros(len(vxyz), np.uint32)
+    if kind == "single":
+        return t                                                    # one ground-truth segment (all labels 0)
     if kind == "colour":
         for l in lists:
             t[l] = (int(vrgba[l[0]]) & 255) // 40 + 1
@@ -158,7 +169,7 @@ def main():
     graphs = {}
     for name, gsel, flags, thr in CASES:
         if gsel not in graphs:
-            graphs[gsel] = hub_graph(gsel[1], gsel[1]) if gsel[0] == "hub" else frame_graph(vga=gsel[0] == "vga")
+            graphs[gsel] = hub_graph(gsel[1], gsel[1]) if gsel[0] == "hub" else frame_graph(vga=gsel[0] == "vga", bundled=gsel[0] == "bundled")
         vxyz, vrgba, labels, lists, cen, nrm, adj = graphs[gsel]
         gname = "_".join(map(str, gsel))
         if gname + "/vxyz" not in out:
@@ -173,7 +184,7 @@ def main():
     out["sweep_names"] = np.array([c[0] for c in SWEEPS])
     for name, gsel, flags, (t0, t1, dt), kind in SWEEPS:
         if gsel not in graphs:
-            graphs[gsel] = hub_graph(gsel[1], gsel[1]) if gsel[0] == "hub" else frame_graph(vga=gsel[0] == "vga")
+            graphs[gsel] = hub_graph(gsel[1], gsel[1]) if gsel[0] == "hub" else frame_graph(vga=gsel[0] == "vga", bundled=gsel[0] == "bundled")
         graph = graphs[gsel]
         truth = truth_for(kind, graph, lib, lut, flags)
         thr, perf, best = ref_all_thresh(lib, lut, *graph, *flags, truth, t0, t1, dt)
