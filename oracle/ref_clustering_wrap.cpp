@@ -117,3 +117,28 @@ extern "C" void ref_color_distances(int64_t n, const float* c1, const float* c2,
         if (eucl) eucl[i] = ColorUtilities::rgb_eucl(a, b);
     }
 }
+
+// The reference's exception behaviour, case by case (the facade and the C ABI's status codes mirror it): returns 0 = no exception,
+// 1 = std::logic_error, 2 = std::invalid_argument, 3 = std::out_of_range, 4 = anything else.
+extern "C" int ref_exception_case(int which) {
+    try {
+        PointLCloudT::Ptr one = boost::make_shared<PointLCloudT>(), none = boost::make_shared<PointLCloudT>();
+        PointLT p; p.x = p.y = p.z = 0; p.label = 0; one->push_back(p);
+        switch (which) {
+            case 0: { Clustering c(LAB_CIEDE00, NORMALS_DIFF, MANUAL_LAMBDA); c.set_lambda(1.5f); break; }          // clustering.cpp:578-579
+            case 1: { Clustering c(LAB_CIEDE00, NORMALS_DIFF, ADAPTIVE_LAMBDA); c.set_lambda(0.5f); break; }        // :575-577
+            case 2: { Clustering c(LAB_CIEDE00, NORMALS_DIFF, EQUALIZATION); c.set_bins_num(-3); break; }           // :593-594
+            case 3: { Clustering c(LAB_CIEDE00, NORMALS_DIFF, ADAPTIVE_LAMBDA); c.set_bins_num(10); break; }        // :590-592
+            case 4: { Clustering c; c.cluster(0.2f); break; }                                                       // :671-673
+            case 5: { Clustering c; c.all_thresh(one, 1.5f, 1.0f, 0.005f); break; }                                 // :694-698
+            case 6: { Testing t(none, one); break; }                                                                // testing.cpp:420-423
+            case 7: { Testing t(one, none); break; }                                                                // :430-433
+            case 8: { Clustering c(LAB_CIEDE00, NORMALS_DIFF, MANUAL_LAMBDA); c.set_lambda(1.0f); c.set_lambda(0.0f); break; }   // the closed range is accepted
+            default: return 4;
+        }
+        return 0;
+    } catch (const std::out_of_range&) { return 3; }
+    catch (const std::invalid_argument&) { return 2; }
+    catch (const std::logic_error&) { return 1; }
+    catch (...) { return 4; }
+}

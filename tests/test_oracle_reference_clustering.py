@@ -149,3 +149,26 @@ def test_oracle_colour_distances_equal_reference_live(oracle_mod):
     assert np.array_equal(bits(got_de), bits(ref_de[::step])) and np.array_equal(bits(got_eu), bits(ref_eu[::step]))
     head = np.array([o.lab_ciede00(a, b) for a, b in zip(lab1[:6100:7], lab2[:6100:7])], np.float32)      # the constructed cases, densely
     assert np.array_equal(bits(head), bits(ref_de[:6100:7]))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/clustering.cpp"), reason="the reference tree exists in the build container only")
+def test_reference_exception_behaviour_live():
+    """The exception types of the compiled reference, case by case: what host/facade.cpp throws and what the C ABI's status codes map to
+    (F3PS_ERR_LOGIC / F3PS_ERR_INVALID_ARGUMENT / std::out_of_range; tests/test_gpu_parity.py::test_error_behaviour_matches_reference,
+    tests/test_gpu_eval.py::test_eval_errors and host/facade_selftest check the product side)."""
+    import ctypes as C
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_clustering.so"))
+    NONE, LOGIC, INVALID, RANGE = 0, 1, 2, 3
+    want = {0: INVALID,     # set_lambda outside [0, 1]
+            1: LOGIC,       # set_lambda when the criterion is not MANUAL_LAMBDA
+            2: INVALID,     # set_bins_num < 0
+            3: LOGIC,       # set_bins_num when the criterion is not EQUALIZATION
+            4: LOGIC,       # cluster before set_initialstate
+            5: RANGE,       # all_thresh with a threshold outside [0, 1]
+            6: INVALID,     # Testing with an empty segmentation
+            7: INVALID,     # Testing with an empty ground truth
+            8: NONE}        # lambda = 0 and lambda = 1 are accepted
+    for case, code in want.items():
+        assert lib.ref_exception_case(case) == code, case
